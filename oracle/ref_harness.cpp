@@ -1,0 +1,403 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// C-ABI harness around the *reference's own* device-model objects.  The BSIM4
+// translation units are compiled where they lie under /root/reference (see
+// oracle/Makefile) and linked with oracle/shim/xyce_shim.cpp; this file drives them
+// exactly as Xyce's loader does:
+//   Config<Traits>::addConfiguration -> Traits::factory (Master) -> addModel/addInstance
+//   registerLIDs / registerStateLIDs / registerStoreLIDs / registerJacLIDs / setupPointers
+//     (Topology: N_TOP_CktGraphBasic.C:374-416, :588-637; N_TOP_Indexor.C:149-214)
+//   Master::updateState -> loadDAEVectors -> loadDAEMatrices
+//     (DeviceMgr: Core/N_DEV_DeviceMgr.C:3857-3936, :4156-4284, :3980-4115)
+// on CSR-backed Linear::Matrix objects with the N_LAS_EpetraMatrix.C:658-664 addressing
+// rule (row base + offset, ground -> scratch).  It also exports the instance / bin /
+// model constants that Xyce's host code (processParams / updateTemperature) computed,
+// which is what a real adaptor would upload to the GPU, and the reference's cached
+// intermediates for name-by-name comparison.
+#include <Xyce_config.h>
+#include <algorithm>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+// compiled with -fno-access-control (oracle/Makefile): the harness reads private members
+#include <N_DEV_MOSFET_B4.h>
+#include <N_DEV_Configuration.h>
+#include <N_DEV_DeviceBlock.h>
+#include <N_DEV_DeviceMaster.h>
+#include <N_DEV_DeviceOptions.h>
+#include <N_DEV_ExternData.h>
+#include <N_DEV_MatrixLoadData.h>
+#include <N_DEV_SolverState.h>
+#include <N_LAS_Matrix.h>
+#include <N_UTL_Math.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+#include "../xyce_b200/csrc/bsim4_fields.def"
+#include "b4_mid_members.def"
+
+using namespace Xyce;
+using namespace Xyce::Device;
+
+namespace {
+
+// CSR matrix with the reference's element addressing semantics.
+class CsrMatrix : public Linear::Matrix {
+ public:
+  std::vector<int> rowptr, colind;
+  std::vector<double> vals;
+  void setGround(int lid) { groundLID_ = lid; }
+  double *operator()(int row, int off) override {
+    if (row != groundLID_ && row >= 0 && off >= 0) return &vals[rowptr[row] + off];
+    return &groundNode_;
+  }
+  const double *operator()(int row, int off) const override {
+    if (row != groundLID_ && row >= 0 && off >= 0) return &vals[rowptr[row] + off];
+    return &groundNode_;
+  }
+  double *returnRawEntryPointer(int r, int c) override {
+    if (r == groundLID_ || r < 0 || c < 0) return &groundNode_;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) if (colind[k] == c) return &vals[k];
+    return &groundNode_;
+  }
+  void put(double s) override { std::fill(vals.begin(), vals.end(), s); }
+  // unused parts of the interface
+  int setUseTranspose(bool) override { return 0; }
+  bool useTranspose() const override { return false; }
+  bool putRow(int, int, const double *, const int *) override { return false; }
+  void add(const Linear::Matrix &) override {}
+  void matvec(bool, const Linear::MultiVector &, Linear::MultiVector &) const override {}
+  void linearCombo(const double, const Linear::Matrix &, const double, const Linear::Matrix &) override {}
+  void getDiagonal(Linear::Vector &) const override {}
+  bool replaceDiagonal(const Linear::Vector &) override { return false; }
+  int getRowLength(int r) const override { return rowptr[r + 1] - rowptr[r]; }
+  int getLocalRowLength(int r) const override { return rowptr[r + 1] - rowptr[r]; }
+  int getLocalRowView(int, int &, double *&, int *&) const override { return -1; }
+  void getRowCopy(int, int, int &, double *, int *) const override {}
+  void getLocalRowCopy(int, int, int &, double *, int *) const override {}
+  int getNumRows() const override { return (int)rowptr.size() - 1; }
+  int getLocalNumRows() const override { return (int)rowptr.size() - 1; }
+  bool addIntoLocalRow(int, int, const double *, const int *) override { return false; }
+  bool putLocalRow(int, int, const double *, const int *) override { return false; }
+  void writeToFile(const char *, bool, bool) const override {}
+  const Parallel::ParMap *getColMap(const Parallel::Communicator &) const override { return 0; }
+  const Linear::Graph *getGraph() const override { return 0; }
+  void scale(double) override {}
+  void print(std::ostream &) const override {}
+};
+
+struct InstRec {
+  DeviceInstance *inst;
+  std::vector<int> ext;      // external node ids (-1 = ground)
+  std::vector<int> lids;     // ext + int LIDs
+  int sta0, sto0;
+};
+
+struct Ctx {
+  DeviceOptions devOptions;
+  SolverState solState;
+  ExternData extData;
+  MatrixLoadData mlData;
+  FactoryBlock *fb = 0;
+  Config<MOSFET_B4::Traits> *cfgB4 = 0;
+  Xyce::Device::Device *masterB4 = 0;
+  std::vector<InstRec> insts;
+  int nExt = 0, n = 0, nSta = 0, nSto = 0;
+  CsrMatrix dFdx, dQdx;
+  std::vector<double> f, q, b, fl, ql, nextSta, currSta, nextSto, currSto, sol;
+  bool finalized = false;
+};
+
+alignas(64) char g_fake_mgr[4096];
+alignas(64) char g_fake_cmd[4096];
+
+std::vector<Param> make_params(int n, const char **keys, const double *vals) {
+  std::vector<Param> v;
+  for (int i = 0; i < n; ++i) {
+    Param p(std::string(keys[i]), vals[i], true);
+    v.push_back(p);
+  }
+  return v;
+}
+
+}  // namespace
+
+static void xref_segv(int) { void *bt[64]; int n = backtrace(bt, 64); backtrace_symbols_fd(bt, n, 2); _exit(139); }
+
+extern "C" {
+
+void *xref_new() {
+  if (getenv("XREF_DEBUG")) signal(SIGSEGV, xref_segv);
+  Ctx *c = new Ctx;
+  c->fb = new FactoryBlock(*reinterpret_cast<DeviceMgr *>(g_fake_mgr), c->devOptions, c->solState, c->mlData,
+                           c->extData, *reinterpret_cast<IO::CmdParse *>(g_fake_cmd));
+  return c;
+}
+
+int xref_set_num_external_nodes(void *h, int n) { ((Ctx *)h)->nExt = n; return 0; }
+
+// type: "nmos" / "pmos"; level 54 BSIM4.
+int xref_b4_add_model(void *h, const char *name, const char *type, int np, const char **keys, const double *vals) {
+  Ctx *c = (Ctx *)h;
+  if (!c->cfgB4) {
+    c->cfgB4 = &Config<MOSFET_B4::Traits>::addConfiguration();
+    c->masterB4 = MOSFET_B4::Traits::factory(*c->cfgB4, *c->fb);
+  }
+  ModelBlock mb(name, type, 54);
+  mb.params = make_params(np, keys, vals);
+  DeviceModel *m = c->masterB4->addModel(mb, *c->fb);
+  return m ? 0 : 1;
+}
+
+int xref_b4_add_instance(void *h, const char *name, const char *model, const int *nodes4, int np,
+                         const char **keys, const double *vals) {
+  Ctx *c = (Ctx *)h;
+  InstanceBlock ib{std::string(name)};
+  ib.setModelName(ModelName(model));
+  ib.params = make_params(np, keys, vals);
+  ib.iNumNodes = 4;
+  ib.numExtVars = 4;
+  ib.modelFlag = true;
+  DeviceInstance *di = c->masterB4->addInstance(ib, *c->fb);
+  if (!di) return 1;
+  InstRec r;
+  r.inst = di;
+  r.ext.assign(nodes4, nodes4 + 4);
+  c->insts.push_back(r);
+  return 0;
+}
+
+// Assign LIDs, build the CSR pattern from every instance's jacobianStamp(), register
+// everything with the instances.  Returns number of unknowns.
+int xref_finalize(void *h) {
+  Ctx *c = (Ctx *)h;
+  int next = c->nExt;
+  for (auto &r : c->insts) {
+    r.lids = r.ext;
+    for (int k = 0; k < r.inst->getNumIntVars(); ++k) r.lids.push_back(next++);
+  }
+  c->n = next;
+  const int ground = c->n;
+  std::vector<std::set<int>> rows(c->n);
+  for (auto &r : c->insts) {
+    const std::vector<std::vector<int>> &st = r.inst->jacobianStamp();
+    for (size_t i = 0; i < st.size(); ++i) {
+      int gr = r.lids[i];
+      if (gr < 0) continue;
+      for (int cj : st[i]) { int gc = r.lids[cj]; if (gc >= 0) rows[gr].insert(gc); }
+    }
+  }
+  for (CsrMatrix *M : {&c->dFdx, &c->dQdx}) {
+    M->rowptr.assign(1, 0);
+    M->colind.clear();
+    for (int i = 0; i < c->n; ++i) {
+      for (int cc : rows[i]) M->colind.push_back(cc);
+      M->rowptr.push_back((int)M->colind.size());
+    }
+    M->vals.assign(M->colind.size(), 0.0);
+    M->setGround(ground);
+  }
+  int sta = 0, sto = 0;
+  for (auto &r : c->insts) {
+    std::vector<int> ext, in;
+    const int ne = r.inst->getNumExtVars();
+    for (int k = 0; k < ne; ++k) ext.push_back(r.lids[k] < 0 ? ground : r.lids[k]);
+    for (size_t k = ne; k < r.lids.size(); ++k) in.push_back(r.lids[k]);
+    r.inst->registerLIDs(in, ext);
+    std::vector<int> sv, tv;
+    r.sta0 = sta; r.sto0 = sto;
+    for (int k = 0; k < r.inst->getNumStateVars(); ++k) sv.push_back(sta++);
+    for (int k = 0; k < r.inst->getNumStoreVars(); ++k) tv.push_back(sto++);
+    r.inst->registerStateLIDs(sv);
+    r.inst->registerStoreLIDs(tv);
+    const std::vector<std::vector<int>> &st = r.inst->jacobianStamp();
+    std::vector<std::vector<int>> jl(st.size());
+    for (size_t i = 0; i < st.size(); ++i) {
+      jl[i].assign(st[i].size(), -1);
+      int gr = r.lids[i];
+      if (gr < 0) continue;
+      for (size_t j = 0; j < st[i].size(); ++j) {
+        int gc = r.lids[st[i][j]];
+        if (gc < 0) continue;
+        const int *b = &c->dFdx.colind[c->dFdx.rowptr[gr]], *e = &c->dFdx.colind[c->dFdx.rowptr[gr + 1]];
+        jl[i][j] = (int)(std::lower_bound(b, e, gc) - b);
+      }
+    }
+    r.inst->registerJacLIDs(jl);
+  }
+  c->nSta = sta; c->nSto = sto;
+  c->f.assign(c->n + 1, 0); c->q = c->b = c->fl = c->ql = c->f;
+  c->sol.assign(c->n + 1, 0);
+  c->nextSta.assign(sta + 1, 0); c->currSta = c->nextSta;
+  c->nextSto.assign(sto + 1, 0); c->currSto = c->nextSto;
+  ExternData &e = c->extData;
+  e.dFdxMatrixPtr = &c->dFdx; e.dQdxMatrixPtr = &c->dQdx;
+  e.daeFVectorRawPtr = c->f.data(); e.daeQVectorRawPtr = c->q.data(); e.daeBVectorRawPtr = c->b.data();
+  e.dFdxdVpVectorRawPtr = c->fl.data(); e.dQdxdVpVectorRawPtr = c->ql.data();
+  e.nextSolVectorRawPtr = e.currSolVectorRawPtr = e.lastSolVectorRawPtr = c->sol.data();
+  e.nextStaVectorRawPtr = c->nextSta.data(); e.currStaVectorRawPtr = e.lastStaVectorRawPtr = c->currSta.data();
+  e.nextStoVectorRawPtr = c->nextSto.data(); e.currStoVectorRawPtr = e.lastStoVectorRawPtr = c->currSto.data();
+  for (auto &r : c->insts) r.inst->setupPointers();
+  c->finalized = true;
+  return c->n;
+}
+
+int xref_nnz(void *h) { return (int)((Ctx *)h)->dFdx.colind.size(); }
+void xref_pattern(void *h, int *rowptr, int *colind) {
+  Ctx *c = (Ctx *)h;
+  std::copy(c->dFdx.rowptr.begin(), c->dFdx.rowptr.end(), rowptr);
+  std::copy(c->dFdx.colind.begin(), c->dFdx.colind.end(), colind);
+}
+int xref_num_state(void *h) { return ((Ctx *)h)->nSta; }
+int xref_num_store(void *h) { return ((Ctx *)h)->nSto; }
+
+// flags[]: dcop, tranop, acop, transient, dcsweep, initJct, initFix, initTran, newtonIter,
+//          locaEnabled, artParameter, voltageLimiter
+// dvals[]: gmin, gainScale, nltermScale
+void xref_set_flags(void *h, const int *fl, const double *dv) {
+  Ctx *c = (Ctx *)h;
+  SolverState &s = c->solState;
+  s.dcopFlag = fl[0]; s.tranopFlag = fl[1]; s.acopFlag = fl[2]; s.transientFlag = fl[3];
+  s.dcsweepFlag = fl[4]; s.initJctFlag_ = fl[5]; s.initFixFlag = fl[6]; s.initTranFlag_ = fl[7];
+  s.newtonIter = fl[8]; s.locaEnabledFlag = fl[9]; s.artParameterFlag_ = fl[10];
+  c->devOptions.voltageLimiterFlag = fl[11];
+  c->devOptions.gmin = dv[0]; s.gainScale_ = dv[1]; s.nltermScale_ = dv[2];
+}
+
+void xref_set_state(void *h, const double *currSto, const double *nextSto, const double *currSta) {
+  Ctx *c = (Ctx *)h;
+  if (currSto) std::copy(currSto, currSto + c->nSto, c->currSto.begin());
+  if (nextSto) std::copy(nextSto, nextSto + c->nSto, c->nextSto.begin());
+  if (currSta) std::copy(currSta, currSta + c->nSta, c->currSta.begin());
+}
+void xref_get_state(void *h, double *currSto, double *nextSto, double *currSta, double *nextSta) {
+  Ctx *c = (Ctx *)h;
+  if (currSto) std::copy(c->currSto.begin(), c->currSto.begin() + c->nSto, currSto);
+  if (nextSto) std::copy(c->nextSto.begin(), c->nextSto.begin() + c->nSto, nextSto);
+  if (currSta) std::copy(c->currSta.begin(), c->currSta.begin() + c->nSta, currSta);
+  if (nextSta) std::copy(c->nextSta.begin(), c->nextSta.begin() + c->nSta, nextSta);
+}
+// carried limiter threshold `von` of every BSIM4 instance
+void xref_b4_set_von(void *h, const double *von) {
+  Ctx *c = (Ctx *)h;
+  for (size_t i = 0; i < c->insts.size(); ++i) static_cast<MOSFET_B4::Instance *>(c->insts[i].inst)->von = von[i];
+}
+void xref_b4_get_von(void *h, double *von) {
+  Ctx *c = (Ctx *)h;
+  for (size_t i = 0; i < c->insts.size(); ++i) von[i] = static_cast<MOSFET_B4::Instance *>(c->insts[i].inst)->von;
+}
+
+// One updateState + loadDAEVectors + loadDAEMatrices pass at solution x[0..n).
+// Outputs (each length n, matrices nnz): f, q, dFdxdVp, dQdxdVp, dFdx values, dQdx values.
+int xref_load(void *h, const double *x, double *f, double *q, double *fl, double *ql, double *dfdx, double *dqdx) {
+  Ctx *c = (Ctx *)h;
+  std::copy(x, x + c->n, c->sol.begin());
+  c->sol[c->n] = 0.0;
+  for (auto *v : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(v->begin(), v->end(), 0.0);
+  c->dFdx.put(0.0); c->dQdx.put(0.0);
+  bool ok = c->masterB4->updateState(c->sol.data(), c->nextSta.data(), c->nextSto.data());
+  ok = c->masterB4->loadDAEVectors(c->sol.data(), c->f.data(), c->q.data(), c->b.data(), 0, 0, 0) && ok;
+  ok = c->masterB4->loadDAEMatrices(c->dFdx, c->dQdx) && ok;
+  if (f) std::copy(c->f.begin(), c->f.begin() + c->n, f);
+  if (q) std::copy(c->q.begin(), c->q.begin() + c->n, q);
+  if (fl) std::copy(c->fl.begin(), c->fl.begin() + c->n, fl);
+  if (ql) std::copy(c->ql.begin(), c->ql.begin() + c->n, ql);
+  if (dfdx) std::copy(c->dFdx.vals.begin(), c->dFdx.vals.end(), dfdx);
+  if (dqdx) std::copy(c->dQdx.vals.begin(), c->dQdx.vals.end(), dqdx);
+  return ok ? 0 : 1;
+}
+
+// Timing helper for the CPU baseline: `reps` evaluation passes, no output copies.
+int xref_load_repeat(void *h, int reps) {
+  Ctx *c = (Ctx *)h;
+  for (int r = 0; r < reps; ++r) {
+    for (auto *v : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(v->begin(), v->end(), 0.0);
+    c->dFdx.put(0.0); c->dQdx.put(0.0);
+    c->masterB4->updateState(c->sol.data(), c->nextSta.data(), c->nextSto.data());
+    c->masterB4->loadDAEVectors(c->sol.data(), c->f.data(), c->q.data(), c->b.data(), 0, 0, 0);
+    c->masterB4->loadDAEMatrices(c->dFdx, c->dQdx);
+  }
+  return 0;
+}
+void xref_set_solution(void *h, const double *x) {
+  Ctx *c = (Ctx *)h;
+  std::copy(x, x + c->n, c->sol.begin());
+}
+
+// ---- parameter-record export (what a host adaptor uploads) ----
+int xref_b4_counts(int *out) {
+#define CNT(n) +1
+  out[0] = 0 XB_B4_MODEL_D(CNT); out[1] = 0 XB_B4_MODEL_I(CNT); out[2] = 0 XB_B4_SIZE_D(CNT);
+  out[3] = 0 XB_B4_INST_D(CNT); out[4] = 0 XB_B4_INST_I(CNT);
+  out[5] = 0 XB_B4_MID_REF_D(CNT); out[6] = 1 XB_B4_MID_REF_I(CNT);
+#undef CNT
+  return 0;
+}
+// names, newline separated, in export order: which = 0 model_d,1 model_i,2 size_d,3 inst_d,4 inst_i,5 mid_d,6 mid_i
+const char *xref_b4_names(int which) {
+#define NM(n) #n "\n"
+  switch (which) {
+    case 0: return XB_B4_MODEL_D(NM);
+    case 1: return XB_B4_MODEL_I(NM);
+    case 2: return XB_B4_SIZE_D(NM);
+    case 3: return XB_B4_INST_D(NM);
+    case 4: return XB_B4_INST_I(NM);
+    case 5: return XB_B4_MID_REF_D(NM);
+    case 6: return "origFlag\n" XB_B4_MID_REF_I(NM);
+  }
+#undef NM
+  return "";
+}
+// model/bin identity (pointers as integers) lets the caller de-duplicate records
+void xref_b4_export(void *h, int idx, double *model_d, int *model_i, double *size_d, double *inst_d, int *inst_i,
+                    long long *model_id, long long *size_id, int *lids12, int *sta0, int *sto0) {
+  Ctx *c = (Ctx *)h;
+  MOSFET_B4::Instance &in = *static_cast<MOSFET_B4::Instance *>(c->insts[idx].inst);
+  MOSFET_B4::Model &mo = in.model_;
+  const MOSFET_B4::SizeDependParam &sp = *in.paramPtr;
+  int k;
+#define PUT(n) model_d[k++] = mo.n;
+  k = 0; XB_B4_MODEL_D(PUT)
+#undef PUT
+#define PUT(n) model_i[k++] = (int)mo.n;
+  k = 0; XB_B4_MODEL_I(PUT)
+#undef PUT
+#define PUT(n) size_d[k++] = sp.n;
+  k = 0; XB_B4_SIZE_D(PUT)
+#undef PUT
+#define PUT(n) inst_d[k++] = in.n;
+  k = 0; XB_B4_INST_D(PUT)
+#undef PUT
+#define PUT(n) inst_i[k++] = (int)in.n;
+  k = 0; XB_B4_INST_I(PUT)
+#undef PUT
+  *model_id = (long long)(size_t)&mo;
+  *size_id = (long long)(size_t)&sp;
+  const int g = c->n;
+  int l[12] = {in.li_Drain, in.li_GateExt, in.li_Source, in.li_Body, in.li_DrainPrime, in.li_SourcePrime,
+               in.li_GatePrime, in.li_GateMid, in.li_BodyPrime, in.li_SourceBody, in.li_DrainBody,
+               in.trnqsMod ? in.li_Charge : g};
+  for (int i = 0; i < 12; ++i) lids12[i] = (l[i] == g) ? -1 : l[i];
+  *sta0 = c->insts[idx].sta0;
+  *sto0 = c->insts[idx].sto0;
+}
+void xref_b4_mid(void *h, int idx, double *mid_d, int *mid_i) {
+  Ctx *c = (Ctx *)h;
+  MOSFET_B4::Instance &in = *static_cast<MOSFET_B4::Instance *>(c->insts[idx].inst);
+  int k = 0;
+#define PUT(n) mid_d[k++] = in.n;
+  XB_B4_MID_REF_D(PUT)
+#undef PUT
+  k = 0;
+  mid_i[k++] = in.origFlag;
+#define PUT(n) mid_i[k++] = (int)in.n;
+  XB_B4_MID_REF_I(PUT)
+#undef PUT
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+"""ctypes wrapper around oracle/_ref/libxyce_ref.so (the reference's own BSIM4 objects).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU
+baseline legs.  Nothing under xyce_b200/ may import this module.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "..", "oracle", "_ref", "libxyce_ref.so")
+
+FLAG_NAMES = ["dcop", "tranop", "acop", "transient", "dcsweep", "initJct", "initFix", "initTran",
+              "newtonIter", "locaEnabled", "artParameter", "voltageLimiter"]
+
+
+def available():
+    return os.path.exists(REF_SO)
+
+
+def _lib():
+    lib = C.CDLL(REF_SO)
+    lib.xref_new.restype = C.c_void_p
+    lib.xref_b4_names.restype = C.c_char_p
+    return lib
+
+
+def _keys(d):
+    ks = list(d.keys())
+    arr = (C.c_char_p * len(ks))(*[k.encode() for k in ks])
+    vals = np.array([float(d[k]) for k in ks], dtype=np.float64)
+    return len(ks), arr, vals
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+class RefCircuit:
+    """A netlist of BSIM4 instances evaluated by the reference's own C++ objects."""
+
+    def __init__(self, n_ext_nodes):
+        self.lib = _lib()
+        self.h = C.c_void_p(self.lib.xref_new())
+        self.lib.xref_set_num_external_nodes(self.h, int(n_ext_nodes))
+        self.n_inst = 0
+        self.n = None
+
+    def add_model(self, name, mtype, params):
+        n, ks, vs = _keys(params)
+        rc = self.lib.xref_b4_add_model(self.h, name.encode(), mtype.encode(), n, ks, dptr(vs))
+        assert rc == 0
+
+    def add_instance(self, name, model, nodes, params):
+        n, ks, vs = _keys(params)
+        nd = np.array(nodes, dtype=np.int32)
+        rc = self.lib.xref_b4_add_instance(self.h, name.encode(), model.encode(), iptr(nd), n, ks, dptr(vs))
+        assert rc == 0
+        self.n_inst += 1
+
+    def finalize(self):
+        self.n = self.lib.xref_finalize(self.h)
+        self.nnz = self.lib.xref_nnz(self.h)
+        self.rowptr = np.zeros(self.n + 1, dtype=np.int32)
+        self.colind = np.zeros(self.nnz, dtype=np.int32)
+        self.lib.xref_pattern(self.h, iptr(self.rowptr), iptr(self.colind))
+        self.n_sta = self.lib.xref_num_state(self.h)
+        self.n_sto = self.lib.xref_num_store(self.h)
+        return self.n
+
+    def set_flags(self, gmin=1e-12, gainScale=1.0, nltermScale=1.0, **fl):
+        f = np.zeros(len(FLAG_NAMES), dtype=np.int32)
+        f[FLAG_NAMES.index("voltageLimiter")] = 1
+        for k, v in fl.items():
+            f[FLAG_NAMES.index(k)] = int(v)
+        d = np.array([gmin, gainScale, nltermScale], dtype=np.float64)
+        self.lib.xref_set_flags(self.h, iptr(f), dptr(d))
+        self.flags = dict(zip(FLAG_NAMES, f.tolist()), gmin=gmin, gainScale=gainScale, nltermScale=nltermScale)
+
+    def set_state(self, curr_sto=None, next_sto=None, curr_sta=None):
+        cv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        a, b, c = cv(curr_sto), cv(next_sto), cv(curr_sta)
+        self.lib.xref_set_state(self.h, dptr(a), dptr(b), dptr(c))
+
+    def get_state(self):
+        cs, ns = np.zeros(self.n_sto), np.zeros(self.n_sto)
+        ca, na = np.zeros(self.n_sta), np.zeros(self.n_sta)
+        self.lib.xref_get_state(self.h, dptr(cs), dptr(ns), dptr(ca), dptr(na))
+        return dict(curr_sto=cs, next_sto=ns, curr_sta=ca, next_sta=na)
+
+    def set_von(self, von):
+        v = np.ascontiguousarray(von, dtype=np.float64)
+        self.lib.xref_b4_set_von(self.h, dptr(v))
+
+    def get_von(self):
+        v = np.zeros(self.n_inst)
+        self.lib.xref_b4_get_von(self.h, dptr(v))
+        return v
+
+    def load(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = {k: np.zeros(self.n) for k in ("f", "q", "dFdxdVp", "dQdxdVp")}
+        out["dFdx"] = np.zeros(self.nnz)
+        out["dQdx"] = np.zeros(self.nnz)
+        rc = self.lib.xref_load(self.h, dptr(x), dptr(out["f"]), dptr(out["q"]), dptr(out["dFdxdVp"]),
+                                dptr(out["dQdxdVp"]), dptr(out["dFdx"]), dptr(out["dQdx"]))
+        assert rc == 0
+        return out
+
+    def load_repeat(self, x, reps):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.lib.xref_set_solution(self.h, dptr(x))
+        self.lib.xref_load_repeat(self.h, int(reps))
+
+    def names(self, which):
+        return self.lib.xref_b4_names(which).decode().split()
+
+    def export(self, idx):
+        cnt = np.zeros(7, dtype=np.int32)
+        self.lib.xref_b4_counts(iptr(cnt))
+        md, mi = np.zeros(cnt[0]), np.zeros(cnt[1], dtype=np.int32)
+        sd = np.zeros(cnt[2])
+        idd, ii = np.zeros(cnt[3]), np.zeros(cnt[4], dtype=np.int32)
+        mid, sid = C.c_longlong(), C.c_longlong()
+        lids = np.zeros(12, dtype=np.int32)
+        sta0, sto0 = C.c_int(), C.c_int()
+        self.lib.xref_b4_export(self.h, idx, dptr(md), iptr(mi), dptr(sd), dptr(idd), iptr(ii),
+                                C.byref(mid), C.byref(sid), iptr(lids), C.byref(sta0), C.byref(sto0))
+        return dict(model_d=md, model_i=mi, size_d=sd, inst_d=idd, inst_i=ii, model_id=mid.value,
+                    size_id=sid.value, lids=lids, sta0=sta0.value, sto0=sto0.value)
+
+    def mid(self, idx):
+        cnt = np.zeros(7, dtype=np.int32)
+        self.lib.xref_b4_counts(iptr(cnt))
+        d, i = np.zeros(cnt[5]), np.zeros(cnt[6], dtype=np.int32)
+        self.lib.xref_b4_mid(self.h, idx, dptr(d), iptr(i))
+        return dict(zip(self.names(5), d.tolist())), dict(zip(self.names(6), i.tolist()))

@@ -1,0 +1,141 @@
+// xyce_b200 -- common definitions shared by every compact-model evaluator.
+//
+// Single-source: this header is compiled by nvcc for sm_100a (the product) and,
+// for CPU-side unit tests only, by g++ (tests/host_mirror).  It holds no state.
+//
+// Constants follow the reference's values so that results are comparable at
+// 1e-12: src/DeviceModelPKG/Core/N_DEV_Const.h:42-113 and the BSIM4-local
+// overrides in src/DeviceModelPKG/OpenModels/N_DEV_MOSFET_B4p82.C:58-105.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define XB_HD __host__ __device__ __forceinline__
+#define XB_D __device__ __forceinline__
+#else
+#define XB_HD inline
+#define XB_D inline
+#endif
+
+namespace xb {
+
+// ---- physical constants (N_DEV_Const.h) -----------------------------------
+constexpr double kQ        = 1.6021918e-19;
+constexpr double kCtoK     = 273.15;
+constexpr double kBoltz    = 1.3806226e-23;
+constexpr double kKoverQ   = kBoltz / kQ;
+constexpr double kVt0      = kBoltz * (27.0 + kCtoK) / kQ;   // CONSTvt0
+constexpr double kEpsOx    = 3.453133e-11;
+constexpr double kEpsSi    = 1.03594e-10;
+constexpr double kEps0B4   = 8.85418e-12;                    // B4p82.C:58
+constexpr double kChargeQ  = 1.60219e-19;                    // B4p82.C:60
+constexpr double kMaxExp   = 5.834617425e14;
+constexpr double kMinExp   = 1.713908431e-15;
+constexpr double kExpThr   = 34.0;
+constexpr double kMaxExpL  = 2.688117142e+43;
+constexpr double kMinExpL  = 3.720075976e-44;
+constexpr double kExpLThr  = 100.0;
+constexpr double kDelta1   = 0.02;
+constexpr double kDelta3   = 0.02;
+constexpr double kDelta4   = 0.02;
+constexpr double kMachEps  = 2.220446049250313e-16;          // MachineDependentParams::MachinePrecision()
+constexpr int    kMM       = 3;                              // B4 smoothing coefficient
+
+// ---- per-launch solver/device flag block ----------------------------------
+// Mirrors the subset of Device::SolverState (Core/N_DEV_SolverState.h:114-217)
+// and Device::DeviceOptions (Core/N_DEV_DeviceOptions.C:79-150) that is read
+// inside model evaluation.
+struct SolverFlags {
+  int dcopFlag;
+  int tranopFlag;
+  int acopFlag;
+  int transientFlag;
+  int dcsweepFlag;
+  int initJctFlag;
+  int initFixFlag;
+  int initTranFlag;
+  int newtonIter;
+  int locaEnabledFlag;
+  int artParameterFlag;
+  int voltageLimiterFlag;
+  double gmin;
+  double gainScale;
+  double nltermScale;
+  double vgstConst;
+  double vdsScaleMin;
+  double sizeScale;      // MOS1 homotopy (unused by BSIM4)
+  double currTimeStep;   // unused by BSIM4 eval
+};
+
+// ---- smoothed exponentials (B4p82.C:82-105) --------------------------------
+XB_HD void dexp(double a, double &b, double &c) {
+  if (a > kExpThr) { b = kMaxExp * (1.0 + a - kExpThr); c = kMaxExp; }
+  else if (a < -kExpThr) { b = kMinExp; c = 0.0; }
+  else { b = exp(a); c = b; }
+}
+XB_HD double dexp2(double a) {
+  if (a > kExpThr) return kMaxExp * (1.0 + a - kExpThr);
+  if (a < -kExpThr) return kMinExp;
+  return exp(a);
+}
+
+XB_HD double dmax(double a, double b) { return a < b ? b : a; }   // std::max semantics
+XB_HD double dmin(double a, double b) { return b < a ? b : a; }   // std::min semantics
+
+// ---- SPICE3 Newton limiters (Core/N_DEV_DeviceSupport.C:161-393) ------------
+XB_HD double limvds(double vnew, double vold) {
+  if (vold >= 3.5) {
+    if (vnew > vold) vnew = dmin(vnew, 3.0 * vold + 2.0);
+    else if (vnew < 3.5) vnew = dmax(vnew, 2.0);
+  } else {
+    if (vnew > vold) vnew = dmin(vnew, 4.0);
+    else vnew = dmax(vnew, -0.5);
+  }
+  return vnew;
+}
+
+XB_HD double pnjlim(double vnew, double vold, double vt, double vcrit, int &icheck) {
+  if ((vnew > vcrit) && (fabs(vnew - vold) > (vt + vt))) {
+    if (vold > 0) {
+      double arg = 1 + (vnew - vold) / vt;
+      vnew = (arg > 0) ? vold + vt * log(arg) : vcrit;
+    } else {
+      vnew = vt * log(vnew / vt);
+    }
+    icheck = 1;
+  } else {
+    icheck = 0;
+  }
+  return vnew;
+}
+
+XB_HD double fetlim(double vnew, double vold, double vto) {
+  const double vtsthi = fabs(2 * (vold - vto)) + 2;
+  const double vtstlo = vtsthi / 2 + 2;
+  const double vtox = vto + 3.5;
+  const double delv = vnew - vold;
+  if (vold >= vto) {
+    if (vold >= vtox) {
+      if (delv <= 0) {
+        if (vnew >= vtox) { if (-delv > vtstlo) vnew = vold - vtstlo; }
+        else vnew = dmax(vnew, vto + 2.0);
+      } else {
+        if (delv >= vtsthi) vnew = vold + vtsthi;
+      }
+    } else {
+      vnew = (delv <= 0) ? dmax(vnew, vto - 0.5) : dmin(vnew, vto + 4.0);
+    }
+  } else {
+    if (delv <= 0) {
+      if (-delv > vtsthi) vnew = vold - vtsthi;
+    } else {
+      const double vtemp = vto + 0.5;
+      if (vnew <= vtemp) { if (delv > vtstlo) vnew = vold + vtstlo; }
+      else vnew = vtemp;
+    }
+  }
+  return vnew;
+}
+
+}  // namespace xb
