@@ -1,0 +1,124 @@
+"""Shared BSIM4 test helpers: model cards, synthetic netlists, host-mirror wrapper, assembly in numpy."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_SO = os.path.join(HERE, "host_mirror", "libxb_host.so")
+
+# 45 nm-like level-54 cards.  Only parameters that differ from BSIM4 defaults are listed.
+NMOS_CARD = dict(TOXE=1.8e-9, TOXP=1.5e-9, TOXM=1.8e-9, VTH0=0.42, K1=0.45, K2=0.01, U0=0.045, VSAT=1.2e5,
+                 NDEP=2.5e18, XJ=1.4e-8, RDSW=150.0, CGSO=1.1e-10, CGDO=1.1e-10, CJS=1.0e-3, CJSWS=2.0e-10,
+                 CJSWGS=3.0e-10, PBS=0.9, PBSWS=0.9, PBSWGS=0.9, MJS=0.45, JSS=1.0e-4, JSWS=1.0e-11,
+                 ETA0=0.06, DSUB=0.1, PCLM=0.6, NFACTOR=1.8, VOFF=-0.12, CAPMOD=2, MOBMOD=0)
+PMOS_CARD = dict(TOXE=1.9e-9, TOXP=1.6e-9, TOXM=1.9e-9, VTH0=-0.40, K1=0.40, K2=-0.01, U0=0.012, VSAT=9.0e4,
+                 NDEP=2.0e18, XJ=1.4e-8, RDSW=200.0, CGSO=1.0e-10, CGDO=1.0e-10, CJS=1.1e-3, CJSWS=2.2e-10,
+                 CJSWGS=3.2e-10, PBS=0.9, PBSWS=0.9, PBSWGS=0.9, MJS=0.45, JSS=1.0e-4, JSWS=1.0e-11,
+                 ETA0=0.05, DSUB=0.1, PCLM=0.7, NFACTOR=1.6, VOFF=-0.10, CAPMOD=2, MOBMOD=0)
+
+# model-card variants that switch on otherwise-dormant code paths
+VARIANTS = {
+    "default": ({}, {}),
+    "igc": (dict(IGCMOD=1, IGBMOD=1), dict(IGCMOD=1, IGBMOD=1)),
+    "igc2": (dict(IGCMOD=2, IGBMOD=1, TEMPMOD=2), dict(IGCMOD=2, IGBMOD=1, TEMPMOD=2)),
+    "capmod0": (dict(CAPMOD=0), dict(CAPMOD=0, XPART=1.0)),
+    "capmod1": (dict(CAPMOD=1, XPART=0.0), dict(CAPMOD=1, XPART=0.5)),
+    "capmod2_xpart": (dict(CAPMOD=2, XPART=1.0), dict(CAPMOD=2, XPART=0.5)),
+    "mob1": (dict(MOBMOD=1), dict(MOBMOD=2)),
+    "mob3": (dict(MOBMOD=3), dict(MOBMOD=4)),
+    "mob5": (dict(MOBMOD=5), dict(MOBMOD=6)),
+    "diomod0": (dict(DIOMOD=0), dict(DIOMOD=2, BVS=5.0, XJBVS=1.0)),
+    "gidl": (dict(AGIDL=1e-9, BGIDL=1e9, AGISL=1e-9, BGISL=1e9), dict(GIDLMOD=1, AGIDL=1e-9, BGIDL=1e9, AGISL=1e-9, BGISL=1e9)),
+    "rdsmod": (dict(RDSMOD=1, RSH=5.0), dict(RDSMOD=1, RSH=5.0)),
+    "rsh": (dict(RSH=8.0), dict(RSH=8.0)),
+    "rgate": (dict(RGATEMOD=1, RSHG=2.0), dict(RGATEMOD=2, RSHG=2.0)),
+    "rgate3": (dict(RGATEMOD=3, RSHG=2.0), dict(RGATEMOD=3, RSHG=2.0)),
+    "rbody": (dict(RBODYMOD=1), dict(RBODYMOD=1)),
+    "pocket": (dict(DVTP0=1e-7, DVTP1=0.1, LAMBDA=1e-9, VTL=2e5, ALPHA0=1e-7, BETA0=20.0),
+               dict(DVTP0=1e-7, DVTP1=0.1, ALPHA0=1e-7, BETA0=20.0)),
+    "cvcharge": (dict(CVCHARGEMOD=1), dict(CVCHARGEMOD=1)),
+    "mtrl": (dict(MTRLMOD=1, EOT=1.7e-9, PHIG=4.2, EPSRGATE=11.7), dict(TNOIMOD=1)),
+}
+
+FLAG_NAMES = ["dcop", "tranop", "acop", "transient", "dcsweep", "initJct", "initFix", "initTran",
+              "newtonIter", "locaEnabled", "artParameter", "voltageLimiter"]
+
+
+def build_host_mirror():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "host_mirror")])
+    return HOST_SO
+
+
+class HostMirror:
+    """ctypes wrapper of tests/host_mirror/libxb_host.so (the kernel source compiled for CPU)."""
+
+    def __init__(self):
+        build_host_mirror()
+        self.lib = C.CDLL(HOST_SO)
+        self.lib.xbh_b4_mid_names.restype = C.c_char_p
+        self.mid_d_names = self.lib.xbh_b4_mid_names(0).decode().split()
+        self.mid_i_names = self.lib.xbh_b4_mid_names(1).decode().split()
+        self.slot_row = np.zeros(62, dtype=np.int32)
+        self.slot_col = np.zeros(62, dtype=np.int32)
+        self.lib.xbh_b4_slot_tables(self.slot_row.ctypes.data_as(C.POINTER(C.c_int)),
+                                    self.slot_col.ctypes.data_as(C.POINTER(C.c_int)))
+
+    def eval(self, rec, flags, V12, sto_old13, have_old, von_prev):
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        fl = np.array([flags.get(k, 1 if k == "voltageLimiter" else 0) for k in FLAG_NAMES], dtype=np.int32)
+        fd = np.array([flags.get("gmin", 1e-12), flags.get("gainScale", 1.0), flags.get("nltermScale", 1.0)])
+        out = dict(F=np.zeros(11), Q=np.zeros(11), FL=np.zeros(11), QL=np.zeros(11), JF=np.zeros(62),
+                   JQ=np.zeros(62), store=np.zeros(22), state=np.zeros(3))
+        md = np.zeros(len(self.mid_d_names))
+        mi = np.zeros(len(self.mid_i_names), dtype=np.int32)
+        V = np.ascontiguousarray(V12, dtype=np.float64)
+        so = np.ascontiguousarray(sto_old13, dtype=np.float64)
+        self.lib.xbh_b4_eval(dp(rec["model_d"]), ip(rec["model_i"]), dp(rec["size_d"]), dp(rec["inst_d"]),
+                             ip(rec["inst_i"]), ip(fl), dp(fd), dp(V), dp(so), int(have_old), C.c_double(von_prev),
+                             dp(out["F"]), dp(out["Q"]), dp(out["FL"]), dp(out["QL"]), dp(out["JF"]), dp(out["JQ"]),
+                             dp(out["store"]), dp(out["state"]), dp(md), ip(mi))
+        out["mid_d"] = dict(zip(self.mid_d_names, md.tolist()))
+        out["mid_i"] = dict(zip(self.mid_i_names, mi.tolist()))
+        return out
+
+
+def isolated_devices(ref_cls, n_pairs, variant="default", seed=0, inst_extra=None):
+    """n_pairs nmos + n_pairs pmos, every terminal on its own node (4 nodes per device)."""
+    rng = np.random.default_rng(seed)
+    ndev = 2 * n_pairs
+    c = ref_cls(4 * ndev)
+    nv, pv = VARIANTS[variant]
+    c.add_model("nch", "NMOS", {**NMOS_CARD, **nv})
+    c.add_model("pch", "PMOS", {**PMOS_CARD, **pv})
+    for i in range(ndev):
+        is_n = (i % 2 == 0)
+        ip = dict(L=float(rng.choice([6e-8, 1e-7, 2.5e-7])), W=float(rng.choice([2e-7, 1e-6, 4e-6])),
+                  AD=2e-13, AS=2e-13, PD=2.4e-6, PS=2.4e-6)
+        if inst_extra:
+            ip.update(inst_extra)
+        c.add_instance("M:%d" % i, "nch" if is_n else "pch", [4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3], ip)
+    c.finalize()
+    return c
+
+
+def assemble_general(hm, per_inst, lids, n, rowptr, colind):
+    """Scatter per-instance general-stamp outputs into global vectors / CSR values (numpy, small cases)."""
+    f, q, fl, ql = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    jf, jq = np.zeros(len(colind)), np.zeros(len(colind))
+    for o, l in zip(per_inst, lids):
+        for r in range(11):
+            g = l[r]
+            if g < 0:
+                continue
+            f[g] += o["F"][r]; q[g] += o["Q"][r]; fl[g] += o["FL"][r]; ql[g] += o["QL"][r]
+        for s in range(62):
+            gr, gc = l[hm.slot_row[s]], l[hm.slot_col[s]]
+            if gr < 0 or gc < 0 or (o["JF"][s] == 0.0 and o["JQ"][s] == 0.0):
+                continue
+            seg = colind[rowptr[gr]:rowptr[gr + 1]]
+            k = rowptr[gr] + int(np.searchsorted(seg, gc))
+            assert colind[k] == gc, "stamp entry outside the reference's CSR pattern"
+            jf[k] += o["JF"][s]; jq[k] += o["JQ"][s]
+    return dict(f=f, q=q, dFdxdVp=fl, dQdxdVp=ql, dFdx=jf, dQdx=jq)

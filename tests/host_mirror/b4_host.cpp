@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE ONLY: compiles the single-source BSIM4 evaluator (xyce_b200/csrc/*.h)
+// for the host so that CPU-only CI can check its arithmetic against the reference-built
+// oracle (oracle/_ref) without a GPU.  Never loaded by the product; the product path is
+// the CUDA library and fails loudly when that is missing.
+#include <cstring>
+#include "../../xyce_b200/csrc/bsim4_instance.h"
+
+using namespace xb;
+using namespace xb::b4;
+
+namespace {
+struct GeneralEmitter {
+  double F[kNumRows], Q[kNumRows], FL[kNumRows], QL[kNumRows], JF[kNumSlots], JQ[kNumSlots];
+  template <int R> void f(double v) { F[R] += v; }
+  template <int R> void q(double v) { Q[R] += v; }
+  template <int R> void fl(double v) { FL[R] += v; }
+  template <int R> void ql(double v) { QL[R] += v; }
+  template <int S> void jf(double v) { JF[S] += v; }
+  template <int S> void jq(double v) { JQ[S] += v; }
+};
+}  // namespace
+
+extern "C" {
+
+const char *xbh_b4_mid_names(int which) {
+#define NM(n) #n "\n"
+  return which == 0 ? XB_B4_MID_D(NM) XB_B4_MID_EXTRA_D(NM) : XB_B4_MID_I(NM);
+#undef NM
+}
+int xbh_b4_mid_count(int which) {
+#define CNT(n) +1
+  return which == 0 ? (0 XB_B4_MID_D(CNT) XB_B4_MID_EXTRA_D(CNT)) : (0 XB_B4_MID_I(CNT));
+#undef CNT
+}
+
+int xbh_b4_eval(const double *model_d, const int *model_i, const double *size_d, const double *inst_d,
+                const int *inst_i, const int *fl, const double *fd, const double *V12, const double *sto_old13,
+                int have_old, double von_prev, double *F, double *Q, double *FL, double *QL, double *JF,
+                double *JQ, double *store22, double *state3, double *mid_d, int *mid_i) {
+  B4Model M; B4Size P; B4Inst I; SolverFlags S;
+  int k;
+#define GET(n) M.n = model_d[k++];
+  k = 0; XB_B4_MODEL_D(GET)
+#undef GET
+#define GET(n) M.n = model_i[k++];
+  k = 0; XB_B4_MODEL_I(GET)
+#undef GET
+#define GET(n) P.n = size_d[k++];
+  k = 0; XB_B4_SIZE_D(GET)
+#undef GET
+#define GET(n) I.n = inst_d[k++];
+  k = 0; XB_B4_INST_D(GET)
+#undef GET
+#define GET(n) I.n = inst_i[k++];
+  k = 0; XB_B4_INST_I(GET)
+#undef GET
+  std::memset(&S, 0, sizeof(S));
+  S.dcopFlag = fl[0]; S.tranopFlag = fl[1]; S.acopFlag = fl[2]; S.transientFlag = fl[3]; S.dcsweepFlag = fl[4];
+  S.initJctFlag = fl[5]; S.initFixFlag = fl[6]; S.initTranFlag = fl[7]; S.newtonIter = fl[8];
+  S.locaEnabledFlag = fl[9]; S.artParameterFlag = fl[10]; S.voltageLimiterFlag = fl[11];
+  S.gmin = fd[0]; S.gainScale = fd[1]; S.nltermScale = fd[2]; S.vgstConst = 4.5; S.vdsScaleMin = 0.3;
+  B4Mid W;
+  std::memset(&W, 0, sizeof(W));
+  GeneralEmitter e;
+  std::memset(&e, 0, sizeof(e));
+  evaluate(S, M, P, I, V12, sto_old13, have_old != 0, von_prev, W, e);
+  std::memcpy(F, e.F, sizeof(e.F)); std::memcpy(Q, e.Q, sizeof(e.Q));
+  std::memcpy(FL, e.FL, sizeof(e.FL)); std::memcpy(QL, e.QL, sizeof(e.QL));
+  std::memcpy(JF, e.JF, sizeof(e.JF)); std::memcpy(JQ, e.JQ, sizeof(e.JQ));
+  for_each_store(W, [&](int s, double v) { store22[s] = v; });
+  state3[sa_qb] = W.qb; state3[sa_qg] = W.qg; state3[sa_qd] = W.qd;
+  k = 0;
+#define PUT(n) mid_d[k++] = W.n;
+  XB_B4_MID_D(PUT) XB_B4_MID_EXTRA_D(PUT)
+#undef PUT
+  k = 0;
+#define PUT(n) mid_i[k++] = W.n;
+  XB_B4_MID_I(PUT)
+#undef PUT
+  return 0;
+}
+
+void xbh_b4_slot_tables(int *row, int *col) {
+  for (int s = 0; s < kNumSlots; ++s) { row[s] = kSlotRow[s]; col[s] = kSlotCol[s]; }
+}
+
+}  // extern "C"

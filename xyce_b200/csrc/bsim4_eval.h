@@ -135,7 +135,7 @@ XB_HD void stage_voltages(const SolverFlags &S, const B4Model &M, const B4Inst &
                           double von_prev, B4Mid &W) {
   const double Vd = V[kD], Vs = V[kS], Vb = V[kB], Vsp = V[kSP], Vdp = V[kDP];
   const double Vgp = V[kGP], Vbp = V[kBP], Vge = V[kGE];
-  const double Vgm = (I.rgateMod == 3) ? V[kGM] : 0.0;
+  const double Vgm = V[kGM];   // li_GateMid aliases li_GateExt unless rgateMod == 3 (B4.C:6228-6235)
   const double Vdb = V[kDB], Vsb = V[kSB];
   const double Qtotal = I.trnqsMod ? V[kQ] : 0.0;
   const double ty = (double)M.dtype;

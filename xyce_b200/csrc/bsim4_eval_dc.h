@@ -265,7 +265,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   double n, dn_dVb, dn_dVd;
   {
     const double tmp1 = epssub / Xdep;
-    W.nstar = M.vtm / kQ * (M.coxe + tmp1 + P.cit);
+    // (nstar, a noise-only quantity at B4p82.C:3908, is not evaluated)
     const double tmp2 = P.nfactor * tmp1;
     const double tmp3 = P.cdsc + P.cdscb * Vbseff + P.cdscd * Vds;
     const double tmp4 = (tmp2 + tmp3 * Theta0 + P.cit) / M.coxe;
@@ -1479,6 +1479,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.Vdsat = Vdsat;
     W.Vdseff = Vdseff;
   }
+
+  W.Vds_s = Vds; W.Vgs_s = Vgs; W.Vbs_s = Vbs;   // reference members Vds, Vgs, Vbs
 
   // ---- hand over to the C-V stage ---------------------------------------------------------------------
   C.Vds = Vds; C.Vgs = Vgs; C.Vbs = Vbs; C.Vdb = Vdb;
