@@ -1,0 +1,113 @@
+/* xyce_b200 -- C ABI of the B200-native Newton-step engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Xyce itself has
+ * no C ABI on this path; each entry point below replaces the reference *C++ virtual* it cites
+ * and is what adaptor subclasses (GpuMaster<Traits> : DeviceMaster<Traits>, GpuSolver :
+ * Linear::Solver -- see INTEGRATION.md) call.  All functions return 0 on success and a
+ * non-zero code otherwise (xgpu_last_error gives the text), never throw, and must be called
+ * from the single host thread that owns the context (the reference's loaders are
+ * single-threaded per rank).  "d_" arguments are DEVICE pointers.
+ */
+#ifndef XYCE_B200_H
+#define XYCE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xgpu_ctx xgpu_ctx;
+
+/* Per-launch constant block: the members of Device::SolverState
+ * (src/DeviceModelPKG/Core/N_DEV_SolverState.h:114-217) and Device::DeviceOptions
+ * (Core/N_DEV_DeviceOptions.C:79-150) that model evaluation reads.  Filled by the adaptor
+ * from getSolverState()/getDeviceOptions() before every xgpu_update_state call
+ * (replaces DeviceMgr::setupSolverInfo, Core/N_DEV_DeviceMgr.C:3872-3873). */
+typedef struct xgpu_solver_state {
+  int dcopFlag, tranopFlag, acopFlag, transientFlag, dcsweepFlag;
+  int initJctFlag, initFixFlag, initTranFlag, newtonIter, locaEnabledFlag;
+  int artParameterFlag, voltageLimiterFlag;
+  double gmin, gainScale, nltermScale, vgstConst, vdsScaleMin, sizeScale, currTimeStep;
+} xgpu_solver_state;
+
+/* ---- lifetime ---- */
+int xgpu_create(int device, xgpu_ctx **out);
+void xgpu_destroy(xgpu_ctx *ctx);
+const char *xgpu_last_error(const xgpu_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
+int xgpu_set_stream(xgpu_ctx *ctx, void *cuda_stream);
+int xgpu_sync(xgpu_ctx *ctx);
+
+/* ---- linear-system shape ----
+ * CSR pattern shared by dFdx, dQdx and the Jacobian: the output of
+ * SerialLSUtil::generateRowColData (src/TopoManagerPKG/N_TOP_SerialLSUtil.C:620-703), ground
+ * rows/columns stripped, columns sorted within a row. */
+int xgpu_pattern_set(xgpu_ctx *ctx, int n_unknowns, const int32_t *rowptr, const int32_t *colind);
+/* Lengths of the state and store vectors (TimeIntg::DataStore, N_TIA_DataStore.h:145-300). */
+int xgpu_sizes_set(xgpu_ctx *ctx, int n_state, int n_store);
+
+/* ---- BSIM4 (level 14/54, v4.8.2) device group ----
+ * Replaces Device::addModel / addInstance bookkeeping plus Instance::registerLIDs,
+ * registerStateLIDs, registerStoreLIDs (N_DEV_MOSFET_B4.C:6179-6487): the adaptor passes the
+ * constants Xyce's own processParams4p82_/updateTemperature4p82_ computed and the LIDs the
+ * Topology package handed out.  Record field order: xgpu_b4_field_names(). */
+/* which: 0 model doubles, 1 model ints, 2 size-bin doubles, 3 instance doubles, 4 instance ints */
+int xgpu_b4_field_count(int which);
+const char *xgpu_b4_field_names(int which);            /* newline-separated, in record order */
+int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const int32_t *model_i,
+                       int n_sizes, const double *size_d);
+/* Adds n_inst instances (arrays are instance-major / "array of records").  lids12: the 12 node
+ * LIDs {Drain,GateExt,Source,Body,DrainPrime,SourcePrime,GatePrime,GateMid,BodyPrime,SourceBody,
+ * DrainBody,Charge} with collapsed nodes aliased exactly as registerLIDs does, -1 = ground.
+ * Store slot s of instance i lives at sto_lid0[i] + s*sto_stride (same for state).
+ * Returns the group id (>= 0) or a negative error. */
+int xgpu_b4_group_add(xgpu_ctx *ctx, int n_inst, const double *inst_d, const int32_t *inst_i,
+                      const int32_t *model_idx, const int32_t *size_idx, const int32_t *lids12,
+                      const int32_t *sto_lid0, int sto_stride, const int32_t *sta_lid0, int sta_stride);
+/* Builds the stamp -> CSR gather maps (replaces Instance::registerJacLIDs/setupPointers,
+ * N_DEV_MOSFET_B4.C:6524-6846, and Indexor::matrixGlobalToLocal, N_TOP_Indexor.C:149-214). */
+int xgpu_finalize(xgpu_ctx *ctx);
+
+/* Carried per-instance limiter threshold (Instance::von); instance order = insertion order. */
+int xgpu_b4_von_set(xgpu_ctx *ctx, int group, const double *von);
+int xgpu_b4_von_get(xgpu_ctx *ctx, int group, double *von);
+
+/* ---- hot path (device pointers) ----
+ * xgpu_update_state   <- Device::updateState            (Core/N_DEV_Device.h:312-332;
+ *                        DeviceMgr::updateState, Core/N_DEV_DeviceMgr.C:3857-3936)
+ *   evaluates every instance of every group at d_sol, writes next store/state (and current state
+ *   on the first transient Newton step) and the per-instance contributions.
+ * xgpu_load_vectors   <- Device::loadDAEVectors         (N_DEV_Device.h:378-404; DeviceMgr :4156-4284)
+ * xgpu_load_matrices  <- Device::loadDAEMatrices        (N_DEV_Device.h:427-450; DeviceMgr :3980-4115)
+ *   accumulate != 0 keeps the "+=" contract (caller zeroed / other devices already loaded);
+ *   accumulate == 0 overwrites, which saves the caller's zero-fill pass.
+ * xgpu_all_converged  <- DeviceMgr::allDevicesConverged (Core/N_DEV_DeviceMgr.C:5603-5640) */
+int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, double *d_curr_sta,
+                      double *d_next_sto, double *d_curr_sto, const xgpu_solver_state *ss);
+int xgpu_load_vectors(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_dFdxdVp, double *d_dQdxdVp,
+                      int accumulate);
+int xgpu_load_matrices(xgpu_ctx *ctx, double *d_dFdx, double *d_dQdx, int accumulate);
+int xgpu_all_converged(xgpu_ctx *ctx, int *converged);
+/* J = qscalar*dQdx + fscalar*dFdx  <- Matrix::linearCombo as used by OneStep::obtainJacobian
+ * (N_LAS_EpetraMatrix.C:629-648, N_TIA_OneStep.C:490-495). */
+int xgpu_jacobian_combine(xgpu_ctx *ctx, double qscalar, const double *d_dQdx, double fscalar,
+                          const double *d_dFdx, double *d_jac);
+
+/* ---- host-buffer convenience path (what a non-GPU-aware caller uses; copies inside) ----
+ * One updateState + loadDAEVectors + loadDAEMatrices pass.  Vectors have n_unknowns entries,
+ * matrices nnz entries; next/curr store and state live in the context between calls. */
+int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double *h_f, double *h_q,
+                   double *h_dFdxdVp, double *h_dQdxdVp, double *h_dFdx, double *h_dQdx);
+/* which: 0 next store, 1 curr store, 2 next state, 3 curr state */
+int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h_vals);
+int xgpu_state_get(xgpu_ctx *ctx, int which, double *h_vals);
+/* Device pointers of the context-owned buffers used by xgpu_load_host:
+ * 0 sol, 1 f, 2 q, 3 dFdxdVp, 4 dQdxdVp, 5 dFdx, 6 dQdx, 7 next sto, 8 curr sto, 9 next sta, 10 curr sta */
+double *xgpu_device_buffer(xgpu_ctx *ctx, int which);
+
+/* Kernel launches issued by this context since creation (bench bookkeeping). */
+long long xgpu_launch_count(const xgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XYCE_B200_H */

@@ -122,3 +122,57 @@ def assemble_general(hm, per_inst, lids, n, rowptr, colind):
             assert colind[k] == gc, "stamp entry outside the reference's CSR pattern"
             jf[k] += o["JF"][s]; jq[k] += o["JQ"][s]
     return dict(f=f, q=q, dFdxdVp=fl, dQdxdVp=ql, dFdx=jf, dQdx=jq)
+
+
+def records_from_ref(ref):
+    """Collect de-duplicated model / size-bin records and per-instance records from a RefCircuit."""
+    models, sizes = {}, {}
+    md, mi, sd = [], [], []
+    inst_d, inst_i, midx, sidx, lids, sto0, sta0 = [], [], [], [], [], [], []
+    for i in range(ref.n_inst):
+        e = ref.export(i)
+        if e["model_id"] not in models:
+            models[e["model_id"]] = len(md); md.append(e["model_d"]); mi.append(e["model_i"])
+        if e["size_id"] not in sizes:
+            sizes[e["size_id"]] = len(sd); sd.append(e["size_d"])
+        inst_d.append(e["inst_d"]); inst_i.append(e["inst_i"])
+        midx.append(models[e["model_id"]]); sidx.append(sizes[e["size_id"]])
+        lids.append(e["lids"]); sto0.append(e["sto0"]); sta0.append(e["sta0"])
+    return dict(model_d=np.array(md), model_i=np.array(mi, dtype=np.int32), size_d=np.array(sd),
+                inst_d=np.array(inst_d), inst_i=np.array(inst_i, dtype=np.int32),
+                model_idx=np.array(midx, dtype=np.int32), size_idx=np.array(sidx, dtype=np.int32),
+                lids=np.array(lids, dtype=np.int32), sto0=np.array(sto0, dtype=np.int32),
+                sta0=np.array(sta0, dtype=np.int32))
+
+
+def engine_from_ref(ref, device=0):
+    """Upload a RefCircuit's topology and Xyce-computed constants into a GPU Engine (what a
+    GpuMaster adaptor does at setup time)."""
+    import xyce_b200
+    rec = records_from_ref(ref)
+    eng = xyce_b200.Engine(device)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.b4_set_models(rec["model_d"], rec["model_i"], rec["size_d"])
+    eng.b4_add_group(rec["inst_d"], rec["inst_i"], rec["model_idx"], rec["size_idx"], rec["lids"],
+                     rec["sto0"], 1, rec["sta0"], 1)
+    eng.finalize()
+    return eng, rec
+
+
+def solver_state(**kw):
+    import xyce_b200
+    m = dict(dcop="dcopFlag", tranop="tranopFlag", acop="acopFlag", transient="transientFlag",
+             dcsweep="dcsweepFlag", initJct="initJctFlag", initFix="initFixFlag", initTran="initTranFlag",
+             newtonIter="newtonIter", locaEnabled="locaEnabledFlag", artParameter="artParameterFlag",
+             voltageLimiter="voltageLimiterFlag")
+    return xyce_b200.SolverState(**{m.get(k, k): v for k, v in kw.items()})
+
+
+def rel_err(a, b, scale=None):
+    """max |a-b| / max(|b|, scale): element-wise relative error with an absolute floor."""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.size == 0:
+        return 0.0
+    s = np.maximum(np.abs(b), 1e-300 if scale is None else scale)
+    return float(np.max(np.abs(a - b) / s))

@@ -1,0 +1,71 @@
+"""GPU parity: CUDA BSIM4 evaluation + assembly (through the C ABI, host buffers) against the
+reference's own BSIM4 objects (oracle/_ref).  Tolerance: 1e-12 relative, scaled by the magnitude
+of the entry or, for sums that cancel, by the largest entry of the same vector/matrix
+(BASELINE.json north_star; SURVEY.md 8a accumulation-order note)."""
+import numpy as np
+import pytest
+
+import oracle_ref
+from b4_common import VARIANTS, engine_from_ref, isolated_devices, rel_err, solver_state
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+FLAG_CASES = {
+    "tran_iter1": dict(transient=1, newtonIter=1),
+    "tran_iter0": dict(transient=1, newtonIter=0),
+    "tran_init": dict(transient=1, newtonIter=0, initTran=1),
+    "dcop_initjct": dict(dcop=1, tranop=1, transient=1, initJct=1, newtonIter=0),
+    "dcop_iter2": dict(dcop=1, tranop=1, transient=1, newtonIter=2),
+    "dc_nocharge": dict(dcop=1, newtonIter=1),
+    "nolimit": dict(transient=1, newtonIter=1, voltageLimiter=0),
+}
+
+
+def run_case(variant, flags, n_pairs=16, seed=3, store_noise=0.3):
+    assert oracle_ref.available(), "oracle/_ref/libxyce_ref.so must travel with the snapshot"
+    ref = isolated_devices(oracle_ref.RefCircuit, n_pairs, variant, seed=seed)
+    eng, rec = engine_from_ref(ref)
+    rng = np.random.default_rng(seed + 100)
+    x = rng.uniform(-0.3, 1.3, ref.n)
+    nsto = rng.normal(0.3, store_noise, ref.n_sto)
+    csto = rng.normal(0.3, store_noise, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    ref.set_flags(**flags)
+    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=np.zeros(ref.n_sta))
+    ref.set_von(von)
+    eng.set_state(0, nsto); eng.set_state(1, csto)
+    eng.b4_set_von(0, von)
+    want = ref.load(x)
+    got = eng.load_host(x, solver_state(**flags))
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < TOL, (variant, flags, k)
+        # and entry-wise wherever no cancellation is involved
+    st = ref.get_state()
+    assert rel_err(eng.get_state(0), st["next_sto"], 1e-30) < TOL
+    assert rel_err(eng.get_state(2), st["next_sta"], 1e-30) < TOL
+    assert rel_err(eng.get_state(3), st["curr_sta"], 1e-30) < TOL
+    assert rel_err(eng.b4_get_von(0, ref.n_inst), ref.get_von(), 1e-30) < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_variants_transient(variant):
+    run_case(variant, FLAG_CASES["tran_iter1"])
+
+
+@pytest.mark.parametrize("case", sorted(FLAG_CASES))
+def test_flag_cases_default_card(case):
+    run_case("default", FLAG_CASES[case])
+
+
+@pytest.mark.parametrize("case", ["tran_iter0", "dcop_initjct", "nolimit"])
+@pytest.mark.parametrize("variant", ["rgate3", "rbody", "rdsmod", "igc"])
+def test_flag_cases_general_topology(variant, case):
+    run_case(variant, FLAG_CASES[case])
+
+
+def test_pass_through_limiters():
+    # previous iterate == present voltages: limiters take the pass-through branch (C2 operating point)
+    run_case("default", FLAG_CASES["tran_iter1"], store_noise=0.0)

@@ -1,0 +1,184 @@
+"""ctypes binding of include/xyce_b200.h.  No CPU fallback: a missing library or GPU raises."""
+import ctypes as C
+import os
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libxyce_b200.so")
+_lib = None
+
+FLAG_FIELDS = ["dcopFlag", "tranopFlag", "acopFlag", "transientFlag", "dcsweepFlag", "initJctFlag", "initFixFlag",
+               "initTranFlag", "newtonIter", "locaEnabledFlag", "artParameterFlag", "voltageLimiterFlag"]
+REAL_FIELDS = ["gmin", "gainScale", "nltermScale", "vgstConst", "vdsScaleMin", "sizeScale", "currTimeStep"]
+
+
+class SolverState(C.Structure):
+    """Mirror of xgpu_solver_state (Device::SolverState + DeviceOptions subset)."""
+    _fields_ = [(n, C.c_int) for n in FLAG_FIELDS] + [(n, C.c_double) for n in REAL_FIELDS]
+
+    def __init__(self, **kw):
+        super().__init__()
+        # DeviceOptions defaults: Core/N_DEV_DeviceOptions.C:79-150
+        self.voltageLimiterFlag = 1
+        self.gmin = 1e-12
+        self.gainScale = 1.0
+        self.nltermScale = 1.0
+        self.vgstConst = 4.5
+        self.vdsScaleMin = 0.3
+        self.sizeScale = 1.0
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def load_library():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("xyce_b200: %s is missing -- run __graft_entry__.build() (nvcc, sm_100a); "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.xgpu_last_error.restype = C.c_char_p
+    lib.xgpu_b4_field_names.restype = C.c_char_p
+    lib.xgpu_device_buffer.restype = C.c_void_p
+    lib.xgpu_launch_count.restype = C.c_longlong
+    lib.xgpu_jacobian_combine.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One GPU context (one process per GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.xgpu_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("xgpu_create failed with code %d (a CUDA device is required; no CPU fallback)" % rc)
+        self.h = h
+        self.n = 0
+        self.nnz = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("xyce_b200 error %d: %s" % (rc, self.lib.xgpu_last_error(self.h).decode()))
+
+    def close(self):
+        if self.h:
+            self.lib.xgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.lib.xgpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._chk(self.lib.xgpu_sync(self.h))
+
+    def set_pattern(self, rowptr, colind):
+        rowptr, colind = _i32(rowptr), _i32(colind)
+        self.n, self.nnz = len(rowptr) - 1, len(colind)
+        self._chk(self.lib.xgpu_pattern_set(self.h, self.n, _ip(rowptr), _ip(colind)))
+
+    def set_sizes(self, n_state, n_store):
+        self.n_state, self.n_store = int(n_state), int(n_store)
+        self._chk(self.lib.xgpu_sizes_set(self.h, self.n_state, self.n_store))
+
+    def field_names(self, which):
+        return self.lib.xgpu_b4_field_names(which).decode().split()
+
+    def b4_set_models(self, model_d, model_i, size_d):
+        model_d, model_i, size_d = _f64(model_d), _i32(model_i), _f64(size_d)
+        self._chk(self.lib.xgpu_b4_models_set(self.h, model_d.shape[0], _dp(model_d), _ip(model_i),
+                                              size_d.shape[0], _dp(size_d)))
+
+    def b4_add_group(self, inst_d, inst_i, model_idx, size_idx, lids12, sto_lid0, sto_stride, sta_lid0, sta_stride):
+        inst_d, inst_i = _f64(inst_d), _i32(inst_i)
+        a = [_i32(x) for x in (model_idx, size_idx, lids12, sto_lid0, sta_lid0)]
+        gid = self.lib.xgpu_b4_group_add(self.h, inst_d.shape[0], _dp(inst_d), _ip(inst_i), _ip(a[0]), _ip(a[1]),
+                                         _ip(a[2]), _ip(a[3]), int(sto_stride), _ip(a[4]), int(sta_stride))
+        if gid < 0:
+            raise RuntimeError("xgpu_b4_group_add failed (%d): %s" % (gid, self.lib.xgpu_last_error(self.h).decode()))
+        return gid
+
+    def finalize(self):
+        self._chk(self.lib.xgpu_finalize(self.h))
+
+    def b4_set_von(self, group, von):
+        von = _f64(von)
+        self._chk(self.lib.xgpu_b4_von_set(self.h, group, _dp(von)))
+
+    def b4_get_von(self, group, n):
+        von = np.zeros(n)
+        self._chk(self.lib.xgpu_b4_von_get(self.h, group, _dp(von)))
+        return von
+
+    def set_state(self, which, vals):
+        vals = _f64(vals)
+        self._chk(self.lib.xgpu_state_set(self.h, which, _dp(vals)))
+
+    def get_state(self, which):
+        out = np.zeros(self.n_store if which < 2 else self.n_state)
+        self._chk(self.lib.xgpu_state_get(self.h, which, _dp(out)))
+        return out
+
+    def load_host(self, x, ss, want_matrices=True):
+        """Host-buffer path: H2D solution, evaluate + assemble on the GPU, D2H results."""
+        x = _f64(x)
+        out = {k: np.zeros(self.n) for k in ("f", "q", "dFdxdVp", "dQdxdVp")}
+        out["dFdx"] = np.zeros(self.nnz) if want_matrices else None
+        out["dQdx"] = np.zeros(self.nnz) if want_matrices else None
+        self._chk(self.lib.xgpu_load_host(self.h, _dp(x), C.byref(ss), _dp(out["f"]), _dp(out["q"]),
+                                          _dp(out["dFdxdVp"]), _dp(out["dQdxdVp"]), _dp(out["dFdx"]), _dp(out["dQdx"])))
+        return out
+
+    def device_buffer(self, which):
+        return self.lib.xgpu_device_buffer(self.h, which)
+
+    # device-pointer hot path (pointers as integers, e.g. torch.Tensor.data_ptr())
+    def update_state(self, d_sol, d_next_sta, d_curr_sta, d_next_sto, d_curr_sto, ss):
+        p = C.c_void_p
+        self._chk(self.lib.xgpu_update_state(self.h, p(d_sol), p(d_next_sta), p(d_curr_sta), p(d_next_sto),
+                                             p(d_curr_sto), C.byref(ss)))
+
+    def load_vectors(self, d_f, d_q, d_fl, d_ql, accumulate=False):
+        p = C.c_void_p
+        self._chk(self.lib.xgpu_load_vectors(self.h, p(d_f), p(d_q), p(d_fl), p(d_ql), int(accumulate)))
+
+    def load_matrices(self, d_dfdx, d_dqdx, accumulate=False):
+        p = C.c_void_p
+        self._chk(self.lib.xgpu_load_matrices(self.h, p(d_dfdx), p(d_dqdx), int(accumulate)))
+
+    def jacobian_combine(self, qs, d_dqdx, fs, d_dfdx, d_jac):
+        p = C.c_void_p
+        self._chk(self.lib.xgpu_jacobian_combine(self.h, qs, p(d_dqdx), fs, p(d_dfdx), p(d_jac)))
+
+    def all_converged(self):
+        v = C.c_int()
+        self._chk(self.lib.xgpu_all_converged(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def launch_count(self):
+        return int(self.lib.xgpu_launch_count(self.h))

@@ -1,0 +1,95 @@
+// xyce_b200 -- assembly kernels (sm_100a).  HBM-bandwidth bound: per destination the kernel
+// reads 4 bytes of map + 8 bytes per contribution per plane and writes 8 bytes per plane.
+#include "assembly.cuh"
+
+namespace xb {
+namespace {
+
+constexpr int kMaxPlanes = 4;
+struct PlaneSet {
+  const double *in[kMaxPlanes];
+  double *out[kMaxPlanes];
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256) gather_short_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= m.ndst) return;
+  const int64_t b = m.ptr[d], e = m.ptr[d + 1];
+  if (e - b > kLongThreshold) return;   // handled by gather_long_kernel
+  double acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = accumulate ? ps.out[p][d] : 0.0;
+  for (int64_t k = b; k < e; ++k) {
+    const int32_t s = __ldg(m.src + k);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) ps.out[p][d] = acc[p];
+}
+
+// One block per long destination; fixed-shape reduction: each thread sums a strided
+// subsequence in index order, then a shared-memory tree combines the 256 partials.
+template <int NP>
+__global__ void __launch_bounds__(256) gather_long_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
+  __shared__ double sh[NP][256];
+  const int d = m.long_dst[blockIdx.x];
+  const int64_t b = m.ptr[d], e = m.ptr[d + 1];
+  double acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
+  for (int64_t k = b + threadIdx.x; k < e; k += 256) {
+    const int32_t s = __ldg(m.src + k);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] += sh[p][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) ps.out[p][d] = (accumulate ? ps.out[p][d] : 0.0) + sh[p][0];
+  }
+}
+
+__global__ void __launch_bounds__(256) linear_combo_kernel(int64_t nnz, double a, const double *__restrict__ A,
+                                                           double b, const double *__restrict__ B,
+                                                           double *__restrict__ J) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nnz) J[k] = a * A[k] + b * B[k];
+}
+
+template <int NP>
+void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
+  if (m.ndst > 0) gather_short_kernel<NP><<<(m.ndst + 255) / 256, 256, 0, stream>>>(m, ps, accumulate);
+  if (m.nlong > 0) gather_long_kernel<NP><<<m.nlong, 256, 0, stream>>>(m, ps, accumulate);
+}
+
+}  // namespace
+
+void launch_gather(const GatherMapDev &m, int nplanes, const double *const *planes, int64_t, double *const *dst,
+                   bool accumulate, cudaStream_t stream) {
+  PlaneSet ps{};
+  for (int p = 0; p < nplanes; ++p) { ps.in[p] = planes[p]; ps.out[p] = dst[p]; }
+  switch (nplanes) {
+    case 1: launch_np<1>(m, ps, accumulate, stream); break;
+    case 2: launch_np<2>(m, ps, accumulate, stream); break;
+    case 4: launch_np<4>(m, ps, accumulate, stream); break;
+    default: break;
+  }
+}
+
+void launch_linear_combo(int64_t nnz, double a, const double *A, double b, const double *B, double *J,
+                         cudaStream_t stream) {
+  if (nnz > 0) linear_combo_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(nnz, a, A, b, B, J);
+}
+
+}  // namespace xb

@@ -1,0 +1,47 @@
+// xyce_b200 -- deterministic, atomic-free assembly of device contributions into the
+// DAE vectors (F, Q, dFdxdVp, dQdxdVp) and CSR matrices (dF/dx, dQ/dx).
+//
+// Replaces the reference's scattered "+=" through raw pointers (Master::loadDAEVectors /
+// loadDAEMatrices, e.g. N_DEV_MOSFET_B4.C:10691-10776, :11038-11278; address rule
+// N_LAS_EpetraMatrix.C:658-664; offsets from N_TOP_Indexor.C:149-214) by a gather:
+// every destination (vector row / CSR nonzero) owns the list of contribution-plane
+// elements that land on it, ordered device-type-major, instance-minor -- the reference's
+// accumulation order (Core/N_DEV_DeviceMgr.C:4238-4248) -- and sums them in that fixed
+// order.  Destinations with a very long list (supply rails) are summed by one block with a
+// fixed-shape tree, so results are bitwise reproducible run to run.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace xb {
+
+// CSR-by-destination gather map.  src[] indexes one contribution plane.
+struct GatherMapHost {
+  std::vector<int64_t> ptr;   // [ndst+1]
+  std::vector<int32_t> src;   // [total]
+  std::vector<int32_t> long_dst;   // destinations with more than kLongThreshold sources
+};
+
+struct GatherMapDev {
+  int ndst = 0;
+  int nlong = 0;
+  int64_t total = 0;
+  int64_t *ptr = nullptr;
+  int32_t *src = nullptr;
+  int32_t *long_dst = nullptr;
+};
+
+constexpr int kLongThreshold = 96;
+
+// Sum `nplanes` planes through one map.  dst[p][d] = (accumulate ? dst[p][d] : 0) + sum_k plane[p][src[k]].
+// Long destinations are skipped by the short kernel and handled by the block kernel.
+void launch_gather(const GatherMapDev &m, int nplanes, const double *const *planes, int64_t plane_stride,
+                   double *const *dst, bool accumulate, cudaStream_t stream);
+
+// J = qscalar * dQdx + fscalar * dFdx over one CSR pattern (N_LAS_EpetraMatrix.C:629-648 linearCombo
+// as used by OneStep::obtainJacobian, N_TIA_OneStep.C:490-495).
+void launch_linear_combo(int64_t nnz, double a, const double *A, double b, const double *B, double *J,
+                         cudaStream_t stream);
+
+}  // namespace xb

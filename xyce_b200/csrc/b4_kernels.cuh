@@ -1,0 +1,60 @@
+// xyce_b200 -- device-side data layout and launch interface of the BSIM4 group kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "bsim4_instance.h"
+
+namespace xb {
+namespace b4 {
+
+// Packed per-instance topology word (replaces the 7 int members of B4Inst in HBM).
+XB_HD int pack_topo(const B4Inst &I) {
+  return (I.rgateMod & 3) | ((I.rbodyMod & 3) << 2) | ((I.trnqsMod & 1) << 4) | ((I.acnqsMod & 1) << 5) |
+         ((I.OFF & 1) << 6) | ((I.drainMOSFET_B4Exists & 1) << 7) | ((I.sourceMOSFET_B4Exists & 1) << 8);
+}
+XB_HD void unpack_topo(int w, B4Inst &I) {
+  I.rgateMod = w & 3; I.rbodyMod = (w >> 2) & 3; I.trnqsMod = (w >> 4) & 1; I.acnqsMod = (w >> 5) & 1;
+  I.OFF = (w >> 6) & 1; I.drainMOSFET_B4Exists = (w >> 7) & 1; I.sourceMOSFET_B4Exists = (w >> 8) & 1;
+}
+constexpr int kDefaultTopoMask = 0x1bf;   // every bit except OFF must be zero for the 4-terminal fast path
+
+// Contribution layout of one instance group inside the assembly planes.
+//   default topology: 4 rows, 16 slots (slot = 4*row + col over {D,G,S,B})
+//   general topology: 11 rows, 62 slots (B4Slot order)
+constexpr int kRowsDefault = 4, kSlotsDefault = 16;
+constexpr int kRowsGeneral = kNumRows, kSlotsGeneral = kNumSlots;
+
+// One group of BSIM4 instances evaluated by one launch.  All pointers are device pointers.
+struct GroupDev {
+  int n;                    // instances
+  int general;              // 0: default-topology fast path, 1: general stamp
+  const B4Model *models;    // [n_models]
+  const B4Size *sizes;      // [n_sizes]
+  const double *inst_d;     // [kNumInstD][n]  structure of arrays
+  const int *topo;          // [n] packed topology word
+  const int *model_idx;     // [n]
+  const int *size_idx;      // [n]
+  const int *lids;          // [4][n] (default) or [12][n] (general); -1 = ground
+  const int *sto_lid0;      // [n] LID of store slot 0
+  const int *sta_lid0;      // [n] LID of state slot 0
+  int sto_stride;           // LID distance between consecutive store slots of one instance
+  int sta_stride;
+  double *von;              // [n] carried limiter threshold (Instance::von)
+  int *orig_flag;           // [n] 1 = no limiting happened (DeviceInstance::origFlag)
+  // contribution planes (see assembly.cuh): element (row r, instance i) of this group lives at
+  // vec_base + r*n + i inside each of the 4 vector planes; slot s at mat_base + s*n + i.
+  long long vec_base, mat_base;
+};
+
+struct LoadArgs {
+  SolverFlags S;
+  const double *sol;        // next solution (length >= n_unknowns)
+  double *next_sto, *curr_sto;
+  double *next_sta, *curr_sta;
+  double *vec_planes[4];    // F, Q, dFdxdVp, dQdxdVp contribution planes
+  double *mat_planes[2];    // dFdx, dQdx contribution planes
+};
+
+void launch_b4_group(const GroupDev &g, const LoadArgs &a, cudaStream_t stream);
+
+}  // namespace b4
+}  // namespace xb

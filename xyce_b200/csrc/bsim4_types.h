@@ -54,6 +54,8 @@ enum B4Slot {
 };
 static_assert(kNumSlots == 62, "general BSIM4 stamp has 62 entries");
 
+#define XB_SLOT_ROW2(name, r, c) r,
+#define XB_SLOT_COL2(name, r, c) c,
 #define XB_SLOT_ROW(name, r, c) r,
 #define XB_SLOT_COL(name, r, c) c,
 // row / column node of each slot (host + device constexpr tables)
@@ -65,6 +67,11 @@ constexpr int kSlotCol[kNumSlots] = { XB_B4_SLOTS(XB_SLOT_COL) };
 // Default topology (rgateMod = rbodyMod = 0, no S/D resistor nodes, no NQS):
 // general node -> one of the 4 external terminals {D,G,S,B} = {0,1,2,3}.
 constexpr int kDefaultCollapse[kNumRows] = {0, 1, 2, 3, 0, 2, 1, 1, 3, 3, 3};
+
+// constexpr accessors usable in device code (namespace-scope constexpr arrays are host-only)
+XB_HD constexpr int slot_row(int s) { constexpr int t[kNumSlots] = { XB_B4_SLOTS(XB_SLOT_ROW2) }; return t[s]; }
+XB_HD constexpr int slot_col(int s) { constexpr int t[kNumSlots] = { XB_B4_SLOTS(XB_SLOT_COL2) }; return t[s]; }
+XB_HD constexpr int default_collapse(int r) { constexpr int t[kNumRows] = {0, 1, 2, 3, 0, 2, 1, 1, 3, 3, 3}; return t[r]; }
 
 // Store-vector slot order (Instance::registerStoreLIDs, N_DEV_MOSFET_B4.C:6445-6487).
 enum B4Store {

@@ -1,0 +1,480 @@
+// xyce_b200 -- implementation of the C ABI declared in include/xyce_b200.h.
+// Host-side C++: owns device copies of the parameter records and gather maps, builds the
+// stamp -> CSR maps once, and launches the sm_100a kernels.  There is deliberately no CPU
+// fallback: every entry point fails with an error code if CUDA is unavailable.
+#include "../../include/xyce_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "assembly.cuh"
+#include "b4_kernels.cuh"
+
+using namespace xb;
+using namespace xb::b4;
+
+namespace {
+
+struct HostGroup {
+  int n = 0;
+  int general = 0;
+  std::vector<int32_t> lids;       // [12][n] transposed (node-major)
+  GroupDev dev{};
+  // owned device memory
+  double *d_inst_d = nullptr, *d_von = nullptr;
+  int *d_topo = nullptr, *d_model_idx = nullptr, *d_size_idx = nullptr, *d_lids = nullptr;
+  int *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
+};
+
+}  // namespace
+
+struct xgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long long launches = 0;
+
+  int n = 0;
+  int64_t nnz = 0;
+  std::vector<int32_t> rowptr, colind;
+  int n_state = 0, n_store = 0;
+
+  B4Model *d_models = nullptr;
+  B4Size *d_sizes = nullptr;
+  int n_models = 0, n_sizes = 0;
+  std::vector<HostGroup> groups;
+  bool finalized = false;
+
+  // contribution planes
+  int64_t vec_plane = 0, mat_plane = 0;
+  double *d_vec_planes = nullptr;   // 4 * vec_plane
+  double *d_mat_planes = nullptr;   // 2 * mat_plane
+  GatherMapDev vec_map, mat_map;
+  int *d_conv = nullptr;
+
+  // context-owned system buffers (host-convenience path)
+  double *buf[11] = {nullptr};
+};
+
+namespace {
+
+int fail(xgpu_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define XG_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(ctx, 100 + (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+cudaError_t upload(T **dst, const T *src, size_t count) {
+  cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (count) e = cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+cudaError_t upload_map(const GatherMapHost &h, GatherMapDev &d) {
+  d.ndst = (int)h.ptr.size() - 1;
+  d.total = (int64_t)h.src.size();
+  d.nlong = (int)h.long_dst.size();
+  cudaError_t e;
+  if ((e = upload(&d.ptr, h.ptr.data(), h.ptr.size())) != cudaSuccess) return e;
+  if ((e = upload(&d.src, h.src.data(), h.src.size())) != cudaSuccess) return e;
+  return upload(&d.long_dst, h.long_dst.data(), h.long_dst.size());
+}
+
+void finish_map(GatherMapHost &m, const std::vector<int64_t> &count) {
+  const size_t nd = count.size();
+  m.ptr.assign(nd + 1, 0);
+  for (size_t d = 0; d < nd; ++d) m.ptr[d + 1] = m.ptr[d] + count[d];
+  m.src.assign((size_t)m.ptr[nd], 0);
+  m.long_dst.clear();
+  for (size_t d = 0; d < nd; ++d)
+    if (count[d] > kLongThreshold) m.long_dst.push_back((int32_t)d);
+}
+
+}  // namespace
+
+extern "C" {
+
+int xgpu_create(int device, xgpu_ctx **out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return 2;   // no CUDA device: no fallback by design
+  if (device < 0 || device >= ndev) return 3;
+  xgpu_ctx *ctx = new xgpu_ctx;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&ctx->stream) != cudaSuccess) {
+    delete ctx;
+    return 4;
+  }
+  ctx->own_stream = true;
+  *out = ctx;
+  return 0;
+}
+
+void xgpu_destroy(xgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &g : ctx->groups) {
+    cudaFree(g.d_inst_d); cudaFree(g.d_von); cudaFree(g.d_topo); cudaFree(g.d_model_idx);
+    cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig);
+  }
+  cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
+  for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); }
+  cudaFree(ctx->d_conv);
+  for (double *b : ctx->buf) cudaFree(b);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *xgpu_last_error(const xgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int xgpu_set_stream(xgpu_ctx *ctx, void *s) {
+  if (!ctx) return 1;
+  if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+  ctx->stream = (cudaStream_t)s;
+  return 0;
+}
+
+int xgpu_sync(xgpu_ctx *ctx) {
+  if (!ctx) return 1;
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int xgpu_pattern_set(xgpu_ctx *ctx, int n, const int32_t *rowptr, const int32_t *colind) {
+  if (!ctx || n < 0 || !rowptr) return 1;
+  if (ctx->finalized) return fail(ctx, 5, "pattern_set after finalize");
+  ctx->n = n;
+  ctx->rowptr.assign(rowptr, rowptr + n + 1);
+  ctx->nnz = rowptr[n];
+  ctx->colind.assign(colind, colind + ctx->nnz);
+  for (int r = 0; r < n; ++r)
+    for (int k = rowptr[r] + 1; k < rowptr[r + 1]; ++k)
+      if (colind[k] <= colind[k - 1]) return fail(ctx, 6, "CSR columns must be strictly increasing within a row");
+  return 0;
+}
+
+int xgpu_sizes_set(xgpu_ctx *ctx, int n_state, int n_store) {
+  if (!ctx || n_state < 0 || n_store < 0) return 1;
+  ctx->n_state = n_state;
+  ctx->n_store = n_store;
+  return 0;
+}
+
+int xgpu_b4_field_count(int which) {
+  switch (which) {
+    case 0: return kNumModelD;
+    case 1: return kNumModelI;
+    case 2: return kNumSizeD;
+    case 3: return kNumInstD;
+    case 4: return kNumInstI;
+  }
+  return -1;
+}
+
+const char *xgpu_b4_field_names(int which) {
+#define NM(n) #n "\n"
+  switch (which) {
+    case 0: return XB_B4_MODEL_D(NM);
+    case 1: return XB_B4_MODEL_I(NM);
+    case 2: return XB_B4_SIZE_D(NM);
+    case 3: return XB_B4_INST_D(NM);
+    case 4: return XB_B4_INST_I(NM);
+  }
+#undef NM
+  return "";
+}
+
+int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const int32_t *model_i, int n_sizes,
+                       const double *size_d) {
+  if (!ctx || n_models <= 0 || n_sizes <= 0 || !model_d || !model_i || !size_d) return 1;
+  XG_CUDA(cudaSetDevice(ctx->device));
+  std::vector<B4Model> M(n_models);
+  std::vector<B4Size> P(n_sizes);
+  for (int m = 0; m < n_models; ++m) {
+    int k = 0;
+#define GET(name) M[m].name = model_d[(size_t)m * kNumModelD + (k++)];
+    XB_B4_MODEL_D(GET)
+#undef GET
+    k = 0;
+#define GET(name) M[m].name = model_i[(size_t)m * kNumModelI + (k++)];
+    XB_B4_MODEL_I(GET)
+#undef GET
+  }
+  for (int s = 0; s < n_sizes; ++s) {
+    int k = 0;
+#define GET(name) P[s].name = size_d[(size_t)s * kNumSizeD + (k++)];
+    XB_B4_SIZE_D(GET)
+#undef GET
+  }
+  cudaFree(ctx->d_models); cudaFree(ctx->d_sizes);
+  ctx->d_models = nullptr; ctx->d_sizes = nullptr;
+  XG_CUDA(upload(&ctx->d_models, M.data(), M.size()));
+  XG_CUDA(upload(&ctx->d_sizes, P.data(), P.size()));
+  ctx->n_models = n_models;
+  ctx->n_sizes = n_sizes;
+  for (auto &g : ctx->groups) { g.dev.models = ctx->d_models; g.dev.sizes = ctx->d_sizes; }
+  return 0;
+}
+
+int xgpu_b4_group_add(xgpu_ctx *ctx, int n, const double *inst_d, const int32_t *inst_i, const int32_t *model_idx,
+                      const int32_t *size_idx, const int32_t *lids12, const int32_t *sto_lid0, int sto_stride,
+                      const int32_t *sta_lid0, int sta_stride) {
+  if (!ctx || n <= 0 || !inst_d || !inst_i || !model_idx || !size_idx || !lids12 || !sto_lid0 || !sta_lid0) return -1;
+  if (ctx->finalized) { fail(ctx, 5, "group_add after finalize"); return -5; }
+  if (!ctx->d_models) { fail(ctx, 7, "xgpu_b4_models_set must precede xgpu_b4_group_add"); return -7; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -4;
+  HostGroup g;
+  g.n = n;
+  // records -> structure of arrays; topology word; choose the kernel variant
+  std::vector<double> soa((size_t)kNumInstD * n);
+  std::vector<int> topo(n);
+  bool all_default = true;
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < kNumInstD; ++k) soa[(size_t)k * n + i] = inst_d[(size_t)i * kNumInstD + k];
+    B4Inst I{};
+    int k = 0;
+#define GET(name) I.name = inst_i[(size_t)i * kNumInstI + (k++)];
+    XB_B4_INST_I(GET)
+#undef GET
+    if (I.trnqsMod) { fail(ctx, 8, "trnqsMod = 1 is not supported (the reference marks it unimplemented)"); return -8; }
+    topo[i] = pack_topo(I);
+    if (topo[i] & kDefaultTopoMask) all_default = false;
+    if (model_idx[i] < 0 || model_idx[i] >= ctx->n_models || size_idx[i] < 0 || size_idx[i] >= ctx->n_sizes) {
+      fail(ctx, 9, "model/size index out of range");
+      return -9;
+    }
+  }
+  g.general = all_default ? 0 : 1;
+  const int nn = g.general ? kNumNodes : 4;
+  g.lids.assign((size_t)kNumNodes * n, -1);
+  for (int i = 0; i < n; ++i)
+    for (int t = 0; t < kNumNodes; ++t) {
+      const int l = lids12[(size_t)i * kNumNodes + t];
+      if (l >= ctx->n && ctx->n > 0) { fail(ctx, 10, "node LID outside the pattern"); return -10; }
+      g.lids[(size_t)t * n + i] = l;
+    }
+  std::vector<double> von(n, 0.0);
+  std::vector<int> orig(n, 1);
+  bool ok = upload(&g.d_inst_d, soa.data(), soa.size()) == cudaSuccess &&
+            upload(&g.d_topo, topo.data(), topo.size()) == cudaSuccess &&
+            upload(&g.d_model_idx, model_idx, (size_t)n) == cudaSuccess &&
+            upload(&g.d_size_idx, size_idx, (size_t)n) == cudaSuccess &&
+            upload(&g.d_lids, g.lids.data(), (size_t)nn * n) == cudaSuccess &&
+            upload(&g.d_sto0, sto_lid0, (size_t)n) == cudaSuccess &&
+            upload(&g.d_sta0, sta_lid0, (size_t)n) == cudaSuccess &&
+            upload(&g.d_von, von.data(), (size_t)n) == cudaSuccess &&
+            upload(&g.d_orig, orig.data(), (size_t)n) == cudaSuccess;
+  if (!ok) { fail(ctx, 11, "device allocation failed in group_add"); return -11; }
+  GroupDev &d = g.dev;
+  d.n = n; d.general = g.general; d.models = ctx->d_models; d.sizes = ctx->d_sizes;
+  d.inst_d = g.d_inst_d; d.topo = g.d_topo; d.model_idx = g.d_model_idx; d.size_idx = g.d_size_idx;
+  d.lids = g.d_lids; d.sto_lid0 = g.d_sto0; d.sta_lid0 = g.d_sta0; d.sto_stride = sto_stride;
+  d.sta_stride = sta_stride; d.von = g.d_von; d.orig_flag = g.d_orig;
+  ctx->groups.push_back(std::move(g));
+  return (int)ctx->groups.size() - 1;
+}
+
+int xgpu_finalize(xgpu_ctx *ctx) {
+  if (!ctx) return 1;
+  if (ctx->finalized) return 0;
+  if (ctx->rowptr.empty()) return fail(ctx, 12, "xgpu_pattern_set must precede xgpu_finalize");
+  XG_CUDA(cudaSetDevice(ctx->device));
+  // plane layout
+  int64_t vb = 0, mb = 0;
+  for (auto &g : ctx->groups) {
+    const int R = g.general ? kRowsGeneral : kRowsDefault, S = g.general ? kSlotsGeneral : kSlotsDefault;
+    g.dev.vec_base = vb; g.dev.mat_base = mb;
+    vb += (int64_t)R * g.n; mb += (int64_t)S * g.n;
+  }
+  if (vb >= (1LL << 31) || mb >= (1LL << 31)) return fail(ctx, 13, "contribution plane exceeds 2^31 elements");
+  ctx->vec_plane = vb; ctx->mat_plane = mb;
+  // gather maps: two passes (count, fill) in group-major, instance-minor, slot order
+  const int n = ctx->n;
+  GatherMapHost vm, mm;
+  std::vector<int64_t> vcount(n, 0), mcount((size_t)ctx->nnz, 0);
+  auto csr_find = [&](int r, int c) -> int64_t {
+    const int32_t *b = ctx->colind.data() + ctx->rowptr[r], *e = ctx->colind.data() + ctx->rowptr[r + 1];
+    const int32_t *p = std::lower_bound(b, e, c);
+    return (p != e && *p == c) ? (int64_t)(p - ctx->colind.data()) : -1;
+  };
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<int64_t> vfill, mfill;
+    if (pass == 1) {
+      finish_map(vm, vcount); finish_map(mm, mcount);
+      vfill.assign(vm.ptr.begin(), vm.ptr.end() - 1);
+      mfill.assign(mm.ptr.begin(), mm.ptr.end() - 1);
+    }
+    for (auto &g : ctx->groups) {
+      const int gn = g.n;
+      const int R = g.general ? kRowsGeneral : kRowsDefault, S = g.general ? kSlotsGeneral : kSlotsDefault;
+      for (int i = 0; i < gn; ++i) {
+        for (int r = 0; r < R; ++r) {
+          const int l = g.lids[(size_t)r * gn + i];   // default: rows 0..3 are D,G,S,B = nodes 0..3
+          if (l < 0) continue;
+          if (pass == 0) ++vcount[l];
+          else vm.src[(size_t)vfill[l]++] = (int32_t)(g.dev.vec_base + (int64_t)r * gn + i);
+        }
+        for (int s = 0; s < S; ++s) {
+          const int rn = g.general ? kSlotRow[s] : s / 4, cn = g.general ? kSlotCol[s] : s % 4;
+          const int lr = g.lids[(size_t)rn * gn + i], lc = g.lids[(size_t)cn * gn + i];
+          if (lr < 0 || lc < 0) continue;
+          const int64_t k = csr_find(lr, lc);
+          if (k < 0) return fail(ctx, 14, "a device stamp entry is missing from the CSR pattern");
+          if (pass == 0) ++mcount[(size_t)k];
+          else mm.src[(size_t)mfill[(size_t)k]++] = (int32_t)(g.dev.mat_base + (int64_t)s * gn + i);
+        }
+      }
+    }
+  }
+  XG_CUDA(upload_map(vm, ctx->vec_map));
+  XG_CUDA(upload_map(mm, ctx->mat_map));
+  XG_CUDA(cudaMalloc((void **)&ctx->d_vec_planes, std::max<int64_t>(4 * vb, 1) * sizeof(double)));
+  XG_CUDA(cudaMalloc((void **)&ctx->d_mat_planes, std::max<int64_t>(2 * mb, 1) * sizeof(double)));
+  XG_CUDA(cudaMemset(ctx->d_vec_planes, 0, std::max<int64_t>(4 * vb, 1) * sizeof(double)));
+  XG_CUDA(cudaMemset(ctx->d_mat_planes, 0, std::max<int64_t>(2 * mb, 1) * sizeof(double)));
+  XG_CUDA(cudaMalloc((void **)&ctx->d_conv, sizeof(int)));
+  // context-owned system buffers
+  const size_t sizes[11] = {(size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)ctx->nnz, (size_t)ctx->nnz,
+                            (size_t)ctx->n_store, (size_t)ctx->n_store, (size_t)ctx->n_state, (size_t)ctx->n_state};
+  for (int b = 0; b < 11; ++b) {
+    XG_CUDA(cudaMalloc((void **)&ctx->buf[b], std::max<size_t>(sizes[b], 1) * sizeof(double)));
+    XG_CUDA(cudaMemset(ctx->buf[b], 0, std::max<size_t>(sizes[b], 1) * sizeof(double)));
+  }
+  ctx->finalized = true;
+  return 0;
+}
+
+int xgpu_b4_von_set(xgpu_ctx *ctx, int group, const double *von) {
+  if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !von) return 1;
+  XG_CUDA(cudaMemcpyAsync(ctx->groups[group].d_von, von, ctx->groups[group].n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int xgpu_b4_von_get(xgpu_ctx *ctx, int group, double *von) {
+  if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !von) return 1;
+  XG_CUDA(cudaMemcpyAsync(von, ctx->groups[group].d_von, ctx->groups[group].n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, double *d_curr_sta, double *d_next_sto,
+                      double *d_curr_sto, const xgpu_solver_state *ss) {
+  if (!ctx || !ss || !d_sol) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  LoadArgs a{};
+  SolverFlags &S = a.S;
+  S.dcopFlag = ss->dcopFlag; S.tranopFlag = ss->tranopFlag; S.acopFlag = ss->acopFlag;
+  S.transientFlag = ss->transientFlag; S.dcsweepFlag = ss->dcsweepFlag; S.initJctFlag = ss->initJctFlag;
+  S.initFixFlag = ss->initFixFlag; S.initTranFlag = ss->initTranFlag; S.newtonIter = ss->newtonIter;
+  S.locaEnabledFlag = ss->locaEnabledFlag; S.artParameterFlag = ss->artParameterFlag;
+  S.voltageLimiterFlag = ss->voltageLimiterFlag; S.gmin = ss->gmin; S.gainScale = ss->gainScale;
+  S.nltermScale = ss->nltermScale; S.vgstConst = ss->vgstConst; S.vdsScaleMin = ss->vdsScaleMin;
+  S.sizeScale = ss->sizeScale; S.currTimeStep = ss->currTimeStep;
+  a.sol = d_sol; a.next_sta = d_next_sta; a.curr_sta = d_curr_sta; a.next_sto = d_next_sto; a.curr_sto = d_curr_sto;
+  for (int p = 0; p < 4; ++p) a.vec_planes[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
+  for (int p = 0; p < 2; ++p) a.mat_planes[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
+  for (auto &g : ctx->groups) { launch_b4_group(g.dev, a, ctx->stream); ++ctx->launches; }
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int xgpu_load_vectors(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_fl, double *d_ql, int accumulate) {
+  if (!ctx || !d_f || !d_q || !d_fl || !d_ql) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  const double *in[4]; double *out[4] = {d_f, d_q, d_fl, d_ql};
+  for (int p = 0; p < 4; ++p) in[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
+  launch_gather(ctx->vec_map, 4, in, ctx->vec_plane, out, accumulate != 0, ctx->stream);
+  ctx->launches += 1 + (ctx->vec_map.nlong > 0);
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int xgpu_load_matrices(xgpu_ctx *ctx, double *d_dFdx, double *d_dQdx, int accumulate) {
+  if (!ctx || !d_dFdx || !d_dQdx) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  const double *in[2]; double *out[2] = {d_dFdx, d_dQdx};
+  for (int p = 0; p < 2; ++p) in[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
+  launch_gather(ctx->mat_map, 2, in, ctx->mat_plane, out, accumulate != 0, ctx->stream);
+  ctx->launches += 1 + (ctx->mat_map.nlong > 0);
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int xgpu_jacobian_combine(xgpu_ctx *ctx, double qs, const double *d_dQdx, double fs, const double *d_dFdx, double *d_jac) {
+  if (!ctx || !d_dQdx || !d_dFdx || !d_jac) return 1;
+  launch_linear_combo(ctx->nnz, qs, d_dQdx, fs, d_dFdx, d_jac, ctx->stream);
+  ++ctx->launches;
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int xgpu_all_converged(xgpu_ctx *ctx, int *converged) {
+  if (!ctx || !converged) return 1;
+  // small: copy the flags back and AND them on the host (a fused reduction follows with the norms)
+  int all = 1;
+  for (auto &g : ctx->groups) {
+    std::vector<int> h(g.n);
+    XG_CUDA(cudaMemcpyAsync(h.data(), g.d_orig, g.n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int v : h) all &= (v != 0);
+  }
+  *converged = all;
+  return 0;
+}
+
+int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h) {
+  if (!ctx || which < 0 || which > 3 || !h || !ctx->finalized) return 1;
+  const size_t cnt = which < 2 ? ctx->n_store : ctx->n_state;
+  XG_CUDA(cudaMemcpyAsync(ctx->buf[7 + which], h, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int xgpu_state_get(xgpu_ctx *ctx, int which, double *h) {
+  if (!ctx || which < 0 || which > 3 || !h || !ctx->finalized) return 1;
+  const size_t cnt = which < 2 ? ctx->n_store : ctx->n_state;
+  XG_CUDA(cudaMemcpyAsync(h, ctx->buf[7 + which], cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+double *xgpu_device_buffer(xgpu_ctx *ctx, int which) {
+  if (!ctx || which < 0 || which > 10 || !ctx->finalized) return nullptr;
+  return ctx->buf[which];
+}
+
+int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double *h_f, double *h_q,
+                   double *h_fl, double *h_ql, double *h_dFdx, double *h_dQdx) {
+  if (!ctx || !h_sol || !ss) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  double **b = ctx->buf;
+  XG_CUDA(cudaMemcpyAsync(b[0], h_sol, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = xgpu_update_state(ctx, b[0], b[9], b[10], b[7], b[8], ss);
+  if (rc) return rc;
+  if ((rc = xgpu_load_vectors(ctx, b[1], b[2], b[3], b[4], 0))) return rc;
+  if ((rc = xgpu_load_matrices(ctx, b[5], b[6], 0))) return rc;
+  double *hv[4] = {h_f, h_q, h_fl, h_ql};
+  for (int p = 0; p < 4; ++p)
+    if (hv[p]) XG_CUDA(cudaMemcpyAsync(hv[p], b[1 + p], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_dFdx) XG_CUDA(cudaMemcpyAsync(h_dFdx, b[5], ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_dQdx) XG_CUDA(cudaMemcpyAsync(h_dQdx, b[6], ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+long long xgpu_launch_count(const xgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
