@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the Newton-step hot path (BASELINE.json metric: BSIM4 device load+stamp evaluations/s, fp64).
+
+Workload (config.workload): BASELINE config 2 -- 100 000-instance BSIM4 inverter array, one
+`updateState + loadDAEVectors + loadDAEMatrices` pass at a fixed operating point per step.
+  value : whole-job evaluations/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the host-buffer C-ABI call (H2D of x, D2H of F,Q,dFdxdVp,dQdxdVp,dFdx,dQdx)
+  --impl reference : the reference's own BSIM4 C++ (oracle/_ref, compiled from /root/reference)
+                     on all host cores, bounded sample of the same workload.
+Multi-GPU: instances are partitioned into independent arrays, one per rank (no data-path
+collective; weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bsim4_device_load_stamp_evals_per_sec"
+UNIT = "evals/s"
+BYTES_PER_EVAL = 1592.0      # SURVEY.md 8(d) unit U1 (algorithmic bytes per instance evaluation)
+FLOPS_PER_EVAL = 3000.0      # SURVEY.md 8(d) provisional executed flops per evaluation
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def cpu_reference_rate(n_inverters, budget_s):
+    """Time the reference's BSIM4 C++ (oracle/_ref) on one core over a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ref
+    from xyce_b200 import workloads as wl
+    c = oracle_ref.RefCircuit(2 * n_inverters + 1)
+    c.add_model("nch", "NMOS", wl.NMOS_CARD)
+    c.add_model("pch", "PMOS", wl.PMOS_CARD)
+    vdd = 2 * n_inverters
+    for j in range(n_inverters):
+        c.add_instance("M:n%d" % j, "nch", [2 * j + 1, 2 * j, -1, -1], wl.NMOS_INST)
+    for j in range(n_inverters):
+        c.add_instance("M:p%d" % j, "pch", [2 * j + 1, 2 * j, vdd, vdd], wl.PMOS_INST)
+    c.finalize()
+    c.set_flags(transient=1, newtonIter=1)
+    rng = np.random.default_rng(12345)
+    x = rng.uniform(0, 1, c.n)
+    x[vdd] = 1.0
+    c.load(x)                     # warm-up, also leaves a consistent store vector
+    st = c.get_state()
+    c.set_state(curr_sto=st["next_sto"], next_sto=st["next_sto"])
+    t0 = time.perf_counter()
+    c.load_repeat(x, 2)
+    per = (time.perf_counter() - t0) / 2
+    reps = max(1, int(budget_s / max(per, 1e-6)))
+    t0 = time.perf_counter()
+    c.load_repeat(x, reps)
+    dt = time.perf_counter() - t0
+    return 2 * n_inverters * reps / dt, reps
+
+
+def _ref_worker(args):
+    n_inv, budget = args
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 2)
+    t0 = time.perf_counter()
+    rate, reps = cpu_reference_rate(n_inv, budget)
+    return 2 * n_inv * reps, 2 * n_inv * reps / rate, time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference BSIM4 code on all host cores (instance-partitioned, like Xyce's MPI 'parallel load')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    sample_inv = 1000                       # 2000 instances per core
+    budget = min(20.0, max(2.0, 0.5 * args.steps))   # seconds of timed evaluation per core for the whole run
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(sample_inv, budget)] * cores)
+    evals = sum(r[0] for r in res)
+    t = max(r[1] for r in res)
+    value = evals / t
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "100k-instance BSIM4 inverter array (BASELINE config 2), bounded sample",
+                       "instances_per_core": 2 * sample_inv},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "%d BSIM4 instances per core x %d cores, %.0f s budget, oracle/_ref "
+                                       "(reference N_DEV_MOSFET_B4*.C compiled in place)" % (2 * sample_inv, cores, budget)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    from xyce_b200 import workloads as wl
+    from xyce_b200.capi import SolverState
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = wl.inverter_array(args.inverters, seed=12345 + rank)
+    eng = wl.build_engine(w, device=local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    n, nnz, n_inst = w["n_unknowns"], eng.nnz, w["n_inst"]
+    dev = torch.device("cuda", local)
+    f64 = dict(dtype=torch.float64, device=dev)
+    d_x = torch.tensor(w["x"], **f64)
+    d_vec = [torch.zeros(n, **f64) for _ in range(4)]
+    d_mat = [torch.zeros(nnz, **f64) for _ in range(2)]
+    d_sto = [torch.tensor(w["store"], **f64) for _ in range(2)]
+    d_sta = [torch.zeros(w["n_state"], **f64) for _ in range(2)]
+    ss = SolverState(transientFlag=1, newtonIter=1)
+    flush = torch.empty(256 * 1024 * 1024 // 8, **f64)      # 256 MiB > 126 MB L2
+
+    def step():
+        eng.update_state(d_x.data_ptr(), d_sta[0].data_ptr(), d_sta[1].data_ptr(), d_sto[0].data_ptr(),
+                         d_sto[1].data_ptr(), ss)
+
+    def assemble():
+        eng.load_vectors(*[t.data_ptr() for t in d_vec], accumulate=False)
+        eng.load_matrices(d_mat[0].data_ptr(), d_mat[1].data_ptr(), accumulate=False)
+
+    for _ in range(max(args.warmup, 3)):
+        step(); assemble()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(0.0)                   # evict L2 between timed iterations (not timed)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+        assemble()
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if dist:
+        dist.barrier()
+    launches = (eng.launch_count() - l0) / args.steps
+    ms_eval = sum(e[0].elapsed_time(e[1]) for e in ev)
+    ms_total = sum(e[0].elapsed_time(e[2]) for e in ev)
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory) ----
+    h_x = torch.tensor(w["x"], dtype=torch.float64).pin_memory()
+    eng.set_state(0, w["store"]); eng.set_state(1, w["store"])
+    import ctypes as C
+    houts = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(4)] + \
+            [torch.zeros(nnz, dtype=torch.float64).pin_memory() for _ in range(2)]
+    ptr = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    def e2e_step():
+        rc = eng.lib.xgpu_load_host(eng.h, ptr(h_x), C.byref(ss), *[ptr(t) for t in houts])
+        assert rc == 0
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()                          # synchronises internally (results are on the host)
+    t_e2e = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    times = torch.tensor([ms_total, ms_eval, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_eval, ms_e2e = times.tolist()
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    total_evals = world * n_inst * args.steps
+    value = total_evals / (ms_total * 1e-3)
+    e2e_value = world * n_inst * e2e_steps / (ms_e2e * 1e-3)
+    peak, peak_kind = measured_peaks()
+    eval_s = ms_eval * 1e-3 / args.steps
+    achieved = BYTES_PER_EVAL * n_inst / eval_s / 1e9
+    fp64_peak = eng.measure_fp64_peak()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "100k-instance BSIM4 (level 54, v4.8.2) inverter array, updateState+loadDAEVectors+"
+                                   "loadDAEMatrices at a fixed operating point (BASELINE config 2)",
+                       "instances_per_gpu": n_inst, "unknowns_per_gpu": n, "nnz_per_gpu": nnz,
+                       "parallelism": "instances partitioned per rank, no data-path collective",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
+                    "d2h_bytes_per_step": 8 * (4 * n + 2 * nnz)},
+            "gpu_launches": launches, "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_kind, "kernel": "b4_eval_kernel<false>",
+                         "kernel_ms": 1e3 * eval_s,
+                         "fp64": {"achieved_tflops": FLOPS_PER_EVAL * n_inst / eval_s / 1e12,
+                                  "measured_peak_tflops": fp64_peak,
+                                  "frac": FLOPS_PER_EVAL * n_inst / eval_s / 1e12 / fp64_peak}},
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, reps = cpu_reference_rate(2000, 12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": "4000 BSIM4 instances x %d passes (~12 s), oracle/_ref = the reference's "
+                                              "N_DEV_MOSFET_B4*.C compiled in place, same cards/operating points" % reps}
+        except Exception as exc:   # the oracle library did not travel: report, do not fake
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--inverters", type=int, default=50000, help="inverters per GPU (2 BSIM4 instances each)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,13 @@ int xgpu_sync(xgpu_ctx *ctx);
  * SerialLSUtil::generateRowColData (src/TopoManagerPKG/N_TOP_SerialLSUtil.C:620-703), ground
  * rows/columns stripped, columns sorted within a row. */
 int xgpu_pattern_set(xgpu_ctx *ctx, int n_unknowns, const int32_t *rowptr, const int32_t *colind);
+/* Alternative to xgpu_pattern_set for callers without a Topology package: after all device
+ * groups are added, derive the pattern from their Jacobian stamps exactly as
+ * generateRowColData does (union of stamp entries, sorted unique columns per row, ground
+ * stripped).  xgpu_pattern_get copies it out (rowptr: n+1, colind: nnz entries). */
+int xgpu_pattern_build(xgpu_ctx *ctx, int n_unknowns);
+int xgpu_pattern_nnz(const xgpu_ctx *ctx);
+int xgpu_pattern_get(const xgpu_ctx *ctx, int32_t *rowptr, int32_t *colind);
 /* Lengths of the state and store vectors (TimeIntg::DataStore, N_TIA_DataStore.h:145-300). */
 int xgpu_sizes_set(xgpu_ctx *ctx, int n_state, int n_store);
 
@@ -103,6 +110,10 @@ int xgpu_state_get(xgpu_ctx *ctx, int which, double *h_vals);
 /* Device pointers of the context-owned buffers used by xgpu_load_host:
  * 0 sol, 1 f, 2 q, 3 dFdxdVp, 4 dQdxdVp, 5 dFdx, 6 dQdx, 7 next sto, 8 curr sto, 9 next sta, 10 curr sta */
 double *xgpu_device_buffer(xgpu_ctx *ctx, int which);
+
+/* Measured FP64 FMA throughput of this GPU (dependent-chain DFMA microbenchmark, TFLOP/s with
+ * FMA = 2 flops): the denominator for FP64-pipe roofline fractions. */
+int xgpu_measure_fp64_peak(xgpu_ctx *ctx, double *tflops);
 
 /* Kernel launches issued by this context since creation (bench bookkeeping). */
 long long xgpu_launch_count(const xgpu_ctx *ctx);

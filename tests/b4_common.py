@@ -5,17 +5,11 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+import sys
+sys.path.insert(0, os.path.join(HERE, ".."))
 HOST_SO = os.path.join(HERE, "host_mirror", "libxb_host.so")
 
-# 45 nm-like level-54 cards.  Only parameters that differ from BSIM4 defaults are listed.
-NMOS_CARD = dict(TOXE=1.8e-9, TOXP=1.5e-9, TOXM=1.8e-9, VTH0=0.42, K1=0.45, K2=0.01, U0=0.045, VSAT=1.2e5,
-                 NDEP=2.5e18, XJ=1.4e-8, RDSW=150.0, CGSO=1.1e-10, CGDO=1.1e-10, CJS=1.0e-3, CJSWS=2.0e-10,
-                 CJSWGS=3.0e-10, PBS=0.9, PBSWS=0.9, PBSWGS=0.9, MJS=0.45, JSS=1.0e-4, JSWS=1.0e-11,
-                 ETA0=0.06, DSUB=0.1, PCLM=0.6, NFACTOR=1.8, VOFF=-0.12, CAPMOD=2, MOBMOD=0)
-PMOS_CARD = dict(TOXE=1.9e-9, TOXP=1.6e-9, TOXM=1.9e-9, VTH0=-0.40, K1=0.40, K2=-0.01, U0=0.012, VSAT=9.0e4,
-                 NDEP=2.0e18, XJ=1.4e-8, RDSW=200.0, CGSO=1.0e-10, CGDO=1.0e-10, CJS=1.1e-3, CJSWS=2.2e-10,
-                 CJSWGS=3.2e-10, PBS=0.9, PBSWS=0.9, PBSWGS=0.9, MJS=0.45, JSS=1.0e-4, JSWS=1.0e-11,
-                 ETA0=0.05, DSUB=0.1, PCLM=0.7, NFACTOR=1.6, VOFF=-0.10, CAPMOD=2, MOBMOD=0)
+from xyce_b200.workloads import NMOS_CARD, PMOS_CARD  # noqa: E402  (benchmark cards are the base cards)
 
 # model-card variants that switch on otherwise-dormant code paths
 VARIANTS = {

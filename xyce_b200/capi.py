@@ -102,6 +102,19 @@ class Engine:
         self.n, self.nnz = len(rowptr) - 1, len(colind)
         self._chk(self.lib.xgpu_pattern_set(self.h, self.n, _ip(rowptr), _ip(colind)))
 
+    def build_pattern(self, n_unknowns):
+        """Derive the CSR pattern from the device stamps (call after the groups were added)."""
+        self._chk(self.lib.xgpu_pattern_build(self.h, int(n_unknowns)))
+        self.n, self.nnz = int(n_unknowns), int(self.lib.xgpu_pattern_nnz(self.h))
+        rowptr, colind = np.zeros(self.n + 1, dtype=np.int32), np.zeros(self.nnz, dtype=np.int32)
+        self._chk(self.lib.xgpu_pattern_get(self.h, _ip(rowptr), _ip(colind)))
+        return rowptr, colind
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._chk(self.lib.xgpu_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
     def set_sizes(self, n_state, n_store):
         self.n_state, self.n_store = int(n_state), int(n_store)
         self._chk(self.lib.xgpu_sizes_set(self.h, self.n_state, self.n_store))

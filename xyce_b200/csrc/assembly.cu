@@ -67,6 +67,15 @@ __global__ void __launch_bounds__(256) linear_combo_kernel(int64_t nnz, double a
   if (k < nnz) J[k] = a * A[k] + b * B[k];
 }
 
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 template <int NP>
 void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
   if (m.ndst > 0) gather_short_kernel<NP><<<(m.ndst + 255) / 256, 256, 0, stream>>>(m, ps, accumulate);
@@ -85,6 +94,33 @@ void launch_gather(const GatherMapDev &m, int nplanes, const double *const *plan
     case 4: launch_np<4>(m, ps, accumulate, stream); break;
     default: break;
   }
+}
+
+cudaError_t measure_fp64_peak(cudaStream_t stream, double *tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double *out = nullptr;
+  cudaError_t e = cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(double));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, stream);
+    fp64_peak_kernel<<<blocks, threads, 0, stream>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(b, stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  e = cudaGetLastError();
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(out);
+  *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+  return e;
 }
 
 void launch_linear_combo(int64_t nnz, double a, const double *A, double b, const double *B, double *J,

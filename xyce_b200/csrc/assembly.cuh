@@ -44,4 +44,7 @@ void launch_gather(const GatherMapDev &m, int nplanes, const double *const *plan
 void launch_linear_combo(int64_t nnz, double a, const double *A, double b, const double *B, double *J,
                          cudaStream_t stream);
 
+// Dependent-chain DFMA microbenchmark (8 independent chains per thread); returns TFLOP/s.
+cudaError_t measure_fp64_peak(cudaStream_t stream, double *tflops);
+
 }  // namespace xb

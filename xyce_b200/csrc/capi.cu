@@ -167,6 +167,48 @@ int xgpu_pattern_set(xgpu_ctx *ctx, int n, const int32_t *rowptr, const int32_t 
   return 0;
 }
 
+int xgpu_pattern_build(xgpu_ctx *ctx, int n) {
+  if (!ctx || n <= 0) return 1;
+  if (ctx->finalized) return fail(ctx, 5, "pattern_build after finalize");
+  // (row, col) pairs of every stamp entry; sort + unique = generateRowColData
+  std::vector<uint64_t> pairs;
+  for (auto &g : ctx->groups) {
+    const int gn = g.n;
+    const int S = g.general ? kSlotsGeneral : kSlotsDefault;
+    pairs.reserve(pairs.size() + (size_t)S * gn);
+    for (int s = 0; s < S; ++s) {
+      const int rn = g.general ? kSlotRow[s] : s / 4, cn = g.general ? kSlotCol[s] : s % 4;
+      const int32_t *lr = &g.lids[(size_t)rn * gn], *lc = &g.lids[(size_t)cn * gn];
+      for (int i = 0; i < gn; ++i) {
+        if (lr[i] < 0 || lc[i] < 0) continue;
+        if (lr[i] >= n || lc[i] >= n) return fail(ctx, 10, "node LID outside the pattern");
+        pairs.push_back(((uint64_t)(uint32_t)lr[i] << 32) | (uint32_t)lc[i]);
+      }
+    }
+  }
+  std::sort(pairs.begin(), pairs.end());
+  pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+  ctx->n = n;
+  ctx->nnz = (int64_t)pairs.size();
+  ctx->rowptr.assign(n + 1, 0);
+  ctx->colind.resize(pairs.size());
+  for (size_t k = 0; k < pairs.size(); ++k) {
+    ++ctx->rowptr[(pairs[k] >> 32) + 1];
+    ctx->colind[k] = (int32_t)(pairs[k] & 0xffffffffu);
+  }
+  for (int r = 0; r < n; ++r) ctx->rowptr[r + 1] += ctx->rowptr[r];
+  return 0;
+}
+
+int xgpu_pattern_nnz(const xgpu_ctx *ctx) { return ctx ? (int)ctx->nnz : -1; }
+
+int xgpu_pattern_get(const xgpu_ctx *ctx, int32_t *rowptr, int32_t *colind) {
+  if (!ctx || !rowptr || !colind || ctx->rowptr.empty()) return 1;
+  std::copy(ctx->rowptr.begin(), ctx->rowptr.end(), rowptr);
+  std::copy(ctx->colind.begin(), ctx->colind.end(), colind);
+  return 0;
+}
+
 int xgpu_sizes_set(xgpu_ctx *ctx, int n_state, int n_store) {
   if (!ctx || n_state < 0 || n_store < 0) return 1;
   ctx->n_state = n_state;
@@ -264,7 +306,7 @@ int xgpu_b4_group_add(xgpu_ctx *ctx, int n, const double *inst_d, const int32_t 
   for (int i = 0; i < n; ++i)
     for (int t = 0; t < kNumNodes; ++t) {
       const int l = lids12[(size_t)i * kNumNodes + t];
-      if (l >= ctx->n && ctx->n > 0) { fail(ctx, 10, "node LID outside the pattern"); return -10; }
+      if (l >= ctx->n && ctx->n > 0 && !ctx->rowptr.empty()) { fail(ctx, 10, "node LID outside the pattern"); return -10; }
       g.lids[(size_t)t * n + i] = l;
     }
   std::vector<double> von(n, 0.0);
@@ -472,6 +514,16 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
   if (h_dFdx) XG_CUDA(cudaMemcpyAsync(h_dFdx, b[5], ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (h_dQdx) XG_CUDA(cudaMemcpyAsync(h_dQdx, b[6], ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int xgpu_measure_fp64_peak(xgpu_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return 1;
+  XG_CUDA(cudaSetDevice(ctx->device));
+  double t = 0.0;
+  cudaError_t e = xb::measure_fp64_peak(ctx->stream, &t);
+  if (e != cudaSuccess) return fail(ctx, 100 + (int)e, cudaGetErrorString(e));
+  *tflops = t;
   return 0;
 }
 
