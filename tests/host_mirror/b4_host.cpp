@@ -3,6 +3,10 @@
 // oracle (oracle/_ref) without a GPU.  Never loaded by the product; the product path is
 // the CUDA library and fails loudly when that is missing.
 #include <cstring>
+#ifdef XB_COUNT_OPS
+#include "../../xyce_b200/csrc/xb_real.h"
+#define XB_REAL xb::CountReal
+#endif
 #include "../../xyce_b200/csrc/bsim4_instance.h"
 
 using namespace xb;
@@ -11,12 +15,12 @@ using namespace xb::b4;
 namespace {
 struct GeneralEmitter {
   double F[kNumRows], Q[kNumRows], FL[kNumRows], QL[kNumRows], JF[kNumSlots], JQ[kNumSlots];
-  template <int R> void f(double v) { F[R] += v; }
-  template <int R> void q(double v) { Q[R] += v; }
-  template <int R> void fl(double v) { FL[R] += v; }
-  template <int R> void ql(double v) { QL[R] += v; }
-  template <int S> void jf(double v) { JF[S] += v; }
-  template <int S> void jq(double v) { JQ[S] += v; }
+  template <int R> void f(real v) { F[R] += to_double(v); }
+  template <int R> void q(real v) { Q[R] += to_double(v); }
+  template <int R> void fl(real v) { FL[R] += to_double(v); }
+  template <int R> void ql(real v) { QL[R] += to_double(v); }
+  template <int S> void jf(real v) { JF[S] += to_double(v); }
+  template <int S> void jq(real v) { JQ[S] += to_double(v); }
 };
 }  // namespace
 
@@ -63,14 +67,20 @@ int xbh_b4_eval(const double *model_d, const int *model_i, const double *size_d,
   std::memset(&W, 0, sizeof(W));
   GeneralEmitter e;
   std::memset(&e, 0, sizeof(e));
-  evaluate(S, M, P, I, V12, sto_old13, have_old != 0, von_prev, W, e);
+  real Vr[kNumNodes], so[13];
+  for (int t = 0; t < kNumNodes; ++t) Vr[t] = V12[t];
+  for (int t = 0; t < 13; ++t) so[t] = sto_old13[t];
+#ifdef XB_COUNT_OPS
+  xb::op_counts() = xb::OpCounts{};
+#endif
+  evaluate(S, M, P, I, Vr, so, have_old != 0, real(von_prev), W, e);
   std::memcpy(F, e.F, sizeof(e.F)); std::memcpy(Q, e.Q, sizeof(e.Q));
   std::memcpy(FL, e.FL, sizeof(e.FL)); std::memcpy(QL, e.QL, sizeof(e.QL));
   std::memcpy(JF, e.JF, sizeof(e.JF)); std::memcpy(JQ, e.JQ, sizeof(e.JQ));
-  for_each_store(W, [&](int s, double v) { store22[s] = v; });
-  state3[sa_qb] = W.qb; state3[sa_qg] = W.qg; state3[sa_qd] = W.qd;
+  for_each_store(W, [&](int s, real v) { store22[s] = to_double(v); });
+  state3[sa_qb] = to_double(W.qb); state3[sa_qg] = to_double(W.qg); state3[sa_qd] = to_double(W.qd);
   k = 0;
-#define PUT(n) mid_d[k++] = W.n;
+#define PUT(n) mid_d[k++] = to_double(W.n);
   XB_B4_MID_D(PUT) XB_B4_MID_EXTRA_D(PUT)
 #undef PUT
   k = 0;
@@ -78,6 +88,16 @@ int xbh_b4_eval(const double *model_d, const int *model_i, const double *size_d,
   XB_B4_MID_I(PUT)
 #undef PUT
   return 0;
+}
+
+// executed-operation counters of the last xbh_b4_eval call: add, mul, div, sqrt, exp, log, cmp
+void xbh_op_counts(unsigned long long *out) {
+#ifdef XB_COUNT_OPS
+  const xb::OpCounts &c = xb::op_counts();
+  out[0] = c.add; out[1] = c.mul; out[2] = c.div; out[3] = c.sqrt_; out[4] = c.exp_; out[5] = c.log_; out[6] = c.cmp;
+#else
+  for (int i = 0; i < 7; ++i) out[i] = 0;
+#endif
 }
 
 void xbh_b4_slot_tables(int *row, int *col) {

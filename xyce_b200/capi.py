@@ -94,6 +94,9 @@ class Engine:
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.xgpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, name, value):
+        self._chk(self.lib.xgpu_set_option(self.h, name.encode(), int(value)))
+
     def sync(self):
         self._chk(self.lib.xgpu_sync(self.h))
 

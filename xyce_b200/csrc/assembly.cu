@@ -29,13 +29,17 @@ __global__ void __launch_bounds__(256) gather_short_kernel(GatherMapDev m, Plane
   for (int p = 0; p < NP; ++p) ps.out[p][d] = acc[p];
 }
 
-// One block per long destination; fixed-shape reduction: each thread sums a strided
-// subsequence in index order, then a shared-memory tree combines the 256 partials.
+// Long destinations (supply rails): stage 1, one block per chunk of kChunk sources -- every thread
+// sums its strided subsequence in index order, then a fixed-shape shared-memory tree combines the
+// 256 partials; stage 2, one thread per long destination adds its chunk partials in chunk order.
+// Fixed shapes and orders => bitwise reproducible, no atomics.
 template <int NP>
-__global__ void __launch_bounds__(256) gather_long_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
+__global__ void __launch_bounds__(256) gather_chunk_kernel(GatherMapDev m, PlaneSet ps) {
   __shared__ double sh[NP][256];
-  const int d = m.long_dst[blockIdx.x];
-  const int64_t b = m.ptr[d], e = m.ptr[d + 1];
+  const int c = blockIdx.x;
+  const int d = m.long_dst[m.chunk_dst_slot[c]];
+  const int64_t b = m.chunk_begin[c];
+  const int64_t e = min(b + (int64_t)kChunk, m.ptr[d + 1]);
   double acc[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) acc[p] = 0.0;
@@ -54,9 +58,19 @@ __global__ void __launch_bounds__(256) gather_long_kernel(GatherMapDev m, PlaneS
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < NP) m.partials[(size_t)threadIdx.x * m.nchunks + c] = sh[threadIdx.x][0];
+}
+
+template <int NP>
+__global__ void __launch_bounds__(128) gather_long_finish_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m.nlong) return;
+  const int d = m.long_dst[j];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) ps.out[p][d] = (accumulate ? ps.out[p][d] : 0.0) + sh[p][0];
+  for (int p = 0; p < NP; ++p) {
+    double acc = accumulate ? ps.out[p][d] : 0.0;
+    for (int c = m.long_chunk_ptr[j]; c < m.long_chunk_ptr[j + 1]; ++c) acc += m.partials[(size_t)p * m.nchunks + c];
+    ps.out[p][d] = acc;
   }
 }
 
@@ -79,7 +93,10 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 template <int NP>
 void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
   if (m.ndst > 0) gather_short_kernel<NP><<<(m.ndst + 255) / 256, 256, 0, stream>>>(m, ps, accumulate);
-  if (m.nlong > 0) gather_long_kernel<NP><<<m.nlong, 256, 0, stream>>>(m, ps, accumulate);
+  if (m.nlong > 0) {
+    gather_chunk_kernel<NP><<<m.nchunks, 256, 0, stream>>>(m, ps);
+    gather_long_finish_kernel<NP><<<(m.nlong + 127) / 128, 128, 0, stream>>>(m, ps, accumulate);
+  }
 }
 
 }  // namespace

@@ -26,13 +26,22 @@ struct GatherMapHost {
 struct GatherMapDev {
   int ndst = 0;
   int nlong = 0;
+  int nchunks = 0;          // total chunks over all long destinations
   int64_t total = 0;
   int64_t *ptr = nullptr;
   int32_t *src = nullptr;
   int32_t *long_dst = nullptr;
+  // long destinations are cut into chunks of kChunk sources: chunk c covers src[chunk_begin[c] ..
+  // chunk_begin[c]+kChunk) clipped to its destination's end; destination j owns chunks
+  // [long_chunk_ptr[j], long_chunk_ptr[j+1]).
+  int64_t *chunk_begin = nullptr;
+  int32_t *chunk_dst_slot = nullptr;   // index into long_dst
+  int32_t *long_chunk_ptr = nullptr;   // [nlong+1]
+  double *partials = nullptr;          // [4][nchunks]
 };
 
 constexpr int kLongThreshold = 96;
+constexpr int kChunk = 1024;
 
 // Sum `nplanes` planes through one map.  dst[p][d] = (accumulate ? dst[p][d] : 0) + sum_k plane[p][src[k]].
 // Long destinations are skipped by the short kernel and handled by the block kernel.

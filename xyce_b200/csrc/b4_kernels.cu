@@ -9,7 +9,20 @@
 // read exactly once), model / bin records are shared by whole warps (instances are sorted
 // by bin, so these loads broadcast out of L1/L2), node voltages come through the gather map.
 // The kernel is FP64-pipe bound; see DESIGN.md for the per-instance byte and flop budget.
+// Compiled three times (see Makefile) with XB_ARITH =
+//   0 "exact": plain double, -fmad=false  -> every multiply/add rounded separately (parity build)
+//   1 "fma"  : plain double, -fmad=true   -> FMA contraction
+//   2 "fast" : FastReal (branch-free reciprocal division), -fmad=true
+#ifndef XB_ARITH
+#define XB_ARITH 0
+#endif
+#if XB_ARITH == 2
+#include "xb_real.h"
+#define XB_REAL xb::FastReal
+#endif
 #include "b4_kernels.cuh"
+#define XB_CAT2(a, b) a##b
+#define XB_CAT(a, b) XB_CAT2(a, b)
 
 namespace xb {
 namespace b4 {
@@ -29,17 +42,17 @@ struct PlaneEmitter<false> {
 #pragma unroll
     for (int i = 0; i < 16; ++i) JF[i] = JQ[i] = 0.0;
   }
-  template <int R> __device__ __forceinline__ void f(double v) { constexpr int k = default_collapse(R); F[k] += v; }
-  template <int R> __device__ __forceinline__ void q(double v) { constexpr int k = default_collapse(R); Q[k] += v; }
-  template <int R> __device__ __forceinline__ void fl(double v) { constexpr int k = default_collapse(R); FL[k] += v; }
-  template <int R> __device__ __forceinline__ void ql(double v) { constexpr int k = default_collapse(R); QL[k] += v; }
-  template <int S> __device__ __forceinline__ void jf(double v) {
+  template <int R> __device__ __forceinline__ void f(real v) { constexpr int k = default_collapse(R); F[k] += to_double(v); }
+  template <int R> __device__ __forceinline__ void q(real v) { constexpr int k = default_collapse(R); Q[k] += to_double(v); }
+  template <int R> __device__ __forceinline__ void fl(real v) { constexpr int k = default_collapse(R); FL[k] += to_double(v); }
+  template <int R> __device__ __forceinline__ void ql(real v) { constexpr int k = default_collapse(R); QL[k] += to_double(v); }
+  template <int S> __device__ __forceinline__ void jf(real v) {
     constexpr int k = 4 * default_collapse(slot_row(S)) + default_collapse(slot_col(S));
-    JF[k] += v;
+    JF[k] += to_double(v);
   }
-  template <int S> __device__ __forceinline__ void jq(double v) {
+  template <int S> __device__ __forceinline__ void jq(real v) {
     constexpr int k = 4 * default_collapse(slot_row(S)) + default_collapse(slot_col(S));
-    JQ[k] += v;
+    JQ[k] += to_double(v);
   }
 };
 
@@ -52,20 +65,20 @@ struct PlaneEmitter<true> {
 #pragma unroll
     for (int i = 0; i < kNumSlots; ++i) JF[i] = JQ[i] = 0.0;
   }
-  template <int R> __device__ __forceinline__ void f(double v) { F[R] += v; }
-  template <int R> __device__ __forceinline__ void q(double v) { Q[R] += v; }
-  template <int R> __device__ __forceinline__ void fl(double v) { FL[R] += v; }
-  template <int R> __device__ __forceinline__ void ql(double v) { QL[R] += v; }
-  template <int S> __device__ __forceinline__ void jf(double v) { JF[S] += v; }
-  template <int S> __device__ __forceinline__ void jq(double v) { JQ[S] += v; }
+  template <int R> __device__ __forceinline__ void f(real v) { F[R] += to_double(v); }
+  template <int R> __device__ __forceinline__ void q(real v) { Q[R] += to_double(v); }
+  template <int R> __device__ __forceinline__ void fl(real v) { FL[R] += to_double(v); }
+  template <int R> __device__ __forceinline__ void ql(real v) { QL[R] += to_double(v); }
+  template <int S> __device__ __forceinline__ void jf(real v) { JF[S] += to_double(v); }
+  template <int S> __device__ __forceinline__ void jq(real v) { JQ[S] += to_double(v); }
 };
 
 __device__ __forceinline__ double gather(const double *__restrict__ x, int lid) {
   return lid >= 0 ? __ldg(x + lid) : 0.0;
 }
 
-template <bool GENERAL>
-__global__ void __launch_bounds__(128) b4_eval_kernel(GroupDev g, LoadArgs a) {
+template <bool GENERAL, int MINBLOCKS>
+__global__ void __launch_bounds__(128, MINBLOCKS) b4_eval_kernel(GroupDev g, LoadArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const int n = g.n;
@@ -89,7 +102,7 @@ __global__ void __launch_bounds__(128) b4_eval_kernel(GroupDev g, LoadArgs a) {
   const B4Size &P = g.sizes[__ldg(g.size_idx + i)];
 
   // ---- node voltages through the gather map ----
-  double V[kNumNodes];
+  real V[kNumNodes];
   if (GENERAL) {
 #pragma unroll
     for (int t = 0; t < kNumNodes; ++t) V[t] = gather(a.sol, __ldg(g.lids + (size_t)t * n + i));
@@ -106,7 +119,7 @@ __global__ void __launch_bounds__(128) b4_eval_kernel(GroupDev g, LoadArgs a) {
   const int src = old_source(a.S);
   const int sto0 = __ldg(g.sto_lid0 + i);
   const int ss = g.sto_stride;
-  double sto_old[13];
+  real sto_old[13];
   if (src != kOldNone) {
     const double *sv = (src == kOldCurr) ? a.curr_sto : a.next_sto;
     if (GENERAL) {
@@ -126,35 +139,35 @@ __global__ void __launch_bounds__(128) b4_eval_kernel(GroupDev g, LoadArgs a) {
   evaluate(a.S, M, P, I, V, sto_old, src != kOldNone, g.von[i], W, e);
 
   // ---- carried state, store and state vectors ----
-  g.von[i] = W.von;
+  g.von[i] = to_double(W.von);
   g.orig_flag[i] = W.origFlag;
   {
     double *ns = a.next_sto;
-    for_each_store(W, [&](int s, double v) { ns[sto0 + (size_t)s * ss] = v; });
+    for_each_store(W, [&](int s, real v) { ns[sto0 + (size_t)s * ss] = to_double(v); });
   }
   {
     const int sta0 = __ldg(g.sta_lid0 + i);
     const int as = g.sta_stride;
     double *st = a.next_sta;
-    st[sta0 + (size_t)sa_qb * as] = W.qb;
-    st[sta0 + (size_t)sa_qg * as] = W.qg;
-    st[sta0 + (size_t)sa_qd * as] = W.qd;
+    st[sta0 + (size_t)sa_qb * as] = to_double(W.qb);
+    st[sta0 + (size_t)sa_qg * as] = to_double(W.qg);
+    st[sta0 + (size_t)sa_qd * as] = to_double(W.qd);
     if (GENERAL) {
       int k = 3;
-      if (I.rgateMod == 3) st[sta0 + (size_t)(k++) * as] = W.qgmid;
-      if (I.rbodyMod) { st[sta0 + (size_t)(k++) * as] = W.qbs; st[sta0 + (size_t)(k++) * as] = W.qbd; }
+      if (I.rgateMod == 3) st[sta0 + (size_t)(k++) * as] = to_double(W.qgmid);
+      if (I.rbodyMod) { st[sta0 + (size_t)(k++) * as] = to_double(W.qbs); st[sta0 + (size_t)(k++) * as] = to_double(W.qbd); }
     }
     // first Newton step of the first transient step: charges also go to the current state
     // (N_DEV_MOSFET_B4.C:10629-10664)
     if (!a.S.dcopFlag && a.S.initTranFlag && a.S.newtonIter == 0) {
       double *cs = a.curr_sta;
-      cs[sta0 + (size_t)sa_qb * as] = W.qb;
-      cs[sta0 + (size_t)sa_qg * as] = W.qg;
-      cs[sta0 + (size_t)sa_qd * as] = W.qd;
+      cs[sta0 + (size_t)sa_qb * as] = to_double(W.qb);
+      cs[sta0 + (size_t)sa_qg * as] = to_double(W.qg);
+      cs[sta0 + (size_t)sa_qd * as] = to_double(W.qd);
       if (GENERAL) {
         int k = 3;
-        if (I.rgateMod == 3) cs[sta0 + (size_t)(k++) * as] = W.qgmid;
-        if (I.rbodyMod) { cs[sta0 + (size_t)(k++) * as] = W.qbs; cs[sta0 + (size_t)(k++) * as] = W.qbd; }
+        if (I.rgateMod == 3) cs[sta0 + (size_t)(k++) * as] = to_double(W.qgmid);
+        if (I.rbodyMod) { cs[sta0 + (size_t)(k++) * as] = to_double(W.qbs); cs[sta0 + (size_t)(k++) * as] = to_double(W.qbd); }
       }
     }
   }
@@ -184,12 +197,19 @@ __global__ void __launch_bounds__(128) b4_eval_kernel(GroupDev g, LoadArgs a) {
 
 }  // namespace
 
-void launch_b4_group(const GroupDev &g, const LoadArgs &a, cudaStream_t stream) {
+void XB_CAT(launch_b4_group_a, XB_ARITH)(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream) {
   if (g.n <= 0) return;
   const int threads = 128;
   const int blocks = (g.n + threads - 1) / threads;
-  if (g.general) b4_eval_kernel<true><<<blocks, threads, 0, stream>>>(g, a);
-  else b4_eval_kernel<false><<<blocks, threads, 0, stream>>>(g, a);
+  if (g.general) {
+    b4_eval_kernel<true, 2><<<blocks, threads, 0, stream>>>(g, a);
+  } else {
+    switch (minblocks) {
+      case 3: b4_eval_kernel<false, 3><<<blocks, threads, 0, stream>>>(g, a); break;
+      case 4: b4_eval_kernel<false, 4><<<blocks, threads, 0, stream>>>(g, a); break;
+      default: b4_eval_kernel<false, 2><<<blocks, threads, 0, stream>>>(g, a); break;
+    }
+  }
 }
 
 }  // namespace b4

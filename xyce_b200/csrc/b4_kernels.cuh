@@ -54,7 +54,16 @@ struct LoadArgs {
   double *mat_planes[2];    // dFdx, dQdx contribution planes
 };
 
-void launch_b4_group(const GroupDev &g, const LoadArgs &a, cudaStream_t stream);
+// arith: 0 exact (no FMA contraction, IEEE division), 1 fma, 2 fast (fma + reciprocal division);
+// minblocks: 2 (255 registers), 3 (168) or 4 (128) resident blocks per SM for the default-topology kernel.
+void launch_b4_group_a0(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream);
+void launch_b4_group_a1(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream);
+void launch_b4_group_a2(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream);
+inline void launch_b4_group(const GroupDev &g, const LoadArgs &a, int arith, int minblocks, cudaStream_t stream) {
+  if (arith == 2) launch_b4_group_a2(g, a, minblocks, stream);
+  else if (arith == 1) launch_b4_group_a1(g, a, minblocks, stream);
+  else launch_b4_group_a0(g, a, minblocks, stream);
+}
 
 }  // namespace b4
 }  // namespace xb

@@ -23,17 +23,17 @@ namespace xb {
 namespace b4 {
 
 // Poly-gate depletion (N_DEV_MOSFET_B4.C:8819-8857).
-XB_HD void poly_depletion(double phi, double ngate, double epsgate, double coxe,
-                          double vg, double &vg_eff, double &dvg_eff_dvg) {
+XB_HD void poly_depletion(real phi, real ngate, real epsgate, real coxe,
+                          real vg, real &vg_eff, real &dvg_eff_dvg) {
   if ((ngate > 1.0e18) && (ngate < 1.0e25) && (vg > phi) && (epsgate != 0)) {
-    const double t1 = 1.0e6 * kQ * epsgate * ngate / (coxe * coxe);
-    const double t8 = vg - phi;
-    const double t4 = sqrt(1.0 + 2.0 * t8 / t1);
-    const double t2 = 2.0 * t8 / (t4 + 1.0);
-    const double t3 = 0.5 * t2 * t2 / t1;
-    const double t7 = 1.12 - t3 - 0.05;
-    const double t6 = sqrt(t7 * t7 + 0.224);
-    const double t5 = 1.12 - 0.5 * (t7 + t6);
+    const real t1 = 1.0e6 * kQ * epsgate * ngate / (coxe * coxe);
+    const real t8 = vg - phi;
+    const real t4 = sqrt(1.0 + 2.0 * t8 / t1);
+    const real t2 = 2.0 * t8 / (t4 + 1.0);
+    const real t3 = 0.5 * t2 * t2 / t1;
+    const real t7 = 1.12 - t3 - 0.05;
+    const real t6 = sqrt(t7 * t7 + 0.224);
+    const real t5 = 1.12 - 0.5 * (t7 + t6);
     vg_eff = vg - t5;
     dvg_eff_dvg = 1.0 - (0.5 - 0.5 / t4) * (1.0 + t7 / t6);
   } else {
@@ -45,10 +45,10 @@ XB_HD void poly_depletion(double phi, double ngate, double epsgate, double coxe,
 // One bulk junction diode (source or drain side) -- B4p82.C:3348-3480 (source)
 // and :3481-3600 (drain) are the same code with S/D parameter sets.
 struct JctPar {
-  double Nvtm, Isat, xjbv, bv, XExpBV, vjmFwd, vjmRev, IVjmFwd, IVjmRev, slpFwd, slpRev;
+  real Nvtm, Isat, xjbv, bv, XExpBV, vjmFwd, vjmRev, IVjmFwd, IVjmRev, slpFwd, slpRev;
 };
-XB_HD void junction_diode(int dioMod, const JctPar &j, double vj, double gmin,
-                          double &g, double &c) {
+XB_HD void junction_diode(int dioMod, const JctPar &j, real vj, real gmin,
+                          real &g, real &c) {
   if (j.Isat <= 0.0) {
     g = gmin;
     c = g * vj;
@@ -56,43 +56,43 @@ XB_HD void junction_diode(int dioMod, const JctPar &j, double vj, double gmin,
   }
   switch (dioMod) {
     case 0: {
-      const double ev = exp(vj / j.Nvtm);
-      const double t1 = j.xjbv * exp(-(j.bv + vj) / j.Nvtm);
+      const real ev = exp(vj / j.Nvtm);
+      const real t1 = j.xjbv * exp(-(j.bv + vj) / j.Nvtm);
       g = j.Isat * (ev + t1) / j.Nvtm + gmin;
       c = j.Isat * (ev + j.XExpBV - t1 - 1.0) + gmin * vj;
     } break;
     case 1: {
-      const double t2 = vj / j.Nvtm;
+      const real t2 = vj / j.Nvtm;
       if (t2 < -kExpThr) {
         g = gmin;
         c = j.Isat * (kMinExp - 1.0) + gmin * vj;
       } else if (vj <= j.vjmFwd) {
-        const double ev = exp(t2);
+        const real ev = exp(t2);
         g = j.Isat * ev / j.Nvtm + gmin;
         c = j.Isat * (ev - 1.0) + gmin * vj;
       } else {
-        const double t0 = j.IVjmFwd / j.Nvtm;
+        const real t0 = j.IVjmFwd / j.Nvtm;
         g = t0 + gmin;
         c = j.IVjmFwd - j.Isat + t0 * (vj - j.vjmFwd) + gmin * vj;
       }
     } break;
     case 2: {
       if (vj < j.vjmRev) {
-        const double t0 = vj / j.Nvtm;
-        double ev, dev;
+        const real t0 = vj / j.Nvtm;
+        real ev, dev;
         if (t0 < -kExpThr) { ev = kMinExp; dev = 0.0; }
         else { ev = exp(t0); dev = ev / j.Nvtm; }
-        const double t1 = ev - 1.0;
-        const double t2 = j.IVjmRev + j.slpRev * (vj - j.vjmRev);
+        const real t1 = ev - 1.0;
+        const real t2 = j.IVjmRev + j.slpRev * (vj - j.vjmRev);
         g = dev * t2 + t1 * j.slpRev + gmin;
         c = t1 * t2 + gmin * vj;
       } else if (vj <= j.vjmFwd) {
-        const double t0 = vj / j.Nvtm;
-        double ev, dev;
+        const real t0 = vj / j.Nvtm;
+        real ev, dev;
         if (t0 < -kExpThr) { ev = kMinExp; dev = 0.0; }
         else { ev = exp(t0); dev = ev / j.Nvtm; }
-        const double t1 = (j.bv + vj) / j.Nvtm;
-        double t2, t3;
+        const real t1 = (j.bv + vj) / j.Nvtm;
+        real t2, t3;
         if (t1 > kExpThr) { t2 = kMinExp; t3 = 0.0; }
         else { t2 = exp(-t1); t3 = -t2 / j.Nvtm; }
         g = j.Isat * (dev - j.xjbv * t3) + gmin;
@@ -108,8 +108,8 @@ XB_HD void junction_diode(int dioMod, const JctPar &j, double vj, double gmin,
 
 // Trap-assisted tunnelling factor for one junction component (B4p82.C:3608-3690):
 // returns T = DEXP(arg) and its derivative w.r.t. the junction voltage.
-XB_HD void tat_term(double vts, double nvtmr, double vj, double &t, double &dt_dvb) {
-  double t0, t9, t10;
+XB_HD void tat_term(real vts, real nvtmr, real vj, real &t, real &dt_dvb) {
+  real t0, t9, t10;
   if ((vts - vj) < (vts * 1e-3)) {
     t9 = 1.0e3;
     t0 = -vj / nvtmr * t9;
@@ -118,7 +118,7 @@ XB_HD void tat_term(double vts, double nvtmr, double vj, double &t, double &dt_d
   } else {
     t9 = 1.0 / (vts - vj);
     t0 = -vj / nvtmr * vts * t9;
-    const double dt0_dvb = vts / nvtmr * (t9 + vj * t9 * t9);
+    const real dt0_dvb = vts / nvtmr * (t9 + vj * t9 * t9);
     dexp(t0, t, t10);
     dt_dvb = t10 * dt0_dvb;
   }
@@ -131,14 +131,14 @@ XB_HD void tat_term(double vts, double nvtmr, double vj, double &t, double &dt_d
 //            (caller picks currSto vs nextSto exactly as B4p82.C:3096-3148)
 // ---------------------------------------------------------------------------
 XB_HD void stage_voltages(const SolverFlags &S, const B4Model &M, const B4Inst &I,
-                          const double *V, const double *sto_old, bool have_old,
-                          double von_prev, B4Mid &W) {
-  const double Vd = V[kD], Vs = V[kS], Vb = V[kB], Vsp = V[kSP], Vdp = V[kDP];
-  const double Vgp = V[kGP], Vbp = V[kBP], Vge = V[kGE];
-  const double Vgm = V[kGM];   // li_GateMid aliases li_GateExt unless rgateMod == 3 (B4.C:6228-6235)
-  const double Vdb = V[kDB], Vsb = V[kSB];
-  const double Qtotal = I.trnqsMod ? V[kQ] : 0.0;
-  const double ty = (double)M.dtype;
+                          const real *V, const real *sto_old, bool have_old,
+                          real von_prev, B4Mid &W) {
+  const real Vd = V[kD], Vs = V[kS], Vb = V[kB], Vsp = V[kSP], Vdp = V[kDP];
+  const real Vgp = V[kGP], Vbp = V[kBP], Vge = V[kGE];
+  const real Vgm = V[kGM];   // li_GateMid aliases li_GateExt unless rgateMod == 3 (B4.C:6228-6235)
+  const real Vdb = V[kDB], Vsb = V[kSB];
+  const real Qtotal = I.trnqsMod ? V[kQ] : 0.0;
+  const real ty = real(M.dtype);
 
   W.Vddp = Vd - Vdp;   W.Vssp = Vs - Vsp;
   W.Vdbb = Vdb - Vb;   W.Vdbbp = Vdb - Vbp;
@@ -146,13 +146,13 @@ XB_HD void stage_voltages(const SolverFlags &S, const B4Model &M, const B4Inst &
   W.Vbpb = Vbp - Vb;
   W.Vgegp = Vge - Vgp; W.Vgegm = Vge - Vgm; W.Vgmgp = Vgm - Vgp;
 
-  double vds = ty * (Vdp - Vsp), vgs = ty * (Vgp - Vsp), vbs = ty * (Vbp - Vsp);
-  double vges = ty * (Vge - Vsp), vgms = ty * (Vgm - Vsp);
-  double vdbs = ty * (Vdb - Vsp), vsbs = ty * (Vsb - Vsp);
-  double vses = ty * (Vs - Vsp), vdes = ty * (Vd - Vsp);
-  double qdef = ty * Qtotal;
-  double vbd = vbs - vds, vgd = vgs - vds;
-  double vged = vges - vds, vgmd = vgms - vds, vdbd = vdbs - vds;
+  real vds = ty * (Vdp - Vsp), vgs = ty * (Vgp - Vsp), vbs = ty * (Vbp - Vsp);
+  real vges = ty * (Vge - Vsp), vgms = ty * (Vgm - Vsp);
+  real vdbs = ty * (Vdb - Vsp), vsbs = ty * (Vsb - Vsp);
+  real vses = ty * (Vs - Vsp), vdes = ty * (Vd - Vsp);
+  real qdef = ty * Qtotal;
+  real vbd = vbs - vds, vgd = vgs - vds;
+  real vged = vges - vds, vgmd = vgms - vds, vdbd = vdbs - vds;
 
   int origFlag = 1;
   W.vbd_orig = vbd; W.vbs_orig = vbs; W.vgs_orig = vgs; W.vds_orig = vds;
@@ -178,7 +178,7 @@ XB_HD void stage_voltages(const SolverFlags &S, const B4Model &M, const B4Inst &
     vds = vsbs = vdes = vses = qdef = 0.0;
   }
 
-  double o_vbd, o_vbs, o_vgs, o_vds, o_vges, o_vgms, o_vdes, o_vses, o_vdbs, o_vsbs, o_vdbd, o_vged, o_vgmd;
+  real o_vbd, o_vbs, o_vgs, o_vds, o_vges, o_vgms, o_vdes, o_vses, o_vdbs, o_vsbs, o_vdbd, o_vged, o_vgmd;
   if (have_old) {
     o_vbd = sto_old[0]; o_vbs = sto_old[1]; o_vgs = sto_old[2]; o_vds = sto_old[3];
     o_vges = sto_old[4]; o_vgms = sto_old[5]; o_vdes = sto_old[6]; o_vses = sto_old[7];
@@ -189,12 +189,12 @@ XB_HD void stage_voltages(const SolverFlags &S, const B4Model &M, const B4Inst &
     o_vdes = vdes; o_vses = vses; o_vdbs = vdbs; o_vsbs = vsbs; o_vdbd = vdbd;
     o_vged = vged; o_vgmd = vgmd;
   }
-  const double o_vgd = o_vgs - o_vds;
+  const real o_vgd = o_vgs - o_vds;
 
   int limited = 0;
   if (S.voltageLimiterFlag && !(S.initFixFlag && I.OFF)) {
     int Check = 0, Check1 = 0, Check2 = 0;
-    const double vonl = von_prev;
+    const real vonl = von_prev;
     if (S.newtonIter >= 0 && !S.initJctFlag) {
       if (o_vds >= 0.0) {
         vgs = fetlim(vgs, o_vgs, vonl);
@@ -249,8 +249,8 @@ XB_HD void stage_voltages(const SolverFlags &S, const B4Model &M, const B4Inst &
         if (I.rbodyMod) {
           vdbd = pnjlim(vdbd, o_vdbd, kVt0, M.vcrit, Check1);
           vdbs = vdbd + vds;
-          const double o_vsbd = o_vsbs - o_vds;
-          double vsbd = vsbs - vds;
+          const real o_vsbd = o_vsbs - o_vds;
+          real vsbd = vsbs - vds;
           vsbd = pnjlim(vsbd, o_vsbd, kVt0, M.vcrit, Check2);
           vsbs = vsbd + vds;
           if ((Check1 != 0) || (Check2 != 0)) Check = 1;

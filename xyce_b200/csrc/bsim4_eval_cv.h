@@ -10,11 +10,11 @@ namespace b4 {
 
 // Depletion charge / capacitance of one bulk junction: bottom, sidewall and
 // gate-side sidewall components (B4p82.C:6800-6928).
-XB_HD void jct_comp(double v, double cz, double mj, double phib, double &q, double &cap, bool first) {
+XB_HD void jct_comp(real v, real cz, real mj, real phib, real &q, real &cap, bool first) {
   if (cz > 0.0) {
-    const double arg = 1.0 - v / phib;
-    const double sarg = (mj == 0.5) ? 1.0 / sqrt(arg) : exp(-mj * log(arg));
-    const double dq = phib * cz * (1.0 - arg * sarg) / (1.0 - mj);
+    const real arg = 1.0 - v / phib;
+    const real sarg = (mj == 0.5) ? 1.0 / sqrt(arg) : exp(-mj * log(arg));
+    const real dq = phib * cz * (1.0 - arg * sarg) / (1.0 - mj);
     if (first) { q = dq; cap = cz * sarg; }
     else { q += dq; cap += cz * sarg; }
   } else if (first) {
@@ -22,10 +22,10 @@ XB_HD void jct_comp(double v, double cz, double mj, double phib, double &q, doub
     cap = 0.0;
   }
 }
-XB_HD void junction_charge(double v, double cz, double czsw, double czswg,
-                           double mj, double mjsw, double mjswg,
-                           double phib, double phibsw, double phibswg,
-                           double &q, double &cap) {
+XB_HD void junction_charge(real v, real cz, real czsw, real czswg,
+                           real mj, real mjsw, real mjswg,
+                           real phib, real phibsw, real phibswg,
+                           real &q, real &cap) {
   if (v == 0.0) {
     q = 0.0;
     cap = cz + czsw + czswg;
@@ -34,8 +34,8 @@ XB_HD void junction_charge(double v, double cz, double czsw, double czswg,
     jct_comp(v, czsw, mjsw, phibsw, q, cap, false);
     jct_comp(v, czswg, mjswg, phibswg, q, cap, false);
   } else {
-    const double T0 = cz + czsw + czswg;
-    const double T1 = v * (cz * mj / phib + czsw * mjsw / phibsw + czswg * mjswg / phibswg);
+    const real T0 = cz + czsw + czswg;
+    const real T1 = v * (cz * mj / phib + czsw * mjsw / phibsw + czswg * mjswg / phibswg);
     q = v * (T0 + 0.5 * T1);
     cap = T0 + T1;
   }
@@ -43,22 +43,22 @@ XB_HD void junction_charge(double v, double cz, double czsw, double czswg,
 
 XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
                     const B4Inst &I, B4Mid &W, DcCarry &C) {
-  double T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, tmp, tmp1;
+  real T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, tmp, tmp1;
   const bool charge_needed = S.tranopFlag || S.acopFlag || S.transientFlag || S.dcsweepFlag;
   W.ChargeComputationNeeded = charge_needed ? 1 : 0;
 
-  const double Vds = C.Vds, Vbs = C.Vbs, Vbseff = C.Vbseff, dVbseff_dVb = C.dVbseff_dVb;
-  const double Phis = C.Phis, dPhis_dVb = C.dPhis_dVb, sqrtPhis = C.sqrtPhis, dsqrtPhis_dVb = C.dsqrtPhis_dVb;
-  const double Vgs_eff = C.Vgs_eff, dVgs_eff_dVg = C.dVgs_eff_dVg;
-  const double n = C.n, dn_dVb = C.dn_dVb, dn_dVd = C.dn_dVd, Vtm = C.Vtm;
-  const double Abulk0 = C.Abulk0, dAbulk0_dVb = C.dAbulk0_dVb;
-  const double epssub = C.epssub, toxe = C.toxe;
-  double Vth = C.Vth, dVth_dVb = C.dVth_dVb, dVth_dVd = C.dVth_dVd, Vgst = C.Vgst;
-  double Vgsteff = C.Vgsteff, dVgsteff_dVg = C.dVgsteff_dVg, dVgsteff_dVd = C.dVgsteff_dVd,
+  const real Vds = C.Vds, Vbs = C.Vbs, Vbseff = C.Vbseff, dVbseff_dVb = C.dVbseff_dVb;
+  const real Phis = C.Phis, dPhis_dVb = C.dPhis_dVb, sqrtPhis = C.sqrtPhis, dsqrtPhis_dVb = C.dsqrtPhis_dVb;
+  const real Vgs_eff = C.Vgs_eff, dVgs_eff_dVg = C.dVgs_eff_dVg;
+  const real n = C.n, dn_dVb = C.dn_dVb, dn_dVd = C.dn_dVd, Vtm = C.Vtm;
+  const real Abulk0 = C.Abulk0, dAbulk0_dVb = C.dAbulk0_dVb;
+  const real epssub = C.epssub, toxe = C.toxe;
+  real Vth = C.Vth, dVth_dVb = C.dVth_dVb, dVth_dVd = C.dVth_dVd, Vgst = C.Vgst;
+  real Vgsteff = C.Vgsteff, dVgsteff_dVg = C.dVgsteff_dVg, dVgsteff_dVd = C.dVgsteff_dVd,
          dVgsteff_dVb = C.dVgsteff_dVb;
-  double Vdsat = C.Vdsat;
-  double VbseffCV, dVbseffCV_dVb, Vfb, CoxWL;
-  double qgate = 0, qbulk = 0, qdrn = 0, qsrc = 0;
+  real Vdsat = C.Vdsat;
+  real VbseffCV, dVbseffCV_dVb, Vfb, CoxWL;
+  real qgate = 0, qbulk = 0, qdrn = 0, qsrc = 0;
 
   if ((M.xpart < 0) || (!charge_needed)) {
     qgate = qdrn = qsrc = qbulk = 0.0;
@@ -77,7 +77,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
     Vgst = Vgs_eff - Vth;
     dVth_dVb = P.k1ox * dsqrtPhis_dVb * dVbseff_dVb;
     CoxWL = M.coxe * P.weffCV * P.leffCV * I.nf;
-    const double Arg1 = Vgs_eff - VbseffCV - Vfb;
+    const real Arg1 = Vgs_eff - VbseffCV - Vfb;
     if (Arg1 <= 0.0) {            // accumulation
       qgate = CoxWL * Arg1;
       qbulk = -qgate;
@@ -104,14 +104,14 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       W.cbdb = 0.0;
       W.cbsb = -W.cgsb;
     } else {                      // inversion
-      const double One_Third_CoxWL = CoxWL / 3.0;
-      const double Two_Third_CoxWL = 2.0 * One_Third_CoxWL;
-      const double AbulkCV = Abulk0 * P.abulkCVfactor;
-      const double dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb * dVbseff_dVb;
-      const double dVdsat_dVg = 1.0 / AbulkCV;
+      const real One_Third_CoxWL = CoxWL / 3.0;
+      const real Two_Third_CoxWL = 2.0 * One_Third_CoxWL;
+      const real AbulkCV = Abulk0 * P.abulkCVfactor;
+      const real dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb * dVbseff_dVb;
+      const real dVdsat_dVg = 1.0 / AbulkCV;
       Vdsat = Vgst * dVdsat_dVg;
-      const double dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) * dVdsat_dVg;
-      double Alphaz, dAlphaz_dVg, dAlphaz_dVb;
+      const real dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) * dVdsat_dVg;
+      real Alphaz, dAlphaz_dVg, dAlphaz_dVb;
       if (M.xpart > 0.5) {        // 0/100 partition
         if (Vdsat <= Vds) {
           T1 = Vdsat / 3.0;
@@ -276,20 +276,20 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
     }
   } else {
     // ---- capMod 1 / 2 -----------------------------------------------------------------------------
-    double dT0_dVg, dT0_dVd, dT0_dVb, dT1_dVg, dT1_dVd, dT1_dVb;
-    double dT9_dVg, dT9_dVd, dT9_dVb, dT10_dVg, dT10_dVd, dT10_dVb;
-    double Csg, Csd, Csb, Cgg, Cgd, Cgb, Cbg, Cbd, Cbb;
+    real dT0_dVg, dT0_dVd, dT0_dVb, dT1_dVg, dT1_dVd, dT1_dVb;
+    real dT9_dVg, dT9_dVd, dT9_dVb, dT10_dVg, dT10_dVd, dT10_dVb;
+    real Csg, Csd, Csb, Cgg, Cgd, Cgb, Cbg, Cbd, Cbb;
     if (Vbseff < 0.0) { VbseffCV = Vbseff; dVbseffCV_dVb = 1.0; }
     else { VbseffCV = P.phi - Phis; dVbseffCV_dVb = -dPhis_dVb; }
     CoxWL = M.coxe * P.weffCV * P.leffCV * I.nf;
 
     if (M.cvchargeMod == 0) {
-      const double noff = n * P.noff;
-      const double dnoff_dVd = P.noff * dn_dVd;
-      const double dnoff_dVb = P.noff * dn_dVb;
+      const real noff = n * P.noff;
+      const real dnoff_dVd = P.noff * dn_dVd;
+      const real dnoff_dVb = P.noff * dn_dVb;
       T0 = Vtm * noff;
-      const double voffcv = P.voffcv;
-      const double VgstNVt = (Vgst - voffcv) / T0;
+      const real voffcv = P.voffcv;
+      const real VgstNVt = (Vgst - voffcv) / T0;
       if (VgstNVt > kExpThr) {
         Vgsteff = Vgst - voffcv;
         dVgsteff_dVg = dVgs_eff_dVg;
@@ -302,7 +302,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
         dVgsteff_dVb = dVgsteff_dVd * dnoff_dVb;
         dVgsteff_dVd *= dnoff_dVd;
       } else {
-        const double ExpVgst = exp(VgstNVt);
+        const real ExpVgst = exp(VgstNVt);
         Vgsteff = T0 * log(1.0 + ExpVgst);
         dVgsteff_dVg = ExpVgst / (1.0 + ExpVgst);
         dVgsteff_dVd = -dVgsteff_dVg * (dVth_dVd + (Vgst - voffcv) / noff * dnoff_dVd) + Vgsteff / noff * dnoff_dVd;
@@ -325,7 +325,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
         dT10_dVb = T10 * dn_dVb;
         T10 *= n;
       } else {
-        const double ExpVgst = exp(T2);
+        const real ExpVgst = exp(T2);
         T3 = Vtm * log(1.0 + ExpVgst);
         T10 = n * T3;
         dT10_dVg = P.mstarcv * ExpVgst / (1.0 + ExpVgst);
@@ -344,7 +344,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
         T9 = P.mstarcv + T3 * n;
         dT9_dVg = 0.0; dT9_dVd = dn_dVd * T3; dT9_dVb = dn_dVb * T3;
       } else {
-        const double ExpVgst = exp(T2);
+        const real ExpVgst = exp(T2);
         T3 = M.coxe / P.cdep0;
         T4 = T3 * ExpVgst;
         T5 = T1 * T4 / T0;
@@ -364,30 +364,30 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
 
     if (M.capMod == 1) {
       Vfb = I.vfbzb;
-      const double V3 = Vfb - Vgs_eff + VbseffCV - kDelta3;
+      const real V3 = Vfb - Vgs_eff + VbseffCV - kDelta3;
       if (Vfb <= 0.0) T0 = sqrt(V3 * V3 - 4.0 * kDelta3 * Vfb);
       else T0 = sqrt(V3 * V3 + 4.0 * kDelta3 * Vfb);
       T1 = 0.5 * (1.0 + V3 / T0);
-      const double Vfbeff = Vfb - 0.5 * (V3 + T0);
-      const double dVfbeff_dVg = T1 * dVgs_eff_dVg;
-      const double dVfbeff_dVb = -T1 * dVbseffCV_dVb;
-      const double Qac0 = CoxWL * (Vfbeff - Vfb);
-      const double dQac0_dVg = CoxWL * dVfbeff_dVg;
-      const double dQac0_dVb = CoxWL * dVfbeff_dVb;
+      const real Vfbeff = Vfb - 0.5 * (V3 + T0);
+      const real dVfbeff_dVg = T1 * dVgs_eff_dVg;
+      const real dVfbeff_dVb = -T1 * dVbseffCV_dVb;
+      const real Qac0 = CoxWL * (Vfbeff - Vfb);
+      const real dQac0_dVg = CoxWL * dVfbeff_dVg;
+      const real dQac0_dVb = CoxWL * dVfbeff_dVb;
 
       T0 = 0.5 * P.k1ox;
       T3 = Vgs_eff - Vfbeff - VbseffCV - Vgsteff;
       if (P.k1ox == 0.0) { T1 = 0.0; T2 = 0.0; }
       else if (T3 < 0.0) { T1 = T0 + T3 / P.k1ox; T2 = CoxWL; }
       else { T1 = sqrt(T0 * T0 + T3); T2 = CoxWL * T0 / T1; }
-      const double Qsub0 = CoxWL * P.k1ox * (T1 - T0);
-      const double dQsub0_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg);
-      const double dQsub0_dVd = -T2 * dVgsteff_dVd;
-      const double dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb);
+      const real Qsub0 = CoxWL * P.k1ox * (T1 - T0);
+      const real dQsub0_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg);
+      const real dQsub0_dVd = -T2 * dVgsteff_dVd;
+      const real dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb);
 
-      const double AbulkCV = Abulk0 * P.abulkCVfactor;
-      const double dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb;
-      const double VdsatCV = Vgsteff / AbulkCV;
+      const real AbulkCV = Abulk0 * P.abulkCVfactor;
+      const real dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb;
+      const real VdsatCV = Vgsteff / AbulkCV;
       T0 = VdsatCV - Vds - kDelta4;
       dT0_dVg = 1.0 / AbulkCV;
       dT0_dVb = -VdsatCV * dAbulkCV_dVb / AbulkCV;
@@ -396,7 +396,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       dT1_dVd = -T0 / T1;
       dT1_dVb = dT1_dVg * dT0_dVb;
       dT1_dVg *= dT0_dVg;
-      double VdseffCV, dVdseffCV_dVg, dVdseffCV_dVd, dVdseffCV_dVb;
+      real VdseffCV, dVdseffCV_dVg, dVdseffCV_dVd, dVdseffCV_dVb;
       if (T0 >= 0.0) {
         VdseffCV = VdsatCV - 0.5 * (T0 + T1);
         dVdseffCV_dVg = 0.5 * (dT0_dVg - dT1_dVg);
@@ -421,18 +421,18 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       T5 = (6.0 * T0 * (4.0 * Vgsteff - T0) / (T1 * T1) - 0.5);
       T6 = 12.0 * T2 * T2 * Vgsteff;
       qgate = CoxWL * (Vgsteff - 0.5 * VdseffCV + T3);
-      double Cgg1 = CoxWL * (T4 + T5 * dVdseffCV_dVg);
-      const double Cgd1 = CoxWL * T5 * dVdseffCV_dVd + Cgg1 * dVgsteff_dVd;
-      const double Cgb1 = CoxWL * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cgg1 * dVgsteff_dVb;
+      real Cgg1 = CoxWL * (T4 + T5 * dVdseffCV_dVg);
+      const real Cgd1 = CoxWL * T5 * dVdseffCV_dVd + Cgg1 * dVgsteff_dVd;
+      const real Cgb1 = CoxWL * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cgg1 * dVgsteff_dVb;
       Cgg1 *= dVgsteff_dVg;
       T7 = 1.0 - AbulkCV;
       qbulk = CoxWL * T7 * (0.5 * VdseffCV - T3);
       T4 = -T7 * (T4 - 1.0);
       T5 = -T7 * T5;
       T6 = -(T7 * T6 + (0.5 * VdseffCV - T3));
-      double Cbg1 = CoxWL * (T4 + T5 * dVdseffCV_dVg);
-      const double Cbd1 = CoxWL * T5 * dVdseffCV_dVd + Cbg1 * dVgsteff_dVd;
-      const double Cbb1 = CoxWL * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cbg1 * dVgsteff_dVb;
+      real Cbg1 = CoxWL * (T4 + T5 * dVdseffCV_dVg);
+      const real Cbd1 = CoxWL * T5 * dVdseffCV_dVd + Cbg1 * dVgsteff_dVd;
+      const real Cbb1 = CoxWL * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cbg1 * dVgsteff_dVb;
       Cbg1 *= dVgsteff_dVg;
 
       if (M.xpart > 0.5) {
@@ -488,21 +488,21 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       W.cbdb = Cbd;
     } else if (M.capMod == 2) {
       // charge-thickness model
-      const double vfbzb = I.vfbzb;
-      double V3 = vfbzb - Vgs_eff + VbseffCV - kDelta3;
+      const real vfbzb = I.vfbzb;
+      real V3 = vfbzb - Vgs_eff + VbseffCV - kDelta3;
       if (vfbzb <= 0.0) T0 = sqrt(V3 * V3 - 4.0 * kDelta3 * vfbzb);
       else T0 = sqrt(V3 * V3 + 4.0 * kDelta3 * vfbzb);
       T1 = 0.5 * (1.0 + V3 / T0);
-      const double Vfbeff = vfbzb - 0.5 * (V3 + T0);
-      const double dVfbeff_dVg = T1 * dVgs_eff_dVg;
-      const double dVfbeff_dVb = -T1 * dVbseffCV_dVb;
+      const real Vfbeff = vfbzb - 0.5 * (V3 + T0);
+      const real dVfbeff_dVg = T1 * dVgs_eff_dVg;
+      const real dVfbeff_dVb = -T1 * dVbseffCV_dVb;
 
-      const double Cox = I.coxp;
-      double Tox = 1.0e8 * I.toxp;
+      const real Cox = I.coxp;
+      real Tox = 1.0e8 * I.toxp;
       T0 = (Vgs_eff - VbseffCV - vfbzb) / Tox;
       dT0_dVg = dVgs_eff_dVg / Tox;
       dT0_dVb = -dVbseffCV_dVb / Tox;
-      double Tcen, dTcen_dVg, dTcen_dVd, dTcen_dVb;
+      real Tcen, dTcen_dVg, dTcen_dVd, dTcen_dVb;
       tmp = T0 * P.acde;
       if ((-kExpThr < tmp) && (tmp < kExpThr)) {
         Tcen = P.ldeb * exp(tmp);
@@ -516,53 +516,53 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
         Tcen = P.ldeb * kMaxExp;
         dTcen_dVg = dTcen_dVb = 0.0;
       }
-      const double LINK = 1.0e-3 * I.toxp;
+      const real LINK = 1.0e-3 * I.toxp;
       V3 = P.ldeb - Tcen - LINK;
-      const double V4 = sqrt(V3 * V3 + 4.0 * LINK * P.ldeb);
+      const real V4 = sqrt(V3 * V3 + 4.0 * LINK * P.ldeb);
       Tcen = P.ldeb - 0.5 * (V3 + V4);
       T1 = 0.5 * (1.0 + V3 / V4);
       dTcen_dVg *= T1;
       dTcen_dVb *= T1;
 
-      double Ccen = epssub / Tcen;
+      real Ccen = epssub / Tcen;
       T2 = Cox / (Cox + Ccen);
-      double Coxeff = T2 * Ccen;
+      real Coxeff = T2 * Ccen;
       T3 = -Ccen / Tcen;
-      double dCoxeff_dVg = T2 * T2 * T3;
-      double dCoxeff_dVb = dCoxeff_dVg * dTcen_dVb;
-      double dCoxeff_dVd;
+      real dCoxeff_dVg = T2 * T2 * T3;
+      real dCoxeff_dVb = dCoxeff_dVg * dTcen_dVb;
+      real dCoxeff_dVd;
       dCoxeff_dVg *= dTcen_dVg;
-      double CoxWLcen = CoxWL * Coxeff / M.coxe;
+      real CoxWLcen = CoxWL * Coxeff / M.coxe;
 
-      const double Qac0 = CoxWLcen * (Vfbeff - vfbzb);
-      double QovCox = Qac0 / Coxeff;
-      const double dQac0_dVg = CoxWLcen * dVfbeff_dVg + QovCox * dCoxeff_dVg;
-      const double dQac0_dVb = CoxWLcen * dVfbeff_dVb + QovCox * dCoxeff_dVb;
+      const real Qac0 = CoxWLcen * (Vfbeff - vfbzb);
+      real QovCox = Qac0 / Coxeff;
+      const real dQac0_dVg = CoxWLcen * dVfbeff_dVg + QovCox * dCoxeff_dVg;
+      const real dQac0_dVb = CoxWLcen * dVfbeff_dVb + QovCox * dCoxeff_dVb;
 
       T0 = 0.5 * P.k1ox;
       T3 = Vgs_eff - Vfbeff - VbseffCV - Vgsteff;
       if (P.k1ox == 0.0) { T1 = 0.0; T2 = 0.0; }
       else if (T3 < 0.0) { T1 = T0 + T3 / P.k1ox; T2 = CoxWLcen; }
       else { T1 = sqrt(T0 * T0 + T3); T2 = CoxWLcen * T0 / T1; }
-      const double Qsub0 = CoxWLcen * P.k1ox * (T1 - T0);
+      const real Qsub0 = CoxWLcen * P.k1ox * (T1 - T0);
       QovCox = Qsub0 / Coxeff;
-      const double dQsub0_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg) + QovCox * dCoxeff_dVg;
-      const double dQsub0_dVd = -T2 * dVgsteff_dVd;
-      const double dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb) + QovCox * dCoxeff_dVb;
+      const real dQsub0_dVg = T2 * (dVgs_eff_dVg - dVfbeff_dVg - dVgsteff_dVg) + QovCox * dCoxeff_dVg;
+      const real dQsub0_dVd = -T2 * dVgsteff_dVd;
+      const real dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb) + QovCox * dCoxeff_dVb;
 
       // gate-bias dependent delta Phis (inversion charge centroid)
-      double Denomi;
+      real Denomi;
       if (P.k1ox <= 0.0) { Denomi = 0.25 * P.moin * Vtm; T0 = 0.5 * P.sqrtPhi; }
       else { Denomi = P.moin * Vtm * P.k1ox * P.k1ox; T0 = P.k1ox * P.sqrtPhi; }
       T1 = 2.0 * T0 + Vgsteff;
-      const double DeltaPhi = Vtm * log(1.0 + T1 * Vgsteff / Denomi);
-      const double dDeltaPhi_dVg = 2.0 * Vtm * (T1 - T0) / (Denomi + T1 * Vgsteff);
+      const real DeltaPhi = Vtm * log(1.0 + T1 * Vgsteff / Denomi);
+      const real dDeltaPhi_dVg = 2.0 * Vtm * (T1 - T0) / (Denomi + T1 * Vgsteff);
 
       T0 = Vgsteff - DeltaPhi - 0.001;
       dT0_dVg = 1.0 - dDeltaPhi_dVg;
       T1 = sqrt(T0 * T0 + Vgsteff * 0.004);
-      const double VgDP = 0.5 * (T0 + T1);
-      const double dVgDP_dVg = 0.5 * (dT0_dVg + (T0 * dT0_dVg + 0.002) / T1);
+      const real VgDP = 0.5 * (T0 + T1);
+      const real dVgDP_dVg = 0.5 * (dT0_dVg + (T0 * dT0_dVg + 0.002) / T1);
 
       Tox += Tox;
       T0 = (Vgsteff + I.vtfbphi2) / Tox;
@@ -586,9 +586,9 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       CoxWLcen = CoxWL * Coxeff / M.coxe;
       W.Coxeff = Coxeff;
 
-      const double AbulkCV = Abulk0 * P.abulkCVfactor;
-      const double dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb;
-      const double VdsatCV = VgDP / AbulkCV;
+      const real AbulkCV = Abulk0 * P.abulkCVfactor;
+      const real dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb;
+      const real VdsatCV = VgDP / AbulkCV;
       T0 = VdsatCV - Vds - kDelta4;
       dT0_dVg = dVgDP_dVg / AbulkCV;
       dT0_dVb = -VdsatCV * dAbulkCV_dVb / AbulkCV;
@@ -597,7 +597,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       dT1_dVd = -T0 / T1;
       dT1_dVb = dT1_dVg * dT0_dVb;
       dT1_dVg *= dT0_dVg;
-      double VdseffCV, dVdseffCV_dVg, dVdseffCV_dVd, dVdseffCV_dVb;
+      real VdseffCV, dVdseffCV_dVg, dVdseffCV_dVd, dVdseffCV_dVb;
       if (T0 >= 0.0) {
         VdseffCV = VdsatCV - 0.5 * (T0 + T1);
         dVdseffCV_dVg = 0.5 * (dT0_dVg - dT1_dVg);
@@ -623,9 +623,9 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       T6 = T5 * VdseffCV / AbulkCV;
       qgate = CoxWLcen * (T1 - T0 * (0.5 - T3));
       QovCox = qgate / Coxeff;
-      double Cgg1 = CoxWLcen * (T4 * dVgDP_dVg + T5 * dVdseffCV_dVg);
-      const double Cgd1 = CoxWLcen * T5 * dVdseffCV_dVd + Cgg1 * dVgsteff_dVd + QovCox * dCoxeff_dVd;
-      const double Cgb1 = CoxWLcen * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cgg1 * dVgsteff_dVb + QovCox * dCoxeff_dVb;
+      real Cgg1 = CoxWLcen * (T4 * dVgDP_dVg + T5 * dVdseffCV_dVg);
+      const real Cgd1 = CoxWLcen * T5 * dVdseffCV_dVd + Cgg1 * dVgsteff_dVd + QovCox * dCoxeff_dVd;
+      const real Cgb1 = CoxWLcen * (T5 * dVdseffCV_dVb + T6 * dAbulkCV_dVb) + Cgg1 * dVgsteff_dVb + QovCox * dCoxeff_dVb;
       Cgg1 = Cgg1 * dVgsteff_dVg + QovCox * dCoxeff_dVg;
 
       T7 = 1.0 - AbulkCV;
@@ -636,9 +636,9 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       T12 = -(T9 * T1 / AbulkCV + VdseffCV * (0.5 - T0 / T2));
       qbulk = CoxWLcen * T7 * (0.5 * VdseffCV - T0 * VdseffCV / T2);
       QovCox = qbulk / Coxeff;
-      double Cbg1 = CoxWLcen * (T10 + T11 * dVdseffCV_dVg);
-      const double Cbd1 = CoxWLcen * T11 * dVdseffCV_dVd + Cbg1 * dVgsteff_dVd + QovCox * dCoxeff_dVd;
-      const double Cbb1 = CoxWLcen * (T11 * dVdseffCV_dVb + T12 * dAbulkCV_dVb) + Cbg1 * dVgsteff_dVb + QovCox * dCoxeff_dVb;
+      real Cbg1 = CoxWLcen * (T10 + T11 * dVdseffCV_dVg);
+      const real Cbd1 = CoxWLcen * T11 * dVdseffCV_dVd + Cbg1 * dVgsteff_dVd + QovCox * dCoxeff_dVd;
+      const real Cbb1 = CoxWLcen * (T11 * dVdseffCV_dVb + T12 * dAbulkCV_dVb) + Cbg1 * dVgsteff_dVb + QovCox * dCoxeff_dVb;
       Cbg1 = Cbg1 * dVgsteff_dVg + QovCox * dCoxeff_dVg;
 
       if (M.xpart > 0.5) {
@@ -724,12 +724,12 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
 
   // ---- S/D bulk junction depletion charge and capacitance ------------------------------------------
   if (charge_needed) {
-    const double czbd = M.DunitAreaTempJctCap * I.Adeff;
-    const double czbs = M.SunitAreaTempJctCap * I.Aseff;
-    const double czbdsw = M.DunitLengthSidewallTempJctCap * I.Pdeff;
-    const double czbdswg = M.DunitLengthGateSidewallTempJctCap * P.weffCJ * I.nf;
-    const double czbssw = M.SunitLengthSidewallTempJctCap * I.Pseff;
-    const double czbsswg = M.SunitLengthGateSidewallTempJctCap * P.weffCJ * I.nf;
+    const real czbd = M.DunitAreaTempJctCap * I.Adeff;
+    const real czbs = M.SunitAreaTempJctCap * I.Aseff;
+    const real czbdsw = M.DunitLengthSidewallTempJctCap * I.Pdeff;
+    const real czbdswg = M.DunitLengthGateSidewallTempJctCap * P.weffCJ * I.nf;
+    const real czbssw = M.SunitLengthSidewallTempJctCap * I.Pseff;
+    const real czbsswg = M.SunitLengthGateSidewallTempJctCap * P.weffCJ * I.nf;
     junction_charge(W.vbs_jct, czbs, czbssw, czbsswg,
                     M.SbulkJctBotGradingCoeff, M.SbulkJctSideGradingCoeff, M.SbulkJctGateSideGradingCoeff,
                     M.PhiBS, M.PhiBSWS, M.PhiBSWGS, W.qbs, W.capbs);
@@ -741,7 +741,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- gate electrode resistance currents & overlap capacitances -----------------------------------------
-  double vgdx, vgsx;
+  real vgdx, vgsx;
   if (I.rgateMod == 3) { vgdx = W.vgmd; vgsx = W.vgms; }
   else { vgdx = W.vgd; vgsx = W.vgs; }
   W.Igate = W.IgateMid = 0.0;

@@ -10,18 +10,18 @@ namespace b4 {
 
 // Gate-induced drain/source leakage, gidlMod = 0 (B4p82.C:5072-5155).  `T1` is the
 // normalised field term, `vbx` the body-to-(drain|source) voltage.
-XB_HD void gidl_mod0(double T0, double T1, double dveff_dvg, double a, double b, double c,
-                     double weffCJ, double vbx, double &Ig, double &Gd, double &Gg, double &Gb) {
+XB_HD void gidl_mod0(real T0, real T1, real dveff_dvg, real a, real b, real c,
+                     real weffCJ, real vbx, real &Ig, real &Gd, real &Gg, real &Gb) {
   if ((a <= 0.0) || (b <= 0.0) || (T1 <= 0.0) || (c <= 0.0) || (vbx > 0.0)) {
     Ig = Gd = Gg = Gb = 0.0;
     return;
   }
-  const double dT1_dVd = 1.0 / T0;
-  const double dT1_dVg = -dveff_dvg * dT1_dVd;
-  const double T2 = b / T1;
+  const real dT1_dVd = 1.0 / T0;
+  const real dT1_dVg = -dveff_dvg * dT1_dVd;
+  const real T2 = b / T1;
   if (T2 < 100.0) {
     Ig = a * weffCJ * T1 * exp(-T2);
-    const double T3 = Ig * (1.0 + T2) / T1;
+    const real T3 = Ig * (1.0 + T2) / T1;
     Gd = T3 * dT1_dVd;
     Gg = T3 * dT1_dVg;
   } else {
@@ -30,11 +30,11 @@ XB_HD void gidl_mod0(double T0, double T1, double dveff_dvg, double a, double b,
     Gg = Ig * dT1_dVg;
     Ig *= T1;
   }
-  const double T4 = vbx * vbx;
-  const double T5 = -vbx * T4;
-  const double T6 = c + T5;
-  const double T7 = T5 / T6;
-  const double T8 = 3.0 * c * T4 / T6 / T6;
+  const real T4 = vbx * vbx;
+  const real T5 = -vbx * T4;
+  const real T6 = c + T5;
+  const real T7 = T5 / T6;
+  const real T8 = 3.0 * c * T4 / T6 / T6;
   Gd = Gd * T7 + Ig * T8;
   Gg = Gg * T7;
   Gb = -Ig * T8;
@@ -42,17 +42,17 @@ XB_HD void gidl_mod0(double T0, double T1, double dveff_dvg, double a, double b,
 }
 
 // gidlMod = 1 (B4p82.C:5157-5290).
-XB_HD void gidl_mod1(double T0, double T1, double rg, double dveff_dvg, double a, double b, double c,
-                     double k, double f, double weffCJ, double vbx, double clamp,
-                     double &Ig, double &Gd, double &Gg, double &Gb) {
+XB_HD void gidl_mod1(real T0, real T1, real rg, real dveff_dvg, real a, real b, real c,
+                     real k, real f, real weffCJ, real vbx, real clamp,
+                     real &Ig, real &Gd, real &Gg, real &Gb) {
   if ((a <= 0.0) || (b <= 0.0) || (T1 <= 0.0) || (c < 0.0)) {
     Ig = Gd = Gg = Gb = 0.0;
     return;
   }
-  const double dT1_dVd = 1 / T0;
-  const double dT1_dVg = -rg * dT1_dVd * dveff_dvg;
-  const double T2 = b / T1;
-  double T3;
+  const real dT1_dVd = 1 / T0;
+  const real dT1_dVg = -rg * dT1_dVd * dveff_dvg;
+  const real T2 = b / T1;
+  real T3;
   if (T2 < kExpLThr) {
     Ig = weffCJ * a * T1 * exp(-T2);
     T3 = Ig / T1 * (T2 + 1);
@@ -64,10 +64,10 @@ XB_HD void gidl_mod1(double T0, double T1, double rg, double dveff_dvg, double a
     Gd = T3 * dT1_dVd;
     Gg = T3 * dT1_dVg;
   }
-  double T4 = vbx - f;
+  real T4 = vbx - f;
   if (T4 > clamp) T4 = clamp;
-  const double T5 = (T4 == 0) ? kExpLThr : k / T4;
-  double T6;
+  const real T5 = (T4 == 0) ? kExpLThr : k / T4;
+  real T6;
   if (T5 < kExpLThr) {
     T6 = exp(T5);
     Gb = -Ig * T6 * T5 / T4;
@@ -82,30 +82,30 @@ XB_HD void gidl_mod1(double T0, double T1, double rg, double dveff_dvg, double a
 
 // Everything the C-V stage needs from the DC stage besides B4Mid.
 struct DcCarry {
-  double Vds, Vgs, Vbs, Vdb;
-  double Vbseff, dVbseff_dVb, Phis, dPhis_dVb, sqrtPhis, dsqrtPhis_dVb;
-  double Vth, dVth_dVb, dVth_dVd;
-  double Vgs_eff, dVgs_eff_dVg, Vgst;
-  double n, dn_dVb, dn_dVd, Vtm, Vtm0;
-  double Vgsteff, dVgsteff_dVg, dVgsteff_dVd, dVgsteff_dVb;
-  double Vdseff, dVdseff_dVg, dVdseff_dVd, dVdseff_dVb;
-  double Abulk, dAbulk_dVb, dAbulk_dVg, Abulk0, dAbulk0_dVb;
-  double Weff, Leff, epsrox, toxe, epssub;
-  double Vfb;      // flat-band of the gate-current section (0 when igcMod == igbMod == 0)
-  double dCoxeff_dVg;
-  double Vdsat;    // as left by the tnoiMod block
+  real Vds, Vgs, Vbs, Vdb;
+  real Vbseff, dVbseff_dVb, Phis, dPhis_dVb, sqrtPhis, dsqrtPhis_dVb;
+  real Vth, dVth_dVb, dVth_dVd;
+  real Vgs_eff, dVgs_eff_dVg, Vgst;
+  real n, dn_dVb, dn_dVd, Vtm, Vtm0;
+  real Vgsteff, dVgsteff_dVg, dVgsteff_dVd, dVgsteff_dVb;
+  real Vdseff, dVdseff_dVg, dVdseff_dVd, dVdseff_dVb;
+  real Abulk, dAbulk_dVb, dAbulk_dVg, Abulk0, dAbulk0_dVb;
+  real Weff, Leff, epsrox, toxe, epssub;
+  real Vfb;      // flat-band of the gate-current section (0 when igcMod == igbMod == 0)
+  real dCoxeff_dVg;
+  real Vdsat;    // as left by the tnoiMod block
 };
 
 XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
                     const B4Inst &I, B4Mid &W, DcCarry &C) {
-  double T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, T13, T14;
-  double dT0_dVg, dT0_dVd, dT0_dVb, dT1_dVg, dT1_dVd, dT1_dVb;
-  double dT2_dVg, dT2_dVd, dT2_dVb, dT3_dVg, dT3_dVd, dT3_dVb;
-  double dT4_dVd, dT4_dVb, dT5_dVg, dT5_dVd, dT5_dVb;
-  double dT6_dVg, dT6_dVd, dT6_dVb, dT7_dVg, dT7_dVd, dT7_dVb;
-  double dT8_dVg, dT8_dVd, dT8_dVb, dT9_dVg, dT9_dVd, dT9_dVb;
-  double dT10_dVg, dT10_dVd, dT10_dVb;
-  const double gmin = S.gmin;
+  real T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, T13, T14;
+  real dT0_dVg, dT0_dVd, dT0_dVb, dT1_dVg, dT1_dVd, dT1_dVb;
+  real dT2_dVg, dT2_dVd, dT2_dVb, dT3_dVg, dT3_dVd, dT3_dVb;
+  real dT4_dVd, dT4_dVb, dT5_dVg, dT5_dVd, dT5_dVb;
+  real dT6_dVg, dT6_dVd, dT6_dVb, dT7_dVg, dT7_dVd, dT7_dVb;
+  real dT8_dVg, dT8_dVd, dT8_dVb, dT9_dVg, dT9_dVd, dT9_dVb;
+  real dT10_dVg, dT10_dVd, dT10_dVb;
+  const real gmin = S.gmin;
 
   // ---- source / drain bulk junction diodes --------------------------------
   {
@@ -130,7 +130,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     junction_diode(M.dioMod, jd, W.vbd_jct, gmin, W.gbd, W.cbd);
 
     // trap-assisted tunnelling / recombination in reverse bias
-    double t1, d1, t2, d2, t3, d3, t4, d4, t5, d5, t6, d6;
+    real t1, d1, t2, d2, t3, d3, t4, d4, t5, d5, t6, d6;
     tat_term(M.vtss,    M.vtm0 * M.njtsstemp,    W.vbs_jct, t1, d1);
     tat_term(M.vtsd,    M.vtm0 * M.njtsdtemp,    W.vbd_jct, t2, d2);
     tat_term(M.vtssws,  M.vtm0 * M.njtsswstemp,  W.vbs_jct, t3, d3);
@@ -146,22 +146,22 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- mode selection -----------------------------------------------------
-  double Vds, Vgs, Vbs, Vdb;
+  real Vds, Vgs, Vbs, Vdb;
   if (W.vds >= 0.0) { W.mode = 1;  Vds = W.vds;  Vgs = W.vgs; Vbs = W.vbs; Vdb = W.vds - W.vbs; }
   else              { W.mode = -1; Vds = -W.vds; Vgs = W.vgd; Vbs = W.vbd; Vdb = -W.vbs; }
 
-  double epsrox, toxe, epssub;
+  real epsrox, toxe, epssub;
   if (M.mtrlMod) { epsrox = 3.9; toxe = M.eot; epssub = kEps0B4 * M.epsrsub; }
   else { epsrox = M.epsrox; toxe = M.toxe; epssub = kEpsSi; }
 
   if (S.artParameterFlag) {   // DCOP homotopy (DeviceSupport::contVds / contVgst)
-    double mn = S.vdsScaleMin; if (mn <= 0.0) mn = 0.3;
+    real mn = S.vdsScaleMin; if (mn <= 0.0) mn = 0.3;
     Vds = Vds * (S.nltermScale * (1.0 - mn) + mn);
     Vgs = S.gainScale * Vgs + (1.0 - S.gainScale) * S.vgstConst;
   }
 
   // ---- effective body bias ------------------------------------------------
-  double Vbseff, dVbseff_dVb;
+  real Vbseff, dVbseff_dVb;
   T0 = Vbs - I.vbsc - 0.001;
   T1 = sqrt(T0 * T0 - 0.004 * I.vbsc);
   if (T0 >= 0.0) {
@@ -178,32 +178,32 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   Vbseff = T9 - 0.5 * (T0 + T1);
   dVbseff_dVb *= 0.5 * (1.0 + T0 / T1);
 
-  const double Phis = P.phi - Vbseff;
-  const double dPhis_dVb = -1.0;
-  const double sqrtPhis = sqrt(Phis);
-  const double dsqrtPhis_dVb = -0.5 / sqrtPhis;
-  const double Xdep = P.Xdep0 * sqrtPhis / P.sqrtPhi;
-  const double dXdep_dVb = (P.Xdep0 / P.sqrtPhi) * dsqrtPhis_dVb;
-  const double Leff = P.leff;
-  const double Vtm = M.vtm;
-  const double Vtm0 = M.vtm0;
+  const real Phis = P.phi - Vbseff;
+  const real dPhis_dVb = -1.0;
+  const real sqrtPhis = sqrt(Phis);
+  const real dsqrtPhis_dVb = -0.5 / sqrtPhis;
+  const real Xdep = P.Xdep0 * sqrtPhis / P.sqrtPhi;
+  const real dXdep_dVb = (P.Xdep0 / P.sqrtPhi) * dsqrtPhis_dVb;
+  const real Leff = P.leff;
+  const real Vtm = M.vtm;
+  const real Vtm0 = M.vtm0;
 
   // ---- threshold voltage --------------------------------------------------
   T3 = sqrt(Xdep);
-  const double V0 = P.vbi - P.phi;
+  const real V0 = P.vbi - P.phi;
   T0 = P.dvt2 * Vbseff;
   if (T0 >= -0.5) { T1 = 1.0 + T0; T2 = P.dvt2; }
   else { T4 = 1.0 / (3.0 + 8.0 * T0); T1 = (1.0 + 3.0 * T0) * T4; T2 = P.dvt2 * T4 * T4; }
-  const double lt1 = M.factor1 * T3 * T1;
-  const double dlt1_dVb = M.factor1 * (0.5 / T3 * T1 * dXdep_dVb + T3 * T2);
+  const real lt1 = M.factor1 * T3 * T1;
+  const real dlt1_dVb = M.factor1 * (0.5 / T3 * T1 * dXdep_dVb + T3 * T2);
 
   T0 = P.dvt2w * Vbseff;
   if (T0 >= -0.5) { T1 = 1.0 + T0; T2 = P.dvt2w; }
   else { T4 = 1.0 / (3.0 + 8.0 * T0); T1 = (1.0 + 3.0 * T0) * T4; T2 = P.dvt2w * T4 * T4; }
-  const double ltw = M.factor1 * T3 * T1;
-  const double dltw_dVb = M.factor1 * (0.5 / T3 * T1 * dXdep_dVb + T3 * T2);
+  const real ltw = M.factor1 * T3 * T1;
+  const real dltw_dVb = M.factor1 * (0.5 / T3 * T1 * dXdep_dVb + T3 * T2);
 
-  double Theta0, dTheta0_dVb;
+  real Theta0, dTheta0_dVb;
   T0 = P.dvt1 * Leff / lt1;
   if (T0 < kExpThr) {
     T1 = exp(T0);
@@ -218,8 +218,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dTheta0_dVb = 0.0;
   }
   W.thetavth = P.dvt0 * Theta0;
-  const double Delt_vth = W.thetavth * V0;
-  const double dDelt_vth_dVb = P.dvt0 * dTheta0_dVb * V0;
+  const real Delt_vth = W.thetavth * V0;
+  const real dDelt_vth_dVb = P.dvt0 * dTheta0_dVb * V0;
 
   T0 = P.dvt1w * P.weff * Leff / ltw;
   if (T0 < kExpThr) {
@@ -238,10 +238,10 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   T2 = T0 * V0;
   dT2_dVb = P.dvt0w * dT5_dVb * V0;
 
-  const double TempRatio = I.temp / M.tnom - 1.0;
+  const real TempRatio = I.temp / M.tnom - 1.0;
   T0 = sqrt(1.0 + P.lpe0 / Leff);
   T1 = P.k1ox * (T0 - 1.0) * P.sqrtPhi + (P.kt1 + P.kt1l / Leff + P.kt2 * Vbseff) * TempRatio;
-  const double Vth_NarrowW = toxe * P.phi / (P.weff + P.w0);
+  const real Vth_NarrowW = toxe * P.phi / (P.weff + P.w0);
 
   T3 = I.eta0 + P.etab * Vbseff;
   if (T3 < 1.0e-4) {
@@ -251,24 +251,24 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   } else {
     T4 = 1.0;
   }
-  const double dDIBL_Sft_dVd = T3 * P.theta0vb0;
-  const double DIBL_Sft = dDIBL_Sft_dVd * Vds;
-  const double Lpe_Vb = sqrt(1.0 + P.lpeb / Leff);
+  const real dDIBL_Sft_dVd = T3 * P.theta0vb0;
+  const real DIBL_Sft = dDIBL_Sft_dVd * Vds;
+  const real Lpe_Vb = sqrt(1.0 + P.lpeb / Leff);
 
-  double Vth = M.dtype * I.vth0 + (P.k1ox * sqrtPhis - P.k1 * P.sqrtPhi) * Lpe_Vb
+  real Vth = M.dtype * I.vth0 + (P.k1ox * sqrtPhis - P.k1 * P.sqrtPhi) * Lpe_Vb
              - I.k2ox * Vbseff - Delt_vth - T2 + (P.k3 + P.k3b * Vbseff) * Vth_NarrowW + T1 - DIBL_Sft;
-  double dVth_dVb = Lpe_Vb * P.k1ox * dsqrtPhis_dVb - I.k2ox - dDelt_vth_dVb - dT2_dVb
+  real dVth_dVb = Lpe_Vb * P.k1ox * dsqrtPhis_dVb - I.k2ox - dDelt_vth_dVb - dT2_dVb
                   + P.k3b * Vth_NarrowW - P.etab * Vds * P.theta0vb0 * T4 + P.kt2 * TempRatio;
-  double dVth_dVd = -dDIBL_Sft_dVd;
+  real dVth_dVd = -dDIBL_Sft_dVd;
 
   // subthreshold swing factor n
-  double n, dn_dVb, dn_dVd;
+  real n, dn_dVb, dn_dVd;
   {
-    const double tmp1 = epssub / Xdep;
+    const real tmp1 = epssub / Xdep;
     // (nstar, a noise-only quantity at B4p82.C:3908, is not evaluated)
-    const double tmp2 = P.nfactor * tmp1;
-    const double tmp3 = P.cdsc + P.cdscb * Vbseff + P.cdscd * Vds;
-    const double tmp4 = (tmp2 + tmp3 * Theta0 + P.cit) / M.coxe;
+    const real tmp2 = P.nfactor * tmp1;
+    const real tmp3 = P.cdsc + P.cdscb * Vbseff + P.cdscd * Vds;
+    const real tmp4 = (tmp2 + tmp3 * Theta0 + P.cit) / M.coxe;
     if (tmp4 >= -0.5) {
       n = 1.0 + tmp4;
       dn_dVb = (-tmp2 / Xdep * dXdep_dVb + tmp3 * dTheta0_dVb + P.cdscb * Theta0) / M.coxe;
@@ -291,8 +291,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT3_dVd = P.dvtp0 * dT2_dVd;
     if (M.tempMod < 2) { T4 = Vtm * log(Leff / T3); dT4_dVd = -Vtm * dT3_dVd / T3; }
     else { T4 = M.vtm0 * log(Leff / T3); dT4_dVd = -M.vtm0 * dT3_dVd / T3; }
-    const double dDITS_Sft_dVd = dn_dVd * T4 + n * dT4_dVd;
-    const double dDITS_Sft_dVb = T4 * dn_dVb;
+    const real dDITS_Sft_dVd = dn_dVd * T4 + n * dT4_dVd;
+    const real dDITS_Sft_dVb = T4 * dn_dVb;
     Vth -= n * T4;
     dVth_dVd -= dDITS_Sft_dVd;
     dVth_dVb -= dDITS_Sft_dVb;
@@ -300,8 +300,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   if (!((P.dvtp4 == 0.0) || (P.dvtp2factor == 0.0))) {
     T1 = 2.0 * P.dvtp4 * Vds;
     dexp(T1, T0, T10);
-    const double DITS_Sft2 = P.dvtp2factor * (T0 - 1) / (T0 + 1);
-    const double dDITS_Sft2_dVd = P.dvtp2factor * P.dvtp4 * 4.0 * T10 / ((T0 + 1) * (T0 + 1));
+    const real DITS_Sft2 = P.dvtp2factor * (T0 - 1) / (T0 + 1);
+    const real dDITS_Sft2_dVd = P.dvtp2factor * P.dvtp4 * 4.0 * T10 / ((T0 + 1) * (T0 + 1));
     Vth -= DITS_Sft2;
     dVth_dVd -= dDITS_Sft2_dVd;
   }
@@ -313,10 +313,10 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   T1 = (M.mtrlMod == 0) ? kEpsSi : M.epsrgate * kEps0B4;
   poly_depletion(T0, P.ngate, T1, M.coxe, W.vgs, W.vgs_eff, W.dvgs_eff_dvg);
   poly_depletion(T0, P.ngate, T1, M.coxe, W.vgd, W.vgd_eff, W.dvgd_eff_dvg);
-  double Vgs_eff, dVgs_eff_dVg;
+  real Vgs_eff, dVgs_eff_dVg;
   if (W.mode > 0) { Vgs_eff = W.vgs_eff; dVgs_eff_dVg = W.dvgs_eff_dvg; }
   else { Vgs_eff = W.vgd_eff; dVgs_eff_dVg = W.dvgd_eff_dvg; }
-  const double Vgst = Vgs_eff - Vth;
+  const real Vgst = Vgs_eff - Vth;
 
   // ---- effective Vgst -------------------------------------------------------
   T0 = n * Vtm;
@@ -334,7 +334,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT10_dVb = T10 * dn_dVb;
     T10 *= n;
   } else {
-    const double ExpVgst = exp(T2);
+    const real ExpVgst = exp(T2);
     T3 = Vtm * log(1.0 + ExpVgst);
     T10 = n * T3;
     dT10_dVg = P.mstar * ExpVgst / (1.0 + ExpVgst);
@@ -353,7 +353,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     T9 = P.mstar + T3 * n;
     dT9_dVg = 0.0; dT9_dVd = dn_dVd * T3; dT9_dVb = dn_dVb * T3;
   } else {
-    const double ExpVgst = exp(T2);
+    const real ExpVgst = exp(T2);
     T3 = M.coxe / P.cdep0;
     T4 = T3 * ExpVgst;
     T5 = T1 * T4 / T0;
@@ -363,18 +363,18 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT9_dVd = T4 * dn_dVd - dT9_dVg * dVth_dVd - T5 * dn_dVd;
     dT9_dVg *= dVgs_eff_dVg;
   }
-  const double Vgsteff = T10 / T9;
+  const real Vgsteff = T10 / T9;
   W.Vgsteff = Vgsteff;
   T11 = T9 * T9;
-  const double dVgsteff_dVg = (T9 * dT10_dVg - T10 * dT9_dVg) / T11;
-  const double dVgsteff_dVd = (T9 * dT10_dVd - T10 * dT9_dVd) / T11;
-  const double dVgsteff_dVb = (T9 * dT10_dVb - T10 * dT9_dVb) / T11;
+  const real dVgsteff_dVg = (T9 * dT10_dVg - T10 * dT9_dVg) / T11;
+  const real dVgsteff_dVd = (T9 * dT10_dVd - T10 * dT9_dVd) / T11;
+  const real dVgsteff_dVb = (T9 * dT10_dVb - T10 * dT9_dVb) / T11;
 
   // ---- effective channel width & parasitic Rds ------------------------------
   T9 = sqrtPhis - P.sqrtPhi;
-  double Weff = P.weff - 2.0 * (P.dwg * Vgsteff + P.dwb * T9);
-  double dWeff_dVg = -2.0 * P.dwg;
-  double dWeff_dVb = -2.0 * P.dwb * dsqrtPhis_dVb;
+  real Weff = P.weff - 2.0 * (P.dwg * Vgsteff + P.dwb * T9);
+  real dWeff_dVg = -2.0 * P.dwg;
+  real dWeff_dVb = -2.0 * P.dwb * dsqrtPhis_dVb;
   if (Weff < 2.0e-8) {
     T0 = 1.0 / (6.0e-8 - 2.0 * Weff);
     Weff = 2.0e-8 * (4.0e-8 - Weff) * T0;
@@ -382,7 +382,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dWeff_dVg *= T0;
     dWeff_dVb *= T0;
   }
-  double Rds, dRds_dVg, dRds_dVb;
+  real Rds, dRds_dVg, dRds_dVb;
   if (M.rdsMod == 1) {
     Rds = dRds_dVg = dRds_dVb = 0.0;
   } else {
@@ -403,17 +403,17 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- bulk charge effect (Abulk) -------------------------------------------
-  double Abulk, dAbulk_dVb, dAbulk_dVg, Abulk0, dAbulk0_dVb;
+  real Abulk, dAbulk_dVb, dAbulk_dVg, Abulk0, dAbulk0_dVb;
   {
     T9 = 0.5 * P.k1ox * Lpe_Vb / sqrtPhis;
     T1 = T9 + I.k2ox - P.k3b * Vth_NarrowW;
     dT1_dVb = -T9 / sqrtPhis * dsqrtPhis_dVb;
     T9 = sqrt(P.xj * Xdep);
-    const double tmp1 = Leff + 2.0 * T9;
+    const real tmp1 = Leff + 2.0 * T9;
     T5 = Leff / tmp1;
-    const double tmp2 = P.a0 * T5;
-    const double tmp3 = P.weff + P.b1;
-    const double tmp4 = P.b0 / tmp3;
+    const real tmp2 = P.a0 * T5;
+    const real tmp3 = P.weff + P.b1;
+    const real tmp4 = P.b0 / tmp3;
     T2 = tmp2 + tmp4;
     dT2_dVb = -T9 / tmp1 / Xdep * dXdep_dVb;
     T6 = T5 * T5;
@@ -453,7 +453,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- mobility ---------------------------------------------------------------
-  double Denomi, dDenomi_dVg, dDenomi_dVd, dDenomi_dVb;
+  real Denomi, dDenomi_dVg, dDenomi_dVd, dDenomi_dVb;
   if (M.mtrlMod && (M.mtrlCompatMod == 0))
     T14 = 2.0 * M.dtype * (M.phig - M.easub - 0.5 * M.Eg0 + 0.45);
   else
@@ -562,10 +562,10 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     T1 = exp(P.eu * log(T0));
     dT1_dVg = T1 * P.eu * 1.0e-8 / T0 / toxe / 6.0;
     T2 = P.ua + P.uc * Vbseff;
-    const double VgsteffVth = P.VgsteffVth;
+    const real VgsteffVth = P.VgsteffVth;
     T10 = exp(P.ucs * log(0.5 + 0.5 * Vgsteff / VgsteffVth));
     T11 = P.ud / T10;
-    const double dT11_dVg = -0.5 * P.ucs * T11 / (0.5 + 0.5 * Vgsteff / VgsteffVth) / VgsteffVth;
+    const real dT11_dVg = -0.5 * P.ucs * T11 / (0.5 + 0.5 * Vgsteff / VgsteffVth) / VgsteffVth;
     dDenomi_dVg = T2 * dT1_dVg + dT11_dVg;
     dDenomi_dVd = 0.0;
     dDenomi_dVb = T1 * P.uc;
@@ -581,24 +581,24 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dDenomi_dVd *= T9;
     dDenomi_dVb *= T9;
   }
-  const double ueff = I.u0temp / Denomi;
+  const real ueff = I.u0temp / Denomi;
   W.ueff = ueff;
   T9 = -ueff / Denomi;
-  const double dueff_dVg = T9 * dDenomi_dVg;
-  const double dueff_dVd = T9 * dDenomi_dVd;
-  const double dueff_dVb = T9 * dDenomi_dVb;
+  const real dueff_dVg = T9 * dDenomi_dVg;
+  const real dueff_dVd = T9 * dDenomi_dVd;
+  const real dueff_dVb = T9 * dDenomi_dVb;
 
   // ---- saturation voltage ------------------------------------------------------
-  const double WVCox = Weff * I.vsattemp * M.coxe;
-  const double WVCoxRds = WVCox * Rds;
-  double Esat = 2.0 * I.vsattemp / ueff;
-  double EsatL = Esat * Leff;
+  const real WVCox = Weff * I.vsattemp * M.coxe;
+  const real WVCoxRds = WVCox * Rds;
+  real Esat = 2.0 * I.vsattemp / ueff;
+  real EsatL = Esat * Leff;
   T0 = -EsatL / ueff;
-  double dEsatL_dVg = T0 * dueff_dVg;
-  double dEsatL_dVd = T0 * dueff_dVd;
-  double dEsatL_dVb = T0 * dueff_dVb;
+  real dEsatL_dVg = T0 * dueff_dVg;
+  real dEsatL_dVd = T0 * dueff_dVd;
+  real dEsatL_dVb = T0 * dueff_dVb;
 
-  double Lambda, dLambda_dVg;
+  real Lambda, dLambda_dVg;
   if (P.a1 == 0.0) {
     Lambda = P.a2;
     dLambda_dVg = 0.0;
@@ -615,8 +615,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dLambda_dVg = 0.5 * P.a1 * (1.0 + T1 / T2);
   }
 
-  const double Vgst2Vtm = Vgsteff + 2.0 * Vtm;
-  double tmp1, tmp2, tmp3;
+  const real Vgst2Vtm = Vgsteff + 2.0 * Vtm;
+  real tmp1, tmp2, tmp3;
   if (Rds > 0) {
     tmp2 = dRds_dVg / Rds + dWeff_dVg / Weff;
     tmp3 = dRds_dVb / Rds + dWeff_dVb / Weff;
@@ -624,7 +624,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     tmp2 = dWeff_dVg / Weff;
     tmp3 = dWeff_dVb / Weff;
   }
-  double Vdsat, dVdsat_dVg, dVdsat_dVd, dVdsat_dVb;
+  real Vdsat, dVdsat_dVg, dVdsat_dVd, dVdsat_dVb;
   if ((Rds == 0.0) && (Lambda == 1.0)) {
     T0 = 1.0 / (Abulk * EsatL + Vgst2Vtm);
     tmp1 = 0.0;
@@ -669,7 +669,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.Vdsat = Vdsat;
 
   // ---- effective Vds -------------------------------------------------------------
-  double Vdseff, dVdseff_dVg, dVdseff_dVd, dVdseff_dVb;
+  real Vdseff, dVdseff_dVg, dVdseff_dVd, dVdseff_dVb;
   T1 = Vdsat - Vds - P.delta;
   dT1_dVg = dVdsat_dVg;
   dT1_dVd = dVdsat_dVd - 1.0;
@@ -701,7 +701,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVdseff_dVb = 0.0;
   }
   if (Vdseff > Vds) Vdseff = Vds;
-  const double diffVds = Vds - Vdseff;
+  const real diffVds = Vds - Vdseff;
   W.Vdseff = Vdseff;
 
   // ---- velocity overshoot (lambda) ------------------------------------------------
@@ -741,9 +741,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.EsatL = EsatL;
 
   // ---- Vasat -------------------------------------------------------------------
-  double Vasat, dVasat_dVg, dVasat_dVb, dVasat_dVd;
+  real Vasat, dVasat_dVg, dVasat_dVb, dVasat_dVd;
   {
-    const double tmp4 = 1.0 - 0.5 * Abulk * Vdsat / Vgst2Vtm;
+    const real tmp4 = 1.0 - 0.5 * Abulk * Vdsat / Vgst2Vtm;
     T9 = WVCoxRds * Vgsteff;
     T8 = T9 / Vgst2Vtm;
     T0 = EsatL + Vdsat + 2.0 * T9 * tmp4;
@@ -764,8 +764,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- effective oxide capacitance and channel conductance ---------------------------
-  double Idl, dIdl_dVg, dIdl_dVd, dIdl_dVb, dCoxeff_dVg;
-  double beta, dbeta_dVg, dbeta_dVd, dbeta_dVb, CoxeffWovL;
+  real Idl, dIdl_dVg, dIdl_dVd, dIdl_dVb, dCoxeff_dVg;
+  real beta, dbeta_dVg, dbeta_dVd, dbeta_dVb, CoxeffWovL;
   {
     tmp1 = I.vtfbphi2;
     tmp2 = 2.0e8 * I.toxp;
@@ -774,9 +774,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     tmp3 = exp(M.bdos * 0.7 * log(T0));
     T1 = 1.0 + tmp3;
     T2 = M.bdos * 0.7 * tmp3 / T0;
-    const double Tcen = M.ados * 1.9e-9 / T1;
-    const double dTcen_dVg = -Tcen * T2 * dT0_dVg / T1;
-    const double Coxeff = epssub * I.coxp / (epssub + I.coxp * Tcen);
+    const real Tcen = M.ados * 1.9e-9 / T1;
+    const real dTcen_dVg = -Tcen * T2 * dT0_dVg / T1;
+    const real Coxeff = epssub * I.coxp / (epssub + I.coxp * Tcen);
     W.Coxeff = Coxeff;
     dCoxeff_dVg = -Coxeff * Coxeff * dTcen_dVg / epssub;
     CoxeffWovL = Coxeff * Weff / Leff;
@@ -792,19 +792,19 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT0_dVg = -0.5 * (Abulk * dVdseff_dVg - Abulk * Vdseff / Vgst2Vtm + Vdseff * dAbulk_dVg) / Vgst2Vtm;
     dT0_dVd = -0.5 * Abulk * dVdseff_dVd / Vgst2Vtm;
     dT0_dVb = -0.5 * (Abulk * dVdseff_dVb + dAbulk_dVb * Vdseff) / Vgst2Vtm;
-    const double fgche1 = Vgsteff * T0;
-    const double dfgche1_dVg = Vgsteff * dT0_dVg + T0;
-    const double dfgche1_dVd = Vgsteff * dT0_dVd;
-    const double dfgche1_dVb = Vgsteff * dT0_dVb;
+    const real fgche1 = Vgsteff * T0;
+    const real dfgche1_dVg = Vgsteff * dT0_dVg + T0;
+    const real dfgche1_dVd = Vgsteff * dT0_dVd;
+    const real dfgche1_dVb = Vgsteff * dT0_dVb;
     T9 = Vdseff / EsatL;
-    const double fgche2 = 1.0 + T9;
-    const double dfgche2_dVg = (dVdseff_dVg - T9 * dEsatL_dVg) / EsatL;
-    const double dfgche2_dVd = (dVdseff_dVd - T9 * dEsatL_dVd) / EsatL;
-    const double dfgche2_dVb = (dVdseff_dVb - T9 * dEsatL_dVb) / EsatL;
-    const double gche = beta * fgche1 / fgche2;
-    const double dgche_dVg = (beta * dfgche1_dVg + fgche1 * dbeta_dVg - gche * dfgche2_dVg) / fgche2;
-    const double dgche_dVd = (beta * dfgche1_dVd + fgche1 * dbeta_dVd - gche * dfgche2_dVd) / fgche2;
-    const double dgche_dVb = (beta * dfgche1_dVb + fgche1 * dbeta_dVb - gche * dfgche2_dVb) / fgche2;
+    const real fgche2 = 1.0 + T9;
+    const real dfgche2_dVg = (dVdseff_dVg - T9 * dEsatL_dVg) / EsatL;
+    const real dfgche2_dVd = (dVdseff_dVd - T9 * dEsatL_dVd) / EsatL;
+    const real dfgche2_dVb = (dVdseff_dVb - T9 * dEsatL_dVb) / EsatL;
+    const real gche = beta * fgche1 / fgche2;
+    const real dgche_dVg = (beta * dfgche1_dVg + fgche1 * dbeta_dVg - gche * dfgche2_dVg) / fgche2;
+    const real dgche_dVd = (beta * dfgche1_dVd + fgche1 * dbeta_dVd - gche * dfgche2_dVd) / fgche2;
+    const real dgche_dVb = (beta * dfgche1_dVb + fgche1 * dbeta_dVb - gche * dfgche2_dVb) / fgche2;
     T0 = 1.0 + gche * Rds;
     Idl = gche / T0;
     T1 = (1.0 - Idl * Rds) / T0;
@@ -815,14 +815,14 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- output-resistance components: FP, PvagTerm, VACLM, VADIBL, VADITS, VASCBE ------
-  double FP, dFP_dVg;
+  real FP, dFP_dVg;
   if (P.fprout <= 0.0) { FP = 1.0; dFP_dVg = 0.0; }
   else {
     T9 = P.fprout * sqrt(Leff) / Vgst2Vtm;
     FP = 1.0 / (1.0 + T9);
     dFP_dVg = FP * FP * T9 / Vgst2Vtm;
   }
-  double PvagTerm, dPvagTerm_dVg, dPvagTerm_dVb, dPvagTerm_dVd;
+  real PvagTerm, dPvagTerm_dVg, dPvagTerm_dVb, dPvagTerm_dVd;
   T8 = P.pvag / EsatL;
   T9 = T8 * Vgsteff;
   if (T9 > -0.9) {
@@ -839,7 +839,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dPvagTerm_dVb = -T9 * dEsatL_dVb;
     dPvagTerm_dVd = -T9 * dEsatL_dVd;
   }
-  double Cclm, dCclm_dVg, dCclm_dVd, dCclm_dVb, VACLM, dVACLM_dVg, dVACLM_dVd, dVACLM_dVb;
+  real Cclm, dCclm_dVg, dCclm_dVd, dCclm_dVb, VACLM, dVACLM_dVg, dVACLM_dVd, dVACLM_dVb;
   if ((P.pclm > kMinExp) && (diffVds > 1.0e-10)) {
     T0 = 1.0 + Rds * Idl;
     dT0_dVg = dRds_dVg * Idl + Rds * dIdl_dVg;
@@ -863,7 +863,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVACLM_dVd = dVACLM_dVg = dVACLM_dVb = 0.0;
     dCclm_dVd = dCclm_dVg = dCclm_dVb = 0.0;
   }
-  double VADIBL, dVADIBL_dVg, dVADIBL_dVd, dVADIBL_dVb;
+  real VADIBL, dVADIBL_dVg, dVADIBL_dVd, dVADIBL_dVb;
   if (P.thetaRout > kMinExp) {
     T8 = Abulk * Vdsat;
     T0 = Vgst2Vtm * T8;
@@ -903,12 +903,12 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     VADIBL = kMaxExp;
     dVADIBL_dVd = dVADIBL_dVg = dVADIBL_dVb = 0.0;
   }
-  const double Va = Vasat + VACLM;
-  const double dVa_dVg = dVasat_dVg + dVACLM_dVg;
-  const double dVa_dVb = dVasat_dVb + dVACLM_dVb;
-  const double dVa_dVd = dVasat_dVd + dVACLM_dVd;
+  const real Va = Vasat + VACLM;
+  const real dVa_dVg = dVasat_dVg + dVACLM_dVg;
+  const real dVa_dVb = dVasat_dVb + dVACLM_dVb;
+  const real dVa_dVd = dVasat_dVd + dVACLM_dVd;
 
-  double VADITS, dVADITS_dVg, dVADITS_dVd;
+  real VADITS, dVADITS_dVg, dVADITS_dVd;
   T0 = P.pditsd * Vds;
   if (T0 > kExpThr) { T1 = kMaxExp; dT1_dVd = 0; }
   else { T1 = exp(T0); dT1_dVd = T1 * P.pditsd; }
@@ -922,7 +922,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     VADITS = kMaxExp;
     dVADITS_dVg = dVADITS_dVd = 0;
   }
-  double VASCBE, dVASCBE_dVg, dVASCBE_dVd, dVASCBE_dVb;
+  real VASCBE, dVASCBE_dVg, dVASCBE_dVd, dVASCBE_dVb;
   if ((P.pscbe2 > 0.0) && (P.pscbe1 >= 0.0)) {
     if (diffVds > P.pscbe1 * P.litl / kExpThr) {
       T0 = P.pscbe1 * P.litl / diffVds;
@@ -941,7 +941,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- Idsa: DIBL, DITS, CLM ----------------------------------------------------------
-  double Idsa, dIdsa_dVg, dIdsa_dVd, dIdsa_dVb;
+  real Idsa, dIdsa_dVg, dIdsa_dVd, dIdsa_dVb;
   T9 = diffVds / VADIBL;
   T0 = 1.0 + T9;
   Idsa = Idl * T0;
@@ -969,9 +969,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   Idsa *= T9;
 
   // ---- substrate current ----------------------------------------------------------------
-  double Isub, Gbd, Gbb, Gbg;
+  real Isub, Gbd, Gbb, Gbg;
   {
-    const double tmp = P.alpha0 + P.alpha1 * Leff;
+    const real tmp = P.alpha0 + P.alpha1 * Leff;
     if ((tmp <= 0.0) || (P.beta0 <= 0.0)) {
       Isub = Gbd = Gbb = Gbg = 0.0;
     } else {
@@ -1004,7 +1004,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.csub = Isub; W.gbbs = Gbb; W.gbgs = Gbg; W.gbds = Gbd;
 
   // ---- drain current with SCBE; chain rule back to terminal voltages ---------------------
-  double Ids, Gm, Gds, Gmb;
+  real Ids, Gm, Gds, Gmb;
   T9 = diffVds / VASCBE;
   T0 = 1.0 + T9;
   Ids = Idsa * T0;
@@ -1017,20 +1017,20 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   Gm = (Ids * dVdseff_dVg + Vdseff * tmp3) * dVgsteff_dVg;
   Gds = Ids * (dVdseff_dVd + dVdseff_dVg * dVgsteff_dVd) + Vdseff * tmp1;
   Gmb = (Ids * (dVdseff_dVb + dVdseff_dVg * dVgsteff_dVb) + Vdseff * tmp2) * dVbseff_dVb;
-  double cdrain = Ids * Vdseff;
+  real cdrain = Ids * Vdseff;
 
   // source-end velocity limit
   if (M.vtlGiven && (M.vtl > 0.0)) {
     T12 = 1.0 / Leff / CoxeffWovL;
     T11 = T12 / Vgsteff;
     T10 = -T11 / Vgsteff;
-    const double vs = cdrain * T11;
-    const double dvs_dVg = Gm * T11 + cdrain * T10 * dVgsteff_dVg;
-    const double dvs_dVd = Gds * T11 + cdrain * T10 * dVgsteff_dVd;
-    const double dvs_dVb = Gmb * T11 + cdrain * T10 * dVgsteff_dVb;
+    const real vs = cdrain * T11;
+    const real dvs_dVg = Gm * T11 + cdrain * T10 * dVgsteff_dVg;
+    const real dvs_dVd = Gds * T11 + cdrain * T10 * dVgsteff_dVd;
+    const real dvs_dVb = Gmb * T11 + cdrain * T10 * dVgsteff_dVb;
     T0 = 2 * kMM;
     T1 = vs / (P.vtl * P.tfactor);
-    double Fsevl, dFsevl_dVg, dFsevl_dVd, dFsevl_dVb;
+    real Fsevl, dFsevl_dVg, dFsevl_dVd, dFsevl_dVb;
     if (T1 > 0.0) {
       T2 = 1.0 + exp(T0 * log(T1));
       T3 = (T2 - 1.0) * T0 / vs;
@@ -1080,25 +1080,25 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
 
   // ---- bias-dependent source / drain resistance (rdsMod) --------------------------------------
   if (M.rdsMod) {
-    double dgstot_dvd, dgstot_dvg, dgstot_dvs, dgstot_dvb;
-    double dgdtot_dvd, dgdtot_dvg, dgdtot_dvs, dgdtot_dvb;
+    real dgstot_dvd, dgstot_dvg, dgstot_dvs, dgstot_dvb;
+    real dgdtot_dvd, dgdtot_dvg, dgdtot_dvs, dgdtot_dvb;
     T0 = W.vgs - P.vfbsd;
     T1 = sqrt(T0 * T0 + 1.0e-4);
     W.vgs_eff = 0.5 * (T0 + T1);
     W.dvgs_eff_dvg = W.vgs_eff / T1;
     T0 = 1.0 + P.prwg * W.vgs_eff;
-    double dT0_dvg = -P.prwg / T0 / T0 * W.dvgs_eff_dvg;
+    real dT0_dvg = -P.prwg / T0 / T0 * W.dvgs_eff_dvg;
     T1 = -P.prwb * W.vbs;
-    double dT1_dvb = -P.prwb;
+    real dT1_dvb = -P.prwb;
     T2 = 1.0 / T0 + T1;
     T3 = T2 + sqrt(T2 * T2 + 0.01);
-    double dT3_dvg = T3 / (T3 - T2);
-    double dT3_dvb = dT3_dvg * dT1_dvb;
+    real dT3_dvg = T3 / (T3 - T2);
+    real dT3_dvb = dT3_dvg * dT1_dvb;
     dT3_dvg *= dT0_dvg;
     T4 = P.rs0 * 0.5;
-    const double Rs = P.rswmin + T3 * T4;
-    const double dRs_dvg = T4 * dT3_dvg;
-    const double dRs_dvb = T4 * dT3_dvb;
+    const real Rs = P.rswmin + T3 * T4;
+    const real dRs_dvg = T4 * dT3_dvg;
+    const real dRs_dvb = T4 * dT3_dvb;
     T0 = 1.0 + I.sourceConductance * Rs;
     W.gstot = I.sourceConductance / T0;
     T0 = -W.gstot * W.gstot;
@@ -1121,9 +1121,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT3_dvb = dT3_dvg * dT1_dvb;
     dT3_dvg *= dT0_dvg;
     T4 = P.rd0 * 0.5;
-    const double Rd = P.rdwmin + T3 * T4;
-    const double dRd_dvg = T4 * dT3_dvg;
-    const double dRd_dvb = T4 * dT3_dvb;
+    const real Rd = P.rdwmin + T3 * T4;
+    const real dRd_dvg = T4 * dT3_dvg;
+    const real dRd_dvb = T4 * dT3_dvb;
     T0 = 1.0 + I.drainConductance * Rd;
     W.gdtot = I.drainConductance / T0;
     T0 = -W.gdtot * W.gdtot;
@@ -1151,7 +1151,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   // ---- GIDL / GISL ----------------------------------------------------------------------------
   {
     T0 = (M.mtrlMod == 0) ? 3.0 * toxe : M.epsrsub * toxe / epsrox;
-    const double voff = (M.mtrlMod == 0) ? 0.0 : P.vfbsd;
+    const real voff = (M.mtrlMod == 0) ? 0.0 : P.vfbsd;
     if (M.gidlMod == 0) {
       T1 = (M.mtrlMod == 0) ? (W.vds - W.vgs_eff - P.egidl) / T0
                             : (W.vds - W.vgs_eff - P.egidl + P.vfbsd) / T0;
@@ -1175,13 +1175,13 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   // ---- gate direct-tunnelling currents ------------------------------------------------------------
-  double Vfbeff = 0.0, dVfbeff_dVg = 0.0, dVfbeff_dVb = 0.0;
-  double Voxacc = 0.0, dVoxacc_dVg = 0.0, dVoxacc_dVb = 0.0;
-  double Voxdepinv = 0.0, dVoxdepinv_dVg = 0.0, dVoxdepinv_dVd = 0.0, dVoxdepinv_dVb = 0.0;
-  double Vfb = 0.0;
+  real Vfbeff = 0.0, dVfbeff_dVg = 0.0, dVfbeff_dVb = 0.0;
+  real Voxacc = 0.0, dVoxacc_dVg = 0.0, dVoxacc_dVb = 0.0;
+  real Voxdepinv = 0.0, dVoxdepinv_dVg = 0.0, dVoxdepinv_dVd = 0.0, dVoxdepinv_dVb = 0.0;
+  real Vfb = 0.0;
   if ((M.igcMod != 0) || (M.igbMod != 0)) {
     Vfb = I.vfbzb;
-    const double V3 = Vfb - Vgs_eff + Vbseff - kDelta3;
+    const real V3 = Vfb - Vgs_eff + Vbseff - kDelta3;
     if (Vfb <= 0.0) T0 = sqrt(V3 * V3 - 4.0 * kDelta3 * Vfb);
     else T0 = sqrt(V3 * V3 + 4.0 * kDelta3 * Vfb);
     T1 = 0.5 * (1.0 + V3 / T0);
@@ -1215,9 +1215,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVoxdepinv_dVd += dVgsteff_dVd;
     dVoxdepinv_dVb += dVgsteff_dVb;
   }
-  const double vtm_ig = (M.tempMod < 2) ? Vtm : Vtm0;
+  const real vtm_ig = (M.tempMod < 2) ? Vtm : Vtm0;
   if (M.igcMod) {
-    double VxNVt = 0.0, Vaux = 0.0, dVaux_dVg = 0.0, dVaux_dVd = 0.0, dVaux_dVb = 0.0;
+    real VxNVt = 0.0, Vaux = 0.0, dVaux_dVg = 0.0, dVaux_dVd = 0.0, dVaux_dVb = 0.0;
     T0 = vtm_ig * P.nigc;
     if (M.igcMod == 1) {
       VxNVt = (Vgs_eff - M.dtype * I.vth0) / T0;
@@ -1236,7 +1236,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       Vaux = T0 * log(1.0 + kMinExp);
       dVaux_dVg = dVaux_dVd = dVaux_dVb = 0.0;
     } else if ((VxNVt >= -kExpThr) && (VxNVt <= kExpThr)) {
-      const double ExpVxNVt = exp(VxNVt);
+      const real ExpVxNVt = exp(VxNVt);
       Vaux = T0 * log(1.0 + ExpVxNVt);
       dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
       if (M.igcMod == 1) { dVaux_dVd = 0.0; dVaux_dVb = 0.0; }
@@ -1261,11 +1261,11 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       dT6_dVb = dT6_dVg * dVoxdepinv_dVb;
       dT6_dVg *= dVoxdepinv_dVg;
     }
-    const double Igc = T11 * T2 * T6;
-    const double dIgc_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
-    const double dIgc_dVd = T11 * (T2 * dT6_dVd + T6 * dT2_dVd);
-    const double dIgc_dVb = T11 * (T2 * dT6_dVb + T6 * dT2_dVb);
-    double Pigcd, dPigcd_dVg, dPigcd_dVd, dPigcd_dVb;
+    const real Igc = T11 * T2 * T6;
+    const real dIgc_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
+    const real dIgc_dVd = T11 * (T2 * dT6_dVd + T6 * dT2_dVd);
+    const real dIgc_dVb = T11 * (T2 * dT6_dVb + T6 * dT2_dVb);
+    real Pigcd, dPigcd_dVg, dPigcd_dVd, dPigcd_dVb;
     if (M.pigcdGiven) {
       Pigcd = P.pigcd;
       dPigcd_dVg = dPigcd_dVd = dPigcd_dVb = 0.0;
@@ -1303,18 +1303,18 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT10_dVd = (dT9_dVd - dT7_dVd - T10 * dT8_dVd) / T8;
     dT10_dVb = (dT9_dVb - dT7_dVb - T10 * dT8_dVb) / T8;
     W.Igcs = Igc * T10;
-    const double dIgcs_dVg = dIgc_dVg * T10 + Igc * dT10_dVg;
-    const double dIgcs_dVd = dIgc_dVd * T10 + Igc * dT10_dVd;
-    const double dIgcs_dVb = dIgc_dVb * T10 + Igc * dT10_dVb;
+    const real dIgcs_dVg = dIgc_dVg * T10 + Igc * dT10_dVg;
+    const real dIgcs_dVd = dIgc_dVd * T10 + Igc * dT10_dVd;
+    const real dIgcs_dVb = dIgc_dVb * T10 + Igc * dT10_dVb;
     T1 = T9 - 1.0 - 1.0e-4;
     T10 = (T7 * T9 - T1) / T8;
     dT10_dVg = (dT7_dVg * T9 + (T7 - 1.0) * dT9_dVg - T10 * dT8_dVg) / T8;
     dT10_dVd = (dT7_dVd * T9 + (T7 - 1.0) * dT9_dVd - T10 * dT8_dVd) / T8;
     dT10_dVb = (dT7_dVb * T9 + (T7 - 1.0) * dT9_dVb - T10 * dT8_dVb) / T8;
     W.Igcd = Igc * T10;
-    const double dIgcd_dVg = dIgc_dVg * T10 + Igc * dT10_dVg;
-    const double dIgcd_dVd = dIgc_dVd * T10 + Igc * dT10_dVd;
-    const double dIgcd_dVb = dIgc_dVb * T10 + Igc * dT10_dVb;
+    const real dIgcd_dVg = dIgc_dVg * T10 + Igc * dT10_dVg;
+    const real dIgcd_dVd = dIgc_dVd * T10 + Igc * dT10_dVd;
+    const real dIgcd_dVb = dIgc_dVb * T10 + Igc * dT10_dVb;
     W.gIgcsg = dIgcs_dVg; W.gIgcsd = dIgcs_dVd; W.gIgcsb = dIgcs_dVb * dVbseff_dVb;
     W.gIgcdg = dIgcd_dVg; W.gIgcdd = dIgcd_dVd; W.gIgcdb = dIgcd_dVb * dVbseff_dVb;
 
@@ -1333,8 +1333,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     else if (T5 < -kExpThr) { T6 = kMinExp; dT6_dVg = 0.0; }
     else { T6 = exp(T5); dT6_dVg = T6 * T12 * (T3 - 2.0 * T4 * W.vgs_eff) * W.dvgs_eff_dvg; }
     W.Igs = T11 * T2 * T6;
-    const double dIgs_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
-    const double dIgs_dVs = -dIgs_dVg;
+    const real dIgs_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
+    const real dIgs_dVs = -dIgs_dVg;
 
     T0 = W.vgd - (P.vfbsd + P.vfbsdoff);
     W.vgd_eff = sqrt(T0 * T0 + 1.0e-4);
@@ -1349,8 +1349,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     else if (T5 < -kExpThr) { T6 = kMinExp; dT6_dVg = 0.0; }
     else { T6 = exp(T5); dT6_dVg = T6 * T12 * (T3 - 2.0 * T4 * W.vgd_eff) * W.dvgd_eff_dvg; }
     W.Igd = T11 * T2 * T6;
-    const double dIgd_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
-    const double dIgd_dVd = -dIgd_dVg;
+    const real dIgd_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
+    const real dIgd_dVd = -dIgd_dVg;
     W.gIgsg = dIgs_dVg; W.gIgss = dIgs_dVs;
     W.gIgdg = dIgd_dVg; W.gIgdd = dIgd_dVd;
   } else {
@@ -1361,14 +1361,14 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
 
   if (M.igbMod) {
-    double VxNVt, Vaux, dVaux_dVg, dVaux_dVd, dVaux_dVb;
+    real VxNVt, Vaux, dVaux_dVg, dVaux_dVd, dVaux_dVb;
     T0 = vtm_ig * P.nigbacc;
     T1 = -Vgs_eff + Vbseff + Vfb;
     VxNVt = T1 / T0;
     if (VxNVt > kExpThr) { Vaux = T1; dVaux_dVg = -dVgs_eff_dVg; dVaux_dVb = 1.0; }
     else if (VxNVt < -kExpThr) { Vaux = T0 * log(1.0 + kMinExp); dVaux_dVg = dVaux_dVb = 0.0; }
     else {
-      const double ExpVxNVt = exp(VxNVt);
+      const real ExpVxNVt = exp(VxNVt);
       Vaux = T0 * log(1.0 + ExpVxNVt);
       dVaux_dVb = ExpVxNVt / (1.0 + ExpVxNVt);
       dVaux_dVg = -dVaux_dVb * dVgs_eff_dVg;
@@ -1389,9 +1389,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       dT6_dVb = dT6_dVg * dVoxacc_dVb;
       dT6_dVg *= dVoxacc_dVg;
     }
-    const double dIgbacc_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
-    const double dIgbacc_dVb = T11 * (T2 * dT6_dVb + T6 * dT2_dVb);
-    const double Igbacc = T11 * T2 * T6;
+    const real dIgbacc_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
+    const real dIgbacc_dVb = T11 * (T2 * dT6_dVb + T6 * dT2_dVb);
+    const real Igbacc = T11 * T2 * T6;
 
     T0 = vtm_ig * P.nigbinv;
     T1 = Voxdepinv - P.eigbinv;
@@ -1403,7 +1403,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       Vaux = T0 * log(1.0 + kMinExp);
       dVaux_dVg = dVaux_dVd = dVaux_dVb = 0.0;
     } else {
-      const double ExpVxNVt = exp(VxNVt);
+      const real ExpVxNVt = exp(VxNVt);
       Vaux = T0 * log(1.0 + ExpVxNVt);
       dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
       dVaux_dVd = dVaux_dVg * dVoxdepinv_dVd;
@@ -1428,10 +1428,10 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       dT6_dVb = dT6_dVg * dVoxdepinv_dVb;
       dT6_dVg *= dVoxdepinv_dVg;
     }
-    const double Igbinv = T11 * T2 * T6;
-    const double dIgbinv_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
-    const double dIgbinv_dVd = T11 * (T2 * dT6_dVd + T6 * dT2_dVd);
-    const double dIgbinv_dVb = T11 * (T2 * dT6_dVb + T6 * dT2_dVb);
+    const real Igbinv = T11 * T2 * T6;
+    const real dIgbinv_dVg = T11 * (T2 * dT6_dVg + T6 * dT2_dVg);
+    const real dIgbinv_dVd = T11 * (T2 * dT6_dVd + T6 * dT2_dVd);
+    const real dIgbinv_dVb = T11 * (T2 * dT6_dVb + T6 * dT2_dVb);
     W.Igb = Igbinv + Igbacc;
     W.gIgbg = dIgbinv_dVg + dIgbacc_dVg;
     W.gIgbd = dIgbinv_dVd;
@@ -1442,7 +1442,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
 
   // ---- multi-finger scaling ------------------------------------------------------------------------
   if (I.nf != 1.0) {
-    const double nf = I.nf;
+    const real nf = I.nf;
     W.cdrain *= nf; W.gds *= nf; W.gm *= nf; W.gmbs *= nf; W.IdovVds *= nf;
     W.gbbs *= nf; W.gbgs *= nf; W.gbds *= nf; W.csub *= nf;
     W.Igidl *= nf; W.ggidld *= nf; W.ggidlg *= nf; W.ggidlb *= nf;

@@ -19,7 +19,7 @@ XB_HD int old_source(const SolverFlags &S) {
 
 template <class E>
 XB_HD void evaluate(const SolverFlags &S, const B4Model &M, const B4Size &P, const B4Inst &I,
-                    const double *V, const double *sto_old, bool have_old, double von_prev,
+                    const real *V, const real *sto_old, bool have_old, real von_prev,
                     B4Mid &W, E &e) {
   DcCarry C;
   stage_voltages(S, M, I, V, sto_old, have_old, von_prev, W);

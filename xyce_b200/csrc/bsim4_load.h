@@ -24,17 +24,17 @@ namespace b4 {
 // Terminal currents through the optional series resistances, final terminal
 // charges and the capacitance set of the "new DAE" formulation.
 XB_HD void stage_caps(const B4Model &M, const B4Size &P, const B4Inst &I, B4Mid &W) {
-  const double cgdo = W.cgdo, cgso = W.cgso, cgbo = P.cgbo;
+  const real cgdo = W.cgdo, cgso = W.cgso, cgbo = P.cgbo;
   // ---- terminal charges (setupCapacitors_oldDAE, trnqsMod == 0 branch) ----
   if (W.mode > 0) {
     W.qdrn -= W.qgdo;
     if (I.rgateMod == 3) {
-      const double qgmb = cgbo * W.vgmb;
+      const real qgmb = cgbo * W.vgmb;
       W.qgmid = W.qgdo + W.qgso + qgmb;
       W.qbulk -= qgmb;
       W.qsrc = -(W.qgate + W.qgmid + W.qbulk + W.qdrn);
     } else {
-      const double qgb = cgbo * W.vgb;
+      const real qgb = cgbo * W.vgb;
       W.qgate += W.qgdo + W.qgso + qgb;
       W.qbulk -= qgb;
       W.qsrc = -(W.qgate + W.qbulk + W.qdrn);
@@ -42,12 +42,12 @@ XB_HD void stage_caps(const B4Model &M, const B4Size &P, const B4Inst &I, B4Mid 
   } else {
     W.qsrc = W.qdrn - W.qgso;
     if (I.rgateMod == 3) {
-      const double qgmb = cgbo * W.vgmb;
+      const real qgmb = cgbo * W.vgmb;
       W.qgmid = W.qgdo + W.qgso + qgmb;
       W.qbulk -= qgmb;
       W.qdrn = -(W.qgate + W.qgmid + W.qbulk + W.qsrc);
     } else {
-      const double qgb = cgbo * W.vgb;
+      const real qgb = cgbo * W.vgb;
       W.qgate += W.qgdo + W.qgso + qgb;
       W.qbulk -= qgb;
       W.qdrn = -(W.qgate + W.qbulk + W.qsrc);
@@ -57,12 +57,12 @@ XB_HD void stage_caps(const B4Model &M, const B4Size &P, const B4Inst &I, B4Mid 
   // ---- capacitances (setupCapacitors_newDAE, trnqsMod == 0 branch) ----
   // Forward-frame intrinsic blocks; reverse mode swaps the drain/source roles.
   const bool fwd = (W.mode > 0);
-  const double g_d = fwd ? W.cgdb : W.cgsb;           // gate row, column "drain"
-  const double g_s = fwd ? W.cgsb : W.cgdb;
-  const double b_d = fwd ? W.cbdb : W.cbsb;
-  const double b_s = fwd ? W.cbsb : W.cbdb;
-  const double Xg = -(W.cggb + W.cbgb + W.cdgb);      // "source-like" row of the intrinsic block
-  const double Xd = -(W.cgdb + W.cbdb + W.cddb);
+  const real g_d = fwd ? W.cgdb : W.cgsb;           // gate row, column "drain"
+  const real g_s = fwd ? W.cgsb : W.cgdb;
+  const real b_d = fwd ? W.cbdb : W.cbsb;
+  const real b_s = fwd ? W.cbsb : W.cbdb;
+  const real Xg = -(W.cggb + W.cbgb + W.cdgb);      // "source-like" row of the intrinsic block
+  const real Xd = -(W.cgdb + W.cbdb + W.cddb);
   if (I.rgateMod == 3) {
     W.CAPcgmgmb = (cgdo + cgso + cgbo);
     W.CAPcgmdb = -cgdo;
@@ -154,10 +154,10 @@ XB_HD void stage_caps(const B4Model &M, const B4Size &P, const B4Inst &I, B4Mid 
 // Equivalent currents, limiter (Jdxp) terms and the mode-dependent conductance
 // bookkeeping of setupFVectorVars.
 XB_HD void stage_fvars(const B4Model &M, const B4Inst &I, B4Mid &W) {
-  const double ty = (double)M.dtype;
-  const double dvds = W.vds - W.vds_orig, dvgs = W.vgs - W.vgs_orig, dvbs = W.vbs - W.vbs_orig;
-  const double dvgd = W.vgd - W.vgd_orig, dvbd = W.vbd - W.vbd_orig;
-  double T0 = 0.0;
+  const real ty = real(M.dtype);
+  const real dvds = W.vds - W.vds_orig, dvgs = W.vgs - W.vgs_orig, dvbs = W.vbs - W.vbs_orig;
+  const real dvgd = W.vgd - W.vgd_orig, dvbd = W.vbd - W.vbd_orig;
+  real T0 = 0.0;
   W.ceqgcrg_Jdxp = 0.0;
   if (W.mode >= 0) {
     W.Gm = W.gm;
@@ -272,7 +272,7 @@ XB_HD void stage_fvars(const B4Model &M, const B4Inst &I, B4Mid &W) {
       W.ceqgcrg = 0.0;
       W.ceqgcrg_Jdxp = -(W.gcrgd * dvds + W.gcrgg * dvgs + W.gcrgb * dvbs);
     } else {
-      const double tmp_gcrgd = W.gcrgd;
+      const real tmp_gcrgd = W.gcrgd;
       W.gcrgd = W.gcrgs * T0;
       W.gcrgg = W.gcrgg * T0;
       W.gcrgs = tmp_gcrgd * T0;
@@ -317,7 +317,7 @@ XB_HD void stage_fvars(const B4Model &M, const B4Inst &I, B4Mid &W) {
   W.Qeqqg_Jdxp = W.Qeqqd_Jdxp = W.Qeqqb_Jdxp = 0.0;
   W.Qeqqgmid_Jdxp = W.Qeqqjs_Jdxp = W.Qeqqjd_Jdxp = 0.0;
   if (W.ChargeComputationNeeded && !W.origFlag) {
-    const double dvgb = W.vgb - W.vgb_orig, dvgmb = W.vgmb - W.vgmb_orig;
+    const real dvgb = W.vgb - W.vgb_orig, dvgmb = W.vgmb - W.vgmb_orig;
     W.Qeqqg_Jdxp = -W.CAPcggb * dvgb + W.CAPcgdb * dvbd + W.CAPcgsb * dvbs;
     W.Qeqqd_Jdxp = -W.CAPcdgb * dvgb - W.CAPcdgmb * dvgmb + (W.CAPcddb + W.CAPcdbdb) * dvbd
                    - W.CAPcdbdb * (W.vbd_jct - W.vbd_jct_orig) + W.CAPcdsb * dvbs;
@@ -333,12 +333,12 @@ XB_HD void stage_fvars(const B4Model &M, const B4Inst &I, B4Mid &W) {
 
 // ---------------------------------------------------------------------------
 // Emission.  `E` provides:
-//   template<int ROW>  void f(double), q(double), fl(double), ql(double)   (+=)
-//   template<int SLOT> void jf(double), jq(double)                          (+=)
+//   template<int ROW>  void f(real), q(real), fl(real), ql(real)   (+=)
+//   template<int SLOT> void jf(real), jq(real)                          (+=)
 // ---------------------------------------------------------------------------
 template <class E>
 XB_HD void emit_vectors(const SolverFlags &S, const B4Model &M, const B4Inst &I, const B4Mid &W, E &e) {
-  const double np = I.numberParallel;
+  const real np = I.numberParallel;
   e.template f<kDP>(-(W.ceqjd - W.ceqbd - W.ceqdrn + W.Idtoteq) * np);
   e.template f<kGP>(-(-(-W.ceqgcrg + W.Igtoteq) * np));
   if (I.rgateMod == 1) {
@@ -401,11 +401,11 @@ XB_HD void emit_vectors(const SolverFlags &S, const B4Model &M, const B4Inst &I,
   }
 
   // charge rows
-  const double sg = (M.dtype > 0) ? 1.0 : -1.0;
-  const double Qg = sg * W.qg, Qd = sg * W.qd, Qb = sg * W.qb;
-  const double Qjs = I.rbodyMod ? sg * W.qbs : 0.0;
-  const double Qjd = I.rbodyMod ? sg * W.qbd : 0.0;
-  const double Qgmid = (I.rgateMod == 3) ? sg * W.qgmid : 0.0;
+  const real sg = (M.dtype > 0) ? 1.0 : -1.0;
+  const real Qg = sg * W.qg, Qd = sg * W.qd, Qb = sg * W.qb;
+  const real Qjs = I.rbodyMod ? sg * W.qbs : 0.0;
+  const real Qjd = I.rbodyMod ? sg * W.qbd : 0.0;
+  const real Qgmid = (I.rgateMod == 3) ? sg * W.qgmid : 0.0;
   e.template q<kDP>(-(-Qd) * np);
   e.template q<kGP>(-(-(Qg) * np));
   if (I.rgateMod == 3) e.template q<kGM>(-(-(+Qgmid) * np));
@@ -436,12 +436,12 @@ XB_HD void emit_vectors(const SolverFlags &S, const B4Model &M, const B4Inst &I,
 
 template <class E>
 XB_HD void emit_matrices(const B4Model &M, const B4Inst &I, const B4Mid &W, E &e) {
-  const double np = I.numberParallel;
-  const double gjbd = (!I.rbodyMod) ? W.gbd : 0.0;
-  const double gjbs = (!I.rbodyMod) ? W.gbs : 0.0;
-  const double gdpr = (!M.rdsMod) ? I.drainConductance : 0.0;
-  const double gspr = (!M.rdsMod) ? I.sourceConductance : 0.0;
-  const double geltd = I.grgeltd;
+  const real np = I.numberParallel;
+  const real gjbd = (!I.rbodyMod) ? W.gbd : 0.0;
+  const real gjbs = (!I.rbodyMod) ? W.gbs : 0.0;
+  const real gdpr = (!M.rdsMod) ? I.drainConductance : 0.0;
+  const real gspr = (!M.rdsMod) ? I.sourceConductance : 0.0;
+  const real geltd = I.grgeltd;
   // trnqsMod == 0: ggt* = 0, T1 = qdef*gtau multiplies ddxpart = 0, dxpart/sxpart irrelevant.
   if (I.rgateMod == 1) {
     e.template jf<sGEge>((geltd) * np);

@@ -14,7 +14,8 @@ struct B4Size  { XB_B4_SIZE_D(XB_DECL_D) };
 struct B4Inst  { XB_B4_INST_D(XB_DECL_D) XB_B4_INST_I(XB_DECL_I) };
 // Every intermediate that outlives one evaluation stage.  Names follow the
 // reference's Instance members so host tests can compare them one by one.
-struct B4Mid   { XB_B4_MID_D(XB_DECL_D) XB_B4_MID_EXTRA_D(XB_DECL_D) XB_B4_MID_I(XB_DECL_I) };
+#define XB_DECL_R(n) real n;
+struct B4Mid   { XB_B4_MID_D(XB_DECL_R) XB_B4_MID_EXTRA_D(XB_DECL_R) XB_B4_MID_I(XB_DECL_I) };
 
 #define XB_COUNT(n) +1
 constexpr int kNumModelD = 0 XB_B4_MODEL_D(XB_COUNT);

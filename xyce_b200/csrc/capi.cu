@@ -37,6 +37,7 @@ struct xgpu_ctx {
   bool own_stream = false;
   std::string err;
   long long launches = 0;
+  int b4_arith = 0, b4_minblocks = 2;   // kernel variant (xgpu_set_option)
 
   int n = 0;
   int64_t nnz = 0;
@@ -88,7 +89,19 @@ cudaError_t upload_map(const GatherMapHost &h, GatherMapDev &d) {
   cudaError_t e;
   if ((e = upload(&d.ptr, h.ptr.data(), h.ptr.size())) != cudaSuccess) return e;
   if ((e = upload(&d.src, h.src.data(), h.src.size())) != cudaSuccess) return e;
-  return upload(&d.long_dst, h.long_dst.data(), h.long_dst.size());
+  if ((e = upload(&d.long_dst, h.long_dst.data(), h.long_dst.size())) != cudaSuccess) return e;
+  std::vector<int64_t> cb;
+  std::vector<int32_t> cslot, lptr(1, 0);
+  for (size_t j = 0; j < h.long_dst.size(); ++j) {
+    const int dst = h.long_dst[j];
+    for (int64_t b = h.ptr[dst]; b < h.ptr[dst + 1]; b += kChunk) { cb.push_back(b); cslot.push_back((int32_t)j); }
+    lptr.push_back((int32_t)cb.size());
+  }
+  d.nchunks = (int)cb.size();
+  if ((e = upload(&d.chunk_begin, cb.data(), cb.size())) != cudaSuccess) return e;
+  if ((e = upload(&d.chunk_dst_slot, cslot.data(), cslot.size())) != cudaSuccess) return e;
+  if ((e = upload(&d.long_chunk_ptr, lptr.data(), lptr.size())) != cudaSuccess) return e;
+  return cudaMalloc((void **)&d.partials, std::max<size_t>(4 * cb.size(), 1) * sizeof(double));
 }
 
 void finish_map(GatherMapHost &m, const std::vector<int64_t> &count) {
@@ -132,7 +145,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
     cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig);
   }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
-  for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); }
+  for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); }
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -146,6 +159,14 @@ int xgpu_set_stream(xgpu_ctx *ctx, void *s) {
   if (ctx->own_stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
   ctx->stream = (cudaStream_t)s;
   return 0;
+}
+
+int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
+  if (!ctx || !name) return 1;
+  const std::string n(name);
+  if (n == "b4_arith" && value >= 0 && value <= 2) { ctx->b4_arith = value; return 0; }
+  if (n == "b4_minblocks" && value >= 2 && value <= 4) { ctx->b4_minblocks = value; return 0; }
+  return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
 
 int xgpu_sync(xgpu_ctx *ctx) {
@@ -429,7 +450,7 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
   a.sol = d_sol; a.next_sta = d_next_sta; a.curr_sta = d_curr_sta; a.next_sto = d_next_sto; a.curr_sto = d_curr_sto;
   for (int p = 0; p < 4; ++p) a.vec_planes[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
   for (int p = 0; p < 2; ++p) a.mat_planes[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
-  for (auto &g : ctx->groups) { launch_b4_group(g.dev, a, ctx->stream); ++ctx->launches; }
+  for (auto &g : ctx->groups) { launch_b4_group(g.dev, a, ctx->b4_arith, ctx->b4_minblocks, ctx->stream); ++ctx->launches; }
   XG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -440,7 +461,7 @@ int xgpu_load_vectors(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_fl, dou
   const double *in[4]; double *out[4] = {d_f, d_q, d_fl, d_ql};
   for (int p = 0; p < 4; ++p) in[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
   launch_gather(ctx->vec_map, 4, in, ctx->vec_plane, out, accumulate != 0, ctx->stream);
-  ctx->launches += 1 + (ctx->vec_map.nlong > 0);
+  ctx->launches += 1 + 2 * (ctx->vec_map.nlong > 0);
   XG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -451,7 +472,7 @@ int xgpu_load_matrices(xgpu_ctx *ctx, double *d_dFdx, double *d_dQdx, int accumu
   const double *in[2]; double *out[2] = {d_dFdx, d_dQdx};
   for (int p = 0; p < 2; ++p) in[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
   launch_gather(ctx->mat_map, 2, in, ctx->mat_plane, out, accumulate != 0, ctx->stream);
-  ctx->launches += 1 + (ctx->mat_map.nlong > 0);
+  ctx->launches += 1 + 2 * (ctx->mat_map.nlong > 0);
   XG_CUDA(cudaGetLastError());
   return 0;
 }

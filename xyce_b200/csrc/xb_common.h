@@ -18,7 +18,16 @@
 #define XB_D inline
 #endif
 
+// Scalar type of all model arithmetic.  The product uses plain double; tests/host_mirror can
+// substitute an operation-counting wrapper (XB_REAL) to measure executed flops per evaluation.
+#ifndef XB_REAL
+#define XB_REAL double
+#endif
+
 namespace xb {
+
+using real = XB_REAL;
+XB_HD double to_double(double v) { return v; }
 
 // ---- physical constants (N_DEV_Const.h) -----------------------------------
 constexpr double kQ        = 1.6021918e-19;
@@ -69,22 +78,22 @@ struct SolverFlags {
 };
 
 // ---- smoothed exponentials (B4p82.C:82-105) --------------------------------
-XB_HD void dexp(double a, double &b, double &c) {
+XB_HD void dexp(real a, real &b, real &c) {
   if (a > kExpThr) { b = kMaxExp * (1.0 + a - kExpThr); c = kMaxExp; }
   else if (a < -kExpThr) { b = kMinExp; c = 0.0; }
   else { b = exp(a); c = b; }
 }
-XB_HD double dexp2(double a) {
+XB_HD real dexp2(real a) {
   if (a > kExpThr) return kMaxExp * (1.0 + a - kExpThr);
   if (a < -kExpThr) return kMinExp;
   return exp(a);
 }
 
-XB_HD double dmax(double a, double b) { return a < b ? b : a; }   // std::max semantics
-XB_HD double dmin(double a, double b) { return b < a ? b : a; }   // std::min semantics
+XB_HD real dmax(real a, real b) { return a < b ? b : a; }   // std::max semantics
+XB_HD real dmin(real a, real b) { return b < a ? b : a; }   // std::min semantics
 
 // ---- SPICE3 Newton limiters (Core/N_DEV_DeviceSupport.C:161-393) ------------
-XB_HD double limvds(double vnew, double vold) {
+XB_HD real limvds(real vnew, real vold) {
   if (vold >= 3.5) {
     if (vnew > vold) vnew = dmin(vnew, 3.0 * vold + 2.0);
     else if (vnew < 3.5) vnew = dmax(vnew, 2.0);
@@ -95,10 +104,10 @@ XB_HD double limvds(double vnew, double vold) {
   return vnew;
 }
 
-XB_HD double pnjlim(double vnew, double vold, double vt, double vcrit, int &icheck) {
+XB_HD real pnjlim(real vnew, real vold, real vt, real vcrit, int &icheck) {
   if ((vnew > vcrit) && (fabs(vnew - vold) > (vt + vt))) {
     if (vold > 0) {
-      double arg = 1 + (vnew - vold) / vt;
+      real arg = 1 + (vnew - vold) / vt;
       vnew = (arg > 0) ? vold + vt * log(arg) : vcrit;
     } else {
       vnew = vt * log(vnew / vt);
@@ -110,11 +119,11 @@ XB_HD double pnjlim(double vnew, double vold, double vt, double vcrit, int &iche
   return vnew;
 }
 
-XB_HD double fetlim(double vnew, double vold, double vto) {
-  const double vtsthi = fabs(2 * (vold - vto)) + 2;
-  const double vtstlo = vtsthi / 2 + 2;
-  const double vtox = vto + 3.5;
-  const double delv = vnew - vold;
+XB_HD real fetlim(real vnew, real vold, real vto) {
+  const real vtsthi = fabs(2 * (vold - vto)) + 2;
+  const real vtstlo = vtsthi / 2 + 2;
+  const real vtox = vto + 3.5;
+  const real delv = vnew - vold;
   if (vold >= vto) {
     if (vold >= vtox) {
       if (delv <= 0) {
@@ -130,7 +139,7 @@ XB_HD double fetlim(double vnew, double vold, double vto) {
     if (delv <= 0) {
       if (-delv > vtsthi) vnew = vold - vtsthi;
     } else {
-      const double vtemp = vto + 0.5;
+      const real vtemp = vto + 0.5;
       if (vnew <= vtemp) { if (delv > vtstlo) vnew = vold + vtstlo; }
       else vnew = vtemp;
     }

@@ -1,0 +1,93 @@
+// xyce_b200 -- alternative scalar types for the single-source model evaluators.
+//   xb::CountReal   host only: counts executed fp64 operations (each + - * / sqrt exp log = 1),
+//                   used once to establish the executed-flop figure of the roofline unit U1
+//                   (BASELINE.md section 4).
+//   xb::FastReal    device: identical to double except that a/b is computed as a branch-free
+//                   reciprocal-Newton sequence (1 MUFU + 7 DFMA/DMUL, <= 2 ulp) instead of the
+//                   ~20-instruction IEEE division with its slow-path branch.
+// Include before xb_common.h and define XB_REAL to select one of them.
+#pragma once
+#include <math.h>
+#if defined(__CUDACC__)
+#define XBR_HD __host__ __device__ __forceinline__
+#else
+#define XBR_HD inline
+#endif
+
+namespace xb {
+
+struct OpCounts { unsigned long long add, mul, div, sqrt_, exp_, log_, cmp; };
+#if !defined(__CUDA_ARCH__)
+inline OpCounts &op_counts() { static thread_local OpCounts c{}; return c; }
+#endif
+
+struct CountPolicy {
+#if !defined(__CUDA_ARCH__)
+  static double add(double a, double b) { ++op_counts().add; return a + b; }
+  static double sub(double a, double b) { ++op_counts().add; return a - b; }
+  static double mul(double a, double b) { ++op_counts().mul; return a * b; }
+  static double div(double a, double b) { ++op_counts().div; return a / b; }
+  static double sqrt_(double a) { ++op_counts().sqrt_; return ::sqrt(a); }
+  static double exp_(double a) { ++op_counts().exp_; return ::exp(a); }
+  static double log_(double a) { ++op_counts().log_; return ::log(a); }
+  static void cmp() { ++op_counts().cmp; }
+#endif
+};
+
+struct FastDivPolicy {
+  static XBR_HD double add(double a, double b) { return a + b; }
+  static XBR_HD double sub(double a, double b) { return a - b; }
+  static XBR_HD double mul(double a, double b) { return a * b; }
+  static XBR_HD double div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));     // ~20-bit seed (MUFU.RCP64H)
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);                                           // full-precision reciprocal
+    double q = a * r;
+    const double rem = fma(-b, q, a);
+    return fma(rem, r, q);                                       // one correction step
+#else
+    return a / b;
+#endif
+  }
+  static XBR_HD double sqrt_(double a) { return ::sqrt(a); }
+  static XBR_HD double exp_(double a) { return ::exp(a); }
+  static XBR_HD double log_(double a) { return ::log(a); }
+  static XBR_HD void cmp() {}
+};
+
+template <class P>
+struct RealT {
+  double v;
+  XBR_HD RealT() {}
+  XBR_HD RealT(double x) : v(x) {}
+  XBR_HD RealT &operator+=(const RealT &o) { v = P::add(v, o.v); return *this; }
+  XBR_HD RealT &operator-=(const RealT &o) { v = P::sub(v, o.v); return *this; }
+  XBR_HD RealT &operator*=(const RealT &o) { v = P::mul(v, o.v); return *this; }
+  XBR_HD RealT &operator/=(const RealT &o) { v = P::div(v, o.v); return *this; }
+  friend XBR_HD RealT operator-(const RealT &a) { return RealT(-a.v); }
+  friend XBR_HD RealT operator+(const RealT &a) { return a; }
+  friend XBR_HD RealT operator+(const RealT &a, const RealT &b) { return RealT(P::add(a.v, b.v)); }
+  friend XBR_HD RealT operator-(const RealT &a, const RealT &b) { return RealT(P::sub(a.v, b.v)); }
+  friend XBR_HD RealT operator*(const RealT &a, const RealT &b) { return RealT(P::mul(a.v, b.v)); }
+  friend XBR_HD RealT operator/(const RealT &a, const RealT &b) { return RealT(P::div(a.v, b.v)); }
+  friend XBR_HD bool operator<(const RealT &a, const RealT &b) { P::cmp(); return a.v < b.v; }
+  friend XBR_HD bool operator>(const RealT &a, const RealT &b) { P::cmp(); return a.v > b.v; }
+  friend XBR_HD bool operator<=(const RealT &a, const RealT &b) { P::cmp(); return a.v <= b.v; }
+  friend XBR_HD bool operator>=(const RealT &a, const RealT &b) { P::cmp(); return a.v >= b.v; }
+  friend XBR_HD bool operator==(const RealT &a, const RealT &b) { P::cmp(); return a.v == b.v; }
+  friend XBR_HD bool operator!=(const RealT &a, const RealT &b) { P::cmp(); return a.v != b.v; }
+  friend XBR_HD RealT sqrt(const RealT &a) { return RealT(P::sqrt_(a.v)); }
+  friend XBR_HD RealT exp(const RealT &a) { return RealT(P::exp_(a.v)); }
+  friend XBR_HD RealT log(const RealT &a) { return RealT(P::log_(a.v)); }
+  friend XBR_HD RealT fabs(const RealT &a) { return RealT(::fabs(a.v)); }
+  friend XBR_HD double to_double(const RealT &a) { return a.v; }
+};
+
+using CountReal = RealT<CountPolicy>;
+using FastReal = RealT<FastDivPolicy>;
+
+}  // namespace xb
