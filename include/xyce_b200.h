@@ -36,9 +36,10 @@ const char *xgpu_last_error(const xgpu_ctx *ctx);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
 int xgpu_set_stream(xgpu_ctx *ctx, void *cuda_stream);
 int xgpu_sync(xgpu_ctx *ctx);
-/* Tuning knobs.  "b4_arith": 0 = parity arithmetic (no FMA contraction, IEEE division; default),
- * 1 = FMA contraction, 2 = FMA + branch-free reciprocal division (<= 2 ulp per divide).
- * "b4_minblocks": 2, 3 or 4 resident 128-thread blocks per SM (255 / 168 / 128 registers). */
+/* Tuning knobs.  "b4_arith": 0 = strict arithmetic (no FMA contraction, IEEE division),
+ * 1 = FMA contraction, 2 = FMA + branch-free reciprocal division (<= 2 ulp per divide; default --
+ * validated against the reference at 1e-12 by tests/test_gpu_bsim4_parity.py like the others).
+ * "b4_minblocks": 2, 3 or 4 (default) resident 128-thread blocks per SM (255 / 168 / 128 registers). */
 int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value);
 
 /* ---- linear-system shape ----

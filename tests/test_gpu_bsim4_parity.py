@@ -22,10 +22,12 @@ FLAG_CASES = {
 }
 
 
-def run_case(variant, flags, n_pairs=16, seed=3, store_noise=0.3):
+def run_case(variant, flags, n_pairs=16, seed=3, store_noise=0.3, arith=None):
     assert oracle_ref.available(), "oracle/_ref/libxyce_ref.so must travel with the snapshot"
     ref = isolated_devices(oracle_ref.RefCircuit, n_pairs, variant, seed=seed)
     eng, rec = engine_from_ref(ref)
+    if arith is not None:
+        eng.set_option("b4_arith", arith)
     rng = np.random.default_rng(seed + 100)
     x = rng.uniform(-0.3, 1.3, ref.n)
     nsto = rng.normal(0.3, store_noise, ref.n_sto)
@@ -64,6 +66,13 @@ def test_flag_cases_default_card(case):
 @pytest.mark.parametrize("variant", ["rgate3", "rbody", "rdsmod", "igc"])
 def test_flag_cases_general_topology(variant, case):
     run_case(variant, FLAG_CASES[case])
+
+
+@pytest.mark.parametrize("arith", [0, 1, 2])
+@pytest.mark.parametrize("variant", ["default", "igc", "capmod1", "rgate3", "rbody"])
+def test_every_arithmetic_variant(variant, arith):
+    # 0 strict (no FMA, IEEE division), 1 FMA contraction, 2 FMA + reciprocal division (library default)
+    run_case(variant, FLAG_CASES["tran_iter1"], arith=arith)
 
 
 def test_pass_through_limiters():

@@ -75,6 +75,10 @@ class Engine:
         self.h = h
         self.n = 0
         self.nnz = 0
+        # optional overrides of the kernel variant (see xgpu_set_option in include/xyce_b200.h)
+        for env, opt in (("XYCE_B200_B4_ARITH", "b4_arith"), ("XYCE_B200_B4_MINBLOCKS", "b4_minblocks")):
+            if os.environ.get(env):
+                self.set_option(opt, int(os.environ[env]))
 
     def _chk(self, rc):
         if rc != 0:

@@ -37,7 +37,7 @@ struct xgpu_ctx {
   bool own_stream = false;
   std::string err;
   long long launches = 0;
-  int b4_arith = 0, b4_minblocks = 2;   // kernel variant (xgpu_set_option)
+  int b4_arith = 2, b4_minblocks = 4;   // kernel variant (xgpu_set_option); 0/2 = strict parity arithmetic
 
   int n = 0;
   int64_t nnz = 0;
