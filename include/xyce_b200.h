@@ -104,6 +104,27 @@ int xgpu_all_converged(xgpu_ctx *ctx, int *converged);
 int xgpu_jacobian_combine(xgpu_ctx *ctx, double qscalar, const double *d_dQdx, double fscalar,
                           const double *d_dFdx, double *d_jac);
 
+/* ---- sparse direct solver (KLU-pattern LU) ----
+ * Replaces Linear::AmesosSolver::doSolve with Amesos_Klu (N_LAS_AmesosSolver.C:216-470):
+ *   xgpu_lu_analyze   <- SymbolicFactorization (:335) + the first pivoting NumericFactorization (:363):
+ *                        BTF, per-block fill-reducing ordering, Gilbert-Peierls LU with threshold partial
+ *                        pivoting (tol 0.001, diagonal preferred) on the HOST; fixes pattern + pivot order
+ *   xgpu_lu_refactor  <- NumericFactorization with "Refactorize" (KLU_REPIVOT=0, :316-318) on the GPU
+ *   xgpu_lu_solve     <- Solve (:396) on the GPU
+ * d_vals: the nnz CSR values of the matrix with the pattern given to xgpu_pattern_set/_build.
+ * Return codes: 0 ok, 1 structurally singular, 2 numerically singular (zero/non-finite pivot; the
+ * reference then zeroes the update and warns, :372-388), other = CUDA / usage error.
+ * info[8] (xgpu_lu_info): n, number of BTF blocks, largest block, nnz(L), nnz(U) incl. diagonal,
+ * off-diagonal-block entries, solve levels, refactor flops. */
+int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals);
+int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals);
+int xgpu_lu_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x);
+int xgpu_lu_info(const xgpu_ctx *ctx, double *info8);
+/* Host-only symbolic analysis + pivoting factorization + solve (no GPU, no context): the code path
+ * xgpu_lu_analyze runs on the host, exposed so that CPU-only CI can test it. */
+int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colind, const double *vals,
+                              const double *rhs, double *x, double *info8);
+
 /* ---- host-buffer convenience path (what a non-GPU-aware caller uses; copies inside) ----
  * One updateState + loadDAEVectors + loadDAEMatrices pass.  Vectors have n_unknowns entries,
  * matrices nnz entries; next/curr store and state live in the context between calls. */

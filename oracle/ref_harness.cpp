@@ -400,4 +400,31 @@ void xref_b4_mid(void *h, int idx, double *mid_d, int *mid_i) {
 #undef PUT
 }
 
+// ---- Kundert Sparse 1.3 (reference tree: LinearAlgebraServicesPKG/ksparse) ----
+// Same call sequence as Epetra_CrsKundertSparse (ksparse/Epetra_CrsKundertSparse.C:60-190):
+// spCreate, spGetElement per CSR entry (1-based), spOrderAndFactor, spSolve.
+extern "C" {
+char *spCreate(int, int, int *);
+double *spGetElement(char *, int, int);
+int spOrderAndFactor(char *, double *, double, double, int, int);
+int spSolve(char *, double *, double *, double *, double *);
+void spDestroy(char *);
+}
+int xref_ksparse_solve(int n, const int *rowptr, const int *colind, const double *vals, const double *rhs, double *x) {
+  int err = 0;
+  char *M = spCreate(n, 0, &err);
+  if (err) return 100 + err;
+  for (int i = 0; i < n; ++i)
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) *spGetElement(M, i + 1, colind[k] + 1) = vals[k];
+  // thresholds: N_LAS_KSparseSolver defaults (relative 1e-3, absolute 1e-13, diagonal pivoting on)
+  int rc = spOrderAndFactor(M, 0, 1.0e-3, 1.0e-13, 1, 1);
+  if (!rc) {
+    std::vector<double> b(rhs, rhs + n), s(n);
+    rc = spSolve(M, b.data() - 1, s.data() - 1, 0, 0);
+    std::copy(s.begin(), s.end(), x);
+  }
+  spDestroy(M);
+  return rc;
+}
+
 }  // extern "C"

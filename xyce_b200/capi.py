@@ -195,6 +195,28 @@ class Engine:
         p = C.c_void_p
         self._chk(self.lib.xgpu_jacobian_combine(self.h, qs, p(d_dqdx), fs, p(d_dfdx), p(d_jac)))
 
+    # ---- sparse LU ----
+    def lu_analyze(self, d_vals):
+        rc = self.lib.xgpu_lu_analyze(self.h, C.c_void_p(d_vals))
+        if rc not in (0, 2):
+            self._chk(rc)
+        return rc
+
+    def lu_refactor(self, d_vals):
+        rc = self.lib.xgpu_lu_refactor(self.h, C.c_void_p(d_vals))
+        if rc not in (0, 2):
+            self._chk(rc)
+        return rc
+
+    def lu_solve(self, d_vals, d_rhs, d_x):
+        self._chk(self.lib.xgpu_lu_solve(self.h, C.c_void_p(d_vals), C.c_void_p(d_rhs), C.c_void_p(d_x)))
+
+    def lu_info(self):
+        info = np.zeros(8)
+        self._chk(self.lib.xgpu_lu_info(self.h, _dp(info)))
+        keys = ("n", "blocks", "largest_block", "nnz_L", "nnz_U", "offdiag", "levels", "refactor_flops")
+        return dict(zip(keys, info.tolist()))
+
     def all_converged(self):
         v = C.c_int()
         self._chk(self.lib.xgpu_all_converged(self.h, C.byref(v)))

@@ -12,6 +12,7 @@
 
 #include "assembly.cuh"
 #include "b4_kernels.cuh"
+#include "lu.h"
 
 using namespace xb;
 using namespace xb::b4;
@@ -59,6 +60,11 @@ struct xgpu_ctx {
 
   // context-owned system buffers (host-convenience path)
   double *buf[11] = {nullptr};
+
+  // sparse LU
+  xb::lu::LuPlan lu_plan;
+  xb::lu::LuDev lu_dev;
+  bool lu_ready = false;
 };
 
 namespace {
@@ -148,6 +154,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); }
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
+  xb::lu::free_plan(ctx->lu_dev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -535,6 +542,69 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
   if (h_dFdx) XG_CUDA(cudaMemcpyAsync(h_dFdx, b[5], ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (h_dQdx) XG_CUDA(cudaMemcpyAsync(h_dQdx, b[6], ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
+  if (!ctx || !d_vals) return 100;
+  if (ctx->rowptr.empty()) return fail(ctx, 112, "no CSR pattern");
+  XG_CUDA(cudaSetDevice(ctx->device));
+  std::vector<double> vals((size_t)ctx->nnz);
+  XG_CUDA(cudaMemcpyAsync(vals.data(), d_vals, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int rc = xb::lu::analyze_and_factor(ctx->n, ctx->rowptr.data(), ctx->colind.data(), vals.data(), 0.001, ctx->lu_plan);
+  if (rc == 1) return fail(ctx, 1, "matrix is structurally singular");
+  XG_CUDA(xb::lu::upload_plan(ctx->lu_plan, ctx->lu_dev));
+  ctx->lu_ready = true;
+  if (rc == 2) return fail(ctx, 2, "matrix is numerically singular");
+  return 0;
+}
+
+int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
+  if (!ctx || !d_vals) return 100;
+  if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
+  ctx->launches += xb::lu::launch_refactor(ctx->lu_dev, d_vals, ctx->stream);
+  XG_CUDA(cudaGetLastError());
+  int status = 0;
+  XG_CUDA(cudaMemcpyAsync(&status, ctx->lu_dev.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (status) return fail(ctx, 2, "zero or non-finite pivot during refactorization");
+  return 0;
+}
+
+int xgpu_lu_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x) {
+  if (!ctx || !d_vals || !d_rhs || !d_x) return 100;
+  if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
+  ctx->launches += xb::lu::launch_solve(ctx->lu_dev, d_vals, d_rhs, d_x, ctx->stream);
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colind, const double *vals,
+                              const double *rhs, double *x, double *info) {
+  if (n <= 0 || !rowptr || !colind || !vals || !rhs || !x) return 100;
+  xb::lu::LuPlan p;
+  const int rc = xb::lu::analyze_and_factor(n, rowptr, colind, vals, 0.001, p);
+  if (rc == 1) return 1;
+  xb::lu::solve_host(p, rhs, x);
+  if (info) {
+    int largest = 0;
+    for (size_t b = 0; b + 1 < p.block_ptr.size(); ++b) largest = std::max(largest, p.block_ptr[b + 1] - p.block_ptr[b]);
+    info[0] = p.n; info[1] = (double)p.block_ptr.size() - 1; info[2] = largest; info[3] = (double)p.Li.size();
+    info[4] = (double)p.Ui.size(); info[5] = (double)p.off_row.size(); info[6] = (double)p.level_ptr.size() - 1;
+    info[7] = p.refactor_flops;
+  }
+  return rc;
+}
+
+int xgpu_lu_info(const xgpu_ctx *ctx, double *info) {
+  if (!ctx || !info || !ctx->lu_ready) return 100;
+  const xb::lu::LuPlan &p = ctx->lu_plan;
+  int largest = 0;
+  for (size_t b = 0; b + 1 < p.block_ptr.size(); ++b) largest = std::max(largest, p.block_ptr[b + 1] - p.block_ptr[b]);
+  info[0] = p.n; info[1] = (double)p.block_ptr.size() - 1; info[2] = largest; info[3] = (double)p.Li.size();
+  info[4] = (double)p.Ui.size(); info[5] = (double)p.off_row.size(); info[6] = (double)p.level_ptr.size() - 1;
+  info[7] = p.refactor_flops;
   return 0;
 }
 

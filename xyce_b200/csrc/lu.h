@@ -1,0 +1,69 @@
+// xyce_b200 -- sparse LU: shared data structures of the host symbolic phase (lu_host.cpp) and the
+// GPU refactor / solve kernels (lu.cu).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace xb {
+namespace lu {
+
+// Permuted system  B = P A Q  (position t holds row row_perm[t] and column col_perm[t] of A) is upper
+// block triangular with diagonal blocks [block_ptr[b], block_ptr[b+1]).  Each diagonal block is
+// factored L U with L unit lower (diagonal not stored) and U upper, both CSC over positions; a U
+// column stores its off-diagonal entries in ascending row order followed by the pivot as its LAST
+// entry.  Entries of A outside the diagonal blocks stay unfactored ("off", by column).
+struct LuPlan {
+  int n = 0;
+  int nnz_a = 0;
+  bool structurally_singular = false;
+  bool singular = false;
+  std::vector<int> row_perm, col_perm, block_ptr;
+  std::vector<int> Lp, Li, Up, Ui;
+  std::vector<double> Lx, Ux;               // values of the first (pivoting) factorization
+  // numeric scatter: column t of B inside its block = { (acol_row[q], A.values[acol_src[q]]) }
+  std::vector<int> acol_ptr, acol_row, acol_src;
+  // off-diagonal entries of column t: rows off_row[q] (in earlier blocks), values A.values[off_src[q]]
+  std::vector<int> off_ptr, off_row, off_src;
+  std::vector<double> off_val_host;
+  // the same entries by ROW position (pull form used by the GPU solve): row r needs
+  // sum_q A.values[offr_src[q]] * y[offr_col[q]] over q in [offr_ptr[r], offr_ptr[r+1])
+  std::vector<int> offr_ptr, offr_col, offr_src;
+  // block levels for the solve: blocks in level l depend only on blocks in levels < l
+  std::vector<int> level_ptr, level_blocks;
+  double refactor_flops = 0.0;
+};
+
+// Symbolic analysis + first numeric factorization with threshold partial pivoting (KLU defaults:
+// pivot_tol = 0.001, diagonal preferred).  Returns 0 ok, 1 structurally singular, 2 numerically singular.
+int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol,
+                       LuPlan &plan);
+void solve_host(const LuPlan &plan, const double *b, double *x);
+
+// Device-resident copy of a plan plus work space; created by upload_plan, used by the kernels.
+struct LuDev {
+  int n = 0, nblocks = 0, nlevels = 0;
+  int *row_perm = nullptr, *col_perm = nullptr, *block_ptr = nullptr;
+  int *Lp = nullptr, *Li = nullptr, *Up = nullptr, *Ui = nullptr;
+  double *Lx = nullptr, *Ux = nullptr;
+  int *acol_ptr = nullptr, *acol_row = nullptr, *acol_src = nullptr;
+  int *offr_ptr = nullptr, *offr_col = nullptr, *offr_src = nullptr;
+  int *level_blocks = nullptr;
+  std::vector<int> level_ptr;     // host copy: one launch per level
+  double *work = nullptr;         // [n] dense column / solution work vector
+  int *status = nullptr;          // device flag: != 0 when a zero or non-finite pivot was met
+};
+
+}  // namespace lu
+}  // namespace xb
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+namespace xb {
+namespace lu {
+cudaError_t upload_plan(const LuPlan &p, LuDev &d);
+void free_plan(LuDev &d);
+int launch_refactor(const LuDev &d, const double *d_A, cudaStream_t s);                       // returns #launches
+int launch_solve(const LuDev &d, const double *d_A, const double *d_rhs, double *d_x, cudaStream_t s);
+}  // namespace lu
+}  // namespace xb
+#endif

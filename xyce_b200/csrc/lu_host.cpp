@@ -1,0 +1,426 @@
+// xyce_b200 -- sparse direct solver, host side: the symbolic phase and the first (pivoting)
+// numeric factorization that fix the pattern and pivot sequence the GPU kernels then reuse.
+//
+// What it stands in for: Amesos_Klu::SymbolicFactorization / NumericFactorization as driven by
+// Linear::AmesosSolver::doSolve (src/LinearAlgebraServicesPKG/N_LAS_AmesosSolver.C:216-470).
+// The arithmetic of that path lives in SuiteSparse KLU/BTF/AMD inside Trilinos Amesos, which is
+// NOT part of the reference tree.  This file restates KLU's published algorithm
+// (Davis & Palamadai Natarajan, ACM TOMS 37(3), 2010) from the description, not from source:
+//   1. maximum transversal  -> zero-free diagonal                     (BTF "maxtrans")
+//   2. strongly connected components -> upper block triangular form   (BTF "strongcomp")
+//   3. fill-reducing ordering of each diagonal block (minimum degree on A+A')   (role of AMD)
+//   4. Gilbert-Peierls left-looking LU of each block with threshold partial pivoting that
+//      prefers the diagonal (tol = 0.001, KLU default); off-diagonal blocks are kept unfactored
+//      and used by block back-substitution.
+// The result (LuPlan) is what xgpu_lu_refactor / xgpu_lu_solve consume: klu_refactor semantics
+// (pattern and pivot order reused, "Refactorize = !KLU_REPIVOT", N_LAS_AmesosSolver.C:316-318).
+#include "lu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <queue>
+
+namespace xb {
+namespace lu {
+
+namespace {
+
+// ---- 1. maximum transversal (augmenting-path DFS with cheap assignment) ----
+// Input: CSC pattern (column j has rows Ai[Ap[j]..Ap[j+1])).  Output: match[i] = column matched to row i.
+int max_transversal(int n, const std::vector<int> &Ap, const std::vector<int> &Ai, std::vector<int> &col_of_row) {
+  col_of_row.assign(n, -1);
+  std::vector<int> cheap(Ap.begin(), Ap.end() - 1), seen(n, -1), js(n), is(n), ps(n);
+  int nmatch = 0;
+  for (int k = 0; k < n; ++k) {
+    int head = 0;
+    bool found = false;
+    js[0] = k;
+    while (head >= 0) {
+      const int j = js[head];
+      if (seen[j] != k) {               // first visit of column j in this search
+        seen[j] = k;
+        int p = cheap[j];
+        for (; p < Ap[j + 1] && !found; ++p) {
+          const int i = Ai[p];
+          if (col_of_row[i] == -1) { found = true; is[head] = i; }
+        }
+        cheap[j] = p;
+        if (found) break;
+        ps[head] = Ap[j];
+      }
+      int p = ps[head];
+      for (; p < Ap[j + 1]; ++p) {
+        const int i = Ai[p];
+        if (seen[col_of_row[i]] == k) continue;
+        ps[head] = p + 1;
+        is[head] = i;
+        js[++head] = col_of_row[i];
+        break;
+      }
+      if (p == Ap[j + 1]) --head;
+    }
+    if (found) {
+      for (int h = head; h >= 0; --h) col_of_row[is[h]] = js[h];
+      ++nmatch;
+    }
+  }
+  return nmatch;
+}
+
+// ---- 2. strongly connected components (iterative Tarjan) of the graph with edge j -> i for
+//         every entry (i, j) of the column-permuted matrix (rows already aligned to the diagonal) ----
+// Produces blocks in an order that makes the permuted matrix UPPER block triangular.
+void strong_components(int n, const std::vector<int> &Ap, const std::vector<int> &Ai, std::vector<int> &perm,
+                       std::vector<int> &block_ptr) {
+  std::vector<int> index(n, -1), low(n, 0), onstack(n, 0), st, callstack, pos(n, 0);
+  perm.clear();
+  block_ptr.assign(1, 0);
+  int counter = 0;
+  for (int s = 0; s < n; ++s) {
+    if (index[s] != -1) continue;
+    callstack.push_back(s);
+    index[s] = low[s] = counter++;
+    st.push_back(s); onstack[s] = 1;
+    pos[s] = Ap[s];
+    while (!callstack.empty()) {
+      const int v = callstack.back();
+      if (pos[v] < Ap[v + 1]) {
+        const int w = Ai[pos[v]++];
+        if (index[w] == -1) {
+          index[w] = low[w] = counter++;
+          st.push_back(w); onstack[w] = 1;
+          pos[w] = Ap[w];
+          callstack.push_back(w);
+        } else if (onstack[w]) {
+          low[v] = std::min(low[v], index[w]);
+        }
+      } else {
+        callstack.pop_back();
+        if (!callstack.empty()) low[callstack.back()] = std::min(low[callstack.back()], low[v]);
+        if (low[v] == index[v]) {
+          int w;
+          do {
+            w = st.back(); st.pop_back(); onstack[w] = 0;
+            perm.push_back(w);
+          } while (w != v);
+          block_ptr.push_back((int)perm.size());
+        }
+      }
+    }
+  }
+  // Tarjan emits a component after everything reachable from it.  With edges column -> row
+  // (j -> i for a(i,j)), a component that is reached (rows) comes first; entries a(i,j) then have
+  // block(i) <= block(j): upper block triangular.
+}
+
+// ---- 3. minimum-degree ordering on the pattern of B + B' (B = one diagonal block) ----
+// A plain quotient-free minimum degree with lazy priority queue: adequate for the block sizes of
+// circuit matrices after BTF; plays the role AMD plays inside KLU.
+void min_degree(int n, const std::vector<std::vector<int>> &adj_in, std::vector<int> &order) {
+  std::vector<std::vector<int>> adj(adj_in);
+  for (auto &a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+  std::vector<char> done(n, 0);
+  typedef std::pair<int, int> DI;
+  std::priority_queue<DI, std::vector<DI>, std::greater<DI>> pq;
+  for (int i = 0; i < n; ++i) pq.push(DI((int)adj[i].size(), i));
+  order.clear();
+  std::vector<int> merged;
+  while ((int)order.size() < n) {
+    DI top = pq.top(); pq.pop();
+    const int v = top.second;
+    if (done[v] || top.first != (int)adj[v].size()) continue;
+    done[v] = 1;
+    order.push_back(v);
+    // eliminate v: its neighbours become a clique
+    std::vector<int> &nb = adj[v];
+    for (int u : nb) {
+      std::vector<int> &au = adj[u];
+      merged.clear();
+      std::set_union(au.begin(), au.end(), nb.begin(), nb.end(), std::back_inserter(merged));
+      au.clear();
+      for (int w : merged) if (w != u && w != v && !done[w]) au.push_back(w);
+      pq.push(DI((int)au.size(), u));
+    }
+    nb.clear(); nb.shrink_to_fit();
+  }
+}
+
+// ---- 4. Gilbert-Peierls left-looking LU of one block with threshold partial pivoting ----
+// B is given by columns in the block's own (ordered) numbering: col j has (row, value) pairs.
+// Output: pinv (row -> pivot position), L/U in CSC over pivot positions; L unit-diagonal (not stored),
+// U column holds off-diagonal entries (sorted ascending) followed by the diagonal as its LAST entry.
+struct BlockLU {
+  int n = 0;
+  std::vector<int> Lp, Li, Up, Ui, pinv;
+  std::vector<double> Lx, Ux;
+  bool singular = false;
+};
+
+void factor_block(int n, const std::vector<std::vector<std::pair<int, double>>> &cols, double tol, BlockLU &f) {
+  f.n = n;
+  f.Lp.assign(1, 0); f.Up.assign(1, 0);
+  f.Li.clear(); f.Ui.clear(); f.Lx.clear(); f.Ux.clear();
+  f.pinv.assign(n, -1);
+  std::vector<double> x(n, 0.0);
+  std::vector<int> mark(n, -1), topo, dfs_stack, dfs_pos(n), pattern;
+  std::vector<int> prow(n, -1);   // pivot position -> original row
+  for (int k = 0; k < n; ++k) {
+    // symbolic: reach of the column's rows through the graph of L (over pivoted rows)
+    topo.clear(); pattern.clear();
+    for (const auto &e : cols[k]) {
+      int r = e.first;
+      if (mark[r] == k) continue;
+      // DFS in pivot-position space for pivoted rows
+      dfs_stack.clear();
+      dfs_stack.push_back(r);
+      mark[r] = k;
+      dfs_pos[r] = (f.pinv[r] >= 0) ? f.Lp[f.pinv[r]] : 0;
+      while (!dfs_stack.empty()) {
+        const int v = dfs_stack.back();
+        const int pv = f.pinv[v];
+        bool pushed = false;
+        if (pv >= 0) {
+          while (dfs_pos[v] < f.Lp[pv + 1]) {
+            const int w = f.Li[dfs_pos[v]++];   // original row index stored in Li during factorization
+            if (mark[w] == k) continue;
+            mark[w] = k;
+            dfs_pos[w] = (f.pinv[w] >= 0) ? f.Lp[f.pinv[w]] : 0;
+            dfs_stack.push_back(w);
+            pushed = true;
+            break;
+          }
+        }
+        if (!pushed) { dfs_stack.pop_back(); topo.push_back(v); }
+      }
+    }
+    // numeric: x = B(:,k); sparse triangular solve in topological order (reverse post-order)
+    for (int v : topo) x[v] = 0.0;
+    for (const auto &e : cols[k]) x[e.first] += e.second;
+    for (int t = (int)topo.size() - 1; t >= 0; --t) {
+      const int v = topo[t];
+      const int pv = f.pinv[v];
+      if (pv < 0) continue;
+      const double xv = x[v];
+      for (int p = f.Lp[pv]; p < f.Lp[pv + 1]; ++p) x[f.Li[p]] -= f.Lx[p] * xv;
+    }
+    // pivot search among non-pivoted rows; prefer the diagonal (row k) if within tol of the largest
+    double amax = 0.0; int imax = -1;
+    for (int v : topo) if (f.pinv[v] < 0) { const double a = std::fabs(x[v]); if (a > amax) { amax = a; imax = v; } }
+    int piv = imax;
+    if (mark[k] == k && f.pinv[k] < 0 && std::fabs(x[k]) >= tol * amax && x[k] != 0.0) piv = k;
+    if (piv < 0 || x[piv] == 0.0) {
+      f.singular = true;
+      // keep the structure consistent: choose any unpivoted row (the structural diagonal if free)
+      if (piv < 0) { for (int r = 0; r < n; ++r) if (f.pinv[r] < 0) { piv = r; break; } }
+    }
+    const double pivot = x[piv];
+    // U(:,k): pivoted rows (by pivot position), diagonal last
+    std::vector<std::pair<int, double>> ucol;
+    for (int v : topo) if (f.pinv[v] >= 0) ucol.push_back(std::make_pair(f.pinv[v], x[v]));
+    std::sort(ucol.begin(), ucol.end());
+    for (auto &u : ucol) { f.Ui.push_back(u.first); f.Ux.push_back(u.second); }
+    f.Ui.push_back(k); f.Ux.push_back(pivot);
+    f.Up.push_back((int)f.Ui.size());
+    // L(:,k): remaining unpivoted rows (original row ids for now), scaled by the pivot
+    f.pinv[piv] = k; prow[k] = piv;
+    for (int v : topo) if (f.pinv[v] < 0) { f.Li.push_back(v); f.Lx.push_back(pivot != 0.0 ? x[v] / pivot : 0.0); }
+    f.Lp.push_back((int)f.Li.size());
+  }
+  // L row indices: original rows -> pivot positions, sorted within each column
+  for (int k = 0; k < n; ++k) {
+    std::vector<std::pair<int, double>> lcol;
+    for (int p = f.Lp[k]; p < f.Lp[k + 1]; ++p) lcol.push_back(std::make_pair(f.pinv[f.Li[p]], f.Lx[p]));
+    std::sort(lcol.begin(), lcol.end());
+    for (int p = f.Lp[k], t = 0; p < f.Lp[k + 1]; ++p, ++t) { f.Li[p] = lcol[t].first; f.Lx[p] = lcol[t].second; }
+  }
+}
+
+}  // namespace
+
+int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol, LuPlan &plan) {
+  plan = LuPlan();
+  plan.n = n;
+  const int nnz = rowptr[n];
+  plan.nnz_a = nnz;
+  // CSR -> CSC with a back-pointer to the CSR value index
+  std::vector<int> Ap(n + 1, 0), Ai(nnz), Aidx(nnz);
+  for (int k = 0; k < nnz; ++k) ++Ap[colind[k] + 1];
+  for (int j = 0; j < n; ++j) Ap[j + 1] += Ap[j];
+  {
+    std::vector<int> fill(Ap.begin(), Ap.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { const int p = fill[colind[k]]++; Ai[p] = i; Aidx[p] = k; }
+  }
+  // 1. maximum transversal: column matched to each row; Q0[i] = column placed at diagonal position i
+  std::vector<int> col_of_row;
+  const int nmatch = max_transversal(n, Ap, Ai, col_of_row);
+  if (nmatch < n) { plan.structurally_singular = true; return 1; }
+  // permuted pattern C = A * Q0 has c(i, i') = a(i, col_of_row[i']): column i' of C is column col_of_row[i'] of A
+  std::vector<int> Cp(n + 1, 0), Ci;
+  Ci.reserve(nnz);
+  for (int jp = 0; jp < n; ++jp) {
+    const int j = col_of_row[jp];
+    for (int p = Ap[j]; p < Ap[j + 1]; ++p) Ci.push_back(Ai[p]);
+    Cp[jp + 1] = (int)Ci.size();
+  }
+  // 2. strongly connected components of C (symmetric permutation)
+  std::vector<int> sperm, bptr;
+  strong_components(n, Cp, Ci, sperm, bptr);
+  const int nblocks = (int)bptr.size() - 1;
+  // 3. per-block fill-reducing ordering (within-block symmetric permutation)
+  std::vector<int> where(n, -1), blk_of(n, -1);
+  for (int b = 0; b < nblocks; ++b)
+    for (int t = bptr[b]; t < bptr[b + 1]; ++t) blk_of[sperm[t]] = b;
+  std::vector<int> final_order(n);   // position -> index in C numbering
+  {
+    std::vector<int> local(n, -1);
+    for (int b = 0; b < nblocks; ++b) {
+      const int nb = bptr[b + 1] - bptr[b];
+      if (nb <= 2) { for (int t = bptr[b]; t < bptr[b + 1]; ++t) final_order[t] = sperm[t]; continue; }
+      for (int t = 0; t < nb; ++t) local[sperm[bptr[b] + t]] = t;
+      std::vector<std::vector<int>> adj(nb);
+      for (int t = 0; t < nb; ++t) {
+        const int jc = sperm[bptr[b] + t];
+        for (int p = Cp[jc]; p < Cp[jc + 1]; ++p) {
+          const int ic = Ci[p];
+          if (blk_of[ic] != b || ic == jc) continue;
+          adj[t].push_back(local[ic]); adj[local[ic]].push_back(t);
+        }
+      }
+      std::vector<int> ord;
+      min_degree(nb, adj, ord);
+      for (int t = 0; t < nb; ++t) final_order[bptr[b] + t] = sperm[bptr[b] + ord[t]];
+    }
+  }
+  for (int t = 0; t < n; ++t) where[final_order[t]] = t;   // C index -> position
+  // At this point position t holds row final_order[t] (of A) and column col_of_row[final_order[t]].
+  std::vector<int> rowpos(n), colpos(n);
+  for (int t = 0; t < n; ++t) { rowpos[final_order[t]] = t; colpos[col_of_row[final_order[t]]] = t; }
+
+  // 4. factor each diagonal block; collect off-diagonal entries
+  plan.block_ptr = bptr;
+  plan.Lp.assign(1, 0); plan.Up.assign(1, 0);
+  plan.row_perm.assign(n, -1);   // position -> row of A   (includes pivoting)
+  plan.col_perm.assign(n, -1);   // position -> column of A
+  std::vector<int> a_row(n), a_col(n);
+  for (int t = 0; t < n; ++t) { a_row[t] = final_order[t]; a_col[t] = col_of_row[final_order[t]]; }
+  std::vector<int> pre_rowpos(rowpos);    // pre-pivot row positions
+  std::vector<int> new_rowpos(n, -1);     // row of A -> final position
+  plan.singular = false;
+  for (int b = 0; b < nblocks; ++b) {
+    const int k0 = bptr[b], nb = bptr[b + 1] - bptr[b];
+    std::vector<std::vector<std::pair<int, double>>> cols(nb);
+    for (int t = 0; t < nb; ++t) {
+      const int j = a_col[k0 + t];
+      for (int p = Ap[j]; p < Ap[j + 1]; ++p) {
+        const int rp = pre_rowpos[Ai[p]];
+        if (rp >= k0 && rp < k0 + nb) cols[t].push_back(std::make_pair(rp - k0, vals[Aidx[p]]));
+      }
+    }
+    BlockLU f;
+    factor_block(nb, cols, pivot_tol, f);
+    if (f.singular) plan.singular = true;
+    for (int r = 0; r < nb; ++r) new_rowpos[a_row[k0 + r]] = k0 + f.pinv[r];
+    for (int k = 0; k < nb; ++k) {
+      for (int p = f.Lp[k]; p < f.Lp[k + 1]; ++p) { plan.Li.push_back(k0 + f.Li[p]); plan.Lx.push_back(f.Lx[p]); }
+      plan.Lp.push_back((int)plan.Li.size());
+      for (int p = f.Up[k]; p < f.Up[k + 1]; ++p) { plan.Ui.push_back(k0 + f.Ui[p]); plan.Ux.push_back(f.Ux[p]); }
+      plan.Up.push_back((int)plan.Ui.size());
+    }
+  }
+  for (int r = 0; r < n; ++r) plan.row_perm[new_rowpos[r]] = r;
+  for (int t = 0; t < n; ++t) plan.col_perm[t] = a_col[t];
+  // scatter maps: every entry of A goes either into a diagonal block column (dense work vector slot)
+  // or into the off-diagonal list used by block back-substitution
+  plan.acol_ptr.assign(n + 1, 0);
+  plan.off_ptr.assign(n + 1, 0);
+  std::vector<int> blk_of_pos(n);
+  for (int b = 0; b < nblocks; ++b) for (int t = bptr[b]; t < bptr[b + 1]; ++t) blk_of_pos[t] = b;
+  for (int t = 0; t < n; ++t) {
+    const int j = plan.col_perm[t];
+    for (int p = Ap[j]; p < Ap[j + 1]; ++p) {
+      const int rp = new_rowpos[Ai[p]];
+      if (blk_of_pos[rp] == blk_of_pos[t]) { plan.acol_row.push_back(rp); plan.acol_src.push_back(Aidx[p]); }
+      else { plan.off_row.push_back(rp); plan.off_src.push_back(Aidx[p]); plan.off_val_host.push_back(vals[Aidx[p]]); }
+    }
+    plan.acol_ptr[t + 1] = (int)plan.acol_row.size();
+    plan.off_ptr[t + 1] = (int)plan.off_row.size();
+  }
+  // row-major copy of the off-diagonal entries
+  {
+    plan.offr_ptr.assign(n + 1, 0);
+    for (int r : plan.off_row) ++plan.offr_ptr[r + 1];
+    for (int r = 0; r < n; ++r) plan.offr_ptr[r + 1] += plan.offr_ptr[r];
+    plan.offr_col.resize(plan.off_row.size()); plan.offr_src.resize(plan.off_row.size());
+    std::vector<int> fill(plan.offr_ptr.begin(), plan.offr_ptr.end() - 1);
+    for (int t = 0; t < n; ++t)
+      for (int q = plan.off_ptr[t]; q < plan.off_ptr[t + 1]; ++q) {
+        const int d = fill[plan.off_row[q]]++;
+        plan.offr_col[d] = t; plan.offr_src[d] = plan.off_src[q];
+      }
+  }
+  // block dependency levels for the solve: block b needs every block c > b that has an entry in b's rows
+  std::vector<int> level(nblocks, 0);
+  int maxlevel = 0;
+  {
+    // off-diagonal entry (row position rp in block b, column position t in block c), c > b
+    std::vector<std::vector<int>> dep(nblocks);
+    for (int t = 0; t < n; ++t)
+      for (int p = plan.off_ptr[t]; p < plan.off_ptr[t + 1]; ++p) dep[blk_of_pos[plan.off_row[p]]].push_back(blk_of_pos[t]);
+    for (int b = nblocks - 1; b >= 0; --b) {
+      int lv = 0;
+      for (int c : dep[b]) lv = std::max(lv, level[c] + 1);
+      level[b] = lv;
+      maxlevel = std::max(maxlevel, lv);
+    }
+  }
+  plan.level_ptr.assign(maxlevel + 2, 0);
+  for (int b = 0; b < nblocks; ++b) ++plan.level_ptr[level[b] + 1];
+  for (int l = 0; l <= maxlevel; ++l) plan.level_ptr[l + 1] += plan.level_ptr[l];
+  plan.level_blocks.assign(nblocks, 0);
+  {
+    std::vector<int> fill(plan.level_ptr.begin(), plan.level_ptr.end() - 1);
+    for (int b = 0; b < nblocks; ++b) plan.level_blocks[fill[level[b]]++] = b;
+  }
+  // flop count of one refactorization: sum_k 2 |L_k| |U_k(offdiag)| + divisions
+  double fl = 0.0;
+  for (int k = 0; k < n; ++k) {
+    for (int p = plan.Up[k]; p < plan.Up[k + 1] - 1; ++p) {
+      const int i = plan.Ui[p];
+      fl += 2.0 * (plan.Lp[i + 1] - plan.Lp[i]);
+    }
+    fl += plan.Lp[k + 1] - plan.Lp[k];
+  }
+  plan.refactor_flops = fl;
+  return plan.singular ? 2 : 0;
+}
+
+// CPU reference of the refactor + solve on a fixed plan (used by the first solve and by tests of the
+// plan itself; the product's per-iteration path is the GPU one).
+void solve_host(const LuPlan &p, const double *b, double *x) {
+  const int n = p.n;
+  std::vector<double> y(n);
+  for (int t = 0; t < n; ++t) y[t] = b[p.row_perm[t]];
+  const int nblocks = (int)p.block_ptr.size() - 1;
+  for (int bb = nblocks - 1; bb >= 0; --bb) {
+    const int k0 = p.block_ptr[bb], k1 = p.block_ptr[bb + 1];
+    for (int k = k0; k < k1; ++k) {
+      const double yk = y[k];
+      for (int q = p.Lp[k]; q < p.Lp[k + 1]; ++q) y[p.Li[q]] -= p.Lx[q] * yk;
+    }
+    for (int k = k1 - 1; k >= k0; --k) {
+      const int d = p.Up[k + 1] - 1;
+      y[k] /= p.Ux[d];
+      const double yk = y[k];
+      for (int q = p.Up[k]; q < d; ++q) y[p.Ui[q]] -= p.Ux[q] * yk;
+    }
+    // push this block's solution into the rows of earlier blocks (off-diagonal columns)
+    for (int k = k0; k < k1; ++k)
+      for (int q = p.off_ptr[k]; q < p.off_ptr[k + 1]; ++q) y[p.off_row[q]] -= p.off_val_host[q] * y[k];
+  }
+  for (int t = 0; t < n; ++t) x[p.col_perm[t]] = y[t];
+}
+
+}  // namespace lu
+}  // namespace xb
