@@ -170,3 +170,33 @@ def rel_err(a, b, scale=None):
         return 0.0
     s = np.maximum(np.abs(b), 1e-300 if scale is None else scale)
     return float(np.max(np.abs(a - b) / s))
+
+
+def load_golden():
+    """tests/golden/b4_cases.npz -> {case: dict}; outputs of the reference's own BSIM4 code (scripts/make_golden.py)."""
+    z = np.load(os.path.join(HERE, "golden", "b4_cases.npz"))
+    cases = {}
+    for name in z["cases"]:
+        pre = str(name) + "/"
+        cases[str(name)] = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+    return cases
+
+
+def host_mirror_case(hm, g):
+    """Evaluate one golden case with the host mirror of the kernel source and assemble in numpy."""
+    flags = dict(zip(FLAG_NAMES, [int(v) for v in g["flags"]]))
+    newton0 = flags["newtonIter"] == 0
+    use_curr = newton0 and (not flags["dcop"] or flags["locaEnabled"])
+    have_old = not (newton0 and not use_curr)
+    sto_src = g["csto"] if use_curr else g["nsto"]
+    per, lids = [], []
+    for i in range(len(g["von"])):
+        rec = {k: np.ascontiguousarray(g["rec_" + k][idx]) for k, idx in
+               (("model_d", g["rec_model_idx"][i]), ("model_i", g["rec_model_idx"][i]),
+                ("size_d", g["rec_size_idx"][i]), ("inst_d", i), ("inst_i", i))}
+        l = g["rec_lids"][i]
+        V = np.array([g["x"][t] if t >= 0 else 0.0 for t in l])
+        so = sto_src[g["rec_sto0"][i]:g["rec_sto0"][i] + 13]
+        per.append(hm.eval(rec, flags, V, so, have_old, float(g["von"][i])))
+        lids.append(l)
+    return per, assemble_general(hm, per, lids, len(g["x"]), g["rowptr"], g["colind"])

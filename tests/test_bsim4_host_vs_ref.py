@@ -1,0 +1,46 @@
+"""CPU-only: kernel source (host mirror) against the live reference objects (oracle/_ref), including the
+name-by-name comparison of ~230 cached intermediates; skipped where oracle/_ref is not built."""
+import numpy as np
+import pytest
+
+import oracle_ref
+from b4_common import VARIANTS, assemble_general, isolated_devices, rel_err
+
+pytestmark = pytest.mark.skipif(not oracle_ref.available(), reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("variant", ["default", "igc2", "capmod0", "capmod1", "rgate3", "rbody", "rdsmod", "pocket"])
+def test_intermediates_and_assembly(host_mirror, variant):
+    ref = isolated_devices(oracle_ref.RefCircuit, 4, variant, seed=21)
+    rng = np.random.default_rng(5)
+    flags = dict(transient=1, newtonIter=1)
+    ref.set_flags(**flags)
+    x = rng.uniform(-0.2, 1.2, ref.n)
+    nsto = rng.normal(0, 0.3, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    ref.set_state(next_sto=nsto, curr_sto=nsto); ref.set_von(von)
+    want = ref.load(x)
+    per, lids = [], []
+    for i in range(ref.n_inst):
+        e = ref.export(i)
+        V = np.array([x[g] if g >= 0 else 0.0 for g in e["lids"]])
+        o = host_mirror.eval(e, flags, V, nsto[e["sto0"]:e["sto0"] + 13], True, von[i])
+        per.append(o); lids.append(e["lids"])
+        md, mi = ref.mid(i)
+        for k, v in md.items():
+            assert abs(o["mid_d"][k] - v) <= 1e-12 * max(abs(v), 1e-300), (variant, i, k)
+        for k, v in mi.items():
+            assert o["mid_i"][k] == v, (variant, i, k)
+    asm = assemble_general(host_mirror, per, lids, ref.n, ref.rowptr, ref.colind)
+    for k in want:
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(asm[k], want[k], scale) < 1e-12
+
+
+def test_variants_really_change_the_topology():
+    sizes = {}
+    for v in ("default", "rgate", "rgate3", "rbody", "rdsmod"):
+        ref = isolated_devices(oracle_ref.RefCircuit, 1, v, seed=1)
+        sizes[v] = ref.n
+    assert sizes["default"] == 8 and sizes["rgate"] > 8 and sizes["rgate3"] > sizes["rgate"]
+    assert sizes["rbody"] == 8 + 2 * 3 and sizes["rdsmod"] == 8 + 2 * 2

@@ -78,3 +78,35 @@ def test_every_arithmetic_variant(variant, arith):
 def test_pass_through_limiters():
     # previous iterate == present voltages: limiters take the pass-through branch (C2 operating point)
     run_case("default", FLAG_CASES["tran_iter1"], store_noise=0.0)
+
+
+# ---- against the committed golden fixtures (no oracle library needed at run time) ----
+from b4_common import load_golden  # noqa: E402
+
+GOLD = load_golden()
+
+
+@pytest.mark.parametrize("case", sorted(GOLD))
+def test_gpu_matches_reference_golden(case):
+    import xyce_b200
+    g = GOLD[case]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(g["rowptr"], g["colind"])
+    eng.set_sizes(int(g["n_sta"]), int(g["n_sto"]))
+    eng.b4_set_models(g["rec_model_d"], g["rec_model_i"], g["rec_size_d"])
+    eng.b4_add_group(g["rec_inst_d"], g["rec_inst_i"], g["rec_model_idx"], g["rec_size_idx"], g["rec_lids"],
+                     g["rec_sto0"], 1, g["rec_sta0"], 1)
+    eng.finalize()
+    eng.set_state(0, g["nsto"]); eng.set_state(1, g["csto"]); eng.b4_set_von(0, g["von"])
+    from b4_common import FLAG_NAMES
+    flags = dict(zip(FLAG_NAMES, [int(v) for v in g["flags"]]))
+    got = eng.load_host(g["x"], solver_state(**flags))
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        want = g["ref_" + k]
+        scale = 1e-3 * np.max(np.abs(want)) if np.any(want) else 1e-300
+        assert rel_err(got[k], want, scale) < TOL, (case, k)
+    assert rel_err(eng.get_state(0), g["next_sto"], 1e-30) < TOL
+    assert rel_err(eng.get_state(2), g["next_sta"], 1e-30) < TOL
+    assert rel_err(eng.get_state(3), g["curr_sta"], 1e-30) < TOL
+    assert rel_err(eng.b4_get_von(0, len(g["von"])), g["von_out"], 1e-30) < TOL
+    eng.close()
