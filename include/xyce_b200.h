@@ -125,6 +125,36 @@ int xgpu_lu_info(const xgpu_ctx *ctx, double *info8);
 int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colind, const double *vals,
                               const double *rhs, double *x, double *info8);
 
+/* ---- linear devices, sources, Newton + transient loop (callers of the hot path) ----
+ * xgpu_linear_set: constant conductance (G) and capacitance (C) stamps of the linear devices as COO
+ *   triplets (duplicates are summed, entries with a -1 index = ground are dropped).  Replayed on every
+ *   load exactly like the reference's FilteredMatrix pair (N_LOA_CktLoader.C:504-578, :700-788;
+ *   N_LAS_FilteredMatrix.C:473-548, :632-667).  Call before xgpu_pattern_build / xgpu_finalize.
+ * xgpu_sources_set: independent sources; source k adds scale[k]*s_k(t) to B[row[k]]
+ *   (Vsrc: row = branch equation, scale +1, N_DEV_Vsrc.C:834-; Isrc: two entries).  type 0 = DC
+ *   (params7[0]), 1 = PULSE(v1 v2 td tr tf pw per).  Evaluated on the host once per load
+ *   (DeviceMgr::updateSources, Core/N_DEV_DeviceMgr.C:4900-4917).
+ * xgpu_tran_run: .TRAN ... NOOP from the initial solution h_x0 -- DampedNewton (N_NLS_DampedNewton.C:362-515,
+ *   :1191-1397) inside the variable-step trapezoid of OneStep (N_TIA_OneStep.C) with LTE step control.
+ *   Outputs: accepted time points and probe waveforms, one record {t, h, newton iterations, order, status}
+ *   per step attempt, and counters stats16 = {accepted, rejected, newton iterations, Jacobian loads,
+ *   residual loads, linear solves, LU analyses, LU refactors, time points, attempts, driver rc}. */
+typedef struct xgpu_tran_params {
+  double tstop, tstep, delmax;
+  int maxNewtonStep;                 /* 0 = reference default (20) */
+  double deltaXTol, absTol, relTol, RHSTol;   /* 0 = reference defaults 0.33, 1e-6, 1e-2, 1e-2 */
+  double relErrorTol, absErrorTol;   /* 0 = 1e-3, 1e-6 */
+  int maxOrder;                      /* 0 = 2 (trapezoid) */
+  int maxSteps;
+} xgpu_tran_params;
+int xgpu_linear_set(xgpu_ctx *ctx, int nG, const int32_t *g_row, const int32_t *g_col, const double *g_val,
+                    int nC, const int32_t *c_row, const int32_t *c_col, const double *c_val);
+int xgpu_sources_set(xgpu_ctx *ctx, int n_sources, const int32_t *row, const double *scale, const int32_t *type,
+                     const double *params7);
+int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0, int n_probes,
+                  const int32_t *probes, int max_out, int *n_out, double *h_times, double *h_wave,
+                  int max_steps_out, int *n_steps_out, double *h_step_info5, double *stats16);
+
 /* ---- host-buffer convenience path (what a non-GPU-aware caller uses; copies inside) ----
  * One updateState + loadDAEVectors + loadDAEMatrices pass.  Vectors have n_unknowns entries,
  * matrices nnz entries; next/curr store and state live in the context between calls. */

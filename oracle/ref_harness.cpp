@@ -40,6 +40,7 @@
 
 #include "../xyce_b200/csrc/bsim4_fields.def"
 #include "b4_mid_members.def"
+#include "../xyce_b200/csrc/tran_driver.h"   // control flow only (Newton / OneStep restatement)
 
 using namespace Xyce;
 using namespace Xyce::Device;
@@ -111,6 +112,7 @@ struct Ctx {
   CsrMatrix dFdx, dQdx;
   std::vector<double> f, q, b, fl, ql, nextSta, currSta, nextSto, currSto, sol;
   bool finalized = false;
+  std::vector<std::pair<int, int>> extra_pattern;   // linear-device entries
 };
 
 alignas(64) char g_fake_mgr[4096];
@@ -192,6 +194,7 @@ int xref_finalize(void *h) {
       for (int cj : st[i]) { int gc = r.lids[cj]; if (gc >= 0) rows[gr].insert(gc); }
     }
   }
+  for (auto &e : c->extra_pattern) rows[e.first].insert(e.second);
   for (CsrMatrix *M : {&c->dFdx, &c->dQdx}) {
     M->rowptr.assign(1, 0);
     M->colind.clear();
@@ -400,16 +403,151 @@ void xref_b4_mid(void *h, int idx, double *mid_d, int *mid_i) {
 #undef PUT
 }
 
-// ---- Kundert Sparse 1.3 (reference tree: LinearAlgebraServicesPKG/ksparse) ----
-// Same call sequence as Epetra_CrsKundertSparse (ksparse/Epetra_CrsKundertSparse.C:60-190):
-// spCreate, spGetElement per CSR entry (1-based), spOrderAndFactor, spSolve.
+}  // extern "C" (reopened below)
+
+// ---- transient run around the REFERENCE device code and the reference tree's Kundert Sparse ----
+// Same control flow (tran_driver.h) as the product, but every load is the reference's
+// Master::updateState/loadDAEVectors/loadDAEMatrices and every linear solve is ksparse
+// (spOrderAndFactor each Newton iteration, as N_LAS_KSparseSolver does).
 extern "C" {
 char *spCreate(int, int, int *);
 double *spGetElement(char *, int, int);
 int spOrderAndFactor(char *, double *, double, double, int, int);
 int spSolve(char *, double *, double *, double *, double *);
+void spClear(char *);
 void spDestroy(char *);
 }
+namespace {
+struct Coo { std::vector<int> r, c; std::vector<double> v; };
+struct RefBackend {
+  Ctx *c;
+  int n_;
+  std::vector<std::vector<double>> v;
+  std::vector<double> J;
+  Coo G, C;
+  std::vector<int> Gpos, Cpos;
+  struct Src { int row; double scale; int type; double p[7]; };
+  std::vector<Src> sources;
+  std::vector<int> probes;
+  std::vector<double> times, wave;
+  char *M = 0;
+  std::vector<double *> addr;
+  bool first = true;
+
+  int n() const { return n_; }
+  void copy(int d, int a) { v[d] = v[a]; }
+  void fill(int d, double x) { std::fill(v[d].begin(), v[d].end(), x); }
+  void scale(int d, double a) { for (double &x : v[d]) x = a * x + 0.0 * x; }
+  void axpby(int d, double a, int x, double b, int y) { for (int i = 0; i < n_; ++i) v[d][i] = a * v[x][i] + b * v[y][i]; }
+  void axpy(int d, double a, int x) { for (int i = 0; i < n_; ++i) v[d][i] = 1.0 * v[d][i] + a * v[x][i]; }
+  double norm2(int x) { double s = 0; for (double t : v[x]) s += t * t; return std::sqrt(s); }
+  double norm_inf(int x) { double s = 0; for (double t : v[x]) s = std::max(s, std::fabs(t)); return s; }
+  double wmax_norm(int x, int w) { double s = 0; for (int i = 0; i < n_; ++i) s = std::max(s, std::fabs(v[x][i] / v[w][i])); return s; }
+  double wrms_norm(int x, int w) { double s = 0; for (int i = 0; i < n_; ++i) { double t = v[x][i] / v[w][i]; s += t * t; } return std::sqrt(s / n_); }
+  void sol_weights(int d, double rel, double ab, int a, int b) { for (int i = 0; i < n_; ++i) v[d][i] = rel * std::max(std::fabs(v[a][i]), std::fabs(v[b][i])) + ab; }
+  void abs_weights(int d, double rel, double ab, int a) { for (int i = 0; i < n_; ++i) v[d][i] = rel * std::fabs(v[a][i]) + ab; }
+
+  bool load_rhs(const xb::sim::Flags &fl, double time) {
+    SolverState &s = c->solState;
+    s.dcopFlag = fl.dcop; s.tranopFlag = fl.tranop; s.transientFlag = fl.transient; s.initTranFlag_ = fl.initTran;
+    s.newtonIter = fl.newtonIter; s.initJctFlag_ = fl.initJct; s.currTimeStep_ = fl.currTimeStep;
+    std::copy(v[xb::sim::vNextSol].begin(), v[xb::sim::vNextSol].end(), c->sol.begin());
+    c->sol[c->n] = 0.0;
+    for (auto *q : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(q->begin(), q->end(), 0.0);
+    bool ok = c->masterB4->updateState(c->sol.data(), c->nextSta.data(), c->nextSto.data());
+    ok = c->masterB4->loadDAEVectors(c->sol.data(), c->f.data(), c->q.data(), c->b.data(), 0, 0, 0) && ok;
+    for (size_t k = 0; k < G.r.size(); ++k) c->f[G.r[k]] += G.v[k] * c->sol[G.c[k]];
+    for (size_t k = 0; k < C.r.size(); ++k) c->q[C.r[k]] += C.v[k] * c->sol[C.c[k]];
+    for (const Src &q : sources) c->b[q.row] += q.scale * (q.type == 1 ? xb::sim::pulse_value(q.p, time) : q.p[0]);
+    std::copy(c->f.begin(), c->f.begin() + n_, v[xb::sim::vF].begin());
+    std::copy(c->q.begin(), c->q.begin() + n_, v[xb::sim::vQ].begin());
+    std::copy(c->b.begin(), c->b.begin() + n_, v[xb::sim::vB].begin());
+    std::copy(c->fl.begin(), c->fl.begin() + n_, v[xb::sim::vFlim].begin());
+    std::copy(c->ql.begin(), c->ql.begin() + n_, v[xb::sim::vQlim].begin());
+    return ok;
+  }
+  void load_jacobian(double qs, double fs) {
+    c->dFdx.put(0.0); c->dQdx.put(0.0);
+    c->masterB4->loadDAEMatrices(c->dFdx, c->dQdx);
+    for (size_t k = 0; k < G.r.size(); ++k) c->dFdx.vals[Gpos[k]] += G.v[k];
+    for (size_t k = 0; k < C.r.size(); ++k) c->dQdx.vals[Cpos[k]] += C.v[k];
+    for (size_t k = 0; k < J.size(); ++k) J[k] = qs * c->dQdx.vals[k] + fs * c->dFdx.vals[k];
+  }
+  int solve() {
+    const CsrMatrix &A = c->dFdx;
+    if (!M) {
+      int err = 0;
+      M = spCreate(n_, 0, &err);
+      for (int i = 0; i < n_; ++i)
+        for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) addr.push_back(spGetElement(M, i + 1, A.colind[k] + 1));
+    } else {
+      spClear(M);
+    }
+    for (size_t k = 0; k < J.size(); ++k) *addr[k] = J[k];
+    int rc = spOrderAndFactor(M, 0, 1.0e-3, 1.0e-13, 1, first ? 1 : 0);
+    first = false;
+    if (rc) { fill(xb::sim::vDX, 0.0); return rc; }
+    std::vector<double> b(v[xb::sim::vRHS]);
+    return spSolve(M, b.data() - 1, v[xb::sim::vDX].data() - 1, 0, 0);
+  }
+  bool all_devices_converged() {
+    bool all = true;
+    for (auto &r : c->insts) all = all && r.inst->isConverged();
+    return all;
+  }
+  bool limiter_active() const { return c->devOptions.voltageLimiterFlag; }
+  void accept_state() { c->currSta = c->nextSta; c->currSto = c->nextSto; }
+  void record(double t) { times.push_back(t); for (int p : probes) wave.push_back(v[xb::sim::vNextSol][p]); }
+};
+}  // namespace
+
+extern "C" {
+
+// params: tstop, tstep, delmax.  Linear part as COO (G, C), sources {row, scale, type, p[7]}.
+int xref_tran_run(void *h, const double *params3, const double *x0, int nG, const int *gr, const int *gc, const double *gv,
+                  int nC, const int *cr, const int *cc, const double *cv, int ns, const int *srow, const double *sscale,
+                  const int *stype, const double *sp7, int n_probes, const int *probes, int max_out, int *n_out,
+                  double *times, double *wave, int max_steps, int *n_steps, double *step_info5, double *stats16) {
+  Ctx *c = (Ctx *)h;
+  RefBackend B;
+  B.c = c; B.n_ = c->n;
+  B.v.assign(xb::sim::kNumVec, std::vector<double>(c->n, 0.0));
+  B.J.assign(c->dFdx.vals.size(), 0.0);
+  auto pos = [&](int r, int col) {
+    const int *b = &c->dFdx.colind[c->dFdx.rowptr[r]], *e = &c->dFdx.colind[c->dFdx.rowptr[r + 1]];
+    return (int)(std::lower_bound(b, e, col) - c->dFdx.colind.data());
+  };
+  for (int k = 0; k < nG; ++k) if (gr[k] >= 0 && gc[k] >= 0) { B.G.r.push_back(gr[k]); B.G.c.push_back(gc[k]); B.G.v.push_back(gv[k]); B.Gpos.push_back(pos(gr[k], gc[k])); }
+  for (int k = 0; k < nC; ++k) if (cr[k] >= 0 && cc[k] >= 0) { B.C.r.push_back(cr[k]); B.C.c.push_back(cc[k]); B.C.v.push_back(cv[k]); B.Cpos.push_back(pos(cr[k], cc[k])); }
+  for (int k = 0; k < ns; ++k) if (srow[k] >= 0) { RefBackend::Src q; q.row = srow[k]; q.scale = sscale[k]; q.type = stype[k]; std::memcpy(q.p, sp7 + 7 * k, 7 * sizeof(double)); B.sources.push_back(q); }
+  B.probes.assign(probes, probes + n_probes);
+  std::copy(x0, x0 + c->n, B.v[xb::sim::vNextSol].begin());
+  std::copy(x0, x0 + c->n, B.v[xb::sim::vCurrSol].begin());
+  c->solState.transientFlag = true;
+  xb::sim::TranParams P;
+  P.tstop = params3[0]; P.tstep = params3[1]; P.delmax = params3[2];
+  xb::sim::TransientDriver<RefBackend> drv(B, P);
+  const int rc = drv.run();
+  *n_out = std::min((int)B.times.size(), max_out);
+  for (int i = 0; i < *n_out; ++i) { times[i] = B.times[i]; for (int p = 0; p < n_probes; ++p) wave[(size_t)i * n_probes + p] = B.wave[(size_t)i * n_probes + p]; }
+  *n_steps = std::min((int)drv.steps.size(), max_steps);
+  for (int i = 0; i < *n_steps; ++i) { const auto &r = drv.steps[i]; double *o = step_info5 + 5 * (size_t)i; o[0] = r.t; o[1] = r.h; o[2] = r.newton_iters; o[3] = r.order; o[4] = r.status; }
+  const auto &t = drv.stats;
+  const double st[16] = {(double)t.accepted, (double)t.rejected, (double)t.newton_total, (double)t.jacobian_loads, (double)t.residual_loads, (double)t.linear_solves, 0, 0, (double)B.times.size(), (double)drv.steps.size(), (double)rc, 0, 0, 0, 0, 0};
+  std::memcpy(stats16, st, sizeof(st));
+  if (B.M) spDestroy(B.M);
+  return rc;
+}
+
+// The pattern must also hold the linear-device entries: call before xref_finalize.
+void xref_add_pattern_entries(void *h, int n, const int *r, const int *cidx) {
+  Ctx *c = (Ctx *)h;
+  for (int k = 0; k < n; ++k) if (r[k] >= 0 && cidx[k] >= 0) c->extra_pattern.push_back(std::make_pair(r[k], cidx[k]));
+}
+
+// ---- Kundert Sparse 1.3 (reference tree: LinearAlgebraServicesPKG/ksparse) ----
+// Same call sequence as Epetra_CrsKundertSparse (ksparse/Epetra_CrsKundertSparse.C:60-190):
+// spCreate, spGetElement per CSR entry (1-based), spOrderAndFactor, spSolve.
 int xref_ksparse_solve(int n, const int *rowptr, const int *colind, const double *vals, const double *rhs, double *x) {
   int err = 0;
   char *M = spCreate(n, 0, &err);

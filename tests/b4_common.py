@@ -200,3 +200,19 @@ def host_mirror_case(hm, g):
         per.append(hm.eval(rec, flags, V, so, have_old, float(g["von"][i])))
         lids.append(l)
     return per, assemble_general(hm, per, lids, len(g["x"]), g["rowptr"], g["colind"])
+
+
+def ref_circuit_from_workload(ref_cls, w):
+    """Build the reference-object circuit (oracle/_ref) for a workloads.* dict with BSIM4 + linear devices."""
+    from xyce_b200 import workloads as wl
+    c = ref_cls(w["n_unknowns"])
+    c.add_model("nch", "NMOS", wl.NMOS_CARD)
+    c.add_model("pch", "PMOS", wl.PMOS_CARD)
+    for i in range(w["n_inst"]):
+        is_n = w["kind"][i] == 0
+        nodes = [int(v) for v in w["lids"][i][:4]]
+        c.add_instance("M:%d" % i, "nch" if is_n else "pch", nodes, wl.NMOS_INST if is_n else wl.PMOS_INST)
+    L = w["linear"]
+    c.add_pattern_entries(np.concatenate([L["g_row"], L["c_row"]]), np.concatenate([L["g_col"], L["c_col"]]))
+    c.finalize()
+    return c

@@ -116,6 +116,31 @@ class RefCircuit:
         self.lib.xref_set_solution(self.h, dptr(x))
         self.lib.xref_load_repeat(self.h, int(reps))
 
+    def add_pattern_entries(self, rows, cols):
+        r, c = np.ascontiguousarray(rows, dtype=np.int32), np.ascontiguousarray(cols, dtype=np.int32)
+        self.lib.xref_add_pattern_entries(self.h, len(r), iptr(r), iptr(c))
+
+    def tran_run(self, x0, tstop, tstep, probes, linear, sources, delmax=0.0, max_out=200000):
+        """Transient run: tran_driver.h control flow around the reference device code + ksparse."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        par = f64([tstop, tstep, delmax])
+        L = {k: (i32(v) if k.endswith(("row", "col")) else f64(v)) for k, v in linear.items()}
+        S = dict(row=i32(sources["row"]), scale=f64(sources["scale"]), type=i32(sources["type"]), params=f64(sources["params"]))
+        probes = i32(probes)
+        times, wave = np.zeros(max_out), np.zeros((max_out, len(probes)))
+        steps, stats = np.zeros((max_out, 5)), np.zeros(16)
+        n_out, n_steps = C.c_int(), C.c_int()
+        rc = self.lib.xref_tran_run(self.h, dptr(par), dptr(f64(x0)), len(L["g_row"]), iptr(L["g_row"]), iptr(L["g_col"]),
+                                    dptr(L["g_val"]), len(L["c_row"]), iptr(L["c_row"]), iptr(L["c_col"]), dptr(L["c_val"]),
+                                    len(S["row"]), iptr(S["row"]), dptr(S["scale"]), iptr(S["type"]), dptr(S["params"]),
+                                    len(probes), iptr(probes), max_out, C.byref(n_out), dptr(times), dptr(wave),
+                                    max_out, C.byref(n_steps), dptr(steps), dptr(stats))
+        keys = ("accepted", "rejected", "newton_iters", "jacobian_loads", "residual_loads", "linear_solves",
+                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc")
+        return dict(rc=rc, t=times[:n_out.value], wave=wave[:n_out.value], steps=steps[:n_steps.value],
+                    stats=dict(zip(keys, stats.tolist())))
+
     def names(self, which):
         return self.lib.xref_b4_names(which).decode().split()
 

@@ -1,0 +1,42 @@
+"""End-to-end .TRAN on the GPU (device eval + assembly + KLU-pattern LU + Newton/OneStep driver) against the
+same control flow around the REFERENCE device code and Kundert Sparse (oracle/_ref):
+Newton iteration counts per step identical, waveforms within Xyce's RELTOL/ABSTOL (1e-3 / 1e-6)."""
+import numpy as np
+import pytest
+
+import oracle_ref
+from b4_common import ref_circuit_from_workload
+from xyce_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(n_rings, stages, tstop, tstep=1e-12):
+    w = wl.ring_oscillator_array(n_rings, stages)
+    probes = [0, 1, stages // 2, w["vdd"], w["branch"]]
+    ref = ref_circuit_from_workload(oracle_ref.RefCircuit, w)
+    ref.set_flags(transient=1)
+    want = ref.tran_run(w["x"], tstop, tstep, probes, w["linear"], w["sources"])
+    eng = wl.build_engine(w)
+    got = eng.tran_run(w["x"], tstop, tstep, probes)
+    eng.close()
+    return w, want, got
+
+
+@pytest.mark.parametrize("n_rings,stages,tstop", [(1, 11, 2e-9), (1, 101, 2e-9), (3, 31, 1e-9)])
+def test_ring_oscillator_tran_matches_reference_flow(n_rings, stages, tstop):
+    w, want, got = run_both(n_rings, stages, tstop)
+    assert want["rc"] == 0 and got["rc"] == 0, got.get("error")
+    # identical step sequence and Newton iteration counts
+    assert got["stats"]["accepted"] == want["stats"]["accepted"]
+    assert got["stats"]["rejected"] == want["stats"]["rejected"]
+    assert np.array_equal(got["steps"][:, 2], want["steps"][:, 2])          # Newton iterations per attempt
+    assert np.array_equal(got["steps"][:, 4], want["steps"][:, 4])          # status per attempt
+    assert np.allclose(got["t"], want["t"], rtol=1e-9, atol=0)
+    # waveforms within RELTOL/ABSTOL
+    tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
+    assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
+    # it really oscillates
+    v = want["wave"][:, 0]
+    assert v.max() > 0.9 and v.min() < 0.1
+    assert got["stats"]["lu_analyses"] >= 1 and got["stats"]["lu_refactors"] > 0

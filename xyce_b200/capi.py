@@ -11,6 +11,13 @@ FLAG_FIELDS = ["dcopFlag", "tranopFlag", "acopFlag", "transientFlag", "dcsweepFl
 REAL_FIELDS = ["gmin", "gainScale", "nltermScale", "vgstConst", "vdsScaleMin", "sizeScale", "currTimeStep"]
 
 
+class TranParams(C.Structure):
+    """Mirror of xgpu_tran_params; zeros select the reference defaults."""
+    _fields_ = [("tstop", C.c_double), ("tstep", C.c_double), ("delmax", C.c_double), ("maxNewtonStep", C.c_int),
+                ("deltaXTol", C.c_double), ("absTol", C.c_double), ("relTol", C.c_double), ("RHSTol", C.c_double),
+                ("relErrorTol", C.c_double), ("absErrorTol", C.c_double), ("maxOrder", C.c_int), ("maxSteps", C.c_int)]
+
+
 class SolverState(C.Structure):
     """Mirror of xgpu_solver_state (Device::SolverState + DeviceOptions subset)."""
     _fields_ = [(n, C.c_int) for n in FLAG_FIELDS] + [(n, C.c_double) for n in REAL_FIELDS]
@@ -194,6 +201,31 @@ class Engine:
     def jacobian_combine(self, qs, d_dqdx, fs, d_dfdx, d_jac):
         p = C.c_void_p
         self._chk(self.lib.xgpu_jacobian_combine(self.h, qs, p(d_dqdx), fs, p(d_dfdx), p(d_jac)))
+
+    # ---- linear devices, sources, transient ----
+    def set_linear(self, g_row, g_col, g_val, c_row, c_col, c_val):
+        a = [_i32(g_row), _i32(g_col), _f64(g_val), _i32(c_row), _i32(c_col), _f64(c_val)]
+        self._chk(self.lib.xgpu_linear_set(self.h, len(a[0]), _ip(a[0]), _ip(a[1]), _dp(a[2]),
+                                           len(a[3]), _ip(a[3]), _ip(a[4]), _dp(a[5])))
+
+    def set_sources(self, row, scale, stype, params7):
+        a = [_i32(row), _f64(scale), _i32(stype), _f64(params7)]
+        self._chk(self.lib.xgpu_sources_set(self.h, len(a[0]), _ip(a[0]), _dp(a[1]), _ip(a[2]), _dp(a[3])))
+
+    def tran_run(self, x0, tstop, tstep, probes, delmax=0.0, max_out=200000, **kw):
+        tp = TranParams(tstop=tstop, tstep=tstep, delmax=delmax, **kw)
+        probes = _i32(probes)
+        x0 = _f64(x0)
+        times, wave = np.zeros(max_out), np.zeros((max_out, len(probes)))
+        steps, stats = np.zeros((max_out, 5)), np.zeros(16)
+        n_out, n_steps = C.c_int(), C.c_int()
+        rc = self.lib.xgpu_tran_run(self.h, C.byref(tp), _dp(x0), len(probes), _ip(probes), max_out, C.byref(n_out),
+                                    _dp(times), _dp(wave), max_out, C.byref(n_steps), _dp(steps), _dp(stats))
+        keys = ("accepted", "rejected", "newton_iters", "jacobian_loads", "residual_loads", "linear_solves",
+                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc")
+        return dict(rc=rc, t=times[:n_out.value], wave=wave[:n_out.value], steps=steps[:n_steps.value],
+                    stats=dict(zip(keys, stats.tolist())),
+                    error=self.lib.xgpu_last_error(self.h).decode() if rc else "")
 
     # ---- sparse LU ----
     def lu_analyze(self, d_vals):

@@ -2,7 +2,6 @@
 // Host-side C++: owns device copies of the parameter records and gather maps, builds the
 // stamp -> CSR maps once, and launches the sm_100a kernels.  There is deliberately no CPU
 // fallback: every entry point fails with an error code if CUDA is unavailable.
-#include "../../include/xyce_b200.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -10,69 +9,15 @@
 #include <string>
 #include <vector>
 
-#include "assembly.cuh"
-#include "b4_kernels.cuh"
-#include "lu.h"
+#include "ctx.h"
+#include "vecops.cuh"
 
 using namespace xb;
 using namespace xb::b4;
 
 namespace {
 
-struct HostGroup {
-  int n = 0;
-  int general = 0;
-  std::vector<int32_t> lids;       // [12][n] transposed (node-major)
-  GroupDev dev{};
-  // owned device memory
-  double *d_inst_d = nullptr, *d_von = nullptr;
-  int *d_topo = nullptr, *d_model_idx = nullptr, *d_size_idx = nullptr, *d_lids = nullptr;
-  int *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
-};
-
-}  // namespace
-
-struct xgpu_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  std::string err;
-  long long launches = 0;
-  int b4_arith = 2, b4_minblocks = 4;   // kernel variant (xgpu_set_option); 0/2 = strict parity arithmetic
-
-  int n = 0;
-  int64_t nnz = 0;
-  std::vector<int32_t> rowptr, colind;
-  int n_state = 0, n_store = 0;
-
-  B4Model *d_models = nullptr;
-  B4Size *d_sizes = nullptr;
-  int n_models = 0, n_sizes = 0;
-  std::vector<HostGroup> groups;
-  bool finalized = false;
-
-  // contribution planes
-  int64_t vec_plane = 0, mat_plane = 0;
-  double *d_vec_planes = nullptr;   // 4 * vec_plane
-  double *d_mat_planes = nullptr;   // 2 * mat_plane
-  GatherMapDev vec_map, mat_map;
-  int *d_conv = nullptr;
-
-  // context-owned system buffers (host-convenience path)
-  double *buf[11] = {nullptr};
-
-  // sparse LU
-  xb::lu::LuPlan lu_plan;
-  xb::lu::LuDev lu_dev;
-  bool lu_ready = false;
-};
-
-namespace {
-
-int fail(xgpu_ctx *c, int code, const std::string &msg) {
-  if (c) c->err = msg;
-  return code;
-}
+int fail(xgpu_ctx *c, int code, const std::string &msg) { return xg_fail(c, code, msg); }
 #define XG_CUDA(call)                                                                      \
   do {                                                                                     \
     cudaError_t e_ = (call);                                                               \
@@ -122,6 +67,13 @@ void finish_map(GatherMapHost &m, const std::vector<int64_t> &count) {
 
 }  // namespace
 
+int xg_fail(xgpu_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+int xg_finalize_linear(xgpu_ctx *ctx);
+
 extern "C" {
 
 int xgpu_create(int device, xgpu_ctx **out) {
@@ -155,6 +107,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
   xb::lu::free_plan(ctx->lu_dev);
+  for (XgLinearPart *L : {&ctx->linG, &ctx->linC}) { cudaFree(L->rows); cudaFree(L->ptr); cudaFree(L->col); cudaFree(L->pos); cudaFree(L->val); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -214,6 +167,11 @@ int xgpu_pattern_build(xgpu_ctx *ctx, int n) {
       }
     }
   }
+  for (const XgLinearPart *L : {&ctx->linG, &ctx->linC})
+    for (size_t k = 0; k < L->h_row.size(); ++k) {
+      if (L->h_row[k] >= n || L->h_col[k] >= n) return fail(ctx, 10, "linear stamp index outside the pattern");
+      pairs.push_back(((uint64_t)(uint32_t)L->h_row[k] << 32) | (uint32_t)L->h_col[k]);
+    }
   std::sort(pairs.begin(), pairs.end());
   pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
   ctx->n = n;
@@ -307,7 +265,7 @@ int xgpu_b4_group_add(xgpu_ctx *ctx, int n, const double *inst_d, const int32_t 
   if (ctx->finalized) { fail(ctx, 5, "group_add after finalize"); return -5; }
   if (!ctx->d_models) { fail(ctx, 7, "xgpu_b4_models_set must precede xgpu_b4_group_add"); return -7; }
   if (cudaSetDevice(ctx->device) != cudaSuccess) return -4;
-  HostGroup g;
+  XgHostGroup g;
   g.n = n;
   // records -> structure of arrays; topology word; choose the kernel variant
   std::vector<double> soa((size_t)kNumInstD * n);
@@ -424,6 +382,7 @@ int xgpu_finalize(xgpu_ctx *ctx) {
     XG_CUDA(cudaMalloc((void **)&ctx->buf[b], std::max<size_t>(sizes[b], 1) * sizeof(double)));
     XG_CUDA(cudaMemset(ctx->buf[b], 0, std::max<size_t>(sizes[b], 1) * sizeof(double)));
   }
+  { const int rc = xg_finalize_linear(ctx); if (rc) return rc; }
   ctx->finalized = true;
   return 0;
 }

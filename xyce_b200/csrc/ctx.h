@@ -1,0 +1,75 @@
+// xyce_b200 -- internal definition of the context behind the C ABI (shared by capi.cu and sim_gpu.cu).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/xyce_b200.h"
+#include "assembly.cuh"
+#include "b4_kernels.cuh"
+#include "lu.h"
+
+struct XgHostGroup {
+  int n = 0;
+  int general = 0;
+  std::vector<int32_t> lids;       // [12][n] transposed (node-major)
+  xb::b4::GroupDev dev{};
+  // owned device memory
+  double *d_inst_d = nullptr, *d_von = nullptr;
+  int *d_topo = nullptr, *d_model_idx = nullptr, *d_size_idx = nullptr, *d_lids = nullptr;
+  int *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
+};
+
+// linear-device part (R, C, V, I): constant stamps replayed every load, like the reference's
+// FilteredMatrix objects (N_LOA_CktLoader.C:504-578, :700-788)
+struct XgLinearPart {
+  int nrows = 0, nnz = 0;
+  int *rows = nullptr, *ptr = nullptr, *col = nullptr, *pos = nullptr;   // CSR over non-empty rows; pos = index in the system CSR
+  double *val = nullptr;
+  std::vector<int32_t> h_row, h_col;     // merged COO (host), kept for pattern building
+  std::vector<double> h_val;
+};
+
+struct XgSource { int row; double scale; int type; double p[7]; };
+
+struct xgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long long launches = 0;
+  int b4_arith = 2, b4_minblocks = 4;   // kernel variant (xgpu_set_option); 0/2 = strict parity arithmetic
+
+  int n = 0;
+  int64_t nnz = 0;
+  std::vector<int32_t> rowptr, colind;
+  int n_state = 0, n_store = 0;
+
+  xb::b4::B4Model *d_models = nullptr;
+  xb::b4::B4Size *d_sizes = nullptr;
+  int n_models = 0, n_sizes = 0;
+  std::vector<XgHostGroup> groups;
+  bool finalized = false;
+
+  // contribution planes
+  int64_t vec_plane = 0, mat_plane = 0;
+  double *d_vec_planes = nullptr;   // 4 * vec_plane
+  double *d_mat_planes = nullptr;   // 2 * mat_plane
+  xb::GatherMapDev vec_map, mat_map;
+  int *d_conv = nullptr;
+
+  // context-owned system buffers (host-convenience path)
+  double *buf[11] = {nullptr};
+
+  // linear devices and independent sources
+  XgLinearPart linG, linC;
+  std::vector<XgSource> sources;
+  double *d_bsrc = nullptr;          // staging for source values
+
+  // sparse LU
+  xb::lu::LuPlan lu_plan;
+  xb::lu::LuDev lu_dev;
+  bool lu_ready = false;
+};
+
+int xg_fail(xgpu_ctx *c, int code, const std::string &msg);

@@ -1,0 +1,273 @@
+// xyce_b200 -- CUDA backend of the Newton / transient driver (tran_driver.h) and its C ABI:
+// linear-device replay (FilteredMatrix semantics), independent sources, device-resident vectors,
+// norms, the KLU-pattern LU, and the time loop itself.  All vectors stay in HBM for the whole run;
+// per Newton iteration the host receives only a handful of scalars (norms, convergence flag).
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "ctx.h"
+#include "tran_driver.h"
+#include "vecops.cuh"
+
+using namespace xb;
+
+namespace {
+
+#define XS_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return xg_fail(ctx, 100 + (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <class T> cudaError_t up(T **d, const std::vector<T> &v) {
+  cudaFree(*d); *d = nullptr;
+  cudaError_t e = cudaMalloc((void **)d, (v.empty() ? 1 : v.size()) * sizeof(T));
+  if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+// merge duplicate (row, col) pairs, drop ground (-1) entries
+void merge_coo(int n, const int32_t *r, const int32_t *c, const double *v, XgLinearPart &L) {
+  std::map<std::pair<int, int>, double> m;
+  for (int k = 0; k < n; ++k) if (r[k] >= 0 && c[k] >= 0) m[std::make_pair(r[k], c[k])] += v[k];
+  L.h_row.clear(); L.h_col.clear(); L.h_val.clear();
+  for (auto &e : m) { L.h_row.push_back(e.first.first); L.h_col.push_back(e.first.second); L.h_val.push_back(e.second); }
+}
+
+__global__ void and_flags_kernel(const int *flags, int n, int *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i] == 0) *out = 0;      // every writer stores the same value
+}
+
+__global__ void gather_kernel(const double *x, const int *idx, int n, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[idx[i]];
+}
+
+__global__ void set_sources_kernel(double *b, const int *rows, const double *vals, int ns) {
+  // one thread: sources may share a row; order is the source order (deterministic)
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < ns; ++k) b[rows[k]] += vals[k];
+}
+
+using xb::sim::pulse_value;
+
+struct GpuBackend {
+  xgpu_ctx *ctx;
+  cudaStream_t s;
+  int n_;
+  std::vector<double *> v;          // kNumVec device vectors
+  double *dFdx = nullptr, *dQdx = nullptr, *J = nullptr, *scratch = nullptr;
+  double *sta[2] = {nullptr, nullptr}, *sto[2] = {nullptr, nullptr};
+  int *d_src_rows = nullptr; double *d_src_vals = nullptr;
+  int *d_probe = nullptr; double *d_probe_out = nullptr;
+  std::vector<int> probes;
+  std::vector<double> times, wave;
+  bool lu_analyzed = false;
+  int rc_alloc = 0;
+  xgpu_solver_state ss{};
+  long long lu_refactors = 0, lu_analyses = 0;
+
+  int n() const { return n_; }
+  void copy(int d, int a) { cudaMemcpyAsync(v[d], v[a], n_ * sizeof(double), cudaMemcpyDeviceToDevice, s); }
+  void fill(int d, double val) { vec::fill(v[d], val, n_, s); ++ctx->launches; }
+  void scale(int d, double a) { vec::axpby(v[d], a, v[d], 0.0, v[d], n_, s); ++ctx->launches; }
+  void axpby(int d, double a, int x, double b, int y) { vec::axpby(v[d], a, v[x], b, v[y], n_, s); ++ctx->launches; }
+  void axpy(int d, double a, int x) { vec::axpby(v[d], 1.0, v[d], a, v[x], n_, s); ++ctx->launches; }
+  double norm2(int x) { ctx->launches += 2; return std::sqrt(vec::reduce(vec::kSumSq, v[x], nullptr, n_, scratch, s)); }
+  double norm_inf(int x) { ctx->launches += 2; return vec::reduce(vec::kMaxAbs, v[x], nullptr, n_, scratch, s); }
+  double wmax_norm(int x, int w) { ctx->launches += 2; return vec::reduce(vec::kWMaxAbs, v[x], v[w], n_, scratch, s); }
+  double wrms_norm(int x, int w) { ctx->launches += 2; return std::sqrt(vec::reduce(vec::kWSumSq, v[x], v[w], n_, scratch, s) / n_); }
+  void sol_weights(int d, double rel, double ab, int a, int b) { vec::sol_weights(v[d], rel, ab, v[a], v[b], n_, s); ++ctx->launches; }
+  void abs_weights(int d, double rel, double ab, int a) { vec::abs_weights(v[d], rel, ab, v[a], n_, s); ++ctx->launches; }
+
+  bool load_rhs(const sim::Flags &fl, double time) {
+    ss.dcopFlag = fl.dcop; ss.tranopFlag = fl.tranop; ss.transientFlag = fl.transient; ss.initTranFlag = fl.initTran;
+    ss.newtonIter = fl.newtonIter; ss.initJctFlag = fl.initJct; ss.currTimeStep = fl.currTimeStep;
+    int rc = xgpu_update_state(ctx, v[sim::vNextSol], sta[0], sta[1], sto[0], sto[1], &ss);
+    rc |= xgpu_load_vectors(ctx, v[sim::vF], v[sim::vQ], v[sim::vFlim], v[sim::vQlim], 0);
+    // linear devices: F += G x, Q += C x  (N_LOA_CktLoader.C:774-782)
+    const XgLinearPart &G = ctx->linG, &C = ctx->linC;
+    vec::spmv_add(G.nrows, G.rows, G.ptr, G.col, G.val, v[sim::vNextSol], v[sim::vF], s);
+    vec::spmv_add(C.nrows, C.rows, C.ptr, C.col, C.val, v[sim::vNextSol], v[sim::vQ], s);
+    ctx->launches += (G.nrows > 0) + (C.nrows > 0);
+    // independent sources evaluated on the host (DeviceMgr::updateSources), B assembled on the device
+    vec::fill(v[sim::vB], 0.0, n_, s); ++ctx->launches;
+    const int ns = (int)ctx->sources.size();
+    if (ns > 0) {
+      std::vector<double> vals(ns);
+      for (int k = 0; k < ns; ++k) {
+        const XgSource &q = ctx->sources[k];
+        vals[k] = q.scale * (q.type == 1 ? pulse_value(q.p, time) : q.p[0]);
+      }
+      cudaMemcpyAsync(d_src_vals, vals.data(), ns * sizeof(double), cudaMemcpyHostToDevice, s);
+      cudaStreamSynchronize(s);     // vals is a stack-lifetime buffer
+      set_sources_kernel<<<1, 32, 0, s>>>(v[sim::vB], d_src_rows, d_src_vals, ns); ++ctx->launches;
+    }
+    return rc == 0;
+  }
+
+  void load_jacobian(double qscalar, double fscalar) {
+    xgpu_load_matrices(ctx, dFdx, dQdx, 0);
+    const XgLinearPart &G = ctx->linG, &C = ctx->linC;
+    vec::scatter_add(G.nnz, G.pos, G.val, dFdx, s);
+    vec::scatter_add(C.nnz, C.pos, C.val, dQdx, s);
+    ctx->launches += (G.nnz > 0) + (C.nnz > 0);
+    xgpu_jacobian_combine(ctx, qscalar, dQdx, fscalar, dFdx, J);
+  }
+
+  int solve() {
+    int rc;
+    if (!lu_analyzed) { rc = xgpu_lu_analyze(ctx, J); lu_analyzed = (rc == 0 || rc == 2); ++lu_analyses; }
+    else {
+      rc = xgpu_lu_refactor(ctx, J); ++lu_refactors;
+      if (rc == 2) { rc = xgpu_lu_analyze(ctx, J); ++lu_analyses; }      // re-pivot on the host
+    }
+    if (rc != 0) { vec::fill(v[sim::vDX], 0.0, n_, s); return rc; }
+    return xgpu_lu_solve(ctx, J, v[sim::vRHS], v[sim::vDX]);
+  }
+
+  bool all_devices_converged() {
+    int one = 1;
+    cudaMemcpyAsync(ctx->d_conv, &one, sizeof(int), cudaMemcpyHostToDevice, s);
+    for (auto &g : ctx->groups) { and_flags_kernel<<<(g.n + 255) / 256, 256, 0, s>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
+    int r = 1;
+    cudaMemcpyAsync(&r, ctx->d_conv, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return r != 0;
+  }
+  bool limiter_active() const { return ss.voltageLimiterFlag != 0; }
+  void accept_state() {
+    cudaMemcpyAsync(sta[1], sta[0], (size_t)ctx->n_state * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(sto[1], sto[0], (size_t)ctx->n_store * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  }
+  void record(double t) {
+    times.push_back(t);
+    const int np = (int)probes.size();
+    if (np == 0) return;
+    gather_kernel<<<(np + 255) / 256, 256, 0, s>>>(v[sim::vNextSol], d_probe, np, d_probe_out); ++ctx->launches;
+    const size_t off = wave.size();
+    wave.resize(off + np);
+    cudaMemcpyAsync(&wave[off], d_probe_out, np * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+  }
+};
+
+int build_linear_dev(xgpu_ctx *ctx, XgLinearPart &L) {
+  // CSR over non-empty rows + position of every entry in the system pattern
+  std::vector<int> rows, ptr(1, 0), col, pos;
+  std::vector<double> val;
+  const size_t m = L.h_row.size();
+  for (size_t k = 0; k < m; ++k) {
+    if (rows.empty() || rows.back() != L.h_row[k]) { if (!rows.empty()) ptr.push_back((int)col.size()); rows.push_back(L.h_row[k]); }
+    col.push_back(L.h_col[k]); val.push_back(L.h_val[k]);
+    const int r = L.h_row[k];
+    const int32_t *b = ctx->colind.data() + ctx->rowptr[r], *e = ctx->colind.data() + ctx->rowptr[r + 1];
+    const int32_t *p = std::lower_bound(b, e, L.h_col[k]);
+    if (p == e || *p != L.h_col[k]) return xg_fail(ctx, 14, "a linear-device stamp entry is missing from the CSR pattern");
+    pos.push_back((int)(p - ctx->colind.data()));
+  }
+  if (!rows.empty()) ptr.push_back((int)col.size());
+  L.nrows = (int)rows.size(); L.nnz = (int)col.size();
+  XS_CUDA(up(&L.rows, rows)); XS_CUDA(up(&L.ptr, ptr)); XS_CUDA(up(&L.col, col)); XS_CUDA(up(&L.pos, pos)); XS_CUDA(up(&L.val, val));
+  return 0;
+}
+
+}  // namespace
+
+int xg_finalize_linear(xgpu_ctx *ctx) {
+  int rc = build_linear_dev(ctx, ctx->linG);
+  if (rc) return rc;
+  return build_linear_dev(ctx, ctx->linC);
+}
+
+extern "C" {
+
+int xgpu_linear_set(xgpu_ctx *ctx, int nG, const int32_t *g_row, const int32_t *g_col, const double *g_val, int nC,
+                    const int32_t *c_row, const int32_t *c_col, const double *c_val) {
+  if (!ctx || nG < 0 || nC < 0) return 1;
+  if (ctx->finalized) return xg_fail(ctx, 5, "linear_set after finalize");
+  merge_coo(nG, g_row, g_col, g_val, ctx->linG);
+  merge_coo(nC, c_row, c_col, c_val, ctx->linC);
+  return 0;
+}
+
+int xgpu_sources_set(xgpu_ctx *ctx, int ns, const int32_t *row, const double *scale, const int32_t *type, const double *params7) {
+  if (!ctx || ns < 0) return 1;
+  ctx->sources.clear();
+  for (int k = 0; k < ns; ++k) {
+    if (row[k] < 0) continue;
+    XgSource q; q.row = row[k]; q.scale = scale[k]; q.type = type[k];
+    std::memcpy(q.p, params7 + 7 * (size_t)k, 7 * sizeof(double));
+    ctx->sources.push_back(q);
+  }
+  return 0;
+}
+
+int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0, int n_probes, const int32_t *probes,
+                  int max_out, int *n_out, double *h_times, double *h_wave, int max_steps_out, int *n_steps_out,
+                  double *h_step_info, double *stats16) {
+  if (!ctx || !tp || !h_x0 || !n_out || !n_steps_out) return 1;
+  if (!ctx->finalized) return xg_fail(ctx, 15, "xgpu_finalize has not been called");
+  XS_CUDA(cudaSetDevice(ctx->device));
+  GpuBackend B;
+  B.ctx = ctx; B.s = ctx->stream; B.n_ = ctx->n;
+  const size_t n = (size_t)ctx->n;
+  B.v.assign(sim::kNumVec, nullptr);
+  double *pool = nullptr;
+  XS_CUDA(cudaMalloc((void **)&pool, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 2048) * sizeof(double)));
+  XS_CUDA(cudaMemsetAsync(pool, 0, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 2048) * sizeof(double), ctx->stream));
+  for (int i = 0; i < sim::kNumVec; ++i) B.v[i] = pool + i * n;
+  B.dFdx = pool + sim::kNumVec * n; B.dQdx = B.dFdx + ctx->nnz; B.J = B.dQdx + ctx->nnz; B.scratch = B.J + ctx->nnz;
+  B.sto[0] = ctx->buf[7]; B.sto[1] = ctx->buf[8]; B.sta[0] = ctx->buf[9]; B.sta[1] = ctx->buf[10];
+  std::vector<int> srows; for (auto &q : ctx->sources) srows.push_back(q.row);
+  XS_CUDA(up(&B.d_src_rows, srows));
+  XS_CUDA(cudaMalloc((void **)&B.d_src_vals, (srows.size() + 1) * sizeof(double)));
+  B.probes.assign(probes, probes + n_probes);
+  XS_CUDA(up(&B.d_probe, B.probes));
+  XS_CUDA(cudaMalloc((void **)&B.d_probe_out, (n_probes + 1) * sizeof(double)));
+  std::memset(&B.ss, 0, sizeof(B.ss));
+  B.ss.voltageLimiterFlag = 1; B.ss.gmin = 1e-12; B.ss.gainScale = 1.0; B.ss.nltermScale = 1.0;
+  B.ss.vgstConst = 4.5; B.ss.vdsScaleMin = 0.3; B.ss.sizeScale = 1.0; B.ss.transientFlag = 1;
+  XS_CUDA(cudaMemcpyAsync(B.v[sim::vNextSol], h_x0, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  XS_CUDA(cudaMemcpyAsync(B.v[sim::vCurrSol], h_x0, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+
+  sim::TranParams P;
+  P.tstop = tp->tstop; P.tstep = tp->tstep; P.delmax = tp->delmax;
+  if (tp->maxNewtonStep > 0) P.maxNewtonStep = tp->maxNewtonStep;
+  if (tp->deltaXTol > 0) P.deltaXTol = tp->deltaXTol;
+  if (tp->absTol > 0) P.absTol = tp->absTol;
+  if (tp->relTol > 0) P.relTol = tp->relTol;
+  if (tp->RHSTol > 0) P.RHSTol = tp->RHSTol;
+  if (tp->relErrorTol > 0) P.relErrorTol = tp->relErrorTol;
+  if (tp->absErrorTol > 0) P.absErrorTol = tp->absErrorTol;
+  if (tp->maxOrder > 0) P.maxOrder = tp->maxOrder;
+  if (tp->maxSteps > 0) P.maxSteps = tp->maxSteps;
+  sim::TransientDriver<GpuBackend> drv(B, P);
+  const int rc = drv.run();
+  XS_CUDA(cudaStreamSynchronize(ctx->stream));
+  XS_CUDA(cudaGetLastError());
+
+  const int nt = (int)B.times.size();
+  *n_out = std::min(nt, max_out);
+  for (int i = 0; i < *n_out; ++i) {
+    if (h_times) h_times[i] = B.times[i];
+    if (h_wave) for (int p = 0; p < n_probes; ++p) h_wave[(size_t)i * n_probes + p] = B.wave[(size_t)i * n_probes + p];
+  }
+  const int nsr = (int)drv.steps.size();
+  *n_steps_out = std::min(nsr, max_steps_out);
+  if (h_step_info)
+    for (int i = 0; i < *n_steps_out; ++i) {
+      const sim::StepRecord &r = drv.steps[i];
+      double *o = h_step_info + 5 * (size_t)i;
+      o[0] = r.t; o[1] = r.h; o[2] = r.newton_iters; o[3] = r.order; o[4] = r.status;
+    }
+  if (stats16) {
+    const sim::TranStats &t = drv.stats;
+    const double st[16] = {(double)t.accepted, (double)t.rejected, (double)t.newton_total, (double)t.jacobian_loads,
+                           (double)t.residual_loads, (double)t.linear_solves, (double)B.lu_analyses, (double)B.lu_refactors,
+                           (double)nt, (double)nsr, (double)rc, 0, 0, 0, 0, 0};
+    std::memcpy(stats16, st, sizeof(st));
+  }
+  cudaFree(pool); cudaFree(B.d_src_rows); cudaFree(B.d_src_vals); cudaFree(B.d_probe); cudaFree(B.d_probe_out);
+  if (rc != 0) return xg_fail(ctx, 200 + rc, rc == 2 ? "transient: time step too small / too many failures" : "transient: step limit reached");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,369 @@
+// xyce_b200 -- host-side caller of the hot path: Newton solve and variable-step transient loop.
+//
+// This is the thin layer that sits directly on top of the loader in the reference (SURVEY.md rows
+// a18, a20 and "next" row f2).  It is a from-scratch restatement of
+//   Nonlinear::DampedNewton::solve / converged_ / updateWeights_   (src/NonlinearSolverPKG/N_NLS_DampedNewton.C:362-515, :1191-1397, :297-360)
+//   TimeIntg::OneStep (trapezoid, variable order 1-2): updateCoeffs, obtainPredictor, obtainResidual,
+//     obtainJacobian, initialize, completeStep, rejectStep, updateHistory
+//                                                                  (src/TimeIntegrationPKG/N_TIA_OneStep.C:135-281, :469-515, :1390-1488, :1584-1669, :1684-1850, :1946-2110, :2124-2310)
+//   TimeIntg::StepErrorControl::evaluateStepError, DataStore::setErrorWtVector / WRMS_errorNorm
+//                                                                  (N_TIA_StepErrorControl.C:470-560, N_TIA_DataStore.C:1300-1520)
+//   Analysis::Transient::doLoopProcess / takeAnIntegrationStep_     (src/AnalysisPKG/N_ANP_Transient.C:1184-1330, :3262-3308)
+// with the transient-mode defaults of N_NLS_NLParams.C:101-112 and N_TIA_TIAParams.C:79-111.
+// The driver is a template over a Backend that owns the vectors and performs the loads, BLAS-1
+// kernels and the linear solve: the product instantiates it with the CUDA backend (sim_gpu.cu); the
+// oracle instantiates the same control flow around the *reference's* device code and Kundert Sparse
+// (oracle/sim_ref.cpp) so that Newton iteration counts and waveforms can be compared.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace xb {
+namespace sim {
+
+// vector slots owned by the backend
+enum Vec {
+  vNextSol, vCurrSol, vF, vQ, vB, vFlim, vQlim, vRHS, vDX, vSolWt, vErrWt, vQErrWt, vXn0, vQn0,
+  vXh0, vXh1, vXh2, vQh0, vQh1, vQh2, vNewtCorr, vQNewtCorr, vTmp, kNumVec
+};
+
+// SPICE PULSE(v1 v2 td tr tf pw per) (PulseData, src/DeviceModelPKG/Core/N_DEV_SourceData.C); no breakpoints.
+inline double pulse_value(const double *p, double t) {
+  const double v1 = p[0], v2 = p[1], td = p[2], tr = p[3], tf = p[4], pw = p[5], per = p[6];
+  double tt = t - td;
+  if (tt <= 0.0) return v1;
+  if (per > 0.0) tt = std::fmod(tt, per);
+  if (tt < tr) return v1 + (v2 - v1) * tt / tr;
+  if (tt < tr + pw) return v2;
+  if (tt < tr + pw + tf) return v2 + (v1 - v2) * (tt - tr - pw) / tf;
+  return v1;
+}
+
+struct TranParams {
+  double tstop = 0, tstep = 0, delmax = 0;
+  // Newton (transient mode defaults)
+  int maxNewtonStep = 20;
+  double deltaXTol = 0.33, absTol = 1e-6, relTol = 1e-2, RHSTol = 1e-2, smallUpdateTol = 1e-6;
+  int enforceDeviceConv = 1;
+  // time integration
+  double relErrorTol = 1e-3, absErrorTol = 1e-6, errTolAcceptance = 1.0;
+  int maxOrder = 2, minOrder = 1;
+  int maxSteps = 1000000;
+};
+
+struct StepRecord { double t, h; int newton_iters, order, status; };
+
+struct TranStats {
+  int accepted = 0, rejected = 0, newton_total = 0, jacobian_loads = 0, residual_loads = 0, linear_solves = 0;
+  int failed = 0;
+};
+
+// Backend concept:
+//   int n(); void copy(Vec dst, Vec src); void fill(Vec, double); void scale(Vec, double);
+//   void axpby(Vec dst, double a, Vec x, double b, Vec y);          dst = a x + b y
+//   void axpy(Vec dst, double a, Vec x);                              dst += a x
+//   double norm2(Vec); double norm_inf(Vec); double wmax_norm(Vec x, Vec w); double wrms_norm(Vec x, Vec w);
+//   void sol_weights(Vec dst, double rel, double abs, Vec a, Vec b);  dst_i = rel*max(|a_i|,|b_i|) + abs
+//   void abs_weights(Vec dst, double rel, double abs, Vec a);         dst_i = rel*|a_i| + abs
+//   bool load_rhs(const Flags&, double time);    evaluates devices at vNextSol: fills vF, vQ, vB, vFlim, vQlim
+//   void load_jacobian(double qscalar, double fscalar);               J = qscalar dQdx + fscalar dFdx
+//   int  solve();                                                      J vDX = vRHS   (0 ok)
+//   bool all_devices_converged(); bool limiter_active();
+//   void accept_state();                                               curr state/store <- next
+//   void record(double t);                                             sample probes
+struct Flags {
+  int dcop = 0, tranop = 0, transient = 1, initTran = 0, newtonIter = 0, initJct = 0;
+  double currTimeStep = 0;
+};
+
+template <class Backend>
+class TransientDriver {
+ public:
+  TransientDriver(Backend &b, const TranParams &p) : B(b), P(p) {}
+  std::vector<StepRecord> steps;
+  TranStats stats;
+
+  // x(0) must already be in vNextSol and vCurrSol ("NOOP / UIC" start, as .TRAN ... NOOP does).
+  int run() {
+    const double machEps = 2.220446049250313e-16;
+    // --- StepErrorControl state (N_TIA_StepErrorControl.C:100-170 defaults) ---
+    initialTime = 0.0; currentTime = 0.0; stopTime = P.tstop;
+    startingTimeStep = P.tstep;
+    maxTimeStep = (P.delmax > 0.0) ? P.delmax : 0.1 * (stopTime - initialTime);
+    minTimeStep = (stopTime - initialTime) * 4.0 * machEps;
+    beginningIntegration = true; stepAttemptStatus = true; stepNumber = 0; iNumCalls = 0;
+    nef = 0;
+    // initial load: Q, F, B at x(0)
+    Flags fl; fl.initTran = 1; fl.newtonIter = 0; fl.currTimeStep = startingTimeStep;
+    B.load_rhs(fl, 0.0); ++stats.residual_loads;
+    set_error_weights();
+    B.fill(vQh1, 0.0);
+    initialize_integrator();          // Transient::doInit
+    B.record(0.0);
+    while (!(currentTime >= stopTime - minTimeStep)) {
+      if ((int)steps.size() >= P.maxSteps) return 3;
+      if (beginningIntegration && stepAttemptStatus) initialize_integrator();
+      update_coeffs();
+      // predictor (OneStep::obtainPredictor)
+      B.copy(vXn0, vXh0); B.copy(vQn0, vQh0);
+      for (int i = 1; i <= currentOrder; ++i) B.axpy(vXn0, beta[i], i == 1 ? vXh1 : vXh2);
+      B.copy(vNextSol, vXn0);
+      const int status = newton_solve();
+      // stepLinearCombo + evaluateStepError
+      B.axpby(vNewtCorr, 1.0, vNextSol, -1.0, vXn0);
+      B.axpby(vQNewtCorr, 1.0, vQ, -1.0, vQn0);
+      bool ok = status > 0;
+      newtonConvergenceStatus = status;
+      const bool testError = ok && stepNumber >= 1 && !beginningIntegration;
+      if (testError) {
+        estOverTol = ck * B.wrms_norm(vNewtCorr, vErrWt);
+        ok = estOverTol <= P.errTolAcceptance;
+      }
+      stepAttemptStatus = ok;
+      StepRecord rec{nextTime, currentTimeStep, nIterations, currentOrder, status};
+      if (ok) {
+        complete_step();
+        B.copy(vCurrSol, vNextSol);
+        B.accept_state();
+        ++stepNumber; ++stats.accepted;
+        beginningIntegration = false;
+        set_error_weights();
+        B.record(currentTime);
+      } else {
+        ++stats.rejected;
+        rec.status = status > 0 ? -100 : status;    // -100: rejected by the LTE test
+        if (!reject_step()) { steps.push_back(rec); stats.failed = 1; return 2; }
+      }
+      steps.push_back(rec);
+    }
+    return 0;
+  }
+
+ private:
+  Backend &B;
+  TranParams P;
+  // StepErrorControl / OneStep members (same names as the reference where possible)
+  double initialTime, currentTime, nextTime, stopTime, lastTime;
+  double currentTimeStep, lastTimeStep, currentTimeStepRatio, currentTimeStepSum, savedTimeStep = 0;
+  double startingTimeStep, minTimeStep, maxTimeStep;
+  double psi[3] = {0, 0, 0}, beta[3] = {1, 0, 0}, alphas = -1.0, ck = 1.0, estOverTol = 0.0;
+  int currentOrder = 1, usedOrder = 1, numberOfSteps = 0, nef = 0, stepNumber = 0, nIterations = 0;
+  int newtonConvergenceStatus = 0, iNumCalls = 0;
+  bool beginningIntegration = true, stepAttemptStatus = true;
+  const double tolAimFac = 0.5, r_min = 0.25, r_max = 0.9, r_hincr_test = 2.0, r_hincr = 2.0;
+  const double h0_safety = 2.0, h0_max_factor = 0.005;
+  const int maxNumfail = 15;
+
+  void set_error_weights() {      // DataStore::setErrorWtVector, newLte = 1 ("point global")
+    const double m = B.norm_inf(vCurrSol);
+    B.fill(vErrWt, P.relErrorTol * m + P.absErrorTol);
+    B.abs_weights(vQErrWt, P.relErrorTol, P.absErrorTol, vQ);
+  }
+
+  void initialize_integrator() {  // OneStep::initialize
+    const double time_to_stop = stopTime - currentTime;
+    // the reference measures qHistory[1] as it stands on entry (zero before the very first call, the
+    // previous call's -h (F - B) afterwards: Transient::doInit calls initialize once before the loop)
+    const double dnorm_q = B.wrms_norm(vQh1, vQErrWt);
+    double h;
+    if (dnorm_q > 0.0) {
+      if (currentTime == initialTime) h = std::min(h0_max_factor * std::fabs(time_to_stop), std::sqrt(2.0) / (h0_safety * dnorm_q));
+      else h = 0.1 * std::min(savedTimeStep, std::fabs(time_to_stop));
+    } else {
+      if (currentTime == initialTime) h = h0_max_factor * std::fabs(time_to_stop);
+      else h = 0.1 * std::min(savedTimeStep, std::fabs(time_to_stop));
+    }
+    if (startingTimeStep > 0.0 && currentTime == initialTime) h = std::min(startingTimeStep, h);
+    if (currentTime != initialTime) currentTimeStep = std::min(currentTimeStep, h);
+    else currentTimeStep = h;
+    currentTimeStep = std::max(currentTimeStep, minTimeStep);
+    currentTimeStep = std::min(currentTimeStep, maxTimeStep);
+    currentTimeStepRatio = 1.0;
+    currentTimeStepSum = 2.0 * currentTimeStep;
+    lastTimeStep = currentTimeStep;
+    nextTime = currentTime + currentTimeStep;
+    B.copy(vXh0, vCurrSol);
+    B.fill(vXh1, 0.0);
+    B.copy(vQh0, vQ);
+    B.axpby(vQh1, 1.0, vF, -1.0, vB);
+    B.scale(vQh1, -currentTimeStep);
+    numberOfSteps = 0; currentOrder = 1; usedOrder = 1;
+    psi[0] = currentTimeStep;
+    nef = 0;
+  }
+
+  void update_coeffs() {          // OneStep::updateCoeffs
+    const double t1 = currentTimeStep;
+    if (currentOrder == 2) psi[2] = psi[1];
+    psi[1] = psi[0];
+    psi[0] = t1;
+    beta[0] = 1.0; alphas = -1.0;
+    if (currentOrder == 2) {
+      const double t2 = psi[1];
+      beta[1] = t1 / t2 + (t1 / t2) * (t1 / t2) / 2;
+      beta[2] = -1.0 * t1 * t1 / t2 / psi[2] / 2;
+      ck = (currentTimeStep / currentTimeStepSum) / 3.0;
+    } else {
+      beta[1] = t1 / psi[1];
+      ck = currentTimeStep / currentTimeStepSum;
+    }
+  }
+
+  // residual of OneStep::obtainResidual: RHS = -[(Q - q0)/h + f (F - B) (+ 1/2 qHistory[2])] + limiter terms
+  double residual(const Flags &fl) {
+    B.load_rhs(fl, nextTime); ++stats.residual_loads;
+    B.axpby(vRHS, 1.0, vQ, -1.0, vQh0);
+    const double inv_h = 1.0 / currentTimeStep;
+    const double fs = (currentOrder == 2) ? 0.5 : 1.0;
+    B.axpby(vTmp, fs, vF, -fs, vB);
+    B.axpby(vRHS, inv_h, vRHS, 1.0, vTmp);
+    if (currentOrder == 2) B.axpy(vRHS, 0.5, vQh2);
+    B.scale(vRHS, -1.0);
+    if (B.limiter_active()) {
+      B.axpy(vRHS, -alphas / currentTimeStep, vQlim);
+      B.axpy(vRHS, fs, vFlim);
+    }
+    return B.norm2(vRHS);
+  }
+
+  int newton_solve() {            // DampedNewton::solve with FULL search (step length 1)
+    Flags fl; fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep;
+    int nlStep = 0;
+    fl.newtonIter = 0;
+    double normRHS = residual(fl);
+    double normRHS_old = normRHS, normRHS_init = normRHS;
+    B.sol_weights(vSolWt, P.relTol, P.absTol, vNextSol, vCurrSol);     // updateWeights_ (transient: once per solve)
+    int status = 0, count = 0;
+    double tmpConvRate = 0.0;
+    const double fs = (currentOrder == 2) ? 0.5 : 1.0;
+    while (status == 0) {
+      ++nlStep;
+      B.load_jacobian(-alphas / currentTimeStep, fs); ++stats.jacobian_loads;
+      const int lin = B.solve(); ++stats.linear_solves;
+      B.axpy(vNextSol, 1.0, vDX);
+      fl.newtonIter = nlStep;
+      normRHS = residual(fl);
+      // ---- converged_ ----
+      if (lin != 0) { status = -9; break; }
+      if (P.enforceDeviceConv) {
+        const bool conv = B.all_devices_converged();
+        if (!conv && nlStep < P.maxNewtonStep) continue;
+        if (!conv && nlStep >= P.maxNewtonStep) { status = -1; break; }
+      }
+      if (!(normRHS == normRHS)) { status = -6; break; }
+      const double maxNormRHS = B.norm_inf(vRHS);
+      const double wtNormDX = B.wmax_norm(vDX, vSolWt);
+      if (normRHS < 2.220446049250313e-16) { status = 1; break; }     // normTooSmall
+      const double normRHS_rel = normRHS / normRHS_init;
+      const double resConvRate = normRHS / normRHS_old;
+      normRHS_old = normRHS;
+      const double updateSize = wtNormDX;
+      if (maxNormRHS <= P.RHSTol && updateSize <= P.deltaXTol) { status = 2; break; }
+      if (nlStep >= P.maxNewtonStep && normRHS_rel <= 0.9 && resConvRate <= 1.0) { status = 3; break; }
+      if (updateSize <= P.smallUpdateTol) { status = 4; break; }
+      if (nlStep >= P.maxNewtonStep) { status = -1; break; }
+      if (resConvRate > 0.5 * 1.7976931348623157e308) { status = -2; break; }
+      if (std::fabs(resConvRate - 1.0) <= 1.0e-3) {
+        if (count == 0 || resConvRate < tmpConvRate) tmpConvRate = resConvRate;
+        ++count;
+      } else {
+        count = 0;
+      }
+      if (count == 5) {
+        count = 0;
+        status = (normRHS_rel < 0.9 && tmpConvRate <= 1.0) ? 3 : -3;
+        break;
+      }
+    }
+    nIterations = nlStep;
+    stats.newton_total += nlStep;
+    ++iNumCalls;
+    return status;
+  }
+
+  void update_history() {         // OneStep::updateHistory
+    if (currentOrder == 2) {
+      B.copy(vXh2, vXh1);
+      B.axpby(vQh2, 1.0, vF, -1.0, vB);
+    }
+    B.axpby(vXh1, 1.0, vNextSol, -1.0, vXh0);
+    B.axpby(vQh1, 1.0, vQ, -1.0, vQh0);
+    B.copy(vXh0, vNextSol);
+    B.copy(vQh0, vQ);
+  }
+
+  void complete_step() {          // OneStep::completeStep (LOCAL_TRUNCATED_ESTIMATES)
+    ++numberOfSteps;
+    nef = 0;
+    lastTime = currentTime;
+    currentTime = nextTime;
+    double newTimeStep = currentTimeStep;
+    lastTimeStep = currentTimeStep;
+    usedOrder = currentOrder;
+    double rr = tolAimFac / (estOverTol + 0.0001);
+    rr = std::pow(rr, 1.0 / (currentOrder + 1.0));
+    if (numberOfSteps >= 2 && P.maxOrder == 2) {
+      if (currentOrder == 1) {
+        currentOrder = 2;
+        rr = tolAimFac / (estOverTol + 0.0001);
+        rr = std::pow(rr, 1.0 / (currentOrder + 1.0));
+        if (rr <= 1.05) currentOrder = P.minOrder;
+      }
+    }
+    if (rr >= r_hincr_test) { rr = r_hincr; newTimeStep = rr * currentTimeStep; }
+    else if (rr <= 1) { rr = std::max(r_min, std::min(r_max, rr)); newTimeStep = rr * currentTimeStep; }
+    // updateHistory uses the order the step was taken with
+    const int orderNow = currentOrder;
+    currentOrder = usedOrder;
+    update_history();
+    currentOrder = orderNow;
+    newTimeStep = std::max(newTimeStep, minTimeStep);
+    newTimeStep = std::min(newTimeStep, maxTimeStep);
+    if ((stopTime - currentTime) >= minTimeStep) {
+      double nextTimePt = currentTime + newTimeStep;
+      if (nextTimePt > stopTime) {
+        savedTimeStep = newTimeStep;
+        nextTimePt = stopTime;
+        newTimeStep = stopTime - currentTime;
+      }
+      nextTime = nextTimePt;
+      currentTimeStepRatio = newTimeStep / lastTimeStep;
+      currentTimeStepSum = newTimeStep + lastTimeStep;
+      currentTimeStep = newTimeStep;
+    }
+  }
+
+  bool reject_step() {            // OneStep::rejectStep
+    double newTimeStep = currentTimeStep;
+    ++nef;
+    for (int i = 1; i <= currentOrder; ++i) psi[i - 1] = psi[i];     // restoreHistory
+    if (nef >= maxNumfail) return false;
+    if (newtonConvergenceStatus <= 0) {
+      newTimeStep = currentTimeStep / 8;
+      currentOrder = P.minOrder;
+    } else if (nef == 1) {
+      currentOrder = P.minOrder;
+      double rr = tolAimFac / (estOverTol + 0.0001);
+      rr = std::pow(rr, 1.0 / (currentOrder + 1.0));
+      rr = std::max(r_min, std::min(r_max, rr));
+      newTimeStep = rr * currentTimeStep;
+    } else {
+      newTimeStep = r_min * currentTimeStep;
+      currentOrder = P.minOrder;
+    }
+    newTimeStep = std::max(newTimeStep, minTimeStep);
+    newTimeStep = std::min(newTimeStep, maxTimeStep);
+    double nextTimePt = currentTime + newTimeStep;
+    if (nextTimePt > stopTime) { nextTimePt = stopTime; newTimeStep = stopTime - currentTime; }
+    nextTime = nextTimePt;
+    currentTimeStepRatio = newTimeStep / lastTimeStep;
+    currentTimeStepSum = newTimeStep + lastTimeStep;
+    currentTimeStep = newTimeStep;
+    if (currentTimeStep <= minTimeStep) return false;
+    return true;
+  }
+};
+
+}  // namespace sim
+}  // namespace xb

@@ -1,0 +1,108 @@
+#include "vecops.cuh"
+namespace xb {
+namespace vec {
+namespace {
+__global__ void fill_k(double *d, double v, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = v; }
+__global__ void axpby_k(double *dst, double a, const double *x, double b, const double *y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a * x[i] + b * y[i];
+}
+__global__ void solw_k(double *dst, double rel, double ab, const double *a, const double *b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = rel * fmax(fabs(a[i]), fabs(b[i])) + ab;
+}
+__global__ void absw_k(double *dst, double rel, double ab, const double *a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = rel * fabs(a[i]) + ab;
+}
+template <int MODE>
+__device__ __forceinline__ double term(const double *x, const double *w, int i) {
+  if (MODE == kSumSq) return x[i] * x[i];
+  if (MODE == kMaxAbs) return fabs(x[i]);
+  if (MODE == kWMaxAbs) return fabs(x[i] / w[i]);
+  const double t = x[i] / w[i];
+  return t * t;
+}
+template <int MODE>
+__device__ __forceinline__ double comb(double a, double b) {
+  if (MODE == kMaxAbs || MODE == kWMaxAbs) return (a != a || b != b) ? (a + b) : fmax(a, b);   // NaN propagates
+  return a + b;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) reduce_k(const double *x, const double *w, int n, double *out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) acc = comb<MODE>(acc, term<MODE>(x, w, i));
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = comb<MODE>(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) reduce_final_k(double *part, int m) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < m; i += 256) acc = comb<MODE>(acc, part[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = comb<MODE>(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[0] = sh[0];
+}
+template <int MODE>
+double reduce_t(const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
+  const int blocks = n < 256 * 1024 ? (n + 255) / 256 : 1024;
+  reduce_k<MODE><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, w, n, scratch);
+  reduce_final_k<MODE><<<1, 256, 0, s>>>(scratch, blocks > 0 ? blocks : 1);
+  double h = 0.0;
+  cudaMemcpyAsync(&h, scratch, sizeof(double), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return h;
+}
+__global__ void spmv_add_k(int nrows, const int *rows, const int *ptr, const int *col, const double *val,
+                           const double *x, double *y) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  double acc = 0.0;
+  for (int k = ptr[r]; k < ptr[r + 1]; ++k) acc += val[k] * x[col[k]];
+  y[rows[r]] += acc;
+}
+__global__ void scatter_add_k(int n, const int *pos, const double *v, double *vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vals[pos[i]] += v[i];
+}
+inline int nb(int n) { return (n + 255) / 256; }
+}  // namespace
+
+void fill(double *d, double v, int n, cudaStream_t s) { if (n > 0) fill_k<<<nb(n), 256, 0, s>>>(d, v, n); }
+void axpby(double *dst, double a, const double *x, double b, const double *y, int n, cudaStream_t s) {
+  if (n > 0) axpby_k<<<nb(n), 256, 0, s>>>(dst, a, x, b, y, n);
+}
+void sol_weights(double *dst, double rel, double ab, const double *a, const double *b, int n, cudaStream_t s) {
+  if (n > 0) solw_k<<<nb(n), 256, 0, s>>>(dst, rel, ab, a, b, n);
+}
+void abs_weights(double *dst, double rel, double ab, const double *a, int n, cudaStream_t s) {
+  if (n > 0) absw_k<<<nb(n), 256, 0, s>>>(dst, rel, ab, a, n);
+}
+double reduce(Reduce mode, const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
+  switch (mode) {
+    case kSumSq: return reduce_t<kSumSq>(x, w, n, scratch, s);
+    case kMaxAbs: return reduce_t<kMaxAbs>(x, w, n, scratch, s);
+    case kWMaxAbs: return reduce_t<kWMaxAbs>(x, w, n, scratch, s);
+    default: return reduce_t<kWSumSq>(x, w, n, scratch, s);
+  }
+}
+void spmv_add(int nrows, const int *rows, const int *ptr, const int *col, const double *val, const double *x,
+              double *y, cudaStream_t s) {
+  if (nrows > 0) spmv_add_k<<<nb(nrows), 256, 0, s>>>(nrows, rows, ptr, col, val, x, y);
+}
+void scatter_add(int n, const int *pos, const double *v, double *vals, cudaStream_t s) {
+  if (n > 0) scatter_add_k<<<nb(n), 256, 0, s>>>(n, pos, v, vals);
+}
+}  // namespace vec
+}  // namespace xb
