@@ -1,0 +1,27 @@
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_tran.py -x -q -m gpu 2>&1 | grep -E "^E " | head -20
+cat > /tmp/one.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+from xyce_b200 import workloads as wl
+w = wl.ring_oscillator_array(4950, 101)
+eng = wl.build_engine(w)
+r = eng.tran_run(w["x"], 1e-11, 1e-12, [0])
+print(r["stats"])
+PY
+ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 600 --csv --log-file gpurun_out/launches_tran.csv python /tmp/one.py > gpurun_out/tran_ncu.log 2>&1
+python - <<'PY'
+import csv, collections
+rows = list(csv.reader(open("gpurun_out/launches_tran.csv")))
+hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+h = rows[hdr]
+ik, iv = h.index("Kernel Name"), h.index("Metric Value")
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[hdr + 1:]:
+    if len(r) <= iv: continue
+    name = r[ik].split("(")[0][-60:]
+    agg[name][0] += 1; agg[name][1] += float(r[iv].replace(",", ""))
+tot = sum(v[1] for v in agg.values())
+for k, v in sorted(agg.items(), key=lambda t: -t[1][1]):
+    print("%-62s n=%4d total=%10.1f us  %5.1f%%  avg=%8.1f us" % (k, v[0], v[1] / 1e3, 100 * v[1] / tot, v[1] / 1e3 / v[0]))
+PY
