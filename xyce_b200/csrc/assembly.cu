@@ -62,16 +62,28 @@ __global__ void __launch_bounds__(256) gather_chunk_kernel(GatherMapDev m, Plane
 }
 
 template <int NP>
-__global__ void __launch_bounds__(128) gather_long_finish_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m.nlong) return;
+__global__ void __launch_bounds__(256) gather_long_finish_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
+  __shared__ double sh[NP][256];
+  const int j = blockIdx.x;
   const int d = m.long_dst[j];
+  double acc[NP];
 #pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    double acc = accumulate ? ps.out[p][d] : 0.0;
-    for (int c = m.long_chunk_ptr[j]; c < m.long_chunk_ptr[j + 1]; ++c) acc += m.partials[(size_t)p * m.nchunks + c];
-    ps.out[p][d] = acc;
+  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
+  for (int c = m.long_chunk_ptr[j] + threadIdx.x; c < m.long_chunk_ptr[j + 1]; c += 256) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] += m.partials[(size_t)p * m.nchunks + c];
   }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] += sh[p][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < NP) ps.out[threadIdx.x][d] = (accumulate ? ps.out[threadIdx.x][d] : 0.0) + sh[threadIdx.x][0];
 }
 
 __global__ void __launch_bounds__(256) linear_combo_kernel(int64_t nnz, double a, const double *__restrict__ A,
@@ -95,7 +107,7 @@ void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaS
   if (m.ndst > 0) gather_short_kernel<NP><<<(m.ndst + 255) / 256, 256, 0, stream>>>(m, ps, accumulate);
   if (m.nlong > 0) {
     gather_chunk_kernel<NP><<<m.nchunks, 256, 0, stream>>>(m, ps);
-    gather_long_finish_kernel<NP><<<(m.nlong + 127) / 128, 128, 0, stream>>>(m, ps, accumulate);
+    gather_long_finish_kernel<NP><<<m.nlong, 256, 0, stream>>>(m, ps, accumulate);
   }
 }
 

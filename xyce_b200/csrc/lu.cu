@@ -72,6 +72,53 @@ __global__ void __launch_bounds__(256) lu_permute_rhs_kernel(LuDev d, const doub
   if (t < d.n) d.work[t] = rhs[d.row_perm[t]];
 }
 
+// Off-diagonal pull of one level: y[r] -= sum_q A[offr_src[q]] * y[offr_col[q]].  Short rows: one warp per
+// row (lane-strided partial sums, shuffle tree).  Long rows (supply rails with ~1e6 entries): one block per
+// 4096-entry chunk with a fixed-shape tree, then one block per row over the chunk partials.  Fixed shapes
+// and orders, no atomics.
+__global__ void __launch_bounds__(256) lu_pull_short_kernel(LuDev d, const double *__restrict__ A, int first, int count) {
+  const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const int r = d.pull_short_rows[first + w];
+  double acc = 0.0;
+  for (int q = d.offr_ptr[r] + lane; q < d.offr_ptr[r + 1]; q += 32) acc += A[d.offr_src[q]] * d.work[d.offr_col[q]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) d.work[r] -= acc;
+}
+
+__device__ __forceinline__ double block_tree_sum(double v, double *sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(256) lu_pull_chunk_kernel(LuDev d, const double *__restrict__ A, int first_chunk) {
+  __shared__ double sh[256];
+  const int c = first_chunk + blockIdx.x;
+  const int r = d.pull_long_rows[d.pull_chunk_row_slot[c]];
+  const int b = d.pull_chunk_begin[c];
+  const int e = min(b + 4096, d.offr_ptr[r + 1]);
+  double acc = 0.0;
+  for (int q = b + threadIdx.x; q < e; q += 256) acc += A[d.offr_src[q]] * d.work[d.offr_col[q]];
+  const double t = block_tree_sum(acc, sh);
+  if (threadIdx.x == 0) d.pull_partials[c] = t;
+}
+
+__global__ void __launch_bounds__(256) lu_pull_finish_kernel(LuDev d, int first_slot) {
+  __shared__ double sh[256];
+  const int slot = first_slot + blockIdx.x;
+  const int r = d.pull_long_rows[slot];
+  double acc = 0.0;
+  for (int c = d.pull_long_chunk_ptr[slot] + threadIdx.x; c < d.pull_long_chunk_ptr[slot + 1]; c += 256) acc += d.pull_partials[c];
+  const double t = block_tree_sum(acc, sh);
+  if (threadIdx.x == 0) d.work[r] -= t;
+}
+
 // One level of the block back-substitution: every block of the level pulls the contributions of the
 // already-solved later blocks into its right-hand side, then does L and U solves inside the block.
 __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev d, const double *__restrict__ A,
@@ -83,17 +130,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev
   const int b = d.level_blocks[first + idx];
   const int k0 = d.block_ptr[b], k1 = d.block_ptr[b + 1];
   double *y = d.work;
-  // pull off-diagonal contributions (fixed summation order: lane-strided partial sums, shuffle tree)
-  for (int r = k0; r < k1; ++r) {
-    const int qb = d.offr_ptr[r], qe = d.offr_ptr[r + 1];
-    if (qb == qe) continue;
-    double acc = 0.0;
-    for (int q = qb + lane; q < qe; q += 32) acc += A[d.offr_src[q]] * y[d.offr_col[q]];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[r] -= acc;
-  }
-  __syncwarp();
   // forward substitution with unit-lower L
   for (int k = k0; k < k1; ++k) {
     const double yk = y[k];
@@ -126,6 +162,8 @@ void free_plan(LuDev &d) {
   cudaFree(d.Up); cudaFree(d.Ui); cudaFree(d.Lx); cudaFree(d.Ux); cudaFree(d.acol_ptr); cudaFree(d.acol_row);
   cudaFree(d.acol_src); cudaFree(d.offr_ptr); cudaFree(d.offr_col); cudaFree(d.offr_src);
   cudaFree(d.level_blocks); cudaFree(d.work); cudaFree(d.status);
+  cudaFree(d.pull_short_rows); cudaFree(d.pull_long_rows); cudaFree(d.pull_chunk_row_slot); cudaFree(d.pull_chunk_begin);
+  cudaFree(d.pull_long_chunk_ptr); cudaFree(d.pull_partials);
   d = LuDev();
 }
 
@@ -139,7 +177,10 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
 #define UP(f) if ((e = up(&d.f, p.f)) != cudaSuccess) return e;
   UP(row_perm) UP(col_perm) UP(block_ptr) UP(Lp) UP(Li) UP(Up) UP(Ui) UP(Lx) UP(Ux)
   UP(acol_ptr) UP(acol_row) UP(acol_src) UP(offr_ptr) UP(offr_col) UP(offr_src) UP(level_blocks)
+  UP(pull_short_rows) UP(pull_long_rows) UP(pull_chunk_row_slot) UP(pull_chunk_begin) UP(pull_long_chunk_ptr)
 #undef UP
+  d.pull_short_ptr = p.pull_short_ptr; d.pull_long_ptr = p.pull_long_ptr; d.pull_chunk_ptr = p.pull_chunk_ptr;
+  if ((e = cudaMalloc((void **)&d.pull_partials, (p.pull_chunk_begin.size() + 1) * sizeof(double))) != cudaSuccess) return e;
   if ((e = cudaMalloc((void **)&d.work, (size_t)(p.n > 0 ? p.n : 1) * sizeof(double))) != cudaSuccess) return e;
   if ((e = cudaMalloc((void **)&d.status, sizeof(int))) != cudaSuccess) return e;
   return cudaMemset(d.status, 0, sizeof(int));
@@ -158,6 +199,14 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
   for (int l = 0; l < d.nlevels; ++l) {
     const int first = d.level_ptr[l], count = d.level_ptr[l + 1] - first;
     if (count <= 0) continue;
+    const int ns = d.pull_short_ptr[l + 1] - d.pull_short_ptr[l];
+    if (ns > 0) { lu_pull_short_kernel<<<(ns * 32 + 255) / 256, 256, 0, s>>>(d, A, d.pull_short_ptr[l], ns); ++launches; }
+    const int nc = d.pull_chunk_ptr[l + 1] - d.pull_chunk_ptr[l], nl = d.pull_long_ptr[l + 1] - d.pull_long_ptr[l];
+    if (nl > 0) {
+      lu_pull_chunk_kernel<<<nc, 256, 0, s>>>(d, A, d.pull_chunk_ptr[l]);
+      lu_pull_finish_kernel<<<nl, 256, 0, s>>>(d, d.pull_long_ptr[l]);
+      launches += 2;
+    }
     lu_solve_level_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, s>>>(d, A, first, count, x);
     ++launches;
   }

@@ -30,6 +30,12 @@ struct LuPlan {
   std::vector<int> offr_ptr, offr_col, offr_src;
   // block levels for the solve: blocks in level l depend only on blocks in levels < l
   std::vector<int> level_ptr, level_blocks;
+  // rows (positions) of each level that own off-diagonal entries, split by list length:
+  // short rows are pulled by one warp each, long rows (supply rails) by chunked block reductions
+  std::vector<int> pull_short_ptr, pull_short_rows;      // per level
+  std::vector<int> pull_long_ptr, pull_long_rows;        // per level
+  std::vector<int> pull_chunk_ptr, pull_chunk_row_slot, pull_chunk_begin;   // per level: chunks of the long rows
+  std::vector<int> pull_long_chunk_ptr;                  // per long row slot: its chunk range
   double refactor_flops = 0.0;
 };
 
@@ -49,6 +55,10 @@ struct LuDev {
   int *offr_ptr = nullptr, *offr_col = nullptr, *offr_src = nullptr;
   int *level_blocks = nullptr;
   std::vector<int> level_ptr;     // host copy: one launch per level
+  int *pull_short_rows = nullptr, *pull_long_rows = nullptr, *pull_chunk_row_slot = nullptr, *pull_chunk_begin = nullptr;
+  int *pull_long_chunk_ptr = nullptr;
+  std::vector<int> pull_short_ptr, pull_long_ptr, pull_chunk_ptr;   // host copies
+  double *pull_partials = nullptr;
   double *work = nullptr;         // [n] dense column / solution work vector
   int *status = nullptr;          // device flag: != 0 when a zero or non-finite pivot was met
 };

@@ -383,6 +383,31 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
     std::vector<int> fill(plan.level_ptr.begin(), plan.level_ptr.end() - 1);
     for (int b = 0; b < nblocks; ++b) plan.level_blocks[fill[level[b]]++] = b;
   }
+  // off-diagonal pull lists per level
+  {
+    const int kLongRow = 4096, kPullChunk = 4096;
+    plan.pull_short_ptr.assign(1, 0); plan.pull_long_ptr.assign(1, 0); plan.pull_chunk_ptr.assign(1, 0);
+    plan.pull_long_chunk_ptr.assign(1, 0);
+    for (int l = 0; l <= maxlevel; ++l) {
+      for (int q = plan.level_ptr[l]; q < plan.level_ptr[l + 1]; ++q) {
+        const int b = plan.level_blocks[q];
+        for (int r = bptr[b]; r < bptr[b + 1]; ++r) {
+          const int cnt = plan.offr_ptr[r + 1] - plan.offr_ptr[r];
+          if (cnt == 0) continue;
+          if (cnt <= kLongRow) { plan.pull_short_rows.push_back(r); continue; }
+          const int slot = (int)plan.pull_long_rows.size();
+          plan.pull_long_rows.push_back(r);
+          for (int c0 = plan.offr_ptr[r]; c0 < plan.offr_ptr[r + 1]; c0 += kPullChunk) {
+            plan.pull_chunk_row_slot.push_back(slot); plan.pull_chunk_begin.push_back(c0);
+          }
+          plan.pull_long_chunk_ptr.push_back((int)plan.pull_chunk_begin.size());
+        }
+      }
+      plan.pull_short_ptr.push_back((int)plan.pull_short_rows.size());
+      plan.pull_long_ptr.push_back((int)plan.pull_long_rows.size());
+      plan.pull_chunk_ptr.push_back((int)plan.pull_chunk_begin.size());
+    }
+  }
   // flop count of one refactorization: sum_k 2 |L_k| |U_k(offdiag)| + divisions
   double fl = 0.0;
   for (int k = 0; k < n; ++k) {
