@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tran.py -x -q -m gpu 2>&1 | grep -E "^E " | head -20
+python -m pytest tests/test_gpu_tran.py -x -q -m gpu 2>&1 | tail -2
 cat > /tmp/one.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
