@@ -75,6 +75,17 @@ int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const
 int xgpu_b4_group_add(xgpu_ctx *ctx, int n_inst, const double *inst_d, const int32_t *inst_i,
                       const int32_t *model_idx, const int32_t *size_idx, const int32_t *lids12,
                       const int32_t *sto_lid0, int sto_stride, const int32_t *sta_lid0, int sta_stride);
+/* ---- small compact models: junction diode (type 1), MOSFET level 1 (2), Gummel-Poon BJT (3), ADMS-shaped
+ * series RLC (4) ----
+ * One flat record per instance holding the model-card values and the temperature-adjusted instance
+ * constants the reference computes in processParams/updateTemperature (field order:
+ * xyce_b200/csrc/simple_fields.def), a flag word, the node LIDs in the device's own node order, and the
+ * first store / state LID.  Replaces Device::addInstance + registerLIDs/StoreLIDs/StateLIDs of
+ * N_DEV_Diode.C, N_DEV_MOSFET1.C, N_DEV_BJT.C and the ADMS-generated classes.  Returns the group id. */
+int xgpu_simple_field_count(int type);
+int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n_inst, const double *rec, const int32_t *flags,
+                          const int32_t *lids, const int32_t *sto_lid0, int sto_stride,
+                          const int32_t *sta_lid0, int sta_stride);
 /* Builds the stamp -> CSR gather maps (replaces Instance::registerJacLIDs/setupPointers,
  * N_DEV_MOSFET_B4.C:6524-6846, and Indexor::matrixGlobalToLocal, N_TOP_Indexor.C:149-214). */
 int xgpu_finalize(xgpu_ctx *ctx);

@@ -25,6 +25,9 @@
 
 // compiled with -fno-access-control (oracle/Makefile): the harness reads private members
 #include <N_DEV_MOSFET_B4.h>
+#include <N_DEV_MOSFET1.h>
+#include <N_DEV_Diode.h>
+#include <N_DEV_BJT.h>
 #include <N_DEV_Configuration.h>
 #include <N_DEV_DeviceBlock.h>
 #include <N_DEV_DeviceMaster.h>
@@ -94,6 +97,7 @@ class CsrMatrix : public Linear::Matrix {
 
 struct InstRec {
   DeviceInstance *inst;
+  int dev;                   // index into Ctx::masters
   std::vector<int> ext;      // external node ids (-1 = ground)
   std::vector<int> lids;     // ext + int LIDs
   int sta0, sto0;
@@ -105,8 +109,38 @@ struct Ctx {
   ExternData extData;
   MatrixLoadData mlData;
   FactoryBlock *fb = 0;
-  Config<MOSFET_B4::Traits> *cfgB4 = 0;
-  Xyce::Device::Device *masterB4 = 0;
+  // one Master per device type, in creation order (= DeviceMgr::devicePtrVec_ order)
+  std::vector<Xyce::Device::Device *> masters;
+  std::vector<std::string> masterType;
+  std::vector<Configuration *> masterCfg;
+  int master(const std::string &t) {
+    for (size_t i = 0; i < masterType.size(); ++i) if (masterType[i] == t) return (int)i;
+    Configuration *cfg = 0; Xyce::Device::Device *m = 0;
+    if (t == "b4") { auto *c = &Config<MOSFET_B4::Traits>::addConfiguration(); cfg = c; m = MOSFET_B4::Traits::factory(*c, *fb); }
+    else if (t == "m1") { auto *c = &Config<MOSFET1::Traits>::addConfiguration(); cfg = c; m = MOSFET1::Traits::factory(*c, *fb); }
+    else if (t == "d") { auto *c = &Config<Diode::Traits>::addConfiguration(); cfg = c; m = Diode::Traits::factory(*c, *fb); }
+    else if (t == "q") { auto *c = &Config<BJT::Traits>::addConfiguration(); cfg = c; m = BJT::Traits::factory(*c, *fb); }
+    else return -1;
+    masters.push_back(m); masterType.push_back(t); masterCfg.push_back(cfg);
+    return (int)masters.size() - 1;
+  }
+  bool updateAll() {
+    bool ok = true;
+    for (auto *m : masters) ok = m->updateState(sol.data(), nextSta.data(), nextSto.data()) && ok;
+    for (auto *m : masters) ok = m->updateSecondaryState(staDeriv.data(), nextSto.data()) && ok;
+    return ok;
+  }
+  bool loadVectorsAll() {
+    bool ok = true;
+    for (auto *m : masters) ok = m->loadDAEVectors(sol.data(), f.data(), q.data(), b.data(), 0, 0, 0) && ok;
+    return ok;
+  }
+  bool loadMatricesAll() {
+    bool ok = true;
+    for (auto *m : masters) ok = m->loadDAEMatrices(dFdx, dQdx) && ok;
+    return ok;
+  }
+  std::vector<double> staDeriv;
   std::vector<InstRec> insts;
   int nExt = 0, n = 0, nSta = 0, nSto = 0;
   CsrMatrix dFdx, dQdx;
@@ -143,35 +177,45 @@ void *xref_new() {
 
 int xref_set_num_external_nodes(void *h, int n) { ((Ctx *)h)->nExt = n; return 0; }
 
-// type: "nmos" / "pmos"; level 54 BSIM4.
-int xref_b4_add_model(void *h, const char *name, const char *type, int np, const char **keys, const double *vals) {
+// devtype: "b4" BSIM4 (level 54), "m1" MOSFET level 1, "d" diode, "q" Gummel-Poon BJT.
+// mtype: the .model type string in upper case (NMOS, PMOS, D, NPN, PNP).
+int xref_add_model(void *h, const char *devtype, const char *name, const char *mtype, int level, int np,
+                   const char **keys, const double *vals) {
   Ctx *c = (Ctx *)h;
-  if (!c->cfgB4) {
-    c->cfgB4 = &Config<MOSFET_B4::Traits>::addConfiguration();
-    c->masterB4 = MOSFET_B4::Traits::factory(*c->cfgB4, *c->fb);
-  }
-  ModelBlock mb(name, type, 54);
+  const int d = c->master(devtype);
+  if (d < 0) return 2;
+  ModelBlock mb(name, mtype, level);
   mb.params = make_params(np, keys, vals);
-  DeviceModel *m = c->masterB4->addModel(mb, *c->fb);
-  return m ? 0 : 1;
+  return c->masters[d]->addModel(mb, *c->fb) ? 0 : 1;
 }
 
-int xref_b4_add_instance(void *h, const char *name, const char *model, const int *nodes4, int np,
-                         const char **keys, const double *vals) {
+int xref_add_instance(void *h, const char *devtype, const char *name, const char *model, int nnodes, const int *nodes,
+                      int np, const char **keys, const double *vals) {
   Ctx *c = (Ctx *)h;
+  const int d = c->master(devtype);
+  if (d < 0) return 2;
   InstanceBlock ib{std::string(name)};
   ib.setModelName(ModelName(model));
   ib.params = make_params(np, keys, vals);
-  ib.iNumNodes = 4;
-  ib.numExtVars = 4;
+  ib.iNumNodes = nnodes;
+  ib.numExtVars = nnodes;
   ib.modelFlag = true;
-  DeviceInstance *di = c->masterB4->addInstance(ib, *c->fb);
+  DeviceInstance *di = c->masters[d]->addInstance(ib, *c->fb);
   if (!di) return 1;
   InstRec r;
   r.inst = di;
-  r.ext.assign(nodes4, nodes4 + 4);
+  r.dev = d;
+  r.ext.assign(nodes, nodes + nnodes);
   c->insts.push_back(r);
   return 0;
+}
+
+int xref_b4_add_model(void *h, const char *name, const char *type, int np, const char **keys, const double *vals) {
+  return xref_add_model(h, "b4", name, type, 54, np, keys, vals);
+}
+int xref_b4_add_instance(void *h, const char *name, const char *model, const int *nodes4, int np,
+                         const char **keys, const double *vals) {
+  return xref_add_instance(h, "b4", name, model, 4, nodes4, np, keys, vals);
 }
 
 // Assign LIDs, build the CSR pattern from every instance's jacobianStamp(), register
@@ -236,7 +280,7 @@ int xref_finalize(void *h) {
   c->nSta = sta; c->nSto = sto;
   c->f.assign(c->n + 1, 0); c->q = c->b = c->fl = c->ql = c->f;
   c->sol.assign(c->n + 1, 0);
-  c->nextSta.assign(sta + 1, 0); c->currSta = c->nextSta;
+  c->nextSta.assign(sta + 1, 0); c->currSta = c->nextSta; c->staDeriv = c->nextSta;
   c->nextSto.assign(sto + 1, 0); c->currSto = c->nextSto;
   ExternData &e = c->extData;
   e.dFdxMatrixPtr = &c->dFdx; e.dQdxMatrixPtr = &c->dQdx;
@@ -244,6 +288,7 @@ int xref_finalize(void *h) {
   e.dFdxdVpVectorRawPtr = c->fl.data(); e.dQdxdVpVectorRawPtr = c->ql.data();
   e.nextSolVectorRawPtr = e.currSolVectorRawPtr = e.lastSolVectorRawPtr = c->sol.data();
   e.nextStaVectorRawPtr = c->nextSta.data(); e.currStaVectorRawPtr = e.lastStaVectorRawPtr = c->currSta.data();
+  e.nextStaDerivVectorRawPtr = c->staDeriv.data();
   e.nextStoVectorRawPtr = c->nextSto.data(); e.currStoVectorRawPtr = e.lastStoVectorRawPtr = c->currSto.data();
   for (auto &r : c->insts) r.inst->setupPointers();
   c->finalized = true;
@@ -288,11 +333,13 @@ void xref_get_state(void *h, double *currSto, double *nextSto, double *currSta, 
 // carried limiter threshold `von` of every BSIM4 instance
 void xref_b4_set_von(void *h, const double *von) {
   Ctx *c = (Ctx *)h;
-  for (size_t i = 0; i < c->insts.size(); ++i) static_cast<MOSFET_B4::Instance *>(c->insts[i].inst)->von = von[i];
+  for (size_t i = 0; i < c->insts.size(); ++i)
+    if (c->masterType[c->insts[i].dev] == "b4") static_cast<MOSFET_B4::Instance *>(c->insts[i].inst)->von = von[i];
 }
 void xref_b4_get_von(void *h, double *von) {
   Ctx *c = (Ctx *)h;
-  for (size_t i = 0; i < c->insts.size(); ++i) von[i] = static_cast<MOSFET_B4::Instance *>(c->insts[i].inst)->von;
+  for (size_t i = 0; i < c->insts.size(); ++i)
+    von[i] = (c->masterType[c->insts[i].dev] == "b4") ? static_cast<MOSFET_B4::Instance *>(c->insts[i].inst)->von : 0.0;
 }
 
 // One updateState + loadDAEVectors + loadDAEMatrices pass at solution x[0..n).
@@ -303,9 +350,9 @@ int xref_load(void *h, const double *x, double *f, double *q, double *fl, double
   c->sol[c->n] = 0.0;
   for (auto *v : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(v->begin(), v->end(), 0.0);
   c->dFdx.put(0.0); c->dQdx.put(0.0);
-  bool ok = c->masterB4->updateState(c->sol.data(), c->nextSta.data(), c->nextSto.data());
-  ok = c->masterB4->loadDAEVectors(c->sol.data(), c->f.data(), c->q.data(), c->b.data(), 0, 0, 0) && ok;
-  ok = c->masterB4->loadDAEMatrices(c->dFdx, c->dQdx) && ok;
+  bool ok = c->updateAll();
+  ok = c->loadVectorsAll() && ok;
+  ok = c->loadMatricesAll() && ok;
   if (f) std::copy(c->f.begin(), c->f.begin() + c->n, f);
   if (q) std::copy(c->q.begin(), c->q.begin() + c->n, q);
   if (fl) std::copy(c->fl.begin(), c->fl.begin() + c->n, fl);
@@ -321,9 +368,9 @@ int xref_load_repeat(void *h, int reps) {
   for (int r = 0; r < reps; ++r) {
     for (auto *v : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(v->begin(), v->end(), 0.0);
     c->dFdx.put(0.0); c->dQdx.put(0.0);
-    c->masterB4->updateState(c->sol.data(), c->nextSta.data(), c->nextSto.data());
-    c->masterB4->loadDAEVectors(c->sol.data(), c->f.data(), c->q.data(), c->b.data(), 0, 0, 0);
-    c->masterB4->loadDAEMatrices(c->dFdx, c->dQdx);
+    c->updateAll();
+    c->loadVectorsAll();
+    c->loadMatricesAll();
   }
   return 0;
 }
@@ -389,6 +436,35 @@ void xref_b4_export(void *h, int idx, double *model_d, int *model_i, double *siz
   *sta0 = c->insts[idx].sta0;
   *sto0 = c->insts[idx].sto0;
 }
+// generic: LIDs of all variables (external then internal, -1 = ground), first state / store LID
+int xref_inst_info(void *h, int idx, int *lids, int max_lids, int *sta0, int *sto0, int *nsta, int *nsto) {
+  Ctx *c = (Ctx *)h;
+  const InstRec &r = c->insts[idx];
+  const int k = (int)r.lids.size();
+  for (int i = 0; i < k && i < max_lids; ++i) lids[i] = r.lids[i];
+  *sta0 = r.sta0; *sto0 = r.sto0; *nsta = r.inst->getNumStateVars(); *nsto = r.inst->getNumStoreVars();
+  return k;
+}
+
+// Diode record in the order of xyce_b200/csrc/diode_eval.h (XB_DIODE_D) + flag word
+#include "../xyce_b200/csrc/simple_fields.def"
+int xref_diode_export(void *h, int idx, double *rec, int *flags, int *lids3) {
+  Ctx *c = (Ctx *)h;
+  Diode::Instance &in = *static_cast<Diode::Instance *>(c->insts[idx].inst);
+  Diode::Model &mo = in.model_;
+  int k = 0;
+#define MOD(n) rec[k++] = mo.n;
+#define INS(n) rec[k++] = in.n;
+  XB_DIODE_FIELDS(MOD, INS)
+#undef MOD
+#undef INS
+  *flags = (mo.BVGiven ? 1 : 0) | (mo.JSWGiven ? 2 : 0) | (mo.NSGiven ? 4 : 0) | (in.InitCondGiven ? 8 : 0) | (in.off ? 16 : 0);
+  const int g = c->n;
+  const int l[3] = {in.li_Pos, in.li_Neg, in.li_Pri};
+  for (int i = 0; i < 3; ++i) lids3[i] = (l[i] == g) ? -1 : l[i];
+  return k;
+}
+
 void xref_b4_mid(void *h, int idx, double *mid_d, int *mid_i) {
   Ctx *c = (Ctx *)h;
   MOSFET_B4::Instance &in = *static_cast<MOSFET_B4::Instance *>(c->insts[idx].inst);
@@ -454,8 +530,8 @@ struct RefBackend {
     std::copy(v[xb::sim::vNextSol].begin(), v[xb::sim::vNextSol].end(), c->sol.begin());
     c->sol[c->n] = 0.0;
     for (auto *q : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(q->begin(), q->end(), 0.0);
-    bool ok = c->masterB4->updateState(c->sol.data(), c->nextSta.data(), c->nextSto.data());
-    ok = c->masterB4->loadDAEVectors(c->sol.data(), c->f.data(), c->q.data(), c->b.data(), 0, 0, 0) && ok;
+    bool ok = c->updateAll();
+    ok = c->loadVectorsAll() && ok;
     for (size_t k = 0; k < G.r.size(); ++k) c->f[G.r[k]] += G.v[k] * c->sol[G.c[k]];
     for (size_t k = 0; k < C.r.size(); ++k) c->q[C.r[k]] += C.v[k] * c->sol[C.c[k]];
     for (const Src &q : sources) c->b[q.row] += q.scale * (q.type == 1 ? xb::sim::pulse_value(q.p, time) : q.p[0]);
@@ -468,7 +544,7 @@ struct RefBackend {
   }
   void load_jacobian(double qs, double fs) {
     c->dFdx.put(0.0); c->dQdx.put(0.0);
-    c->masterB4->loadDAEMatrices(c->dFdx, c->dQdx);
+    c->loadMatricesAll();
     for (size_t k = 0; k < G.r.size(); ++k) c->dFdx.vals[Gpos[k]] += G.v[k];
     for (size_t k = 0; k < C.r.size(); ++k) c->dQdx.vals[Cpos[k]] += C.v[k];
     for (size_t k = 0; k < J.size(); ++k) J[k] = qs * c->dQdx.vals[k] + fs * c->dFdx.vals[k];

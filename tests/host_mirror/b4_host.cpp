@@ -8,6 +8,7 @@
 #define XB_REAL xb::CountReal
 #endif
 #include "../../xyce_b200/csrc/bsim4_instance.h"
+#include "../../xyce_b200/csrc/diode_eval.h"
 
 using namespace xb;
 using namespace xb::b4;
@@ -98,6 +99,37 @@ void xbh_op_counts(unsigned long long *out) {
 #else
   for (int i = 0; i < 7; ++i) out[i] = 0;
 #endif
+}
+
+static void fill_flags(SolverFlags &S, const int *fl, const double *fd) {
+  std::memset(&S, 0, sizeof(S));
+  S.dcopFlag = fl[0]; S.tranopFlag = fl[1]; S.acopFlag = fl[2]; S.transientFlag = fl[3]; S.dcsweepFlag = fl[4];
+  S.initJctFlag = fl[5]; S.initFixFlag = fl[6]; S.initTranFlag = fl[7]; S.newtonIter = fl[8];
+  S.locaEnabledFlag = fl[9]; S.artParameterFlag = fl[10]; S.voltageLimiterFlag = fl[11];
+  S.gmin = fd[0]; S.gainScale = fd[1]; S.nltermScale = fd[2]; S.vgstConst = 4.5; S.vdsScaleMin = 0.3;
+}
+
+// diode: out = F[3] Q[3] FL[3] QL[3] JF[7] JQ[7] store[3] origFlag  (30 doubles)
+int xbh_diode_eval(const double *rec, int flags, const int *fl, const double *fd, const double *V3, double vd_curr,
+                   double vd_next, double *out) {
+  SolverFlags S; fill_flags(S, fl, fd);
+  xb::diode::Rec D;
+  int k = 0;
+#define GET(n) D.n = rec[k++];
+  XB_DIODE_FIELDS(GET, GET)
+#undef GET
+  real V[3] = {V3[0], V3[1], V3[2]};
+  xb::diode::Out o;
+  xb::diode::evaluate(S, D, flags, V, real(vd_curr), real(vd_next), o);
+  k = 0;
+  for (int i = 0; i < 3; ++i) out[k++] = to_double(o.F[i]);
+  for (int i = 0; i < 3; ++i) out[k++] = to_double(o.Q[i]);
+  for (int i = 0; i < 3; ++i) out[k++] = to_double(o.FL[i]);
+  for (int i = 0; i < 3; ++i) out[k++] = to_double(o.QL[i]);
+  for (int i = 0; i < 7; ++i) out[k++] = to_double(o.JF[i]);
+  for (int i = 0; i < 7; ++i) out[k++] = to_double(o.JQ[i]);
+  out[k++] = to_double(o.Vd); out[k++] = to_double(o.Qd); out[k++] = to_double(o.Cd); out[k++] = o.origFlag;
+  return k;
 }
 
 void xbh_b4_slot_tables(int *row, int *col) {

@@ -62,6 +62,32 @@ class RefCircuit:
         assert rc == 0
         self.n_inst += 1
 
+    def add_dev_model(self, devtype, name, mtype, level, params):
+        n, ks, vs = _keys(params)
+        rc = self.lib.xref_add_model(self.h, devtype.encode(), name.encode(), mtype.encode(), int(level), n, ks, dptr(vs))
+        assert rc == 0
+
+    def add_dev_instance(self, devtype, name, model, nodes, params):
+        n, ks, vs = _keys(params)
+        nd = np.array(nodes, dtype=np.int32)
+        rc = self.lib.xref_add_instance(self.h, devtype.encode(), name.encode(), model.encode(), len(nd), iptr(nd), n, ks, dptr(vs))
+        assert rc == 0
+        self.n_inst += 1
+
+    def inst_info(self, idx):
+        lids = np.zeros(16, dtype=np.int32)
+        v = [C.c_int() for _ in range(4)]
+        k = self.lib.xref_inst_info(self.h, idx, iptr(lids), 16, *[C.byref(x) for x in v])
+        return dict(lids=lids[:k].copy(), sta0=v[0].value, sto0=v[1].value, nsta=v[2].value, nsto=v[3].value)
+
+    def diode_export(self, idx):
+        rec = np.zeros(64)
+        flags = C.c_int()
+        lids = np.zeros(3, dtype=np.int32)
+        k = self.lib.xref_diode_export(self.h, idx, dptr(rec), C.byref(flags), iptr(lids))
+        info = self.inst_info(idx)
+        return dict(rec=rec[:k].copy(), flags=flags.value, lids=lids, sto0=info["sto0"], sta0=info["sta0"])
+
     def finalize(self):
         self.n = self.lib.xref_finalize(self.h)
         self.nnz = self.lib.xref_nnz(self.h)

@@ -1,0 +1,47 @@
+"""GPU parity of the small compact models through the C ABI against the reference's own device objects
+(oracle/_ref): assembled F, Q, limiter vectors, dFdx, dQdx and store vector at 1e-12."""
+import numpy as np
+import pytest
+
+import oracle_ref
+import xyce_b200
+from b4_common import rel_err, solver_state
+from dev_common import DIODE_CARDS, diode_circuit
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"tran1": dict(transient=1, newtonIter=1), "tran0": dict(transient=1, newtonIter=0),
+         "dcop_init": dict(dcop=1, tranop=1, initJct=1, newtonIter=0), "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0)}
+
+
+def check(ref, eng, flags, x, nsto, csto):
+    ref.set_flags(**flags)
+    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=np.zeros(ref.n_sta))
+    eng.set_state(0, nsto); eng.set_state(1, csto)
+    want = ref.load(x)
+    got = eng.load_host(x, solver_state(**flags))
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, k
+    st = ref.get_state()
+    assert rel_err(eng.get_state(0), st["next_sto"], 1e-30) < 1e-12
+    if ref.n_sta:
+        assert rel_err(eng.get_state(2), st["next_sta"], 1e-30) < 1e-12
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("card", sorted(DIODE_CARDS))
+def test_diode(card, case):
+    ref = diode_circuit(oracle_ref.RefCircuit, card, n_dev=40, seed=5)
+    ex = [ref.diode_export(i) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(1, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1)
+    eng.finalize()
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-9.0, 1.2, ref.n)
+    x[1::2] = rng.uniform(-0.3, 0.3, len(x[1::2]))
+    check(ref, eng, CASES[case], x, rng.normal(0.3, 0.4, ref.n_sto), rng.normal(0.3, 0.4, ref.n_sto))
+    eng.close()

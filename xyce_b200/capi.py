@@ -150,6 +150,16 @@ class Engine:
             raise RuntimeError("xgpu_b4_group_add failed (%d): %s" % (gid, self.lib.xgpu_last_error(self.h).decode()))
         return gid
 
+    def add_simple_group(self, dev_type, rec, flags, lids, sto_lid0, sto_stride=1, sta_lid0=None, sta_stride=1):
+        """dev_type: 1 diode, 2 MOSFET level 1, 3 BJT, 4 ADMS-shaped RLC; rec: [n, nfields] records."""
+        rec, flags, lids, sto_lid0 = _f64(rec), _i32(flags), _i32(lids), _i32(sto_lid0)
+        sta = _i32(sta_lid0) if sta_lid0 is not None else None
+        gid = self.lib.xgpu_simple_group_add(self.h, int(dev_type), rec.shape[0], _dp(rec), _ip(flags), _ip(lids),
+                                             _ip(sto_lid0), int(sto_stride), _ip(sta), int(sta_stride))
+        if gid < 0:
+            raise RuntimeError("xgpu_simple_group_add failed (%d): %s" % (gid, self.lib.xgpu_last_error(self.h).decode()))
+        return gid
+
     def finalize(self):
         self._chk(self.lib.xgpu_finalize(self.h))
 

@@ -55,6 +55,32 @@ cudaError_t upload_map(const GatherMapHost &h, GatherMapDev &d) {
   return cudaMalloc((void **)&d.partials, std::max<size_t>(4 * cb.size(), 1) * sizeof(double));
 }
 
+// uniform view of one device group for pattern / map construction
+struct GroupView {
+  int n, R, S;
+  const int32_t *lids;            // node-major [nodes][n]
+  std::vector<int> srow, scol;    // node index of each slot's row / column
+  int64_t *vec_base, *mat_base;
+};
+std::vector<GroupView> group_views(xgpu_ctx *ctx) {
+  std::vector<GroupView> v;
+  for (auto &g : ctx->groups) {
+    GroupView w;
+    w.n = g.n; w.R = g.general ? kRowsGeneral : kRowsDefault; w.S = g.general ? kSlotsGeneral : kSlotsDefault;
+    w.lids = g.lids.data();
+    for (int s = 0; s < w.S; ++s) { w.srow.push_back(g.general ? kSlotRow[s] : s / 4); w.scol.push_back(g.general ? kSlotCol[s] : s % 4); }
+    w.vec_base = (int64_t *)&g.dev.vec_base; w.mat_base = (int64_t *)&g.dev.mat_base;
+    v.push_back(w);
+  }
+  for (auto &g : ctx->sgroups) {
+    GroupView w;
+    w.n = g.n; w.R = g.nodes; w.S = g.slots; w.lids = g.lids.data(); w.srow = g.slot_row; w.scol = g.slot_col;
+    w.vec_base = (int64_t *)&g.dev.vec_base; w.mat_base = (int64_t *)&g.dev.mat_base;
+    v.push_back(w);
+  }
+  return v;
+}
+
 void finish_map(GatherMapHost &m, const std::vector<int64_t> &count) {
   const size_t nd = count.size();
   m.ptr.assign(nd + 1, 0);
@@ -102,6 +128,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
     cudaFree(g.d_inst_d); cudaFree(g.d_von); cudaFree(g.d_topo); cudaFree(g.d_model_idx);
     cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig);
   }
+  for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
   for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); }
   cudaFree(ctx->d_conv);
@@ -153,13 +180,11 @@ int xgpu_pattern_build(xgpu_ctx *ctx, int n) {
   if (ctx->finalized) return fail(ctx, 5, "pattern_build after finalize");
   // (row, col) pairs of every stamp entry; sort + unique = generateRowColData
   std::vector<uint64_t> pairs;
-  for (auto &g : ctx->groups) {
+  for (auto &g : group_views(ctx)) {
     const int gn = g.n;
-    const int S = g.general ? kSlotsGeneral : kSlotsDefault;
-    pairs.reserve(pairs.size() + (size_t)S * gn);
-    for (int s = 0; s < S; ++s) {
-      const int rn = g.general ? kSlotRow[s] : s / 4, cn = g.general ? kSlotCol[s] : s % 4;
-      const int32_t *lr = &g.lids[(size_t)rn * gn], *lc = &g.lids[(size_t)cn * gn];
+    pairs.reserve(pairs.size() + (size_t)g.S * gn);
+    for (int s = 0; s < g.S; ++s) {
+      const int32_t *lr = g.lids + (size_t)g.srow[s] * gn, *lc = g.lids + (size_t)g.scol[s] * gn;
       for (int i = 0; i < gn; ++i) {
         if (lr[i] < 0 || lc[i] < 0) continue;
         if (lr[i] >= n || lc[i] >= n) return fail(ctx, 10, "node LID outside the pattern");
@@ -248,6 +273,7 @@ int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const
     XB_B4_SIZE_D(GET)
 #undef GET
   }
+  for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes);
   ctx->d_models = nullptr; ctx->d_sizes = nullptr;
   XG_CUDA(upload(&ctx->d_models, M.data(), M.size()));
@@ -316,6 +342,41 @@ int xgpu_b4_group_add(xgpu_ctx *ctx, int n, const double *inst_d, const int32_t 
   return (int)ctx->groups.size() - 1;
 }
 
+int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n, const double *rec, const int32_t *flags, const int32_t *lids,
+                          const int32_t *sto_lid0, int sto_stride, const int32_t *sta_lid0, int sta_stride) {
+  if (!ctx || n <= 0 || !rec || !lids) return -1;
+  if (ctx->finalized) { fail(ctx, 5, "group_add after finalize"); return -5; }
+  const xb::simple::TypeInfo *ti = xb::simple::type_info(type);
+  if (!ti) { fail(ctx, 17, "unknown device type"); return -17; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -4;
+  XgSimpleGroup g;
+  g.type = type; g.n = n; g.nodes = ti->nodes; g.slots = ti->slots; g.nfields = ti->nfields; g.nstore = ti->nstore; g.nstate = ti->nstate;
+  g.slot_row.assign(ti->slot_row, ti->slot_row + ti->slots);
+  g.slot_col.assign(ti->slot_col, ti->slot_col + ti->slots);
+  std::vector<double> soa((size_t)g.nfields * n);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < g.nfields; ++k) soa[(size_t)k * n + i] = rec[(size_t)i * g.nfields + k];
+  g.lids.assign((size_t)g.nodes * n, -1);
+  for (int i = 0; i < n; ++i) for (int t = 0; t < g.nodes; ++t) g.lids[(size_t)t * n + i] = lids[(size_t)i * g.nodes + t];
+  std::vector<int> fl(n, 0), zero(n, 0), one(n, 1);
+  if (flags) fl.assign(flags, flags + n);
+  bool ok = upload(&g.d_rec, soa.data(), soa.size()) == cudaSuccess && upload(&g.d_flags, fl.data(), fl.size()) == cudaSuccess &&
+            upload(&g.d_lids, g.lids.data(), g.lids.size()) == cudaSuccess &&
+            upload(&g.d_sto0, sto_lid0 ? sto_lid0 : zero.data(), (size_t)n) == cudaSuccess &&
+            upload(&g.d_sta0, sta_lid0 ? sta_lid0 : zero.data(), (size_t)n) == cudaSuccess &&
+            upload(&g.d_orig, one.data(), (size_t)n) == cudaSuccess;
+  if (!ok) { fail(ctx, 11, "device allocation failed in simple_group_add"); return -11; }
+  xb::simple::GroupDev &d = g.dev;
+  d.type = type; d.n = n; d.rec = g.d_rec; d.flags = g.d_flags; d.lids = g.d_lids; d.sto_lid0 = g.d_sto0; d.sta_lid0 = g.d_sta0;
+  d.sto_stride = sto_stride; d.sta_stride = sta_stride; d.orig_flag = g.d_orig;
+  ctx->sgroups.push_back(std::move(g));
+  return (int)ctx->sgroups.size() - 1;
+}
+
+int xgpu_simple_field_count(int type) {
+  const xb::simple::TypeInfo *ti = xb::simple::type_info(type);
+  return ti ? ti->nfields : -1;
+}
+
 int xgpu_finalize(xgpu_ctx *ctx) {
   if (!ctx) return 1;
   if (ctx->finalized) return 0;
@@ -323,10 +384,10 @@ int xgpu_finalize(xgpu_ctx *ctx) {
   XG_CUDA(cudaSetDevice(ctx->device));
   // plane layout
   int64_t vb = 0, mb = 0;
-  for (auto &g : ctx->groups) {
-    const int R = g.general ? kRowsGeneral : kRowsDefault, S = g.general ? kSlotsGeneral : kSlotsDefault;
-    g.dev.vec_base = vb; g.dev.mat_base = mb;
-    vb += (int64_t)R * g.n; mb += (int64_t)S * g.n;
+  std::vector<GroupView> views = group_views(ctx);
+  for (auto &g : views) {
+    *g.vec_base = vb; *g.mat_base = mb;
+    vb += (int64_t)g.R * g.n; mb += (int64_t)g.S * g.n;
   }
   if (vb >= (1LL << 31) || mb >= (1LL << 31)) return fail(ctx, 13, "contribution plane exceeds 2^31 elements");
   ctx->vec_plane = vb; ctx->mat_plane = mb;
@@ -346,24 +407,23 @@ int xgpu_finalize(xgpu_ctx *ctx) {
       vfill.assign(vm.ptr.begin(), vm.ptr.end() - 1);
       mfill.assign(mm.ptr.begin(), mm.ptr.end() - 1);
     }
-    for (auto &g : ctx->groups) {
+    for (auto &g : views) {
       const int gn = g.n;
-      const int R = g.general ? kRowsGeneral : kRowsDefault, S = g.general ? kSlotsGeneral : kSlotsDefault;
       for (int i = 0; i < gn; ++i) {
-        for (int r = 0; r < R; ++r) {
-          const int l = g.lids[(size_t)r * gn + i];   // default: rows 0..3 are D,G,S,B = nodes 0..3
+        for (int r = 0; r < g.R; ++r) {
+          const int l = g.lids[(size_t)r * gn + i];
           if (l < 0) continue;
+          if (l >= n) return fail(ctx, 10, "node LID outside the pattern");
           if (pass == 0) ++vcount[l];
-          else vm.src[(size_t)vfill[l]++] = (int32_t)(g.dev.vec_base + (int64_t)r * gn + i);
+          else vm.src[(size_t)vfill[l]++] = (int32_t)(*g.vec_base + (int64_t)r * gn + i);
         }
-        for (int s = 0; s < S; ++s) {
-          const int rn = g.general ? kSlotRow[s] : s / 4, cn = g.general ? kSlotCol[s] : s % 4;
-          const int lr = g.lids[(size_t)rn * gn + i], lc = g.lids[(size_t)cn * gn + i];
+        for (int s = 0; s < g.S; ++s) {
+          const int lr = g.lids[(size_t)g.srow[s] * gn + i], lc = g.lids[(size_t)g.scol[s] * gn + i];
           if (lr < 0 || lc < 0) continue;
           const int64_t k = csr_find(lr, lc);
           if (k < 0) return fail(ctx, 14, "a device stamp entry is missing from the CSR pattern");
           if (pass == 0) ++mcount[(size_t)k];
-          else mm.src[(size_t)mfill[(size_t)k]++] = (int32_t)(g.dev.mat_base + (int64_t)s * gn + i);
+          else mm.src[(size_t)mfill[(size_t)k]++] = (int32_t)(*g.mat_base + (int64_t)s * gn + i);
         }
       }
     }
@@ -417,6 +477,7 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
   for (int p = 0; p < 4; ++p) a.vec_planes[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
   for (int p = 0; p < 2; ++p) a.mat_planes[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
   for (auto &g : ctx->groups) { launch_b4_group(g.dev, a, ctx->b4_arith, ctx->b4_minblocks, ctx->stream); ++ctx->launches; }
+  for (auto &g : ctx->sgroups) { xb::simple::launch_group(g.dev, a, ctx->stream); ++ctx->launches; }
   XG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -456,6 +517,12 @@ int xgpu_all_converged(xgpu_ctx *ctx, int *converged) {
   // small: copy the flags back and AND them on the host (a fused reduction follows with the norms)
   int all = 1;
   for (auto &g : ctx->groups) {
+    std::vector<int> h(g.n);
+    XG_CUDA(cudaMemcpyAsync(h.data(), g.d_orig, g.n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int v : h) all &= (v != 0);
+  }
+  for (auto &g : ctx->sgroups) {
     std::vector<int> h(g.n);
     XG_CUDA(cudaMemcpyAsync(h.data(), g.d_orig, g.n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     XG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -8,6 +8,7 @@
 #include "assembly.cuh"
 #include "b4_kernels.cuh"
 #include "lu.h"
+#include "simple_kernels.cuh"
 
 struct XgHostGroup {
   int n = 0;
@@ -18,6 +19,17 @@ struct XgHostGroup {
   double *d_inst_d = nullptr, *d_von = nullptr;
   int *d_topo = nullptr, *d_model_idx = nullptr, *d_size_idx = nullptr, *d_lids = nullptr;
   int *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
+};
+
+// groups of the small compact models (diode, MOSFET level 1, BJT, ADMS-shaped rlc): flat per-instance records
+struct XgSimpleGroup {
+  int type = 0;                    // xb::simple::Type
+  int n = 0, nodes = 0, slots = 0, nfields = 0, nstore = 0, nstate = 0;
+  std::vector<int32_t> lids;       // [nodes][n]
+  std::vector<int> slot_row, slot_col;
+  xb::simple::GroupDev dev{};
+  double *d_rec = nullptr;
+  int *d_flags = nullptr, *d_lids = nullptr, *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
 };
 
 // linear-device part (R, C, V, I): constant stamps replayed every load, like the reference's
@@ -49,6 +61,7 @@ struct xgpu_ctx {
   xb::b4::B4Size *d_sizes = nullptr;
   int n_models = 0, n_sizes = 0;
   std::vector<XgHostGroup> groups;
+  std::vector<XgSimpleGroup> sgroups;       // evaluated after the BSIM4 groups, in insertion order
   bool finalized = false;
 
   // contribution planes

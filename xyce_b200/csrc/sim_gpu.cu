@@ -127,6 +127,7 @@ struct GpuBackend {
     int one = 1;
     cudaMemcpyAsync(ctx->d_conv, &one, sizeof(int), cudaMemcpyHostToDevice, s);
     for (auto &g : ctx->groups) { and_flags_kernel<<<(g.n + 255) / 256, 256, 0, s>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
+    for (auto &g : ctx->sgroups) { and_flags_kernel<<<(g.n + 255) / 256, 256, 0, s>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
     int r = 1;
     cudaMemcpyAsync(&r, ctx->d_conv, sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);

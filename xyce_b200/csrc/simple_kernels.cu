@@ -1,0 +1,71 @@
+// xyce_b200 -- kernels of the small compact models (sm_100a).  Memory-bound-ish (few hundred flops per
+// instance): records are read once, coalesced; planes written coalesced.
+#include "simple_kernels.cuh"
+#include "diode_eval.h"
+
+namespace xb {
+namespace simple {
+
+namespace {
+
+__device__ __forceinline__ double gatherv(const double *__restrict__ x, int lid) { return lid >= 0 ? __ldg(x + lid) : 0.0; }
+
+__global__ void __launch_bounds__(128) diode_kernel(GroupDev g, b4::LoadArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const int n = g.n;
+  diode::Rec D;
+  {
+    int k = 0;
+#define LD(name) D.name = __ldg(g.rec + (size_t)(k++) * n + i);
+    XB_DIODE_FIELDS(LD, LD)
+#undef LD
+  }
+  real V[diode::kNodes];
+#pragma unroll
+  for (int t = 0; t < diode::kNodes; ++t) V[t] = gatherv(a.sol, __ldg(g.lids + (size_t)t * n + i));
+  const int sto0 = __ldg(g.sto_lid0 + i), ss = g.sto_stride;
+  diode::Out o;
+  diode::evaluate(a.S, D, __ldg(g.flags + i), V, a.curr_sto[sto0], a.next_sto[sto0], o);
+  a.next_sto[sto0] = to_double(o.Vd);
+  a.next_sto[sto0 + (size_t)ss] = to_double(o.Qd);
+  a.next_sto[sto0 + 2 * (size_t)ss] = to_double(o.Cd);
+  g.orig_flag[i] = o.origFlag;
+#pragma unroll
+  for (int r = 0; r < diode::kNodes; ++r) {
+    a.vec_planes[0][g.vec_base + (size_t)r * n + i] = to_double(o.F[r]);
+    a.vec_planes[1][g.vec_base + (size_t)r * n + i] = to_double(o.Q[r]);
+    a.vec_planes[2][g.vec_base + (size_t)r * n + i] = to_double(o.FL[r]);
+    a.vec_planes[3][g.vec_base + (size_t)r * n + i] = to_double(o.QL[r]);
+  }
+#pragma unroll
+  for (int s = 0; s < diode::kSlots; ++s) {
+    a.mat_planes[0][g.mat_base + (size_t)s * n + i] = to_double(o.JF[s]);
+    a.mat_planes[1][g.mat_base + (size_t)s * n + i] = to_double(o.JQ[s]);
+  }
+}
+
+const int kDiodeRow[diode::kSlots] = {0, 0, 1, 1, 2, 2, 2};
+const int kDiodeCol[diode::kSlots] = {0, 2, 1, 2, 0, 1, 2};
+const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3, 0, kDiodeRow, kDiodeCol};
+
+}  // namespace
+
+const TypeInfo *type_info(int type) {
+  switch (type) {
+    case kDiode: return &kDiodeInfo;
+    default: return nullptr;
+  }
+}
+
+void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
+  if (g.n <= 0) return;
+  const int blocks = (g.n + 127) / 128;
+  switch (g.type) {
+    case kDiode: diode_kernel<<<blocks, 128, 0, s>>>(g, a); break;
+    default: break;
+  }
+}
+
+}  // namespace simple
+}  // namespace xb

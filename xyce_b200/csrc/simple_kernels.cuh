@@ -1,0 +1,30 @@
+// xyce_b200 -- device groups of the small compact models: one thread per instance, flat SoA records,
+// contributions written to the same assembly planes as BSIM4 (assembly.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include "b4_kernels.cuh"   // LoadArgs
+
+namespace xb {
+namespace simple {
+
+enum Type { kDiode = 1, kMos1 = 2, kBjt = 3, kRlc = 4 };
+
+struct GroupDev {
+  int type, n;
+  const double *rec;      // [nfields][n]
+  const int *flags;       // [n]
+  const int *lids;        // [nodes][n], -1 = ground
+  const int *sto_lid0, *sta_lid0;
+  int sto_stride, sta_stride;
+  int *orig_flag;
+  long long vec_base, mat_base;
+};
+
+// static description of a device type (host side)
+struct TypeInfo { int nodes, slots, nfields, nstore, nstate; const int *slot_row, *slot_col; };
+const TypeInfo *type_info(int type);
+
+void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
+
+}  // namespace simple
+}  // namespace xb
