@@ -207,6 +207,8 @@ void XB_CAT(launch_b4_group_a, XB_ARITH)(const GroupDev &g, const LoadArgs &a, i
     switch (minblocks) {
       case 3: b4_eval_kernel<false, 3><<<blocks, threads, 0, stream>>>(g, a); break;
       case 4: b4_eval_kernel<false, 4><<<blocks, threads, 0, stream>>>(g, a); break;
+      case 5: b4_eval_kernel<false, 5><<<blocks, threads, 0, stream>>>(g, a); break;
+      case 6: b4_eval_kernel<false, 6><<<blocks, threads, 0, stream>>>(g, a); break;
       default: b4_eval_kernel<false, 2><<<blocks, threads, 0, stream>>>(g, a); break;
     }
   }

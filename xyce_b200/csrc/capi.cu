@@ -152,7 +152,7 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (!ctx || !name) return 1;
   const std::string n(name);
   if (n == "b4_arith" && value >= 0 && value <= 2) { ctx->b4_arith = value; return 0; }
-  if (n == "b4_minblocks" && value >= 2 && value <= 4) { ctx->b4_minblocks = value; return 0; }
+  if (n == "b4_minblocks" && value >= 2 && value <= 6) { ctx->b4_minblocks = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
 
