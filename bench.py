@@ -26,37 +26,40 @@ sys.path.insert(0, ROOT)
 METRIC = "bsim4_device_load_stamp_evals_per_sec"
 UNIT = "evals/s"
 BYTES_PER_EVAL = 1592.0      # SURVEY.md 8(d) unit U1 (algorithmic bytes per instance evaluation)
-FLOPS_PER_EVAL = 3000.0      # SURVEY.md 8(d) provisional executed flops per evaluation
+FLOPS_PER_EVAL = 1889.0      # executed fp64 operations per evaluation, measured (xyce_b200/data/b4_flop_count.json)
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML every few milliseconds during the timed region
+    (nvidia-smi itself needs ~100 ms per query, longer than one benchmark step)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as exc:   # NVML missing: report, do not invent numbers
+            self.reasons.add("nvml_unavailable: %s" % exc)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def measured_peaks():
@@ -243,7 +246,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 8 * (4 * n + 2 * nnz)},
             "gpu_launches": launches, "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_kind, "kernel": "b4_eval_kernel<false>",
+                         "traffic": None, "peak_source": peak_kind, "kernel": "b4_eval_kernel<default topology, 128 regs, FMA + reciprocal division>",
                          "kernel_ms": 1e3 * eval_s,
                          "fp64": {"achieved_tflops": FLOPS_PER_EVAL * n_inst / eval_s / 1e12,
                                   "measured_peak_tflops": fp64_peak,
