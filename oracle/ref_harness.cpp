@@ -534,7 +534,7 @@ struct RefBackend {
     ok = c->loadVectorsAll() && ok;
     for (size_t k = 0; k < G.r.size(); ++k) c->f[G.r[k]] += G.v[k] * c->sol[G.c[k]];
     for (size_t k = 0; k < C.r.size(); ++k) c->q[C.r[k]] += C.v[k] * c->sol[C.c[k]];
-    for (const Src &q : sources) c->b[q.row] += q.scale * (q.type == 1 ? xb::sim::pulse_value(q.p, time) : q.p[0]);
+    for (const Src &q : sources) c->b[q.row] += q.scale * xb::sim::source_value(q.type, q.p, time);
     std::copy(c->f.begin(), c->f.begin() + n_, v[xb::sim::vF].begin());
     std::copy(c->q.begin(), c->q.begin() + n_, v[xb::sim::vQ].begin());
     std::copy(c->b.begin(), c->b.begin() + n_, v[xb::sim::vB].begin());

@@ -45,3 +45,31 @@ def test_diode(card, case):
     x[1::2] = rng.uniform(-0.3, 0.3, len(x[1::2]))
     check(ref, eng, CASES[case], x, rng.normal(0.3, 0.4, ref.n_sto), rng.normal(0.3, 0.4, ref.n_sto))
     eng.close()
+
+
+# ---- ADMS-shaped plugin device (user_plugin/rlc.va) ----
+def test_rlc_plugin_equals_discrete_and_analytic():
+    """user_plugin/rlc_adms.cir: the ADMS-shaped device must reproduce (a) the same circuit built from
+    discrete R, L, C stamps (reference analogue: utils/ADMS/examples/toys/rlc_series.cir) step for step and
+    (b) the analytic ODE solution within the integrator tolerance."""
+    from scipy.integrate import solve_ivp
+    from xyce_b200 import workloads as wl
+    res = {}
+    for plugin in (True, False):
+        w = wl.rlc_series(3, as_plugin=plugin)
+        eng = wl.build_engine_generic(w)
+        res[plugin] = eng.tran_run(w["x"], 4e-6, 1e-9, w["probes"])
+        assert res[plugin]["rc"] == 0, res[plugin]["error"]
+        eng.close()
+    a, b = res[True], res[False]
+    assert np.array_equal(a["steps"][:, 2], b["steps"][:, 2]) and len(a["t"]) == len(b["t"])
+    assert np.allclose(a["t"], b["t"], rtol=1e-12)
+    assert np.allclose(a["wave"], b["wave"], rtol=1e-9, atol=1e-12)
+    # analytic: L di/dt = v_i2, C d(v_i1 - v_i2)/dt = i, (v1 - v_i1)/R = i  with v1 = 5 + 5 sin(2 pi f t)
+    R, L, C, f = 1e3, 1e-3, 1e-12, 20e6
+    def rhs(t, y):          # y = [i, vc]  (vc = v_i1 - v_i2)
+        v1 = 5 + 5 * np.sin(2 * np.pi * f * t)
+        return [(v1 - R * y[0] - y[1]) / L, y[0] / C]
+    sol = solve_ivp(rhs, [0, 4e-6], [0.0, 5.0], t_eval=a["t"], rtol=1e-10, atol=1e-14, method="LSODA")
+    i_gpu = a["wave"][:, 3]
+    assert np.max(np.abs(i_gpu - sol.y[0])) < 2e-2 * np.max(np.abs(sol.y[0])) + 1e-9

@@ -94,7 +94,7 @@ struct GpuBackend {
       std::vector<double> vals(ns);
       for (int k = 0; k < ns; ++k) {
         const XgSource &q = ctx->sources[k];
-        vals[k] = q.scale * (q.type == 1 ? pulse_value(q.p, time) : q.p[0]);
+        vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time);
       }
       cudaMemcpyAsync(d_src_vals, vals.data(), ns * sizeof(double), cudaMemcpyHostToDevice, s);
       cudaStreamSynchronize(s);     // vals is a stack-lifetime buffer

@@ -2,6 +2,7 @@
 // instance): records are read once, coalesced; planes written coalesced.
 #include "simple_kernels.cuh"
 #include "diode_eval.h"
+#include "adms_rlc_eval.h"
 
 namespace xb {
 namespace simple {
@@ -45,6 +46,36 @@ __global__ void __launch_bounds__(128) diode_kernel(GroupDev g, b4::LoadArgs a) 
   }
 }
 
+__global__ void __launch_bounds__(128) rlc_kernel(GroupDev g, b4::LoadArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const int n = g.n;
+  namespace R = adms::rlc;
+  const double r = __ldg(g.rec + i), l = __ldg(g.rec + (size_t)n + i), c = __ldg(g.rec + 2 * (size_t)n + i);
+  real V[R::kNodes];
+#pragma unroll
+  for (int t = 0; t < R::kNodes; ++t) V[t] = gatherv(a.sol, __ldg(g.lids + (size_t)t * n + i));
+  R::Out o;
+  R::evaluate(r, l, c, V, o);
+  g.orig_flag[i] = 1;
+#pragma unroll
+  for (int t = 0; t < R::kNodes; ++t) {
+    a.vec_planes[0][g.vec_base + (size_t)t * n + i] = to_double(o.F[t]);
+    a.vec_planes[1][g.vec_base + (size_t)t * n + i] = to_double(o.Q[t]);
+    a.vec_planes[2][g.vec_base + (size_t)t * n + i] = 0.0;
+    a.vec_planes[3][g.vec_base + (size_t)t * n + i] = 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < R::kSlots; ++s) {
+    a.mat_planes[0][g.mat_base + (size_t)s * n + i] = to_double(o.JF[s]);
+    a.mat_planes[1][g.mat_base + (size_t)s * n + i] = to_double(o.JQ[s]);
+  }
+}
+
+const int kRlcRow[adms::rlc::kSlots] = {0, 0, 2, 2, 2, 3, 3, 3, 1, 4, 4, 4};
+const int kRlcCol[adms::rlc::kSlots] = {0, 2, 0, 2, 3, 2, 3, 4, 4, 3, 1, 4};
+const TypeInfo kRlcInfo = {adms::rlc::kNodes, adms::rlc::kSlots, adms::rlc::kNumFields, 0, 0, kRlcRow, kRlcCol};
+
 const int kDiodeRow[diode::kSlots] = {0, 0, 1, 1, 2, 2, 2};
 const int kDiodeCol[diode::kSlots] = {0, 2, 1, 2, 0, 1, 2};
 const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3, 0, kDiodeRow, kDiodeCol};
@@ -54,6 +85,7 @@ const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3,
 const TypeInfo *type_info(int type) {
   switch (type) {
     case kDiode: return &kDiodeInfo;
+    case kRlc: return &kRlcInfo;
     default: return nullptr;
   }
 }
@@ -63,6 +95,7 @@ void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
   const int blocks = (g.n + 127) / 128;
   switch (g.type) {
     case kDiode: diode_kernel<<<blocks, 128, 0, s>>>(g, a); break;
+    case kRlc: rlc_kernel<<<blocks, 128, 0, s>>>(g, a); break;
     default: break;
   }
 }

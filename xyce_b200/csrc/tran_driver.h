@@ -40,6 +40,17 @@ inline double pulse_value(const double *p, double t) {
   return v1;
 }
 
+// SPICE SIN(v0 va freq td theta phase_deg) (SinData, N_DEV_SourceData.C)
+inline double sin_value(const double *p, double t) {
+  const double v0 = p[0], va = p[1], f = p[2], td = p[3], theta = p[4], ph = p[5];
+  const double two_pi = 6.283185307179586;
+  if (t < td) return v0 + va * std::sin(two_pi * ph / 360.0);
+  return v0 + va * std::sin(two_pi * (f * (t - td) + ph / 360.0)) * std::exp(-(t - td) * theta);
+}
+inline double source_value(int type, const double *p, double t) {
+  return type == 1 ? pulse_value(p, t) : (type == 2 ? sin_value(p, t) : p[0]);
+}
+
 struct TranParams {
   double tstop = 0, tstep = 0, delmax = 0;
   // Newton (transient mode defaults)
