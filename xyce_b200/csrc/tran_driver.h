@@ -324,11 +324,7 @@ class TransientDriver {
     }
     if (rr >= r_hincr_test) { rr = r_hincr; newTimeStep = rr * currentTimeStep; }
     else if (rr <= 1) { rr = std::max(r_min, std::min(r_max, rr)); newTimeStep = rr * currentTimeStep; }
-    // updateHistory uses the order the step was taken with
-    const int orderNow = currentOrder;
-    currentOrder = usedOrder;
-    update_history();
-    currentOrder = orderNow;
+    update_history();     // with the order selected for the NEXT step, as the reference does (:2228)
     newTimeStep = std::max(newTimeStep, minTimeStep);
     newTimeStep = std::min(newTimeStep, maxTimeStep);
     if ((stopTime - currentTime) >= minTimeStep) {
