@@ -1,0 +1,99 @@
+"""World-size-2 CPU (gloo) test of the multi-GPU decomposition logic in xyce_b200/partition.py: instance
+partition, shared-unknown classification, and the block-distributed (Schur) solve with the shared system
+all-reduced -- against the undistributed solution.  Interior blocks are factored by the library's host LU."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from test_lu_host import host_solve, ring_array_matrix
+from xyce_b200 import partition as pt
+from xyce_b200 import workloads as wl
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_rings, stages, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = sp.csr_matrix(ring_array_matrix(n_rings, stages, seed=3)); A.sort_indices()
+    n = A.shape[0]
+    rng = np.random.default_rng(7)
+    xt = rng.normal(size=n)
+    b = A @ xt
+    # ownership: ring r belongs to rank floor(r / rings_per_rank); vdd and the source branch are shared
+    bnd = pt.split_ranges(n_rings, world)
+    owner = np.full(n, -1)
+    for r in range(world):
+        owner[bnd[r] * stages:bnd[r + 1] * stages] = r
+    glob, loc, ni = pt.local_numbering(owner, rank)
+    # local system = rows/cols of this rank's unknowns; shared x shared entries and shared rhs split between ranks
+    Al = sp.csr_matrix(A[glob][:, glob]); Al.sort_indices()
+    vals = Al.data.copy()
+    rows = np.repeat(np.arange(Al.shape[0]), np.diff(Al.indptr))
+    ss = (rows >= ni) & (Al.indices >= ni)
+    vals[ss] = vals[ss] / world                     # every rank contributes a share of the shared block
+    rhs = b[glob].copy()
+    rhs[ni:] /= world
+    sysm = pt.BlockArrowSystem(Al.indptr, Al.indices, ni)
+    Aii = sp.csr_matrix((vals[sysm.ii_src], sysm.ii_colind, sysm.ii_rowptr), shape=(ni, ni))
+
+    def solve_interior(B):
+        Y = np.zeros_like(B)
+        for k in range(B.shape[1]):
+            rc, x, _ = host_solve(Aii, np.ascontiguousarray(B[:, k]))
+            assert rc == 0
+            Y[:, k] = x
+        return Y
+
+    def allreduce(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    x = pt.schur_solve(np, sysm, vals, rhs, solve_interior, allreduce)
+    err = float(np.max(np.abs(x - xt[glob])) / np.max(np.abs(xt)))
+    out_q.put((rank, err, ni, len(glob) - ni))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rings,stages", [(4, 7), (9, 31)])
+def test_block_distributed_solve_world2(n_rings, stages):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_rings, stages, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, ni, ns in res:
+        assert err < 1e-10, (rank, err)
+        assert ns == 2                                 # supply node + source branch are the shared unknowns
+    assert sum(r[2] for r in res) == n_rings * stages
+
+
+def test_ring_partition_is_consistent():
+    w = wl.ring_oscillator_array(6, 11)
+    parts = [pt.partition_ring_array(w, 3, r) for r in range(3)]
+    assert sum(p["n_inst"] for p in parts) == w["n_inst"]
+    assert sum(p["n_interior"] for p in parts) + parts[0]["n_shared"] == w["n_unknowns"]
+    for p in parts:
+        assert p["n_shared"] == 2 and p["lids"].max() < p["n_unknowns"]
+        # interior unknowns of different ranks are disjoint
+    allint = np.concatenate([p["glob_of_local"][:p["n_interior"]] for p in parts])
+    assert len(np.unique(allint)) == len(allint)
+    # the supply source (linear G stamps on shared unknowns + the source itself) is kept by rank 0 only
+    assert len(parts[0]["sources"]["row"]) == 1 and all(len(p["sources"]["row"]) == 0 for p in parts[1:])
+    assert len(parts[0]["linear"]["g_row"]) == 2 and all(len(p["linear"]["g_row"]) == 0 for p in parts[1:])
