@@ -132,7 +132,10 @@ def main():
         e1.lu_solve(gJ.data_ptr(), grhs.data_ptr(), gdx.data_ptr()); torch.cuda.synchronize()
         want = gdx[torch.tensor(w["glob_of_local"], dtype=torch.long, device=dev)]
         err = float((dx - want).abs().max() / want.abs().max())
+        dxn = float(want.abs().max())
         e1.close()
+    if rank == 0 and a.check:
+        print("debug: max|dx| single-GPU = %.6e, distributed = %.6e, max abs diff = %.3e" % (dxn, float(dx.abs().max()), float((dx - want).abs().max())))
     errs = torch.tensor([err if err is not None else 0.0], **f64)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     if rank == 0:
