@@ -1,0 +1,3 @@
+export XYCE_B200_B4_THREADS=256 XYCE_B200_B4_MINBLOCKS=1 XYCE_B200_B4_UNIFORM=1
+ncu --set full --clock-control none --import-source on -k regex:b4_eval -s 3 -c 1 -o gpurun_out/prof_b4_256x1_1m python scripts/prof_one.py 500000 > gpurun_out/p2.log 2>&1
+tail -3 gpurun_out/p2.log

@@ -77,10 +77,11 @@ __device__ __forceinline__ double gather(const double *__restrict__ x, int lid) 
   return lid >= 0 ? __ldg(x + lid) : 0.0;
 }
 
-template <bool GENERAL, int MINBLOCKS>
-__global__ void __launch_bounds__(128, MINBLOCKS) b4_eval_kernel(GroupDev g, LoadArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
+// One instance, end to end.  `valid` = false marks a padding thread of a lock-step block: it runs the
+// arithmetic on the last instance's data (so every thread reaches the block barriers) and stores nothing.
+template <bool GENERAL>
+__device__ __forceinline__ void eval_instance(const GroupDev &g, const LoadArgs &a, const B4Model &M, const B4Size &P,
+                                              const int i, const bool valid) {
   const int n = g.n;
 
   // ---- parameter records ----
@@ -98,8 +99,6 @@ __global__ void __launch_bounds__(128, MINBLOCKS) b4_eval_kernel(GroupDev g, Loa
     I.drainMOSFET_B4Exists = 0; I.sourceMOSFET_B4Exists = 0;
     I.OFF = (__ldg(g.topo + i) >> 6) & 1;
   }
-  const B4Model &M = g.models[__ldg(g.model_idx + i)];
-  const B4Size &P = g.sizes[__ldg(g.size_idx + i)];
 
   // ---- node voltages through the gather map ----
   real V[kNumNodes];
@@ -138,6 +137,7 @@ __global__ void __launch_bounds__(128, MINBLOCKS) b4_eval_kernel(GroupDev g, Loa
   PlaneEmitter<GENERAL> e;
   evaluate(a.S, M, P, I, V, sto_old, src != kOldNone, g.von[i], W, e);
 
+  if (!valid) return;
   // ---- carried state, store and state vectors ----
   g.von[i] = to_double(W.von);
   g.orig_flag[i] = W.origFlag;
@@ -195,23 +195,82 @@ __global__ void __launch_bounds__(128, MINBLOCKS) b4_eval_kernel(GroupDev g, Loa
   }
 }
 
+
+// Variant A ("per-thread records"): every thread fetches its own model / bin record through the index
+// arrays.  Works for any mix of bins inside a block; the loads broadcast out of L1 when neighbours agree.
+template <bool GENERAL, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) b4_eval_kernel(const __grid_constant__ GroupDev g,
+                                                                     const __grid_constant__ LoadArgs a) {
+  int i = blockIdx.x * THREADS + threadIdx.x;
+#if XB_LOCKSTEP
+  const bool valid = i < g.n;
+  if (!valid) i = g.n - 1;
+#else
+  if (i >= g.n) return;
+  const bool valid = true;
+#endif
+  const B4Model &M = g.models[__ldg(g.model_idx + i)];
+  const B4Size &P = g.sizes[__ldg(g.size_idx + i)];
+  eval_instance<GENERAL>(g, a, M, P, i, valid);
+}
+
+// Variant B ("uniform records"): instances are sorted by (model, bin); blockIdx.y selects one run of equal
+// records whose model card and bin live in the kernel parameter block (constant bank), so every parameter
+// is a uniform operand: no per-thread loads, no vector registers, and the model's mode switches
+// (capMod, mobMod, igcMod, ...) become uniform branches.
+template <bool GENERAL, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS) b4_eval_uniform_kernel(const __grid_constant__ GroupDev g,
+                                                                             const __grid_constant__ LoadArgs a,
+                                                                             const __grid_constant__ BinPack bp) {
+  const BinRun &run = bp.run[blockIdx.y];
+  int k = blockIdx.x * THREADS + threadIdx.x;
+#if XB_LOCKSTEP
+  if (blockIdx.x * THREADS >= run.count) return;       // whole block outside this run
+  const bool valid = k < run.count;
+  if (!valid) k = run.count - 1;
+#else
+  if (k >= run.count) return;
+  const bool valid = true;
+#endif
+  eval_instance<GENERAL>(g, a, run.M, run.P, run.start + k, valid);
+}
+
+template <bool GENERAL, int THREADS, int MINBLOCKS>
+void launch_variant(const GroupDev &g, const LoadArgs &a, const BinPack *packs, int npacks, cudaStream_t stream) {
+  if (packs && npacks > 0) {
+    for (int p = 0; p < npacks; ++p) {
+      int most = 0;
+      for (int r = 0; r < packs[p].nruns; ++r) most = packs[p].run[r].count > most ? packs[p].run[r].count : most;
+      const dim3 grid((most + THREADS - 1) / THREADS, packs[p].nruns);
+      b4_eval_uniform_kernel<GENERAL, THREADS, MINBLOCKS><<<grid, THREADS, 0, stream>>>(g, a, packs[p]);
+    }
+  } else {
+#if !XB_LOCKSTEP
+    b4_eval_kernel<GENERAL, THREADS, MINBLOCKS><<<(g.n + THREADS - 1) / THREADS, THREADS, 0, stream>>>(g, a);
+#endif
+  }
+}
+
 }  // namespace
 
-void XB_CAT(launch_b4_group_a, XB_ARITH)(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream) {
-  if (g.n <= 0) return;
-  const int threads = 128;
-  const int blocks = (g.n + threads - 1) / threads;
+#if XB_LOCKSTEP
+#define XB_LAUNCH_NAME XB_CAT(XB_CAT(launch_b4_group_a, XB_ARITH), s)
+#else
+#define XB_LAUNCH_NAME XB_CAT(launch_b4_group_a, XB_ARITH)
+#endif
+
+int XB_LAUNCH_NAME(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks,
+                   cudaStream_t stream) {
+  if (g.n <= 0) return 0;
+  const int launches = (packs && npacks > 0) ? npacks : 1;
   if (g.general) {
-    b4_eval_kernel<true, 2><<<blocks, threads, 0, stream>>>(g, a);
-  } else {
-    switch (minblocks) {
-      case 3: b4_eval_kernel<false, 3><<<blocks, threads, 0, stream>>>(g, a); break;
-      case 4: b4_eval_kernel<false, 4><<<blocks, threads, 0, stream>>>(g, a); break;
-      case 5: b4_eval_kernel<false, 5><<<blocks, threads, 0, stream>>>(g, a); break;
-      case 6: b4_eval_kernel<false, 6><<<blocks, threads, 0, stream>>>(g, a); break;
-      default: b4_eval_kernel<false, 2><<<blocks, threads, 0, stream>>>(g, a); break;
-    }
+    launch_variant<true, 128, 2>(g, a, packs, npacks, stream);
+    return launches;
   }
+#define XB_CASE(T, B) if (threads == T && minblocks == B) { launch_variant<false, T, B>(g, a, packs, npacks, stream); return launches; }
+  XB_B4_LAUNCH_SHAPES(XB_CASE)
+#undef XB_CASE
+  return -1;   // unsupported (threads, minblocks) pair
 }
 
 }  // namespace b4

@@ -54,15 +54,38 @@ struct LoadArgs {
   double *mat_planes[2];    // dFdx, dQdx contribution planes
 };
 
+// Runs of instances that share one (model card, bin) pair, passed by value in the kernel parameter block.
+struct BinRun {
+  B4Model M;
+  B4Size P;
+  int start, count;         // instance range [start, start + count) inside the group
+};
+constexpr int kRunsPerPack = 8;
+struct BinPack {
+  BinRun run[kRunsPerPack];
+  int nruns;
+};
+constexpr int kMaxUniformRuns = 64;   // groups with more distinct runs use the per-thread-record kernel
+
+// (threads per block, resident blocks per SM) shapes compiled for the default-topology kernel;
+// registers per thread = 65536 / (threads * blocks), capped at 255.
+#define XB_B4_LAUNCH_SHAPES(X) \
+  X(128, 2) X(128, 3) X(128, 4) X(128, 5) X(256, 1) X(256, 2) X(384, 1) X(512, 1)
+
 // arith: 0 exact (no FMA contraction, IEEE division), 1 fma, 2 fast (fma + reciprocal division);
-// minblocks: 2 (255 registers), 3 (168) or 4 (128) resident blocks per SM for the default-topology kernel.
-void launch_b4_group_a0(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream);
-void launch_b4_group_a1(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream);
-void launch_b4_group_a2(const GroupDev &g, const LoadArgs &a, int minblocks, cudaStream_t stream);
-inline void launch_b4_group(const GroupDev &g, const LoadArgs &a, int arith, int minblocks, cudaStream_t stream) {
-  if (arith == 2) launch_b4_group_a2(g, a, minblocks, stream);
-  else if (arith == 1) launch_b4_group_a1(g, a, minblocks, stream);
-  else launch_b4_group_a0(g, a, minblocks, stream);
+// lockstep: block-wide barriers between evaluation sections keep the warps of a block inside the same
+// instruction-cache window (arith 2 only); packs != nullptr selects the uniform-record kernel.
+// Returns the number of kernel launches, -1 for an unsupported shape.
+int launch_b4_group_a0(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+int launch_b4_group_a1(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+int launch_b4_group_a2(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+int launch_b4_group_a2s(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+inline int launch_b4_group(const GroupDev &g, const LoadArgs &a, int arith, int lockstep, int threads, int minblocks,
+                           const BinPack *packs, int npacks, cudaStream_t stream) {
+  if (arith == 2) return lockstep ? launch_b4_group_a2s(g, a, threads, minblocks, packs, npacks, stream)
+                                  : launch_b4_group_a2(g, a, threads, minblocks, packs, npacks, stream);
+  if (arith == 1) return launch_b4_group_a1(g, a, threads, minblocks, packs, npacks, stream);
+  return launch_b4_group_a0(g, a, threads, minblocks, packs, npacks, stream);
 }
 
 }  // namespace b4

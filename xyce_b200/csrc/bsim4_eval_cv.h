@@ -362,6 +362,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
     }
     W.Vgsteff = Vgsteff;
 
+    XB_SYNC_POINT_U(1);
     if (M.capMod == 1) {
       Vfb = I.vfbzb;
       const real V3 = Vfb - Vgs_eff + VbseffCV - kDelta3;
@@ -550,6 +551,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       const real dQsub0_dVd = -T2 * dVgsteff_dVd;
       const real dQsub0_dVb = -T2 * (dVfbeff_dVb + dVbseffCV_dVb + dVgsteff_dVb) + QovCox * dCoxeff_dVb;
 
+      XB_SYNC_POINT_U(2);
       // gate-bias dependent delta Phis (inversion charge centroid)
       real Denomi;
       if (P.k1ox <= 0.0) { Denomi = 0.25 * P.moin * Vtm; T0 = 0.5 * P.sqrtPhi; }
@@ -709,6 +711,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.cbbb = -W.cbgb - W.cbdb - W.cbsb;
   W.csbb = -W.cgbb - W.cdbb - W.cbbb;
 
+  XB_SYNC_POINT(1);
   // NQS: relaxation-time conductance
   if (I.trnqsMod || I.acnqsMod) {
     W.qchqs = W.qcheq = -(qbulk + qgate);
@@ -740,6 +743,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.qbs = W.qbd = W.capbs = W.capbd = 0.0;
   }
 
+  XB_SYNC_POINT(2);
   // ---- gate electrode resistance currents & overlap capacitances -----------------------------------------
   real vgdx, vgsx;
   if (I.rgateMod == 3) { vgdx = W.vgmd; vgsx = W.vgms; }

@@ -107,6 +107,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   real dT10_dVg, dT10_dVd, dT10_dVb;
   const real gmin = S.gmin;
 
+  XB_SYNC_POINT(2);
   // ---- source / drain bulk junction diodes --------------------------------
   {
     JctPar js;
@@ -145,6 +146,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
            + I.DswgTempRevSatCur * (t6 - 1.0);
   }
 
+  XB_SYNC_POINT(2);
   // ---- mode selection -----------------------------------------------------
   real Vds, Vgs, Vbs, Vdb;
   if (W.vds >= 0.0) { W.mode = 1;  Vds = W.vds;  Vgs = W.vgs; Vbs = W.vbs; Vdb = W.vds - W.vbs; }
@@ -160,6 +162,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     Vgs = S.gainScale * Vgs + (1.0 - S.gainScale) * S.vgstConst;
   }
 
+  XB_SYNC_POINT(2);
   // ---- effective body bias ------------------------------------------------
   real Vbseff, dVbseff_dVb;
   T0 = Vbs - I.vbsc - 0.001;
@@ -188,6 +191,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   const real Vtm = M.vtm;
   const real Vtm0 = M.vtm0;
 
+  XB_SYNC_POINT(1);
   // ---- threshold voltage --------------------------------------------------
   T3 = sqrt(Xdep);
   const real V0 = P.vbi - P.phi;
@@ -308,6 +312,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.Vth = Vth;
   W.von = Vth;
 
+  XB_SYNC_POINT(2);
   // ---- poly gate depletion -------------------------------------------------
   T0 = I.vfb + P.phi;
   T1 = (M.mtrlMod == 0) ? kEpsSi : M.epsrgate * kEps0B4;
@@ -318,6 +323,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   else { Vgs_eff = W.vgd_eff; dVgs_eff_dVg = W.dvgd_eff_dvg; }
   const real Vgst = Vgs_eff - Vth;
 
+  XB_SYNC_POINT(2);
   // ---- effective Vgst -------------------------------------------------------
   T0 = n * Vtm;
   T1 = P.mstar * Vgst;
@@ -370,6 +376,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   const real dVgsteff_dVd = (T9 * dT10_dVd - T10 * dT9_dVd) / T11;
   const real dVgsteff_dVb = (T9 * dT10_dVb - T10 * dT9_dVb) / T11;
 
+  XB_SYNC_POINT(2);
   // ---- effective channel width & parasitic Rds ------------------------------
   T9 = sqrtPhis - P.sqrtPhi;
   real Weff = P.weff - 2.0 * (P.dwg * Vgsteff + P.dwb * T9);
@@ -402,6 +409,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.grdsw = (Rds > 0.0) ? 1.0 / Rds * I.nf : 0.0;
   }
 
+  XB_SYNC_POINT(2);
   // ---- bulk charge effect (Abulk) -------------------------------------------
   real Abulk, dAbulk_dVb, dAbulk_dVg, Abulk0, dAbulk0_dVb;
   {
@@ -452,6 +460,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     Abulk0 *= T0;
   }
 
+  XB_SYNC_POINT(1);
   // ---- mobility ---------------------------------------------------------------
   real Denomi, dDenomi_dVg, dDenomi_dVd, dDenomi_dVb;
   if (M.mtrlMod && (M.mtrlCompatMod == 0))
@@ -588,6 +597,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   const real dueff_dVd = T9 * dDenomi_dVd;
   const real dueff_dVb = T9 * dDenomi_dVb;
 
+  XB_SYNC_POINT(1);
   // ---- saturation voltage ------------------------------------------------------
   const real WVCox = Weff * I.vsattemp * M.coxe;
   const real WVCoxRds = WVCox * Rds;
@@ -668,6 +678,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
   W.Vdsat = Vdsat;
 
+  XB_SYNC_POINT(2);
   // ---- effective Vds -------------------------------------------------------------
   real Vdseff, dVdseff_dVg, dVdseff_dVd, dVdseff_dVb;
   T1 = Vdsat - Vds - P.delta;
@@ -704,6 +715,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   const real diffVds = Vds - Vdseff;
   W.Vdseff = Vdseff;
 
+  XB_SYNC_POINT(2);
   // ---- velocity overshoot (lambda) ------------------------------------------------
   if (M.lambdaGiven && (M.lambda > 0.0)) {
     T1 = Leff * ueff;
@@ -740,6 +752,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
   W.EsatL = EsatL;
 
+  XB_SYNC_POINT(2);
   // ---- Vasat -------------------------------------------------------------------
   real Vasat, dVasat_dVg, dVasat_dVb, dVasat_dVd;
   {
@@ -763,6 +776,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVasat_dVd = dT0_dVd / T1;
   }
 
+  XB_SYNC_POINT(2);
   // ---- effective oxide capacitance and channel conductance ---------------------------
   real Idl, dIdl_dVg, dIdl_dVd, dIdl_dVb, dCoxeff_dVg;
   real beta, dbeta_dVg, dbeta_dVd, dbeta_dVb, CoxeffWovL;
@@ -814,6 +828,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dIdl_dVb = T1 * dgche_dVb - T2 * dRds_dVb;
   }
 
+  XB_SYNC_POINT(1);
   // ---- output-resistance components: FP, PvagTerm, VACLM, VADIBL, VADITS, VASCBE ------
   real FP, dFP_dVg;
   if (P.fprout <= 0.0) { FP = 1.0; dFP_dVg = 0.0; }
@@ -940,6 +955,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVASCBE_dVg = dVASCBE_dVd = dVASCBE_dVb = 0.0;
   }
 
+  XB_SYNC_POINT(2);
   // ---- Idsa: DIBL, DITS, CLM ----------------------------------------------------------
   real Idsa, dIdsa_dVg, dIdsa_dVd, dIdsa_dVb;
   T9 = diffVds / VADIBL;
@@ -968,6 +984,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   dIdsa_dVd = dIdsa_dVd * T9 + Idsa * dT9_dVd;
   Idsa *= T9;
 
+  XB_SYNC_POINT(1);
   // ---- substrate current ----------------------------------------------------------------
   real Isub, Gbd, Gbb, Gbg;
   {
@@ -1003,6 +1020,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   }
   W.csub = Isub; W.gbbs = Gbb; W.gbgs = Gbg; W.gbds = Gbd;
 
+  XB_SYNC_POINT(2);
   // ---- drain current with SCBE; chain rule back to terminal voltages ---------------------
   real Ids, Gm, Gds, Gmb;
   T9 = diffVds / VASCBE;
@@ -1056,6 +1074,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.IdovVds = Ids;
   if (W.IdovVds <= M.idovvdsc) W.IdovVds = M.idovvdsc;
 
+  XB_SYNC_POINT(2);
   // ---- bias-dependent intrinsic-input (gate) resistance ---------------------------------------
   if ((I.rgateMod > 1) || (I.trnqsMod != 0) || (I.acnqsMod != 0)) {
     T9 = P.xrcrg2 * M.vtm;
@@ -1078,6 +1097,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.gcrgs = -(W.gcrgg + W.gcrgd + W.gcrgb);
   }
 
+  XB_SYNC_POINT(2);
   // ---- bias-dependent source / drain resistance (rdsMod) --------------------------------------
   if (M.rdsMod) {
     real dgstot_dvd, dgstot_dvg, dgstot_dvs, dgstot_dvb;
@@ -1148,6 +1168,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.gdtots = W.gdtotb = 0.0;
   }
 
+  XB_SYNC_POINT(2);
   // ---- GIDL / GISL ----------------------------------------------------------------------------
   {
     T0 = (M.mtrlMod == 0) ? 3.0 * toxe : M.epsrsub * toxe / epsrox;
@@ -1174,6 +1195,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     (void)voff;
   }
 
+  XB_SYNC_POINT(1);
   // ---- gate direct-tunnelling currents ------------------------------------------------------------
   real Vfbeff = 0.0, dVfbeff_dVg = 0.0, dVfbeff_dVb = 0.0;
   real Voxacc = 0.0, dVoxacc_dVg = 0.0, dVoxacc_dVb = 0.0;
@@ -1440,6 +1462,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.Igb = W.gIgbg = W.gIgbd = W.gIgbs = W.gIgbb = 0.0;
   }
 
+  XB_SYNC_POINT(1);
   // ---- multi-finger scaling ------------------------------------------------------------------------
   if (I.nf != 1.0) {
     const real nf = I.nf;
@@ -1482,6 +1505,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
 
   W.Vds_s = Vds; W.Vgs_s = Vgs; W.Vbs_s = Vbs;   // reference members Vds, Vgs, Vbs
 
+  XB_SYNC_POINT(2);
   // ---- hand over to the C-V stage ---------------------------------------------------------------------
   C.Vds = Vds; C.Vgs = Vgs; C.Vbs = Vbs; C.Vdb = Vdb;
   C.Vbseff = Vbseff; C.dVbseff_dVb = dVbseff_dVb;

@@ -23,12 +23,19 @@ XB_HD void evaluate(const SolverFlags &S, const B4Model &M, const B4Size &P, con
                     B4Mid &W, E &e) {
   DcCarry C;
   stage_voltages(S, M, I, V, sto_old, have_old, von_prev, W);
+  XB_SYNC_POINT(1);
   stage_dc(S, M, P, I, W, C);
+  XB_SYNC_POINT(1);
   stage_cv(S, M, P, I, W, C);
+  XB_SYNC_POINT(1);
   stage_caps(M, P, I, W);
+  XB_SYNC_POINT(1);
   stage_fvars(M, I, W);
+  XB_SYNC_POINT(1);
   emit_vectors(S, M, I, W, e);
+  XB_SYNC_POINT(1);
   emit_matrices(M, I, W, e);
+  XB_SYNC_POINT(2);
 }
 
 // The 22 store-vector values published by Master::updateState (N_DEV_MOSFET_B4.C:10552-10580).

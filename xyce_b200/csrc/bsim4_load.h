@@ -54,6 +54,7 @@ XB_HD void stage_caps(const B4Model &M, const B4Size &P, const B4Inst &I, B4Mid 
     }
   }
 
+  XB_SYNC_POINT(2);
   // ---- capacitances (setupCapacitors_newDAE, trnqsMod == 0 branch) ----
   // Forward-frame intrinsic blocks; reverse mode swaps the drain/source roles.
   const bool fwd = (W.mode > 0);
@@ -127,6 +128,7 @@ XB_HD void stage_caps(const B4Model &M, const B4Size &P, const B4Inst &I, B4Mid 
   }
   W.CAPcbbb = -(W.CAPcbdb + W.CAPcbgb + W.CAPcbsb + W.CAPcbgmb);
 
+  XB_SYNC_POINT(2);
   // ---- series-resistance currents (B4p82.C:7011-7032) ----
   if (M.rdsMod == 1) {
     W.Idrain = W.gdtot * W.Vddp;

@@ -152,7 +152,10 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (!ctx || !name) return 1;
   const std::string n(name);
   if (n == "b4_arith" && value >= 0 && value <= 2) { ctx->b4_arith = value; return 0; }
-  if (n == "b4_minblocks" && value >= 2 && value <= 6) { ctx->b4_minblocks = value; return 0; }
+  if (n == "b4_minblocks" && value >= 1 && value <= 6) { ctx->b4_minblocks = value; return 0; }
+  if (n == "b4_threads" && value >= 64 && value <= 512) { ctx->b4_threads = value; return 0; }
+  if (n == "b4_uniform" && (value == 0 || value == 1)) { ctx->b4_uniform = value; return 0; }
+  if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
 
@@ -280,7 +283,9 @@ int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const
   XG_CUDA(upload(&ctx->d_sizes, P.data(), P.size()));
   ctx->n_models = n_models;
   ctx->n_sizes = n_sizes;
-  for (auto &g : ctx->groups) { g.dev.models = ctx->d_models; g.dev.sizes = ctx->d_sizes; }
+  ctx->h_models = M;
+  ctx->h_sizes = P;
+  for (auto &g : ctx->groups) { g.dev.models = ctx->d_models; g.dev.sizes = ctx->d_sizes; g.packs_valid = false; }
   return 0;
 }
 
@@ -313,6 +318,10 @@ int xgpu_b4_group_add(xgpu_ctx *ctx, int n, const double *inst_d, const int32_t 
     }
   }
   g.general = all_default ? 0 : 1;
+  for (int i = 0; i < n; ++i) {
+    if (i > 0 && model_idx[i] == model_idx[i - 1] && size_idx[i] == size_idx[i - 1]) { ++g.run_count.back(); continue; }
+    g.run_model.push_back(model_idx[i]); g.run_size.push_back(size_idx[i]); g.run_start.push_back(i); g.run_count.push_back(1);
+  }
   const int nn = g.general ? kNumNodes : 4;
   g.lids.assign((size_t)kNumNodes * n, -1);
   for (int i = 0; i < n; ++i)
@@ -476,7 +485,25 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
   a.sol = d_sol; a.next_sta = d_next_sta; a.curr_sta = d_curr_sta; a.next_sto = d_next_sto; a.curr_sto = d_curr_sto;
   for (int p = 0; p < 4; ++p) a.vec_planes[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
   for (int p = 0; p < 2; ++p) a.mat_planes[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
-  for (auto &g : ctx->groups) { launch_b4_group(g.dev, a, ctx->b4_arith, ctx->b4_minblocks, ctx->stream); ++ctx->launches; }
+  for (auto &g : ctx->groups) {
+    const bool lockstep = ctx->b4_lockstep && ctx->b4_arith == 2;
+    const bool uniform = (ctx->b4_uniform || lockstep) && (int)g.run_start.size() <= kMaxUniformRuns;
+    if (lockstep && !uniform) return fail(ctx, 18, "b4_lockstep needs the uniform-record kernel (at most 64 model/bin runs per group)");
+    if (uniform && !g.packs_valid) {
+      g.packs.clear();
+      for (size_t r = 0; r < g.run_start.size(); ++r) {
+        if (r % kRunsPerPack == 0) { g.packs.emplace_back(); g.packs.back().nruns = 0; }
+        BinRun &br = g.packs.back().run[g.packs.back().nruns++];
+        br.M = ctx->h_models[g.run_model[r]]; br.P = ctx->h_sizes[g.run_size[r]];
+        br.start = g.run_start[r]; br.count = g.run_count[r];
+      }
+      g.packs_valid = true;
+    }
+    const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, ctx->b4_threads, ctx->b4_minblocks,
+                                   uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream);
+    if (nl < 0) return fail(ctx, 19, "unsupported BSIM4 launch shape (b4_threads, b4_minblocks)");
+    ctx->launches += nl;
+  }
   for (auto &g : ctx->sgroups) { xb::simple::launch_group(g.dev, a, ctx->stream); ++ctx->launches; }
   XG_CUDA(cudaGetLastError());
   return 0;

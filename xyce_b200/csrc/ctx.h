@@ -19,6 +19,11 @@ struct XgHostGroup {
   double *d_inst_d = nullptr, *d_von = nullptr;
   int *d_topo = nullptr, *d_model_idx = nullptr, *d_size_idx = nullptr, *d_lids = nullptr;
   int *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
+  // runs of equal (model, bin) along the instance order; packs = their records, rebuilt when the
+  // model table changes (empty = more than kMaxUniformRuns runs -> per-thread-record kernel)
+  std::vector<int32_t> run_model, run_size, run_start, run_count;
+  std::vector<xb::b4::BinPack> packs;
+  bool packs_valid = false;
 };
 
 // groups of the small compact models (diode, MOSFET level 1, BJT, ADMS-shaped rlc): flat per-instance records
@@ -50,7 +55,9 @@ struct xgpu_ctx {
   bool own_stream = false;
   std::string err;
   long long launches = 0;
-  int b4_arith = 2, b4_minblocks = 4;   // kernel variant (xgpu_set_option); 0/2 = strict parity arithmetic
+  // BSIM4 kernel variant (xgpu_set_option): arithmetic 0 strict / 1 fma / 2 fma + reciprocal division,
+  // block shape, uniform-record kernel on/off, lock-step barriers 0/1
+  int b4_arith = 2, b4_threads = 128, b4_minblocks = 4, b4_uniform = 1, b4_lockstep = 0;
 
   int n = 0;
   int64_t nnz = 0;
@@ -59,6 +66,8 @@ struct xgpu_ctx {
 
   xb::b4::B4Model *d_models = nullptr;
   xb::b4::B4Size *d_sizes = nullptr;
+  std::vector<xb::b4::B4Model> h_models;
+  std::vector<xb::b4::B4Size> h_sizes;
   int n_models = 0, n_sizes = 0;
   std::vector<XgHostGroup> groups;
   std::vector<XgSimpleGroup> sgroups;       // evaluated after the BSIM4 groups, in insertion order

@@ -24,6 +24,22 @@
 #define XB_REAL double
 #endif
 
+// Lock-step builds (XB_LOCKSTEP=1, device only) put a block-wide barrier between the sections of the
+// large evaluators so that all warps of a block execute the same ~1-2k instruction window and share
+// instruction-cache lines.  Every thread of the block must reach each XB_SYNC_POINT().
+#ifndef XB_LOCKSTEP
+#define XB_LOCKSTEP 0
+#endif
+// XB_SYNC_POINT(level): level 1 = coarse grid (about every 1k instructions), 2 = fine grid; active when
+// level <= XB_LOCKSTEP.  XB_SYNC_POINT_U marks points inside branches on model-card / bin / solver-flag
+// values: legal only when those are uniform per block (the uniform-record kernel).
+#if XB_LOCKSTEP && defined(__CUDA_ARCH__)
+#define XB_SYNC_POINT(level) do { if ((level) <= XB_LOCKSTEP) __syncthreads(); } while (0)
+#else
+#define XB_SYNC_POINT(level) ((void)0)
+#endif
+#define XB_SYNC_POINT_U(level) XB_SYNC_POINT(level)
+
 namespace xb {
 
 using real = XB_REAL;

@@ -8,6 +8,7 @@
 // Include before xb_common.h and define XB_REAL to select one of them.
 #pragma once
 #include <math.h>
+#include "xb_fastmath.h"
 #if defined(__CUDACC__)
 #define XBR_HD __host__ __device__ __forceinline__
 #else
@@ -40,22 +41,19 @@ struct FastDivPolicy {
   static XBR_HD double mul(double a, double b) { return a * b; }
   static XBR_HD double div(double a, double b) {
 #if defined(__CUDA_ARCH__)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));     // ~20-bit seed (MUFU.RCP64H)
-    double e = fma(-b, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-b, r, 1.0);
-    r = fma(r, e, r);                                           // full-precision reciprocal
-    double q = a * r;
-    const double rem = fma(-b, q, a);
-    return fma(rem, r, q);                                       // one correction step
+    return fm::div(a, b);
 #else
     return a / b;
 #endif
   }
   static XBR_HD double sqrt_(double a) { return ::sqrt(a); }
+#if defined(__CUDA_ARCH__)
+  static XBR_HD double exp_(double a) { return fm::exp(a); }
+  static XBR_HD double log_(double a) { return fm::log(a); }
+#else
   static XBR_HD double exp_(double a) { return ::exp(a); }
   static XBR_HD double log_(double a) { return ::log(a); }
+#endif
   static XBR_HD void cmp() {}
 };
 
