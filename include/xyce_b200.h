@@ -39,8 +39,14 @@ int xgpu_sync(xgpu_ctx *ctx);
 /* Tuning knobs.  "b4_arith": 0 = strict arithmetic (no FMA contraction, IEEE division),
  * 1 = FMA contraction, 2 = FMA + branch-free reciprocal division (<= 2 ulp per divide; default --
  * validated against the reference at 1e-12 by tests/test_gpu_bsim4_parity.py like the others).
- * "b4_minblocks": 2, 3 or 4 (default) resident 128-thread blocks per SM (255 / 168 / 128 registers). */
+ * "b4_threads" / "b4_minblocks": block shape of the BSIM4 kernel (threads per block x resident blocks per
+ * SM; registers per thread = 65536 / (threads * blocks), capped at 255); b4_threads = 0 (default) picks the
+ * shape from the group size.  "b4_uniform": 1 (default) = model card and bin of a run of equal instances are
+ * passed in the kernel parameter block, 0 = every thread loads its own records.  "b4_lockstep": 1 = block
+ * barriers between evaluation sections (diagnostic variant, needs b4_uniform). */
 int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value);
+/* Diagnostics: evaluate the fast-variant exp (which = 0), log (1) or a/b (2) on host arrays of length n. */
+int xgpu_selftest_fastmath(xgpu_ctx *ctx, int which, int n, const double *h_a, const double *h_b, double *h_out);
 
 /* ---- linear-system shape ----
  * CSR pattern shared by dFdx, dQdx and the Jacobian: the output of

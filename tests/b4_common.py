@@ -78,18 +78,20 @@ class HostMirror:
         return out
 
 
-def isolated_devices(ref_cls, n_pairs, variant="default", seed=0, inst_extra=None):
-    """n_pairs nmos + n_pairs pmos, every terminal on its own node (4 nodes per device)."""
+def isolated_devices(ref_cls, n_pairs, variant="default", seed=0, inst_extra=None, sorted_bins=False):
+    """n_pairs nmos + n_pairs pmos, every terminal on its own node (4 nodes per device).  sorted_bins orders
+    the instances by (type, L, W) like an adaptor does, so that equal (model, bin) records form long runs."""
     rng = np.random.default_rng(seed)
     ndev = 2 * n_pairs
     c = ref_cls(4 * ndev)
     nv, pv = VARIANTS[variant]
     c.add_model("nch", "NMOS", {**NMOS_CARD, **nv})
     c.add_model("pch", "PMOS", {**PMOS_CARD, **pv})
-    for i in range(ndev):
-        is_n = (i % 2 == 0)
-        ip = dict(L=float(rng.choice([6e-8, 1e-7, 2.5e-7])), W=float(rng.choice([2e-7, 1e-6, 4e-6])),
-                  AD=2e-13, AS=2e-13, PD=2.4e-6, PS=2.4e-6)
+    specs = [((i % 2 == 0), float(rng.choice([6e-8, 1e-7, 2.5e-7])), float(rng.choice([2e-7, 1e-6, 4e-6]))) for i in range(ndev)]
+    if sorted_bins:
+        specs.sort(key=lambda t: (not t[0], t[1], t[2]))
+    for i, (is_n, L, W) in enumerate(specs):
+        ip = dict(L=L, W=W, AD=2e-13, AS=2e-13, PD=2.4e-6, PS=2.4e-6)
         if inst_extra:
             ip.update(inst_extra)
         c.add_instance("M:%d" % i, "nch" if is_n else "pch", [4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3], ip)

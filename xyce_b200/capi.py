@@ -131,6 +131,14 @@ class Engine:
         self._chk(self.lib.xgpu_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    def selftest_fastmath(self, which, a, b=None):
+        """fast-variant exp (0) / log (1) / a/b (2) of the BSIM4 kernel, evaluated on the device."""
+        a = _f64(a)
+        b = None if b is None else _f64(b)
+        out = np.empty_like(a)
+        self._chk(self.lib.xgpu_selftest_fastmath(self.h, int(which), len(a), _dp(a), _dp(b), _dp(out)))
+        return out
+
     def set_sizes(self, n_state, n_store):
         self.n_state, self.n_store = int(n_state), int(n_store)
         self._chk(self.lib.xgpu_sizes_set(self.h, self.n_state, self.n_store))

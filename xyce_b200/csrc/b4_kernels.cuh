@@ -70,7 +70,7 @@ constexpr int kMaxUniformRuns = 64;   // groups with more distinct runs use the 
 // (threads per block, resident blocks per SM) shapes compiled for the default-topology kernel;
 // registers per thread = 65536 / (threads * blocks), capped at 255.
 #define XB_B4_LAUNCH_SHAPES(X) \
-  X(128, 2) X(128, 3) X(128, 4) X(128, 5) X(256, 1) X(256, 2) X(384, 1) X(512, 1)
+  X(64, 4) X(64, 6) X(96, 4) X(128, 2) X(128, 3) X(128, 4) X(256, 1) X(384, 1) X(512, 1)
 
 // arith: 0 exact (no FMA contraction, IEEE division), 1 fma, 2 fast (fma + reciprocal division);
 // lockstep: block-wide barriers between evaluation sections keep the warps of a block inside the same

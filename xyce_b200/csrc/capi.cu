@@ -153,7 +153,7 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   const std::string n(name);
   if (n == "b4_arith" && value >= 0 && value <= 2) { ctx->b4_arith = value; return 0; }
   if (n == "b4_minblocks" && value >= 1 && value <= 6) { ctx->b4_minblocks = value; return 0; }
-  if (n == "b4_threads" && value >= 64 && value <= 512) { ctx->b4_threads = value; return 0; }
+  if (n == "b4_threads" && (value == 0 || (value >= 64 && value <= 512))) { ctx->b4_threads = value; return 0; }
   if (n == "b4_uniform" && (value == 0 || value == 1)) { ctx->b4_uniform = value; return 0; }
   if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
@@ -499,7 +499,13 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
       }
       g.packs_valid = true;
     }
-    const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, ctx->b4_threads, ctx->b4_minblocks,
+    // b4_threads == 0: pick the block shape from the group size (measured on B200 at the C2 operating
+    // point, profiles/r01_b4_kernel_variants_v2.json): up to ~300k instances the run is a few waves long and
+    // 12 warps per SM (128 x 3, 168 registers) finish soonest; beyond that 8 warps per SM without any
+    // spill (128 x 2, 255 registers) deliver the most evaluations per second
+    int threads = ctx->b4_threads, minblocks = ctx->b4_minblocks;
+    if (threads == 0) { threads = 128; minblocks = g.n <= 300000 ? 3 : 2; }
+    const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, threads, minblocks,
                                    uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream);
     if (nl < 0) return fail(ctx, 19, "unsupported BSIM4 launch shape (b4_threads, b4_minblocks)");
     ctx->launches += nl;

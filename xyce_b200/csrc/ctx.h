@@ -57,7 +57,7 @@ struct xgpu_ctx {
   long long launches = 0;
   // BSIM4 kernel variant (xgpu_set_option): arithmetic 0 strict / 1 fma / 2 fma + reciprocal division,
   // block shape, uniform-record kernel on/off, lock-step barriers 0/1
-  int b4_arith = 2, b4_threads = 128, b4_minblocks = 4, b4_uniform = 1, b4_lockstep = 0;
+  int b4_arith = 2, b4_threads = 0 /* auto */, b4_minblocks = 2, b4_uniform = 1, b4_lockstep = 0;
 
   int n = 0;
   int64_t nnz = 0;
