@@ -34,6 +34,7 @@
 #include <N_DEV_DeviceOptions.h>
 #include <N_DEV_ExternData.h>
 #include <N_DEV_MatrixLoadData.h>
+#include <N_LAS_Vector.h>
 #include <N_DEV_SolverState.h>
 #include <N_LAS_Matrix.h>
 #include <N_UTL_Math.h>
@@ -95,6 +96,60 @@ class CsrMatrix : public Linear::Matrix {
   void print(std::ostream &) const override {}
 };
 
+// View of a std::vector<double> with the Linear::Vector element-access contract (operator[] on the
+// overlapped storage, N_LAS_EpetraVector.h:183-198); MOSFET level 1 and the BJT read their solution and
+// store/state history through these objects rather than through the raw pointers.
+class RawVector : public Linear::Vector {
+ public:
+  std::vector<double> *v = nullptr;
+  double &operator[](int i) override { return (*v)[i]; }
+  const double &operator[](int i) const override { return (*v)[i]; }
+  Linear::Vector &operator=(const Linear::Vector &) override { return *this; }
+  Linear::MultiVector &operator=(const Linear::MultiVector &) override { return *this; }
+  Linear::Vector *cloneVector() const override { return 0; }
+  Linear::Vector *cloneCopyVector() const override { return 0; }
+  double dotProduct(const Linear::Vector &) const override { return 0; }
+  Linear::MultiVector *clone() const override { return 0; }
+  Linear::MultiVector *cloneCopy() const override { return 0; }
+  void dotProduct(const Linear::MultiVector &, std::vector<double> &) const override {}
+  void scale(const double) override {}
+  void multiply(const Linear::MultiVector &) override {}
+  void update(double, const Linear::MultiVector &, double) override {}
+  void update(double, const Linear::MultiVector &, double, const Linear::MultiVector &, double) override {}
+  int lpNorm(const int, double *) const override { return 0; }
+  int infNorm(double *, int *) const override { return 0; }
+  int wRMSNorm(const Linear::MultiVector &, double *) const override { return 0; }
+  int wMaxNorm(const Linear::MultiVector &, double *, int *) const override { return 0; }
+  void random() override {}
+  void putScalar(const double a) override { std::fill(v->begin(), v->end(), a); }
+  void addScalar(const double) override {}
+  void absValue(const Linear::MultiVector &) override {}
+  void reciprocal(const Linear::MultiVector &) override {}
+  double *operator()(int r, int) override { return &(*v)[r]; }
+  const double *operator()(int r, int) const override { return &(*v)[r]; }
+  const Linear::Vector *getVectorView(int) const override { return this; }
+  Linear::Vector *getNonConstVectorView(int) override { return this; }
+  const Linear::Vector *getVectorViewAssembled(int) const override { return this; }
+  Linear::Vector *getNonConstVectorViewAssembled(int) override { return this; }
+  int globalLength() const override { return (int)v->size(); }
+  int localLength() const override { return (int)v->size(); }
+  int numVectors() const override { return 1; }
+  int externVectorSize() const override { return 0; }
+  bool vectorImport(const Linear::MultiVector *, Linear::Importer *) override { return false; }
+  bool importOverlap() override { return false; }
+  void writeToFile(const char *, bool, bool) const override {}
+  const double &getElementByGlobalIndex(const int &i, const int &) const override { return (*v)[i]; }
+  bool setElementByGlobalIndex(const int &, const double &, const int &) override { return false; }
+  bool sumElementByGlobalIndex(const int &, const double &, const int &) override { return false; }
+  void clearExternVectorMap() override {}
+  void addElementToExternVectorMap(const int &, const double &) override {}
+  void print(std::ostream &) const override {}
+  const Parallel::ParMap *pmap() const override { return 0; }
+  const Parallel::ParMap *omap() const override { return 0; }
+  const Parallel::Communicator *pdsComm() const override { return 0; }
+  void fillComplete() override {}
+};
+
 struct InstRec {
   DeviceInstance *inst;
   int dev;                   // index into Ctx::masters
@@ -107,6 +162,7 @@ struct Ctx {
   DeviceOptions devOptions;
   SolverState solState;
   ExternData extData;
+  RawVector vSol, vCurrSta, vNextSta, vCurrSto, vNextSto;
   MatrixLoadData mlData;
   FactoryBlock *fb = 0;
   // one Master per device type, in creation order (= DeviceMgr::devicePtrVec_ order)
@@ -290,6 +346,10 @@ int xref_finalize(void *h) {
   e.nextStaVectorRawPtr = c->nextSta.data(); e.currStaVectorRawPtr = e.lastStaVectorRawPtr = c->currSta.data();
   e.nextStaDerivVectorRawPtr = c->staDeriv.data();
   e.nextStoVectorRawPtr = c->nextSto.data(); e.currStoVectorRawPtr = e.lastStoVectorRawPtr = c->currSto.data();
+  c->vSol.v = &c->sol; c->vCurrSta.v = &c->currSta; c->vNextSta.v = &c->nextSta; c->vCurrSto.v = &c->currSto; c->vNextSto.v = &c->nextSto;
+  e.nextSolVectorPtr = e.currSolVectorPtr = e.lastSolVectorPtr = &c->vSol;
+  e.currStaVectorPtr = e.lastStaVectorPtr = &c->vCurrSta; e.nextStaVectorPtr = &c->vNextSta;
+  e.currStoVectorPtr = e.lastStoVectorPtr = &c->vCurrSto; e.nextStoVectorPtr = &c->vNextSto;
   for (auto &r : c->insts) r.inst->setupPointers();
   c->finalized = true;
   return c->n;
@@ -462,6 +522,40 @@ int xref_diode_export(void *h, int idx, double *rec, int *flags, int *lids3) {
   const int g = c->n;
   const int l[3] = {in.li_Pos, in.li_Neg, in.li_Pri};
   for (int i = 0; i < 3; ++i) lids3[i] = (l[i] == g) ? -1 : l[i];
+  return k;
+}
+
+// MOSFET level 1 / BJT records in the order of XB_MOS1_FIELDS / XB_BJT_FIELDS + flag word + node LIDs
+int xref_mos1_export(void *h, int idx, double *rec, int *flags, int *lids6) {
+  Ctx *c = (Ctx *)h;
+  MOSFET1::Instance &in = *static_cast<MOSFET1::Instance *>(c->insts[idx].inst);
+  MOSFET1::Model &mo = in.getModel();
+  int k = 0;
+#define MOD(n) rec[k++] = mo.n;
+#define INS(n) rec[k++] = in.n;
+  XB_MOS1_FIELDS(MOD, INS)
+#undef MOD
+#undef INS
+  *flags = (in.IC_GIVEN ? 1 : 0) | (in.OFF ? 2 : 0);
+  const int g = c->n;
+  const int l[6] = {in.li_Drain, in.li_Gate, in.li_Source, in.li_Bulk, in.li_DrainPrime, in.li_SourcePrime};
+  for (int i = 0; i < 6; ++i) lids6[i] = (l[i] == g) ? -1 : l[i];
+  return k;
+}
+int xref_bjt_export(void *h, int idx, double *rec, int *flags, int *lids7) {
+  Ctx *c = (Ctx *)h;
+  BJT::Instance &in = *static_cast<BJT::Instance *>(c->insts[idx].inst);
+  BJT::Model &mo = in.model_;
+  int k = 0;
+#define MOD(n) rec[k++] = mo.n;
+#define INS(n) rec[k++] = in.n;
+  XB_BJT_FIELDS(MOD, INS)
+#undef MOD
+#undef INS
+  *flags = (in.IC_GIVEN ? 1 : 0) | (in.OFF ? 2 : 0);
+  const int g = c->n;
+  const int l[7] = {in.li_Coll, in.li_Base, in.li_Emit, in.li_Subst, in.li_CollP, in.li_BaseP, in.li_EmitP};
+  for (int i = 0; i < 7; ++i) lids7[i] = (l[i] == g) ? -1 : l[i];
   return k;
 }
 

@@ -48,6 +48,67 @@ class HostDevices:
                     orig=int(out[29]))
 
 
+    def simple(self, type_id, e, flags, V, curr_sto, next_sto, curr_sta, nodes, slots, nstore, nstate):
+        """MOSFET level 1 (type 2) / BJT (type 3) through the host build of the kernel source"""
+        fl, fd = flag_arrays(flags)
+        out = np.zeros(4 * nodes + 2 * slots + nstore + nstate + 1)
+        dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (e["rec"], V, curr_sto, next_sto, curr_sta)]
+        k = self.lib.xbh_simple_eval(int(type_id), dp(keep[0]), int(e["flags"]), ip(fl), dp(fd), dp(keep[1]), dp(keep[2]),
+                                     dp(keep[3]), dp(keep[4]), out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert k == len(out)
+        n, s = nodes, slots
+        return dict(F=out[0:n], Q=out[n:2 * n], FL=out[2 * n:3 * n], QL=out[3 * n:4 * n], JF=out[4 * n:4 * n + s],
+                    JQ=out[4 * n + s:4 * n + 2 * s], store=out[4 * n + 2 * s:4 * n + 2 * s + nstore],
+                    state=out[4 * n + 2 * s + nstore:4 * n + 2 * s + nstore + nstate], orig=int(out[-1]))
+
+
+MOS1_SLOT_ROW = [0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5]
+MOS1_SLOT_COL = [0, 4, 1, 3, 4, 5, 2, 5, 1, 3, 4, 5, 0, 1, 3, 4, 5, 1, 2, 3, 4, 5]
+BJT_SLOT_ROW = [0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6]
+BJT_SLOT_COL = [0, 4, 1, 4, 5, 6, 2, 6, 3, 4, 0, 1, 3, 4, 5, 6, 1, 4, 5, 6, 2, 4, 5, 6]
+# (type id, devtype key of the oracle harness, nodes, store entries used, state entries)
+SIMPLE = {"mos1": (2, "m1", 6, 6, 8, MOS1_SLOT_ROW, MOS1_SLOT_COL), "bjt": (3, "q", 7, 3, 6, BJT_SLOT_ROW, BJT_SLOT_COL)}
+
+MOS1_CARDS = {
+    "basic": ("NMOS", dict(VTO=0.7, KP=1.1e-4, GAMMA=0.4, PHI=0.65, LAMBDA=0.02, TOX=2e-8, CBD=2e-14, CBS=2e-14, IS=1e-14,
+                            CGSO=2e-10, CGDO=2e-10, CGBO=1e-10)),
+    "pmos_rs": ("PMOS", dict(VTO=-0.8, KP=4e-5, GAMMA=0.5, PHI=0.7, LAMBDA=0.03, TOX=2e-8, RD=15.0, RS=12.0, CJ=3e-4, CJSW=2e-10,
+                              MJ=0.4, MJSW=0.3, PB=0.85, JS=1e-6, CGSO=1.5e-10, CGDO=1.5e-10)),
+    "sheet": ("NMOS", dict(VTO=0.5, KP=8e-5, GAMMA=0.3, PHI=0.6, TOX=1.5e-8, RSH=20.0, CJ=2e-4, MJ=0.5, CJSW=1e-10, MJSW=0.5,
+                            NSUB=1e16, UO=500.0)),
+}
+BJT_CARDS = {
+    "basic": ("NPN", dict(IS=1e-15, BF=120.0, BR=2.0, VAF=80.0, CJE=1e-12, CJC=5e-13, TF=3e-10, TR=1e-8)),
+    "res_pnp": ("PNP", dict(IS=2e-15, BF=80.0, BR=1.5, VAF=60.0, VAR=20.0, IKF=5e-2, IKR=1e-2, ISE=1e-13, NE=1.6, ISC=1e-13, NC=1.8,
+                             RB=50.0, RBM=10.0, IRB=1e-3, RC=8.0, RE=1.5, CJE=1.2e-12, VJE=0.8, MJE=0.35, CJC=6e-13, VJC=0.7,
+                             MJC=0.4, XCJC=0.7, CJS=2e-13, VJS=0.6, MJS=0.3, TF=2e-10, XTF=2.0, VTF=3.0, ITF=0.05, TR=5e-9)),
+    "hicur": ("NPN", dict(IS=5e-16, BF=200.0, IKF=1e-2, NK=0.6, RB=100.0, RE=1.0, CJE=8e-13, CJC=4e-13, TF=1e-10, XTF=1.0, ITF=0.02)),
+}
+
+
+def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0):
+    """n_dev isolated devices, every terminal on its own node"""
+    rng = np.random.default_rng(seed)
+    nt = 4
+    c = ref_cls(nt * n_dev)
+    if kind == "mos1":
+        mtype, p = MOS1_CARDS[card]
+        c.add_dev_model("m1", "mmod", mtype, 1, p)
+        for i in range(n_dev):
+            ip = dict(L=float(rng.choice([1e-6, 2e-6])), W=float(rng.choice([5e-6, 2e-5])), AD=2e-11, AS=2e-11, PD=2e-5, PS=2e-5,
+                      NRD=1.0, NRS=1.0)
+            c.add_dev_instance("m1", "M:%d" % i, "mmod", [nt * i, nt * i + 1, nt * i + 2, nt * i + 3], ip)
+    else:
+        mtype, p = BJT_CARDS[card]
+        c.add_dev_model("q", "qmod", mtype, 1, p)
+        for i in range(n_dev):
+            c.add_dev_instance("q", "Q:%d" % i, "qmod", [nt * i, nt * i + 1, nt * i + 2, nt * i + 3], dict(AREA=float(rng.choice([1.0, 3.0]))))
+    c.finalize()
+    return c
+
+
 DIODE_SLOT_ROW = [0, 0, 1, 1, 2, 2, 2]
 DIODE_SLOT_COL = [0, 2, 1, 2, 0, 1, 2]
 

@@ -9,6 +9,8 @@
 #endif
 #include "../../xyce_b200/csrc/bsim4_instance.h"
 #include "../../xyce_b200/csrc/diode_eval.h"
+#include "../../xyce_b200/csrc/mos1_eval.h"
+#include "../../xyce_b200/csrc/bjt_eval.h"
 
 using namespace xb;
 using namespace xb::b4;
@@ -129,6 +131,57 @@ int xbh_diode_eval(const double *rec, int flags, const int *fl, const double *fd
   for (int i = 0; i < 7; ++i) out[k++] = to_double(o.JF[i]);
   for (int i = 0; i < 7; ++i) out[k++] = to_double(o.JQ[i]);
   out[k++] = to_double(o.Vd); out[k++] = to_double(o.Qd); out[k++] = to_double(o.Cd); out[k++] = o.origFlag;
+  return k;
+}
+
+// MOSFET level 1 (type 2) / BJT (type 3):
+// out = F[n] Q[n] FL[n] QL[n] JF[s] JQ[s] store[..] state[..] origFlag; returns the number of doubles written
+int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const double *fd, const double *Vn,
+                    const double *curr_sto, const double *next_sto, const double *curr_sta, double *out) {
+  SolverFlags S; fill_flags(S, fl, fd);
+  int k = 0;
+  if (type == 2) {
+    namespace D = xb::mos1;
+    D::Rec R; int j = 0;
+#define GET(n) R.n = rec[j++];
+    XB_MOS1_FIELDS(GET, GET)
+#undef GET
+    real V[D::kNodes], cs[D::kNumStore], ns[D::kNumStore], ca[D::kNumState];
+    for (int i = 0; i < D::kNodes; ++i) V[i] = Vn[i];
+    for (int i = 0; i < D::kNumStore; ++i) { cs[i] = curr_sto[i]; ns[i] = next_sto[i]; }
+    for (int i = 0; i < D::kNumState; ++i) ca[i] = curr_sta[i];
+    D::Out o;
+    D::evaluate(S, R, flags, V, cs, ns, ca, o);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.F[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.Q[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.FL[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.QL[i]);
+    for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JF[i]);
+    for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JQ[i]);
+    for (int i = 0; i < D::kNumStore; ++i) out[k++] = to_double(o.store[i]);
+    for (int i = 0; i < D::kNumState; ++i) out[k++] = to_double(o.state[i]);
+    out[k++] = o.origFlag;
+  } else if (type == 3) {
+    namespace D = xb::bjt;
+    D::Rec R; int j = 0;
+#define GET(n) R.n = rec[j++];
+    XB_BJT_FIELDS(GET, GET)
+#undef GET
+    real V[D::kNodes], cs[3], ns[3];
+    for (int i = 0; i < D::kNodes; ++i) V[i] = Vn[i];
+    for (int i = 0; i < 3; ++i) { cs[i] = curr_sto[i]; ns[i] = next_sto[i]; }
+    D::Out o;
+    D::evaluate(S, R, flags, V, cs, ns, o);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.F[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.Q[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.FL[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.QL[i]);
+    for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JF[i]);
+    for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JQ[i]);
+    for (int i = 0; i < 3; ++i) out[k++] = to_double(o.store[i]);
+    for (int i = 0; i < D::kNumState; ++i) out[k++] = to_double(o.state[i]);
+    out[k++] = o.origFlag;
+  }
   return k;
 }
 

@@ -6,7 +6,7 @@ import pytest
 import oracle_ref
 import xyce_b200
 from b4_common import rel_err, solver_state
-from dev_common import DIODE_CARDS, diode_circuit
+from dev_common import BJT_CARDS, DIODE_CARDS, MOS1_CARDS, SIMPLE, diode_circuit, simple_circuit
 
 pytestmark = pytest.mark.gpu
 
@@ -14,10 +14,13 @@ CASES = {"tran1": dict(transient=1, newtonIter=1), "tran0": dict(transient=1, ne
          "dcop_init": dict(dcop=1, tranop=1, initJct=1, newtonIter=0), "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0)}
 
 
-def check(ref, eng, flags, x, nsto, csto):
+def check(ref, eng, flags, x, nsto, csto, csta=None):
+    csta = np.zeros(ref.n_sta) if csta is None else csta
     ref.set_flags(**flags)
-    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=np.zeros(ref.n_sta))
+    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta)
     eng.set_state(0, nsto); eng.set_state(1, csto)
+    if ref.n_sta:
+        eng.set_state(3, csta)
     want = ref.load(x)
     got = eng.load_host(x, solver_state(**flags))
     for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
@@ -47,6 +50,67 @@ def test_diode(card, case):
     eng.close()
 
 
+SIMPLE_CASES = dict(CASES, dcop2=dict(dcop=1, tranop=1, newtonIter=2), tran_init=dict(transient=1, newtonIter=0, initTran=1))
+
+
+@pytest.mark.parametrize("case", sorted(SIMPLE_CASES))
+@pytest.mark.parametrize("kind,card", [("mos1", c) for c in sorted(MOS1_CARDS)] + [("bjt", c) for c in sorted(BJT_CARDS)])
+def test_mos1_and_bjt(kind, card, case):
+    type_id, key, nodes, nstore, nstate, srow, scol = SIMPLE[kind]
+    ref = simple_circuit(oracle_ref.RefCircuit, kind, card, n_dev=150, seed=5)
+    ex = [ref.dev_export(i, key) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(type_id, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.finalize()
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-1.5, 1.5, ref.n)
+    check(ref, eng, SIMPLE_CASES[case], x, rng.normal(0.2, 0.5, ref.n_sto), rng.normal(0.2, 0.5, ref.n_sto),
+          rng.normal(0.0, 1e-14, ref.n_sta))
+    if case == "tran_init":
+        assert rel_err(eng.get_state(3), ref.get_state()["curr_sta"], 1e-30) < 1e-12
+    eng.close()
+
+
+def test_mixed_device_types_in_one_system():
+    """BASELINE config 5 shape: diode + BJT + MOSFET level 1 groups loaded into one CSR system, accumulation in
+    device-type order like DeviceMgr's devicePtrVec_ loop (N_DEV_DeviceMgr.C:4238-4248)."""
+    rng = np.random.default_rng(8)
+    n_each = 40
+    ref = oracle_ref.RefCircuit(6)                      # 6 shared nodes: every device lands on the same few rows
+    mt, mp = MOS1_CARDS["pmos_rs"]; qt, qp = BJT_CARDS["res_pnp"]
+    dp = dict(DIODE_CARDS["rs_bv"]); dp.pop("LEVEL", None)
+    ref.add_dev_model("d", "dmod", "D", 1, dp)
+    ref.add_dev_model("q", "qmod", qt, 1, qp)
+    ref.add_dev_model("m1", "mmod", mt, 1, mp)
+    kinds = []
+    for i in range(n_each):
+        ref.add_dev_instance("d", "D:%d" % i, "dmod", [int(v) for v in rng.choice(6, 2, replace=False)], dict(AREA=1.0)); kinds.append("d")
+    for i in range(n_each):
+        ref.add_dev_instance("q", "Q:%d" % i, "qmod", [int(v) for v in rng.choice(6, 4, replace=False)], dict(AREA=1.0)); kinds.append("q")
+    for i in range(n_each):
+        ref.add_dev_instance("m1", "M:%d" % i, "mmod", [int(v) for v in rng.choice(6, 4, replace=False)],
+                             dict(L=1e-6, W=1e-5, AD=2e-11, AS=2e-11, PD=2e-5, PS=2e-5, NRD=1.0, NRS=1.0)); kinds.append("m1")
+    ref.finalize()
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    idx = lambda k: [i for i, kk in enumerate(kinds) if kk == k]
+    ex = [ref.diode_export(i) for i in idx("d")]
+    eng.add_simple_group(1, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    for tid, key in ((3, "q"), (2, "m1")):
+        ex = [ref.dev_export(i, key) for i in idx(key)]
+        eng.add_simple_group(tid, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                             [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.finalize()
+    x = rng.uniform(-1.0, 1.0, ref.n)
+    check(ref, eng, CASES["tran1"], x, rng.normal(0.2, 0.4, ref.n_sto), rng.normal(0.2, 0.4, ref.n_sto), rng.normal(0, 1e-14, ref.n_sta))
+    eng.close()
+
+
 # ---- ADMS-shaped plugin device (user_plugin/rlc.va) ----
 def test_rlc_plugin_equals_discrete_and_analytic():
     """user_plugin/rlc_adms.cir: the ADMS-shaped device must reproduce (a) the same circuit built from
@@ -67,7 +131,9 @@ def test_rlc_plugin_equals_discrete_and_analytic():
     assert abs(len(a["t"]) - len(b["t"])) <= 0.02 * len(b["t"])
     for p in range(a["wave"].shape[1]):
         wb = np.interp(a["t"], b["t"], b["wave"][:, p])
-        assert np.max(np.abs(a["wave"][:, p] - wb)) <= 3e-2 * np.max(np.abs(wb)) + 1e-9   # two LTE-controlled runs
+        # two LTE-controlled runs with different step sequences: each is only held to the integrator's
+        # RELTOL / ABSTOL (1e-3 / 1e-6 per unknown per step), so compare at a few times that
+        assert np.max(np.abs(a["wave"][:, p] - wb)) <= 3e-2 * np.max(np.abs(wb)) + 5e-6
     # analytic: L di/dt = v_i2, C d(v_i1 - v_i2)/dt = i, (v1 - v_i1)/R = i  with v1 = 5 + 5 sin(2 pi f t)
     R, L, C, f = 1e3, 1e-3, 1e-12, 20e6
     def rhs(t, y):          # y = [i, vc]  (vc = v_i1 - v_i2)

@@ -1,0 +1,55 @@
+"""CPU-only: MOSFET level 1 and Gummel-Poon BJT evaluator sources (host build of the kernel headers) against
+the reference's own device objects (oracle/_ref): assembled F, Q, limiter vectors, dFdx, dQdx, store and
+state vectors at 1e-12."""
+import numpy as np
+import pytest
+
+import oracle_ref
+from b4_common import rel_err
+from dev_common import BJT_CARDS, MOS1_CARDS, SIMPLE, HostDevices, assemble, simple_circuit
+
+pytestmark = pytest.mark.skipif(not oracle_ref.available(), reason="oracle/_ref not built")
+
+CASES = {"tran1": dict(transient=1, newtonIter=1), "tran0": dict(transient=1, newtonIter=0),
+         "dcop_init": dict(dcop=1, tranop=1, initJct=1, newtonIter=0), "dcop2": dict(dcop=1, tranop=1, newtonIter=2),
+         "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0)}
+
+
+def run(kind, card, case, seed=3):
+    type_id, key, nodes, nstore, nstate, srow, scol = SIMPLE[kind]
+    hd = HostDevices()
+    ref = simple_circuit(oracle_ref.RefCircuit, kind, card, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    flags = CASES[case]
+    ref.set_flags(**flags)
+    x = rng.uniform(-1.5, 1.5, ref.n)
+    nsto, csto = rng.normal(0.2, 0.5, ref.n_sto), rng.normal(0.2, 0.5, ref.n_sto)
+    csta = rng.normal(0.0, 1e-14, ref.n_sta)
+    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta)
+    want = ref.load(x)
+    st = ref.get_state()
+    per, lids = [], []
+    for i in range(ref.n_inst):
+        e = ref.dev_export(i, key)
+        V = [x[g] if g >= 0 else 0.0 for g in e["lids"]]
+        o = hd.simple(type_id, e, flags, V, csto[e["sto0"]:e["sto0"] + nstore], nsto[e["sto0"]:e["sto0"] + nstore],
+                      csta[e["sta0"]:e["sta0"] + nstate], nodes, len(srow), nstore, nstate)
+        per.append(o); lids.append(e["lids"])
+        assert rel_err(o["store"], st["next_sto"][e["sto0"]:e["sto0"] + nstore], 1e-25) < 1e-12, (i, "store")
+        assert rel_err(o["state"], st["next_sta"][e["sta0"]:e["sta0"] + nstate], 1e-25) < 1e-12, (i, "state")
+    asm = assemble(per, lids, srow, scol, ref.n, ref.rowptr, ref.colind)
+    for k in want:
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(asm[k], want[k], scale) < 1e-12, (kind, card, case, k)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("card", sorted(MOS1_CARDS))
+def test_mos1(card, case):
+    run("mos1", card, case)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("card", sorted(BJT_CARDS))
+def test_bjt(card, case):
+    run("bjt", card, case)

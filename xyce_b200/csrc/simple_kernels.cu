@@ -3,6 +3,8 @@
 #include "simple_kernels.cuh"
 #include "diode_eval.h"
 #include "adms_rlc_eval.h"
+#include "bjt_eval.h"
+#include "mos1_eval.h"
 
 namespace xb {
 namespace simple {
@@ -46,6 +48,89 @@ __global__ void __launch_bounds__(128) diode_kernel(GroupDev g, b4::LoadArgs a) 
   }
 }
 
+// shared tail of the small-device kernels: contributions -> planes (coalesced, plane[row][instance])
+template <class Out, int NODES, int SLOTS>
+__device__ __forceinline__ void store_planes(const GroupDev &g, const b4::LoadArgs &a, const Out &o, int i) {
+  const int n = g.n;
+#pragma unroll
+  for (int r = 0; r < NODES; ++r) {
+    a.vec_planes[0][g.vec_base + (size_t)r * n + i] = to_double(o.F[r]);
+    a.vec_planes[1][g.vec_base + (size_t)r * n + i] = to_double(o.Q[r]);
+    a.vec_planes[2][g.vec_base + (size_t)r * n + i] = to_double(o.FL[r]);
+    a.vec_planes[3][g.vec_base + (size_t)r * n + i] = to_double(o.QL[r]);
+  }
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    a.mat_planes[0][g.mat_base + (size_t)s * n + i] = to_double(o.JF[s]);
+    a.mat_planes[1][g.mat_base + (size_t)s * n + i] = to_double(o.JQ[s]);
+  }
+}
+
+__global__ void __launch_bounds__(128) mos1_kernel(GroupDev g, b4::LoadArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const int n = g.n;
+  namespace D = mos1;
+  D::Rec R;
+  {
+    int k = 0;
+#define LD(name) R.name = __ldg(g.rec + (size_t)(k++) * n + i);
+    XB_MOS1_FIELDS(LD, LD)
+#undef LD
+  }
+  real V[D::kNodes];
+#pragma unroll
+  for (int t = 0; t < D::kNodes; ++t) V[t] = gatherv(a.sol, __ldg(g.lids + (size_t)t * n + i));
+  const int sto0 = __ldg(g.sto_lid0 + i), ss = g.sto_stride, sta0 = __ldg(g.sta_lid0 + i), as = g.sta_stride;
+  real cs[D::kNumStore], ns[D::kNumStore], ca[D::kNumState];
+#pragma unroll
+  for (int t = 0; t < D::kNumStore; ++t) { cs[t] = a.curr_sto[sto0 + (size_t)t * ss]; ns[t] = a.next_sto[sto0 + (size_t)t * ss]; }
+#pragma unroll
+  for (int t = 0; t < D::kNumState; ++t) ca[t] = a.curr_sta[sta0 + (size_t)t * as];
+  D::Out o;
+  D::evaluate(a.S, R, __ldg(g.flags + i), V, cs, ns, ca, o);
+#pragma unroll
+  for (int t = 0; t < D::kNumStore; ++t) a.next_sto[sto0 + (size_t)t * ss] = to_double(o.store[t]);
+#pragma unroll
+  for (int t = 0; t < D::kNumState; ++t) a.next_sta[sta0 + (size_t)t * as] = to_double(o.state[t]);
+  g.orig_flag[i] = o.origFlag;
+  store_planes<D::Out, D::kNodes, D::kSlots>(g, a, o, i);
+}
+
+__global__ void __launch_bounds__(128) bjt_kernel(GroupDev g, b4::LoadArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const int n = g.n;
+  namespace D = bjt;
+  D::Rec R;
+  {
+    int k = 0;
+#define LD(name) R.name = __ldg(g.rec + (size_t)(k++) * n + i);
+    XB_BJT_FIELDS(LD, LD)
+#undef LD
+  }
+  real V[D::kNodes];
+#pragma unroll
+  for (int t = 0; t < D::kNodes; ++t) V[t] = gatherv(a.sol, __ldg(g.lids + (size_t)t * n + i));
+  const int sto0 = __ldg(g.sto_lid0 + i), ss = g.sto_stride, sta0 = __ldg(g.sta_lid0 + i), as = g.sta_stride;
+  real cs[3], ns[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) { cs[t] = a.curr_sto[sto0 + (size_t)t * ss]; ns[t] = a.next_sto[sto0 + (size_t)t * ss]; }
+  D::Out o;
+  D::evaluate(a.S, R, __ldg(g.flags + i), V, cs, ns, o);
+#pragma unroll
+  for (int t = 0; t < 3; ++t) a.next_sto[sto0 + (size_t)t * ss] = to_double(o.store[t]);
+#pragma unroll
+  for (int t = 0; t < D::kNumState; ++t) a.next_sta[sta0 + (size_t)t * as] = to_double(o.state[t]);
+  // first Newton step of the first transient step: charges also go to the current state (N_DEV_BJT.C:4135-4147)
+  if (!a.S.dcopFlag && a.S.initTranFlag && a.S.newtonIter == 0) {
+#pragma unroll
+    for (int t = 0; t < D::kNumState; ++t) a.curr_sta[sta0 + (size_t)t * as] = to_double(o.state[t]);
+  }
+  g.orig_flag[i] = o.origFlag;
+  store_planes<D::Out, D::kNodes, D::kSlots>(g, a, o, i);
+}
+
 __global__ void __launch_bounds__(128) rlc_kernel(GroupDev g, b4::LoadArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
@@ -76,6 +161,13 @@ const int kRlcRow[adms::rlc::kSlots] = {0, 0, 2, 2, 2, 3, 3, 3, 1, 4, 4, 4};
 const int kRlcCol[adms::rlc::kSlots] = {0, 2, 0, 2, 3, 2, 3, 4, 4, 3, 1, 4};
 const TypeInfo kRlcInfo = {adms::rlc::kNodes, adms::rlc::kSlots, adms::rlc::kNumFields, 0, 0, kRlcRow, kRlcCol};
 
+const int kMos1Row[mos1::kSlots] = {0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5};
+const int kMos1Col[mos1::kSlots] = {0, 4, 1, 3, 4, 5, 2, 5, 1, 3, 4, 5, 0, 1, 3, 4, 5, 1, 2, 3, 4, 5};
+const TypeInfo kMos1Info = {mos1::kNodes, mos1::kSlots, mos1::kNumFields, mos1::kNumStore, mos1::kNumState, kMos1Row, kMos1Col};
+const int kBjtRow[bjt::kSlots] = {0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6};
+const int kBjtCol[bjt::kSlots] = {0, 4, 1, 4, 5, 6, 2, 6, 3, 4, 0, 1, 3, 4, 5, 6, 1, 4, 5, 6, 2, 4, 5, 6};
+const TypeInfo kBjtInfo = {bjt::kNodes, bjt::kSlots, bjt::kNumFields, bjt::kNumStore, bjt::kNumState, kBjtRow, kBjtCol};
+
 const int kDiodeRow[diode::kSlots] = {0, 0, 1, 1, 2, 2, 2};
 const int kDiodeCol[diode::kSlots] = {0, 2, 1, 2, 0, 1, 2};
 const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3, 0, kDiodeRow, kDiodeCol};
@@ -85,6 +177,8 @@ const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3,
 const TypeInfo *type_info(int type) {
   switch (type) {
     case kDiode: return &kDiodeInfo;
+    case kMos1: return &kMos1Info;
+    case kBjt: return &kBjtInfo;
     case kRlc: return &kRlcInfo;
     default: return nullptr;
   }
@@ -95,6 +189,8 @@ void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
   const int blocks = (g.n + 127) / 128;
   switch (g.type) {
     case kDiode: diode_kernel<<<blocks, 128, 0, s>>>(g, a); break;
+    case kMos1: mos1_kernel<<<blocks, 128, 0, s>>>(g, a); break;
+    case kBjt: bjt_kernel<<<blocks, 128, 0, s>>>(g, a); break;
     case kRlc: rlc_kernel<<<blocks, 128, 0, s>>>(g, a); break;
     default: break;
   }

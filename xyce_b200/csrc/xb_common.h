@@ -106,6 +106,7 @@ XB_HD real dexp2(real a) {
 }
 
 XB_HD double rpow(double a, double b) { return pow(a, b); }      // overloaded for the wrapper scalar types
+XB_HD double rtan(double a) { return tan(a); }
 XB_HD real dmax(real a, real b) { return a < b ? b : a; }   // std::max semantics
 XB_HD real dmin(real a, real b) { return b < a ? b : a; }   // std::min semantics
 

@@ -82,6 +82,7 @@ struct RealT {
   friend XBR_HD RealT exp(const RealT &a) { return RealT(P::exp_(a.v)); }
   friend XBR_HD RealT log(const RealT &a) { return RealT(P::log_(a.v)); }
   friend XBR_HD RealT rpow(const RealT &a, const RealT &b) { return RealT(::pow(a.v, b.v)); }
+  friend XBR_HD RealT rtan(const RealT &a) { return RealT(::tan(a.v)); }
   friend XBR_HD RealT fabs(const RealT &a) { return RealT(::fabs(a.v)); }
   friend XBR_HD double to_double(const RealT &a) { return a.v; }
 };
