@@ -25,7 +25,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bsim4_device_load_stamp_evals_per_sec"
 UNIT = "evals/s"
-BYTES_PER_EVAL = 1592.0      # SURVEY.md 8(d) unit U1 (algorithmic bytes per instance evaluation)
+BYTES_PER_EVAL = 1592.0      # SURVEY.md 8(d) unit U1 (algorithmic bytes per instance evaluation incl. assembly re-read)
+BYTES_PER_EVAL_KERNEL = 1128.0   # the evaluation kernel's share of U1: 544 B read + 584 B written per instance
+# dram__bytes_read.sum + dram__bytes_write.sum of one b4_eval launch on this workload (ncu --set full capture
+# summarised in profiles/r01_b4_eval_kernel_v2_ncu_summary.md): 40.8 MB read + 30.5 MB written
+EVAL_KERNEL_DRAM_BYTES = 71.3e6
 FLOPS_PER_EVAL = 1889.0      # executed fp64 operations per evaluation, measured (xyce_b200/data/b4_flop_count.json)
 
 
@@ -135,6 +139,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def tran_extra(device):
+    """BASELINE config 3 (reported next to the headline, not the metric): 1M-MOSFET ring-oscillator array,
+    a short .TRAN on the GPU (device eval + assembly + KLU-pattern refactor/solve + Newton/OneStep driver),
+    wall clock around the C-ABI call, host LU analysis reported separately."""
+    from xyce_b200 import workloads as wl
+    w = wl.ring_oscillator_array(4950, 101)
+    t0 = time.perf_counter()
+    eng = wl.build_engine(w, device=device)
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r0 = eng.tran_run(w["x"], 2e-12, 1e-12, [0])          # first call: includes the one-time host LU analysis
+    t_first = time.perf_counter() - t0
+    eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
+    t0 = time.perf_counter()
+    r = eng.tran_run(w["x"], 4e-11, 1e-12, [0])           # LU pattern already analysed: refactor-only path
+    dt = time.perf_counter() - t0
+    s = r["stats"]
+    eng.close()
+    return {"workload": "4950 x 101-stage BSIM4 ring oscillators sharing VDD (999 900 MOSFETs, %d unknowns), .TRAN 40 ps" % w["n_unknowns"],
+            "rc": r["rc"], "accepted_steps": s["accepted"], "rejected_steps": s["attempts"] - s["accepted"],
+            "newton_iters": s["newton_iters"], "wall_s": dt, "ms_per_newton_iter": 1e3 * dt / max(s["newton_iters"], 1),
+            "newton_iters_per_s": s["newton_iters"] / dt, "lu_analyses_in_timed_run": s["lu_analyses"],
+            "setup_s": t_setup, "first_call_s_incl_host_lu_analysis": t_first}
+
+
 def run_ours(args):
     import torch
     from xyce_b200 import workloads as wl
@@ -163,7 +192,6 @@ def run_ours(args):
     d_sta = [torch.zeros(w["n_state"], **f64) for _ in range(2)]
     ss = SolverState(transientFlag=1, newtonIter=1)
     flush = torch.empty(256 * 1024 * 1024 // 8, **f64)      # 256 MiB > 126 MB L2
-    settle_cycles = int(os.environ.get("XYCE_B200_SETTLE_CYCLES", "200000"))   # ~100 us at 1.9 GHz
 
     ctxbuf = [eng.device_buffer(i) for i in range(11)]
 
@@ -196,7 +224,6 @@ def run_ours(args):
         if os.environ.get("XYCE_B200_BENCH_SYNC"):
             torch.cuda.synchronize()
         flush.fill_(0.0)                   # evict L2 between timed iterations (not timed)
-        torch.cuda._sleep(settle_cycles)   # let the write-back of the flush buffer drain (not timed)
         ev[k][0].record(stream)
         step()
         ev[k][1].record(stream)
@@ -248,7 +275,7 @@ def run_ours(args):
     e2e_value = world * n_inst * e2e_steps / (ms_e2e * 1e-3)
     peak, peak_kind = measured_peaks()
     eval_s = ms_eval * 1e-3 / args.steps
-    achieved = BYTES_PER_EVAL * n_inst / eval_s / 1e9
+    achieved = BYTES_PER_EVAL_KERNEL * n_inst / eval_s / 1e9
     fp64_peak = eng.measure_fp64_peak()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -257,18 +284,24 @@ def run_ours(args):
                                    "loadDAEMatrices at a fixed operating point (BASELINE config 2)",
                        "instances_per_gpu": n_inst, "unknowns_per_gpu": n, "nnz_per_gpu": nnz,
                        "parallelism": "instances partitioned per rank, no data-path collective",
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush), then ~100 us idle so its "
-                             "write-back does not overlap the timed step"},
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                     "d2h_bytes_per_step": 8 * (4 * n + 2 * nnz)},
             "gpu_launches": launches, "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_kind, "kernel": "b4_eval_kernel<default topology, 128 regs, FMA + reciprocal division>",
-                         "kernel_ms": 1e3 * eval_s,
+                         "traffic": EVAL_KERNEL_DRAM_BYTES, "peak_source": peak_kind,
+                         "kernel": "b4_eval_uniform_kernel<default topology, 128 threads x 3 blocks/SM (168 regs), FMA + constant-bank exp/log/div>",
+                         "kernel_ms": 1e3 * eval_s, "algorithmic_bytes_per_eval": BYTES_PER_EVAL_KERNEL,
+                         "note": "the kernel is bound by instruction delivery, not by HBM or the FP64 pipe (DESIGN.md section 3)",
                          "fp64": {"achieved_tflops": FLOPS_PER_EVAL * n_inst / eval_s / 1e12,
                                   "measured_peak_tflops": fp64_peak,
                                   "frac": FLOPS_PER_EVAL * n_inst / eval_s / 1e12 / fp64_peak}},
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}
+    if world == 1 and not args.no_tran:
+        try:
+            line["tran_c3"] = tran_extra(local)
+        except Exception as exc:
+            line["tran_c3"] = {"error": str(exc)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             rate, reps = cpu_reference_rate(2000, 12.0)
@@ -290,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inverters", type=int, default=50000, help="inverters per GPU (2 BSIM4 instances each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tran", action="store_true", help="skip the 1M-MOSFET .TRAN extra (BASELINE config 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,7 +41,7 @@ def test_ring_oscillator_tran_matches_reference_flow(n_rings, stages, tstop):
     tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
     assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
     # it really oscillates
-    if stages <= 31:          # short rings complete several periods inside tstop
-        v = want["wave"][:, 0]
-        assert v.max() > 0.9 and v.min() < 0.1
+    if stages <= 31:          # the switching front passes at least one of the probed ring nodes inside tstop
+        swing = [want["wave"][:, p].max() - want["wave"][:, p].min() for p in range(3)]
+        assert max(swing) > 0.8
     assert got["stats"]["lu_analyses"] >= 1 and got["stats"]["lu_refactors"] > 0

@@ -209,6 +209,7 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   XS_CUDA(cudaSetDevice(ctx->device));
   GpuBackend B;
   B.ctx = ctx; B.s = ctx->stream; B.n_ = ctx->n;
+  B.lu_analyzed = ctx->lu_ready;      // a plan from an earlier run is reused (refactor; re-analysed on a bad pivot)
   const size_t n = (size_t)ctx->n;
   B.v.assign(sim::kNumVec, nullptr);
   double *pool = nullptr;
