@@ -115,6 +115,12 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
 int xgpu_load_vectors(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_dFdxdVp, double *d_dQdxdVp,
                       int accumulate);
 int xgpu_load_matrices(xgpu_ctx *ctx, double *d_dFdx, double *d_dQdx, int accumulate);
+/* The three calls above in one: updateState, then loadDAEVectors and loadDAEMatrices assembled by the same three
+ * launches (what NonlinearEquationLoader::loadRHS + loadJacobian ask for when both are wanted at one iterate,
+ * src/LoaderServicesPKG/N_LOA_NonlinearEquationLoader.C:374-558).  Identical sums in identical order. */
+int xgpu_load_dae(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, double *d_curr_sta, double *d_next_sto,
+                  double *d_curr_sto, const xgpu_solver_state *ss, double *d_f, double *d_q, double *d_dFdxdVp,
+                  double *d_dQdxdVp, double *d_dFdx, double *d_dQdx, int accumulate);
 int xgpu_all_converged(xgpu_ctx *ctx, int *converged);
 /* J = qscalar*dQdx + fscalar*dFdx  <- Matrix::linearCombo as used by OneStep::obtainJacobian
  * (N_LAS_EpetraMatrix.C:629-648, N_TIA_OneStep.C:490-495). */

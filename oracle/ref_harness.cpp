@@ -665,6 +665,19 @@ struct RefBackend {
     for (auto &r : c->insts) all = all && r.inst->isConverged();
     return all;
   }
+  void residual_and_norms(double inv_h, double fs, bool order2, bool limiter, double qlim_coef, xb::sim::NewtonNorms &out) {
+    using namespace xb::sim;
+    axpby(vRHS, 1.0, vQ, -1.0, vQh0);
+    axpby(vTmp, fs, vF, -fs, vB);
+    axpby(vRHS, inv_h, vRHS, 1.0, vTmp);
+    if (order2) axpy(vRHS, 0.5, vQh2);
+    scale(vRHS, -1.0);
+    if (limiter) { axpy(vRHS, qlim_coef, vQlim); axpy(vRHS, fs, vFlim); }
+    out.rhs_norm2 = norm2(vRHS);
+    out.rhs_norm_inf = norm_inf(vRHS);
+    out.dx_wmax = wmax_norm(vDX, vSolWt);
+    out.devices_converged = all_devices_converged();
+  }
   bool limiter_active() const { return c->devOptions.voltageLimiterFlag; }
   void accept_state() { c->currSta = c->nextSta; c->currSto = c->nextSto; }
   void record(double t) { times.push_back(t); for (int p : probes) wave.push_back(v[xb::sim::vNextSol][p]); }

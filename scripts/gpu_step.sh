@@ -1,17 +1,10 @@
 mkdir -p gpurun_out
-export XYCE_B200_B4_THREADS=128 XYCE_B200_B4_MINBLOCKS=3
-ncu --set full --clock-control none --import-source on -k regex:b4_eval -s 3 -c 1 -o gpurun_out/prof_b4_v2_100k python scripts/prof_one.py 50000 > gpurun_out/p7.log 2>&1
-export XYCE_B200_B4_MINBLOCKS=2
-ncu --set full --clock-control none --import-source on -k regex:b4_eval -s 3 -c 1 -o /tmp/prof_b4_v2_1m python scripts/prof_one.py 500000 > gpurun_out/p8.log 2>&1
-unset XYCE_B200_B4_THREADS XYCE_B200_B4_MINBLOCKS
-(echo "== 100k instances, 128 x 3"; python scripts/ncu_summarize.py gpurun_out/prof_b4_v2_100k.ncu-rep; echo "== 1M instances, 128 x 2"; python scripts/ncu_summarize.py /tmp/prof_b4_v2_1m.ncu-rep) > gpurun_out/prof_v2_summary.txt 2>&1
-for f in gpurun_out/prof_b4_v2_100k.ncu-rep /tmp/prof_b4_v2_1m.ncu-rep; do ncu -i $f --page raw --csv 2>/dev/null | python -c "
-import csv,sys
-rows=list(csv.reader(sys.stdin)); h=rows[0]; u=rows[1]; v=rows[2]
-keys=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','launch__registers_per_thread','sm__warps_active.avg.per_cycle_active','smsp__inst_executed.sum','sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.per_cycle_active','l1tex__t_sector_hit_rate.pct','lts__t_sector_hit_rate.pct','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','sm__throughput.avg.pct_of_peak_sustained_elapsed','launch__grid_size','launch__block_size','smsp__sass_inst_executed_op_local_ld.sum','smsp__sass_inst_executed_op_local_st.sum']
-for i,k in enumerate(h):
-    if k in keys: print(k,u[i],v[i])
-print()
-"; done >> gpurun_out/prof_v2_summary.txt
-ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 80 --csv --log-file gpurun_out/launches_v2.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-tran > gpurun_out/b_ncu_v2.log 2>&1
-cat gpurun_out/prof_v2_summary.txt
+python -m pytest tests -x -q -m gpu 2>&1 | grep -v Netlist | tail -4
+python scripts/tran_bench.py 2>&1 | grep -v Netlist | python -c "
+import sys, json
+for l in sys.stdin:
+    try: r = json.loads(l)
+    except Exception: continue
+    print(r['impl'][:20], r['mosfets'], 'iters', r['newton_iters'], 'ms/iter %.3f' % r['ms_per_newton_iter'], 'wall %.3f' % r['wall_s'], 'launches', r.get('launches'))
+"
+XYCE_B200_BENCH_VERBOSE=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_d.json 2> gpurun_out/bench_d.err; grep "ms:" gpurun_out/bench_d.err | cut -c1-200; tail -c 1500 gpurun_out/bench_d.json

@@ -218,6 +218,12 @@ class Engine:
         p = C.c_void_p
         self._chk(self.lib.xgpu_load_matrices(self.h, p(d_dfdx), p(d_dqdx), int(accumulate)))
 
+    def load_dae(self, d_sol, d_next_sta, d_curr_sta, d_next_sto, d_curr_sto, ss, d_f, d_q, d_fl, d_ql, d_dfdx, d_dqdx,
+                 accumulate=False):
+        p = C.c_void_p
+        self._chk(self.lib.xgpu_load_dae(self.h, p(d_sol), p(d_next_sta), p(d_curr_sta), p(d_next_sto), p(d_curr_sto),
+                                         C.byref(ss), p(d_f), p(d_q), p(d_fl), p(d_ql), p(d_dfdx), p(d_dqdx), int(accumulate)))
+
     def jacobian_combine(self, qs, d_dqdx, fs, d_dfdx, d_jac):
         p = C.c_void_p
         self._chk(self.lib.xgpu_jacobian_combine(self.h, qs, p(d_dqdx), fs, p(d_dfdx), p(d_jac)))

@@ -86,6 +86,94 @@ __global__ void __launch_bounds__(256) gather_long_finish_kernel(GatherMapDev m,
   if (threadIdx.x < NP) ps.out[threadIdx.x][d] = (accumulate ? ps.out[threadIdx.x][d] : 0.0) + sh[threadIdx.x][0];
 }
 
+// ---- fused vector + matrix assembly: the same three stages, one launch each for both maps ----
+// (threads / blocks beyond the vector map's range work on the matrix map)
+template <int NP>
+__device__ __forceinline__ void short_body(const GatherMapDev &m, const PlaneSet &ps, int d, bool accumulate) {
+  const int64_t b = m.ptr[d], e = m.ptr[d + 1];
+  if (e - b > kLongThreshold) return;
+  double acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = accumulate ? ps.out[p][d] : 0.0;
+  for (int64_t k = b; k < e; ++k) {
+    const int32_t s = __ldg(m.src + k);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) ps.out[p][d] = acc[p];
+}
+
+template <int NP>
+__device__ __forceinline__ void chunk_body(const GatherMapDev &m, const PlaneSet &ps, int c, double (*sh)[256]) {
+  const int d = m.long_dst[m.chunk_dst_slot[c]];
+  const int64_t b = m.chunk_begin[c];
+  const int64_t e = min(b + (int64_t)kChunk, m.ptr[d + 1]);
+  double acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
+  for (int64_t k = b + threadIdx.x; k < e; k += 256) {
+    const int32_t s = __ldg(m.src + k);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] += sh[p][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < NP) m.partials[(size_t)threadIdx.x * m.nchunks + c] = sh[threadIdx.x][0];
+}
+
+template <int NP>
+__device__ __forceinline__ void finish_body(const GatherMapDev &m, const PlaneSet &ps, int j, bool accumulate, double (*sh)[256]) {
+  const int d = m.long_dst[j];
+  double acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
+  for (int c = m.long_chunk_ptr[j] + threadIdx.x; c < m.long_chunk_ptr[j + 1]; c += 256) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] += m.partials[(size_t)p * m.nchunks + c];
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] += sh[p][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < NP) ps.out[threadIdx.x][d] = (accumulate ? ps.out[threadIdx.x][d] : 0.0) + sh[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(256) fused_short_kernel(GatherMapDev mv, PlaneSet pv, GatherMapDev mm, PlaneSet pm,
+                                                          int vec_blocks, bool accumulate) {
+  if ((int)blockIdx.x < vec_blocks) {
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d < mv.ndst) short_body<4>(mv, pv, d, accumulate);
+  } else {
+    const int d = (blockIdx.x - vec_blocks) * 256 + threadIdx.x;
+    if (d < mm.ndst) short_body<2>(mm, pm, d, accumulate);
+  }
+}
+__global__ void __launch_bounds__(256) fused_chunk_kernel(GatherMapDev mv, PlaneSet pv, GatherMapDev mm, PlaneSet pm) {
+  __shared__ double sh[4][256];
+  if ((int)blockIdx.x < mv.nchunks) chunk_body<4>(mv, pv, blockIdx.x, sh);
+  else chunk_body<2>(mm, pm, blockIdx.x - mv.nchunks, sh);
+}
+__global__ void __launch_bounds__(256) fused_finish_kernel(GatherMapDev mv, PlaneSet pv, GatherMapDev mm, PlaneSet pm, bool accumulate) {
+  __shared__ double sh[4][256];
+  if ((int)blockIdx.x < mv.nlong) finish_body<4>(mv, pv, blockIdx.x, accumulate, sh);
+  else finish_body<2>(mm, pm, blockIdx.x - mv.nlong, accumulate, sh);
+}
+
 __global__ void __launch_bounds__(256) linear_combo_kernel(int64_t nnz, double a, const double *__restrict__ A,
                                                            double b, const double *__restrict__ B,
                                                            double *__restrict__ J) {
@@ -123,6 +211,22 @@ void launch_gather(const GatherMapDev &m, int nplanes, const double *const *plan
     case 4: launch_np<4>(m, ps, accumulate, stream); break;
     default: break;
   }
+}
+
+int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, double *const *vdst, const GatherMapDev &mm,
+                        const double *const *mplanes, double *const *mdst, bool accumulate, cudaStream_t stream) {
+  PlaneSet pv{}, pm{};
+  for (int p = 0; p < 4; ++p) { pv.in[p] = vplanes[p]; pv.out[p] = vdst[p]; }
+  for (int p = 0; p < 2; ++p) { pm.in[p] = mplanes[p]; pm.out[p] = mdst[p]; }
+  int launches = 0;
+  const int vb = (mv.ndst + 255) / 256, mb = (mm.ndst + 255) / 256;
+  if (vb + mb > 0) { fused_short_kernel<<<vb + mb, 256, 0, stream>>>(mv, pv, mm, pm, vb, accumulate); ++launches; }
+  if (mv.nchunks + mm.nchunks > 0) {
+    fused_chunk_kernel<<<mv.nchunks + mm.nchunks, 256, 0, stream>>>(mv, pv, mm, pm);
+    fused_finish_kernel<<<mv.nlong + mm.nlong, 256, 0, stream>>>(mv, pv, mm, pm, accumulate);
+    launches += 2;
+  }
+  return launches;
 }
 
 cudaError_t measure_fp64_peak(cudaStream_t stream, double *tflops) {

@@ -48,6 +48,11 @@ constexpr int kChunk = 1024;
 void launch_gather(const GatherMapDev &m, int nplanes, const double *const *planes, int64_t plane_stride,
                    double *const *dst, bool accumulate, cudaStream_t stream);
 
+// Vector planes (4, map mv) and matrix planes (2, map mm) in the same three launches.  Same sums in the same
+// order as two launch_gather calls; returns the number of kernel launches.
+int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, double *const *vdst, const GatherMapDev &mm,
+                        const double *const *mplanes, double *const *mdst, bool accumulate, cudaStream_t stream);
+
 // J = qscalar * dQdx + fscalar * dFdx over one CSR pattern (N_LAS_EpetraMatrix.C:629-648 linearCombo
 // as used by OneStep::obtainJacobian, N_TIA_OneStep.C:490-495).
 void launch_linear_combo(int64_t nnz, double a, const double *A, double b, const double *B, double *J,

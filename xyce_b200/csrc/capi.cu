@@ -537,6 +537,21 @@ int xgpu_load_matrices(xgpu_ctx *ctx, double *d_dFdx, double *d_dQdx, int accumu
   return 0;
 }
 
+int xgpu_load_dae(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, double *d_curr_sta, double *d_next_sto,
+                  double *d_curr_sto, const xgpu_solver_state *ss, double *d_f, double *d_q, double *d_fl, double *d_ql,
+                  double *d_dFdx, double *d_dQdx, int accumulate) {
+  if (!ctx || !d_f || !d_q || !d_fl || !d_ql || !d_dFdx || !d_dQdx) return 1;
+  const int rc = xgpu_update_state(ctx, d_sol, d_next_sta, d_curr_sta, d_next_sto, d_curr_sto, ss);
+  if (rc) return rc;
+  const double *vin[4], *min_[2];
+  double *vout[4] = {d_f, d_q, d_fl, d_ql}, *mout[2] = {d_dFdx, d_dQdx};
+  for (int p = 0; p < 4; ++p) vin[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
+  for (int p = 0; p < 2; ++p) min_[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
+  ctx->launches += launch_gather_fused(ctx->vec_map, vin, vout, ctx->mat_map, min_, mout, accumulate != 0, ctx->stream);
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int xgpu_jacobian_combine(xgpu_ctx *ctx, double qs, const double *d_dQdx, double fs, const double *d_dFdx, double *d_jac) {
   if (!ctx || !d_dQdx || !d_dFdx || !d_jac) return 1;
   launch_linear_combo(ctx->nnz, qs, d_dQdx, fs, d_dFdx, d_jac, ctx->stream);
@@ -591,10 +606,8 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
   if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
   double **b = ctx->buf;
   XG_CUDA(cudaMemcpyAsync(b[0], h_sol, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = xgpu_update_state(ctx, b[0], b[9], b[10], b[7], b[8], ss);
+  const int rc = xgpu_load_dae(ctx, b[0], b[9], b[10], b[7], b[8], ss, b[1], b[2], b[3], b[4], b[5], b[6], 0);
   if (rc) return rc;
-  if ((rc = xgpu_load_vectors(ctx, b[1], b[2], b[3], b[4], 0))) return rc;
-  if ((rc = xgpu_load_matrices(ctx, b[5], b[6], 0))) return rc;
   double *hv[4] = {h_f, h_q, h_fl, h_ql};
   for (int p = 0; p < 4; ++p)
     if (hv[p]) XG_CUDA(cudaMemcpyAsync(hv[p], b[1 + p], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -45,6 +45,11 @@ __global__ void set_sources_kernel(double *b, const int *rows, const double *val
   // one thread: sources may share a row; order is the source order (deterministic)
   if (blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < ns; ++k) b[rows[k]] += vals[k];
 }
+// up to 24 source values travel in the kernel parameter block: no staging copy, no host synchronisation
+struct SrcVals { int n; int rows[24]; double vals[24]; };
+__global__ void set_sources_byval_kernel(double *b, SrcVals sv) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < sv.n; ++k) b[sv.rows[k]] += sv.vals[k];
+}
 
 using xb::sim::pulse_value;
 
@@ -90,7 +95,14 @@ struct GpuBackend {
     // independent sources evaluated on the host (DeviceMgr::updateSources), B assembled on the device
     vec::fill(v[sim::vB], 0.0, n_, s); ++ctx->launches;
     const int ns = (int)ctx->sources.size();
-    if (ns > 0) {
+    if (ns > 0 && ns <= 24) {
+      SrcVals sv; sv.n = ns;
+      for (int k = 0; k < ns; ++k) {
+        const XgSource &q = ctx->sources[k];
+        sv.rows[k] = q.row; sv.vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time);
+      }
+      set_sources_byval_kernel<<<1, 32, 0, s>>>(v[sim::vB], sv); ++ctx->launches;
+    } else if (ns > 0) {
       std::vector<double> vals(ns);
       for (int k = 0; k < ns; ++k) {
         const XgSource &q = ctx->sources[k];
@@ -133,6 +145,23 @@ struct GpuBackend {
     cudaStreamSynchronize(s);
     return r != 0;
   }
+  void residual_and_norms(double inv_h, double fs, bool order2, bool limiter, double qlim_coef, sim::NewtonNorms &out) {
+    vec::ResidualArgs a{};
+    a.rhs = v[sim::vRHS]; a.q = v[sim::vQ]; a.qh0 = v[sim::vQh0]; a.f = v[sim::vF]; a.b = v[sim::vB]; a.qh2 = v[sim::vQh2];
+    a.qlim = v[sim::vQlim]; a.flim = v[sim::vFlim]; a.dx = v[sim::vDX]; a.w = v[sim::vSolWt];
+    a.inv_h = inv_h; a.fs = fs; a.qlim_coef = qlim_coef; a.order2 = order2; a.limiter = limiter; a.n = n_;
+    a.nflag_arrays = 0;
+    bool overflow = false;
+    for (auto &g : ctx->groups) { if (a.nflag_arrays < 8) { a.flags[a.nflag_arrays] = g.d_orig; a.flag_n[a.nflag_arrays++] = g.n; } else overflow = true; }
+    for (auto &g : ctx->sgroups) { if (a.nflag_arrays < 8) { a.flags[a.nflag_arrays] = g.d_orig; a.flag_n[a.nflag_arrays++] = g.n; } else overflow = true; }
+    vec::residual_norms(a, scratch, scratch + 4 * 1024, s); ctx->launches += 2;
+    cudaMemcpyAsync(h_norms, scratch + 4 * 1024, 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    out.rhs_norm2 = std::sqrt(h_norms[0]); out.rhs_norm_inf = h_norms[1]; out.dx_wmax = h_norms[2];
+    out.devices_converged = h_norms[3] != 0.0;
+    if (overflow) out.devices_converged = all_devices_converged();     // more than 8 device groups: separate pass
+  }
+  double *h_norms = nullptr;          // pinned
   bool limiter_active() const { return ss.voltageLimiterFlag != 0; }
   void accept_state() {
     cudaMemcpyAsync(sta[1], sta[0], (size_t)ctx->n_state * sizeof(double), cudaMemcpyDeviceToDevice, s);
@@ -213,8 +242,8 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   const size_t n = (size_t)ctx->n;
   B.v.assign(sim::kNumVec, nullptr);
   double *pool = nullptr;
-  XS_CUDA(cudaMalloc((void **)&pool, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 2048) * sizeof(double)));
-  XS_CUDA(cudaMemsetAsync(pool, 0, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 2048) * sizeof(double), ctx->stream));
+  XS_CUDA(cudaMalloc((void **)&pool, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 8192) * sizeof(double)));
+  XS_CUDA(cudaMemsetAsync(pool, 0, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 8192) * sizeof(double), ctx->stream));
   for (int i = 0; i < sim::kNumVec; ++i) B.v[i] = pool + i * n;
   B.dFdx = pool + sim::kNumVec * n; B.dQdx = B.dFdx + ctx->nnz; B.J = B.dQdx + ctx->nnz; B.scratch = B.J + ctx->nnz;
   B.sto[0] = ctx->buf[7]; B.sto[1] = ctx->buf[8]; B.sta[0] = ctx->buf[9]; B.sta[1] = ctx->buf[10];
@@ -224,6 +253,7 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   B.probes.assign(probes, probes + n_probes);
   XS_CUDA(up(&B.d_probe, B.probes));
   XS_CUDA(cudaMalloc((void **)&B.d_probe_out, (n_probes + 1) * sizeof(double)));
+  XS_CUDA(cudaMallocHost((void **)&B.h_norms, 8 * sizeof(double)));
   std::memset(&B.ss, 0, sizeof(B.ss));
   B.ss.voltageLimiterFlag = 1; B.ss.gmin = 1e-12; B.ss.gainScale = 1.0; B.ss.nltermScale = 1.0;
   B.ss.vgstConst = 4.5; B.ss.vdsScaleMin = 0.3; B.ss.sizeScale = 1.0; B.ss.transientFlag = 1;
@@ -267,6 +297,7 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
                            (double)nt, (double)nsr, (double)rc, 0, 0, 0, 0, 0};
     std::memcpy(stats16, st, sizeof(st));
   }
+  cudaFreeHost(B.h_norms);
   cudaFree(pool); cudaFree(B.d_src_rows); cudaFree(B.d_src_vals); cudaFree(B.d_probe); cudaFree(B.d_probe_out);
   if (rc != 0) return xg_fail(ctx, 200 + rc, rc == 2 ? "transient: time step too small / too many failures" : "transient: step limit reached");
   return 0;

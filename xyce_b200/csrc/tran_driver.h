@@ -80,9 +80,16 @@ struct TranStats {
 //   bool load_rhs(const Flags&, double time);    evaluates devices at vNextSol: fills vF, vQ, vB, vFlim, vQlim
 //   void load_jacobian(double qscalar, double fscalar);               J = qscalar dQdx + fscalar dFdx
 //   int  solve();                                                      J vDX = vRHS   (0 ok)
-//   bool all_devices_converged(); bool limiter_active();
+//   void residual_and_norms(double inv_h, double fs, bool order2, bool limiter, double qlim_coef, NewtonNorms &out);
+//        vRHS = -[(vQ - vQh0) inv_h + fs (vF - vB) (+ 1/2 vQh2)] (+ qlim_coef vQlim + fs vFlim), element by element in
+//        exactly the operation order of the axpby sequence it replaces; then ||RHS||_2, ||RHS||_inf,
+//        max |vDX / vSolWt| and the AND of the devices' convergence flags
+//   bool limiter_active();
 //   void accept_state();                                               curr state/store <- next
 //   void record(double t);                                             sample probes
+// everything DampedNewton::converged_ looks at after one residual evaluation, fetched in one go
+struct NewtonNorms { double rhs_norm2 = 0, rhs_norm_inf = 0, dx_wmax = 0; bool devices_converged = true; };
+
 struct Flags {
   int dcop = 0, tranop = 0, transient = 1, initTran = 0, newtonIter = 0, initJct = 0;
   double currTimeStep = 0;
@@ -224,19 +231,11 @@ class TransientDriver {
   // residual of OneStep::obtainResidual: RHS = -[(Q - q0)/h + f (F - B) (+ 1/2 qHistory[2])] + limiter terms
   double residual(const Flags &fl) {
     B.load_rhs(fl, nextTime); ++stats.residual_loads;
-    B.axpby(vRHS, 1.0, vQ, -1.0, vQh0);
-    const double inv_h = 1.0 / currentTimeStep;
     const double fs = (currentOrder == 2) ? 0.5 : 1.0;
-    B.axpby(vTmp, fs, vF, -fs, vB);
-    B.axpby(vRHS, inv_h, vRHS, 1.0, vTmp);
-    if (currentOrder == 2) B.axpy(vRHS, 0.5, vQh2);
-    B.scale(vRHS, -1.0);
-    if (B.limiter_active()) {
-      B.axpy(vRHS, -alphas / currentTimeStep, vQlim);
-      B.axpy(vRHS, fs, vFlim);
-    }
-    return B.norm2(vRHS);
+    B.residual_and_norms(1.0 / currentTimeStep, fs, currentOrder == 2, B.limiter_active(), -alphas / currentTimeStep, nn);
+    return nn.rhs_norm2;
   }
+  NewtonNorms nn;
 
   int newton_solve() {            // DampedNewton::solve with FULL search (step length 1)
     Flags fl; fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep;
@@ -258,13 +257,13 @@ class TransientDriver {
       // ---- converged_ ----
       if (lin != 0) { status = -9; break; }
       if (P.enforceDeviceConv) {
-        const bool conv = B.all_devices_converged();
+        const bool conv = nn.devices_converged;
         if (!conv && nlStep < P.maxNewtonStep) continue;
         if (!conv && nlStep >= P.maxNewtonStep) { status = -1; break; }
       }
       if (!(normRHS == normRHS)) { status = -6; break; }
-      const double maxNormRHS = B.norm_inf(vRHS);
-      const double wtNormDX = B.wmax_norm(vDX, vSolWt);
+      const double maxNormRHS = nn.rhs_norm_inf;
+      const double wtNormDX = nn.dx_wmax;
       if (normRHS < 2.220446049250313e-16) { status = 1; break; }     // normTooSmall
       const double normRHS_rel = normRHS / normRHS_init;
       const double resConvRate = normRHS / normRHS_old;

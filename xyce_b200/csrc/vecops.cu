@@ -64,6 +64,66 @@ double reduce_t(const double *x, const double *w, int n, double *scratch, cudaSt
   cudaStreamSynchronize(s);
   return h;
 }
+constexpr int kResBlocks = 1024;
+__global__ void __launch_bounds__(256) residual_norms_k(ResidualArgs a, double *part) {
+  __shared__ double sh[3][256];
+  __shared__ int shf;
+  if (threadIdx.x == 0) shf = 1;
+  __syncthreads();
+  double s2 = 0.0, mx = 0.0, wm = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < a.n; i += gridDim.x * 256) {
+    double r = 1.0 * a.q[i] + -1.0 * a.qh0[i];
+    const double t = a.fs * a.f[i] + (-a.fs) * a.b[i];
+    r = a.inv_h * r + 1.0 * t;
+    if (a.order2) r = 1.0 * r + 0.5 * a.qh2[i];
+    r = -1.0 * r + 0.0 * r;
+    if (a.limiter) { r = 1.0 * r + a.qlim_coef * a.qlim[i]; r = 1.0 * r + a.fs * a.flim[i]; }
+    a.rhs[i] = r;
+    s2 = comb<kSumSq>(s2, r * r);
+    mx = comb<kMaxAbs>(mx, fabs(r));
+    wm = comb<kWMaxAbs>(wm, fabs(a.dx[i] / a.w[i]));
+  }
+  int ok = 1;
+  for (int k = 0; k < a.nflag_arrays; ++k)
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < a.flag_n[k]; i += gridDim.x * 256) if (a.flags[k][i] == 0) ok = 0;
+  if (!ok) shf = 0;        // every writer stores the same value
+  sh[0][threadIdx.x] = s2; sh[1][threadIdx.x] = mx; sh[2][threadIdx.x] = wm;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] = comb<kSumSq>(sh[0][threadIdx.x], sh[0][threadIdx.x + s]);
+      sh[1][threadIdx.x] = comb<kMaxAbs>(sh[1][threadIdx.x], sh[1][threadIdx.x + s]);
+      sh[2][threadIdx.x] = comb<kWMaxAbs>(sh[2][threadIdx.x], sh[2][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = sh[0][0]; part[kResBlocks + blockIdx.x] = sh[1][0]; part[2 * kResBlocks + blockIdx.x] = sh[2][0];
+    part[3 * kResBlocks + blockIdx.x] = (double)shf;
+  }
+}
+__global__ void __launch_bounds__(256) residual_norms_final_k(const double *part, int m, double *out4) {
+  __shared__ double sh[4][256];
+  double s2 = 0.0, mx = 0.0, wm = 0.0, ok = 1.0;
+  for (int i = threadIdx.x; i < m; i += 256) {
+    s2 = comb<kSumSq>(s2, part[i]);
+    mx = comb<kMaxAbs>(mx, part[kResBlocks + i]);
+    wm = comb<kWMaxAbs>(wm, part[2 * kResBlocks + i]);
+    ok = fmin(ok, part[3 * kResBlocks + i]);
+  }
+  sh[0][threadIdx.x] = s2; sh[1][threadIdx.x] = mx; sh[2][threadIdx.x] = wm; sh[3][threadIdx.x] = ok;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] = comb<kSumSq>(sh[0][threadIdx.x], sh[0][threadIdx.x + s]);
+      sh[1][threadIdx.x] = comb<kMaxAbs>(sh[1][threadIdx.x], sh[1][threadIdx.x + s]);
+      sh[2][threadIdx.x] = comb<kWMaxAbs>(sh[2][threadIdx.x], sh[2][threadIdx.x + s]);
+      sh[3][threadIdx.x] = fmin(sh[3][threadIdx.x], sh[3][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) out4[threadIdx.x] = sh[threadIdx.x][0];
+}
 __global__ void spmv_add_k(int nrows, const int *rows, const int *ptr, const int *col, const double *val,
                            const double *x, double *y) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,6 +156,14 @@ double reduce(Reduce mode, const double *x, const double *w, int n, double *scra
     case kWMaxAbs: return reduce_t<kWMaxAbs>(x, w, n, scratch, s);
     default: return reduce_t<kWSumSq>(x, w, n, scratch, s);
   }
+}
+void residual_norms(const ResidualArgs &a, double *scratch, double *out4, cudaStream_t s) {
+  int work = a.n;
+  for (int k = 0; k < a.nflag_arrays; ++k) work = work > a.flag_n[k] ? work : a.flag_n[k];
+  int blocks = work < 256 * kResBlocks ? (work + 255) / 256 : kResBlocks;
+  if (blocks < 1) blocks = 1;
+  residual_norms_k<<<blocks, 256, 0, s>>>(a, scratch);
+  residual_norms_final_k<<<1, 256, 0, s>>>(scratch, blocks, out4);
 }
 void spmv_add(int nrows, const int *rows, const int *ptr, const int *col, const double *val, const double *x,
               double *y, cudaStream_t s) {
