@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuDev d,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerCta + warp;
   if (b >= d.nblocks) return;
+  if (d.block_big[b]) return;                  // large blocks: column-level schedule (lu_big_* kernels)
   const int k0 = d.block_ptr[b], k1 = d.block_ptr[b + 1];
   const int nb = k1 - k0;
   if (nb == 1) {                               // 1x1 block: the pivot is the matrix entry itself
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev
   const int idx = blockIdx.x * kWarpsPerCta + warp;
   if (idx >= count) return;
   const int b = d.level_blocks[first + idx];
+  if (d.block_big[b]) return;                  // large blocks: row-level schedule
   const int k0 = d.block_ptr[b], k1 = d.block_ptr[b + 1];
   double *y = d.work;
   // forward substitution with unit-lower L
@@ -144,6 +146,113 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev
     if (lane == 0) { y[k] = yk; xout[d.col_perm[k]] = yk; }
     for (int q = d.Up[k] + lane; q < ue; q += 32) y[d.Ui[q]] -= d.Ux[q] * yk;
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Large diagonal blocks.  Refactor: one warp per column, columns of one dependency level per launch;
+// the column is built in place in the factor arrays (row -> slot by binary search in the fixed pattern).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_dev(const int *a, int lo, int hi, int key) {
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) lu_big_cols_kernel(LuDev d, const double *__restrict__ A, int first, int count) {
+  const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const int k = d.rf_cols[first + w];
+  const int ub = d.Up[k], ue = d.Up[k + 1] - 1, lb = d.Lp[k], le = d.Lp[k + 1];
+  for (int q = ub + lane; q <= ue; q += 32) d.Ux[q] = 0.0;
+  for (int q = lb + lane; q < le; q += 32) d.Lx[q] = 0.0;
+  __syncwarp();
+  for (int q = d.acol_ptr[k] + lane; q < d.acol_ptr[k + 1]; q += 32) {
+    const int dst = d.acol_dst[q];
+    const double v = A[d.acol_src[q]];
+    if (dst >= 0) d.Ux[dst] = v; else d.Lx[~dst] = v;
+  }
+  __syncwarp();
+  for (int q = ub; q < ue; ++q) {
+    const int i = d.Ui[q];
+    const double u = d.Ux[q];
+    for (int t = d.Lp[i] + lane; t < d.Lp[i + 1]; t += 32) {
+      const int r = d.Li[t];
+      const double val = d.Lx[t] * u;
+      if (r < k) d.Ux[lower_bound_dev(d.Ui, q + 1, ue, r)] -= val;
+      else if (r == k) d.Ux[ue] -= val;
+      else d.Lx[lower_bound_dev(d.Li, lb, le, r)] -= val;
+    }
+    __syncwarp();
+  }
+  const double pivot = d.Ux[ue];
+  if (lane == 0 && bad_pivot(pivot)) *d.status = 1;
+  for (int q = lb + lane; q < le; q += 32) d.Lx[q] = d.Lx[q] / pivot;
+}
+
+// Dense columns (supply rails): x = L^-1 A(:,k) over the whole block by the forward row stages, then gathered.
+__global__ void __launch_bounds__(256) lu_dense_scatter_kernel(LuDev d, const double *__restrict__ A, int k) {
+  const int q = d.acol_ptr[k] + blockIdx.x * 256 + threadIdx.x;
+  if (q < d.acol_ptr[k + 1]) d.work2[d.acol_row[q]] = A[d.acol_src[q]];
+}
+__global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuDev d, int k) {
+  const int ub = d.Up[k], ue = d.Up[k + 1] - 1, lb = d.Lp[k], le = d.Lp[k + 1];
+  const double pivot = d.work2[k];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t == 0) { d.Ux[ue] = pivot; if (bad_pivot(pivot)) *d.status = 1; }
+  if (t < ue - ub) d.Ux[ub + t] = d.work2[d.Ui[ub + t]];
+  if (t < le - lb) d.Lx[lb + t] = d.work2[d.Li[lb + t]] / pivot;
+}
+
+// One stage of a row-form triangular sweep: vec[r] -= sum_{col < col_limit} L(r, col) vec[col].
+// WARP: one warp per row (lane-strided partial sums, shuffle tree); otherwise one CTA per row (fixed tree).
+template <bool WARP>
+__global__ void __launch_bounds__(256) lu_fwd_rows_kernel(LuDev d, double *vec, const int *__restrict__ rows, int first, int count,
+                                                          int col_limit) {
+  __shared__ double sh[256];
+  const int lane = threadIdx.x & 31;
+  const int idx = WARP ? ((blockIdx.x * 256 + threadIdx.x) >> 5) : blockIdx.x;
+  if (idx >= count) return;
+  const int r = rows[first + idx];
+  double acc = 0.0;
+  const int step = WARP ? 32 : 256, off = WARP ? lane : threadIdx.x;
+  for (int q = d.Lr_ptr[r] + off; q < d.Lr_ptr[r + 1]; q += step) {
+    const int c = d.Lr_col[q];
+    if (c < col_limit) acc += d.Lx[d.Lr_src[q]] * vec[c];
+  }
+  if (WARP) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) vec[r] -= acc;
+  } else {
+    const double t = block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) vec[r] -= t;
+  }
+}
+// backward stage: y[r] = (y[r] - sum U(r, col) y[col]) / U(r, r), solution scattered to the caller's ordering
+template <bool WARP>
+__global__ void __launch_bounds__(256) lu_bwd_rows_kernel(LuDev d, const int *__restrict__ rows, int first, int count,
+                                                          double *__restrict__ xout) {
+  __shared__ double sh[256];
+  const int lane = threadIdx.x & 31;
+  const int idx = WARP ? ((blockIdx.x * 256 + threadIdx.x) >> 5) : blockIdx.x;
+  if (idx >= count) return;
+  const int r = rows[first + idx];
+  double *y = d.work;
+  double acc = 0.0;
+  const int step = WARP ? 32 : 256, off = WARP ? lane : threadIdx.x;
+  for (int q = d.Ur_ptr[r] + off; q < d.Ur_ptr[r + 1]; q += step) acc += d.Ux[d.Ur_src[q]] * y[d.Ur_col[q]];
+  double total;
+  if (WARP) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    total = acc;
+  } else {
+    total = block_tree_sum(acc, sh);
+  }
+  if ((WARP ? lane : (int)threadIdx.x) == 0) {
+    const double yr = (y[r] - total) / d.Ux[d.Up[r + 1] - 1];
+    y[r] = yr;
+    xout[d.col_perm[r]] = yr;
   }
 }
 
@@ -164,6 +273,9 @@ void free_plan(LuDev &d) {
   cudaFree(d.level_blocks); cudaFree(d.work); cudaFree(d.status);
   cudaFree(d.pull_short_rows); cudaFree(d.pull_long_rows); cudaFree(d.pull_chunk_row_slot); cudaFree(d.pull_chunk_begin);
   cudaFree(d.pull_long_chunk_ptr); cudaFree(d.pull_partials);
+  cudaFree(d.work2); cudaFree(d.block_big); cudaFree(d.acol_dst); cudaFree(d.rf_cols); cudaFree(d.Lr_ptr); cudaFree(d.Lr_col);
+  cudaFree(d.Lr_src); cudaFree(d.Ur_ptr); cudaFree(d.Ur_col); cudaFree(d.Ur_src); cudaFree(d.fs_short_rows); cudaFree(d.fs_long_rows);
+  cudaFree(d.bs_short_rows); cudaFree(d.bs_long_rows);
   d = LuDev();
 }
 
@@ -178,7 +290,26 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
   UP(row_perm) UP(col_perm) UP(block_ptr) UP(Lp) UP(Li) UP(Up) UP(Ui) UP(Lx) UP(Ux)
   UP(acol_ptr) UP(acol_row) UP(acol_src) UP(offr_ptr) UP(offr_col) UP(offr_src) UP(level_blocks)
   UP(pull_short_rows) UP(pull_long_rows) UP(pull_chunk_row_slot) UP(pull_chunk_begin) UP(pull_long_chunk_ptr)
+  UP(block_big) UP(acol_dst) UP(rf_cols) UP(Lr_ptr) UP(Lr_col) UP(Lr_src) UP(Ur_ptr) UP(Ur_col) UP(Ur_src)
+  UP(fs_short_rows) UP(fs_long_rows) UP(bs_short_rows) UP(bs_long_rows)
 #undef UP
+  d.rf_level_ptr = p.rf_level_ptr; d.rf_dense_ptr = p.rf_dense_ptr; d.rf_dense_cols = p.rf_dense_cols;
+  d.fs_short_ptr = p.fs_short_ptr; d.fs_long_ptr = p.fs_long_ptr; d.bs_short_ptr = p.bs_short_ptr; d.bs_long_ptr = p.bs_long_ptr;
+  d.big_blocks = p.big_blocks; d.big_fs_begin = p.big_fs_begin; d.big_fs_end = p.big_fs_end;
+  d.big_bs_begin = p.big_bs_begin; d.big_bs_end = p.big_bs_end; d.block_ptr_h = p.block_ptr;
+  {
+    std::vector<int> level_of_block(d.nblocks, 0);
+    for (int l = 0; l < d.nlevels; ++l) for (int q = p.level_ptr[l]; q < p.level_ptr[l + 1]; ++q) level_of_block[p.level_blocks[q]] = l;
+    d.block_level_of_big.clear();
+    for (int b : p.big_blocks) d.block_level_of_big.push_back(level_of_block[b]);
+    d.dense_col_block.clear();
+    for (int k : p.rf_dense_cols) {
+      int bi = 0;
+      while (!(p.block_ptr[p.big_blocks[bi]] <= k && k < p.block_ptr[p.big_blocks[bi] + 1])) ++bi;
+      d.dense_col_block.push_back(bi);
+    }
+  }
+  if ((e = cudaMalloc((void **)&d.work2, (size_t)(p.n > 0 ? p.n : 1) * sizeof(double))) != cudaSuccess) return e;
   d.pull_short_ptr = p.pull_short_ptr; d.pull_long_ptr = p.pull_long_ptr; d.pull_chunk_ptr = p.pull_chunk_ptr;
   if ((e = cudaMalloc((void **)&d.pull_partials, (p.pull_chunk_begin.size() + 1) * sizeof(double))) != cudaSuccess) return e;
   if ((e = cudaMalloc((void **)&d.work, (size_t)(p.n > 0 ? p.n : 1) * sizeof(double))) != cudaSuccess) return e;
@@ -186,11 +317,40 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
   return cudaMemset(d.status, 0, sizeof(int));
 }
 
+namespace {
+// forward row stages [s0, s1) of one large block applied to `vec`
+int run_fwd_stages(const LuDev &d, double *vec, int s0, int s1, int col_limit, cudaStream_t s) {
+  int launches = 0;
+  for (int st = s0; st < s1; ++st) {
+    const int ns = d.fs_short_ptr[st + 1] - d.fs_short_ptr[st], nl = d.fs_long_ptr[st + 1] - d.fs_long_ptr[st];
+    if (ns > 0) { lu_fwd_rows_kernel<true><<<(ns * 32 + 255) / 256, 256, 0, s>>>(d, vec, d.fs_short_rows, d.fs_short_ptr[st], ns, col_limit); ++launches; }
+    if (nl > 0) { lu_fwd_rows_kernel<false><<<nl, 256, 0, s>>>(d, vec, d.fs_long_rows, d.fs_long_ptr[st], nl, col_limit); ++launches; }
+  }
+  return launches;
+}
+}  // namespace
+
 int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
   cudaMemsetAsync(d.status, 0, sizeof(int), s);
   const int ctas = (d.nblocks + kWarpsPerCta - 1) / kWarpsPerCta;
   lu_refactor_kernel<<<ctas, 32 * kWarpsPerCta, 0, s>>>(d, A);
-  return 1;
+  int launches = 1;
+  // large blocks: columns level by level; dense columns of a level after its normal columns
+  const int nlev = (int)d.rf_level_ptr.size() - 1;
+  for (int l = 0; l < nlev; ++l) {
+    const int first = d.rf_level_ptr[l], count = d.rf_level_ptr[l + 1] - first;
+    if (count > 0) { lu_big_cols_kernel<<<(count * 32 + 255) / 256, 256, 0, s>>>(d, A, first, count); ++launches; }
+    for (int q = d.rf_dense_ptr[l]; q < d.rf_dense_ptr[l + 1]; ++q) {
+      const int k = d.rf_dense_cols[q], bi = d.dense_col_block[q], b = d.big_blocks[bi];
+      const int k0 = d.block_ptr_h[b], k1 = d.block_ptr_h[b + 1];
+      cudaMemsetAsync(d.work2 + k0, 0, (size_t)(k1 - k0) * sizeof(double), s);
+      lu_dense_scatter_kernel<<<(k1 - k0 + 255) / 256 + 1, 256, 0, s>>>(d, A, k);      // >= number of A entries in the column
+      launches += 1 + run_fwd_stages(d, d.work2, d.big_fs_begin[bi], d.big_fs_end[bi], k, s);
+      lu_dense_gather_kernel<<<(k1 - k0 + 255) / 256 + 1, 256, 0, s>>>(d, k);
+      ++launches;
+    }
+  }
+  return launches;
 }
 
 int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, cudaStream_t s) {
@@ -209,6 +369,15 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
     }
     lu_solve_level_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, s>>>(d, A, first, count, x);
     ++launches;
+    for (size_t bi = 0; bi < d.big_blocks.size(); ++bi) {
+      if (d.block_level_of_big[bi] != l) continue;
+      launches += run_fwd_stages(d, d.work, d.big_fs_begin[bi], d.big_fs_end[bi], 0x7fffffff, s);
+      for (int st = d.big_bs_begin[bi]; st < d.big_bs_end[bi]; ++st) {
+        const int nsr = d.bs_short_ptr[st + 1] - d.bs_short_ptr[st], nlr = d.bs_long_ptr[st + 1] - d.bs_long_ptr[st];
+        if (nsr > 0) { lu_bwd_rows_kernel<true><<<(nsr * 32 + 255) / 256, 256, 0, s>>>(d, d.bs_short_rows, d.bs_short_ptr[st], nsr, x); ++launches; }
+        if (nlr > 0) { lu_bwd_rows_kernel<false><<<nlr, 256, 0, s>>>(d, d.bs_long_rows, d.bs_long_ptr[st], nlr, x); ++launches; }
+      }
+    }
   }
   return launches;
 }

@@ -37,7 +37,28 @@ struct LuPlan {
   std::vector<int> pull_chunk_ptr, pull_chunk_row_slot, pull_chunk_begin;   // per level: chunks of the long rows
   std::vector<int> pull_long_chunk_ptr;                  // per long row slot: its chunk range
   double refactor_flops = 0.0;
+
+  // ---- large diagonal blocks (more than kBigBlock rows): column-level / row-level schedules ----
+  // A single warp per block (the small-block kernels) would walk such a block column by column; instead
+  //   refactor: columns are grouped by dependency level (column k needs every column i with U(i,k) != 0);
+  //             one warp factors one column in place (values addressed through binary search in the fixed
+  //             pattern), all columns of a level in one launch.  Columns whose U part is longer than
+  //             kDenseCol (supply rails) are computed as a forward substitution over the whole block instead.
+  //   solve:    L and U of the block in row form; rows grouped by level, one warp (or one CTA for rows longer
+  //             than kLongRow) per row.
+  std::vector<int> block_big;                   // [nblocks] 1 = large block
+  std::vector<int> acol_dst;                    // per acol entry of a large-block column: >= 0 index into Ux, < 0 ~index into Lx
+  std::vector<int> rf_level_ptr, rf_cols;       // normal columns of all large blocks by level
+  std::vector<int> rf_dense_ptr, rf_dense_cols; // dense columns by level (processed one at a time after the level's normal columns)
+  std::vector<int> Lr_ptr, Lr_col, Lr_src;      // [n+1] row form of L (rows of large blocks only; others empty), src indexes Lx
+  std::vector<int> Ur_ptr, Ur_col, Ur_src;      // row form of strict U, src indexes Ux
+  // stages: every stage is a set of independent rows; short rows (one warp each) and long rows (one CTA each)
+  std::vector<int> fs_short_ptr, fs_short_rows, fs_long_ptr, fs_long_rows;   // forward (L) stages, all large blocks back to back
+  std::vector<int> bs_short_ptr, bs_short_rows, bs_long_ptr, bs_long_rows;   // backward (U) stages
+  std::vector<int> big_blocks;                  // ids of the large blocks
+  std::vector<int> big_fs_begin, big_fs_end, big_bs_begin, big_bs_end;       // per large block: its stage ranges
 };
+constexpr int kBigBlock = 512, kDenseCol = 4096, kLongRow = 2048;
 
 // Symbolic analysis + first numeric factorization with threshold partial pivoting (KLU defaults:
 // pivot_tol = 0.001, diagonal preferred).  Returns 0 ok, 1 structurally singular, 2 numerically singular.
@@ -60,7 +81,15 @@ struct LuDev {
   std::vector<int> pull_short_ptr, pull_long_ptr, pull_chunk_ptr;   // host copies
   double *pull_partials = nullptr;
   double *work = nullptr;         // [n] dense column / solution work vector
+  double *work2 = nullptr;        // [n] dense-column work vector of the large-block refactor
   int *status = nullptr;          // device flag: != 0 when a zero or non-finite pivot was met
+  // large blocks (see LuPlan)
+  int *block_big = nullptr, *acol_dst = nullptr, *rf_cols = nullptr;
+  int *Lr_ptr = nullptr, *Lr_col = nullptr, *Lr_src = nullptr, *Ur_ptr = nullptr, *Ur_col = nullptr, *Ur_src = nullptr;
+  int *fs_short_rows = nullptr, *fs_long_rows = nullptr, *bs_short_rows = nullptr, *bs_long_rows = nullptr;
+  std::vector<int> rf_level_ptr, rf_dense_ptr, rf_dense_cols, fs_short_ptr, fs_long_ptr, bs_short_ptr, bs_long_ptr;
+  std::vector<int> big_blocks, big_fs_begin, big_fs_end, big_bs_begin, big_bs_end, block_ptr_h, block_level_of_big;
+  std::vector<int> dense_col_block;   // block id of every dense column (parallel to rf_dense_cols)
 };
 
 }  // namespace lu

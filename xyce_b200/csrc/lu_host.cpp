@@ -423,6 +423,96 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
       plan.pull_chunk_ptr.push_back((int)plan.pull_chunk_begin.size());
     }
   }
+  // ---- large blocks: column levels for the refactor, row form + row levels for the solves ----
+  {
+    plan.block_big.assign(nblocks, 0);
+    for (int b = 0; b < nblocks; ++b) if (bptr[b + 1] - bptr[b] > kBigBlock) { plan.block_big[b] = 1; plan.big_blocks.push_back(b); }
+    plan.acol_dst.assign(plan.acol_row.size(), 0);
+    plan.Lr_ptr.assign(n + 1, 0); plan.Ur_ptr.assign(n + 1, 0);
+    std::vector<int> clev(n, 0);
+    int max_clev = -1;
+    std::vector<char> dense(n, 0);
+    for (int b : plan.big_blocks) {
+      for (int k = bptr[b]; k < bptr[b + 1]; ++k) {
+        const int ub = plan.Up[k], ue = plan.Up[k + 1] - 1, lb = plan.Lp[k], le = plan.Lp[k + 1];
+        // destination of every A entry of this column inside the factor arrays
+        for (int q = plan.acol_ptr[k]; q < plan.acol_ptr[k + 1]; ++q) {
+          const int r = plan.acol_row[q];
+          if (r == k) plan.acol_dst[q] = ue;
+          else if (r < k) plan.acol_dst[q] = (int)(std::lower_bound(plan.Ui.begin() + ub, plan.Ui.begin() + ue, r) - plan.Ui.begin());
+          else plan.acol_dst[q] = ~(int)(std::lower_bound(plan.Li.begin() + lb, plan.Li.begin() + le, r) - plan.Li.begin());
+        }
+        int lv = 0;
+        for (int q = ub; q < ue; ++q) lv = std::max(lv, clev[plan.Ui[q]] + 1);
+        clev[k] = lv; max_clev = std::max(max_clev, lv);
+        dense[k] = (ue - ub) > kDenseCol;
+        for (int q = lb; q < le; ++q) ++plan.Lr_ptr[plan.Li[q] + 1];
+        for (int q = ub; q < ue; ++q) ++plan.Ur_ptr[plan.Ui[q] + 1];
+      }
+    }
+    for (int r = 0; r < n; ++r) { plan.Lr_ptr[r + 1] += plan.Lr_ptr[r]; plan.Ur_ptr[r + 1] += plan.Ur_ptr[r]; }
+    plan.Lr_col.resize(plan.Lr_ptr[n]); plan.Lr_src.resize(plan.Lr_ptr[n]);
+    plan.Ur_col.resize(plan.Ur_ptr[n]); plan.Ur_src.resize(plan.Ur_ptr[n]);
+    {
+      std::vector<int> lf(plan.Lr_ptr.begin(), plan.Lr_ptr.end() - 1), uf(plan.Ur_ptr.begin(), plan.Ur_ptr.end() - 1);
+      for (int b : plan.big_blocks)
+        for (int k = bptr[b]; k < bptr[b + 1]; ++k) {       // ascending k => columns ascending inside every row
+          for (int q = plan.Lp[k]; q < plan.Lp[k + 1]; ++q) { const int d = lf[plan.Li[q]]++; plan.Lr_col[d] = k; plan.Lr_src[d] = q; }
+          for (int q = plan.Up[k]; q < plan.Up[k + 1] - 1; ++q) { const int d = uf[plan.Ui[q]]++; plan.Ur_col[d] = k; plan.Ur_src[d] = q; }
+        }
+    }
+    // refactor schedule
+    plan.rf_level_ptr.assign(1, 0); plan.rf_dense_ptr.assign(1, 0);
+    if (max_clev >= 0) {
+      std::vector<std::vector<int>> by_level(max_clev + 1), dense_by_level(max_clev + 1);
+      for (int b : plan.big_blocks)
+        for (int k = bptr[b]; k < bptr[b + 1]; ++k) (dense[k] ? dense_by_level : by_level)[clev[k]].push_back(k);
+      for (int l = 0; l <= max_clev; ++l) {
+        plan.rf_cols.insert(plan.rf_cols.end(), by_level[l].begin(), by_level[l].end());
+        plan.rf_level_ptr.push_back((int)plan.rf_cols.size());
+        plan.rf_dense_cols.insert(plan.rf_dense_cols.end(), dense_by_level[l].begin(), dense_by_level[l].end());
+        plan.rf_dense_ptr.push_back((int)plan.rf_dense_cols.size());
+      }
+    }
+    // solve schedules, one block after the other
+    plan.fs_short_ptr.assign(1, 0); plan.fs_long_ptr.assign(1, 0); plan.bs_short_ptr.assign(1, 0); plan.bs_long_ptr.assign(1, 0);
+    std::vector<int> lev(n, 0);
+    for (int b : plan.big_blocks) {
+      const int k0 = bptr[b], k1 = bptr[b + 1];
+      int maxl = 0;
+      for (int r = k0; r < k1; ++r) {
+        int lv = 0;
+        for (int q = plan.Lr_ptr[r]; q < plan.Lr_ptr[r + 1]; ++q) lv = std::max(lv, lev[plan.Lr_col[q]] + 1);
+        lev[r] = lv; maxl = std::max(maxl, lv);
+      }
+      plan.big_fs_begin.push_back((int)plan.fs_short_ptr.size() - 1);
+      {
+        std::vector<std::vector<int>> rows(maxl + 1);
+        for (int r = k0; r < k1; ++r) if (plan.Lr_ptr[r + 1] > plan.Lr_ptr[r]) rows[lev[r]].push_back(r);
+        for (int l = 1; l <= maxl; ++l) {        // level 0 rows have no L entries
+          for (int r : rows[l]) ((plan.Lr_ptr[r + 1] - plan.Lr_ptr[r] > kLongRow) ? plan.fs_long_rows : plan.fs_short_rows).push_back(r);
+          plan.fs_short_ptr.push_back((int)plan.fs_short_rows.size()); plan.fs_long_ptr.push_back((int)plan.fs_long_rows.size());
+        }
+      }
+      plan.big_fs_end.push_back((int)plan.fs_short_ptr.size() - 1);
+      maxl = 0;
+      for (int r = k1 - 1; r >= k0; --r) {
+        int lv = 0;
+        for (int q = plan.Ur_ptr[r]; q < plan.Ur_ptr[r + 1]; ++q) lv = std::max(lv, lev[plan.Ur_col[q]] + 1);
+        lev[r] = lv; maxl = std::max(maxl, lv);
+      }
+      plan.big_bs_begin.push_back((int)plan.bs_short_ptr.size() - 1);
+      {
+        std::vector<std::vector<int>> rows(maxl + 1);
+        for (int r = k0; r < k1; ++r) rows[lev[r]].push_back(r);     // every row divides by its pivot, also level 0
+        for (int l = 0; l <= maxl; ++l) {
+          for (int r : rows[l]) ((plan.Ur_ptr[r + 1] - plan.Ur_ptr[r] > kLongRow) ? plan.bs_long_rows : plan.bs_short_rows).push_back(r);
+          plan.bs_short_ptr.push_back((int)plan.bs_short_rows.size()); plan.bs_long_ptr.push_back((int)plan.bs_long_rows.size());
+        }
+      }
+      plan.big_bs_end.push_back((int)plan.bs_short_ptr.size() - 1);
+    }
+  }
   // flop count of one refactorization: sum_k 2 |L_k| |U_k(offdiag)| + divisions
   double fl = 0.0;
   for (int k = 0; k < n; ++k) {
