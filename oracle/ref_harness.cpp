@@ -525,6 +525,8 @@ int xref_diode_export(void *h, int idx, double *rec, int *flags, int *lids3) {
   return k;
 }
 
+int xref_inst_converged(void *h, int idx) { return ((Ctx *)h)->insts[idx].inst->isConverged() ? 1 : 0; }
+
 // MOSFET level 1 / BJT records in the order of XB_MOS1_FIELDS / XB_BJT_FIELDS + flag word + node LIDs
 int xref_mos1_export(void *h, int idx, double *rec, int *flags, int *lids6) {
   Ctx *c = (Ctx *)h;

@@ -160,7 +160,7 @@ int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const
     for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JQ[i]);
     for (int i = 0; i < D::kNumStore; ++i) out[k++] = to_double(o.store[i]);
     for (int i = 0; i < D::kNumState; ++i) out[k++] = to_double(o.state[i]);
-    out[k++] = o.origFlag;
+    out[k++] = o.converged;
   } else if (type == 3) {
     namespace D = xb::bjt;
     D::Rec R; int j = 0;

@@ -59,6 +59,8 @@ def run_case(variant, flags, n_pairs=16, seed=3, store_noise=0.3, arith=None, op
         else:
             assert rel_err(got_s, want_s, 1e-30) < TOL, key
     assert rel_err(eng.b4_get_von(0, ref.n_inst), ref.get_von(), 1e-30) < TOL
+    # DeviceMgr::allDevicesConverged = AND of Instance::isConverged() (= !limitedFlag for BSIM4)
+    assert eng.all_converged() == all(ref.lib.xref_inst_converged(ref.h, i) for i in range(ref.n_inst))
     eng.close()
 
 

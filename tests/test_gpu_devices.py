@@ -30,6 +30,7 @@ def check(ref, eng, flags, x, nsto, csto, csta=None):
     assert rel_err(eng.get_state(0), st["next_sto"], 1e-30) < 1e-12
     if ref.n_sta:
         assert rel_err(eng.get_state(2), st["next_sta"], 1e-30) < 1e-12
+    assert eng.all_converged() == all(ref.lib.xref_inst_converged(ref.h, i) for i in range(ref.n_inst))
 
 
 @pytest.mark.parametrize("case", sorted(CASES))

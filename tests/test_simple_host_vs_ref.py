@@ -37,6 +37,7 @@ def run(kind, card, case, seed=3):
         per.append(o); lids.append(e["lids"])
         assert rel_err(o["store"], st["next_sto"][e["sto0"]:e["sto0"] + nstore], 1e-25) < 1e-12, (i, "store")
         assert rel_err(o["state"], st["next_sta"][e["sta0"]:e["sta0"] + nstate], 1e-25) < 1e-12, (i, "state")
+        assert o["orig"] == ref.lib.xref_inst_converged(ref.h, i), (i, "isConverged")
     asm = assemble(per, lids, srow, scol, ref.n, ref.rowptr, ref.colind)
     for k in want:
         scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300

@@ -140,7 +140,7 @@ __device__ __forceinline__ void eval_instance(const GroupDev &g, const LoadArgs 
   if (!valid) return;
   // ---- carried state, store and state vectors ----
   g.von[i] = to_double(W.von);
-  g.orig_flag[i] = W.origFlag;
+  g.orig_flag[i] = !W.limitedFlag;      // Instance::isConverged() (N_DEV_MOSFET_B4.h:2328-2331): only pnjlim invalidates convergence
   {
     double *ns = a.next_sto;
     for_each_store(W, [&](int s, real v) { ns[sto0 + (size_t)s * ss] = to_double(v); });

@@ -39,7 +39,7 @@ struct GroupDev {
   int sto_stride;           // LID distance between consecutive store slots of one instance
   int sta_stride;
   double *von;              // [n] carried limiter threshold (Instance::von)
-  int *orig_flag;           // [n] 1 = no limiting happened (DeviceInstance::origFlag)
+  int *orig_flag;           // [n] Instance::isConverged(): 1 unless pnjlim limited a junction voltage in this evaluation
   // contribution planes (see assembly.cuh): element (row r, instance i) of this group lives at
   // vec_base + r*n + i inside each of the 4 vector planes; slot s at mat_base + s*n + i.
   long long vec_base, mat_base;

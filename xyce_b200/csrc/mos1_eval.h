@@ -40,7 +40,8 @@ constexpr int kNumFields = 0 XB_MOS1_FIELDS(XB_CNT, XB_CNT);
 struct Out {
   real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots];
   real store[kNumStore], state[kNumState];
-  int origFlag;
+  int origFlag;       // 0 when any limited voltage differs from the solution (switches the Jdxp terms on)
+  int converged;      // Instance::isConverged() = !limitedFlag: only pnjlim invalidates convergence (N_DEV_MOSFET1.h:771-774)
 };
 
 // Meyer gate capacitances (half of the non-constant part; N_DEV_DeviceSupport.C:507-579)
@@ -124,6 +125,7 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
     vgd_old = vgs_old - vds_old;
   }
 
+  int limited = 0;
   if (S.voltageLimiterFlag) {
     if (!(S.initFixFlag && OFF)) {
       int Check = 1;
@@ -145,6 +147,7 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
         vbd = pnjlim(vbd, vbd_old, M.vt, M.drainVcrit, Check);
         vbs = vbd + vds;
       }
+      if (Check == 1) limited = 1;
     }
   }
   vbd = vbs - vds;
@@ -300,6 +303,7 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
   o.state[sa_capgs] = capgs; o.state[sa_capgd] = capgd; o.state[sa_capgb] = capgb;
   o.state[sa_qbd] = qbd; o.state[sa_qbs] = qbs;
   o.origFlag = origFlag;
+  o.converged = !limited;
 
   // ---- Master::loadDAEVectors ----
   const real np = M.numberParallel;

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) mos1_kernel(GroupDev g, b4::LoadArgs a) {
   for (int t = 0; t < D::kNumStore; ++t) a.next_sto[sto0 + (size_t)t * ss] = to_double(o.store[t]);
 #pragma unroll
   for (int t = 0; t < D::kNumState; ++t) a.next_sta[sta0 + (size_t)t * as] = to_double(o.state[t]);
-  g.orig_flag[i] = o.origFlag;
+  g.orig_flag[i] = o.converged;
   store_planes<D::Out, D::kNodes, D::kSlots>(g, a, o, i);
 }
 

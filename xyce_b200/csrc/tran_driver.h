@@ -17,6 +17,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace xb {
@@ -236,6 +238,7 @@ class TransientDriver {
     return nn.rhs_norm2;
   }
   NewtonNorms nn;
+  const bool trace_ = std::getenv("XB_TRAN_TRACE") != nullptr;     // diagnostics: one line per Newton iteration on stderr
 
   int newton_solve() {            // DampedNewton::solve with FULL search (step length 1)
     Flags fl; fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep;
@@ -258,6 +261,7 @@ class TransientDriver {
       if (lin != 0) { status = -9; break; }
       if (P.enforceDeviceConv) {
         const bool conv = nn.devices_converged;
+        if (trace_ && !conv) std::fprintf(stderr, "NEWTON t=%.9e it=%d devices not converged ||rhs||2=%.17g\n", nextTime, nlStep, normRHS);
         if (!conv && nlStep < P.maxNewtonStep) continue;
         if (!conv && nlStep >= P.maxNewtonStep) { status = -1; break; }
       }
@@ -269,6 +273,8 @@ class TransientDriver {
       const double resConvRate = normRHS / normRHS_old;
       normRHS_old = normRHS;
       const double updateSize = wtNormDX;
+      if (trace_) std::fprintf(stderr, "NEWTON t=%.9e it=%d ||rhs||2=%.17g ||rhs||inf=%.17g ||dx||w=%.17g devconv=%d\n", nextTime,
+                               nlStep, normRHS, maxNormRHS, updateSize, (int)nn.devices_converged);
       if (maxNormRHS <= P.RHSTol && updateSize <= P.deltaXTol) { status = 2; break; }
       if (nlStep >= P.maxNewtonStep && normRHS_rel <= 0.9 && resConvRate <= 1.0) { status = 3; break; }
       if (updateSize <= P.smallUpdateTol) { status = 4; break; }
