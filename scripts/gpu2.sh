@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_devices.py -x -q -m gpu 2>&1 | tail -3
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
-tail -c 1500 gpurun_out/bench_2gpu.json; tail -3 gpurun_out/bench_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 4 --warmup 1 2>/dev/null | tail -c 600
-python bench.py --steps 30 --warmup 5 > gpurun_out/bench_1gpu.json 2>/dev/null; tail -c 2500 gpurun_out/bench_1gpu.json
+tail -c 900 gpurun_out/bench_2gpu.json; grep -v "Netlist\|OMP_NUM\|\*\*\*" gpurun_out/bench_2gpu.err | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/multi_gpu_newton.py --rings 40 --check 1 2>&1 | grep -v "OMP_NUM\|\*\*\*" | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 scripts/multi_gpu_newton.py --rings 4950 --check 0 --iters 5 2>&1 | grep -v "OMP_NUM\|\*\*\*" | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 4 --warmup 1 2>/dev/null | tail -c 500
