@@ -1,0 +1,177 @@
+"""BASELINE-size runs checked through size-independent properties and sampled oracle parity:
+config 2 (100 000 BSIM4 instances, load + stamp) and config 3 (999 900 MOSFETs, Jacobian + KLU-pattern LU)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_ref
+import xyce_b200
+from b4_common import rel_err, solver_state
+from xyce_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+FLAGS = dict(transient=1, newtonIter=1)
+
+
+def load(eng, w, x=None):
+    eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
+    return eng.load_host(w["x"] if x is None else x, solver_state(**FLAGS))
+
+
+def test_c2_sampled_oracle_parity_and_determinism():
+    n_inv = 50000
+    w = wl.inverter_array(n_inv, store_noise=0.3)          # limiters active on part of the array
+    eng = wl.build_engine(w)
+    a = load(eng, w)
+    b = load(eng, w)
+    for k in a:                                             # atomic-free assembly: bitwise reproducible
+        assert np.array_equal(a[k], b[k]), k
+    # oracle on a sample: inverters [s0, s0 + m) as their own array, same node voltages and limiter history
+    m, s0 = 1500, 31000
+    ws = wl.inverter_array(m)
+    ref = oracle_ref.RefCircuit(2 * m + 1)
+    ref.add_model("nch", "NMOS", wl.NMOS_CARD); ref.add_model("pch", "PMOS", wl.PMOS_CARD)
+    vdd_s = 2 * m
+    for j in range(m):
+        ref.add_instance("M:n%d" % j, "nch", [2 * j + 1, 2 * j, -1, -1], wl.NMOS_INST)
+    for j in range(m):
+        ref.add_instance("M:p%d" % j, "pch", [2 * j + 1, 2 * j, vdd_s, vdd_s], wl.PMOS_INST)
+    ref.finalize()
+    xs = np.concatenate([w["x"][2 * s0:2 * (s0 + m)], [w["x"][2 * n_inv]]])
+    sto_big = w["store"].reshape(22, 2 * n_inv)
+    idx = np.concatenate([np.arange(s0, s0 + m), n_inv + np.arange(s0, s0 + m)])     # NMOS then PMOS of the sample
+    sto_s = np.zeros(ref.n_sto)
+    sto_s.reshape(2 * m, 22)[:, :] = sto_big[:, idx].T                                 # reference layout: instance-major
+    ref.set_flags(**FLAGS)
+    ref.set_state(curr_sto=sto_s, next_sto=sto_s); ref.set_von(w["von"][idx])
+    want = ref.load(xs)
+    rows = slice(2 * s0, 2 * (s0 + m))                                                  # in / out rows of the sample
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp"):
+        scale = 1e-3 * np.max(np.abs(want[k][:2 * m])) if np.any(want[k][:2 * m]) else 1e-300
+        assert rel_err(a[k][rows], want[k][:2 * m], scale) < 1e-12, k
+    # matrix rows of the sample: same (row, col) entries with the supply column remapped
+    rp, ci = w["rowptr"], w["colind"]
+    for k in ("dFdx", "dQdx"):
+        got = {}
+        for r in range(2 * s0, 2 * (s0 + m)):
+            for p in range(rp[r], rp[r + 1]):
+                c = ci[p]
+                got[(r - 2 * s0, c - 2 * s0 if c < 2 * n_inv else vdd_s)] = a[k][p]
+        ref_vals = want[k]
+        scale = 1e-3 * np.max(np.abs(ref_vals))
+        cnt = 0
+        for r in range(2 * m):
+            for p in range(ref.rowptr[r], ref.rowptr[r + 1]):
+                g = got[(r, ref.colind[p])]
+                assert abs(g - ref_vals[p]) <= 1e-12 * max(abs(ref_vals[p]), scale), (k, r)
+                cnt += 1
+        assert cnt == len(got)
+    eng.close()
+
+
+def test_c2_supply_rail_row_is_consistent_with_its_column():
+    """Size-independent property at 100 000 instances: source and bulk of every PMOS sit on the supply node, and a
+    MOSFET's currents do not change when all four terminals move together, so the column sums of its dF/dx stamp
+    vanish.  Hence the supply-row diagonal -- one destination with 100 000 contributions, reduced by the chunked
+    block tree -- must equal minus the sum of the supply-column entries of all other rows, which are assembled by
+    the short-destination path.  Checks the long-destination reduction and 32-bit indexing at full size."""
+    n_inv = 50000
+    w = wl.inverter_array(n_inv)
+    eng = wl.build_engine(w)
+    a = load(eng, w)
+    rp, ci = w["rowptr"], w["colind"]
+    vdd = 2 * n_inv
+    assert np.all(np.isfinite(a["dFdx"])) and np.all(np.isfinite(a["dQdx"]))
+    for k in ("dFdx", "dQdx"):
+        diag = a[k][rp[vdd] + np.searchsorted(ci[rp[vdd]:rp[vdd + 1]], vdd)]
+        col = 0.0
+        mag = abs(diag)
+        for r in range(2 * n_inv):
+            seg = ci[rp[r]:rp[r + 1]]
+            p = np.searchsorted(seg, vdd)
+            if p < len(seg) and seg[p] == vdd:
+                col += a[k][rp[r] + p]; mag += abs(a[k][rp[r] + p])
+        assert abs(diag + col) <= 1e-10 * mag, k
+    eng.close()
+
+
+def test_c3_jacobian_lu_residual_at_full_size():
+    w = wl.ring_oscillator_array(4950, 101)
+    eng = wl.build_engine(w)
+    n, nnz = w["n_unknowns"], eng.nnz
+    dev = dict(dtype=torch.float64, device="cuda")
+    ss = solver_state(**FLAGS)
+    x = torch.tensor(w["x"], **dev)
+    sta = [torch.zeros(w["n_state"], **dev) for _ in range(2)]; sto = [torch.zeros(w["n_store"], **dev) for _ in range(2)]
+    out = [torch.zeros(n, **dev) for _ in range(4)] + [torch.zeros(nnz, **dev) for _ in range(2)]
+    eng.load_dae(x.data_ptr(), sta[0].data_ptr(), sta[1].data_ptr(), sto[0].data_ptr(), sto[1].data_ptr(), ss,
+                 *[t.data_ptr() for t in out], accumulate=False)
+    J = torch.zeros(nnz, **dev)
+    h = 1e-12
+    eng.jacobian_combine(1.0 / h, out[5].data_ptr(), 1.0, out[4].data_ptr(), J.data_ptr())
+    # linear part (load capacitors / h, source branch) added through the pattern
+    L = w["linear"]; rp, ci = w["rowptr"], w["colind"]
+    Jh = J.cpu().numpy()
+    for pre, sc in (("g", 1.0), ("c", 1.0 / h)):
+        r, c, v = L[pre + "_row"], L[pre + "_col"], L[pre + "_val"]
+        pos = np.array([rp[a] + np.searchsorted(ci[rp[a]:rp[a + 1]], b) for a, b in zip(r, c)])
+        np.add.at(Jh, pos, sc * v)
+    J = torch.tensor(Jh, **dev)
+    rng = np.random.default_rng(0)
+    xt = rng.normal(size=n)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((Jh, ci, rp), shape=(n, n))
+    b = torch.tensor(A @ xt, **dev); sol = torch.zeros(n, **dev)
+    assert eng.lu_analyze(J.data_ptr()) == 0
+    info = eng.lu_info()
+    assert info["blocks"] == 4950 + 2 and info["largest_block"] == 101      # every ring its own BTF block
+    assert eng.lu_refactor(J.data_ptr()) == 0
+    eng.lu_solve(J.data_ptr(), b.data_ptr(), sol.data_ptr()); eng.sync()
+    xs = sol.cpu().numpy()
+    assert np.max(np.abs(A @ xs - A @ xt)) <= 1e-10 * np.max(np.abs(A @ xt))
+    assert np.max(np.abs(xs - xt)) <= 1e-8 * np.max(np.abs(xt))
+    eng.close()
+
+
+@pytest.mark.parametrize("n_inv", [1, 2, 63, 64, 65, 129])
+def test_ragged_and_tiny_groups(n_inv):
+    """group sizes around the block boundaries (and a single inverter): same results as the oracle"""
+    w = wl.inverter_array(n_inv, store_noise=0.2)
+    eng = wl.build_engine(w)
+    a = load(eng, w)
+    ref = oracle_ref.RefCircuit(2 * n_inv + 1)
+    ref.add_model("nch", "NMOS", wl.NMOS_CARD); ref.add_model("pch", "PMOS", wl.PMOS_CARD)
+    for j in range(n_inv):
+        ref.add_instance("M:n%d" % j, "nch", [2 * j + 1, 2 * j, -1, -1], wl.NMOS_INST)
+    for j in range(n_inv):
+        ref.add_instance("M:p%d" % j, "pch", [2 * j + 1, 2 * j, 2 * n_inv, 2 * n_inv], wl.PMOS_INST)
+    ref.finalize()
+    sto = np.zeros(ref.n_sto); sto.reshape(2 * n_inv, 22)[:, :] = w["store"].reshape(22, 2 * n_inv).T
+    ref.set_flags(**FLAGS); ref.set_state(curr_sto=sto, next_sto=sto); ref.set_von(w["von"])
+    want = ref.load(w["x"])
+    assert np.array_equal(ref.rowptr, w["rowptr"]) and np.array_equal(ref.colind, w["colind"])
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(a[k], want[k], scale) < 1e-12, k
+    eng.close()
+
+
+def test_accumulate_keeps_the_plus_equals_contract():
+    w = wl.inverter_array(300)
+    eng = wl.build_engine(w)
+    n, nnz = w["n_unknowns"], eng.nnz
+    dev = dict(dtype=torch.float64, device="cuda")
+    ss = solver_state(**FLAGS)
+    x = torch.tensor(w["x"], **dev)
+    sta = [torch.zeros(w["n_state"], **dev) for _ in range(2)]; sto = [torch.tensor(w["store"], **dev) for _ in range(2)]
+    base = [torch.full((n,), 3.0, **dev) for _ in range(4)] + [torch.full((nnz,), -2.0, **dev) for _ in range(2)]
+    zero = [torch.zeros(n, **dev) for _ in range(4)] + [torch.zeros(nnz, **dev) for _ in range(2)]
+    st = (x.data_ptr(), sta[0].data_ptr(), sta[1].data_ptr(), sto[0].data_ptr(), sto[1].data_ptr(), ss)
+    eng.load_dae(*st, *[t.data_ptr() for t in zero], accumulate=False)
+    for t in sto: t.copy_(torch.tensor(w["store"], **dev))
+    eng.b4_set_von(0, w["von"])
+    eng.load_dae(*st, *[t.data_ptr() for t in base], accumulate=True)
+    eng.sync()
+    for z, b, c in zip(zero, base, [3.0] * 4 + [-2.0] * 2):
+        assert torch.allclose(b, z + c, rtol=0, atol=1e-12 * float(z.abs().max() + 1))
+    eng.close()
