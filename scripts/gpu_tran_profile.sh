@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tran.py -x -q -m gpu 2>&1 | tail -2
 cat > /tmp/one.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -9,10 +8,10 @@ eng = wl.build_engine(w)
 r = eng.tran_run(w["x"], 1e-11, 1e-12, [0])
 print(r["stats"])
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 600 --csv --log-file gpurun_out/launches_tran.csv python /tmp/one.py > gpurun_out/tran_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 500 --csv --log-file gpurun_out/launches_tran_v2.csv python /tmp/one.py > gpurun_out/tran_ncu_v2.log 2>&1
 python - <<'PY'
 import csv, collections
-rows = list(csv.reader(open("gpurun_out/launches_tran.csv")))
+rows = list(csv.reader(open("gpurun_out/launches_tran_v2.csv")))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 h = rows[hdr]
 ik, iv = h.index("Kernel Name"), h.index("Metric Value")
@@ -22,6 +21,8 @@ for r in rows[hdr + 1:]:
     name = r[ik].split("(")[0][-60:]
     agg[name][0] += 1; agg[name][1] += float(r[iv].replace(",", ""))
 tot = sum(v[1] for v in agg.values())
+nit = agg[[k for k in agg if "lu_refactor_kernel" in k][0]][0]
+print("Newton iterations in window:", nit, " total kernel time per iteration: %.1f us" % (tot / 1e3 / nit))
 for k, v in sorted(agg.items(), key=lambda t: -t[1][1]):
-    print("%-62s n=%4d total=%10.1f us  %5.1f%%  avg=%8.1f us" % (k, v[0], v[1] / 1e3, 100 * v[1] / tot, v[1] / 1e3 / v[0]))
+    print("%-62s n=%4d per-iter=%8.1f us  %5.1f%%  avg=%8.1f us" % (k, v[0], v[1] / 1e3 / nit, 100 * v[1] / tot, v[1] / 1e3 / v[0]))
 PY

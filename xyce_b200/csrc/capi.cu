@@ -560,22 +560,22 @@ int xgpu_jacobian_combine(xgpu_ctx *ctx, double qs, const double *d_dQdx, double
   return 0;
 }
 
+namespace {
+__global__ void and_flags_k(const int *flags, int n, int *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i] == 0) *out = 0;      // every writer stores the same value
+}
+}  // namespace
+
 int xgpu_all_converged(xgpu_ctx *ctx, int *converged) {
   if (!ctx || !converged) return 1;
-  // small: copy the flags back and AND them on the host (a fused reduction follows with the norms)
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
   int all = 1;
-  for (auto &g : ctx->groups) {
-    std::vector<int> h(g.n);
-    XG_CUDA(cudaMemcpyAsync(h.data(), g.d_orig, g.n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int v : h) all &= (v != 0);
-  }
-  for (auto &g : ctx->sgroups) {
-    std::vector<int> h(g.n);
-    XG_CUDA(cudaMemcpyAsync(h.data(), g.d_orig, g.n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int v : h) all &= (v != 0);
-  }
+  XG_CUDA(cudaMemcpyAsync(ctx->d_conv, &all, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  for (auto &g : ctx->groups) { and_flags_k<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
+  for (auto &g : ctx->sgroups) { and_flags_k<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
+  XG_CUDA(cudaMemcpyAsync(&all, ctx->d_conv, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
   *converged = all;
   return 0;
 }

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuDev d,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerCta + warp;
   if (b >= d.nblocks) return;
-  if (d.block_big[b]) return;                  // large blocks: column-level schedule (lu_big_* kernels)
+  if (d.block_big[b]) return;                  // large blocks: lu_big_* kernels; staged small blocks: lu_*_staged_kernel
   const int k0 = d.block_ptr[b], k1 = d.block_ptr[b + 1];
   const int nb = k1 - k0;
   if (nb == 1) {                               // 1x1 block: the pivot is the matrix entry itself
@@ -88,6 +88,16 @@ __global__ void __launch_bounds__(256) lu_pull_short_kernel(LuDev d, const doubl
   if (lane == 0) d.work[r] -= acc;
 }
 
+// rows with a handful of off-diagonal entries (every ring node couples to the supply column only): one thread per row
+__global__ void __launch_bounds__(256) lu_pull_tiny_kernel(LuDev d, const double *__restrict__ A, int first, int count) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= count) return;
+  const int r = d.pull_tiny_rows[first + t];
+  double acc = 0.0;
+  for (int q = d.offr_ptr[r]; q < d.offr_ptr[r + 1]; ++q) acc += A[d.offr_src[q]] * d.work[d.offr_col[q]];
+  d.work[r] -= acc;
+}
+
 __device__ __forceinline__ double block_tree_sum(double v, double *sh) {
   sh[threadIdx.x] = v;
   __syncthreads();
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev
   const int idx = blockIdx.x * kWarpsPerCta + warp;
   if (idx >= count) return;
   const int b = d.level_blocks[first + idx];
-  if (d.block_big[b]) return;                  // large blocks: row-level schedule
+  if (d.block_big[b]) return;                  // large blocks: row-level schedule; staged small blocks: lu_solve_staged_kernel
   const int k0 = d.block_ptr[b], k1 = d.block_ptr[b + 1];
   double *y = d.work;
   // forward substitution with unit-lower L
@@ -147,6 +157,95 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev
     for (int q = d.Up[k] + lane; q < ue; q += 32) y[d.Ui[q]] -= d.Ux[q] * yk;
     __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged small blocks (block_big == 2): the whole factor of the block -- column pointers, row indices, values
+// and one dense column -- sits in a per-warp slice of shared memory, so the column chain of the left-looking
+// update runs on shared-memory latency instead of a dozen dependent global loads per column.
+// Slice layout: double x[nb], Lx[nl], Ux[nu]; int Lp[nb+1], Up[nb+1], Li[nl], Ui[nu]  (indices local to the block).
+// ---------------------------------------------------------------------------------------------
+struct StagedView { double *x, *Lx, *Ux; int *Lp, *Up, *Li, *Ui; int nb, nl, nu, k0, l0, u0; };
+__device__ __forceinline__ StagedView staged_load(const LuDev &d, int b, unsigned char *slice, int lane, bool values) {
+  StagedView v;
+  v.k0 = d.block_ptr[b]; v.nb = d.block_ptr[b + 1] - v.k0;
+  v.l0 = d.Lp[v.k0]; v.nl = d.Lp[v.k0 + v.nb] - v.l0;
+  v.u0 = d.Up[v.k0]; v.nu = d.Up[v.k0 + v.nb] - v.u0;
+  v.x = (double *)slice; v.Lx = v.x + v.nb; v.Ux = v.Lx + v.nl;
+  v.Lp = (int *)(v.Ux + v.nu); v.Up = v.Lp + v.nb + 1; v.Li = v.Up + v.nb + 1; v.Ui = v.Li + v.nl;
+  for (int i = lane; i <= v.nb; i += 32) { v.Lp[i] = d.Lp[v.k0 + i] - v.l0; v.Up[i] = d.Up[v.k0 + i] - v.u0; }
+  for (int i = lane; i < v.nl; i += 32) { v.Li[i] = d.Li[v.l0 + i] - v.k0; if (values) v.Lx[i] = d.Lx[v.l0 + i]; }
+  for (int i = lane; i < v.nu; i += 32) { v.Ui[i] = d.Ui[v.u0 + i] - v.k0; if (values) v.Ux[i] = d.Ux[v.u0 + i]; }
+  return v;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_staged_kernel(LuDev d, const double *__restrict__ A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarpsPerCta + warp;
+  if (b >= d.nblocks || d.block_big[b] != 2) return;
+  StagedView v = staged_load(d, b, smem + (size_t)warp * d.staged_bytes, lane, false);
+  for (int i = lane; i < v.nl; i += 32) v.Lx[i] = 0.0;
+  for (int i = lane; i < v.nu; i += 32) v.Ux[i] = 0.0;
+  __syncwarp();
+  // A -> factor slots (acol_dst: >= 0 index into Ux, < 0 ~index into Lx), all columns of the block at once
+  const int a0 = d.acol_ptr[v.k0], a1 = d.acol_ptr[v.k0 + v.nb];
+  for (int q = a0 + lane; q < a1; q += 32) {
+    const int dst = d.acol_dst[q];
+    const double val = A[d.acol_src[q]];
+    if (dst >= 0) v.Ux[dst - v.u0] = val; else v.Lx[~dst - v.l0] = val;
+  }
+  __syncwarp();
+  bool bad = false;
+  for (int k = 0; k < v.nb; ++k) {
+    const int ub = v.Up[k], ue = v.Up[k + 1] - 1, lb = v.Lp[k], le = v.Lp[k + 1];
+    // dense column from the slots
+    for (int q = ub + lane; q < ue; q += 32) v.x[v.Ui[q]] = v.Ux[q];
+    for (int q = lb + lane; q < le; q += 32) v.x[v.Li[q]] = v.Lx[q];
+    if (lane == 0) v.x[k] = v.Ux[ue];
+    __syncwarp();
+    for (int q = ub; q < ue; ++q) {
+      const int i = v.Ui[q];
+      const double u = v.x[i];
+      if (lane == 0) v.Ux[q] = u;
+      for (int t = v.Lp[i] + lane; t < v.Lp[i + 1]; t += 32) v.x[v.Li[t]] -= v.Lx[t] * u;
+      __syncwarp();
+    }
+    const double pivot = v.x[k];
+    if (bad_pivot(pivot)) bad = true;
+    if (lane == 0) v.Ux[ue] = pivot;
+    for (int q = lb + lane; q < le; q += 32) v.Lx[q] = v.x[v.Li[q]] / pivot;
+    __syncwarp();
+  }
+  if (bad && lane == 0) *d.status = 1;
+  for (int i = lane; i < v.nl; i += 32) d.Lx[v.l0 + i] = v.Lx[i];
+  for (int i = lane; i < v.nu; i += 32) d.Ux[v.u0 + i] = v.Ux[i];
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_staged_kernel(LuDev d, int first, int count, double *__restrict__ xout) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * kWarpsPerCta + warp;
+  if (idx >= count) return;
+  const int b = d.level_blocks[first + idx];
+  if (d.block_big[b] != 2) return;
+  StagedView v = staged_load(d, b, smem + (size_t)warp * d.staged_bytes, lane, true);
+  for (int i = lane; i < v.nb; i += 32) v.x[i] = d.work[v.k0 + i];
+  __syncwarp();
+  for (int k = 0; k < v.nb; ++k) {                       // unit-lower forward substitution
+    const double yk = v.x[k];
+    for (int q = v.Lp[k] + lane; q < v.Lp[k + 1]; q += 32) v.x[v.Li[q]] -= v.Lx[q] * yk;
+    __syncwarp();
+  }
+  for (int k = v.nb - 1; k >= 0; --k) {                  // backward substitution, pivot stored last in the column
+    const int ue = v.Up[k + 1] - 1;
+    const double yk = v.x[k] / v.Ux[ue];
+    __syncwarp();
+    if (lane == 0) v.x[k] = yk;
+    for (int q = v.Up[k] + lane; q < ue; q += 32) v.x[v.Ui[q]] -= v.Ux[q] * yk;
+    __syncwarp();
+  }
+  for (int i = lane; i < v.nb; i += 32) { const double yi = v.x[i]; d.work[v.k0 + i] = yi; xout[d.col_perm[v.k0 + i]] = yi; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -273,7 +372,7 @@ void free_plan(LuDev &d) {
   cudaFree(d.level_blocks); cudaFree(d.work); cudaFree(d.status);
   cudaFree(d.pull_short_rows); cudaFree(d.pull_long_rows); cudaFree(d.pull_chunk_row_slot); cudaFree(d.pull_chunk_begin);
   cudaFree(d.pull_long_chunk_ptr); cudaFree(d.pull_partials);
-  cudaFree(d.work2); cudaFree(d.block_big); cudaFree(d.acol_dst); cudaFree(d.rf_cols); cudaFree(d.Lr_ptr); cudaFree(d.Lr_col);
+  cudaFree(d.pull_tiny_rows); cudaFree(d.work2); cudaFree(d.block_big); cudaFree(d.acol_dst); cudaFree(d.rf_cols); cudaFree(d.Lr_ptr); cudaFree(d.Lr_col);
   cudaFree(d.Lr_src); cudaFree(d.Ur_ptr); cudaFree(d.Ur_col); cudaFree(d.Ur_src); cudaFree(d.fs_short_rows); cudaFree(d.fs_long_rows);
   cudaFree(d.bs_short_rows); cudaFree(d.bs_long_rows);
   d = LuDev();
@@ -290,9 +389,10 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
   UP(row_perm) UP(col_perm) UP(block_ptr) UP(Lp) UP(Li) UP(Up) UP(Ui) UP(Lx) UP(Ux)
   UP(acol_ptr) UP(acol_row) UP(acol_src) UP(offr_ptr) UP(offr_col) UP(offr_src) UP(level_blocks)
   UP(pull_short_rows) UP(pull_long_rows) UP(pull_chunk_row_slot) UP(pull_chunk_begin) UP(pull_long_chunk_ptr)
-  UP(block_big) UP(acol_dst) UP(rf_cols) UP(Lr_ptr) UP(Lr_col) UP(Lr_src) UP(Ur_ptr) UP(Ur_col) UP(Ur_src)
+  UP(pull_tiny_rows) UP(block_big) UP(acol_dst) UP(rf_cols) UP(Lr_ptr) UP(Lr_col) UP(Lr_src) UP(Ur_ptr) UP(Ur_col) UP(Ur_src)
   UP(fs_short_rows) UP(fs_long_rows) UP(bs_short_rows) UP(bs_long_rows)
 #undef UP
+  d.pull_tiny_ptr = p.pull_tiny_ptr; d.staged_bytes = p.staged_bytes;
   d.rf_level_ptr = p.rf_level_ptr; d.rf_dense_ptr = p.rf_dense_ptr; d.rf_dense_cols = p.rf_dense_cols;
   d.fs_short_ptr = p.fs_short_ptr; d.fs_long_ptr = p.fs_long_ptr; d.bs_short_ptr = p.bs_short_ptr; d.bs_long_ptr = p.bs_long_ptr;
   d.big_blocks = p.big_blocks; d.big_fs_begin = p.big_fs_begin; d.big_fs_end = p.big_fs_end;
@@ -308,6 +408,11 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
       while (!(p.block_ptr[p.big_blocks[bi]] <= k && k < p.block_ptr[p.big_blocks[bi] + 1])) ++bi;
       d.dense_col_block.push_back(bi);
     }
+  }
+  if (d.staged_bytes > 0) {
+    const int bytes = kWarpsPerCta * d.staged_bytes;      // 4 x 12 KB at most, above the 48 KB default limit
+    if ((e = cudaFuncSetAttribute(lu_refactor_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lu_solve_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
   }
   if ((e = cudaMalloc((void **)&d.work2, (size_t)(p.n > 0 ? p.n : 1) * sizeof(double))) != cudaSuccess) return e;
   d.pull_short_ptr = p.pull_short_ptr; d.pull_long_ptr = p.pull_long_ptr; d.pull_chunk_ptr = p.pull_chunk_ptr;
@@ -335,6 +440,7 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
   const int ctas = (d.nblocks + kWarpsPerCta - 1) / kWarpsPerCta;
   lu_refactor_kernel<<<ctas, 32 * kWarpsPerCta, 0, s>>>(d, A);
   int launches = 1;
+  if (d.staged_bytes > 0) { lu_refactor_staged_kernel<<<ctas, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * d.staged_bytes, s>>>(d, A); ++launches; }
   // large blocks: columns level by level; dense columns of a level after its normal columns
   const int nlev = (int)d.rf_level_ptr.size() - 1;
   for (int l = 0; l < nlev; ++l) {
@@ -359,6 +465,8 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
   for (int l = 0; l < d.nlevels; ++l) {
     const int first = d.level_ptr[l], count = d.level_ptr[l + 1] - first;
     if (count <= 0) continue;
+    const int nt = d.pull_tiny_ptr[l + 1] - d.pull_tiny_ptr[l];
+    if (nt > 0) { lu_pull_tiny_kernel<<<(nt + 255) / 256, 256, 0, s>>>(d, A, d.pull_tiny_ptr[l], nt); ++launches; }
     const int ns = d.pull_short_ptr[l + 1] - d.pull_short_ptr[l];
     if (ns > 0) { lu_pull_short_kernel<<<(ns * 32 + 255) / 256, 256, 0, s>>>(d, A, d.pull_short_ptr[l], ns); ++launches; }
     const int nc = d.pull_chunk_ptr[l + 1] - d.pull_chunk_ptr[l], nl = d.pull_long_ptr[l + 1] - d.pull_long_ptr[l];
@@ -369,6 +477,10 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
     }
     lu_solve_level_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, s>>>(d, A, first, count, x);
     ++launches;
+    if (d.staged_bytes > 0) {
+      lu_solve_staged_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * d.staged_bytes, s>>>(d, first, count, x);
+      ++launches;
+    }
     for (size_t bi = 0; bi < d.big_blocks.size(); ++bi) {
       if (d.block_level_of_big[bi] != l) continue;
       launches += run_fwd_stages(d, d.work, d.big_fs_begin[bi], d.big_fs_end[bi], 0x7fffffff, s);

@@ -32,6 +32,7 @@ struct LuPlan {
   std::vector<int> level_ptr, level_blocks;
   // rows (positions) of each level that own off-diagonal entries, split by list length:
   // short rows are pulled by one warp each, long rows (supply rails) by chunked block reductions
+  std::vector<int> pull_tiny_ptr, pull_tiny_rows;        // per level: rows with at most 8 entries (one thread each)
   std::vector<int> pull_short_ptr, pull_short_rows;      // per level
   std::vector<int> pull_long_ptr, pull_long_rows;        // per level
   std::vector<int> pull_chunk_ptr, pull_chunk_row_slot, pull_chunk_begin;   // per level: chunks of the long rows
@@ -46,7 +47,8 @@ struct LuPlan {
   //             kDenseCol (supply rails) are computed as a forward substitution over the whole block instead.
   //   solve:    L and U of the block in row form; rows grouped by level, one warp (or one CTA for rows longer
   //             than kLongRow) per row.
-  std::vector<int> block_big;                   // [nblocks] 1 = large block
+  std::vector<int> block_big;                   // [nblocks] 0 = medium (warp per block, global indices), 1 = large, 2 = staged small block
+  int staged_bytes = 0;                         // shared-memory slice per warp of the staged kernels
   std::vector<int> acol_dst;                    // per acol entry of a large-block column: >= 0 index into Ux, < 0 ~index into Lx
   std::vector<int> rf_level_ptr, rf_cols;       // normal columns of all large blocks by level
   std::vector<int> rf_dense_ptr, rf_dense_cols; // dense columns by level (processed one at a time after the level's normal columns)
@@ -58,7 +60,7 @@ struct LuPlan {
   std::vector<int> big_blocks;                  // ids of the large blocks
   std::vector<int> big_fs_begin, big_fs_end, big_bs_begin, big_bs_end;       // per large block: its stage ranges
 };
-constexpr int kBigBlock = 512, kDenseCol = 4096, kLongRow = 2048;
+constexpr int kBigBlock = 512, kDenseCol = 4096, kLongRow = 2048, kStagedBytes = 12288;
 
 // Symbolic analysis + first numeric factorization with threshold partial pivoting (KLU defaults:
 // pivot_tol = 0.001, diagonal preferred).  Returns 0 ok, 1 structurally singular, 2 numerically singular.
@@ -68,7 +70,7 @@ void solve_host(const LuPlan &plan, const double *b, double *x);
 
 // Device-resident copy of a plan plus work space; created by upload_plan, used by the kernels.
 struct LuDev {
-  int n = 0, nblocks = 0, nlevels = 0;
+  int n = 0, nblocks = 0, nlevels = 0, staged_bytes = 0;
   int *row_perm = nullptr, *col_perm = nullptr, *block_ptr = nullptr;
   int *Lp = nullptr, *Li = nullptr, *Up = nullptr, *Ui = nullptr;
   double *Lx = nullptr, *Ux = nullptr;
@@ -76,6 +78,7 @@ struct LuDev {
   int *offr_ptr = nullptr, *offr_col = nullptr, *offr_src = nullptr;
   int *level_blocks = nullptr;
   std::vector<int> level_ptr;     // host copy: one launch per level
+  int *pull_tiny_rows = nullptr; std::vector<int> pull_tiny_ptr;
   int *pull_short_rows = nullptr, *pull_long_rows = nullptr, *pull_chunk_row_slot = nullptr, *pull_chunk_begin = nullptr;
   int *pull_long_chunk_ptr = nullptr;
   std::vector<int> pull_short_ptr, pull_long_ptr, pull_chunk_ptr;   // host copies

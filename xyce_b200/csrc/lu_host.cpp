@@ -400,7 +400,8 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
   }
   // off-diagonal pull lists per level
   {
-    const int kLongRow = 4096, kPullChunk = 4096;
+    const int kPullLong = 4096, kPullChunk = 4096, kPullTiny = 8;
+    plan.pull_tiny_ptr.assign(1, 0);
     plan.pull_short_ptr.assign(1, 0); plan.pull_long_ptr.assign(1, 0); plan.pull_chunk_ptr.assign(1, 0);
     plan.pull_long_chunk_ptr.assign(1, 0);
     for (int l = 0; l <= maxlevel; ++l) {
@@ -409,7 +410,8 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
         for (int r = bptr[b]; r < bptr[b + 1]; ++r) {
           const int cnt = plan.offr_ptr[r + 1] - plan.offr_ptr[r];
           if (cnt == 0) continue;
-          if (cnt <= kLongRow) { plan.pull_short_rows.push_back(r); continue; }
+          if (cnt <= kPullTiny) { plan.pull_tiny_rows.push_back(r); continue; }      // one thread per row
+          if (cnt <= kPullLong) { plan.pull_short_rows.push_back(r); continue; }     // one warp per row
           const int slot = (int)plan.pull_long_rows.size();
           plan.pull_long_rows.push_back(r);
           for (int c0 = plan.offr_ptr[r]; c0 < plan.offr_ptr[r + 1]; c0 += kPullChunk) {
@@ -418,6 +420,7 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
           plan.pull_long_chunk_ptr.push_back((int)plan.pull_chunk_begin.size());
         }
       }
+      plan.pull_tiny_ptr.push_back((int)plan.pull_tiny_rows.size());
       plan.pull_short_ptr.push_back((int)plan.pull_short_rows.size());
       plan.pull_long_ptr.push_back((int)plan.pull_long_rows.size());
       plan.pull_chunk_ptr.push_back((int)plan.pull_chunk_begin.size());
@@ -432,16 +435,29 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
     std::vector<int> clev(n, 0);
     int max_clev = -1;
     std::vector<char> dense(n, 0);
+    // destination of every A entry inside the factor arrays (all blocks)
+    for (int k = 0; k < n; ++k) {
+      const int ub = plan.Up[k], ue = plan.Up[k + 1] - 1, lb = plan.Lp[k], le = plan.Lp[k + 1];
+      for (int q = plan.acol_ptr[k]; q < plan.acol_ptr[k + 1]; ++q) {
+        const int r = plan.acol_row[q];
+        if (r == k) plan.acol_dst[q] = ue;
+        else if (r < k) plan.acol_dst[q] = (int)(std::lower_bound(plan.Ui.begin() + ub, plan.Ui.begin() + ue, r) - plan.Ui.begin());
+        else plan.acol_dst[q] = ~(int)(std::lower_bound(plan.Li.begin() + lb, plan.Li.begin() + le, r) - plan.Li.begin());
+      }
+    }
+    // small blocks whose factor (indices + values + one dense column) fits a per-warp shared-memory slice are
+    // "staged": block_big = 2.  Slice = 2 (nb + 1) + nl + nu ints and nb + nl + nu doubles.
+    plan.staged_bytes = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      const int k0 = bptr[b], k1 = bptr[b + 1], nb = k1 - k0;
+      if (nb < 2 || plan.block_big[b]) continue;
+      const int nl = plan.Lp[k1] - plan.Lp[k0], nu = plan.Up[k1] - plan.Up[k0];
+      const int bytes = 8 * (nb + nl + nu) + 4 * (2 * (nb + 1) + nl + nu + 2);
+      if (bytes <= kStagedBytes) { plan.block_big[b] = 2; plan.staged_bytes = std::max(plan.staged_bytes, (bytes + 15) / 16 * 16); }
+    }
     for (int b : plan.big_blocks) {
       for (int k = bptr[b]; k < bptr[b + 1]; ++k) {
         const int ub = plan.Up[k], ue = plan.Up[k + 1] - 1, lb = plan.Lp[k], le = plan.Lp[k + 1];
-        // destination of every A entry of this column inside the factor arrays
-        for (int q = plan.acol_ptr[k]; q < plan.acol_ptr[k + 1]; ++q) {
-          const int r = plan.acol_row[q];
-          if (r == k) plan.acol_dst[q] = ue;
-          else if (r < k) plan.acol_dst[q] = (int)(std::lower_bound(plan.Ui.begin() + ub, plan.Ui.begin() + ue, r) - plan.Ui.begin());
-          else plan.acol_dst[q] = ~(int)(std::lower_bound(plan.Li.begin() + lb, plan.Li.begin() + le, r) - plan.Li.begin());
-        }
         int lv = 0;
         for (int q = ub; q < ue; ++q) lv = std::max(lv, clev[plan.Ui[q]] + 1);
         clev[k] = lv; max_clev = std::max(max_clev, lv);
