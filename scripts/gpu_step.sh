@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_lu.py tests/test_gpu_tran.py tests/test_gpu_full_size.py -x -q -m gpu 2>&1 | grep -v Netlist | tail -4
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import sys, json
-r = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.3e' % r['value'], 'tran_c3', r['tran_c3'])"
-bash scripts/gpu_tran_profile.sh 2>&1 | head -12
+timeout 300 compute-sanitizer --tool memcheck --print-limit 3 python scripts/sanitize_shapes.py 2>&1 | grep -v Netlist | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | grep -v Netlist | tail -4
+XYCE_B200_BENCH_VERBOSE=1 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_e.json 2> gpurun_out/bench_e.err; grep "ms:" gpurun_out/bench_e.err | cut -c1-160; tail -c 2400 gpurun_out/bench_e.json

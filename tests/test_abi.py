@@ -47,3 +47,20 @@ def test_benchmark_fixture_matches_field_lists():
     rec = wl.load_b4_records()
     for which, key in enumerate(("model_d", "model_i", "size_d", "inst_d", "inst_i")):
         assert list(rec["names_" + key]) == lib.xgpu_b4_field_names(which).decode().split()
+
+
+def test_specialised_kernel_mode_set_is_consistent():
+    """the mode set substituted by scripts/gen_spec.py must be the one the launcher checks model cards against"""
+    import importlib.util
+    src = open(os.path.join(ROOT, "scripts", "gen_spec.py")).read()
+    spec = eval("dict(" + src.split("SPEC = dict(")[1].split(")\n")[0] + ")")
+    hdr = open(os.path.join(ROOT, "xyce_b200", "csrc", "b4_kernels.cuh")).read()
+    modes = [int(v) for v in hdr.split("kSpecModes[17] = {")[1].split("}")[0].split(",")]
+    lib = xyce_b200.load_library()
+    names = lib.xgpu_b4_field_names(1).decode().split()
+    assert len(names) == len(modes) == 17
+    for n, m in zip(names, modes):
+        if m == -2:
+            assert n not in spec
+        else:
+            assert spec[n] == m, n

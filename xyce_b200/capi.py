@@ -85,7 +85,7 @@ class Engine:
         # optional overrides of the kernel variant (see xgpu_set_option in include/xyce_b200.h)
         for env, opt in (("XYCE_B200_B4_ARITH", "b4_arith"), ("XYCE_B200_B4_MINBLOCKS", "b4_minblocks"),
                          ("XYCE_B200_B4_THREADS", "b4_threads"), ("XYCE_B200_B4_UNIFORM", "b4_uniform"),
-                         ("XYCE_B200_B4_LOCKSTEP", "b4_lockstep")):
+                         ("XYCE_B200_B4_LOCKSTEP", "b4_lockstep"), ("XYCE_B200_B4_SPEC", "b4_spec")):
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
 

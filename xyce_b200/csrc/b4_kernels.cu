@@ -245,7 +245,7 @@ void launch_variant(const GroupDev &g, const LoadArgs &a, const BinPack *packs, 
       b4_eval_uniform_kernel<GENERAL, THREADS, MINBLOCKS><<<grid, THREADS, 0, stream>>>(g, a, packs[p]);
     }
   } else {
-#if !XB_LOCKSTEP
+#if !XB_LOCKSTEP && !XB_SPEC
     b4_eval_kernel<GENERAL, THREADS, MINBLOCKS><<<(g.n + THREADS - 1) / THREADS, THREADS, 0, stream>>>(g, a);
 #endif
   }
@@ -253,7 +253,12 @@ void launch_variant(const GroupDev &g, const LoadArgs &a, const BinPack *packs, 
 
 }  // namespace
 
-#if XB_LOCKSTEP
+#ifndef XB_SPEC
+#define XB_SPEC 0
+#endif
+#if XB_SPEC
+#define XB_LAUNCH_NAME XB_CAT(XB_CAT(launch_b4_group_a, XB_ARITH), x)
+#elif XB_LOCKSTEP
 #define XB_LAUNCH_NAME XB_CAT(XB_CAT(launch_b4_group_a, XB_ARITH), s)
 #else
 #define XB_LAUNCH_NAME XB_CAT(launch_b4_group_a, XB_ARITH)

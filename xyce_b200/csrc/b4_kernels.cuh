@@ -80,8 +80,13 @@ int launch_b4_group_a0(const GroupDev &g, const LoadArgs &a, int threads, int mi
 int launch_b4_group_a1(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
 int launch_b4_group_a2(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
 int launch_b4_group_a2s(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+// mode-specialised build (scripts/gen_spec.py): only for groups whose model cards all carry kSpecModes
+int launch_b4_group_a2x(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+// mode set of the specialised object in XB_B4_MODEL_I order; -2 = not specialised (dtype)
+constexpr int kSpecModes[17] = {2, 0, 1, -2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 inline int launch_b4_group(const GroupDev &g, const LoadArgs &a, int arith, int lockstep, int threads, int minblocks,
-                           const BinPack *packs, int npacks, cudaStream_t stream) {
+                           const BinPack *packs, int npacks, cudaStream_t stream, bool spec = false) {
+  if (arith == 2 && spec && !lockstep && !g.general && packs) return launch_b4_group_a2x(g, a, threads, minblocks, packs, npacks, stream);
   if (arith == 2) return lockstep ? launch_b4_group_a2s(g, a, threads, minblocks, packs, npacks, stream)
                                   : launch_b4_group_a2(g, a, threads, minblocks, packs, npacks, stream);
   if (arith == 1) return launch_b4_group_a1(g, a, threads, minblocks, packs, npacks, stream);

@@ -124,6 +124,15 @@ XB_HD void tat_term(real vts, real nvtmr, real vj, real &t, real &dt_dvb) {
   }
 }
 
+// value-in / value-out entry points of the helpers above (real functions in the fast device build, see XB_HELPER)
+XB_HELPER Real2 junction_diode_v(int dioMod, JctPar j, real vj, real gmin) {
+  Real2 r; junction_diode(dioMod, j, vj, gmin, r.a, r.b); return r;
+}
+XB_HELPER Real2 tat_term_v(real vts, real nvtmr, real vj) { Real2 r; tat_term(vts, nvtmr, vj, r.a, r.b); return r; }
+XB_HELPER Real2 poly_depletion_v(real phi, real ngate, real epsgate, real coxe, real vg) {
+  Real2 r; poly_depletion(phi, ngate, epsgate, coxe, vg, r.a, r.b); return r;
+}
+
 // ---------------------------------------------------------------------------
 // Stage 1: terminal voltages, initial-condition overrides, Newton limiting.
 //   V[]      node voltages in general-stamp order (see B4Node)

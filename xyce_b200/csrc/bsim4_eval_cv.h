@@ -41,6 +41,11 @@ XB_HD void junction_charge(real v, real cz, real czsw, real czswg,
   }
 }
 
+XB_HELPER Real2 junction_charge_v(real v, real cz, real czsw, real czswg, real mj, real mjsw, real mjswg,
+                                  real phib, real phibsw, real phibswg) {
+  Real2 r; junction_charge(v, cz, czsw, czswg, mj, mjsw, mjswg, phib, phibsw, phibswg, r.a, r.b); return r;
+}
+
 XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
                     const B4Inst &I, B4Mid &W, DcCarry &C) {
   real T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, tmp, tmp1;
@@ -733,12 +738,14 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
     const real czbdswg = M.DunitLengthGateSidewallTempJctCap * P.weffCJ * I.nf;
     const real czbssw = M.SunitLengthSidewallTempJctCap * I.Pseff;
     const real czbsswg = M.SunitLengthGateSidewallTempJctCap * P.weffCJ * I.nf;
-    junction_charge(W.vbs_jct, czbs, czbssw, czbsswg,
+    Real2 qc = junction_charge_v(W.vbs_jct, czbs, czbssw, czbsswg,
                     M.SbulkJctBotGradingCoeff, M.SbulkJctSideGradingCoeff, M.SbulkJctGateSideGradingCoeff,
-                    M.PhiBS, M.PhiBSWS, M.PhiBSWGS, W.qbs, W.capbs);
-    junction_charge(W.vbd_jct, czbd, czbdsw, czbdswg,
+                    M.PhiBS, M.PhiBSWS, M.PhiBSWGS);
+    W.qbs = qc.a; W.capbs = qc.b;
+    qc = junction_charge_v(W.vbd_jct, czbd, czbdsw, czbdswg,
                     M.DbulkJctBotGradingCoeff, M.DbulkJctSideGradingCoeff, M.DbulkJctGateSideGradingCoeff,
-                    M.PhiBD, M.PhiBSWD, M.PhiBSWGD, W.qbd, W.capbd);
+                    M.PhiBD, M.PhiBSWD, M.PhiBSWGD);
+    W.qbd = qc.a; W.capbd = qc.b;
   } else {
     W.qbs = W.qbd = W.capbs = W.capbd = 0.0;
   }

@@ -81,6 +81,14 @@ XB_HD void gidl_mod1(real T0, real T1, real rg, real dveff_dvg, real a, real b, 
 }
 
 // Everything the C-V stage needs from the DC stage besides B4Mid.
+XB_HELPER Real4 gidl_mod0_v(real T0, real T1, real dveff_dvg, real a, real b, real c, real weffCJ, real vbx) {
+  Real4 r; gidl_mod0(T0, T1, dveff_dvg, a, b, c, weffCJ, vbx, r.a, r.b, r.c, r.d); return r;
+}
+XB_HELPER Real4 gidl_mod1_v(real T0, real T1, real rg, real dveff_dvg, real a, real b, real c, real k, real f, real weffCJ,
+                            real vbx, real clamp) {
+  Real4 r; gidl_mod1(T0, T1, rg, dveff_dvg, a, b, c, k, f, weffCJ, vbx, clamp, r.a, r.b, r.c, r.d); return r;
+}
+
 struct DcCarry {
   real Vds, Vgs, Vbs, Vdb;
   real Vbseff, dVbseff_dVb, Phis, dPhis_dVb, sqrtPhis, dsqrtPhis_dVb;
@@ -118,7 +126,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     js.xjbv = M.xjbvs; js.bv = M.bvs; js.XExpBV = I.XExpBVS;
     js.vjmFwd = I.vjsmFwd; js.vjmRev = I.vjsmRev; js.IVjmFwd = I.IVjsmFwd; js.IVjmRev = I.IVjsmRev;
     js.slpFwd = I.SslpFwd; js.slpRev = I.SslpRev;
-    junction_diode(M.dioMod, js, W.vbs_jct, gmin, W.gbs, W.cbs);
+    { const Real2 r = junction_diode_v(M.dioMod, js, W.vbs_jct, gmin); W.gbs = r.a; W.cbs = r.b; }
 
     JctPar jd;
     jd.Nvtm = M.vtm * M.DjctEmissionCoeff;
@@ -128,16 +136,16 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     jd.xjbv = M.xjbvd; jd.bv = M.bvd; jd.XExpBV = I.XExpBVD;
     jd.vjmFwd = I.vjdmFwd; jd.vjmRev = I.vjdmRev; jd.IVjmFwd = I.IVjdmFwd; jd.IVjmRev = I.IVjdmRev;
     jd.slpFwd = I.DslpFwd; jd.slpRev = I.DslpRev;
-    junction_diode(M.dioMod, jd, W.vbd_jct, gmin, W.gbd, W.cbd);
+    { const Real2 r = junction_diode_v(M.dioMod, jd, W.vbd_jct, gmin); W.gbd = r.a; W.cbd = r.b; }
 
     // trap-assisted tunnelling / recombination in reverse bias
     real t1, d1, t2, d2, t3, d3, t4, d4, t5, d5, t6, d6;
-    tat_term(M.vtss,    M.vtm0 * M.njtsstemp,    W.vbs_jct, t1, d1);
-    tat_term(M.vtsd,    M.vtm0 * M.njtsdtemp,    W.vbd_jct, t2, d2);
-    tat_term(M.vtssws,  M.vtm0 * M.njtsswstemp,  W.vbs_jct, t3, d3);
-    tat_term(M.vtsswd,  M.vtm0 * M.njtsswdtemp,  W.vbd_jct, t4, d4);
-    tat_term(M.vtsswgs, M.vtm0 * M.njtsswgstemp, W.vbs_jct, t5, d5);
-    tat_term(M.vtsswgd, M.vtm0 * M.njtsswgdtemp, W.vbd_jct, t6, d6);
+    { const Real2 r = tat_term_v(M.vtss, M.vtm0 * M.njtsstemp, W.vbs_jct); t1 = r.a; d1 = r.b; }
+    { const Real2 r = tat_term_v(M.vtsd, M.vtm0 * M.njtsdtemp, W.vbd_jct); t2 = r.a; d2 = r.b; }
+    { const Real2 r = tat_term_v(M.vtssws, M.vtm0 * M.njtsswstemp, W.vbs_jct); t3 = r.a; d3 = r.b; }
+    { const Real2 r = tat_term_v(M.vtsswd, M.vtm0 * M.njtsswdtemp, W.vbd_jct); t4 = r.a; d4 = r.b; }
+    { const Real2 r = tat_term_v(M.vtsswgs, M.vtm0 * M.njtsswgstemp, W.vbs_jct); t5 = r.a; d5 = r.b; }
+    { const Real2 r = tat_term_v(M.vtsswgd, M.vtm0 * M.njtsswgdtemp, W.vbd_jct); t6 = r.a; d6 = r.b; }
     W.gbs += I.SjctTempRevSatCur * d1 + I.SswTempRevSatCur * d3 + I.SswgTempRevSatCur * d5;
     W.cbs -= I.SjctTempRevSatCur * (t1 - 1.0) + I.SswTempRevSatCur * (t3 - 1.0)
            + I.SswgTempRevSatCur * (t5 - 1.0);
@@ -316,8 +324,8 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   // ---- poly gate depletion -------------------------------------------------
   T0 = I.vfb + P.phi;
   T1 = (M.mtrlMod == 0) ? kEpsSi : M.epsrgate * kEps0B4;
-  poly_depletion(T0, P.ngate, T1, M.coxe, W.vgs, W.vgs_eff, W.dvgs_eff_dvg);
-  poly_depletion(T0, P.ngate, T1, M.coxe, W.vgd, W.vgd_eff, W.dvgd_eff_dvg);
+  { const Real2 r = poly_depletion_v(T0, P.ngate, T1, M.coxe, W.vgs); W.vgs_eff = r.a; W.dvgs_eff_dvg = r.b; }
+  { const Real2 r = poly_depletion_v(T0, P.ngate, T1, M.coxe, W.vgd); W.vgd_eff = r.a; W.dvgd_eff_dvg = r.b; }
   real Vgs_eff, dVgs_eff_dVg;
   if (W.mode > 0) { Vgs_eff = W.vgs_eff; dVgs_eff_dVg = W.dvgs_eff_dvg; }
   else { Vgs_eff = W.vgd_eff; dVgs_eff_dVg = W.dvgd_eff_dvg; }
@@ -1176,21 +1184,19 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     if (M.gidlMod == 0) {
       T1 = (M.mtrlMod == 0) ? (W.vds - W.vgs_eff - P.egidl) / T0
                             : (W.vds - W.vgs_eff - P.egidl + P.vfbsd) / T0;
-      gidl_mod0(T0, T1, W.dvgs_eff_dvg, P.agidl, P.bgidl, P.cgidl, P.weffCJ, W.vbd,
-                W.Igidl, W.ggidld, W.ggidlg, W.ggidlb);
+      { const Real4 r = gidl_mod0_v(T0, T1, W.dvgs_eff_dvg, P.agidl, P.bgidl, P.cgidl, P.weffCJ, W.vbd); W.Igidl = r.a; W.ggidld = r.b; W.ggidlg = r.c; W.ggidlb = r.d; }
       T1 = (M.mtrlMod == 0) ? (-W.vds - W.vgd_eff - P.egisl) / T0
                             : (-W.vds - W.vgd_eff - P.egisl + P.vfbsd) / T0;
-      gidl_mod0(T0, T1, W.dvgd_eff_dvg, P.agisl, P.bgisl, P.cgisl, P.weffCJ, W.vbs,
-                W.Igisl, W.ggisls, W.ggislg, W.ggislb);
+      { const Real4 r = gidl_mod0_v(T0, T1, W.dvgd_eff_dvg, P.agisl, P.bgisl, P.cgisl, P.weffCJ, W.vbs); W.Igisl = r.a; W.ggisls = r.b; W.ggislg = r.c; W.ggislb = r.d; }
     } else {
       T1 = (M.mtrlMod == 0) ? (-W.vds - P.rgisl * W.vgd_eff - P.egisl) / T0
                             : (-W.vds - P.rgisl * W.vgd_eff - P.egisl + P.vfbsd) / T0;
-      gidl_mod1(T0, T1, P.rgisl, W.dvgd_eff_dvg, P.agisl, P.bgisl, P.cgisl, P.kgisl, P.fgisl,
-                P.weffCJ, W.vbs, M.gidlclamp, W.Igisl, W.ggisls, W.ggislg, W.ggislb);
+      { const Real4 r = gidl_mod1_v(T0, T1, P.rgisl, W.dvgd_eff_dvg, P.agisl, P.bgisl, P.cgisl, P.kgisl, P.fgisl,
+                P.weffCJ, W.vbs, M.gidlclamp); W.Igisl = r.a; W.ggisls = r.b; W.ggislg = r.c; W.ggislb = r.d; }
       T1 = (M.mtrlMod == 0) ? (W.vds - P.rgidl * W.vgs_eff - P.egidl) / T0
                             : (W.vds - P.rgidl * W.vgs_eff - P.egidl + P.vfbsd) / T0;
-      gidl_mod1(T0, T1, P.rgidl, W.dvgs_eff_dvg, P.agidl, P.bgidl, P.cgidl, P.kgidl, P.fgidl,
-                P.weffCJ, W.vbd, M.gidlclamp, W.Igidl, W.ggidld, W.ggidlg, W.ggidlb);
+      { const Real4 r = gidl_mod1_v(T0, T1, P.rgidl, W.dvgs_eff_dvg, P.agidl, P.bgidl, P.cgidl, P.kgidl, P.fgidl,
+                P.weffCJ, W.vbd, M.gidlclamp); W.Igidl = r.a; W.ggidld = r.b; W.ggidlg = r.c; W.ggidlb = r.d; }
     }
     (void)voff;
   }

@@ -156,6 +156,7 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (n == "b4_threads" && (value == 0 || (value >= 64 && value <= 512))) { ctx->b4_threads = value; return 0; }
   if (n == "b4_uniform" && (value == 0 || value == 1)) { ctx->b4_uniform = value; return 0; }
   if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
+  if (n == "b4_spec" && (value == 0 || value == 1)) { ctx->b4_spec = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
 
@@ -498,15 +499,25 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
         br.start = g.run_start[r]; br.count = g.run_count[r];
       }
       g.packs_valid = true;
+      g.spec_ok = true;
+      for (size_t r = 0; r < g.run_start.size(); ++r) {
+        const B4Model &M = ctx->h_models[g.run_model[r]];
+        int k = 0;
+#define CHK(name) if (kSpecModes[k] != -2 && M.name != kSpecModes[k]) g.spec_ok = false; ++k;
+        XB_B4_MODEL_I(CHK)
+#undef CHK
+      }
     }
-    // b4_threads == 0: pick the block shape from the group size (measured on B200 at the C2 operating
-    // point, profiles/r01_b4_kernel_variants_v2.json): up to ~300k instances the run is a few waves long and
-    // 12 warps per SM (128 x 3, 168 registers) finish soonest; beyond that 8 warps per SM without any
-    // spill (128 x 2, 255 registers) deliver the most evaluations per second
+    // b4_threads == 0: pick the block shape (measured on B200 at the C2 operating point,
+    // profiles/r01_b4_kernel_variants_v3.json).  Once the kernel image is compact enough for the instruction
+    // caches, 12 warps per SM (128 x 3, 168 registers) beat 8 warps without spills; the mode-specialised build
+    // on large groups gains a little more from 16 warps (128 x 4).
+    const bool spec = ctx->b4_spec && uniform && g.spec_ok && ctx->b4_arith == 2 && !lockstep && !g.general;
     int threads = ctx->b4_threads, minblocks = ctx->b4_minblocks;
-    if (threads == 0) { threads = 128; minblocks = g.n <= 300000 ? 3 : 2; }
+    if (threads == 0) { threads = 128; minblocks = (spec && g.n > 300000) ? 4 : 3; }
     const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, threads, minblocks,
-                                   uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream);
+                                   uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream,
+                                   spec);
     if (nl < 0) return fail(ctx, 19, "unsupported BSIM4 launch shape (b4_threads, b4_minblocks)");
     ctx->launches += nl;
   }

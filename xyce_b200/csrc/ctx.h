@@ -24,6 +24,7 @@ struct XgHostGroup {
   std::vector<int32_t> run_model, run_size, run_start, run_count;
   std::vector<xb::b4::BinPack> packs;
   bool packs_valid = false;
+  bool spec_ok = false;            // every run's model card carries the mode set of the specialised kernel build
 };
 
 // groups of the small compact models (diode, MOSFET level 1, BJT, ADMS-shaped rlc): flat per-instance records
@@ -57,7 +58,7 @@ struct xgpu_ctx {
   long long launches = 0;
   // BSIM4 kernel variant (xgpu_set_option): arithmetic 0 strict / 1 fma / 2 fma + reciprocal division,
   // block shape, uniform-record kernel on/off, lock-step barriers 0/1
-  int b4_arith = 2, b4_threads = 0 /* auto */, b4_minblocks = 2, b4_uniform = 1, b4_lockstep = 0;
+  int b4_arith = 2, b4_threads = 0 /* auto */, b4_minblocks = 2, b4_uniform = 1, b4_lockstep = 0, b4_spec = 1;
 
   int n = 0;
   int64_t nnz = 0;

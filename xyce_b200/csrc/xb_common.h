@@ -23,6 +23,15 @@
 #ifndef XB_REAL
 #define XB_REAL double
 #endif
+// Helpers that are called from several places of an evaluator (junction diode for source and drain, limiters,
+// GIDL / GISL, ...): real functions in the fast device build -- the second call finds the code in the instruction
+// caches -- and inlined everywhere else (strict builds, host mirror).
+// They take and return values only (no references into the caller's frame).
+#if defined(__CUDACC__) && defined(XB_ARITH) && XB_ARITH == 2 && !defined(XB_HELPERS_INLINE)
+#define XB_HELPER static __host__ __device__ __noinline__
+#else
+#define XB_HELPER XB_HD
+#endif
 
 // Lock-step builds (XB_LOCKSTEP=1, device only) put a block-wide barrier between the sections of the
 // large evaluators so that all warps of a block execute the same ~1-2k instruction window and share
@@ -43,6 +52,8 @@
 namespace xb {
 
 using real = XB_REAL;
+struct Real2 { real a, b; };
+struct Real4 { real a, b, c, d; };
 XB_HD double to_double(double v) { return v; }
 
 // ---- physical constants (N_DEV_Const.h) -----------------------------------

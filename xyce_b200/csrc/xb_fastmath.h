@@ -46,7 +46,13 @@ __device__ __forceinline__ double div(double a, double b) {
   return fma(fma(-b, q, a), r, q);
 }
 
-__device__ __forceinline__ double exp(double x) {
+// exp / log / sqrt are real functions (not inlined): the evaluation kernel is bound by instruction delivery, and
+// one 40-instruction body that stays in the instruction caches beats 50 inlined copies (measured: C2 0.087 -> 0.063 ms)
+#ifndef XB_FM_INLINE
+#define XB_FM_INLINE __noinline__
+#endif
+static __device__ XB_FM_INLINE double sqrt(double x) { return ::sqrt(x); }
+static __device__ XB_FM_INLINE double exp(double x) {
   x = x < kExpK[3] ? kExpK[3] : x;          // NaN stays NaN (comparisons false)
   x = x > kExpK[4] ? kExpK[4] : x;
   const double shifter = 6755399441055744.0;              // 1.5 * 2^52
@@ -66,7 +72,7 @@ __device__ __forceinline__ double exp(double x) {
   return p * s1 * s2;
 }
 
-__device__ __forceinline__ double log(double x) {
+static __device__ XB_FM_INLINE double log(double x) {
   if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return ::log(x);   // 0, < 0, denormal, inf, NaN
   int hi = __double2hiint(x);
   const int lo = __double2loint(x);

@@ -46,11 +46,12 @@ struct FastDivPolicy {
     return a / b;
 #endif
   }
-  static XBR_HD double sqrt_(double a) { return ::sqrt(a); }
 #if defined(__CUDA_ARCH__)
+  static XBR_HD double sqrt_(double a) { return fm::sqrt(a); }
   static XBR_HD double exp_(double a) { return fm::exp(a); }
   static XBR_HD double log_(double a) { return fm::log(a); }
 #else
+  static XBR_HD double sqrt_(double a) { return ::sqrt(a); }
   static XBR_HD double exp_(double a) { return ::exp(a); }
   static XBR_HD double log_(double a) { return ::log(a); }
 #endif
