@@ -483,6 +483,13 @@ void xref_b4_export(void *h, int idx, double *model_d, int *model_i, double *siz
 #define PUT(n) inst_d[k++] = in.n;
   k = 0; XB_B4_INST_D(PUT)
 #undef PUT
+  // toxp / coxp became instance members in 4.8.2 (N_DEV_MOSFET_B4.h:584-585); the 4.7.0 and 4.6.1 evaluators
+  // read the model's (N_DEV_MOSFET_B4p70.C:4527, :4537): an adaptor fills the instance record from there
+  if (mo.versionDouble < 4.8) {
+#define PUT(n) if (!std::strcmp(#n, "toxp")) inst_d[k] = mo.toxp; if (!std::strcmp(#n, "coxp")) inst_d[k] = mo.coxp; ++k;
+    k = 0; XB_B4_INST_D(PUT)
+#undef PUT
+  }
 #define PUT(n) inst_i[k++] = (int)in.n;
   k = 0; XB_B4_INST_I(PUT)
 #undef PUT

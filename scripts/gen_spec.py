@@ -16,5 +16,6 @@ for f in os.listdir(src):
         if f.startswith("bsim4_") and f.endswith(".h") and f not in ("bsim4_types.h",):
             for k, v in SPEC.items():
                 text = re.sub(r"\bM\.%s\b" % k, "(%d)" % v, text)
+            text = re.sub(r"\bM\.versionDouble\b", "(4.82)", text)      # the specialised build is the 4.8.2 evaluator
         open(os.path.join(out, f), "w").write(text)
 print(",".join("%s=%d" % kv for kv in sorted(SPEC.items())))

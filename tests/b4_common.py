@@ -35,6 +35,15 @@ VARIANTS = {
     "mtrl": (dict(MTRLMOD=1, EOT=1.7e-9, PHIG=4.2, EPSRGATE=11.7), dict(TNOIMOD=1)),
 }
 
+# the 4.7.0 and 4.6.1 evaluators (N_DEV_MOSFET_B4p70.C, N_DEV_MOSFET_B4p61.C) on the variants whose code differs
+for _base, _vers in (("default", (4.7, 4.61)), ("igc2", (4.7, 4.61)), ("gidl", (4.7, 4.61)), ("mob3", (4.61,)),
+                     ("mtrl", (4.7, 4.61)), ("pocket", (4.7, 4.61)), ("capmod0", (4.61,)),
+                     ("mob1", (4.61,)), ("rdsmod", (4.61,)), ("diomod0", (4.61,)), ("igc", (4.61,))):
+    for _v in _vers:
+        VARIANTS["%s_v%d" % (_base, round(_v * 100))] = tuple({**c, "VERSION": _v} for c in VARIANTS[_base])
+# mobMod 4-6 do not exist before 4.8 (the 4.7.0 code would read an unset VgsteffVth): high-k mobility on both cards
+VARIANTS["mob3_v470"] = (dict(MOBMOD=3, VERSION=4.7), dict(MOBMOD=3, VERSION=4.7))
+
 FLAG_NAMES = ["dcop", "tranop", "acop", "transient", "dcsweep", "initJct", "initFix", "initTran",
               "newtonIter", "locaEnabled", "artParameter", "voltageLimiter"]
 

@@ -32,3 +32,23 @@ def test_golden_covers_limiting_and_both_modes():
     # sanity of the fixture itself: limiter terms present, forward and reverse mode both exercised
     g = GOLD["default__tran_iter1"]
     assert np.any(g["ref_dFdxdVp"] != 0.0) and np.any(g["ref_dQdxdVp"] != 0.0)
+
+
+@pytest.mark.parametrize("key", ["igc2_v470__tran_iter1", "igc2_v461__tran_iter1",
+                                 "capmod0_v461__tran_iter1", "pocket_v461__tran_iter1"])
+def test_version_switch_matters_on_the_versioned_fixtures(host_mirror, key):
+    # evaluating a 4.7.0 / 4.6.1 fixture (N_DEV_MOSFET_B4p70.C, N_DEV_MOSFET_B4p61.C outputs) as if it were 4.8.2
+    # must NOT reproduce the reference: otherwise the fixture would not exercise the version branches
+    g = dict(GOLD[key])
+    md = g["rec_model_d"].copy()
+    col = [j for j in range(md.shape[1]) if np.all(np.isin(md[:, j], (4.7, 4.61)))]
+    assert len(col) == 1
+    md[:, col[0]] = 4.82
+    g["rec_model_d"] = md
+    _, asm = host_mirror_case(host_mirror, g)
+    worst = 0.0
+    for k in ("f", "q", "dFdx", "dQdx"):
+        want = g["ref_" + k]
+        scale = 1e-3 * np.max(np.abs(want)) if np.any(want) else 1e-300
+        worst = max(worst, rel_err(asm[k], want, scale))
+    assert worst > 1e-9, worst

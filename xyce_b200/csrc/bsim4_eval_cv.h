@@ -51,6 +51,7 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
   real T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, tmp, tmp1;
   const bool charge_needed = S.tranopFlag || S.acopFlag || S.transientFlag || S.dcsweepFlag;
   W.ChargeComputationNeeded = charge_needed ? 1 : 0;
+  const bool kV47 = M.versionDouble >= 4.7;      // 4.6.1 differences of the capMod = 0 branch
 
   const real Vds = C.Vds, Vbs = C.Vbs, Vbseff = C.Vbseff, dVbseff_dVb = C.dVbseff_dVb;
   const real Phis = C.Phis, dPhis_dVb = C.dPhis_dVb, sqrtPhis = C.sqrtPhis, dsqrtPhis_dVb = C.dsqrtPhis_dVb;
@@ -76,11 +77,11 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
     W.gtau = 0.0;
   } else if (M.capMod == 0) {
     if (Vbseff < 0.0) { VbseffCV = Vbs; dVbseffCV_dVb = 1.0; }
-    else { VbseffCV = P.phi - Phis; dVbseffCV_dVb = -dPhis_dVb * dVbseff_dVb; }
+    else { VbseffCV = P.phi - Phis; dVbseffCV_dVb = kV47 ? -dPhis_dVb * dVbseff_dVb : -dPhis_dVb; }
     Vfb = P.vfbcv;
     Vth = Vfb + P.phi + P.k1ox * sqrtPhis;
     Vgst = Vgs_eff - Vth;
-    dVth_dVb = P.k1ox * dsqrtPhis_dVb * dVbseff_dVb;
+    dVth_dVb = kV47 ? P.k1ox * dsqrtPhis_dVb * dVbseff_dVb : P.k1ox * dsqrtPhis_dVb;
     CoxWL = M.coxe * P.weffCV * P.leffCV * I.nf;
     const real Arg1 = Vgs_eff - VbseffCV - Vfb;
     if (Arg1 <= 0.0) {            // accumulation
@@ -112,10 +113,18 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
       const real One_Third_CoxWL = CoxWL / 3.0;
       const real Two_Third_CoxWL = 2.0 * One_Third_CoxWL;
       const real AbulkCV = Abulk0 * P.abulkCVfactor;
-      const real dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb * dVbseff_dVb;
-      const real dVdsat_dVg = 1.0 / AbulkCV;
-      Vdsat = Vgst * dVdsat_dVg;
-      const real dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) * dVdsat_dVg;
+      real dAbulkCV_dVb, dVdsat_dVg, dVdsat_dVb;
+      if (kV47) {
+        dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb * dVbseff_dVb;
+        dVdsat_dVg = 1.0 / AbulkCV;
+        Vdsat = Vgst * dVdsat_dVg;
+        dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) * dVdsat_dVg;
+      } else {      // N_DEV_MOSFET_B4p61.C capMod = 0 inversion branch
+        dAbulkCV_dVb = P.abulkCVfactor * dAbulk0_dVb;
+        Vdsat = Vgst / AbulkCV;
+        dVdsat_dVg = dVgs_eff_dVg / AbulkCV;
+        dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) / AbulkCV;
+      }
       real Alphaz, dAlphaz_dVg, dAlphaz_dVb;
       if (M.xpart > 0.5) {        // 0/100 partition
         if (Vdsat <= Vds) {
@@ -221,7 +230,8 @@ XB_HD void stage_cv(const SolverFlags &S, const B4Model &M, const B4Size &P,
           qbulk = -(qgate - T4 * T7);
           T7 *= T9;
           T0 = 4.0 * T4 * (1.0 - T5);
-          T12 = (-T7 * dAlphaz_dVg - T0 * dVdsat_dVg) * dVgs_eff_dVg - W.cdgb;
+          T12 = kV47 ? (-T7 * dAlphaz_dVg - T0 * dVdsat_dVg) * dVgs_eff_dVg - W.cdgb
+                     : (-T7 * dAlphaz_dVg - W.cdgb - T0 * dVdsat_dVg) * dVgs_eff_dVg;
           T11 = -T7 * dAlphaz_dVb - T10 - T0 * dVdsat_dVb;
           T10 = -4.0 * T4 * (T2 - 0.5 + 0.5 * T5) - W.cddb;
           tmp = -(T10 + T11 + T12);

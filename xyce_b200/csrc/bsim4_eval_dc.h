@@ -114,13 +114,15 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   real dT8_dVg, dT8_dVd, dT8_dVb, dT9_dVg, dT9_dVd, dT9_dVb;
   real dT10_dVg, dT10_dVd, dT10_dVb;
   const real gmin = S.gmin;
+  const bool kV48 = M.versionDouble >= 4.8;
+  const bool kV47 = M.versionDouble >= 4.7;      // 4.6.1 evaluator differences (N_DEV_MOSFET_B4p61.C vs B4p70.C)
 
   XB_SYNC_POINT(2);
   // ---- source / drain bulk junction diodes --------------------------------
   {
     JctPar js;
     js.Nvtm = M.vtm * M.SjctEmissionCoeff;
-    if ((I.Aseff <= 0.0) && (I.Pseff <= 0.0)) js.Isat = 0.0;
+    if ((I.Aseff <= 0.0) && (I.Pseff <= 0.0)) js.Isat = kV47 ? 0.0 : 1.0e-14;      // B4p61.C: 1.0e-14
     else js.Isat = I.Aseff * M.SjctTempSatCurDensity + I.Pseff * M.SjctSidewallTempSatCurDensity
                  + P.weffCJ * I.nf * M.SjctGateSidewallTempSatCurDensity;
     js.xjbv = M.xjbvs; js.bv = M.bvs; js.XExpBV = I.XExpBVS;
@@ -130,7 +132,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
 
     JctPar jd;
     jd.Nvtm = M.vtm * M.DjctEmissionCoeff;
-    if ((I.Adeff <= 0.0) && (I.Pdeff <= 0.0)) jd.Isat = 0.0;
+    if ((I.Adeff <= 0.0) && (I.Pdeff <= 0.0)) jd.Isat = kV47 ? 0.0 : 1.0e-14;
     else jd.Isat = I.Adeff * M.DjctTempSatCurDensity + I.Pdeff * M.DjctSidewallTempSatCurDensity
                  + P.weffCJ * I.nf * M.DjctGateSidewallTempSatCurDensity;
     jd.xjbv = M.xjbvd; jd.bv = M.bvd; jd.XExpBV = I.XExpBVD;
@@ -309,7 +311,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVth_dVd -= dDITS_Sft_dVd;
     dVth_dVb -= dDITS_Sft_dVb;
   }
-  if (!((P.dvtp4 == 0.0) || (P.dvtp2factor == 0.0))) {
+  if (kV47 && !((P.dvtp4 == 0.0) || (P.dvtp2factor == 0.0))) {      // DITS_SFT2: 4.7 and later
     T1 = 2.0 * P.dvtp4 * Vds;
     dexp(T1, T0, T10);
     const real DITS_Sft2 = P.dvtp2factor * (T0 - 1) / (T0 + 1);
@@ -414,7 +416,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     Rds = P.rdswmin + T3 * T4;
     dRds_dVg = T4 * dT3_dVg;
     dRds_dVb = T4 * dT3_dVb;
-    W.grdsw = (Rds > 0.0) ? 1.0 / Rds * I.nf : 0.0;
+    W.grdsw = (Rds > 0.0) ? (kV47 ? 1.0 / Rds * I.nf : 1.0 / Rds) : 0.0;      // no nf factor in B4p61.C
   }
 
   XB_SYNC_POINT(2);
@@ -471,7 +473,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   XB_SYNC_POINT(1);
   // ---- mobility ---------------------------------------------------------------
   real Denomi, dDenomi_dVg, dDenomi_dVd, dDenomi_dVb;
-  if (M.mtrlMod && (M.mtrlCompatMod == 0))
+  if (M.mtrlMod && (!kV47 || M.mtrlCompatMod == 0))      // mtrlCompatMod: 4.7 and later
     T14 = 2.0 * M.dtype * (M.phig - M.easub - 0.5 * M.Eg0 + 0.45);
   else
     T14 = 0.0;
@@ -510,7 +512,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dDenomi_dVd = T13 * dVth_dVd;
     dDenomi_dVb = T13 * dVth_dVb + P.uc * T4;
     dDenomi_dVg += T7;
-  } else if (M.mobMod == 2) {
+  } else if (M.mobMod == 2 || !kV47) {      // B4p61.C: plain else
     T0 = (Vgsteff + I.vtfbphi1) / toxe;
     T1 = exp(P.eu * log(T0));
     dT1_dVg = T1 * P.eu / T0 / toxe;
@@ -528,7 +530,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     T13 = 2.0 * (T11 + T8);
     dDenomi_dVd = T13 * dVth_dVd;
     dDenomi_dVb = T13 * dVth_dVb + T1 * P.uc;
-  } else if (M.mobMod == 4) {
+  } else if (M.mobMod == 4 && kV48) {      // mobMod 4-6: 4.8 and later (B4p82.C:4266-4319)
     T0 = Vgsteff + I.vtfbphi1 - T14;
     T2 = P.ua + P.uc * Vbseff;
     T3 = T0 / toxe;
@@ -543,7 +545,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dDenomi_dVd = 0.0;
     dDenomi_dVb = P.uc * T3;
     dDenomi_dVg += T7;
-  } else if (M.mobMod == 5) {
+  } else if (M.mobMod == 5 && kV48) {
     T0 = Vgsteff + I.vtfbphi1 - T14;
     T2 = 1.0 + P.uc * Vbseff;
     T3 = T0 / toxe;
@@ -559,7 +561,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dDenomi_dVd = 0.0;
     dDenomi_dVb = P.uc * T4;
     dDenomi_dVg += T7;
-  } else if (M.mobMod == 6) {
+  } else if (M.mobMod == 6 && kV48) {
     T0 = (Vgsteff + I.vtfbphi1) / toxe;
     T1 = exp(P.eu * log(T0));
     dT1_dVg = T1 * P.eu / T0 / toxe;
@@ -756,7 +758,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dEsatL_dVd *= T10; dEsatL_dVd += EsatL * dT10_dVd;
     dEsatL_dVb *= T10; dEsatL_dVb += EsatL * dT10_dVb;
     EsatL *= T10;
-    Esat = EsatL / Leff;
+    if (kV47) Esat = EsatL / Leff;      // not in B4p61.C
   }
   W.EsatL = EsatL;
 
@@ -946,7 +948,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dVADITS_dVg = dVADITS_dVd = 0;
   }
   real VASCBE, dVASCBE_dVg, dVASCBE_dVd, dVASCBE_dVb;
-  if ((P.pscbe2 > 0.0) && (P.pscbe1 >= 0.0)) {
+  if ((P.pscbe2 > 0.0) && (!kV47 || P.pscbe1 >= 0.0)) {
     if (diffVds > P.pscbe1 * P.litl / kExpThr) {
       T0 = P.pscbe1 * P.litl / diffVds;
       VASCBE = Leff * exp(T0) / P.pscbe2;
@@ -1080,7 +1082,10 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   W.cdrain = cdrain;
   W.gds = Gds; W.gm = Gm; W.gmbs = Gmb;
   W.IdovVds = Ids;
-  if (W.IdovVds <= M.idovvdsc) W.IdovVds = M.idovvdsc;
+  {   // the floor became a model parameter in 4.8 (N_DEV_MOSFET_B4p82.C:4972; 1.0e-9 in B4p70.C / B4p61.C)
+    const real floor_ = (M.versionDouble >= 4.8) ? M.idovvdsc : 1.0e-9;
+    if (W.IdovVds <= floor_) W.IdovVds = floor_;
+  }
 
   XB_SYNC_POINT(2);
   // ---- bias-dependent intrinsic-input (gate) resistance ---------------------------------------
@@ -1181,7 +1186,9 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
   {
     T0 = (M.mtrlMod == 0) ? 3.0 * toxe : M.epsrsub * toxe / epsrox;
     const real voff = (M.mtrlMod == 0) ? 0.0 : P.vfbsd;
-    if (M.gidlMod == 0) {
+    // the T4 clamp of the gidlMod = 1 branch exists from 4.8 on (B4p82.C:5233, :5290; not in B4p70.C)
+    const real gidlclamp = (M.versionDouble >= 4.8) ? M.gidlclamp : 1.7976931348623157e308;
+    if (M.gidlMod == 0 || !kV47) {      // gidlMod: 4.7 and later
       T1 = (M.mtrlMod == 0) ? (W.vds - W.vgs_eff - P.egidl) / T0
                             : (W.vds - W.vgs_eff - P.egidl + P.vfbsd) / T0;
       { const Real4 r = gidl_mod0_v(T0, T1, W.dvgs_eff_dvg, P.agidl, P.bgidl, P.cgidl, P.weffCJ, W.vbd); W.Igidl = r.a; W.ggidld = r.b; W.ggidlg = r.c; W.ggidlb = r.d; }
@@ -1192,11 +1199,11 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       T1 = (M.mtrlMod == 0) ? (-W.vds - P.rgisl * W.vgd_eff - P.egisl) / T0
                             : (-W.vds - P.rgisl * W.vgd_eff - P.egisl + P.vfbsd) / T0;
       { const Real4 r = gidl_mod1_v(T0, T1, P.rgisl, W.dvgd_eff_dvg, P.agisl, P.bgisl, P.cgisl, P.kgisl, P.fgisl,
-                P.weffCJ, W.vbs, M.gidlclamp); W.Igisl = r.a; W.ggisls = r.b; W.ggislg = r.c; W.ggislb = r.d; }
+                P.weffCJ, W.vbs, gidlclamp); W.Igisl = r.a; W.ggisls = r.b; W.ggislg = r.c; W.ggislb = r.d; }
       T1 = (M.mtrlMod == 0) ? (W.vds - P.rgidl * W.vgs_eff - P.egidl) / T0
                             : (W.vds - P.rgidl * W.vgs_eff - P.egidl + P.vfbsd) / T0;
       { const Real4 r = gidl_mod1_v(T0, T1, P.rgidl, W.dvgs_eff_dvg, P.agidl, P.bgidl, P.cgidl, P.kgidl, P.fgidl,
-                P.weffCJ, W.vbd, M.gidlclamp); W.Igidl = r.a; W.ggidld = r.b; W.ggidlg = r.c; W.ggidlb = r.d; }
+                P.weffCJ, W.vbd, gidlclamp); W.Igidl = r.a; W.ggidld = r.b; W.ggidlg = r.c; W.ggidlb = r.d; }
     }
     (void)voff;
   }
@@ -1268,7 +1275,11 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       Vaux = T0 * log(1.0 + ExpVxNVt);
       dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
       if (M.igcMod == 1) { dVaux_dVd = 0.0; dVaux_dVb = 0.0; }
-      else if (M.igcMod == 2) { dVaux_dVd = -dVaux_dVg * dVth_dVd; dVaux_dVb = -dVaux_dVg * dVth_dVb; }
+      else if (M.igcMod == 2) {
+        // 4.8: -dVaux_dVg (B4p82.C:5423); 4.7 / 4.6.1: -dVgs_eff_dVg (B4p70.C, B4p61.C same place)
+        const real k_ = (M.versionDouble >= 4.8) ? dVaux_dVg : dVgs_eff_dVg;
+        dVaux_dVd = -k_ * dVth_dVd; dVaux_dVb = -k_ * dVth_dVb;
+      }
       dVaux_dVg *= dVgs_eff_dVg;
     }
     T2 = Vgs_eff * Vaux;
@@ -1298,7 +1309,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
       Pigcd = P.pigcd;
       dPigcd_dVg = dPigcd_dVd = dPigcd_dVb = 0.0;
     } else {
-      T11 = -P.Bechvb;
+      T11 = kV47 ? -P.Bechvb : P.Bechvb * toxe;      // B4p61.C (same place)
       T12 = Vgsteff + 1.0e-20;
       T13 = T11 / T12 / T12;
       T14 = -T13 / T12;
@@ -1312,6 +1323,7 @@ XB_HD void stage_dc(const SolverFlags &S, const B4Model &M, const B4Size &P,
     dT7_dVd = -Vdseff * dPigcd_dVd - Pigcd * dVdseff_dVd + dT7_dVg * dVgsteff_dVd;
     dT7_dVb = -Vdseff * dPigcd_dVb - Pigcd * dVdseff_dVb + dT7_dVg * dVgsteff_dVb;
     dT7_dVg *= dVgsteff_dVg;
+    if (M.versionDouble < 4.8) dT7_dVb *= dVbseff_dVb;      // dropped in 4.8 (B4p82.C:5482)
     T8 = T7 * T7 + 2.0e-4;
     dT8_dVg = 2.0 * T7;
     dT8_dVd = dT8_dVg * dT7_dVd;

@@ -506,6 +506,7 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
 #define CHK(name) if (kSpecModes[k] != -2 && M.name != kSpecModes[k]) g.spec_ok = false; ++k;
         XB_B4_MODEL_I(CHK)
 #undef CHK
+        if (!(M.versionDouble >= 4.8)) g.spec_ok = false;      // the specialised build is the 4.8.2 evaluator
       }
     }
     // b4_threads == 0: pick the block shape (measured on B200 at the C2 operating point,
