@@ -161,14 +161,18 @@ int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colin
  *   :1191-1397) inside the variable-step trapezoid of OneStep (N_TIA_OneStep.C) with LTE step control.
  *   Outputs: accepted time points and probe waveforms, one record {t, h, newton iterations, order, status}
  *   per step attempt, and counters stats16 = {accepted, rejected, newton iterations, Jacobian loads,
- *   residual loads, linear solves, LU analyses, LU refactors, time points, attempts, driver rc}. */
+ *   residual loads, linear solves, LU analyses, LU refactors, time points, attempts, driver rc,
+ *   Newton iterations of the DC operating point, its convergence status}. */
 typedef struct xgpu_tran_params {
   double tstop, tstep, delmax;
   int maxNewtonStep;                 /* 0 = reference default (20) */
   double deltaXTol, absTol, relTol, RHSTol;   /* 0 = reference defaults 0.33, 1e-6, 1e-2, 1e-2 */
   double relErrorTol, absErrorTol;   /* 0 = 1e-3, 1e-6 */
-  int maxOrder;                      /* 0 = 2 (trapezoid) */
+  int maxOrder;                      /* 0 = 2 */
   int maxSteps;
+  int method;                        /* .OPTIONS TIMEINT METHOD: 0 / 7 = trapezoid (OneStep, N_TIA_OneStep.C), 8 = Gear (N_TIA_Gear12.C) */
+  int dcop;                          /* 0 = start from x0 (.TRAN ... NOOP / UIC); 1 = DC operating point from x0 first
+                                        (NoTimeIntegration + DampedNewton DC_OP defaults, N_TIA_NoTimeIntegration.C:161-173, :291-298) */
 } xgpu_tran_params;
 int xgpu_linear_set(xgpu_ctx *ctx, int nG, const int32_t *g_row, const int32_t *g_col, const double *g_val,
                     int nC, const int32_t *c_row, const int32_t *c_col, const double *c_val);

@@ -629,7 +629,7 @@ struct RefBackend {
   bool load_rhs(const xb::sim::Flags &fl, double time) {
     SolverState &s = c->solState;
     s.dcopFlag = fl.dcop; s.tranopFlag = fl.tranop; s.transientFlag = fl.transient; s.initTranFlag_ = fl.initTran;
-    s.newtonIter = fl.newtonIter; s.initJctFlag_ = fl.initJct; s.currTimeStep_ = fl.currTimeStep;
+    s.newtonIter = fl.newtonIter; s.initJctFlag_ = fl.initJct; s.initFixFlag = fl.initFix; s.currTimeStep_ = fl.currTimeStep;
     std::copy(v[xb::sim::vNextSol].begin(), v[xb::sim::vNextSol].end(), c->sol.begin());
     c->sol[c->n] = 0.0;
     for (auto *q : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(q->begin(), q->end(), 0.0);
@@ -674,14 +674,27 @@ struct RefBackend {
     for (auto &r : c->insts) all = all && r.inst->isConverged();
     return all;
   }
-  void residual_and_norms(double inv_h, double fs, bool order2, bool limiter, double qlim_coef, xb::sim::NewtonNorms &out) {
+  void residual_and_norms(const xb::sim::ResidualForm &f, xb::sim::NewtonNorms &out) {
     using namespace xb::sim;
-    axpby(vRHS, 1.0, vQ, -1.0, vQh0);
-    axpby(vTmp, fs, vF, -fs, vB);
-    axpby(vRHS, inv_h, vRHS, 1.0, vTmp);
-    if (order2) axpy(vRHS, 0.5, vQh2);
-    scale(vRHS, -1.0);
-    if (limiter) { axpy(vRHS, qlim_coef, vQlim); axpy(vRHS, fs, vFlim); }
+    if (f.form == 0) {            // OneStep::obtainResidual (N_TIA_OneStep.C:219-281)
+      axpby(vRHS, 1.0, vQ, -1.0, vQh0);
+      axpby(vTmp, f.fs, vF, -f.fs, vB);
+      axpby(vRHS, f.inv_h, vRHS, 1.0, vTmp);
+      if (f.order2) axpy(vRHS, 0.5, vQh2);
+      scale(vRHS, -1.0);
+      if (f.limiter) { axpy(vRHS, f.qlim_coef, vQlim); axpy(vRHS, f.fs, vFlim); }
+    } else if (f.form == 1) {     // Gear12::obtainResidual (N_TIA_Gear12.C:208-262)
+      axpby(vRHS, f.a0, vQ, f.a1, vQh0);
+      if (f.order2) axpy(vRHS, f.a2, vQh1);
+      axpby(vTmp, 1.0, vF, -1.0, vB);
+      axpby(vRHS, f.inv_h, vRHS, 1.0, vTmp);
+      scale(vRHS, -1.0);
+      if (f.limiter) { axpy(vRHS, f.qlim_coef, vQlim); axpy(vRHS, 1.0, vFlim); }
+    } else {                      // NoTimeIntegration::obtainResidual (N_TIA_NoTimeIntegration.C:161-173)
+      axpby(vRHS, 1.0, vF, -1.0, vB);
+      scale(vRHS, -1.0);
+      if (f.limiter) axpy(vRHS, 1.0, vFlim);
+    }
     out.rhs_norm2 = norm2(vRHS);
     out.rhs_norm_inf = norm_inf(vRHS);
     out.dx_wmax = wmax_norm(vDX, vSolWt);
@@ -695,8 +708,8 @@ struct RefBackend {
 
 extern "C" {
 
-// params: tstop, tstep, delmax.  Linear part as COO (G, C), sources {row, scale, type, p[7]}.
-int xref_tran_run(void *h, const double *params3, const double *x0, int nG, const int *gr, const int *gc, const double *gv,
+// params: tstop, tstep, delmax, method (0 / 7 trapezoid, 8 Gear), dcop (0 / 1).  Linear part as COO (G, C), sources {row, scale, type, p[7]}.
+int xref_tran_run(void *h, const double *params5, const double *x0, int nG, const int *gr, const int *gc, const double *gv,
                   int nC, const int *cr, const int *cc, const double *cv, int ns, const int *srow, const double *sscale,
                   const int *stype, const double *sp7, int n_probes, const int *probes, int max_out, int *n_out,
                   double *times, double *wave, int max_steps, int *n_steps, double *step_info5, double *stats16) {
@@ -717,7 +730,9 @@ int xref_tran_run(void *h, const double *params3, const double *x0, int nG, cons
   std::copy(x0, x0 + c->n, B.v[xb::sim::vCurrSol].begin());
   c->solState.transientFlag = true;
   xb::sim::TranParams P;
-  P.tstop = params3[0]; P.tstep = params3[1]; P.delmax = params3[2];
+  P.tstop = params5[0]; P.tstep = params5[1]; P.delmax = params5[2];
+  if ((int)params5[3] == 8) P.method = 8;
+  P.dcop = params5[4] != 0.0;
   xb::sim::TransientDriver<RefBackend> drv(B, P);
   const int rc = drv.run();
   *n_out = std::min((int)B.times.size(), max_out);
@@ -725,7 +740,7 @@ int xref_tran_run(void *h, const double *params3, const double *x0, int nG, cons
   *n_steps = std::min((int)drv.steps.size(), max_steps);
   for (int i = 0; i < *n_steps; ++i) { const auto &r = drv.steps[i]; double *o = step_info5 + 5 * (size_t)i; o[0] = r.t; o[1] = r.h; o[2] = r.newton_iters; o[3] = r.order; o[4] = r.status; }
   const auto &t = drv.stats;
-  const double st[16] = {(double)t.accepted, (double)t.rejected, (double)t.newton_total, (double)t.jacobian_loads, (double)t.residual_loads, (double)t.linear_solves, 0, 0, (double)B.times.size(), (double)drv.steps.size(), (double)rc, 0, 0, 0, 0, 0};
+  const double st[16] = {(double)t.accepted, (double)t.rejected, (double)t.newton_total, (double)t.jacobian_loads, (double)t.residual_loads, (double)t.linear_solves, 0, 0, (double)B.times.size(), (double)drv.steps.size(), (double)rc, (double)t.dcop_newton, (double)t.dcop_status, 0, 0, 0};
   std::memcpy(stats16, st, sizeof(st));
   if (B.M) spDestroy(B.M);
   return rc;

@@ -129,3 +129,61 @@ def assemble(per, lids, slot_row, slot_col, n, rowptr, colind):
             assert colind[k] == gc
             jf[k] += o["JF"][s]; jq[k] += o["JQ"][s]
     return dict(f=f, q=q, dFdxdVp=fl, dQdxdVp=ql, dFdx=jf, dQdx=jq)
+
+
+def mixed_netlist():
+    """BASELINE config 5 shape: diode clipper + Gummel-Poon common-emitter stage + MOSFET level 1 inverter + R, C, V in
+    one netlist, built on the reference's own Diode / BJT / MOSFET1 objects.  Returns (ref, lin, src, x0, probes)."""
+    import oracle_ref
+    IN, A, VCC, B, C, E, D, BR_IN, BR_CC = range(9)
+    ref = oracle_ref.RefCircuit(9)
+    dp = dict(DIODE_CARDS["rs_bv"]); dp.pop("LEVEL", None)
+    qt, qp = BJT_CARDS["basic"]; mt, mp = MOS1_CARDS["basic"]
+    ref.add_dev_model("d", "dmod", "D", 1, dp)
+    ref.add_dev_model("q", "qmod", qt, 1, dict(qp, RB=20.0, RC=5.0, RE=0.5))
+    ref.add_dev_model("m1", "mmod", mt, 1, dict(mp, RD=10.0, RS=10.0))
+    ref.add_dev_instance("d", "D:1", "dmod", [A, -1], dict(AREA=1.0))
+    ref.add_dev_instance("d", "D:2", "dmod", [-1, A], dict(AREA=1.0))
+    ref.add_dev_instance("q", "Q:1", "qmod", [C, B, E, -1], dict(AREA=1.0))
+    ref.add_dev_instance("m1", "M:1", "mmod", [D, A, -1, -1], dict(L=2e-6, W=2e-5, AD=2e-11, AS=2e-11, PD=2e-5, PS=2e-5))
+    g, c = [], []
+    def res(a, b, r):
+        gg = 1.0 / r
+        for (i, j, v) in ((a, a, gg), (a, b, -gg), (b, a, -gg), (b, b, gg)):
+            if i >= 0 and j >= 0: g.append((i, j, v))
+    def cap(a, b, v):
+        for (i, j, s) in ((a, a, v), (a, b, -v), (b, a, -v), (b, b, v)):
+            if i >= 0 and j >= 0: c.append((i, j, s))
+    def vsrc(node, br):
+        g.append((node, br, 1.0)); g.append((br, node, 1.0))
+    vsrc(IN, BR_IN); vsrc(VCC, BR_CC)
+    res(IN, A, 1e3); cap(IN, B, 1e-10); res(VCC, B, 47e3); res(B, -1, 10e3); res(VCC, C, 2.2e3); res(E, -1, 470.0)
+    res(VCC, D, 10e3); cap(D, -1, 1e-12); cap(C, -1, 2e-12)
+    lin = dict(g_row=np.array([t[0] for t in g], dtype=np.int32), g_col=np.array([t[1] for t in g], dtype=np.int32),
+               g_val=np.array([t[2] for t in g]), c_row=np.array([t[0] for t in c], dtype=np.int32),
+               c_col=np.array([t[1] for t in c], dtype=np.int32), c_val=np.array([t[2] for t in c]))
+    src = dict(row=np.array([BR_IN, BR_CC], dtype=np.int32), scale=np.ones(2), type=np.array([2, 0], dtype=np.int32),
+               params=np.array([[0.0, 2.0, 1e6, 0, 0, 0, 0], [5.0, 0, 0, 0, 0, 0, 0]]))
+    ref.add_pattern_entries(np.concatenate([lin["g_row"], lin["c_row"]]), np.concatenate([lin["g_col"], lin["c_col"]]))
+    ref.finalize()
+    x0 = np.zeros(ref.n); x0[VCC] = 5.0
+    probes = [IN, A, B, C, D, BR_CC]
+    return ref, lin, src, x0, probes
+
+
+def mixed_engine(ref, lin, src):
+    """The GPU engine for mixed_netlist(): records exported from the reference objects (what an adaptor uploads)."""
+    import xyce_b200
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    ex = [ref.diode_export(i) for i in (0, 1)]
+    eng.add_simple_group(1, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    for tid, key, idx in ((3, "q", 2), (2, "m1", 3)):
+        e = ref.dev_export(idx, key)
+        eng.add_simple_group(tid, np.array([e["rec"]]), [e["flags"]], np.array([e["lids"]]), [e["sto0"]], 1, [e["sta0"]], 1)
+    eng.set_linear(lin["g_row"], lin["g_col"], lin["g_val"], lin["c_row"], lin["c_col"], lin["c_val"])
+    eng.set_sources(src["row"], src["scale"], src["type"], src["params"])
+    eng.finalize()
+    return eng

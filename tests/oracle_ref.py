@@ -157,11 +157,11 @@ class RefCircuit:
         r, c = np.ascontiguousarray(rows, dtype=np.int32), np.ascontiguousarray(cols, dtype=np.int32)
         self.lib.xref_add_pattern_entries(self.h, len(r), iptr(r), iptr(c))
 
-    def tran_run(self, x0, tstop, tstep, probes, linear, sources, delmax=0.0, max_out=200000):
+    def tran_run(self, x0, tstop, tstep, probes, linear, sources, delmax=0.0, max_out=200000, method=0, dcop=0):
         """Transient run: tran_driver.h control flow around the reference device code + ksparse."""
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        par = f64([tstop, tstep, delmax])
+        par = f64([tstop, tstep, delmax, method, dcop])
         L = {k: (i32(v) if k.endswith(("row", "col")) else f64(v)) for k, v in linear.items()}
         S = dict(row=i32(sources["row"]), scale=f64(sources["scale"]), type=i32(sources["type"]), params=f64(sources["params"]))
         probes = i32(probes)
@@ -174,7 +174,7 @@ class RefCircuit:
                                     len(probes), iptr(probes), max_out, C.byref(n_out), dptr(times), dptr(wave),
                                     max_out, C.byref(n_steps), dptr(steps), dptr(stats))
         keys = ("accepted", "rejected", "newton_iters", "jacobian_loads", "residual_loads", "linear_solves",
-                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc")
+                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc", "dcop_newton_iters", "dcop_status")
         return dict(rc=rc, t=times[:n_out.value], wave=wave[:n_out.value], steps=steps[:n_steps.value],
                     stats=dict(zip(keys, stats.tolist())))
 

@@ -15,7 +15,8 @@ class TranParams(C.Structure):
     """Mirror of xgpu_tran_params; zeros select the reference defaults."""
     _fields_ = [("tstop", C.c_double), ("tstep", C.c_double), ("delmax", C.c_double), ("maxNewtonStep", C.c_int),
                 ("deltaXTol", C.c_double), ("absTol", C.c_double), ("relTol", C.c_double), ("RHSTol", C.c_double),
-                ("relErrorTol", C.c_double), ("absErrorTol", C.c_double), ("maxOrder", C.c_int), ("maxSteps", C.c_int)]
+                ("relErrorTol", C.c_double), ("absErrorTol", C.c_double), ("maxOrder", C.c_int), ("maxSteps", C.c_int),
+                ("method", C.c_int), ("dcop", C.c_int)]
 
 
 class SolverState(C.Structure):
@@ -248,7 +249,7 @@ class Engine:
         rc = self.lib.xgpu_tran_run(self.h, C.byref(tp), _dp(x0), len(probes), _ip(probes), max_out, C.byref(n_out),
                                     _dp(times), _dp(wave), max_out, C.byref(n_steps), _dp(steps), _dp(stats))
         keys = ("accepted", "rejected", "newton_iters", "jacobian_loads", "residual_loads", "linear_solves",
-                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc")
+                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc", "dcop_newton_iters", "dcop_status")
         return dict(rc=rc, t=times[:n_out.value], wave=wave[:n_out.value], steps=steps[:n_steps.value],
                     stats=dict(zip(keys, stats.tolist())),
                     error=self.lib.xgpu_last_error(self.h).decode() if rc else "")

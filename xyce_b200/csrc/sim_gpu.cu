@@ -84,7 +84,7 @@ struct GpuBackend {
 
   bool load_rhs(const sim::Flags &fl, double time) {
     ss.dcopFlag = fl.dcop; ss.tranopFlag = fl.tranop; ss.transientFlag = fl.transient; ss.initTranFlag = fl.initTran;
-    ss.newtonIter = fl.newtonIter; ss.initJctFlag = fl.initJct; ss.currTimeStep = fl.currTimeStep;
+    ss.newtonIter = fl.newtonIter; ss.initJctFlag = fl.initJct; ss.initFixFlag = fl.initFix; ss.currTimeStep = fl.currTimeStep;
     int rc = xgpu_update_state(ctx, v[sim::vNextSol], sta[0], sta[1], sto[0], sto[1], &ss);
     rc |= xgpu_load_vectors(ctx, v[sim::vF], v[sim::vQ], v[sim::vFlim], v[sim::vQlim], 0);
     // linear devices: F += G x, Q += C x  (N_LOA_CktLoader.C:774-782)
@@ -145,11 +145,12 @@ struct GpuBackend {
     cudaStreamSynchronize(s);
     return r != 0;
   }
-  void residual_and_norms(double inv_h, double fs, bool order2, bool limiter, double qlim_coef, sim::NewtonNorms &out) {
+  void residual_and_norms(const sim::ResidualForm &f, sim::NewtonNorms &out) {
     vec::ResidualArgs a{};
-    a.rhs = v[sim::vRHS]; a.q = v[sim::vQ]; a.qh0 = v[sim::vQh0]; a.f = v[sim::vF]; a.b = v[sim::vB]; a.qh2 = v[sim::vQh2];
-    a.qlim = v[sim::vQlim]; a.flim = v[sim::vFlim]; a.dx = v[sim::vDX]; a.w = v[sim::vSolWt];
-    a.inv_h = inv_h; a.fs = fs; a.qlim_coef = qlim_coef; a.order2 = order2; a.limiter = limiter; a.n = n_;
+    a.rhs = v[sim::vRHS]; a.q = v[sim::vQ]; a.qh0 = v[sim::vQh0]; a.qh1 = v[sim::vQh1]; a.f = v[sim::vF]; a.b = v[sim::vB];
+    a.qh2 = v[sim::vQh2]; a.qlim = v[sim::vQlim]; a.flim = v[sim::vFlim]; a.dx = v[sim::vDX]; a.w = v[sim::vSolWt];
+    a.form = f.form; a.inv_h = f.inv_h; a.fs = f.fs; a.qlim_coef = f.qlim_coef; a.a0 = f.a0; a.a1 = f.a1; a.a2 = f.a2;
+    a.order2 = f.order2; a.limiter = f.limiter; a.n = n_;
     a.nflag_arrays = 0;
     bool overflow = false;
     for (auto &g : ctx->groups) { if (a.nflag_arrays < 8) { a.flags[a.nflag_arrays] = g.d_orig; a.flag_n[a.nflag_arrays++] = g.n; } else overflow = true; }
@@ -271,6 +272,9 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   if (tp->absErrorTol > 0) P.absErrorTol = tp->absErrorTol;
   if (tp->maxOrder > 0) P.maxOrder = tp->maxOrder;
   if (tp->maxSteps > 0) P.maxSteps = tp->maxSteps;
+  if (tp->method != 0 && tp->method != 7 && tp->method != 8) return xg_fail(ctx, 16, "tran: method must be 0 / 7 (trapezoid) or 8 (Gear)");
+  if (tp->method == 8) P.method = 8;
+  P.dcop = tp->dcop ? 1 : 0;
   sim::TransientDriver<GpuBackend> drv(B, P);
   const int rc = drv.run();
   XS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -294,12 +298,13 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
     const sim::TranStats &t = drv.stats;
     const double st[16] = {(double)t.accepted, (double)t.rejected, (double)t.newton_total, (double)t.jacobian_loads,
                            (double)t.residual_loads, (double)t.linear_solves, (double)B.lu_analyses, (double)B.lu_refactors,
-                           (double)nt, (double)nsr, (double)rc, 0, 0, 0, 0, 0};
+                           (double)nt, (double)nsr, (double)rc, (double)t.dcop_newton, (double)t.dcop_status, 0, 0, 0};
     std::memcpy(stats16, st, sizeof(st));
   }
   cudaFreeHost(B.h_norms);
   cudaFree(pool); cudaFree(B.d_src_rows); cudaFree(B.d_src_vals); cudaFree(B.d_probe); cudaFree(B.d_probe_out);
-  if (rc != 0) return xg_fail(ctx, 200 + rc, rc == 2 ? "transient: time step too small / too many failures" : "transient: step limit reached");
+  if (rc != 0) return xg_fail(ctx, 200 + rc, rc == 2 ? "transient: time step too small / too many failures"
+                                             : (rc == 4 ? "transient: the DC operating point did not converge" : "transient: step limit reached"));
   return 0;
 }
 

@@ -9,6 +9,11 @@
 //   TimeIntg::StepErrorControl::evaluateStepError, DataStore::setErrorWtVector / WRMS_errorNorm
 //                                                                  (N_TIA_StepErrorControl.C:470-560, N_TIA_DataStore.C:1300-1520)
 //   Analysis::Transient::doLoopProcess / takeAnIntegrationStep_     (src/AnalysisPKG/N_ANP_Transient.C:1184-1330, :3262-3308)
+//   TimeIntg::Gear12 (BDF, variable order 1-2; `method = 8`): updateCoeffs, obtainPredictor, obtainResidual, obtainJacobian,
+//     initialize, updateHistory, rejectStep, completeStep       (N_TIA_Gear12.C:131-190, :208-262, :477-500, :822-880, :1050-1100, :1183-1300, :1439-1560, :1639-1800)
+//   TimeIntg::NoTimeIntegration::obtainResidual / obtainJacobian (DC operating point, `dcop = 1`; N_TIA_NoTimeIntegration.C:161-173, :291-298)
+//     with DampedNewton in DC_OP mode (defaults N_NLS_NLParams.h:462-663; weights re-evaluated every iteration, N_NLS_DampedNewton.C:473-474)
+//     and the initJct / initFix flags of SolverState (Core/N_DEV_SolverState.C:374-420)
 // with the transient-mode defaults of N_NLS_NLParams.C:101-112 and N_TIA_TIAParams.C:79-111.
 // The driver is a template over a Backend that owns the vectors and performs the loads, BLAS-1
 // kernels and the linear solve: the product instantiates it with the CUDA backend (sim_gpu.cu); the
@@ -63,6 +68,11 @@ struct TranParams {
   double relErrorTol = 1e-3, absErrorTol = 1e-6, errTolAcceptance = 1.0;
   int maxOrder = 2, minOrder = 1;
   int maxSteps = 1000000;
+  int method = 7;      // .OPTIONS TIMEINT METHOD: 7 = trapezoid (OneStep, the reference default), 8 = Gear (Gear12)
+  int dcop = 0;        // 0 = start from x0 as given (.TRAN ... NOOP / UIC), 1 = DC operating point from x0 first
+  // Newton, DC_OP mode defaults (NLParams constructor)
+  int dcMaxNewtonStep = 200;
+  double dcDeltaXTol = 1.0, dcAbsTol = 1e-12, dcRelTol = 1e-3, dcRHSTol = 1e-6;
 };
 
 struct StepRecord { double t, h; int newton_iters, order, status; };
@@ -70,6 +80,7 @@ struct StepRecord { double t, h; int newton_iters, order, status; };
 struct TranStats {
   int accepted = 0, rejected = 0, newton_total = 0, jacobian_loads = 0, residual_loads = 0, linear_solves = 0;
   int failed = 0;
+  int dcop_newton = 0, dcop_status = 0;
 };
 
 // Backend concept:
@@ -82,18 +93,26 @@ struct TranStats {
 //   bool load_rhs(const Flags&, double time);    evaluates devices at vNextSol: fills vF, vQ, vB, vFlim, vQlim
 //   void load_jacobian(double qscalar, double fscalar);               J = qscalar dQdx + fscalar dFdx
 //   int  solve();                                                      J vDX = vRHS   (0 ok)
-//   void residual_and_norms(double inv_h, double fs, bool order2, bool limiter, double qlim_coef, NewtonNorms &out);
-//        vRHS = -[(vQ - vQh0) inv_h + fs (vF - vB) (+ 1/2 vQh2)] (+ qlim_coef vQlim + fs vFlim), element by element in
-//        exactly the operation order of the axpby sequence it replaces; then ||RHS||_2, ||RHS||_inf,
-//        max |vDX / vSolWt| and the AND of the devices' convergence flags
+//   void residual_and_norms(const ResidualForm &f, NewtonNorms &out);
+//        form 0 (OneStep):  vRHS = -[(vQ - vQh0) inv_h + fs (vF - vB) (+ 1/2 vQh2)] (+ qlim_coef vQlim + fs vFlim)
+//        form 1 (Gear12):   vRHS = -[(a0 vQ + a1 vQh0 (+ a2 vQh1)) inv_h + vF - vB] (+ qlim_coef vQlim + vFlim)
+//        form 2 (DC):       vRHS = -(vF - vB) (+ vFlim)
+//        element by element in the operation order of the vector-update sequence it replaces; then ||RHS||_2,
+//        ||RHS||_inf, max |vDX / vSolWt| and the AND of the devices' convergence flags
 //   bool limiter_active();
 //   void accept_state();                                               curr state/store <- next
 //   void record(double t);                                             sample probes
 // everything DampedNewton::converged_ looks at after one residual evaluation, fetched in one go
 struct NewtonNorms { double rhs_norm2 = 0, rhs_norm_inf = 0, dx_wmax = 0; bool devices_converged = true; };
 
+struct ResidualForm {
+  int form = 0;                     // 0 OneStep, 1 Gear12, 2 DC
+  double inv_h = 0, fs = 1, qlim_coef = 0, a0 = 1, a1 = -1, a2 = 0;
+  bool order2 = false, limiter = false;
+};
+
 struct Flags {
-  int dcop = 0, tranop = 0, transient = 1, initTran = 0, newtonIter = 0, initJct = 0;
+  int dcop = 0, tranop = 0, transient = 1, initTran = 0, newtonIter = 0, initJct = 0, initFix = 0;
   double currTimeStep = 0;
 };
 
@@ -114,6 +133,14 @@ class TransientDriver {
     minTimeStep = (stopTime - initialTime) * 4.0 * machEps;
     beginningIntegration = true; stepAttemptStatus = true; stepNumber = 0; iNumCalls = 0;
     nef = 0;
+    if (P.dcop) {      // Transient::doInit: DC operating point, then the solution becomes the current one
+      const int st = newton_solve(true);
+      stats.dcop_status = st; stats.dcop_newton = nIterations;
+      if (st <= 0) { stats.failed = 1; return 4; }
+      B.copy(vCurrSol, vNextSol);
+      B.accept_state();
+      iNumCalls = 0;
+    }
     // initial load: Q, F, B at x(0)
     Flags fl; fl.initTran = 1; fl.newtonIter = 0; fl.currTimeStep = startingTimeStep;
     B.load_rhs(fl, 0.0); ++stats.residual_loads;
@@ -126,10 +153,18 @@ class TransientDriver {
       if (beginningIntegration && stepAttemptStatus) initialize_integrator();
       update_coeffs();
       // predictor (OneStep::obtainPredictor)
-      B.copy(vXn0, vXh0); B.copy(vQn0, vQh0);
-      for (int i = 1; i <= currentOrder; ++i) B.axpy(vXn0, beta[i], i == 1 ? vXh1 : vXh2);
+      if (gear()) {       // Gear12::obtainPredictor: sum over i = 0..order of beta_i * history_i
+        B.fill(vXn0, 0.0); B.fill(vQn0, 0.0);
+        for (int i = 0; i <= currentOrder; ++i) {
+          B.axpy(vXn0, beta[i], i == 0 ? vXh0 : (i == 1 ? vXh1 : vXh2));
+          B.axpy(vQn0, beta[i], i == 0 ? vQh0 : vQh1);     // qHistory[2] is never filled by Gear12::updateHistory (stays 0)
+        }
+      } else {
+        B.copy(vXn0, vXh0); B.copy(vQn0, vQh0);
+        for (int i = 1; i <= currentOrder; ++i) B.axpy(vXn0, beta[i], i == 1 ? vXh1 : vXh2);
+      }
       B.copy(vNextSol, vXn0);
-      const int status = newton_solve();
+      const int status = newton_solve(false);
       // stepLinearCombo + evaluateStepError
       B.axpby(vNewtCorr, 1.0, vNextSol, -1.0, vXn0);
       B.axpby(vQNewtCorr, 1.0, vQ, -1.0, vQn0);
@@ -167,7 +202,8 @@ class TransientDriver {
   double initialTime, currentTime, nextTime, stopTime, lastTime;
   double currentTimeStep, lastTimeStep, currentTimeStepRatio, currentTimeStepSum, savedTimeStep = 0;
   double startingTimeStep, minTimeStep, maxTimeStep;
-  double psi[3] = {0, 0, 0}, beta[3] = {1, 0, 0}, alphas = -1.0, ck = 1.0, estOverTol = 0.0;
+  double psi[3] = {0, 0, 0}, beta[3] = {1, 0, 0}, alpha[3] = {1, -1, 0}, alphas = -1.0, ck = 1.0, estOverTol = 0.0;
+  bool gear() const { return P.method == 8; }
   int currentOrder = 1, usedOrder = 1, numberOfSteps = 0, nef = 0, stepNumber = 0, nIterations = 0;
   int newtonConvergenceStatus = 0, iNumCalls = 0;
   bool beginningIntegration = true, stepAttemptStatus = true;
@@ -204,10 +240,15 @@ class TransientDriver {
     lastTimeStep = currentTimeStep;
     nextTime = currentTime + currentTimeStep;
     B.copy(vXh0, vCurrSol);
-    B.fill(vXh1, 0.0);
     B.copy(vQh0, vQ);
-    B.axpby(vQh1, 1.0, vF, -1.0, vB);
-    B.scale(vQh1, -currentTimeStep);
+    if (gear()) {         // Gear12::initialize (:1262-1266)
+      B.copy(vXh1, vCurrSol);
+      B.copy(vQh1, vQ);
+    } else {
+      B.fill(vXh1, 0.0);
+      B.axpby(vQh1, 1.0, vF, -1.0, vB);
+      B.scale(vQh1, -currentTimeStep);
+    }
     numberOfSteps = 0; currentOrder = 1; usedOrder = 1;
     psi[0] = currentTimeStep;
     nef = 0;
@@ -219,6 +260,26 @@ class TransientDriver {
     psi[1] = psi[0];
     psi[0] = t1;
     beta[0] = 1.0; alphas = -1.0;
+    if (gear()) {         // Gear12::updateCoeffs (:1072-1100)
+      if (currentOrder == 2) {
+        beta[2] = t1 / psi[2] * (t1 + psi[1]) / (psi[1] + psi[2]);
+        beta[1] = -t1 / psi[1] - beta[2] * (psi[1] + psi[2]) / psi[1];
+        beta[0] = 1.0 - beta[2] - beta[1];
+        alpha[2] = -t1 / psi[1] * t1 / (2 * t1 + psi[1]);
+        alpha[1] = 1 - alpha[2];
+        alpha[0] = -alpha[1] - alpha[2] * (1 + psi[1] / t1);
+        alpha[2] = alpha[2] / alpha[0];
+        alpha[1] = alpha[1] / alpha[0];
+        alpha[0] = -1 / alpha[0];
+        ck = currentTimeStep / (t1 + psi[1] + psi[2]);
+      } else {
+        beta[0] = 1.0 + t1 / psi[1];
+        beta[1] = -t1 / psi[1];
+        alpha[0] = 1.0; alpha[1] = -1.0;
+        ck = currentTimeStep / (t1 + psi[1]);
+      }
+      return;
+    }
     if (currentOrder == 2) {
       const double t2 = psi[1];
       beta[1] = t1 / t2 + (t1 / t2) * (t1 / t2) / 2;
@@ -231,39 +292,65 @@ class TransientDriver {
   }
 
   // residual of OneStep::obtainResidual: RHS = -[(Q - q0)/h + f (F - B) (+ 1/2 qHistory[2])] + limiter terms
-  double residual(const Flags &fl) {
-    B.load_rhs(fl, nextTime); ++stats.residual_loads;
-    const double fs = (currentOrder == 2) ? 0.5 : 1.0;
-    B.residual_and_norms(1.0 / currentTimeStep, fs, currentOrder == 2, B.limiter_active(), -alphas / currentTimeStep, nn);
+  // Gear12::obtainResidual: RHS = -[(a0 Q + a1 qHistory[0] (+ a2 qHistory[1]))/h + F - B] + (a0/h) dQdxdVp + dFdxdVp
+  // NoTimeIntegration::obtainResidual: RHS = -(F - B) + dFdxdVp
+  double residual(const Flags &fl, bool dc) {
+    B.load_rhs(fl, dc ? 0.0 : nextTime); ++stats.residual_loads;
+    ResidualForm f;
+    f.limiter = B.limiter_active();
+    if (dc) {
+      f.form = 2;
+    } else if (gear()) {
+      f.form = 1; f.inv_h = 1.0 / currentTimeStep; f.order2 = currentOrder == 2;
+      f.a0 = alpha[0]; f.a1 = alpha[1]; f.a2 = alpha[2]; f.qlim_coef = alpha[0] / currentTimeStep;
+    } else {
+      f.form = 0; f.inv_h = 1.0 / currentTimeStep; f.fs = (currentOrder == 2) ? 0.5 : 1.0; f.order2 = currentOrder == 2;
+      f.qlim_coef = -alphas / currentTimeStep;
+    }
+    B.residual_and_norms(f, nn);
     return nn.rhs_norm2;
   }
   NewtonNorms nn;
   const bool trace_ = std::getenv("XB_TRAN_TRACE") != nullptr;     // diagnostics: one line per Newton iteration on stderr
 
-  int newton_solve() {            // DampedNewton::solve with FULL search (step length 1)
-    Flags fl; fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep;
+  // DampedNewton::solve with FULL search (step length 1); dc = DC_OP mode on NoTimeIntegration
+  int newton_solve(bool dc) {
+    Flags fl;
+    if (dc) { fl.dcop = 1; fl.tranop = 1; fl.initJct = 1; fl.currTimeStep = 0.0; }
+    else { fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep; }
+    const int maxNewtonStep = dc ? P.dcMaxNewtonStep : P.maxNewtonStep;
+    const double deltaXTol = dc ? P.dcDeltaXTol : P.deltaXTol, RHSTol = dc ? P.dcRHSTol : P.RHSTol;
+    const double relTol = dc ? P.dcRelTol : P.relTol, absTol = dc ? P.dcAbsTol : P.absTol;
     int nlStep = 0;
     fl.newtonIter = 0;
-    double normRHS = residual(fl);
+    double normRHS = residual(fl, dc);
     double normRHS_old = normRHS, normRHS_init = normRHS;
-    B.sol_weights(vSolWt, P.relTol, P.absTol, vNextSol, vCurrSol);     // updateWeights_ (transient: once per solve)
+    if (!dc) B.sol_weights(vSolWt, relTol, absTol, vNextSol, vCurrSol);     // updateWeights_ (transient: once per solve)
     int status = 0, count = 0;
     double tmpConvRate = 0.0;
     const double fs = (currentOrder == 2) ? 0.5 : 1.0;
     while (status == 0) {
       ++nlStep;
-      B.load_jacobian(-alphas / currentTimeStep, fs); ++stats.jacobian_loads;
+      if (dc) B.load_jacobian(1.0e-20, 1.0);
+      else if (gear()) B.load_jacobian(alpha[0] / currentTimeStep, 1.0);
+      else B.load_jacobian(-alphas / currentTimeStep, fs);
+      ++stats.jacobian_loads;
       const int lin = B.solve(); ++stats.linear_solves;
       B.axpy(vNextSol, 1.0, vDX);
+      if (dc) {           // updateWeights_ every iteration outside TRANSIENT mode (:473-474, :297-313)
+        if (iNumCalls == 0 && B.norm_inf(vNextSol) <= 2.2250738585072014e-308) B.fill(vSolWt, relTol + absTol);
+        else B.sol_weights(vSolWt, relTol, absTol, vNextSol, vCurrSol);
+      }
       fl.newtonIter = nlStep;
-      normRHS = residual(fl);
+      if (dc) { fl.initJct = 0; fl.initFix = nn.devices_converged ? 0 : 1; }     // SolverState.C:387-420
+      normRHS = residual(fl, dc);
       // ---- converged_ ----
       if (lin != 0) { status = -9; break; }
       if (P.enforceDeviceConv) {
         const bool conv = nn.devices_converged;
         if (trace_ && !conv) std::fprintf(stderr, "NEWTON t=%.9e it=%d devices not converged ||rhs||2=%.17g\n", nextTime, nlStep, normRHS);
-        if (!conv && nlStep < P.maxNewtonStep) continue;
-        if (!conv && nlStep >= P.maxNewtonStep) { status = -1; break; }
+        if (!conv && nlStep < maxNewtonStep) continue;
+        if (!conv && nlStep >= maxNewtonStep) { status = -1; break; }
       }
       if (!(normRHS == normRHS)) { status = -6; break; }
       const double maxNormRHS = nn.rhs_norm_inf;
@@ -275,10 +362,10 @@ class TransientDriver {
       const double updateSize = wtNormDX;
       if (trace_) std::fprintf(stderr, "NEWTON t=%.9e it=%d ||rhs||2=%.17g ||rhs||inf=%.17g ||dx||w=%.17g devconv=%d\n", nextTime,
                                nlStep, normRHS, maxNormRHS, updateSize, (int)nn.devices_converged);
-      if (maxNormRHS <= P.RHSTol && updateSize <= P.deltaXTol) { status = 2; break; }
-      if (nlStep >= P.maxNewtonStep && normRHS_rel <= 0.9 && resConvRate <= 1.0) { status = 3; break; }
+      if (maxNormRHS <= RHSTol && updateSize <= deltaXTol) { status = 2; break; }
+      if (nlStep >= maxNewtonStep && normRHS_rel <= 0.9 && resConvRate <= 1.0) { status = 3; break; }
       if (updateSize <= P.smallUpdateTol) { status = 4; break; }
-      if (nlStep >= P.maxNewtonStep) { status = -1; break; }
+      if (nlStep >= maxNewtonStep) { status = -1; break; }
       if (resConvRate > 0.5 * 1.7976931348623157e308) { status = -2; break; }
       if (std::fabs(resConvRate - 1.0) <= 1.0e-3) {
         if (count == 0 || resConvRate < tmpConvRate) tmpConvRate = resConvRate;
@@ -298,7 +385,15 @@ class TransientDriver {
     return status;
   }
 
-  void update_history() {         // OneStep::updateHistory
+  void update_history() {         // OneStep::updateHistory / Gear12::updateHistory
+    if (gear()) {
+      if (currentOrder == 2) B.copy(vXh2, vXh1);
+      B.copy(vQh1, vQh0);
+      B.copy(vXh1, vXh0);
+      B.copy(vXh0, vNextSol);
+      B.copy(vQh0, vQ);
+      return;
+    }
     if (currentOrder == 2) {
       B.copy(vXh2, vXh1);
       B.axpby(vQh2, 1.0, vF, -1.0, vB);
@@ -355,7 +450,7 @@ class TransientDriver {
       newTimeStep = currentTimeStep / 8;
       currentOrder = P.minOrder;
     } else if (nef == 1) {
-      currentOrder = P.minOrder;
+      if (!gear()) currentOrder = P.minOrder;     // Gear12::rejectStep keeps the order on the first error-test failure (:1484-1491)
       double rr = tolAimFac / (estOverTol + 0.0001);
       rr = std::pow(rr, 1.0 / (currentOrder + 1.0));
       rr = std::max(r_min, std::min(r_max, rr));

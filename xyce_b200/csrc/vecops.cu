@@ -72,12 +72,26 @@ __global__ void __launch_bounds__(256) residual_norms_k(ResidualArgs a, double *
   __syncthreads();
   double s2 = 0.0, mx = 0.0, wm = 0.0;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < a.n; i += gridDim.x * 256) {
-    double r = 1.0 * a.q[i] + -1.0 * a.qh0[i];
-    const double t = a.fs * a.f[i] + (-a.fs) * a.b[i];
-    r = a.inv_h * r + 1.0 * t;
-    if (a.order2) r = 1.0 * r + 0.5 * a.qh2[i];
-    r = -1.0 * r + 0.0 * r;
-    if (a.limiter) { r = 1.0 * r + a.qlim_coef * a.qlim[i]; r = 1.0 * r + a.fs * a.flim[i]; }
+    double r;
+    if (a.form == 0) {             // OneStep::obtainResidual
+      r = 1.0 * a.q[i] + -1.0 * a.qh0[i];
+      const double t = a.fs * a.f[i] + (-a.fs) * a.b[i];
+      r = a.inv_h * r + 1.0 * t;
+      if (a.order2) r = 1.0 * r + 0.5 * a.qh2[i];
+      r = -1.0 * r + 0.0 * r;
+      if (a.limiter) { r = 1.0 * r + a.qlim_coef * a.qlim[i]; r = 1.0 * r + a.fs * a.flim[i]; }
+    } else if (a.form == 1) {      // Gear12::obtainResidual
+      r = a.a0 * a.q[i] + a.a1 * a.qh0[i];
+      if (a.order2) r = 1.0 * r + a.a2 * a.qh1[i];
+      const double t = 1.0 * a.f[i] + -1.0 * a.b[i];
+      r = a.inv_h * r + 1.0 * t;
+      r = -1.0 * r + 0.0 * r;
+      if (a.limiter) { r = 1.0 * r + a.qlim_coef * a.qlim[i]; r = 1.0 * r + 1.0 * a.flim[i]; }
+    } else {                       // NoTimeIntegration::obtainResidual
+      r = 1.0 * a.f[i] + -1.0 * a.b[i];
+      r = -1.0 * r + 0.0 * r;
+      if (a.limiter) r = 1.0 * r + 1.0 * a.flim[i];
+    }
     a.rhs[i] = r;
     s2 = comb<kSumSq>(s2, r * r);
     mx = comb<kMaxAbs>(mx, fabs(r));
