@@ -36,8 +36,7 @@ VARIANTS = {
 }
 
 # the 4.7.0 and 4.6.1 evaluators (N_DEV_MOSFET_B4p70.C, N_DEV_MOSFET_B4p61.C) on the variants whose code differs
-for _base, _vers in (("default", (4.7, 4.61)), ("igc2", (4.7, 4.61)), ("gidl", (4.7, 4.61)), ("mob3", (4.61,)),
-                     ("mtrl", (4.7, 4.61)), ("pocket", (4.7, 4.61)), ("capmod0", (4.61,)),
+for _base, _vers in (("default", (4.7, 4.61)), ("igc2", (4.7, 4.61)), ("gidl", (4.7, 4.61)), ("mtrl", (4.7, 4.61)), ("pocket", (4.7, 4.61)), ("capmod0", (4.61,)),
                      ("mob1", (4.61,)), ("rdsmod", (4.61,)), ("diomod0", (4.61,)), ("igc", (4.61,))):
     for _v in _vers:
         VARIANTS["%s_v%d" % (_base, round(_v * 100))] = tuple({**c, "VERSION": _v} for c in VARIANTS[_base])
