@@ -176,6 +176,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = wl.inverter_array(args.inverters, seed=12345 + rank)

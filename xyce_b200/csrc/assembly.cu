@@ -11,83 +11,7 @@ struct PlaneSet {
   double *out[kMaxPlanes];
 };
 
-template <int NP>
-__global__ void __launch_bounds__(256) gather_short_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= m.ndst) return;
-  const int64_t b = m.ptr[d], e = m.ptr[d + 1];
-  if (e - b > kLongThreshold) return;   // handled by gather_long_kernel
-  double acc[NP];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) acc[p] = accumulate ? ps.out[p][d] : 0.0;
-  for (int64_t k = b; k < e; ++k) {
-    const int32_t s = __ldg(m.src + k);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
-  }
-#pragma unroll
-  for (int p = 0; p < NP; ++p) ps.out[p][d] = acc[p];
-}
-
-// Long destinations (supply rails): stage 1, one block per chunk of kChunk sources -- every thread
-// sums its strided subsequence in index order, then a fixed-shape shared-memory tree combines the
-// 256 partials; stage 2, one thread per long destination adds its chunk partials in chunk order.
-// Fixed shapes and orders => bitwise reproducible, no atomics.
-template <int NP>
-__global__ void __launch_bounds__(256) gather_chunk_kernel(GatherMapDev m, PlaneSet ps) {
-  __shared__ double sh[NP][256];
-  const int c = blockIdx.x;
-  const int d = m.long_dst[m.chunk_dst_slot[c]];
-  const int64_t b = m.chunk_begin[c];
-  const int64_t e = min(b + (int64_t)kChunk, m.ptr[d + 1]);
-  double acc[NP];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
-  for (int64_t k = b + threadIdx.x; k < e; k += 256) {
-    const int32_t s = __ldg(m.src + k);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
-  }
-#pragma unroll
-  for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] += sh[p][threadIdx.x + w];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x < NP) m.partials[(size_t)threadIdx.x * m.nchunks + c] = sh[threadIdx.x][0];
-}
-
-template <int NP>
-__global__ void __launch_bounds__(256) gather_long_finish_kernel(GatherMapDev m, PlaneSet ps, bool accumulate) {
-  __shared__ double sh[NP][256];
-  const int j = blockIdx.x;
-  const int d = m.long_dst[j];
-  double acc[NP];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) acc[p] = 0.0;
-  for (int c = m.long_chunk_ptr[j] + threadIdx.x; c < m.long_chunk_ptr[j + 1]; c += 256) {
-#pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] += m.partials[(size_t)p * m.nchunks + c];
-  }
-#pragma unroll
-  for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] += sh[p][threadIdx.x + w];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x < NP) ps.out[threadIdx.x][d] = (accumulate ? ps.out[threadIdx.x][d] : 0.0) + sh[threadIdx.x][0];
-}
-
-// ---- fused vector + matrix assembly: the same three stages, one launch each for both maps ----
-// (threads / blocks beyond the vector map's range work on the matrix map)
+// ---- per-destination and per-chunk bodies ----
 template <int NP>
 __device__ __forceinline__ void short_body(const GatherMapDev &m, const PlaneSet &ps, int d, bool accumulate) {
   const int64_t b = m.ptr[d], e = m.ptr[d + 1];
@@ -130,16 +54,35 @@ __device__ __forceinline__ void chunk_body(const GatherMapDev &m, const PlaneSet
   if (threadIdx.x < NP) m.partials[(size_t)threadIdx.x * m.nchunks + c] = sh[threadIdx.x][0];
 }
 
+// ---- one-launch assembly -------------------------------------------------------------------------------
+// Grid = [chunk blocks of map A][chunk blocks of map B][short blocks of A][short blocks of B].  A chunk block
+// publishes its partials (__threadfence), takes a ticket on its destination's counter, and the block that
+// draws the last ticket runs the finish stage for that destination -- the same fixed-order sum of the chunk
+// partials whichever block ends up doing it, so the result stays bitwise reproducible.
 template <int NP>
-__device__ __forceinline__ void finish_body(const GatherMapDev &m, const PlaneSet &ps, int j, bool accumulate, double (*sh)[256]) {
+__device__ __forceinline__ void chunk_then_finish(const GatherMapDev &m, const PlaneSet &ps, int c, bool accumulate,
+                                                  double (*sh)[256]) {
+  __shared__ int last;
+  chunk_body<NP>(m, ps, c, sh);
+  const int j = m.chunk_dst_slot[c];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int need = m.long_chunk_ptr[j + 1] - m.long_chunk_ptr[j];
+    last = (atomicAdd(m.done + j, 1) == need - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) m.done[j] = 0;          // ready for the next launch
   const int d = m.long_dst[j];
   double acc[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) acc[p] = 0.0;
-  for (int c = m.long_chunk_ptr[j] + threadIdx.x; c < m.long_chunk_ptr[j + 1]; c += 256) {
+  for (int cc = m.long_chunk_ptr[j] + threadIdx.x; cc < m.long_chunk_ptr[j + 1]; cc += 256) {
 #pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] += m.partials[(size_t)p * m.nchunks + c];
+    for (int p = 0; p < NP; ++p) acc[p] += __ldcg(m.partials + (size_t)p * m.nchunks + cc);
   }
+  __syncthreads();
 #pragma unroll
   for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
   __syncthreads();
@@ -153,25 +96,22 @@ __device__ __forceinline__ void finish_body(const GatherMapDev &m, const PlaneSe
   if (threadIdx.x < NP) ps.out[threadIdx.x][d] = (accumulate ? ps.out[threadIdx.x][d] : 0.0) + sh[threadIdx.x][0];
 }
 
-__global__ void __launch_bounds__(256) fused_short_kernel(GatherMapDev mv, PlaneSet pv, GatherMapDev mm, PlaneSet pm,
-                                                          int vec_blocks, bool accumulate) {
-  if ((int)blockIdx.x < vec_blocks) {
-    const int d = blockIdx.x * 256 + threadIdx.x;
-    if (d < mv.ndst) short_body<4>(mv, pv, d, accumulate);
+template <int NPA, int NPB>
+__global__ void __launch_bounds__(256) assemble_kernel(GatherMapDev ma, PlaneSet pa, GatherMapDev mb, PlaneSet pb,
+                                                       int short_a, bool accumulate) {
+  __shared__ double sh[(NPA > NPB ? NPA : NPB)][256];
+  int b = blockIdx.x;
+  if (b < ma.nchunks) { chunk_then_finish<NPA>(ma, pa, b, accumulate, sh); return; }
+  b -= ma.nchunks;
+  if (b < mb.nchunks) { chunk_then_finish<NPB>(mb, pb, b, accumulate, sh); return; }
+  b -= mb.nchunks;
+  if (b < short_a) {
+    const int d = b * 256 + threadIdx.x;
+    if (d < ma.ndst) short_body<NPA>(ma, pa, d, accumulate);
   } else {
-    const int d = (blockIdx.x - vec_blocks) * 256 + threadIdx.x;
-    if (d < mm.ndst) short_body<2>(mm, pm, d, accumulate);
+    const int d = (b - short_a) * 256 + threadIdx.x;
+    if (d < mb.ndst) short_body<NPB>(mb, pb, d, accumulate);
   }
-}
-__global__ void __launch_bounds__(256) fused_chunk_kernel(GatherMapDev mv, PlaneSet pv, GatherMapDev mm, PlaneSet pm) {
-  __shared__ double sh[4][256];
-  if ((int)blockIdx.x < mv.nchunks) chunk_body<4>(mv, pv, blockIdx.x, sh);
-  else chunk_body<2>(mm, pm, blockIdx.x - mv.nchunks, sh);
-}
-__global__ void __launch_bounds__(256) fused_finish_kernel(GatherMapDev mv, PlaneSet pv, GatherMapDev mm, PlaneSet pm, bool accumulate) {
-  __shared__ double sh[4][256];
-  if ((int)blockIdx.x < mv.nlong) finish_body<4>(mv, pv, blockIdx.x, accumulate, sh);
-  else finish_body<2>(mm, pm, blockIdx.x - mv.nlong, accumulate, sh);
 }
 
 __global__ void __launch_bounds__(256) linear_combo_kernel(int64_t nnz, double a, const double *__restrict__ A,
@@ -192,11 +132,9 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 
 template <int NP>
 void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
-  if (m.ndst > 0) gather_short_kernel<NP><<<(m.ndst + 255) / 256, 256, 0, stream>>>(m, ps, accumulate);
-  if (m.nlong > 0) {
-    gather_chunk_kernel<NP><<<m.nchunks, 256, 0, stream>>>(m, ps);
-    gather_long_finish_kernel<NP><<<m.nlong, 256, 0, stream>>>(m, ps, accumulate);
-  }
+  const int sb = (m.ndst + 255) / 256;
+  GatherMapDev none{};
+  if (m.nchunks + sb > 0) assemble_kernel<NP, 1><<<m.nchunks + sb, 256, 0, stream>>>(m, ps, none, PlaneSet{}, sb, accumulate);
 }
 
 }  // namespace
@@ -218,15 +156,11 @@ int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, do
   PlaneSet pv{}, pm{};
   for (int p = 0; p < 4; ++p) { pv.in[p] = vplanes[p]; pv.out[p] = vdst[p]; }
   for (int p = 0; p < 2; ++p) { pm.in[p] = mplanes[p]; pm.out[p] = mdst[p]; }
-  int launches = 0;
   const int vb = (mv.ndst + 255) / 256, mb = (mm.ndst + 255) / 256;
-  if (vb + mb > 0) { fused_short_kernel<<<vb + mb, 256, 0, stream>>>(mv, pv, mm, pm, vb, accumulate); ++launches; }
-  if (mv.nchunks + mm.nchunks > 0) {
-    fused_chunk_kernel<<<mv.nchunks + mm.nchunks, 256, 0, stream>>>(mv, pv, mm, pm);
-    fused_finish_kernel<<<mv.nlong + mm.nlong, 256, 0, stream>>>(mv, pv, mm, pm, accumulate);
-    launches += 2;
-  }
-  return launches;
+  const int blocks = mv.nchunks + mm.nchunks + vb + mb;
+  if (blocks == 0) return 0;
+  assemble_kernel<4, 2><<<blocks, 256, 0, stream>>>(mv, pv, mm, pm, vb, accumulate);
+  return 1;
 }
 
 cudaError_t measure_fp64_peak(cudaStream_t stream, double *tflops) {

@@ -8,7 +8,9 @@
 // elements that land on it, ordered device-type-major, instance-minor -- the reference's
 // accumulation order (Core/N_DEV_DeviceMgr.C:4238-4248) -- and sums them in that fixed
 // order.  Destinations with a very long list (supply rails) are summed by one block with a
-// fixed-shape tree, so results are bitwise reproducible run to run.
+// fixed-shape tree, so results are bitwise reproducible run to run.  The whole assembly is ONE launch:
+// chunk blocks come first in the grid; the chunk block that finishes last for its destination (integer
+// ticket counter, the only atomic in the path -- it carries no data) adds the chunk partials in chunk order.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -38,6 +40,7 @@ struct GatherMapDev {
   int32_t *chunk_dst_slot = nullptr;   // index into long_dst
   int32_t *long_chunk_ptr = nullptr;   // [nlong+1]
   double *partials = nullptr;          // [4][nchunks]
+  int32_t *done = nullptr;             // [nlong] chunk blocks finished so far (ticket counter; zero between launches)
 };
 
 constexpr int kLongThreshold = 96;
@@ -48,7 +51,7 @@ constexpr int kChunk = 1024;
 void launch_gather(const GatherMapDev &m, int nplanes, const double *const *planes, int64_t plane_stride,
                    double *const *dst, bool accumulate, cudaStream_t stream);
 
-// Vector planes (4, map mv) and matrix planes (2, map mm) in the same three launches.  Same sums in the same
+// Vector planes (4, map mv) and matrix planes (2, map mm) in the same launch.  Same sums in the same
 // order as two launch_gather calls; returns the number of kernel launches.
 int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, double *const *vdst, const GatherMapDev &mm,
                         const double *const *mplanes, double *const *mdst, bool accumulate, cudaStream_t stream);

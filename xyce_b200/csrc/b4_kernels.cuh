@@ -71,6 +71,8 @@ constexpr int kMaxUniformRuns = 64;   // groups with more distinct runs use the 
 // registers per thread = 65536 / (threads * blocks), capped at 255.
 #define XB_B4_LAUNCH_SHAPES(X) \
   X(64, 4) X(64, 6) X(96, 4) X(128, 2) X(128, 3) X(128, 4) X(256, 1) X(384, 1) X(512, 1)
+// (20-24 warps per SM -- 128 x 5, 128 x 6, 64 x 11 at 80-96 registers -- were measured and are slower at every
+// group size: the local-memory spills cost more than the occupancy gains; profiles/r01_b4_occupancy.json)
 
 // arith: 0 exact (no FMA contraction, IEEE division), 1 fma, 2 fast (fma + reciprocal division);
 // lockstep: block-wide barriers between evaluation sections keep the warps of a block inside the same

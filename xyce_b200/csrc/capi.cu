@@ -52,7 +52,9 @@ cudaError_t upload_map(const GatherMapHost &h, GatherMapDev &d) {
   if ((e = upload(&d.chunk_begin, cb.data(), cb.size())) != cudaSuccess) return e;
   if ((e = upload(&d.chunk_dst_slot, cslot.data(), cslot.size())) != cudaSuccess) return e;
   if ((e = upload(&d.long_chunk_ptr, lptr.data(), lptr.size())) != cudaSuccess) return e;
-  return cudaMalloc((void **)&d.partials, std::max<size_t>(4 * cb.size(), 1) * sizeof(double));
+  if ((e = cudaMalloc((void **)&d.partials, std::max<size_t>(4 * cb.size(), 1) * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMalloc((void **)&d.done, std::max<size_t>(h.long_dst.size(), 1) * sizeof(int32_t))) != cudaSuccess) return e;
+  return cudaMemset(d.done, 0, std::max<size_t>(h.long_dst.size(), 1) * sizeof(int32_t));
 }
 
 // uniform view of one device group for pattern / map construction
@@ -515,7 +517,7 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
     // on large groups gains a little more from 16 warps (128 x 4).
     const bool spec = ctx->b4_spec && uniform && g.spec_ok && ctx->b4_arith == 2 && !lockstep && !g.general;
     int threads = ctx->b4_threads, minblocks = ctx->b4_minblocks;
-    if (threads == 0) { threads = 128; minblocks = (spec && g.n > 300000) ? 4 : 3; }
+    if (threads == 0) { threads = 128; minblocks = (spec && g.n > 150000) ? 4 : 3;      // crossover measured between 100k and 200k instances }
     const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, threads, minblocks,
                                    uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream,
                                    spec);
@@ -533,7 +535,7 @@ int xgpu_load_vectors(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_fl, dou
   const double *in[4]; double *out[4] = {d_f, d_q, d_fl, d_ql};
   for (int p = 0; p < 4; ++p) in[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
   launch_gather(ctx->vec_map, 4, in, ctx->vec_plane, out, accumulate != 0, ctx->stream);
-  ctx->launches += 1 + 2 * (ctx->vec_map.nlong > 0);
+  ++ctx->launches;
   XG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -544,7 +546,7 @@ int xgpu_load_matrices(xgpu_ctx *ctx, double *d_dFdx, double *d_dQdx, int accumu
   const double *in[2]; double *out[2] = {d_dFdx, d_dQdx};
   for (int p = 0; p < 2; ++p) in[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
   launch_gather(ctx->mat_map, 2, in, ctx->mat_plane, out, accumulate != 0, ctx->stream);
-  ctx->launches += 1 + 2 * (ctx->mat_map.nlong > 0);
+  ++ctx->launches;
   XG_CUDA(cudaGetLastError());
   return 0;
 }
