@@ -517,7 +517,7 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
     // on large groups gains a little more from 16 warps (128 x 4).
     const bool spec = ctx->b4_spec && uniform && g.spec_ok && ctx->b4_arith == 2 && !lockstep && !g.general;
     int threads = ctx->b4_threads, minblocks = ctx->b4_minblocks;
-    if (threads == 0) { threads = 128; minblocks = (spec && g.n > 150000) ? 4 : 3;      // crossover measured between 100k and 200k instances }
+    if (threads == 0) { threads = 128; minblocks = (spec && g.n > 150000) ? 4 : 3; }      // crossover between 100k and 200k (profiles/r01_b4_occupancy.json)
     const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, threads, minblocks,
                                    uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream,
                                    spec);
