@@ -12,20 +12,54 @@ struct PlaneSet {
 };
 
 // ---- per-destination and per-chunk bodies ----
+// One thread sums U destinations (d0, d0 + 256, ...): all ELL slots are fetched first, then all plane
+// elements, so U * ell_w * NP independent loads are in flight per thread instead of a dependent chain per
+// destination; the additions then run in list order per destination.
+template <int NP> struct ShortUnroll { static constexpr int U = NP >= 4 ? 2 : 4; };
+
 template <int NP>
-__device__ __forceinline__ void short_body(const GatherMapDev &m, const PlaneSet &ps, int d, bool accumulate) {
-  const int64_t b = m.ptr[d], e = m.ptr[d + 1];
-  if (e - b > kLongThreshold) return;
-  double acc[NP];
+__device__ __forceinline__ void short_body(const GatherMapDev &m, const double *const (&in)[NP], double *const (&out)[NP],
+                                           int d0, bool accumulate) {
+  constexpr int U = ShortUnroll<NP>::U;
+  int32_t s[U][kEllMax];
 #pragma unroll
-  for (int p = 0; p < NP; ++p) acc[p] = accumulate ? ps.out[p][d] : 0.0;
-  for (int64_t k = b; k < e; ++k) {
-    const int32_t s = __ldg(m.src + k);
+  for (int j = 0; j < U; ++j) {
+    const int d = d0 + j * 256;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
+    for (int k = 0; k < kEllMax; ++k) s[j][k] = (k < m.ell_w && d < m.ndst) ? __ldg(m.ell + (size_t)k * m.ndst + d) : -1;
   }
+  double val[U][kEllMax][NP];
 #pragma unroll
-  for (int p = 0; p < NP; ++p) ps.out[p][d] = acc[p];
+  for (int j = 0; j < U; ++j)
+#pragma unroll
+    for (int k = 0; k < kEllMax; ++k)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) val[j][k][p] = (s[j][k] >= 0) ? __ldg(in[p] + s[j][k]) : 0.0;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int d = d0 + j * 256;
+    if (d >= m.ndst || s[j][0] == kEllLong) continue;      // out of range / handled by the chunk blocks
+    const bool tail = (s[j][1] == kEllTail) || (s[j][kEllMax - 1] == kEllTail);      // the flag sits in slot ell_w - 1
+    double acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] = accumulate ? out[p][d] : 0.0;
+#pragma unroll
+    for (int k = 0; k < kEllMax; ++k)
+      if (s[j][k] >= 0) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p] += val[j][k][p];
+      }
+    if (tail) {                             // more than ell_w sources: the rest in list order
+      const int64_t b = m.ptr[d] + m.ell_w - 1, e = m.ptr[d + 1];
+      for (int64_t k = b; k < e; ++k) {
+        const int32_t t = __ldg(m.src + k);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p] += __ldg(in[p] + t);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) out[p][d] = acc[p];
+  }
 }
 
 template <int NP>
@@ -33,14 +67,26 @@ __device__ __forceinline__ void chunk_body(const GatherMapDev &m, const PlaneSet
   const int d = m.long_dst[m.chunk_dst_slot[c]];
   const int64_t b = m.chunk_begin[c];
   const int64_t e = min(b + (int64_t)kChunk, m.ptr[d + 1]);
+  // the thread's kChunk / 256 strided sources: indices first, then all plane elements (independent loads),
+  // then the additions in index order
+  constexpr int R = kChunk / 256;
+  int32_t si[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { const int64_t k = b + threadIdx.x + r * 256; si[r] = (k < e) ? __ldg(m.src + k) : -1; }
+  double v[R][NP];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) v[r][p] = (si[r] >= 0) ? __ldg(ps.in[p] + si[r]) : 0.0;
   double acc[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) acc[p] = 0.0;
-  for (int64_t k = b + threadIdx.x; k < e; k += 256) {
-    const int32_t s = __ldg(m.src + k);
 #pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] += __ldg(ps.in[p] + s);
-  }
+  for (int r = 0; r < R; ++r)
+    if (si[r] >= 0) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) acc[p] += v[r][p];
+    }
 #pragma unroll
   for (int p = 0; p < NP; ++p) sh[p][threadIdx.x] = acc[p];
   __syncthreads();
@@ -93,7 +139,10 @@ __device__ __forceinline__ void chunk_then_finish(const GatherMapDev &m, const P
     }
     __syncthreads();
   }
-  if (threadIdx.x < NP) ps.out[threadIdx.x][d] = (accumulate ? ps.out[threadIdx.x][d] : 0.0) + sh[threadIdx.x][0];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) ps.out[p][d] = (accumulate ? ps.out[p][d] : 0.0) + sh[p][0];      // static plane indices
+  }
 }
 
 template <int NPA, int NPB>
@@ -105,12 +154,17 @@ __global__ void __launch_bounds__(256) assemble_kernel(GatherMapDev ma, PlaneSet
   b -= ma.nchunks;
   if (b < mb.nchunks) { chunk_then_finish<NPB>(mb, pb, b, accumulate, sh); return; }
   b -= mb.nchunks;
+  // plane pointers into registers (static indices only: no local-memory copy of the parameter structs)
   if (b < short_a) {
-    const int d = b * 256 + threadIdx.x;
-    if (d < ma.ndst) short_body<NPA>(ma, pa, d, accumulate);
+    const double *in[NPA]; double *out[NPA];
+#pragma unroll
+    for (int p = 0; p < NPA; ++p) { in[p] = pa.in[p]; out[p] = pa.out[p]; }
+    short_body<NPA>(ma, in, out, b * (256 * ShortUnroll<NPA>::U) + threadIdx.x, accumulate);
   } else {
-    const int d = (b - short_a) * 256 + threadIdx.x;
-    if (d < mb.ndst) short_body<NPB>(mb, pb, d, accumulate);
+    const double *in[NPB]; double *out[NPB];
+#pragma unroll
+    for (int p = 0; p < NPB; ++p) { in[p] = pb.in[p]; out[p] = pb.out[p]; }
+    short_body<NPB>(mb, in, out, (b - short_a) * (256 * ShortUnroll<NPB>::U) + threadIdx.x, accumulate);
   }
 }
 
@@ -132,7 +186,8 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 
 template <int NP>
 void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
-  const int sb = (m.ndst + 255) / 256;
+  const int per = 256 * ShortUnroll<NP>::U;
+  const int sb = (m.ndst + per - 1) / per;
   GatherMapDev none{};
   if (m.nchunks + sb > 0) assemble_kernel<NP, 1><<<m.nchunks + sb, 256, 0, stream>>>(m, ps, none, PlaneSet{}, sb, accumulate);
 }
@@ -156,7 +211,8 @@ int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, do
   PlaneSet pv{}, pm{};
   for (int p = 0; p < 4; ++p) { pv.in[p] = vplanes[p]; pv.out[p] = vdst[p]; }
   for (int p = 0; p < 2; ++p) { pm.in[p] = mplanes[p]; pm.out[p] = mdst[p]; }
-  const int vb = (mv.ndst + 255) / 256, mb = (mm.ndst + 255) / 256;
+  const int pv_ = 256 * ShortUnroll<4>::U, pm_ = 256 * ShortUnroll<2>::U;
+  const int vb = (mv.ndst + pv_ - 1) / pv_, mb = (mm.ndst + pm_ - 1) / pm_;
   const int blocks = mv.nchunks + mm.nchunks + vb + mb;
   if (blocks == 0) return 0;
   assemble_kernel<4, 2><<<blocks, 256, 0, stream>>>(mv, pv, mm, pm, vb, accumulate);

@@ -40,11 +40,19 @@ struct GatherMapDev {
   int32_t *chunk_dst_slot = nullptr;   // index into long_dst
   int32_t *long_chunk_ptr = nullptr;   // [nlong+1]
   double *partials = nullptr;          // [4][nchunks]
+  // ELL view of the short destinations: ell[k * ndst + d] = k-th source of destination d for k < ell_w (coalesced,
+  // all slots loadable at once: one dependent-load level less than ptr -> src -> plane).  -1 = no such source;
+  // last slot kEllTail = more sources follow, continue in src[] from ptr[d] + ell_w - 1; slot 0 kEllLong = long
+  // destination (left to the chunk blocks).
+  int ell_w = 0;
+  int32_t *ell = nullptr;
   int32_t *done = nullptr;             // [nlong] chunk blocks finished so far (ticket counter; zero between launches)
 };
 
 constexpr int kLongThreshold = 96;
 constexpr int kChunk = 1024;
+constexpr int kEllMax = 4;
+constexpr int32_t kEllTail = -2, kEllLong = -3;
 
 // Sum `nplanes` planes through one map.  dst[p][d] = (accumulate ? dst[p][d] : 0) + sum_k plane[p][src[k]].
 // Long destinations are skipped by the short kernel and handled by the block kernel.

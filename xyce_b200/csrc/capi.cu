@@ -52,6 +52,20 @@ cudaError_t upload_map(const GatherMapHost &h, GatherMapDev &d) {
   if ((e = upload(&d.chunk_begin, cb.data(), cb.size())) != cudaSuccess) return e;
   if ((e = upload(&d.chunk_dst_slot, cslot.data(), cslot.size())) != cudaSuccess) return e;
   if ((e = upload(&d.long_chunk_ptr, lptr.data(), lptr.size())) != cudaSuccess) return e;
+  // ELL width: 2 when (almost) every short destination has at most 2 sources, else 4
+  {
+    size_t over2 = 0;
+    for (int dd = 0; dd < d.ndst; ++dd) { const int64_t c = h.ptr[dd + 1] - h.ptr[dd]; if (c > 2 && c <= kLongThreshold) ++over2; }
+    d.ell_w = (over2 * 50 <= (size_t)d.ndst) ? 2 : kEllMax;
+    std::vector<int32_t> ell((size_t)d.ell_w * std::max(d.ndst, 1), -1);
+    for (int dd = 0; dd < d.ndst; ++dd) {
+      const int64_t b = h.ptr[dd], c = h.ptr[dd + 1] - b;
+      if (c > kLongThreshold) { ell[dd] = kEllLong; continue; }
+      for (int k = 0; k < d.ell_w && k < c; ++k) ell[(size_t)k * d.ndst + dd] = h.src[b + k];
+      if (c > d.ell_w) ell[(size_t)(d.ell_w - 1) * d.ndst + dd] = kEllTail;
+    }
+    if ((e = upload(&d.ell, ell.data(), ell.size())) != cudaSuccess) return e;
+  }
   if ((e = cudaMalloc((void **)&d.partials, std::max<size_t>(4 * cb.size(), 1) * sizeof(double))) != cudaSuccess) return e;
   if ((e = cudaMalloc((void **)&d.done, std::max<size_t>(h.long_dst.size(), 1) * sizeof(int32_t))) != cudaSuccess) return e;
   return cudaMemset(d.done, 0, std::max<size_t>(h.long_dst.size(), 1) * sizeof(int32_t));
@@ -132,7 +146,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   }
   for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
-  for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); }
+  for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); cudaFree(m->ell); cudaFree(m->done); }
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
   xb::lu::free_plan(ctx->lu_dev);
