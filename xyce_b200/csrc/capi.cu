@@ -149,6 +149,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); cudaFree(m->ell); cudaFree(m->done); }
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
+  for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
   xb::lu::free_plan(ctx->lu_dev);
   for (XgLinearPart *L : {&ctx->linG, &ctx->linC}) { cudaFree(L->rows); cudaFree(L->ptr); cudaFree(L->col); cudaFree(L->pos); cudaFree(L->val); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -173,6 +174,7 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (n == "b4_uniform" && (value == 0 || value == 1)) { ctx->b4_uniform = value; return 0; }
   if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
   if (n == "b4_spec" && (value == 0 || value == 1)) { ctx->b4_spec = value; return 0; }
+  if (n == "lu_graphs" && (value == 0 || value == 1)) { ctx->lu_graphs = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
 
@@ -645,6 +647,57 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
   return 0;
 }
 
+extern "C++" {
+namespace {
+void lu_drop_graphs(xgpu_ctx *ctx) {
+  for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) {
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    *g = xgpu_ctx::LuGraph();
+  }
+}
+// Run a launch sequence directly, or -- when it is long (launch-latency bound) -- as a CUDA graph captured on the
+// first call with these device pointers.  The kernels read their inputs through those pointers only, so replaying
+// the graph on new VALUES in the same buffers is the same computation.
+constexpr int kGraphMinLaunches = 12;
+template <class F>
+int lu_run(xgpu_ctx *ctx, xgpu_ctx::LuGraph &g, const void *k0, const void *k1, const void *k2, F &&launch) {
+  if (g.exec && g.k0 == k0 && g.k1 == k1 && g.k2 == k2) {
+    XG_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    ctx->launches += g.launches;
+    return 0;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(ctx->stream, &cs);
+  // the legacy default stream cannot be captured
+  const bool capturable = ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && ctx->stream != cudaStreamPerThread;
+  const bool try_graph = ctx->lu_graphs && capturable && cs == cudaStreamCaptureStatusNone && g.launches != -1;
+  if (try_graph && g.launches >= kGraphMinLaunches) {        // second call of a long sequence: capture it
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int n = launch();
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&g.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e == cudaSuccess && g.exec) {
+        g.k0 = k0; g.k1 = k1; g.k2 = k2; g.launches = n;
+        XG_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->launches += n;
+        return 0;
+      }
+      cudaGetLastError();
+      g.exec = nullptr; g.launches = -1;                     // capture not possible here: stay on plain launches
+    }
+  }
+  const int n = launch();
+  if (g.launches != -1) g.launches = n;
+  ctx->launches += n;
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+}  // extern "C++"
+
 int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
   if (!ctx || !d_vals) return 100;
   if (ctx->rowptr.empty()) return fail(ctx, 112, "no CSR pattern");
@@ -654,6 +707,7 @@ int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
   const int rc = xb::lu::analyze_and_factor(ctx->n, ctx->rowptr.data(), ctx->colind.data(), vals.data(), 0.001, ctx->lu_plan);
   if (rc == 1) return fail(ctx, 1, "matrix is structurally singular");
+  lu_drop_graphs(ctx);
   XG_CUDA(xb::lu::upload_plan(ctx->lu_plan, ctx->lu_dev));
   ctx->lu_ready = true;
   if (rc == 2) return fail(ctx, 2, "matrix is numerically singular");
@@ -663,8 +717,11 @@ int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
 int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
   if (!ctx || !d_vals) return 100;
   if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
-  ctx->launches += xb::lu::launch_refactor(ctx->lu_dev, d_vals, ctx->stream);
-  XG_CUDA(cudaGetLastError());
+  {
+    const int rc = lu_run(ctx, ctx->g_refactor, d_vals, nullptr, nullptr,
+                          [&] { return xb::lu::launch_refactor(ctx->lu_dev, d_vals, ctx->stream); });
+    if (rc) return rc;
+  }
   int status = 0;
   XG_CUDA(cudaMemcpyAsync(&status, ctx->lu_dev.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -675,9 +732,8 @@ int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
 int xgpu_lu_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x) {
   if (!ctx || !d_vals || !d_rhs || !d_x) return 100;
   if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
-  ctx->launches += xb::lu::launch_solve(ctx->lu_dev, d_vals, d_rhs, d_x, ctx->stream);
-  XG_CUDA(cudaGetLastError());
-  return 0;
+  return lu_run(ctx, ctx->g_solve, d_vals, d_rhs, d_x,
+                [&] { return xb::lu::launch_solve(ctx->lu_dev, d_vals, d_rhs, d_x, ctx->stream); });
 }
 
 int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colind, const double *vals,

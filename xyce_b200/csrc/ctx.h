@@ -93,6 +93,12 @@ struct xgpu_ctx {
   xb::lu::LuPlan lu_plan;
   xb::lu::LuDev lu_dev;
   bool lu_ready = false;
+  // CUDA graphs of the refactor / solve launch sequences (large diagonal blocks: one launch per level, hundreds of
+  // launches per call).  Captured on first use for a given set of device pointers, replayed afterwards;
+  // dropped whenever the plan changes (xgpu_lu_analyze).
+  struct LuGraph { cudaGraphExec_t exec = nullptr; const void *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; int launches = 0; };
+  LuGraph g_refactor, g_solve;
+  int lu_graphs = 1;          // option "lu_graphs": 0 = plain stream launches
 };
 
 int xg_fail(xgpu_ctx *c, int code, const std::string &msg);
