@@ -165,6 +165,25 @@ def tran_extra(device):
             "setup_s": t_setup, "first_call_s_incl_host_lu_analysis": t_first}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the host cores next to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the
+    pinned host buffers of the e2e path are first-touched on that NUMA node; returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return int(open(base + "/numa_node").read())
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     from xyce_b200 import workloads as wl
@@ -174,11 +193,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner / diagnostics: not on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = wl.inverter_array(args.inverters, seed=12345 + rank)
@@ -284,6 +303,7 @@ def run_ours(args):
                                    "loadDAEMatrices at a fixed operating point (BASELINE config 2)",
                        "instances_per_gpu": n_inst, "unknowns_per_gpu": n, "nnz_per_gpu": nnz,
                        "parallelism": "instances partitioned per rank, no data-path collective",
+                       "host_affinity": ("rank pinned to its GPU's NUMA node %s" % numa_node) if (numa_node is not None and numa_node >= 0) else "default (single NUMA node)",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                     "d2h_bytes_per_step": 8 * (4 * n + 2 * nnz)},
