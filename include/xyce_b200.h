@@ -82,7 +82,7 @@ int xgpu_b4_group_add(xgpu_ctx *ctx, int n_inst, const double *inst_d, const int
                       const int32_t *model_idx, const int32_t *size_idx, const int32_t *lids12,
                       const int32_t *sto_lid0, int sto_stride, const int32_t *sta_lid0, int sta_stride);
 /* ---- small compact models: junction diode (type 1), MOSFET level 1 (2), Gummel-Poon BJT (3), ADMS-shaped
- * series RLC (4) ----
+ * series RLC (4), ADMS-generated MVS 2.0.0 ETSOI transistor (5; N_DEV_ADMSmvs_2_0_0_etsoi.C) ----
  * One flat record per instance holding the model-card values and the temperature-adjusted instance
  * constants the reference computes in processParams/updateTemperature (field order:
  * xyce_b200/csrc/simple_fields.def), a flag word, the node LIDs in the device's own node order, and the

@@ -28,6 +28,7 @@
 #include <N_DEV_MOSFET1.h>
 #include <N_DEV_Diode.h>
 #include <N_DEV_BJT.h>
+#include <N_DEV_ADMSmvs_2_0_0_etsoi.h>
 #include <N_DEV_Configuration.h>
 #include <N_DEV_DeviceBlock.h>
 #include <N_DEV_DeviceMaster.h>
@@ -162,7 +163,7 @@ struct Ctx {
   DeviceOptions devOptions;
   SolverState solState;
   ExternData extData;
-  RawVector vSol, vCurrSta, vNextSta, vCurrSto, vNextSto;
+  RawVector vSol, vCurrSta, vNextSta, vCurrSto, vNextSto, vF, vQ;
   MatrixLoadData mlData;
   FactoryBlock *fb = 0;
   // one Master per device type, in creation order (= DeviceMgr::devicePtrVec_ order)
@@ -176,6 +177,7 @@ struct Ctx {
     else if (t == "m1") { auto *c = &Config<MOSFET1::Traits>::addConfiguration(); cfg = c; m = MOSFET1::Traits::factory(*c, *fb); }
     else if (t == "d") { auto *c = &Config<Diode::Traits>::addConfiguration(); cfg = c; m = Diode::Traits::factory(*c, *fb); }
     else if (t == "q") { auto *c = &Config<BJT::Traits>::addConfiguration(); cfg = c; m = BJT::Traits::factory(*c, *fb); }
+    else if (t == "mvs") { auto *c = &Config<ADMSmvs_2_0_0_etsoi::Traits>::addConfiguration(); cfg = c; m = ADMSmvs_2_0_0_etsoi::Traits::factory(*c, *fb); }
     else return -1;
     masters.push_back(m); masterType.push_back(t); masterCfg.push_back(cfg);
     return (int)masters.size() - 1;
@@ -233,7 +235,7 @@ void *xref_new() {
 
 int xref_set_num_external_nodes(void *h, int n) { ((Ctx *)h)->nExt = n; return 0; }
 
-// devtype: "b4" BSIM4 (level 54), "m1" MOSFET level 1, "d" diode, "q" Gummel-Poon BJT.
+// devtype: "b4" BSIM4 (level 54), "m1" MOSFET level 1, "d" diode, "q" Gummel-Poon BJT, "mvs" ADMS-generated MVS 2.0.0 ETSOI.
 // mtype: the .model type string in upper case (NMOS, PMOS, D, NPN, PNP).
 int xref_add_model(void *h, const char *devtype, const char *name, const char *mtype, int level, int np,
                    const char **keys, const double *vals) {
@@ -348,6 +350,8 @@ int xref_finalize(void *h) {
   e.nextStoVectorRawPtr = c->nextSto.data(); e.currStoVectorRawPtr = e.lastStoVectorRawPtr = c->currSto.data();
   c->vSol.v = &c->sol; c->vCurrSta.v = &c->currSta; c->vNextSta.v = &c->nextSta; c->vCurrSto.v = &c->currSto; c->vNextSto.v = &c->nextSto;
   e.nextSolVectorPtr = e.currSolVectorPtr = e.lastSolVectorPtr = &c->vSol;
+  c->vF.v = &c->f; c->vQ.v = &c->q;
+  e.daeFVectorPtr = &c->vF; e.daeQVectorPtr = &c->vQ;      // ADMS-generated devices load through the Linear::Vector objects
   e.currStaVectorPtr = e.lastStaVectorPtr = &c->vCurrSta; e.nextStaVectorPtr = &c->vNextSta;
   e.currStoVectorPtr = e.lastStoVectorPtr = &c->vCurrSto; e.nextStoVectorPtr = &c->vNextSto;
   for (auto &r : c->insts) r.inst->setupPointers();
@@ -529,6 +533,21 @@ int xref_diode_export(void *h, int idx, double *rec, int *flags, int *lids3) {
   const int g = c->n;
   const int l[3] = {in.li_Pos, in.li_Neg, in.li_Pri};
   for (int i = 0; i < 3; ++i) lids3[i] = (l[i] == g) ? -1 : l[i];
+  return k;
+}
+
+// ADMS-generated MVS 2.0.0 ETSOI: model-card record in XB_MVS_FIELDS order + the 7 unknown LIDs (d g s di si sf branch)
+int xref_mvs_export(void *h, int idx, double *rec, int *lids7) {
+  Ctx *c = (Ctx *)h;
+  ADMSmvs_2_0_0_etsoi::Instance &in = *static_cast<ADMSmvs_2_0_0_etsoi::Instance *>(c->insts[idx].inst);
+  ADMSmvs_2_0_0_etsoi::Model &mo = in.model_;
+  int k = 0;
+#define X(n) rec[k++] = mo.n;
+  XB_MVS_FIELDS(X)
+#undef X
+  const int g = c->n;
+  const int l[7] = {in.li_d, in.li_g, in.li_s, in.li_di, in.li_si, in.li_sf, in.li_BRA_sf_GND};
+  for (int i = 0; i < 7; ++i) lids7[i] = (l[i] == g) ? -1 : l[i];
   return k;
 }
 

@@ -69,7 +69,16 @@ MOS1_SLOT_COL = [0, 4, 1, 3, 4, 5, 2, 5, 1, 3, 4, 5, 0, 1, 3, 4, 5, 1, 2, 3, 4, 
 BJT_SLOT_ROW = [0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6]
 BJT_SLOT_COL = [0, 4, 1, 4, 5, 6, 2, 6, 3, 4, 0, 1, 3, 4, 5, 6, 1, 4, 5, 6, 2, 4, 5, 6]
 # (type id, devtype key of the oracle harness, nodes, store entries used, state entries)
-SIMPLE = {"mos1": (2, "m1", 6, 6, 8, MOS1_SLOT_ROW, MOS1_SLOT_COL), "bjt": (3, "q", 7, 3, 6, BJT_SLOT_ROW, BJT_SLOT_COL)}
+MVS_SLOT_ROW = [0, 0, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 6, 6, 6, 6]
+MVS_SLOT_COL = [3, 0, 2, 4, 4, 3, 5, 0, 4, 3, 5, 2, 6, 5, 4, 1, 3]
+SIMPLE = {"mos1": (2, "m1", 6, 6, 8, MOS1_SLOT_ROW, MOS1_SLOT_COL), "bjt": (3, "q", 7, 3, 6, BJT_SLOT_ROW, BJT_SLOT_COL),
+          "mvs": (5, "mvs", 7, 0, 0, MVS_SLOT_ROW, MVS_SLOT_COL)}
+# ADMS-generated MVS 2.0.0 ETSOI model cards (src/DeviceModelPKG/ADMS/N_DEV_ADMSmvs_2_0_0_etsoi.C:119-250 defaults = "nmos")
+MVS_CARDS = {
+    "nmos": ("NMOS", dict(TYPE=1)),
+    "pmos": ("PMOS", dict(TYPE=-1, W=2e-6, LGDR=60e-9, RS0=200e-6, N0=1.5, DELTA=0.15, ND=0.05, MU_EFF=0.6, KSEE=0.15)),
+    "short": ("NMOS", dict(TYPE=1, LGDR=32e-9, DLG=6e-9, BETA=1.8, THETA=2.2, TJUN=350.0, NU=0.6, ENERGY_DIFF_VOLT=0.1)),
+}
 
 MOS1_CARDS = {
     "basic": ("NMOS", dict(VTO=0.7, KP=1.1e-4, GAMMA=0.4, PHI=0.65, LAMBDA=0.02, TOX=2e-8, CBD=2e-14, CBS=2e-14, IS=1e-14,
@@ -100,6 +109,11 @@ def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0):
             ip = dict(L=float(rng.choice([1e-6, 2e-6])), W=float(rng.choice([5e-6, 2e-5])), AD=2e-11, AS=2e-11, PD=2e-5, PS=2e-5,
                       NRD=1.0, NRS=1.0)
             c.add_dev_instance("m1", "M:%d" % i, "mmod", [nt * i, nt * i + 1, nt * i + 2, nt * i + 3], ip)
+    elif kind == "mvs":
+        mtype, p = MVS_CARDS[card]
+        c.add_dev_model("mvs", "vsmod", mtype, 1, p)
+        for i in range(n_dev):
+            c.add_dev_instance("mvs", "M:%d" % i, "vsmod", [nt * i, nt * i + 1, nt * i + 2], {})
     else:
         mtype, p = BJT_CARDS[card]
         c.add_dev_model("q", "qmod", mtype, 1, p)

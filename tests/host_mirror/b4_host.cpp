@@ -11,6 +11,7 @@
 #include "../../xyce_b200/csrc/diode_eval.h"
 #include "../../xyce_b200/csrc/mos1_eval.h"
 #include "../../xyce_b200/csrc/bjt_eval.h"
+#include "../../xyce_b200/csrc/adms_mvs_eval.h"
 
 using namespace xb;
 using namespace xb::b4;
@@ -181,6 +182,23 @@ int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const
     for (int i = 0; i < 3; ++i) out[k++] = to_double(o.store[i]);
     for (int i = 0; i < D::kNumState; ++i) out[k++] = to_double(o.state[i]);
     out[k++] = o.origFlag;
+  } else if (type == 5) {      // ADMS-generated MVS 2.0.0 ETSOI: static contributions only, no store / state, no limiting
+    namespace D = xb::adms::mvs;
+    D::Rec R; int j = 0;
+#define GET(n) R.n = rec[j++];
+    XB_MVS_FIELDS(GET)
+#undef GET
+    real V[D::kNodes];
+    for (int i = 0; i < D::kNodes; ++i) V[i] = Vn[i];
+    D::Out o;
+    D::evaluate(R, V, o);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.F[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.Q[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.FL[i]);
+    for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.QL[i]);
+    for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JF[i]);
+    for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JQ[i]);
+    out[k++] = 1;
   }
   return k;
 }

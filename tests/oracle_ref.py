@@ -92,10 +92,13 @@ class RefCircuit:
         """record / flag word / node LIDs of a MOSFET level 1 ("m1") or BJT ("q") instance"""
         rec = np.zeros(96)
         flags = C.c_int()
-        nn = {"m1": 6, "q": 7}[devtype]
+        nn = {"m1": 6, "q": 7, "mvs": 7}[devtype]
         lids = np.zeros(nn, dtype=np.int32)
-        fn = {"m1": self.lib.xref_mos1_export, "q": self.lib.xref_bjt_export}[devtype]
-        k = fn(self.h, idx, dptr(rec), C.byref(flags), iptr(lids))
+        if devtype == "mvs":          # ADMS-generated MVS 2.0.0 ETSOI: no flag word
+            k = self.lib.xref_mvs_export(self.h, idx, dptr(rec), iptr(lids))
+        else:
+            fn = {"m1": self.lib.xref_mos1_export, "q": self.lib.xref_bjt_export}[devtype]
+            k = fn(self.h, idx, dptr(rec), C.byref(flags), iptr(lids))
         info = self.inst_info(idx)
         return dict(rec=rec[:k].copy(), flags=flags.value, lids=lids, sto0=info["sto0"], sta0=info["sta0"])
 

@@ -6,7 +6,7 @@ import pytest
 import oracle_ref
 import xyce_b200
 from b4_common import rel_err, solver_state
-from dev_common import BJT_CARDS, DIODE_CARDS, MOS1_CARDS, SIMPLE, diode_circuit, simple_circuit
+from dev_common import BJT_CARDS, DIODE_CARDS, MOS1_CARDS, MVS_CARDS, SIMPLE, diode_circuit, simple_circuit
 
 pytestmark = pytest.mark.gpu
 
@@ -73,6 +73,83 @@ def test_mos1_and_bjt(kind, card, case):
     if case == "tran_init":
         assert rel_err(eng.get_state(3), ref.get_state()["curr_sta"], 1e-30) < 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("case", ["tran1", "dcop2"])
+@pytest.mark.parametrize("card", sorted(MVS_CARDS))
+def test_adms_mvs(card, case):
+    """ADMS-generated compact model (MVS 2.0.0 ETSOI, src/DeviceModelPKG/ADMS/N_DEV_ADMSmvs_2_0_0_etsoi.C: 3 external +
+    3 internal nodes + the branch of a potential contribution, 17 Jacobian entries) against the reference's generated C++."""
+    type_id, key, nodes, nstore, nstate, srow, scol = SIMPLE["mvs"]
+    ref = simple_circuit(oracle_ref.RefCircuit, "mvs", card, n_dev=150, seed=5)
+    ex = [ref.dev_export(i, key) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(type_id, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.finalize()
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-0.6, 1.0, ref.n)
+    flags = dict(tran1=dict(transient=1, newtonIter=1), dcop2=dict(dcop=1, tranop=1, newtonIter=2))[case]
+    ref.set_flags(**flags)
+    want = ref.load(x)
+    got = eng.load_host(x, solver_state(**flags))
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, k
+    assert np.any(want["dFdx"] != 0.0) and not np.any(want["q"]) and eng.all_converged()
+    eng.close()
+
+
+def test_adms_mvs_amplifier_dcop_and_tran_match_reference_flow():
+    """Common-source stage around the ADMS-generated MVS transistor (resistor load, load capacitor, SIN input):
+    DC operating point, then .TRAN, on the GPU against the same driver around the reference's generated device object
+    and Kundert Sparse -- identical Newton iteration counts, waveforms within RELTOL / ABSTOL."""
+    IN, VDD, D, BR_IN, BR_DD = range(5)
+    ref = oracle_ref.RefCircuit(5)
+    mt, mp = MVS_CARDS["nmos"]
+    ref.add_dev_model("mvs", "vsmod", mt, 1, mp)
+    ref.add_dev_instance("mvs", "M:1", "vsmod", [D, IN, -1], {})
+    g, c = [], []
+    def res(a, b, r):
+        for (i, j, v) in ((a, a, 1 / r), (a, b, -1 / r), (b, a, -1 / r), (b, b, 1 / r)):
+            if i >= 0 and j >= 0: g.append((i, j, v))
+    def cap(a, b, v):
+        for (i, j, sgn) in ((a, a, v), (a, b, -v), (b, a, -v), (b, b, v)):
+            if i >= 0 and j >= 0: c.append((i, j, sgn))
+    for node, br in ((IN, BR_IN), (VDD, BR_DD)):
+        g.append((node, br, 1.0)); g.append((br, node, 1.0))
+    res(VDD, D, 2e3); cap(D, -1, 5e-15); cap(IN, D, 1e-15)
+    lin = dict(g_row=np.array([t[0] for t in g], dtype=np.int32), g_col=np.array([t[1] for t in g], dtype=np.int32),
+               g_val=np.array([t[2] for t in g]), c_row=np.array([t[0] for t in c], dtype=np.int32),
+               c_col=np.array([t[1] for t in c], dtype=np.int32), c_val=np.array([t[2] for t in c]))
+    src = dict(row=np.array([BR_IN, BR_DD], dtype=np.int32), scale=np.ones(2), type=np.array([2, 0], dtype=np.int32),
+               params=np.array([[0.0, 0.2, 5e9, 0, 0, 0, 0], [0.9, 0, 0, 0, 0, 0, 0]]))
+    ref.add_pattern_entries(np.concatenate([lin["g_row"], lin["c_row"]]), np.concatenate([lin["g_col"], lin["c_col"]]))
+    ref.finalize()
+    x0 = np.zeros(ref.n); x0[VDD] = 0.9; x0[D] = 0.9
+    probes = list(range(ref.n))
+    ref.set_flags(transient=1)
+    want = ref.tran_run(x0, 4e-10, 1e-12, probes, lin, src, dcop=1)
+    e = ref.dev_export(0, "mvs")
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(5, np.array([e["rec"]]), [e["flags"]], np.array([e["lids"]]), [e["sto0"]], 1, [e["sta0"]], 1)
+    eng.set_linear(lin["g_row"], lin["g_col"], lin["g_val"], lin["c_row"], lin["c_col"], lin["c_val"])
+    eng.set_sources(src["row"], src["scale"], src["type"], src["params"])
+    eng.finalize()
+    got = eng.tran_run(x0, 4e-10, 1e-12, probes, dcop=1)
+    eng.close()
+    assert want["rc"] == 0 and got["rc"] == 0, got.get("error")
+    assert got["stats"]["dcop_newton_iters"] == want["stats"]["dcop_newton_iters"] >= 2
+    assert got["stats"]["accepted"] == want["stats"]["accepted"] and got["stats"]["rejected"] == want["stats"]["rejected"]
+    assert np.array_equal(got["steps"][:, 2], want["steps"][:, 2])
+    tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
+    assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
+    # it amplifies: the drain swings by more than the 0.2 V input amplitude
+    assert 0.05 < want["wave"][0, D] < 0.9 and np.ptp(want["wave"][:, D]) > 0.3
 
 
 def test_mixed_device_types_in_one_system():

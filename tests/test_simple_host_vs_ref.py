@@ -6,7 +6,7 @@ import pytest
 
 import oracle_ref
 from b4_common import rel_err
-from dev_common import BJT_CARDS, MOS1_CARDS, SIMPLE, HostDevices, assemble, simple_circuit
+from dev_common import BJT_CARDS, MOS1_CARDS, MVS_CARDS, SIMPLE, HostDevices, assemble, simple_circuit
 
 pytestmark = pytest.mark.skipif(not oracle_ref.available(), reason="oracle/_ref not built")
 
@@ -22,7 +22,7 @@ def run(kind, card, case, seed=3):
     rng = np.random.default_rng(seed + 1)
     flags = CASES[case]
     ref.set_flags(**flags)
-    x = rng.uniform(-1.5, 1.5, ref.n)
+    x = rng.uniform(-1.5, 1.5, ref.n) if kind != "mvs" else rng.uniform(-0.6, 1.0, ref.n)
     nsto, csto = rng.normal(0.2, 0.5, ref.n_sto), rng.normal(0.2, 0.5, ref.n_sto)
     csta = rng.normal(0.0, 1e-14, ref.n_sta)
     ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta)
@@ -54,3 +54,11 @@ def test_mos1(card, case):
 @pytest.mark.parametrize("card", sorted(BJT_CARDS))
 def test_bjt(card, case):
     run("bjt", card, case)
+
+
+@pytest.mark.parametrize("case", ["tran1", "dcop2"])
+@pytest.mark.parametrize("card", sorted(MVS_CARDS))
+def test_adms_mvs(card, case):
+    """ADMS-generated model (MVS 2.0.0 ETSOI, N_DEV_ADMSmvs_2_0_0_etsoi.C): 3 internal nodes + a branch equation; the
+    reference object runs through the generic per-instance DeviceMaster loops (Core/N_DEV_DeviceMaster.h:666-823)"""
+    run("mvs", card, case)

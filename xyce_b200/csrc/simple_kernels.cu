@@ -3,6 +3,7 @@
 #include "simple_kernels.cuh"
 #include "diode_eval.h"
 #include "adms_rlc_eval.h"
+#include "adms_mvs_eval.h"
 #include "bjt_eval.h"
 #include "mos1_eval.h"
 
@@ -157,6 +158,32 @@ __global__ void __launch_bounds__(128) rlc_kernel(GroupDev g, b4::LoadArgs a) {
   }
 }
 
+// ADMS-generated MVS 2.0.0 ETSOI (N_DEV_ADMSmvs_2_0_0_etsoi.C): static contributions only, no limiting, no state
+__global__ void __launch_bounds__(128) mvs_kernel(GroupDev g, b4::LoadArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const int n = g.n;
+  namespace M = adms::mvs;
+  M::Rec R;
+  {
+    int k = 0;
+#define LD(name) R.name = __ldg(g.rec + (size_t)(k++) * n + i);
+    XB_MVS_FIELDS(LD)
+#undef LD
+  }
+  real V[M::kNodes];
+#pragma unroll
+  for (int t = 0; t < M::kNodes; ++t) V[t] = gatherv(a.sol, __ldg(g.lids + (size_t)t * n + i));
+  M::Out o;
+  M::evaluate(R, V, o);
+  g.orig_flag[i] = 1;
+  store_planes<M::Out, M::kNodes, M::kSlots>(g, a, o, i);
+}
+
+const int kMvsRow[adms::mvs::kSlots] = {0, 0, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 6, 6, 6, 6};
+const int kMvsCol[adms::mvs::kSlots] = {3, 0, 2, 4, 4, 3, 5, 0, 4, 3, 5, 2, 6, 5, 4, 1, 3};
+const TypeInfo kMvsInfo = {adms::mvs::kNodes, adms::mvs::kSlots, adms::mvs::kNumFields, 0, 0, kMvsRow, kMvsCol};
+
 const int kRlcRow[adms::rlc::kSlots] = {0, 0, 2, 2, 2, 3, 3, 3, 1, 4, 4, 4};
 const int kRlcCol[adms::rlc::kSlots] = {0, 2, 0, 2, 3, 2, 3, 4, 4, 3, 1, 4};
 const TypeInfo kRlcInfo = {adms::rlc::kNodes, adms::rlc::kSlots, adms::rlc::kNumFields, 0, 0, kRlcRow, kRlcCol};
@@ -180,6 +207,7 @@ const TypeInfo *type_info(int type) {
     case kMos1: return &kMos1Info;
     case kBjt: return &kBjtInfo;
     case kRlc: return &kRlcInfo;
+    case kMvs: return &kMvsInfo;
     default: return nullptr;
   }
 }
@@ -192,6 +220,7 @@ void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
     case kMos1: mos1_kernel<<<blocks, 128, 0, s>>>(g, a); break;
     case kBjt: bjt_kernel<<<blocks, 128, 0, s>>>(g, a); break;
     case kRlc: rlc_kernel<<<blocks, 128, 0, s>>>(g, a); break;
+    case kMvs: mvs_kernel<<<blocks, 128, 0, s>>>(g, a); break;
     default: break;
   }
 }

@@ -7,7 +7,7 @@
 namespace xb {
 namespace simple {
 
-enum Type { kDiode = 1, kMos1 = 2, kBjt = 3, kRlc = 4 };
+enum Type { kDiode = 1, kMos1 = 2, kBjt = 3, kRlc = 4, kMvs = 5 };
 
 struct GroupDev {
   int type, n;
