@@ -148,21 +148,26 @@ def tran_extra(device):
     w = wl.ring_oscillator_array(4950, 101)
     t0 = time.perf_counter()
     eng = wl.build_engine(w, device=device)
+    if os.environ.get("XYCE_B200_LU_GRAPHS"):
+        eng.set_option("lu_graphs", int(os.environ["XYCE_B200_LU_GRAPHS"]))
     t_setup = time.perf_counter() - t0
     t0 = time.perf_counter()
     r0 = eng.tran_run(w["x"], 2e-12, 1e-12, [0])          # first call: includes the one-time host LU analysis
     t_first = time.perf_counter() - t0
-    eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
-    t0 = time.perf_counter()
-    r = eng.tran_run(w["x"], 4e-11, 1e-12, [0])           # LU pattern already analysed: refactor-only path
-    dt = time.perf_counter() - t0
+    walls = []
+    for _ in range(3):                                    # same run three times; the fastest is reported, all are listed
+        eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
+        t0 = time.perf_counter()
+        r = eng.tran_run(w["x"], 4e-11, 1e-12, [0])       # LU pattern already analysed: refactor-only path
+        walls.append(time.perf_counter() - t0)
+    dt = min(walls)
     s = r["stats"]
     eng.close()
     return {"workload": "4950 x 101-stage BSIM4 ring oscillators sharing VDD (999 900 MOSFETs, %d unknowns), .TRAN 40 ps" % w["n_unknowns"],
             "rc": r["rc"], "accepted_steps": s["accepted"], "rejected_steps": s["attempts"] - s["accepted"],
             "newton_iters": s["newton_iters"], "wall_s": dt, "ms_per_newton_iter": 1e3 * dt / max(s["newton_iters"], 1),
             "newton_iters_per_s": s["newton_iters"] / dt, "lu_analyses_in_timed_run": s["lu_analyses"],
-            "setup_s": t_setup, "first_call_s_incl_host_lu_analysis": t_first}
+            "wall_s_all_runs": walls, "setup_s": t_setup, "first_call_s_incl_host_lu_analysis": t_first}
 
 
 def bind_to_gpu_numa_node(torch, local):
