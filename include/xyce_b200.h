@@ -141,6 +141,20 @@ int xgpu_jacobian_combine(xgpu_ctx *ctx, double qscalar, const double *d_dQdx, d
  * off-diagonal-block entries, solve levels, refactor flops. */
 int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals);
 int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals);
+/* Symbolic result of an EXTERNAL factorization instead of xgpu_lu_analyze: what a KLU-enabled Xyce build gets from
+ * klu_analyze + klu_factor through klu_extract (P, Q, block boundaries R, patterns of L and U; Amesos_Klu holds
+ * them after SymbolicFactorization / NumericFactorization, N_LAS_AmesosSolver.C:335, :363) -- so that the GPU
+ * refactorization and solves run on KLU's own ordering and pivot sequence.  Position t of the permuted matrix holds
+ * row row_perm[t] and column col_perm[t] of A; diagonal blocks [block_ptr[b], block_ptr[b+1]); L, U in CSC over
+ * positions (an explicit unit diagonal in L and any pivot position inside a U column are accepted).  No row scaling
+ * (KLU scale = 0).  Follow with xgpu_lu_refactor (numeric values) and xgpu_lu_solve.  3 = malformed input. */
+int xgpu_lu_import(xgpu_ctx *ctx, const int32_t *row_perm, const int32_t *col_perm, int n_blocks,
+                   const int32_t *block_ptr, const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui);
+/* The current plan in the same conventions (klu_extract analogue): sizes4 = {n, n_blocks, nnz(L), nnz(U)};
+ * any output pointer may be NULL; Lx / Ux = values of the latest factorization on the device. */
+int xgpu_lu_export_sizes(const xgpu_ctx *ctx, int32_t *sizes4);
+int xgpu_lu_export(xgpu_ctx *ctx, int32_t *row_perm, int32_t *col_perm, int32_t *block_ptr, int32_t *Lp, int32_t *Li,
+                   double *Lx, int32_t *Up, int32_t *Ui, double *Ux);
 int xgpu_lu_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x);
 int xgpu_lu_info(const xgpu_ctx *ctx, double *info8);
 /* Host-only symbolic analysis + pivoting factorization + solve (no GPU, no context): the code path

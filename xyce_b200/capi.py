@@ -261,6 +261,29 @@ class Engine:
             self._chk(rc)
         return rc
 
+    def lu_import(self, row_perm, col_perm, block_ptr, Lp, Li, Up, Ui):
+        """plan from an external factorization (xgpu_lu_import); raises on malformed input"""
+        a = [_i32(v) for v in (row_perm, col_perm, block_ptr, Lp, Li, Up, Ui)]
+        self._chk(self.lib.xgpu_lu_import(self.h, _ip(a[0]), _ip(a[1]), len(a[2]) - 1, _ip(a[2]), _ip(a[3]), _ip(a[4]),
+                                          _ip(a[5]), _ip(a[6])))
+
+    def lu_export(self):
+        sz = np.zeros(4, dtype=np.int32)
+        self._chk(self.lib.xgpu_lu_export_sizes(self.h, _ip(sz)))
+        n, nb, nl, nu = [int(v) for v in sz]
+        out = dict(row_perm=np.zeros(n, dtype=np.int32), col_perm=np.zeros(n, dtype=np.int32),
+                   block_ptr=np.zeros(nb + 1, dtype=np.int32), Lp=np.zeros(n + 1, dtype=np.int32),
+                   Li=np.zeros(max(nl, 1), dtype=np.int32), Lx=np.zeros(max(nl, 1)), Up=np.zeros(n + 1, dtype=np.int32),
+                   Ui=np.zeros(max(nu, 1), dtype=np.int32), Ux=np.zeros(max(nu, 1)))
+        self._chk(self.lib.xgpu_lu_export(self.h, _ip(out["row_perm"]), _ip(out["col_perm"]), _ip(out["block_ptr"]),
+                                          _ip(out["Lp"]), _ip(out["Li"]), _dp(out["Lx"]), _ip(out["Up"]), _ip(out["Ui"]),
+                                          _dp(out["Ux"])))
+        for k in ("Li", "Lx"):
+            out[k] = out[k][:nl]
+        for k in ("Ui", "Ux"):
+            out[k] = out[k][:nu]
+        return out
+
     def lu_refactor(self, d_vals):
         rc = self.lib.xgpu_lu_refactor(self.h, C.c_void_p(d_vals))
         if rc not in (0, 2):

@@ -714,6 +714,48 @@ int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
   return 0;
 }
 
+int xgpu_lu_import(xgpu_ctx *ctx, const int32_t *row_perm, const int32_t *col_perm, int nblocks, const int32_t *block_ptr,
+                   const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui) {
+  if (!ctx || !row_perm || !col_perm || !block_ptr || !Lp || !Li || !Up || !Ui) return 100;
+  if (ctx->rowptr.empty()) return fail(ctx, 112, "no CSR pattern");
+  XG_CUDA(cudaSetDevice(ctx->device));
+  const char *why = "";
+  const int rc = xb::lu::import_factorization(ctx->n, ctx->rowptr.data(), ctx->colind.data(), row_perm, col_perm, nblocks,
+                                              block_ptr, Lp, Li, Up, Ui, ctx->lu_plan, &why);
+  if (rc) { ctx->lu_ready = false; return fail(ctx, 3, std::string("xgpu_lu_import: ") + why); }
+  lu_drop_graphs(ctx);
+  XG_CUDA(xb::lu::upload_plan(ctx->lu_plan, ctx->lu_dev));
+  ctx->lu_ready = true;
+  return 0;
+}
+
+int xgpu_lu_export_sizes(const xgpu_ctx *ctx, int32_t *sizes4) {
+  if (!ctx || !sizes4) return 100;
+  if (!ctx->lu_ready) return 113;
+  const xb::lu::LuPlan &p = ctx->lu_plan;
+  sizes4[0] = p.n; sizes4[1] = (int)p.block_ptr.size() - 1; sizes4[2] = (int)p.Li.size(); sizes4[3] = (int)p.Ui.size();
+  return 0;
+}
+
+int xgpu_lu_export(xgpu_ctx *ctx, int32_t *row_perm, int32_t *col_perm, int32_t *block_ptr, int32_t *Lp, int32_t *Li,
+                   double *Lx, int32_t *Up, int32_t *Ui, double *Ux) {
+  if (!ctx) return 100;
+  if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
+  const xb::lu::LuPlan &p = ctx->lu_plan;
+  if (row_perm) std::copy(p.row_perm.begin(), p.row_perm.end(), row_perm);
+  if (col_perm) std::copy(p.col_perm.begin(), p.col_perm.end(), col_perm);
+  if (block_ptr) std::copy(p.block_ptr.begin(), p.block_ptr.end(), block_ptr);
+  if (Lp) std::copy(p.Lp.begin(), p.Lp.end(), Lp);
+  if (Li) std::copy(p.Li.begin(), p.Li.end(), Li);
+  if (Up) std::copy(p.Up.begin(), p.Up.end(), Up);
+  if (Ui) std::copy(p.Ui.begin(), p.Ui.end(), Ui);
+  // numeric values of the latest factorization on the device
+  if (Lx && !p.Li.empty()) XG_CUDA(cudaMemcpyAsync(Lx, ctx->lu_dev.Lx, p.Li.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (Ux && !p.Ui.empty()) XG_CUDA(cudaMemcpyAsync(Ux, ctx->lu_dev.Ux, p.Ui.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
   if (!ctx || !d_vals) return 100;
   if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");

@@ -67,6 +67,11 @@ constexpr int kBigBlock = 512, kDenseCol = 4096, kLongRow = 2048, kStagedBytes =
 int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol,
                        LuPlan &plan);
 void solve_host(const LuPlan &plan, const double *b, double *x);
+// Plan from an external factorization's permutations, block boundaries and L / U patterns (lu_host.cpp);
+// numeric values come from the first refactorization on the GPU.  0 ok, 3 malformed input.
+int import_factorization(int n, const int *rowptr, const int *colind, const int *row_perm, const int *col_perm,
+                         int nblocks, const int *block_ptr, const int *Lp, const int *Li, const int *Up, const int *Ui,
+                         LuPlan &plan, const char **why);
 
 // Device-resident copy of a plan plus work space; created by upload_plan, used by the kernels.
 struct LuDev {

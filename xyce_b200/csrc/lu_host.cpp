@@ -253,99 +253,15 @@ void factor_block(int n, const std::vector<std::vector<std::pair<int, double>>> 
 
 }  // namespace
 
-int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol, LuPlan &plan) {
-  plan = LuPlan();
-  plan.n = n;
-  const int nnz = rowptr[n];
-  plan.nnz_a = nnz;
-  // CSR -> CSC with a back-pointer to the CSR value index
-  std::vector<int> Ap(n + 1, 0), Ai(nnz), Aidx(nnz);
-  for (int k = 0; k < nnz; ++k) ++Ap[colind[k] + 1];
-  for (int j = 0; j < n; ++j) Ap[j + 1] += Ap[j];
-  {
-    std::vector<int> fill(Ap.begin(), Ap.end() - 1);
-    for (int i = 0; i < n; ++i)
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { const int p = fill[colind[k]]++; Ai[p] = i; Aidx[p] = k; }
-  }
-  // 1. maximum transversal: column matched to each row; Q0[i] = column placed at diagonal position i
-  std::vector<int> col_of_row;
-  const int nmatch = max_transversal(n, Ap, Ai, col_of_row);
-  if (nmatch < n) { plan.structurally_singular = true; return 1; }
-  // permuted pattern C = A * Q0 has c(i, i') = a(i, col_of_row[i']): column i' of C is column col_of_row[i'] of A
-  std::vector<int> Cp(n + 1, 0), Ci;
-  Ci.reserve(nnz);
-  for (int jp = 0; jp < n; ++jp) {
-    const int j = col_of_row[jp];
-    for (int p = Ap[j]; p < Ap[j + 1]; ++p) Ci.push_back(Ai[p]);
-    Cp[jp + 1] = (int)Ci.size();
-  }
-  // 2. strongly connected components of C (symmetric permutation)
-  std::vector<int> sperm, bptr;
-  strong_components(n, Cp, Ci, sperm, bptr);
+// Everything the GPU kernels need beyond the permutations and the L / U patterns: scatter maps A -> factor slots,
+// off-diagonal entries by column and by row, block levels, pull lists, large-block schedules, flop count.
+// Inputs already in the plan: n, block_ptr, row_perm (through new_rowpos), col_perm, Lp / Li / Up / Ui.
+// Ap / Ai / Aidx: CSC pattern of A with the CSR value index of every entry; vals may be null (imported plans).
+static void finish_plan(LuPlan &plan, const std::vector<int> &Ap, const std::vector<int> &Ai, const std::vector<int> &Aidx,
+                        const double *vals, const std::vector<int> &new_rowpos) {
+  const int n = plan.n;
+  const std::vector<int> &bptr = plan.block_ptr;
   const int nblocks = (int)bptr.size() - 1;
-  // 3. per-block fill-reducing ordering (within-block symmetric permutation)
-  std::vector<int> where(n, -1), blk_of(n, -1);
-  for (int b = 0; b < nblocks; ++b)
-    for (int t = bptr[b]; t < bptr[b + 1]; ++t) blk_of[sperm[t]] = b;
-  std::vector<int> final_order(n);   // position -> index in C numbering
-  {
-    std::vector<int> local(n, -1);
-    for (int b = 0; b < nblocks; ++b) {
-      const int nb = bptr[b + 1] - bptr[b];
-      if (nb <= 2) { for (int t = bptr[b]; t < bptr[b + 1]; ++t) final_order[t] = sperm[t]; continue; }
-      for (int t = 0; t < nb; ++t) local[sperm[bptr[b] + t]] = t;
-      std::vector<std::vector<int>> adj(nb);
-      for (int t = 0; t < nb; ++t) {
-        const int jc = sperm[bptr[b] + t];
-        for (int p = Cp[jc]; p < Cp[jc + 1]; ++p) {
-          const int ic = Ci[p];
-          if (blk_of[ic] != b || ic == jc) continue;
-          adj[t].push_back(local[ic]); adj[local[ic]].push_back(t);
-        }
-      }
-      std::vector<int> ord;
-      min_degree(nb, adj, ord);
-      for (int t = 0; t < nb; ++t) final_order[bptr[b] + t] = sperm[bptr[b] + ord[t]];
-    }
-  }
-  for (int t = 0; t < n; ++t) where[final_order[t]] = t;   // C index -> position
-  // At this point position t holds row final_order[t] (of A) and column col_of_row[final_order[t]].
-  std::vector<int> rowpos(n), colpos(n);
-  for (int t = 0; t < n; ++t) { rowpos[final_order[t]] = t; colpos[col_of_row[final_order[t]]] = t; }
-
-  // 4. factor each diagonal block; collect off-diagonal entries
-  plan.block_ptr = bptr;
-  plan.Lp.assign(1, 0); plan.Up.assign(1, 0);
-  plan.row_perm.assign(n, -1);   // position -> row of A   (includes pivoting)
-  plan.col_perm.assign(n, -1);   // position -> column of A
-  std::vector<int> a_row(n), a_col(n);
-  for (int t = 0; t < n; ++t) { a_row[t] = final_order[t]; a_col[t] = col_of_row[final_order[t]]; }
-  std::vector<int> pre_rowpos(rowpos);    // pre-pivot row positions
-  std::vector<int> new_rowpos(n, -1);     // row of A -> final position
-  plan.singular = false;
-  for (int b = 0; b < nblocks; ++b) {
-    const int k0 = bptr[b], nb = bptr[b + 1] - bptr[b];
-    std::vector<std::vector<std::pair<int, double>>> cols(nb);
-    for (int t = 0; t < nb; ++t) {
-      const int j = a_col[k0 + t];
-      for (int p = Ap[j]; p < Ap[j + 1]; ++p) {
-        const int rp = pre_rowpos[Ai[p]];
-        if (rp >= k0 && rp < k0 + nb) cols[t].push_back(std::make_pair(rp - k0, vals[Aidx[p]]));
-      }
-    }
-    BlockLU f;
-    factor_block(nb, cols, pivot_tol, f);
-    if (f.singular) plan.singular = true;
-    for (int r = 0; r < nb; ++r) new_rowpos[a_row[k0 + r]] = k0 + f.pinv[r];
-    for (int k = 0; k < nb; ++k) {
-      for (int p = f.Lp[k]; p < f.Lp[k + 1]; ++p) { plan.Li.push_back(k0 + f.Li[p]); plan.Lx.push_back(f.Lx[p]); }
-      plan.Lp.push_back((int)plan.Li.size());
-      for (int p = f.Up[k]; p < f.Up[k + 1]; ++p) { plan.Ui.push_back(k0 + f.Ui[p]); plan.Ux.push_back(f.Ux[p]); }
-      plan.Up.push_back((int)plan.Ui.size());
-    }
-  }
-  for (int r = 0; r < n; ++r) plan.row_perm[new_rowpos[r]] = r;
-  for (int t = 0; t < n; ++t) plan.col_perm[t] = a_col[t];
   // scatter maps: every entry of A goes either into a diagonal block column (dense work vector slot)
   // or into the off-diagonal list used by block back-substitution
   plan.acol_ptr.assign(n + 1, 0);
@@ -357,7 +273,7 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
     for (int p = Ap[j]; p < Ap[j + 1]; ++p) {
       const int rp = new_rowpos[Ai[p]];
       if (blk_of_pos[rp] == blk_of_pos[t]) { plan.acol_row.push_back(rp); plan.acol_src.push_back(Aidx[p]); }
-      else { plan.off_row.push_back(rp); plan.off_src.push_back(Aidx[p]); plan.off_val_host.push_back(vals[Aidx[p]]); }
+      else { plan.off_row.push_back(rp); plan.off_src.push_back(Aidx[p]); plan.off_val_host.push_back(vals ? vals[Aidx[p]] : 0.0); }
     }
     plan.acol_ptr[t + 1] = (int)plan.acol_row.size();
     plan.off_ptr[t + 1] = (int)plan.off_row.size();
@@ -539,7 +455,184 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
     fl += plan.Lp[k + 1] - plan.Lp[k];
   }
   plan.refactor_flops = fl;
+}
+
+int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol, LuPlan &plan) {
+  plan = LuPlan();
+  plan.n = n;
+  const int nnz = rowptr[n];
+  plan.nnz_a = nnz;
+  // CSR -> CSC with a back-pointer to the CSR value index
+  std::vector<int> Ap(n + 1, 0), Ai(nnz), Aidx(nnz);
+  for (int k = 0; k < nnz; ++k) ++Ap[colind[k] + 1];
+  for (int j = 0; j < n; ++j) Ap[j + 1] += Ap[j];
+  {
+    std::vector<int> fill(Ap.begin(), Ap.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { const int p = fill[colind[k]]++; Ai[p] = i; Aidx[p] = k; }
+  }
+  // 1. maximum transversal: column matched to each row; Q0[i] = column placed at diagonal position i
+  std::vector<int> col_of_row;
+  const int nmatch = max_transversal(n, Ap, Ai, col_of_row);
+  if (nmatch < n) { plan.structurally_singular = true; return 1; }
+  // permuted pattern C = A * Q0 has c(i, i') = a(i, col_of_row[i']): column i' of C is column col_of_row[i'] of A
+  std::vector<int> Cp(n + 1, 0), Ci;
+  Ci.reserve(nnz);
+  for (int jp = 0; jp < n; ++jp) {
+    const int j = col_of_row[jp];
+    for (int p = Ap[j]; p < Ap[j + 1]; ++p) Ci.push_back(Ai[p]);
+    Cp[jp + 1] = (int)Ci.size();
+  }
+  // 2. strongly connected components of C (symmetric permutation)
+  std::vector<int> sperm, bptr;
+  strong_components(n, Cp, Ci, sperm, bptr);
+  const int nblocks = (int)bptr.size() - 1;
+  // 3. per-block fill-reducing ordering (within-block symmetric permutation)
+  std::vector<int> where(n, -1), blk_of(n, -1);
+  for (int b = 0; b < nblocks; ++b)
+    for (int t = bptr[b]; t < bptr[b + 1]; ++t) blk_of[sperm[t]] = b;
+  std::vector<int> final_order(n);   // position -> index in C numbering
+  {
+    std::vector<int> local(n, -1);
+    for (int b = 0; b < nblocks; ++b) {
+      const int nb = bptr[b + 1] - bptr[b];
+      if (nb <= 2) { for (int t = bptr[b]; t < bptr[b + 1]; ++t) final_order[t] = sperm[t]; continue; }
+      for (int t = 0; t < nb; ++t) local[sperm[bptr[b] + t]] = t;
+      std::vector<std::vector<int>> adj(nb);
+      for (int t = 0; t < nb; ++t) {
+        const int jc = sperm[bptr[b] + t];
+        for (int p = Cp[jc]; p < Cp[jc + 1]; ++p) {
+          const int ic = Ci[p];
+          if (blk_of[ic] != b || ic == jc) continue;
+          adj[t].push_back(local[ic]); adj[local[ic]].push_back(t);
+        }
+      }
+      std::vector<int> ord;
+      min_degree(nb, adj, ord);
+      for (int t = 0; t < nb; ++t) final_order[bptr[b] + t] = sperm[bptr[b] + ord[t]];
+    }
+  }
+  for (int t = 0; t < n; ++t) where[final_order[t]] = t;   // C index -> position
+  // At this point position t holds row final_order[t] (of A) and column col_of_row[final_order[t]].
+  std::vector<int> rowpos(n), colpos(n);
+  for (int t = 0; t < n; ++t) { rowpos[final_order[t]] = t; colpos[col_of_row[final_order[t]]] = t; }
+
+  // 4. factor each diagonal block; collect off-diagonal entries
+  plan.block_ptr = bptr;
+  plan.Lp.assign(1, 0); plan.Up.assign(1, 0);
+  plan.row_perm.assign(n, -1);   // position -> row of A   (includes pivoting)
+  plan.col_perm.assign(n, -1);   // position -> column of A
+  std::vector<int> a_row(n), a_col(n);
+  for (int t = 0; t < n; ++t) { a_row[t] = final_order[t]; a_col[t] = col_of_row[final_order[t]]; }
+  std::vector<int> pre_rowpos(rowpos);    // pre-pivot row positions
+  std::vector<int> new_rowpos(n, -1);     // row of A -> final position
+  plan.singular = false;
+  for (int b = 0; b < nblocks; ++b) {
+    const int k0 = bptr[b], nb = bptr[b + 1] - bptr[b];
+    std::vector<std::vector<std::pair<int, double>>> cols(nb);
+    for (int t = 0; t < nb; ++t) {
+      const int j = a_col[k0 + t];
+      for (int p = Ap[j]; p < Ap[j + 1]; ++p) {
+        const int rp = pre_rowpos[Ai[p]];
+        if (rp >= k0 && rp < k0 + nb) cols[t].push_back(std::make_pair(rp - k0, vals[Aidx[p]]));
+      }
+    }
+    BlockLU f;
+    factor_block(nb, cols, pivot_tol, f);
+    if (f.singular) plan.singular = true;
+    for (int r = 0; r < nb; ++r) new_rowpos[a_row[k0 + r]] = k0 + f.pinv[r];
+    for (int k = 0; k < nb; ++k) {
+      for (int p = f.Lp[k]; p < f.Lp[k + 1]; ++p) { plan.Li.push_back(k0 + f.Li[p]); plan.Lx.push_back(f.Lx[p]); }
+      plan.Lp.push_back((int)plan.Li.size());
+      for (int p = f.Up[k]; p < f.Up[k + 1]; ++p) { plan.Ui.push_back(k0 + f.Ui[p]); plan.Ux.push_back(f.Ux[p]); }
+      plan.Up.push_back((int)plan.Ui.size());
+    }
+  }
+  for (int r = 0; r < n; ++r) plan.row_perm[new_rowpos[r]] = r;
+  for (int t = 0; t < n; ++t) plan.col_perm[t] = a_col[t];
+  finish_plan(plan, Ap, Ai, Aidx, vals, new_rowpos);
   return plan.singular ? 2 : 0;
+}
+
+// ---- import of an external factorization's symbolic result -------------------------------------------------
+// What a KLU-enabled build hands over after klu_analyze + klu_factor (klu_extract: P, Q, R = block boundaries,
+// patterns of L and U), so that the GPU refactor / solve run on KLU's own ordering and pivot sequence instead
+// of this file's restatement of it.  Conventions (the adaptor converts): position t of the permuted matrix
+// holds row row_perm[t] and column col_perm[t] of A; the permuted matrix is upper block triangular with
+// diagonal blocks [block_ptr[b], block_ptr[b+1]); L and U are CSC over positions with row indices as global
+// positions inside the column's block.  Tolerated on input: an explicit unit diagonal in L (dropped), U rows
+// in any order with the pivot anywhere in the column (sorted, pivot moved last).  No row scaling (KLU scale = 0).
+// Returns 0 ok, 3 malformed input (message in *why).
+int import_factorization(int n, const int *rowptr, const int *colind, const int *row_perm, const int *col_perm,
+                         int nblocks, const int *block_ptr, const int *Lp, const int *Li, const int *Up, const int *Ui,
+                         LuPlan &plan, const char **why) {
+  static const char *msg = "";
+  *why = msg;
+  plan = LuPlan();
+  plan.n = n;
+  const int nnz = rowptr[n];
+  plan.nnz_a = nnz;
+  if (nblocks < 1 || block_ptr[0] != 0 || block_ptr[nblocks] != n) { *why = "block_ptr must run from 0 to n"; return 3; }
+  std::vector<int> new_rowpos(n, -1), colpos(n, -1);
+  for (int t = 0; t < n; ++t) {
+    if (row_perm[t] < 0 || row_perm[t] >= n || col_perm[t] < 0 || col_perm[t] >= n) { *why = "permutation entry out of range"; return 3; }
+    if (new_rowpos[row_perm[t]] != -1 || colpos[col_perm[t]] != -1) { *why = "row_perm / col_perm is not a permutation"; return 3; }
+    new_rowpos[row_perm[t]] = t; colpos[col_perm[t]] = t;
+  }
+  plan.block_ptr.assign(block_ptr, block_ptr + nblocks + 1);
+  plan.row_perm.assign(row_perm, row_perm + n);
+  plan.col_perm.assign(col_perm, col_perm + n);
+  std::vector<int> blk_of_pos(n);
+  for (int b = 0; b < nblocks; ++b) {
+    if (block_ptr[b + 1] <= block_ptr[b]) { *why = "empty or decreasing block"; return 3; }
+    for (int t = block_ptr[b]; t < block_ptr[b + 1]; ++t) blk_of_pos[t] = b;
+  }
+  plan.Lp.assign(1, 0); plan.Up.assign(1, 0);
+  for (int k = 0; k < n; ++k) {
+    const int b = blk_of_pos[k], k0 = block_ptr[b], k1 = block_ptr[b + 1];
+    std::vector<int> lr, ur;
+    for (int q = Lp[k]; q < Lp[k + 1]; ++q) {
+      const int r = Li[q];
+      if (r == k) continue;                                   // explicit unit diagonal
+      if (r < k || r >= k1) { *why = "L entry outside the strictly lower part of its block"; return 3; }
+      lr.push_back(r);
+    }
+    bool diag = false;
+    for (int q = Up[k]; q < Up[k + 1]; ++q) {
+      const int r = Ui[q];
+      if (r == k) { diag = true; continue; }
+      if (r > k || r < k0) { *why = "U entry outside the upper part of its block"; return 3; }
+      ur.push_back(r);
+    }
+    if (!diag) { *why = "U column without its pivot"; return 3; }
+    std::sort(lr.begin(), lr.end()); std::sort(ur.begin(), ur.end());
+    plan.Li.insert(plan.Li.end(), lr.begin(), lr.end()); plan.Lp.push_back((int)plan.Li.size());
+    plan.Ui.insert(plan.Ui.end(), ur.begin(), ur.end()); plan.Ui.push_back(k); plan.Up.push_back((int)plan.Ui.size());
+  }
+  plan.Lx.assign(plan.Li.size(), 0.0); plan.Ux.assign(plan.Ui.size(), 0.0);
+  // CSC of A with CSR value indices
+  std::vector<int> Ap(n + 1, 0), Ai(nnz), Aidx(nnz);
+  for (int k = 0; k < nnz; ++k) ++Ap[colind[k] + 1];
+  for (int j = 0; j < n; ++j) Ap[j + 1] += Ap[j];
+  {
+    std::vector<int> fill(Ap.begin(), Ap.end() - 1);
+    for (int i = 0; i < n; ++i)
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { const int q = fill[colind[k]]++; Ai[q] = i; Aidx[q] = k; }
+  }
+  // every entry of A must fall on the factor pattern of its block or above the block diagonal
+  for (int t = 0; t < n; ++t) {
+    const int j = plan.col_perm[t], b = blk_of_pos[t];
+    for (int q = Ap[j]; q < Ap[j + 1]; ++q) {
+      const int rp = new_rowpos[Ai[q]];
+      if (blk_of_pos[rp] > b) { *why = "the permuted matrix is not upper block triangular"; return 3; }
+      if (blk_of_pos[rp] != b || rp == t) continue;
+      const std::vector<int> &ix = rp < t ? plan.Ui : plan.Li;
+      const int lo = rp < t ? plan.Up[t] : plan.Lp[t], hi = rp < t ? plan.Up[t + 1] - 1 : plan.Lp[t + 1];
+      if (!std::binary_search(ix.begin() + lo, ix.begin() + hi, rp)) { *why = "an entry of A is missing from the L / U pattern"; return 3; }
+    }
+  }
+  finish_plan(plan, Ap, Ai, Aidx, nullptr, new_rowpos);
+  return 0;
 }
 
 // CPU reference of the refactor + solve on a fixed plan (used by the first solve and by tests of the
