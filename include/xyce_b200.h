@@ -146,10 +146,13 @@ int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals);
  * them after SymbolicFactorization / NumericFactorization, N_LAS_AmesosSolver.C:335, :363) -- so that the GPU
  * refactorization and solves run on KLU's own ordering and pivot sequence.  Position t of the permuted matrix holds
  * row row_perm[t] and column col_perm[t] of A; diagonal blocks [block_ptr[b], block_ptr[b+1]); L, U in CSC over
- * positions (an explicit unit diagonal in L and any pivot position inside a U column are accepted).  No row scaling
- * (KLU scale = 0).  Follow with xgpu_lu_refactor (numeric values) and xgpu_lu_solve.  3 = malformed input. */
+ * positions (an explicit unit diagonal in L and any pivot position inside a U column are accepted).  row_scale
+ * (NULL = none): the external solver factored diag(1 / row_scale) P A Q, factors by pivot position (klu_extract's Rs,
+ * KLU scale = 1 or 2); the refactorization then divides A's values entry by entry, xgpu_lu_solve divides the
+ * right-hand side.  Follow with xgpu_lu_refactor (numeric values) and xgpu_lu_solve.  3 = malformed input. */
 int xgpu_lu_import(xgpu_ctx *ctx, const int32_t *row_perm, const int32_t *col_perm, int n_blocks,
-                   const int32_t *block_ptr, const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui);
+                   const int32_t *block_ptr, const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui,
+                   const double *row_scale);
 /* The current plan in the same conventions (klu_extract analogue): sizes4 = {n, n_blocks, nnz(L), nnz(U)};
  * any output pointer may be NULL; Lx / Ux = values of the latest factorization on the device. */
 int xgpu_lu_export_sizes(const xgpu_ctx *ctx, int32_t *sizes4);

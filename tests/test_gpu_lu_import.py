@@ -88,6 +88,29 @@ def test_export_import_round_trip_is_bitwise(n_rings, stages, couple):
     e1.close(); e2.close()
 
 
+@pytest.mark.parametrize("n_rings,stages", [(4, 101), (12, 101)])
+def test_imported_plan_with_row_scaling(n_rings, stages):
+    """the external solver factored the row-scaled matrix diag(1 / Rs) A (KLU's default scale = 2: Rs = max |a_ij| of
+    the row): the GPU refactorization of the UNSCALED values on that plan reproduces its factor, solves agree"""
+    A0 = sp.csr_matrix(coupled(ring_array_matrix(n_rings, stages, seed=7))); A0.sort_indices()
+    rng = np.random.default_rng(9)
+    A0.data = A0.data * np.repeat(10.0 ** rng.uniform(-3, 3, A0.shape[0]), np.diff(A0.indptr))      # badly scaled rows
+    Rs = np.asarray(abs(A0).max(axis=1).todense()).ravel()
+    As = sp.diags(1.0 / Rs) @ A0
+    lu, plan = _superlu_plan(sp.csr_matrix(As))
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(A0.indptr, A0.indices)
+    eng.lu_import(row_scale=Rs[plan["row_perm"]], **plan)
+    b = rng.normal(size=A0.shape[0])
+    x = _gpu_solve(eng, A0, b)
+    assert np.max(np.abs(As @ x - b / Rs)) / np.max(np.abs(b / Rs)) < 1e-10
+    assert np.max(np.abs(x - lu.solve(b / Rs))) / np.max(np.abs(x)) < 1e-9
+    ex = eng.lu_export()
+    Ug = sp.csc_matrix((ex["Ux"], ex["Ui"], ex["Up"]), shape=A0.shape)
+    assert abs(Ug - sp.csc_matrix(lu.U)).max() <= 1e-10 * abs(lu.U).max()
+    eng.close()
+
+
 def test_malformed_plans_are_rejected():
     A0 = sp.csr_matrix(coupled(ring_array_matrix(2, 11, seed=3))); A0.sort_indices()
     _, plan = _superlu_plan(A0)

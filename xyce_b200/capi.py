@@ -261,11 +261,12 @@ class Engine:
             self._chk(rc)
         return rc
 
-    def lu_import(self, row_perm, col_perm, block_ptr, Lp, Li, Up, Ui):
+    def lu_import(self, row_perm, col_perm, block_ptr, Lp, Li, Up, Ui, row_scale=None):
         """plan from an external factorization (xgpu_lu_import); raises on malformed input"""
         a = [_i32(v) for v in (row_perm, col_perm, block_ptr, Lp, Li, Up, Ui)]
+        rs = _f64(row_scale) if row_scale is not None else None
         self._chk(self.lib.xgpu_lu_import(self.h, _ip(a[0]), _ip(a[1]), len(a[2]) - 1, _ip(a[2]), _ip(a[3]), _ip(a[4]),
-                                          _ip(a[5]), _ip(a[6])))
+                                          _ip(a[5]), _ip(a[6]), _dp(rs) if rs is not None else None))
 
     def lu_export(self):
         sz = np.zeros(4, dtype=np.int32)

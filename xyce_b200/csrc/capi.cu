@@ -715,13 +715,13 @@ int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
 }
 
 int xgpu_lu_import(xgpu_ctx *ctx, const int32_t *row_perm, const int32_t *col_perm, int nblocks, const int32_t *block_ptr,
-                   const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui) {
+                   const int32_t *Lp, const int32_t *Li, const int32_t *Up, const int32_t *Ui, const double *row_scale) {
   if (!ctx || !row_perm || !col_perm || !block_ptr || !Lp || !Li || !Up || !Ui) return 100;
   if (ctx->rowptr.empty()) return fail(ctx, 112, "no CSR pattern");
   XG_CUDA(cudaSetDevice(ctx->device));
   const char *why = "";
   const int rc = xb::lu::import_factorization(ctx->n, ctx->rowptr.data(), ctx->colind.data(), row_perm, col_perm, nblocks,
-                                              block_ptr, Lp, Li, Up, Ui, ctx->lu_plan, &why);
+                                              block_ptr, Lp, Li, Up, Ui, row_scale, ctx->lu_plan, &why);
   if (rc) { ctx->lu_ready = false; return fail(ctx, 3, std::string("xgpu_lu_import: ") + why); }
   lu_drop_graphs(ctx);
   XG_CUDA(xb::lu::upload_plan(ctx->lu_plan, ctx->lu_dev));

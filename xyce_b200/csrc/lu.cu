@@ -70,7 +70,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuDev d,
 
 __global__ void __launch_bounds__(256) lu_permute_rhs_kernel(LuDev d, const double *__restrict__ rhs) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < d.n) d.work[t] = rhs[d.row_perm[t]];
+  if (t < d.n) d.work[t] = d.row_scale ? rhs[d.row_perm[t]] / d.row_scale[t] : rhs[d.row_perm[t]];
+}
+// imported plans with row scaling: As = diag(1 / row_scale) A, entry by entry (KLU's SCALE_DIV)
+__global__ void __launch_bounds__(256) lu_scale_values_kernel(LuDev d, const double *__restrict__ A) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < d.nnz_a) d.As[k] = A[k] / d.row_scale[d.nz_rowpos[k]];
 }
 
 // Off-diagonal pull of one level: y[r] -= sum_q A[offr_src[q]] * y[offr_col[q]].  Short rows: one warp per
@@ -375,6 +380,7 @@ void free_plan(LuDev &d) {
   cudaFree(d.pull_tiny_rows); cudaFree(d.work2); cudaFree(d.block_big); cudaFree(d.acol_dst); cudaFree(d.rf_cols); cudaFree(d.Lr_ptr); cudaFree(d.Lr_col);
   cudaFree(d.Lr_src); cudaFree(d.Ur_ptr); cudaFree(d.Ur_col); cudaFree(d.Ur_src); cudaFree(d.fs_short_rows); cudaFree(d.fs_long_rows);
   cudaFree(d.bs_short_rows); cudaFree(d.bs_long_rows);
+  cudaFree(d.row_scale); cudaFree(d.As); cudaFree(d.nz_rowpos);
   d = LuDev();
 }
 
@@ -392,6 +398,12 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
   UP(pull_tiny_rows) UP(block_big) UP(acol_dst) UP(rf_cols) UP(Lr_ptr) UP(Lr_col) UP(Lr_src) UP(Ur_ptr) UP(Ur_col) UP(Ur_src)
   UP(fs_short_rows) UP(fs_long_rows) UP(bs_short_rows) UP(bs_long_rows)
 #undef UP
+  d.nnz_a = p.nnz_a;
+  if (!p.row_scale.empty()) {
+    if ((e = up(&d.row_scale, p.row_scale)) != cudaSuccess) return e;
+    if ((e = up(&d.nz_rowpos, p.nz_rowpos)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&d.As, (size_t)(p.nnz_a > 0 ? p.nnz_a : 1) * sizeof(double))) != cudaSuccess) return e;
+  }
   d.pull_tiny_ptr = p.pull_tiny_ptr; d.staged_bytes = p.staged_bytes;
   d.rf_level_ptr = p.rf_level_ptr; d.rf_dense_ptr = p.rf_dense_ptr; d.rf_dense_cols = p.rf_dense_cols;
   d.fs_short_ptr = p.fs_short_ptr; d.fs_long_ptr = p.fs_long_ptr; d.bs_short_ptr = p.bs_short_ptr; d.bs_long_ptr = p.bs_long_ptr;
@@ -437,9 +449,11 @@ int run_fwd_stages(const LuDev &d, double *vec, int s0, int s1, int col_limit, c
 
 int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
   cudaMemsetAsync(d.status, 0, sizeof(int), s);
+  int extra = 0;
+  if (d.row_scale) { lu_scale_values_kernel<<<(d.nnz_a + 255) / 256, 256, 0, s>>>(d, A); A = d.As; extra = 1; }
   const int ctas = (d.nblocks + kWarpsPerCta - 1) / kWarpsPerCta;
   lu_refactor_kernel<<<ctas, 32 * kWarpsPerCta, 0, s>>>(d, A);
-  int launches = 1;
+  int launches = 1 + extra;
   if (d.staged_bytes > 0) { lu_refactor_staged_kernel<<<ctas, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * d.staged_bytes, s>>>(d, A); ++launches; }
   // large blocks: columns level by level; dense columns of a level after its normal columns
   const int nlev = (int)d.rf_level_ptr.size() - 1;
@@ -460,6 +474,7 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
 }
 
 int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, cudaStream_t s) {
+  if (d.row_scale) A = d.As;      // off-diagonal entries: the scaled copy made by the last refactorization of these values
   lu_permute_rhs_kernel<<<(d.n + 255) / 256, 256, 0, s>>>(d, rhs);
   int launches = 1;
   for (int l = 0; l < d.nlevels; ++l) {

@@ -38,6 +38,10 @@ struct LuPlan {
   std::vector<int> pull_chunk_ptr, pull_chunk_row_slot, pull_chunk_begin;   // per level: chunks of the long rows
   std::vector<int> pull_long_chunk_ptr;                  // per long row slot: its chunk range
   double refactor_flops = 0.0;
+  // optional row scaling of an imported factorization (KLU scale > 0): the factored matrix is diag(1 / row_scale) P A Q,
+  // row_scale by pivot position; nz_rowpos[k] = pivot position of the row of A's k-th CSR entry.  Empty = none.
+  std::vector<double> row_scale;
+  std::vector<int> nz_rowpos;
 
   // ---- large diagonal blocks (more than kBigBlock rows): column-level / row-level schedules ----
   // A single warp per block (the small-block kernels) would walk such a block column by column; instead
@@ -71,7 +75,7 @@ void solve_host(const LuPlan &plan, const double *b, double *x);
 // numeric values come from the first refactorization on the GPU.  0 ok, 3 malformed input.
 int import_factorization(int n, const int *rowptr, const int *colind, const int *row_perm, const int *col_perm,
                          int nblocks, const int *block_ptr, const int *Lp, const int *Li, const int *Up, const int *Ui,
-                         LuPlan &plan, const char **why);
+                         const double *row_scale, LuPlan &plan, const char **why);
 
 // Device-resident copy of a plan plus work space; created by upload_plan, used by the kernels.
 struct LuDev {
@@ -91,6 +95,8 @@ struct LuDev {
   double *work = nullptr;         // [n] dense column / solution work vector
   double *work2 = nullptr;        // [n] dense-column work vector of the large-block refactor
   int *status = nullptr;          // device flag: != 0 when a zero or non-finite pivot was met
+  double *row_scale = nullptr, *As = nullptr;   // row scaling (imported plans): factors by position, scaled copy of A's values
+  int *nz_rowpos = nullptr; int nnz_a = 0;
   // large blocks (see LuPlan)
   int *block_big = nullptr, *acol_dst = nullptr, *rf_cols = nullptr;
   int *Lr_ptr = nullptr, *Lr_col = nullptr, *Lr_src = nullptr, *Ur_ptr = nullptr, *Ur_col = nullptr, *Ur_src = nullptr;

@@ -561,11 +561,12 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
 // holds row row_perm[t] and column col_perm[t] of A; the permuted matrix is upper block triangular with
 // diagonal blocks [block_ptr[b], block_ptr[b+1]); L and U are CSC over positions with row indices as global
 // positions inside the column's block.  Tolerated on input: an explicit unit diagonal in L (dropped), U rows
-// in any order with the pivot anywhere in the column (sorted, pivot moved last).  No row scaling (KLU scale = 0).
+// in any order with the pivot anywhere in the column (sorted, pivot moved last).  row_scale (by position, may be null):
+// the external solver factored diag(1 / row_scale) P A Q (KLU scale = 1 or 2, klu_extract's Rs).
 // Returns 0 ok, 3 malformed input (message in *why).
 int import_factorization(int n, const int *rowptr, const int *colind, const int *row_perm, const int *col_perm,
                          int nblocks, const int *block_ptr, const int *Lp, const int *Li, const int *Up, const int *Ui,
-                         LuPlan &plan, const char **why) {
+                         const double *row_scale, LuPlan &plan, const char **why) {
   static const char *msg = "";
   *why = msg;
   plan = LuPlan();
@@ -630,6 +631,12 @@ int import_factorization(int n, const int *rowptr, const int *colind, const int 
       const int lo = rp < t ? plan.Up[t] : plan.Lp[t], hi = rp < t ? plan.Up[t + 1] - 1 : plan.Lp[t + 1];
       if (!std::binary_search(ix.begin() + lo, ix.begin() + hi, rp)) { *why = "an entry of A is missing from the L / U pattern"; return 3; }
     }
+  }
+  if (row_scale) {
+    for (int t = 0; t < n; ++t) if (!(row_scale[t] > 0.0)) { *why = "row_scale must be positive"; return 3; }
+    plan.row_scale.assign(row_scale, row_scale + n);
+    plan.nz_rowpos.resize(nnz);
+    for (int i = 0; i < n; ++i) for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) plan.nz_rowpos[k] = new_rowpos[i];
   }
   finish_plan(plan, Ap, Ai, Aidx, nullptr, new_rowpos);
   return 0;
