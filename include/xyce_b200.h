@@ -179,7 +179,8 @@ int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colin
  *   Outputs: accepted time points and probe waveforms, one record {t, h, newton iterations, order, status}
  *   per step attempt, and counters stats16 = {accepted, rejected, newton iterations, Jacobian loads,
  *   residual loads, linear solves, LU analyses, LU refactors, time points, attempts, driver rc,
- *   Newton iterations of the DC operating point, its convergence status}. */
+ *   Newton iterations of the DC operating point, its convergence status, seconds spent in set-up (allocation,
+ *   upload), seconds in the time loop, longest single wait for the per-iteration norm readback}. */
 typedef struct xgpu_tran_params {
   double tstop, tstep, delmax;
   int maxNewtonStep;                 /* 0 = reference default (20) */

@@ -249,7 +249,8 @@ class Engine:
         rc = self.lib.xgpu_tran_run(self.h, C.byref(tp), _dp(x0), len(probes), _ip(probes), max_out, C.byref(n_out),
                                     _dp(times), _dp(wave), max_out, C.byref(n_steps), _dp(steps), _dp(stats))
         keys = ("accepted", "rejected", "newton_iters", "jacobian_loads", "residual_loads", "linear_solves",
-                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc", "dcop_newton_iters", "dcop_status")
+                "lu_analyses", "lu_refactors", "time_points", "attempts", "driver_rc", "dcop_newton_iters", "dcop_status",
+                "setup_s", "run_s", "max_readback_wait_s")
         return dict(rc=rc, t=times[:n_out.value], wave=wave[:n_out.value], steps=steps[:n_steps.value],
                     stats=dict(zip(keys, stats.tolist())),
                     error=self.lib.xgpu_last_error(self.h).decode() if rc else "")

@@ -150,6 +150,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
   for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
+  cudaFree(ctx->tran_pool); cudaFree(ctx->tran_ints); cudaFreeHost(ctx->tran_pinned);
   xb::lu::free_plan(ctx->lu_dev);
   for (XgLinearPart *L : {&ctx->linG, &ctx->linC}) { cudaFree(L->rows); cudaFree(L->ptr); cudaFree(L->col); cudaFree(L->pos); cudaFree(L->val); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -99,6 +99,11 @@ struct xgpu_ctx {
   struct LuGraph { cudaGraphExec_t exec = nullptr; const void *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; int launches = 0; };
   LuGraph g_refactor, g_solve;
   int lu_graphs = 1;          // option "lu_graphs": 0 = plain stream launches
+  // work space of xgpu_tran_run, kept between runs (driver-level allocation and pinned-memory calls cost
+  // milliseconds to tenths of a second each): device pool in doubles, small int arena, pinned readback words
+  double *tran_pool = nullptr; size_t tran_pool_len = 0;
+  int *tran_ints = nullptr; size_t tran_ints_len = 0;
+  double *tran_pinned = nullptr;
 };
 
 int xg_fail(xgpu_ctx *c, int code, const std::string &msg);

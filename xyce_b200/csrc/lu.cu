@@ -22,7 +22,7 @@ constexpr int kSmemRows = 512;     // rows staged in shared memory per warp (4 K
 
 __device__ __forceinline__ bool bad_pivot(double p) { return p == 0.0 || !(fabs(p) <= 1.7976931348623157e308); }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuDev d, const double *__restrict__ A) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d, const double *__restrict__ A) {
   __shared__ double sx[kWarpsPerCta][kSmemRows];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerCta + warp;
@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuDev d,
   }
 }
 
-__global__ void __launch_bounds__(256) lu_permute_rhs_kernel(LuDev d, const double *__restrict__ rhs) {
+__global__ void __launch_bounds__(256) lu_permute_rhs_kernel(LuView d, const double *__restrict__ rhs) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < d.n) d.work[t] = d.row_scale ? rhs[d.row_perm[t]] / d.row_scale[t] : rhs[d.row_perm[t]];
 }
 // imported plans with row scaling: As = diag(1 / row_scale) A, entry by entry (KLU's SCALE_DIV)
-__global__ void __launch_bounds__(256) lu_scale_values_kernel(LuDev d, const double *__restrict__ A) {
+__global__ void __launch_bounds__(256) lu_scale_values_kernel(LuView d, const double *__restrict__ A) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < d.nnz_a) d.As[k] = A[k] / d.row_scale[d.nz_rowpos[k]];
 }
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) lu_scale_values_kernel(LuDev d, const dou
 // row (lane-strided partial sums, shuffle tree).  Long rows (supply rails with ~1e6 entries): one block per
 // 4096-entry chunk with a fixed-shape tree, then one block per row over the chunk partials.  Fixed shapes
 // and orders, no atomics.
-__global__ void __launch_bounds__(256) lu_pull_short_kernel(LuDev d, const double *__restrict__ A, int first, int count) {
+__global__ void __launch_bounds__(256) lu_pull_short_kernel(LuView d, const double *__restrict__ A, int first, int count) {
   const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= count) return;
   const int r = d.pull_short_rows[first + w];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) lu_pull_short_kernel(LuDev d, const doubl
 }
 
 // rows with a handful of off-diagonal entries (every ring node couples to the supply column only): one thread per row
-__global__ void __launch_bounds__(256) lu_pull_tiny_kernel(LuDev d, const double *__restrict__ A, int first, int count) {
+__global__ void __launch_bounds__(256) lu_pull_tiny_kernel(LuView d, const double *__restrict__ A, int first, int count) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= count) return;
   const int r = d.pull_tiny_rows[first + t];
@@ -113,7 +113,7 @@ __device__ __forceinline__ double block_tree_sum(double v, double *sh) {
   return sh[0];
 }
 
-__global__ void __launch_bounds__(256) lu_pull_chunk_kernel(LuDev d, const double *__restrict__ A, int first_chunk) {
+__global__ void __launch_bounds__(256) lu_pull_chunk_kernel(LuView d, const double *__restrict__ A, int first_chunk) {
   __shared__ double sh[256];
   const int c = first_chunk + blockIdx.x;
   const int r = d.pull_long_rows[d.pull_chunk_row_slot[c]];
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) lu_pull_chunk_kernel(LuDev d, const doubl
   if (threadIdx.x == 0) d.pull_partials[c] = t;
 }
 
-__global__ void __launch_bounds__(256) lu_pull_finish_kernel(LuDev d, int first_slot) {
+__global__ void __launch_bounds__(256) lu_pull_finish_kernel(LuView d, int first_slot) {
   __shared__ double sh[256];
   const int slot = first_slot + blockIdx.x;
   const int r = d.pull_long_rows[slot];
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) lu_pull_finish_kernel(LuDev d, int first_
 
 // One level of the block back-substitution: every block of the level pulls the contributions of the
 // already-solved later blocks into its right-hand side, then does L and U solves inside the block.
-__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev d, const double *__restrict__ A,
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuView d, const double *__restrict__ A,
                                                                           int first, int count,
                                                                           double *__restrict__ xout) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuDev
 // Slice layout: double x[nb], Lx[nl], Ux[nu]; int Lp[nb+1], Up[nb+1], Li[nl], Ui[nu]  (indices local to the block).
 // ---------------------------------------------------------------------------------------------
 struct StagedView { double *x, *Lx, *Ux; int *Lp, *Up, *Li, *Ui; int nb, nl, nu, k0, l0, u0; };
-__device__ __forceinline__ StagedView staged_load(const LuDev &d, int b, unsigned char *slice, int lane, bool values) {
+__device__ __forceinline__ StagedView staged_load(const LuView &d, int b, unsigned char *slice, int lane, bool values) {
   StagedView v;
   v.k0 = d.block_ptr[b]; v.nb = d.block_ptr[b + 1] - v.k0;
   v.l0 = d.Lp[v.k0]; v.nl = d.Lp[v.k0 + v.nb] - v.l0;
@@ -184,7 +184,7 @@ __device__ __forceinline__ StagedView staged_load(const LuDev &d, int b, unsigne
   return v;
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_staged_kernel(LuDev d, const double *__restrict__ A) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_staged_kernel(LuView d, const double *__restrict__ A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerCta + warp;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_staged_kernel(L
   for (int i = lane; i < v.nu; i += 32) d.Ux[v.u0 + i] = v.Ux[i];
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_staged_kernel(LuDev d, int first, int count, double *__restrict__ xout) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_staged_kernel(LuView d, int first, int count, double *__restrict__ xout) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarpsPerCta + warp;
@@ -262,7 +262,7 @@ __device__ __forceinline__ int lower_bound_dev(const int *a, int lo, int hi, int
   return lo;
 }
 
-__global__ void __launch_bounds__(256) lu_big_cols_kernel(LuDev d, const double *__restrict__ A, int first, int count) {
+__global__ void __launch_bounds__(256) lu_big_cols_kernel(LuView d, const double *__restrict__ A, int first, int count) {
   const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= count) return;
   const int k = d.rf_cols[first + w];
@@ -294,11 +294,11 @@ __global__ void __launch_bounds__(256) lu_big_cols_kernel(LuDev d, const double 
 }
 
 // Dense columns (supply rails): x = L^-1 A(:,k) over the whole block by the forward row stages, then gathered.
-__global__ void __launch_bounds__(256) lu_dense_scatter_kernel(LuDev d, const double *__restrict__ A, int k) {
+__global__ void __launch_bounds__(256) lu_dense_scatter_kernel(LuView d, const double *__restrict__ A, int k) {
   const int q = d.acol_ptr[k] + blockIdx.x * 256 + threadIdx.x;
   if (q < d.acol_ptr[k + 1]) d.work2[d.acol_row[q]] = A[d.acol_src[q]];
 }
-__global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuDev d, int k) {
+__global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuView d, int k) {
   const int ub = d.Up[k], ue = d.Up[k + 1] - 1, lb = d.Lp[k], le = d.Lp[k + 1];
   const double pivot = d.work2[k];
   const int t = blockIdx.x * 256 + threadIdx.x;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuDev d, int k) {
 // One stage of a row-form triangular sweep: vec[r] -= sum_{col < col_limit} L(r, col) vec[col].
 // WARP: one warp per row (lane-strided partial sums, shuffle tree); otherwise one CTA per row (fixed tree).
 template <bool WARP>
-__global__ void __launch_bounds__(256) lu_fwd_rows_kernel(LuDev d, double *vec, const int *__restrict__ rows, int first, int count,
+__global__ void __launch_bounds__(256) lu_fwd_rows_kernel(LuView d, double *vec, const int *__restrict__ rows, int first, int count,
                                                           int col_limit) {
   __shared__ double sh[256];
   const int lane = threadIdx.x & 31;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) lu_fwd_rows_kernel(LuDev d, double *vec, 
 }
 // backward stage: y[r] = (y[r] - sum U(r, col) y[col]) / U(r, r), solution scattered to the caller's ordering
 template <bool WARP>
-__global__ void __launch_bounds__(256) lu_bwd_rows_kernel(LuDev d, const int *__restrict__ rows, int first, int count,
+__global__ void __launch_bounds__(256) lu_bwd_rows_kernel(LuView d, const int *__restrict__ rows, int first, int count,
                                                           double *__restrict__ xout) {
   __shared__ double sh[256];
   const int lane = threadIdx.x & 31;

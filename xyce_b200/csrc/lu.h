@@ -78,7 +78,9 @@ int import_factorization(int n, const int *rowptr, const int *colind, const int 
                          const double *row_scale, LuPlan &plan, const char **why);
 
 // Device-resident copy of a plan plus work space; created by upload_plan, used by the kernels.
-struct LuDev {
+// LuView is the part the kernels see (plain pointers and sizes: it is the kernel parameter, passed by value);
+// LuDev adds the host-side launch schedule.
+struct LuView {
   int n = 0, nblocks = 0, nlevels = 0, staged_bytes = 0;
   int *row_perm = nullptr, *col_perm = nullptr, *block_ptr = nullptr;
   int *Lp = nullptr, *Li = nullptr, *Up = nullptr, *Ui = nullptr;
@@ -86,11 +88,9 @@ struct LuDev {
   int *acol_ptr = nullptr, *acol_row = nullptr, *acol_src = nullptr;
   int *offr_ptr = nullptr, *offr_col = nullptr, *offr_src = nullptr;
   int *level_blocks = nullptr;
-  std::vector<int> level_ptr;     // host copy: one launch per level
-  int *pull_tiny_rows = nullptr; std::vector<int> pull_tiny_ptr;
+  int *pull_tiny_rows = nullptr;
   int *pull_short_rows = nullptr, *pull_long_rows = nullptr, *pull_chunk_row_slot = nullptr, *pull_chunk_begin = nullptr;
   int *pull_long_chunk_ptr = nullptr;
-  std::vector<int> pull_short_ptr, pull_long_ptr, pull_chunk_ptr;   // host copies
   double *pull_partials = nullptr;
   double *work = nullptr;         // [n] dense column / solution work vector
   double *work2 = nullptr;        // [n] dense-column work vector of the large-block refactor
@@ -101,6 +101,11 @@ struct LuDev {
   int *block_big = nullptr, *acol_dst = nullptr, *rf_cols = nullptr;
   int *Lr_ptr = nullptr, *Lr_col = nullptr, *Lr_src = nullptr, *Ur_ptr = nullptr, *Ur_col = nullptr, *Ur_src = nullptr;
   int *fs_short_rows = nullptr, *fs_long_rows = nullptr, *bs_short_rows = nullptr, *bs_long_rows = nullptr;
+};
+struct LuDev : LuView {
+  std::vector<int> level_ptr;     // host copy: one launch per level
+  std::vector<int> pull_tiny_ptr;
+  std::vector<int> pull_short_ptr, pull_long_ptr, pull_chunk_ptr;   // host copies
   std::vector<int> rf_level_ptr, rf_dense_ptr, rf_dense_cols, fs_short_ptr, fs_long_ptr, bs_short_ptr, bs_long_ptr;
   std::vector<int> big_blocks, big_fs_begin, big_fs_end, big_bs_begin, big_bs_end, block_ptr_h, block_level_of_big;
   std::vector<int> dense_col_block;   // block id of every dense column (parallel to rf_dense_cols)

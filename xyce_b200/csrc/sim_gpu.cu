@@ -2,6 +2,7 @@
 // linear-device replay (FilteredMatrix semantics), independent sources, device-resident vectors,
 // norms, the KLU-pattern LU, and the time loop itself.  All vectors stay in HBM for the whole run;
 // per Newton iteration the host receives only a handful of scalars (norms, convergence flag).
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -157,12 +158,15 @@ struct GpuBackend {
     for (auto &g : ctx->sgroups) { if (a.nflag_arrays < 8) { a.flags[a.nflag_arrays] = g.d_orig; a.flag_n[a.nflag_arrays++] = g.n; } else overflow = true; }
     vec::residual_norms(a, scratch, scratch + 4 * 1024, s); ctx->launches += 2;
     cudaMemcpyAsync(h_norms, scratch + 4 * 1024, 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
+    const auto w0 = std::chrono::steady_clock::now();
     cudaStreamSynchronize(s);
+    max_wait_s = std::max(max_wait_s, std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());
     out.rhs_norm2 = std::sqrt(h_norms[0]); out.rhs_norm_inf = h_norms[1]; out.dx_wmax = h_norms[2];
     out.devices_converged = h_norms[3] != 0.0;
     if (overflow) out.devices_converged = all_devices_converged();     // more than 8 device groups: separate pass
   }
   double *h_norms = nullptr;          // pinned
+  double max_wait_s = 0.0;            // longest single wait for the per-iteration readback (diagnostics)
   bool limiter_active() const { return ss.voltageLimiterFlag != 0; }
   void accept_state() {
     cudaMemcpyAsync(sta[1], sta[0], (size_t)ctx->n_state * sizeof(double), cudaMemcpyDeviceToDevice, s);
@@ -237,24 +241,40 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   if (!ctx || !tp || !h_x0 || !n_out || !n_steps_out) return 1;
   if (!ctx->finalized) return xg_fail(ctx, 15, "xgpu_finalize has not been called");
   XS_CUDA(cudaSetDevice(ctx->device));
+  const auto t_begin = std::chrono::steady_clock::now();
   GpuBackend B;
   B.ctx = ctx; B.s = ctx->stream; B.n_ = ctx->n;
   B.lu_analyzed = ctx->lu_ready;      // a plan from an earlier run is reused (refactor; re-analysed on a bad pivot)
   const size_t n = (size_t)ctx->n;
   B.v.assign(sim::kNumVec, nullptr);
-  double *pool = nullptr;
-  XS_CUDA(cudaMalloc((void **)&pool, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 8192) * sizeof(double)));
-  XS_CUDA(cudaMemsetAsync(pool, 0, (sim::kNumVec * n + 3 * (size_t)ctx->nnz + 8192) * sizeof(double), ctx->stream));
+  // one device pool (vectors, matrices, reduction scratch, source values, probe outputs) and one int arena
+  // (source rows, probe indices), both kept in the context between runs
+  std::vector<int> srows; for (auto &q : ctx->sources) srows.push_back(q.row);
+  const size_t need_d = sim::kNumVec * n + 3 * (size_t)ctx->nnz + 8192 + srows.size() + 1 + (size_t)n_probes + 1;
+  const size_t need_i = srows.size() + (size_t)n_probes + 2;
+  if (ctx->tran_pool_len < need_d) {
+    cudaFree(ctx->tran_pool); ctx->tran_pool = nullptr; ctx->tran_pool_len = 0;
+    XS_CUDA(cudaMalloc((void **)&ctx->tran_pool, need_d * sizeof(double)));
+    ctx->tran_pool_len = need_d;
+  }
+  if (ctx->tran_ints_len < need_i) {
+    cudaFree(ctx->tran_ints); ctx->tran_ints = nullptr; ctx->tran_ints_len = 0;
+    XS_CUDA(cudaMalloc((void **)&ctx->tran_ints, need_i * sizeof(int)));
+    ctx->tran_ints_len = need_i;
+  }
+  if (!ctx->tran_pinned) XS_CUDA(cudaMallocHost((void **)&ctx->tran_pinned, 8 * sizeof(double)));
+  double *pool = ctx->tran_pool;
+  XS_CUDA(cudaMemsetAsync(pool, 0, need_d * sizeof(double), ctx->stream));
   for (int i = 0; i < sim::kNumVec; ++i) B.v[i] = pool + i * n;
   B.dFdx = pool + sim::kNumVec * n; B.dQdx = B.dFdx + ctx->nnz; B.J = B.dQdx + ctx->nnz; B.scratch = B.J + ctx->nnz;
   B.sto[0] = ctx->buf[7]; B.sto[1] = ctx->buf[8]; B.sta[0] = ctx->buf[9]; B.sta[1] = ctx->buf[10];
-  std::vector<int> srows; for (auto &q : ctx->sources) srows.push_back(q.row);
-  XS_CUDA(up(&B.d_src_rows, srows));
-  XS_CUDA(cudaMalloc((void **)&B.d_src_vals, (srows.size() + 1) * sizeof(double)));
+  B.d_src_vals = B.scratch + 8192; B.d_probe_out = B.d_src_vals + srows.size() + 1;
+  B.d_src_rows = ctx->tran_ints; B.d_probe = ctx->tran_ints + srows.size() + 1;
+  if (!srows.empty()) XS_CUDA(cudaMemcpyAsync(B.d_src_rows, srows.data(), srows.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   B.probes.assign(probes, probes + n_probes);
-  XS_CUDA(up(&B.d_probe, B.probes));
-  XS_CUDA(cudaMalloc((void **)&B.d_probe_out, (n_probes + 1) * sizeof(double)));
-  XS_CUDA(cudaMallocHost((void **)&B.h_norms, 8 * sizeof(double)));
+  if (n_probes > 0) XS_CUDA(cudaMemcpyAsync(B.d_probe, B.probes.data(), (size_t)n_probes * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  XS_CUDA(cudaStreamSynchronize(ctx->stream));      // srows is a local
+  B.h_norms = ctx->tran_pinned;
   std::memset(&B.ss, 0, sizeof(B.ss));
   B.ss.voltageLimiterFlag = 1; B.ss.gmin = 1e-12; B.ss.gainScale = 1.0; B.ss.nltermScale = 1.0;
   B.ss.vgstConst = 4.5; B.ss.vdsScaleMin = 0.3; B.ss.sizeScale = 1.0; B.ss.transientFlag = 1;
@@ -276,8 +296,11 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   if (tp->method == 8) P.method = 8;
   P.dcop = tp->dcop ? 1 : 0;
   sim::TransientDriver<GpuBackend> drv(B, P);
+  XS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const auto t_setup = std::chrono::steady_clock::now();
   const int rc = drv.run();
   XS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const auto t_run = std::chrono::steady_clock::now();
   XS_CUDA(cudaGetLastError());
 
   const int nt = (int)B.times.size();
@@ -298,11 +321,11 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
     const sim::TranStats &t = drv.stats;
     const double st[16] = {(double)t.accepted, (double)t.rejected, (double)t.newton_total, (double)t.jacobian_loads,
                            (double)t.residual_loads, (double)t.linear_solves, (double)B.lu_analyses, (double)B.lu_refactors,
-                           (double)nt, (double)nsr, (double)rc, (double)t.dcop_newton, (double)t.dcop_status, 0, 0, 0};
+                           (double)nt, (double)nsr, (double)rc, (double)t.dcop_newton, (double)t.dcop_status,
+                           std::chrono::duration<double>(t_setup - t_begin).count(), std::chrono::duration<double>(t_run - t_setup).count(),
+                           B.max_wait_s};
     std::memcpy(stats16, st, sizeof(st));
   }
-  cudaFreeHost(B.h_norms);
-  cudaFree(pool); cudaFree(B.d_src_rows); cudaFree(B.d_src_vals); cudaFree(B.d_probe); cudaFree(B.d_probe_out);
   if (rc != 0) return xg_fail(ctx, 200 + rc, rc == 2 ? "transient: time step too small / too many failures"
                                              : (rc == 4 ? "transient: the DC operating point did not converge" : "transient: step limit reached"));
   return 0;
