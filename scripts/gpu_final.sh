@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_g.json 2> gpurun_out/bench_ref_g.err; tail -c 700 gpurun_out/bench_ref_g.json; echo
-python bench.py > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err; tail -c 300 gpurun_out/bench_g.json; echo; grep -c . gpurun_out/bench_g.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 24 --csv --log-file gpurun_out/launches_v5.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-tran > gpurun_out/b_ncu_v5.log 2>&1
-grep -v "^==" gpurun_out/launches_v5.csv | awk -F'","' '{print $5, $NF}' | cut -c1-60,100-140 | tail -8
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v Netlist | tail -2
+(timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | grep -v Netlist | tail -3) 2>&1 | tee gpurun_out/pytest_gpu.log
+timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python scripts/sanitize_asm_tran.py 2>&1 | grep -v Netlist | tail -2
+python scripts/tran_bench.py 2>&1 | grep -v Netlist | cut -c1-260
+python bench.py > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_g.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['tran_c3']['ms_per_newton_iter'], d['tran_c3']['wall_s_all_runs'], d['clocks'])"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-tran 2>/dev/null | head -c 300
