@@ -96,6 +96,15 @@ int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n_inst, const double *rec
  * N_DEV_MOSFET_B4.C:6524-6846, and Indexor::matrixGlobalToLocal, N_TOP_Indexor.C:149-214). */
 int xgpu_finalize(xgpu_ctx *ctx);
 
+/* Lead currents (Instance::loadLeadCurrent, set by .PRINT I(M1) / P(M1): Master::loadDAEVectors
+ * N_DEV_MOSFET_B4.C:10933-10987; registerBranchDataLIDs :6482-6500).  branch_lid0[i] = li_branch_dev_id of instance i
+ * (id, ig, is, ib are consecutive LIDs of the lead-current vectors; -1 = instance without lead currents).
+ * xgpu_b4_lead_load, called after xgpu_update_state, ASSIGNS leadF, leadQ and junctionV at those LIDs (device
+ * vectors of the DataStore: nextLeadCurrFCompRawPtr, nextLeadCurrQCompRawPtr, nextJunctionVCompRawPtr).
+ * 4-terminal (default-topology) groups only; error 20 for groups with internal nodes. */
+int xgpu_b4_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0);
+int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV);
+
 /* Carried per-instance limiter threshold (Instance::von); instance order = insertion order. */
 int xgpu_b4_von_set(xgpu_ctx *ctx, int group, const double *von);
 int xgpu_b4_von_get(xgpu_ctx *ctx, int group, double *von);

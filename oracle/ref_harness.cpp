@@ -157,6 +157,7 @@ struct InstRec {
   std::vector<int> ext;      // external node ids (-1 = ground)
   std::vector<int> lids;     // ext + int LIDs
   int sta0, sto0;
+  int br0 = -1;              // first branch-data LID (lead currents), -1 when not enabled
 };
 
 struct Ctx {
@@ -190,7 +191,8 @@ struct Ctx {
   }
   bool loadVectorsAll() {
     bool ok = true;
-    for (auto *m : masters) ok = m->loadDAEVectors(sol.data(), f.data(), q.data(), b.data(), 0, 0, 0) && ok;
+    double *lf = leadF.empty() ? 0 : leadF.data(), *lq = leadQ.empty() ? 0 : leadQ.data(), *jv = junctionV.empty() ? 0 : junctionV.data();
+    for (auto *m : masters) ok = m->loadDAEVectors(sol.data(), f.data(), q.data(), b.data(), lf, lq, jv) && ok;
     return ok;
   }
   bool loadMatricesAll() {
@@ -198,7 +200,8 @@ struct Ctx {
     for (auto *m : masters) ok = m->loadDAEMatrices(dFdx, dQdx) && ok;
     return ok;
   }
-  std::vector<double> staDeriv;
+  std::vector<double> staDeriv, leadF, leadQ, junctionV;
+  bool lead = false;         // DeviceInstance::enableLeadCurrentCalc on every instance (what .PRINT I(...) / P(...) triggers)
   std::vector<InstRec> insts;
   int nExt = 0, n = 0, nSta = 0, nSto = 0;
   CsrMatrix dFdx, dQdx;
@@ -307,7 +310,7 @@ int xref_finalize(void *h) {
     M->vals.assign(M->colind.size(), 0.0);
     M->setGround(ground);
   }
-  int sta = 0, sto = 0;
+  int sta = 0, sto = 0, nbr = 0;
   for (auto &r : c->insts) {
     std::vector<int> ext, in;
     const int ne = r.inst->getNumExtVars();
@@ -320,6 +323,13 @@ int xref_finalize(void *h) {
     for (int k = 0; k < r.inst->getNumStoreVars(); ++k) tv.push_back(sto++);
     r.inst->registerStateLIDs(sv);
     r.inst->registerStoreLIDs(tv);
+    if (c->lead) {
+      r.inst->enableLeadCurrentCalc();
+      std::vector<int> bv;
+      r.br0 = nbr;
+      for (int k = 0; k < r.inst->getNumBranchDataVars(); ++k) bv.push_back(nbr++);
+      r.inst->registerBranchDataLIDs(bv);
+    }
     const std::vector<std::vector<int>> &st = r.inst->jacobianStamp();
     std::vector<std::vector<int>> jl(st.size());
     for (size_t i = 0; i < st.size(); ++i) {
@@ -336,6 +346,11 @@ int xref_finalize(void *h) {
     r.inst->registerJacLIDs(jl);
   }
   c->nSta = sta; c->nSto = sto;
+  if (c->lead) {
+    c->leadF.assign(nbr + 1, 0.0); c->leadQ = c->junctionV = c->leadF;
+    c->extData.nextLeadCurrFCompRawPtr = c->leadF.data(); c->extData.nextLeadCurrQCompRawPtr = c->leadQ.data();
+    c->extData.nextJunctionVCompRawPtr = c->junctionV.data();
+  }
   c->f.assign(c->n + 1, 0); c->q = c->b = c->fl = c->ql = c->f;
   c->sol.assign(c->n + 1, 0);
   c->nextSta.assign(sta + 1, 0); c->currSta = c->nextSta; c->staDeriv = c->nextSta;
@@ -549,6 +564,18 @@ int xref_mvs_export(void *h, int idx, double *rec, int *lids7) {
   const int l[7] = {in.li_d, in.li_g, in.li_s, in.li_di, in.li_si, in.li_sf, in.li_BRA_sf_GND};
   for (int i = 0; i < 7; ++i) lids7[i] = (l[i] == g) ? -1 : l[i];
   return k;
+}
+
+// lead currents (loadLeadCurrent): call before xref_finalize; vectors are indexed by branch-data LID
+void xref_enable_lead_currents(void *h) { ((Ctx *)h)->lead = true; }
+int xref_num_branch_data(void *h) { return (int)((Ctx *)h)->leadF.size() - 1; }
+int xref_inst_branch0(void *h, int idx) { return ((Ctx *)h)->insts[idx].br0; }
+void xref_get_lead(void *h, double *leadF, double *leadQ, double *junctionV) {
+  Ctx *c = (Ctx *)h;
+  const size_t n = c->leadF.size() - 1;
+  std::copy(c->leadF.begin(), c->leadF.begin() + n, leadF);
+  std::copy(c->leadQ.begin(), c->leadQ.begin() + n, leadQ);
+  std::copy(c->junctionV.begin(), c->junctionV.begin() + n, junctionV);
 }
 
 int xref_inst_converged(void *h, int idx) { return ((Ctx *)h)->insts[idx].inst->isConverged() ? 1 : 0; }

@@ -86,7 +86,7 @@ class HostMirror:
         return out
 
 
-def isolated_devices(ref_cls, n_pairs, variant="default", seed=0, inst_extra=None, sorted_bins=False):
+def isolated_devices(ref_cls, n_pairs, variant="default", seed=0, inst_extra=None, sorted_bins=False, lead=False):
     """n_pairs nmos + n_pairs pmos, every terminal on its own node (4 nodes per device).  sorted_bins orders
     the instances by (type, L, W) like an adaptor does, so that equal (model, bin) records form long runs."""
     rng = np.random.default_rng(seed)
@@ -103,6 +103,8 @@ def isolated_devices(ref_cls, n_pairs, variant="default", seed=0, inst_extra=Non
         if inst_extra:
             ip.update(inst_extra)
         c.add_instance("M:%d" % i, "nch" if is_n else "pch", [4 * i, 4 * i + 1, 4 * i + 2, 4 * i + 3], ip)
+    if lead:
+        c.enable_lead_currents()
     c.finalize()
     return c
 

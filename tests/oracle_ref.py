@@ -102,6 +102,17 @@ class RefCircuit:
         info = self.inst_info(idx)
         return dict(rec=rec[:k].copy(), flags=flags.value, lids=lids, sto0=info["sto0"], sta0=info["sta0"])
 
+    def enable_lead_currents(self):
+        """DeviceInstance::enableLeadCurrentCalc on every instance (before finalize)"""
+        self.lib.xref_enable_lead_currents(self.h)
+
+    def lead(self):
+        n = self.lib.xref_num_branch_data(self.h)
+        out = [np.zeros(n) for _ in range(3)]
+        self.lib.xref_get_lead(self.h, dptr(out[0]), dptr(out[1]), dptr(out[2]))
+        return dict(leadF=out[0], leadQ=out[1], junctionV=out[2],
+                    branch0=np.array([self.lib.xref_inst_branch0(self.h, i) for i in range(self.n_inst)], dtype=np.int32))
+
     def finalize(self):
         self.n = self.lib.xref_finalize(self.h)
         self.nnz = self.lib.xref_nnz(self.h)

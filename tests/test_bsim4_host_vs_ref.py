@@ -44,3 +44,35 @@ def test_variants_really_change_the_topology():
         sizes[v] = ref.n
     assert sizes["default"] == 8 and sizes["rgate"] > 8 and sizes["rgate3"] > sizes["rgate"]
     assert sizes["rbody"] == 8 + 2 * 3 and sizes["rdsmod"] == 8 + 2 * 2
+
+
+@pytest.mark.parametrize("variant", ["default", "igc", "capmod0", "gidl"])
+def test_lead_currents_of_a_four_terminal_device_are_its_own_row_contributions(host_mirror, variant):
+    """Master::loadDAEVectors' lead-current block (N_DEV_MOSFET_B4.C:10933-10987) for a device without internal nodes:
+    leadF / leadQ of (id, ig, is, ib) equal the instance's F / Q contributions to its drain, gate, source and bulk
+    rows -- the identity xgpu_b4_lead_load relies on -- and junctionV = (Vd - Vs, Vg - Vs, 0, 0)."""
+    ref = isolated_devices(oracle_ref.RefCircuit, 4, variant, seed=21, lead=True)
+    rng = np.random.default_rng(5)
+    flags = dict(transient=1, newtonIter=1)
+    ref.set_flags(**flags)
+    x = rng.uniform(-0.2, 1.2, ref.n)
+    nsto = rng.normal(0, 0.3, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    ref.set_state(next_sto=nsto, curr_sto=nsto); ref.set_von(von)
+    ref.load(x)
+    lead = ref.lead()
+    assert np.all(lead["branch0"] == 4 * np.arange(ref.n_inst))
+    kD, kGE, kS, kB, kDP, kSP, kGP, kGM, kBP, kSB, kDB = range(11)
+    for i in range(ref.n_inst):
+        e = ref.export(i)
+        V = np.array([x[g] if g >= 0 else 0.0 for g in e["lids"]])
+        o = host_mirror.eval(e, flags, V, nsto[e["sto0"]:e["sto0"] + 13], True, von[i])
+        b = lead["branch0"][i]
+        rows = ((kD, kDP), (kGE, kGP, kGM), (kS, kSP), (kB, kBP, kSB, kDB))          # rows that collapse onto d, g, s, b
+        for k, rr in enumerate(rows):
+            for key, vec in (("F", "leadF"), ("Q", "leadQ")):
+                got = sum(o[key][r] for r in rr)
+                want = lead[vec][b + k]
+                assert abs(got - want) <= 1e-12 * max(abs(want), 1e-3 * np.max(np.abs(lead[vec]))), (variant, i, k, key)
+        assert lead["junctionV"][b] == V[kD] - V[kS] and lead["junctionV"][b + 1] == V[kGE] - V[kS]
+        assert lead["junctionV"][b + 2] == 0.0 and lead["junctionV"][b + 3] == 0.0

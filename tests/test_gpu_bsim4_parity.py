@@ -122,6 +122,41 @@ def test_pass_through_limiters():
     run_case("default", FLAG_CASES["tran_iter1"], store_noise=0.0)
 
 
+@pytest.mark.parametrize("variant", ["default", "igc", "capmod1", "gidl"])
+def test_lead_currents(variant):
+    """loadLeadCurrent (.PRINT I(M1)): leadF, leadQ, junctionV at the branch-data LIDs against Master::loadDAEVectors
+    (N_DEV_MOSFET_B4.C:10933-10987) on the reference objects; groups with internal nodes are refused."""
+    import torch
+    ref = isolated_devices(oracle_ref.RefCircuit, 100, variant, seed=4, lead=True)
+    eng, _ = engine_from_ref(ref)
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-0.2, 1.2, ref.n)
+    sto = rng.normal(0.3, 0.3, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    flags = dict(transient=1, newtonIter=1)
+    ref.set_flags(**flags); ref.set_state(curr_sto=sto, next_sto=sto); ref.set_von(von)
+    eng.set_state(0, sto); eng.set_state(1, sto); eng.b4_set_von(0, von)
+    ref.load(x)
+    want = ref.lead()
+    eng.b4_lead_set(0, want["branch0"])
+    eng.load_host(x, solver_state(**flags))
+    nb = len(want["leadF"])
+    out = [torch.full((nb,), 7.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    eng.b4_lead_load(eng.device_buffer(0), *[t.data_ptr() for t in out])
+    eng.sync()
+    for key, t in zip(("leadF", "leadQ", "junctionV"), out):
+        got = t.cpu().numpy()
+        scale = 1e-3 * np.max(np.abs(want[key])) if np.any(want[key]) else 1e-300
+        assert rel_err(got, want[key], scale) < TOL, (variant, key)
+    eng.close()
+    # a group with internal nodes (gate resistance) is refused, not silently wrong
+    ref2 = isolated_devices(oracle_ref.RefCircuit, 2, "rgate3", seed=4, lead=True)
+    eng2, _ = engine_from_ref(ref2)
+    with pytest.raises(RuntimeError, match="4-terminal"):
+        eng2.b4_lead_set(0, ref2.lead()["branch0"])
+    eng2.close()
+
+
 # ---- against the committed golden fixtures (no oracle library needed at run time) ----
 from b4_common import load_golden  # noqa: E402
 

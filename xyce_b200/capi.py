@@ -262,6 +262,13 @@ class Engine:
             self._chk(rc)
         return rc
 
+    def b4_lead_set(self, group, branch_lid0):
+        b = _i32(branch_lid0)
+        self._chk(self.lib.xgpu_b4_lead_set(self.h, int(group), _ip(b)))
+
+    def b4_lead_load(self, d_sol, d_leadF, d_leadQ, d_junctionV):
+        self._chk(self.lib.xgpu_b4_lead_load(self.h, C.c_void_p(d_sol), C.c_void_p(d_leadF), C.c_void_p(d_leadQ), C.c_void_p(d_junctionV)))
+
     def lu_import(self, row_perm, col_perm, block_ptr, Lp, Li, Up, Ui, row_scale=None):
         """plan from an external factorization (xgpu_lu_import); raises on malformed input"""
         a = [_i32(v) for v in (row_perm, col_perm, block_ptr, Lp, Li, Up, Ui)]

@@ -142,7 +142,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto &g : ctx->groups) {
     cudaFree(g.d_inst_d); cudaFree(g.d_von); cudaFree(g.d_topo); cudaFree(g.d_model_idx);
-    cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig);
+    cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); cudaFree(g.d_branch0);
   }
   for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
@@ -473,6 +473,57 @@ int xgpu_finalize(xgpu_ctx *ctx) {
   }
   { const int rc = xg_finalize_linear(ctx); if (rc) return rc; }
   ctx->finalized = true;
+  return 0;
+}
+
+namespace {
+// Lead currents of 4-terminal (default-topology) BSIM4 instances.  With no internal nodes the lead quantities of
+// Master::loadDAEVectors (N_DEV_MOSFET_B4.C:10933-10987) ARE the instance's own F and Q contributions to its
+// drain / gate / source / bulk rows -- leadF[id] = -(ceqjd - ceqbd - ceqdrn + Idtoteq) np is the D' row term (:10691),
+// leadQ[is] = -(Qg + Qb + Qd) np the S' row term (:10893), and so on -- which the evaluation kernel has just
+// written to the contribution planes: this kernel copies them to the branch-data LIDs (assign, not accumulate).
+__global__ void b4_lead_kernel(int n, const double *__restrict__ planeF, const double *__restrict__ planeQ,
+                               const int *__restrict__ lids, const int *__restrict__ branch0,
+                               const double *__restrict__ sol, double *leadF, double *leadQ, double *junctionV) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = branch0[i];
+  if (b < 0) return;
+  // plane rows: 0 drain, 1 gate, 2 source, 3 bulk; branch order: id, ig, is, ib
+  const int row_of[4] = {0, 1, 2, 3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    leadF[b + k] = planeF[(size_t)row_of[k] * n + i];
+    leadQ[b + k] = planeQ[(size_t)row_of[k] * n + i];
+  }
+  const int ld = lids[i], lg = lids[(size_t)n + i], ls = lids[2 * (size_t)n + i];
+  const double vd = ld >= 0 ? sol[ld] : 0.0, vg = lg >= 0 ? sol[lg] : 0.0, vs = ls >= 0 ? sol[ls] : 0.0;
+  junctionV[b + 0] = vd - vs;
+  junctionV[b + 1] = vg - vs;
+  junctionV[b + 2] = 0.0;
+  junctionV[b + 3] = 0.0;
+}
+}  // namespace
+
+int xgpu_b4_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0) {
+  if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !branch_lid0) return 1;
+  XgHostGroup &g = ctx->groups[group];
+  if (g.general) return fail(ctx, 20, "lead currents are implemented for 4-terminal (default-topology) BSIM4 groups only");
+  cudaFree(g.d_branch0); g.d_branch0 = nullptr;
+  XG_CUDA(upload(&g.d_branch0, branch_lid0, (size_t)g.n));
+  return 0;
+}
+
+int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV) {
+  if (!ctx || !d_sol || !d_leadF || !d_leadQ || !d_junctionV) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  for (auto &g : ctx->groups) {
+    if (!g.d_branch0 || g.n == 0) continue;
+    const double *pF = ctx->d_vec_planes + g.dev.vec_base, *pQ = ctx->d_vec_planes + ctx->vec_plane + g.dev.vec_base;
+    b4_lead_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g.n, pF, pQ, g.d_lids, g.d_branch0, d_sol, d_leadF, d_leadQ, d_junctionV);
+    ++ctx->launches;
+  }
+  XG_CUDA(cudaGetLastError());
   return 0;
 }
 
