@@ -168,26 +168,30 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuVie
 // Staged small blocks (block_big == 2): the whole factor of the block -- column pointers, row indices, values
 // and one dense column -- sits in a per-warp slice of shared memory, so the column chain of the left-looking
 // update runs on shared-memory latency instead of a dozen dependent global loads per column.
-// Slice layout: double x[nb], Lx[nl], Ux[nu]; int Lp[nb+1], Up[nb+1], Li[nl], Ui[nu]  (indices local to the block).
+// Slice layout: double x[nb], Lx[nl], Ux[nu]; u16 Lp[nb+1], Up[nb+1], Li[nl], Ui[nu]  (indices local to the block:
+// a staged block has at most 512 rows and its factor fewer than 1536 entries, so 16 bits are enough and more
+// slices fit an SM).  The CTA shape (warps per CTA) is chosen at upload so that the resident warps per SM are
+// maximal for this slice size (staged_warps).
 // ---------------------------------------------------------------------------------------------
-struct StagedView { double *x, *Lx, *Ux; int *Lp, *Up, *Li, *Ui; int nb, nl, nu, k0, l0, u0; };
+typedef unsigned short sidx_t;
+struct StagedView { double *x, *Lx, *Ux; sidx_t *Lp, *Up, *Li, *Ui; int nb, nl, nu, k0, l0, u0; };
 __device__ __forceinline__ StagedView staged_load(const LuView &d, int b, unsigned char *slice, int lane, bool values) {
   StagedView v;
   v.k0 = d.block_ptr[b]; v.nb = d.block_ptr[b + 1] - v.k0;
   v.l0 = d.Lp[v.k0]; v.nl = d.Lp[v.k0 + v.nb] - v.l0;
   v.u0 = d.Up[v.k0]; v.nu = d.Up[v.k0 + v.nb] - v.u0;
   v.x = (double *)slice; v.Lx = v.x + v.nb; v.Ux = v.Lx + v.nl;
-  v.Lp = (int *)(v.Ux + v.nu); v.Up = v.Lp + v.nb + 1; v.Li = v.Up + v.nb + 1; v.Ui = v.Li + v.nl;
-  for (int i = lane; i <= v.nb; i += 32) { v.Lp[i] = d.Lp[v.k0 + i] - v.l0; v.Up[i] = d.Up[v.k0 + i] - v.u0; }
-  for (int i = lane; i < v.nl; i += 32) { v.Li[i] = d.Li[v.l0 + i] - v.k0; if (values) v.Lx[i] = d.Lx[v.l0 + i]; }
-  for (int i = lane; i < v.nu; i += 32) { v.Ui[i] = d.Ui[v.u0 + i] - v.k0; if (values) v.Ux[i] = d.Ux[v.u0 + i]; }
+  v.Lp = (sidx_t *)(v.Ux + v.nu); v.Up = v.Lp + v.nb + 1; v.Li = v.Up + v.nb + 1; v.Ui = v.Li + v.nl;
+  for (int i = lane; i <= v.nb; i += 32) { v.Lp[i] = (sidx_t)(d.Lp[v.k0 + i] - v.l0); v.Up[i] = (sidx_t)(d.Up[v.k0 + i] - v.u0); }
+  for (int i = lane; i < v.nl; i += 32) { v.Li[i] = (sidx_t)(d.Li[v.l0 + i] - v.k0); if (values) v.Lx[i] = d.Lx[v.l0 + i]; }
+  for (int i = lane; i < v.nu; i += 32) { v.Ui[i] = (sidx_t)(d.Ui[v.u0 + i] - v.k0); if (values) v.Ux[i] = d.Ux[v.u0 + i]; }
   return v;
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_staged_kernel(LuView d, const double *__restrict__ A) {
+__global__ void __launch_bounds__(1024) lu_refactor_staged_kernel(LuView d, const double *__restrict__ A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kWarpsPerCta + warp;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= d.nblocks || d.block_big[b] != 2) return;
   StagedView v = staged_load(d, b, smem + (size_t)warp * d.staged_bytes, lane, false);
   for (int i = lane; i < v.nl; i += 32) v.Lx[i] = 0.0;
@@ -227,10 +231,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_staged_kernel(L
   for (int i = lane; i < v.nu; i += 32) d.Ux[v.u0 + i] = v.Ux[i];
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_staged_kernel(LuView d, int first, int count, double *__restrict__ xout) {
+__global__ void __launch_bounds__(1024) lu_solve_staged_kernel(LuView d, int first, int count, double *__restrict__ xout) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kWarpsPerCta + warp;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
   if (idx >= count) return;
   const int b = d.level_blocks[first + idx];
   if (d.block_big[b] != 2) return;
@@ -422,7 +426,18 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
     }
   }
   if (d.staged_bytes > 0) {
-    const int bytes = kWarpsPerCta * d.staged_bytes;      // 4 x 12 KB at most, above the 48 KB default limit
+    // CTA shape: as many resident warps per SM as the shared memory allows (227 KB per SM, 1 KB reserved per CTA,
+    // at most 32 CTAs and 64 warps per SM); fewer, fatter CTAs win when the per-CTA reservation matters
+    int best_w = 1, best_res = 0;
+    for (int w = 1; w <= 32; ++w) {
+      const long long per_cta = (long long)w * d.staged_bytes;
+      if (per_cta > 227 * 1024 - 1024) break;
+      int ctas = (int)((227LL * 1024) / (per_cta + 1024));
+      ctas = std::min(ctas, std::min(32, 64 / w));
+      if (ctas * w > best_res) { best_res = ctas * w; best_w = w; }
+    }
+    d.staged_warps = best_w;
+    const int bytes = d.staged_warps * d.staged_bytes;
     if ((e = cudaFuncSetAttribute(lu_refactor_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lu_solve_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
   }
@@ -454,7 +469,10 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
   const int ctas = (d.nblocks + kWarpsPerCta - 1) / kWarpsPerCta;
   lu_refactor_kernel<<<ctas, 32 * kWarpsPerCta, 0, s>>>(d, A);
   int launches = 1 + extra;
-  if (d.staged_bytes > 0) { lu_refactor_staged_kernel<<<ctas, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * d.staged_bytes, s>>>(d, A); ++launches; }
+  if (d.staged_bytes > 0) {
+    const int w = d.staged_warps;
+    lu_refactor_staged_kernel<<<(d.nblocks + w - 1) / w, 32 * w, (size_t)w * d.staged_bytes, s>>>(d, A); ++launches;
+  }
   // large blocks: columns level by level; dense columns of a level after its normal columns
   const int nlev = (int)d.rf_level_ptr.size() - 1;
   for (int l = 0; l < nlev; ++l) {
@@ -493,7 +511,8 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
     lu_solve_level_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, s>>>(d, A, first, count, x);
     ++launches;
     if (d.staged_bytes > 0) {
-      lu_solve_staged_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, (size_t)kWarpsPerCta * d.staged_bytes, s>>>(d, first, count, x);
+      const int w = d.staged_warps;
+      lu_solve_staged_kernel<<<(count + w - 1) / w, 32 * w, (size_t)w * d.staged_bytes, s>>>(d, first, count, x);
       ++launches;
     }
     for (size_t bi = 0; bi < d.big_blocks.size(); ++bi) {

@@ -81,7 +81,7 @@ int import_factorization(int n, const int *rowptr, const int *colind, const int 
 // LuView is the part the kernels see (plain pointers and sizes: it is the kernel parameter, passed by value);
 // LuDev adds the host-side launch schedule.
 struct LuView {
-  int n = 0, nblocks = 0, nlevels = 0, staged_bytes = 0;
+  int n = 0, nblocks = 0, nlevels = 0, staged_bytes = 0, staged_warps = 4;
   int *row_perm = nullptr, *col_perm = nullptr, *block_ptr = nullptr;
   int *Lp = nullptr, *Li = nullptr, *Up = nullptr, *Ui = nullptr;
   double *Lx = nullptr, *Ux = nullptr;

@@ -362,13 +362,13 @@ static void finish_plan(LuPlan &plan, const std::vector<int> &Ap, const std::vec
       }
     }
     // small blocks whose factor (indices + values + one dense column) fits a per-warp shared-memory slice are
-    // "staged": block_big = 2.  Slice = 2 (nb + 1) + nl + nu ints and nb + nl + nu doubles.
+    // "staged": block_big = 2.  Slice = 2 (nb + 1) + nl + nu 16-bit indices and nb + nl + nu doubles.
     plan.staged_bytes = 0;
     for (int b = 0; b < nblocks; ++b) {
       const int k0 = bptr[b], k1 = bptr[b + 1], nb = k1 - k0;
       if (nb < 2 || plan.block_big[b]) continue;
       const int nl = plan.Lp[k1] - plan.Lp[k0], nu = plan.Up[k1] - plan.Up[k0];
-      const int bytes = 8 * (nb + nl + nu) + 4 * (2 * (nb + 1) + nl + nu + 2);
+      const int bytes = 8 * (nb + nl + nu) + 2 * (2 * (nb + 1) + nl + nu + 4);      // doubles + 16-bit local indices
       if (bytes <= kStagedBytes) { plan.block_big[b] = 2; plan.staged_bytes = std::max(plan.staged_bytes, (bytes + 15) / 16 * 16); }
     }
     for (int b : plan.big_blocks) {
