@@ -149,6 +149,9 @@ template <int NPA, int NPB>
 __global__ void __launch_bounds__(256) assemble_kernel(GatherMapDev ma, PlaneSet pa, GatherMapDev mb, PlaneSet pb,
                                                        int short_a, bool accumulate) {
   __shared__ double sh[(NPA > NPB ? NPA : NPB)][256];
+  // launched with programmatic stream serialization: the grid may start while the evaluation kernel that
+  // produces the planes is still draining; wait here until that kernel has completed and flushed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int b = blockIdx.x;
   if (b < ma.nchunks) { chunk_then_finish<NPA>(ma, pa, b, accumulate, sh); return; }
   b -= ma.nchunks;
@@ -184,12 +187,25 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// 256-thread launch that may overlap the tail of the previous kernel in the stream (programmatic dependent launch);
+// the kernel itself waits for its producer with griddepcontrol.wait before touching memory.
+template <class... KArgs, class... Args>
+void launch_dependent(void (*kernel)(KArgs...), int blocks, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int NP>
 void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
   const int per = 256 * ShortUnroll<NP>::U;
   const int sb = (m.ndst + per - 1) / per;
   GatherMapDev none{};
-  if (m.nchunks + sb > 0) assemble_kernel<NP, 1><<<m.nchunks + sb, 256, 0, stream>>>(m, ps, none, PlaneSet{}, sb, accumulate);
+  if (m.nchunks + sb > 0) launch_dependent(assemble_kernel<NP, 1>, m.nchunks + sb, stream, m, ps, none, PlaneSet{}, sb, accumulate);
 }
 
 }  // namespace
@@ -215,7 +231,7 @@ int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, do
   const int vb = (mv.ndst + pv_ - 1) / pv_, mb = (mm.ndst + pm_ - 1) / pm_;
   const int blocks = mv.nchunks + mm.nchunks + vb + mb;
   if (blocks == 0) return 0;
-  assemble_kernel<4, 2><<<blocks, 256, 0, stream>>>(mv, pv, mm, pm, vb, accumulate);
+  launch_dependent(assemble_kernel<4, 2>, blocks, stream, mv, pv, mm, pm, vb, accumulate);
   return 1;
 }
 

@@ -9,6 +9,7 @@
 // The dense column work vector lives in a per-block slice of a global array; for blocks of at most
 // kSmemRows rows it is staged in shared memory instead.
 // HBM traffic per refactor: 8*nnz(A) read + 12*nnz(L+U) read/write (SURVEY.md 8d unit U3).
+#include "pdl.cuh"
 #include <cuda_runtime.h>
 #include "lu.h"
 
@@ -23,6 +24,7 @@ constexpr int kSmemRows = 512;     // rows staged in shared memory per warp (4 K
 __device__ __forceinline__ bool bad_pivot(double p) { return p == 0.0 || !(fabs(p) <= 1.7976931348623157e308); }
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d, const double *__restrict__ A) {
+  xb::pdl_wait();
   __shared__ double sx[kWarpsPerCta][kSmemRows];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerCta + warp;
@@ -69,11 +71,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d
 }
 
 __global__ void __launch_bounds__(256) lu_permute_rhs_kernel(LuView d, const double *__restrict__ rhs) {
+  xb::pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < d.n) d.work[t] = d.row_scale ? rhs[d.row_perm[t]] / d.row_scale[t] : rhs[d.row_perm[t]];
 }
 // imported plans with row scaling: As = diag(1 / row_scale) A, entry by entry (KLU's SCALE_DIV)
 __global__ void __launch_bounds__(256) lu_scale_values_kernel(LuView d, const double *__restrict__ A) {
+  xb::pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < d.nnz_a) d.As[k] = A[k] / d.row_scale[d.nz_rowpos[k]];
 }
@@ -83,6 +87,7 @@ __global__ void __launch_bounds__(256) lu_scale_values_kernel(LuView d, const do
 // 4096-entry chunk with a fixed-shape tree, then one block per row over the chunk partials.  Fixed shapes
 // and orders, no atomics.
 __global__ void __launch_bounds__(256) lu_pull_short_kernel(LuView d, const double *__restrict__ A, int first, int count) {
+  xb::pdl_wait();
   const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= count) return;
   const int r = d.pull_short_rows[first + w];
@@ -95,6 +100,7 @@ __global__ void __launch_bounds__(256) lu_pull_short_kernel(LuView d, const doub
 
 // rows with a handful of off-diagonal entries (every ring node couples to the supply column only): one thread per row
 __global__ void __launch_bounds__(256) lu_pull_tiny_kernel(LuView d, const double *__restrict__ A, int first, int count) {
+  xb::pdl_wait();
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= count) return;
   const int r = d.pull_tiny_rows[first + t];
@@ -114,6 +120,7 @@ __device__ __forceinline__ double block_tree_sum(double v, double *sh) {
 }
 
 __global__ void __launch_bounds__(256) lu_pull_chunk_kernel(LuView d, const double *__restrict__ A, int first_chunk) {
+  xb::pdl_wait();
   __shared__ double sh[256];
   const int c = first_chunk + blockIdx.x;
   const int r = d.pull_long_rows[d.pull_chunk_row_slot[c]];
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(256) lu_pull_chunk_kernel(LuView d, const doub
 }
 
 __global__ void __launch_bounds__(256) lu_pull_finish_kernel(LuView d, int first_slot) {
+  xb::pdl_wait();
   __shared__ double sh[256];
   const int slot = first_slot + blockIdx.x;
   const int r = d.pull_long_rows[slot];
@@ -140,6 +148,7 @@ __global__ void __launch_bounds__(256) lu_pull_finish_kernel(LuView d, int first
 __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuView d, const double *__restrict__ A,
                                                                           int first, int count,
                                                                           double *__restrict__ xout) {
+  xb::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * kWarpsPerCta + warp;
   if (idx >= count) return;
@@ -189,6 +198,7 @@ __device__ __forceinline__ StagedView staged_load(const LuView &d, int b, unsign
 }
 
 __global__ void __launch_bounds__(1024) lu_refactor_staged_kernel(LuView d, const double *__restrict__ A) {
+  xb::pdl_wait();
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -232,6 +242,7 @@ __global__ void __launch_bounds__(1024) lu_refactor_staged_kernel(LuView d, cons
 }
 
 __global__ void __launch_bounds__(1024) lu_solve_staged_kernel(LuView d, int first, int count, double *__restrict__ xout) {
+  xb::pdl_wait();
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -267,6 +278,7 @@ __device__ __forceinline__ int lower_bound_dev(const int *a, int lo, int hi, int
 }
 
 __global__ void __launch_bounds__(256) lu_big_cols_kernel(LuView d, const double *__restrict__ A, int first, int count) {
+  xb::pdl_wait();
   const int w = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= count) return;
   const int k = d.rf_cols[first + w];
@@ -299,10 +311,12 @@ __global__ void __launch_bounds__(256) lu_big_cols_kernel(LuView d, const double
 
 // Dense columns (supply rails): x = L^-1 A(:,k) over the whole block by the forward row stages, then gathered.
 __global__ void __launch_bounds__(256) lu_dense_scatter_kernel(LuView d, const double *__restrict__ A, int k) {
+  xb::pdl_wait();
   const int q = d.acol_ptr[k] + blockIdx.x * 256 + threadIdx.x;
   if (q < d.acol_ptr[k + 1]) d.work2[d.acol_row[q]] = A[d.acol_src[q]];
 }
 __global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuView d, int k) {
+  xb::pdl_wait();
   const int ub = d.Up[k], ue = d.Up[k + 1] - 1, lb = d.Lp[k], le = d.Lp[k + 1];
   const double pivot = d.work2[k];
   const int t = blockIdx.x * 256 + threadIdx.x;
@@ -316,6 +330,7 @@ __global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuView d, int k) {
 template <bool WARP>
 __global__ void __launch_bounds__(256) lu_fwd_rows_kernel(LuView d, double *vec, const int *__restrict__ rows, int first, int count,
                                                           int col_limit) {
+  xb::pdl_wait();
   __shared__ double sh[256];
   const int lane = threadIdx.x & 31;
   const int idx = WARP ? ((blockIdx.x * 256 + threadIdx.x) >> 5) : blockIdx.x;
@@ -340,6 +355,7 @@ __global__ void __launch_bounds__(256) lu_fwd_rows_kernel(LuView d, double *vec,
 template <bool WARP>
 __global__ void __launch_bounds__(256) lu_bwd_rows_kernel(LuView d, const int *__restrict__ rows, int first, int count,
                                                           double *__restrict__ xout) {
+  xb::pdl_wait();
   __shared__ double sh[256];
   const int lane = threadIdx.x & 31;
   const int idx = WARP ? ((blockIdx.x * 256 + threadIdx.x) >> 5) : blockIdx.x;
@@ -455,8 +471,8 @@ int run_fwd_stages(const LuDev &d, double *vec, int s0, int s1, int col_limit, c
   int launches = 0;
   for (int st = s0; st < s1; ++st) {
     const int ns = d.fs_short_ptr[st + 1] - d.fs_short_ptr[st], nl = d.fs_long_ptr[st + 1] - d.fs_long_ptr[st];
-    if (ns > 0) { lu_fwd_rows_kernel<true><<<(ns * 32 + 255) / 256, 256, 0, s>>>(d, vec, d.fs_short_rows, d.fs_short_ptr[st], ns, col_limit); ++launches; }
-    if (nl > 0) { lu_fwd_rows_kernel<false><<<nl, 256, 0, s>>>(d, vec, d.fs_long_rows, d.fs_long_ptr[st], nl, col_limit); ++launches; }
+    if (ns > 0) { xb::launch_pdl(lu_fwd_rows_kernel<true>, dim3((ns * 32 + 255) / 256), dim3(256), 0, s, d, vec, d.fs_short_rows, d.fs_short_ptr[st], ns, col_limit); ++launches; }
+    if (nl > 0) { xb::launch_pdl(lu_fwd_rows_kernel<false>, dim3(nl), dim3(256), 0, s, d, vec, d.fs_long_rows, d.fs_long_ptr[st], nl, col_limit); ++launches; }
   }
   return launches;
 }
@@ -465,26 +481,26 @@ int run_fwd_stages(const LuDev &d, double *vec, int s0, int s1, int col_limit, c
 int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
   cudaMemsetAsync(d.status, 0, sizeof(int), s);
   int extra = 0;
-  if (d.row_scale) { lu_scale_values_kernel<<<(d.nnz_a + 255) / 256, 256, 0, s>>>(d, A); A = d.As; extra = 1; }
+  if (d.row_scale) { xb::launch_pdl(lu_scale_values_kernel, dim3((d.nnz_a + 255) / 256), dim3(256), 0, s, d, A); A = d.As; extra = 1; }
   const int ctas = (d.nblocks + kWarpsPerCta - 1) / kWarpsPerCta;
-  lu_refactor_kernel<<<ctas, 32 * kWarpsPerCta, 0, s>>>(d, A);
+  xb::launch_pdl(lu_refactor_kernel, dim3(ctas), dim3(32 * kWarpsPerCta), 0, s, d, A);
   int launches = 1 + extra;
   if (d.staged_bytes > 0) {
     const int w = d.staged_warps;
-    lu_refactor_staged_kernel<<<(d.nblocks + w - 1) / w, 32 * w, (size_t)w * d.staged_bytes, s>>>(d, A); ++launches;
+    xb::launch_pdl(lu_refactor_staged_kernel, dim3((d.nblocks + w - 1) / w), dim3(32 * w), (size_t)w * d.staged_bytes, s, d, A); ++launches;
   }
   // large blocks: columns level by level; dense columns of a level after its normal columns
   const int nlev = (int)d.rf_level_ptr.size() - 1;
   for (int l = 0; l < nlev; ++l) {
     const int first = d.rf_level_ptr[l], count = d.rf_level_ptr[l + 1] - first;
-    if (count > 0) { lu_big_cols_kernel<<<(count * 32 + 255) / 256, 256, 0, s>>>(d, A, first, count); ++launches; }
+    if (count > 0) { xb::launch_pdl(lu_big_cols_kernel, dim3((count * 32 + 255) / 256), dim3(256), 0, s, d, A, first, count); ++launches; }
     for (int q = d.rf_dense_ptr[l]; q < d.rf_dense_ptr[l + 1]; ++q) {
       const int k = d.rf_dense_cols[q], bi = d.dense_col_block[q], b = d.big_blocks[bi];
       const int k0 = d.block_ptr_h[b], k1 = d.block_ptr_h[b + 1];
       cudaMemsetAsync(d.work2 + k0, 0, (size_t)(k1 - k0) * sizeof(double), s);
-      lu_dense_scatter_kernel<<<(k1 - k0 + 255) / 256 + 1, 256, 0, s>>>(d, A, k);      // >= number of A entries in the column
+      xb::launch_pdl(lu_dense_scatter_kernel, dim3((k1 - k0 + 255) / 256 + 1), dim3(256), 0, s, d, A, k);      // >= number of A entries in the column
       launches += 1 + run_fwd_stages(d, d.work2, d.big_fs_begin[bi], d.big_fs_end[bi], k, s);
-      lu_dense_gather_kernel<<<(k1 - k0 + 255) / 256 + 1, 256, 0, s>>>(d, k);
+      xb::launch_pdl(lu_dense_gather_kernel, dim3((k1 - k0 + 255) / 256 + 1), dim3(256), 0, s, d, k);
       ++launches;
     }
   }
@@ -493,26 +509,26 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
 
 int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, cudaStream_t s) {
   if (d.row_scale) A = d.As;      // off-diagonal entries: the scaled copy made by the last refactorization of these values
-  lu_permute_rhs_kernel<<<(d.n + 255) / 256, 256, 0, s>>>(d, rhs);
+  xb::launch_pdl(lu_permute_rhs_kernel, dim3((d.n + 255) / 256), dim3(256), 0, s, d, rhs);
   int launches = 1;
   for (int l = 0; l < d.nlevels; ++l) {
     const int first = d.level_ptr[l], count = d.level_ptr[l + 1] - first;
     if (count <= 0) continue;
     const int nt = d.pull_tiny_ptr[l + 1] - d.pull_tiny_ptr[l];
-    if (nt > 0) { lu_pull_tiny_kernel<<<(nt + 255) / 256, 256, 0, s>>>(d, A, d.pull_tiny_ptr[l], nt); ++launches; }
+    if (nt > 0) { xb::launch_pdl(lu_pull_tiny_kernel, dim3((nt + 255) / 256), dim3(256), 0, s, d, A, d.pull_tiny_ptr[l], nt); ++launches; }
     const int ns = d.pull_short_ptr[l + 1] - d.pull_short_ptr[l];
-    if (ns > 0) { lu_pull_short_kernel<<<(ns * 32 + 255) / 256, 256, 0, s>>>(d, A, d.pull_short_ptr[l], ns); ++launches; }
+    if (ns > 0) { xb::launch_pdl(lu_pull_short_kernel, dim3((ns * 32 + 255) / 256), dim3(256), 0, s, d, A, d.pull_short_ptr[l], ns); ++launches; }
     const int nc = d.pull_chunk_ptr[l + 1] - d.pull_chunk_ptr[l], nl = d.pull_long_ptr[l + 1] - d.pull_long_ptr[l];
     if (nl > 0) {
-      lu_pull_chunk_kernel<<<nc, 256, 0, s>>>(d, A, d.pull_chunk_ptr[l]);
-      lu_pull_finish_kernel<<<nl, 256, 0, s>>>(d, d.pull_long_ptr[l]);
+      xb::launch_pdl(lu_pull_chunk_kernel, dim3(nc), dim3(256), 0, s, d, A, d.pull_chunk_ptr[l]);
+      xb::launch_pdl(lu_pull_finish_kernel, dim3(nl), dim3(256), 0, s, d, d.pull_long_ptr[l]);
       launches += 2;
     }
-    lu_solve_level_kernel<<<(count + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, s>>>(d, A, first, count, x);
+    xb::launch_pdl(lu_solve_level_kernel, dim3((count + kWarpsPerCta - 1) / kWarpsPerCta), dim3(32 * kWarpsPerCta), 0, s, d, A, first, count, x);
     ++launches;
     if (d.staged_bytes > 0) {
       const int w = d.staged_warps;
-      lu_solve_staged_kernel<<<(count + w - 1) / w, 32 * w, (size_t)w * d.staged_bytes, s>>>(d, first, count, x);
+      xb::launch_pdl(lu_solve_staged_kernel, dim3((count + w - 1) / w), dim3(32 * w), (size_t)w * d.staged_bytes, s, d, first, count, x);
       ++launches;
     }
     for (size_t bi = 0; bi < d.big_blocks.size(); ++bi) {
@@ -520,8 +536,8 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
       launches += run_fwd_stages(d, d.work, d.big_fs_begin[bi], d.big_fs_end[bi], 0x7fffffff, s);
       for (int st = d.big_bs_begin[bi]; st < d.big_bs_end[bi]; ++st) {
         const int nsr = d.bs_short_ptr[st + 1] - d.bs_short_ptr[st], nlr = d.bs_long_ptr[st + 1] - d.bs_long_ptr[st];
-        if (nsr > 0) { lu_bwd_rows_kernel<true><<<(nsr * 32 + 255) / 256, 256, 0, s>>>(d, d.bs_short_rows, d.bs_short_ptr[st], nsr, x); ++launches; }
-        if (nlr > 0) { lu_bwd_rows_kernel<false><<<nlr, 256, 0, s>>>(d, d.bs_long_rows, d.bs_long_ptr[st], nlr, x); ++launches; }
+        if (nsr > 0) { xb::launch_pdl(lu_bwd_rows_kernel<true>, dim3((nsr * 32 + 255) / 256), dim3(256), 0, s, d, d.bs_short_rows, d.bs_short_ptr[st], nsr, x); ++launches; }
+        if (nlr > 0) { xb::launch_pdl(lu_bwd_rows_kernel<false>, dim3(nlr), dim3(256), 0, s, d, d.bs_long_rows, d.bs_long_ptr[st], nlr, x); ++launches; }
       }
     }
   }

@@ -2,6 +2,7 @@
 // linear-device replay (FilteredMatrix semantics), independent sources, device-resident vectors,
 // norms, the KLU-pattern LU, and the time loop itself.  All vectors stay in HBM for the whole run;
 // per Newton iteration the host receives only a handful of scalars (norms, convergence flag).
+#include "pdl.cuh"
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -33,22 +34,26 @@ void merge_coo(int n, const int32_t *r, const int32_t *c, const double *v, XgLin
 }
 
 __global__ void and_flags_kernel(const int *flags, int n, int *out) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && flags[i] == 0) *out = 0;      // every writer stores the same value
 }
 
 __global__ void gather_kernel(const double *x, const int *idx, int n, double *out) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = x[idx[i]];
 }
 
 __global__ void set_sources_kernel(double *b, const int *rows, const double *vals, int ns) {
+  xb::pdl_wait();
   // one thread: sources may share a row; order is the source order (deterministic)
   if (blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < ns; ++k) b[rows[k]] += vals[k];
 }
 // up to 24 source values travel in the kernel parameter block: no staging copy, no host synchronisation
 struct SrcVals { int n; int rows[24]; double vals[24]; };
 __global__ void set_sources_byval_kernel(double *b, SrcVals sv) {
+  xb::pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < sv.n; ++k) b[sv.rows[k]] += sv.vals[k];
 }
 
@@ -102,7 +107,7 @@ struct GpuBackend {
         const XgSource &q = ctx->sources[k];
         sv.rows[k] = q.row; sv.vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time);
       }
-      set_sources_byval_kernel<<<1, 32, 0, s>>>(v[sim::vB], sv); ++ctx->launches;
+      xb::launch_pdl(set_sources_byval_kernel, dim3(1), dim3(32), 0, s, v[sim::vB], sv); ++ctx->launches;
     } else if (ns > 0) {
       std::vector<double> vals(ns);
       for (int k = 0; k < ns; ++k) {
@@ -111,7 +116,7 @@ struct GpuBackend {
       }
       cudaMemcpyAsync(d_src_vals, vals.data(), ns * sizeof(double), cudaMemcpyHostToDevice, s);
       cudaStreamSynchronize(s);     // vals is a stack-lifetime buffer
-      set_sources_kernel<<<1, 32, 0, s>>>(v[sim::vB], d_src_rows, d_src_vals, ns); ++ctx->launches;
+      xb::launch_pdl(set_sources_kernel, dim3(1), dim3(32), 0, s, v[sim::vB], d_src_rows, d_src_vals, ns); ++ctx->launches;
     }
     return rc == 0;
   }
@@ -139,8 +144,8 @@ struct GpuBackend {
   bool all_devices_converged() {
     int one = 1;
     cudaMemcpyAsync(ctx->d_conv, &one, sizeof(int), cudaMemcpyHostToDevice, s);
-    for (auto &g : ctx->groups) { and_flags_kernel<<<(g.n + 255) / 256, 256, 0, s>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
-    for (auto &g : ctx->sgroups) { and_flags_kernel<<<(g.n + 255) / 256, 256, 0, s>>>(g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
+    for (auto &g : ctx->groups) { xb::launch_pdl(and_flags_kernel, dim3((g.n + 255) / 256), dim3(256), 0, s, g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
+    for (auto &g : ctx->sgroups) { xb::launch_pdl(and_flags_kernel, dim3((g.n + 255) / 256), dim3(256), 0, s, g.d_orig, g.n, ctx->d_conv); ++ctx->launches; }
     int r = 1;
     cudaMemcpyAsync(&r, ctx->d_conv, sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
@@ -176,7 +181,7 @@ struct GpuBackend {
     times.push_back(t);
     const int np = (int)probes.size();
     if (np == 0) return;
-    gather_kernel<<<(np + 255) / 256, 256, 0, s>>>(v[sim::vNextSol], d_probe, np, d_probe_out); ++ctx->launches;
+    xb::launch_pdl(gather_kernel, dim3((np + 255) / 256), dim3(256), 0, s, v[sim::vNextSol], d_probe, np, d_probe_out); ++ctx->launches;
     const size_t off = wave.size();
     wave.resize(off + np);
     cudaMemcpyAsync(&wave[off], d_probe_out, np * sizeof(double), cudaMemcpyDeviceToHost, s);

@@ -1,17 +1,22 @@
+#include "pdl.cuh"
 #include "vecops.cuh"
 namespace xb {
 namespace vec {
 namespace {
-__global__ void fill_k(double *d, double v, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = v; }
+__global__ void fill_k(double *d, double v, int n) {
+  xb::pdl_wait(); int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) d[i] = v; }
 __global__ void axpby_k(double *dst, double a, const double *x, double b, const double *y, int n) {
+  xb::pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = a * x[i] + b * y[i];
 }
 __global__ void solw_k(double *dst, double rel, double ab, const double *a, const double *b, int n) {
+  xb::pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = rel * fmax(fabs(a[i]), fabs(b[i])) + ab;
 }
 __global__ void absw_k(double *dst, double rel, double ab, const double *a, int n) {
+  xb::pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = rel * fabs(a[i]) + ab;
 }
@@ -30,6 +35,7 @@ __device__ __forceinline__ double comb(double a, double b) {
 }
 template <int MODE>
 __global__ void __launch_bounds__(256) reduce_k(const double *x, const double *w, int n, double *out) {
+  xb::pdl_wait();
   __shared__ double sh[256];
   double acc = 0.0;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) acc = comb<MODE>(acc, term<MODE>(x, w, i));
@@ -43,6 +49,7 @@ __global__ void __launch_bounds__(256) reduce_k(const double *x, const double *w
 }
 template <int MODE>
 __global__ void __launch_bounds__(256) reduce_final_k(double *part, int m) {
+  xb::pdl_wait();
   __shared__ double sh[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < m; i += 256) acc = comb<MODE>(acc, part[i]);
@@ -57,8 +64,8 @@ __global__ void __launch_bounds__(256) reduce_final_k(double *part, int m) {
 template <int MODE>
 double reduce_t(const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
   const int blocks = n < 256 * 1024 ? (n + 255) / 256 : 1024;
-  reduce_k<MODE><<<blocks > 0 ? blocks : 1, 256, 0, s>>>(x, w, n, scratch);
-  reduce_final_k<MODE><<<1, 256, 0, s>>>(scratch, blocks > 0 ? blocks : 1);
+  xb::launch_pdl(reduce_k<MODE>, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, s, x, w, n, scratch);
+  xb::launch_pdl(reduce_final_k<MODE>, dim3(1), dim3(256), 0, s, scratch, blocks > 0 ? blocks : 1);
   double h = 0.0;
   cudaMemcpyAsync(&h, scratch, sizeof(double), cudaMemcpyDeviceToHost, s);
   cudaStreamSynchronize(s);
@@ -66,6 +73,7 @@ double reduce_t(const double *x, const double *w, int n, double *scratch, cudaSt
 }
 constexpr int kResBlocks = 1024;
 __global__ void __launch_bounds__(256) residual_norms_k(ResidualArgs a, double *part) {
+  xb::pdl_wait();
   __shared__ double sh[3][256];
   __shared__ int shf;
   if (threadIdx.x == 0) shf = 1;
@@ -117,6 +125,7 @@ __global__ void __launch_bounds__(256) residual_norms_k(ResidualArgs a, double *
   }
 }
 __global__ void __launch_bounds__(256) residual_norms_final_k(const double *part, int m, double *out4) {
+  xb::pdl_wait();
   __shared__ double sh[4][256];
   double s2 = 0.0, mx = 0.0, wm = 0.0, ok = 1.0;
   for (int i = threadIdx.x; i < m; i += 256) {
@@ -140,6 +149,7 @@ __global__ void __launch_bounds__(256) residual_norms_final_k(const double *part
 }
 __global__ void spmv_add_k(int nrows, const int *rows, const int *ptr, const int *col, const double *val,
                            const double *x, double *y) {
+  xb::pdl_wait();
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
   double acc = 0.0;
@@ -147,21 +157,22 @@ __global__ void spmv_add_k(int nrows, const int *rows, const int *ptr, const int
   y[rows[r]] += acc;
 }
 __global__ void scatter_add_k(int n, const int *pos, const double *v, double *vals) {
+  xb::pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) vals[pos[i]] += v[i];
 }
 inline int nb(int n) { return (n + 255) / 256; }
 }  // namespace
 
-void fill(double *d, double v, int n, cudaStream_t s) { if (n > 0) fill_k<<<nb(n), 256, 0, s>>>(d, v, n); }
+void fill(double *d, double v, int n, cudaStream_t s) { if (n > 0) xb::launch_pdl(fill_k, dim3(nb(n)), dim3(256), 0, s, d, v, n); }
 void axpby(double *dst, double a, const double *x, double b, const double *y, int n, cudaStream_t s) {
-  if (n > 0) axpby_k<<<nb(n), 256, 0, s>>>(dst, a, x, b, y, n);
+  if (n > 0) xb::launch_pdl(axpby_k, dim3(nb(n)), dim3(256), 0, s, dst, a, x, b, y, n);
 }
 void sol_weights(double *dst, double rel, double ab, const double *a, const double *b, int n, cudaStream_t s) {
-  if (n > 0) solw_k<<<nb(n), 256, 0, s>>>(dst, rel, ab, a, b, n);
+  if (n > 0) xb::launch_pdl(solw_k, dim3(nb(n)), dim3(256), 0, s, dst, rel, ab, a, b, n);
 }
 void abs_weights(double *dst, double rel, double ab, const double *a, int n, cudaStream_t s) {
-  if (n > 0) absw_k<<<nb(n), 256, 0, s>>>(dst, rel, ab, a, n);
+  if (n > 0) xb::launch_pdl(absw_k, dim3(nb(n)), dim3(256), 0, s, dst, rel, ab, a, n);
 }
 double reduce(Reduce mode, const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
   switch (mode) {
@@ -176,15 +187,15 @@ void residual_norms(const ResidualArgs &a, double *scratch, double *out4, cudaSt
   for (int k = 0; k < a.nflag_arrays; ++k) work = work > a.flag_n[k] ? work : a.flag_n[k];
   int blocks = work < 256 * kResBlocks ? (work + 255) / 256 : kResBlocks;
   if (blocks < 1) blocks = 1;
-  residual_norms_k<<<blocks, 256, 0, s>>>(a, scratch);
-  residual_norms_final_k<<<1, 256, 0, s>>>(scratch, blocks, out4);
+  xb::launch_pdl(residual_norms_k, dim3(blocks), dim3(256), 0, s, a, scratch);
+  xb::launch_pdl(residual_norms_final_k, dim3(1), dim3(256), 0, s, scratch, blocks, out4);
 }
 void spmv_add(int nrows, const int *rows, const int *ptr, const int *col, const double *val, const double *x,
               double *y, cudaStream_t s) {
-  if (nrows > 0) spmv_add_k<<<nb(nrows), 256, 0, s>>>(nrows, rows, ptr, col, val, x, y);
+  if (nrows > 0) xb::launch_pdl(spmv_add_k, dim3(nb(nrows)), dim3(256), 0, s, nrows, rows, ptr, col, val, x, y);
 }
 void scatter_add(int n, const int *pos, const double *v, double *vals, cudaStream_t s) {
-  if (n > 0) scatter_add_k<<<nb(n), 256, 0, s>>>(n, pos, v, vals);
+  if (n > 0) xb::launch_pdl(scatter_add_k, dim3(nb(n)), dim3(256), 0, s, n, pos, v, vals);
 }
 }  // namespace vec
 }  // namespace xb
