@@ -1,5 +1,6 @@
 // xyce_b200 -- assembly kernels (sm_100a).  HBM-bandwidth bound: per destination the kernel
 // reads 4 bytes of map + 8 bytes per contribution per plane and writes 8 bytes per plane.
+#include "pdl.cuh"
 #include "assembly.cuh"
 
 namespace xb {
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(GatherMapDev ma, PlaneSet
 __global__ void __launch_bounds__(256) linear_combo_kernel(int64_t nnz, double a, const double *__restrict__ A,
                                                            double b, const double *__restrict__ B,
                                                            double *__restrict__ J) {
+  xb::pdl_wait();
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nnz) J[k] = a * A[k] + b * B[k];
 }
@@ -264,7 +266,7 @@ cudaError_t measure_fp64_peak(cudaStream_t stream, double *tflops) {
 
 void launch_linear_combo(int64_t nnz, double a, const double *A, double b, const double *B, double *J,
                          cudaStream_t stream) {
-  if (nnz > 0) linear_combo_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(nnz, a, A, b, B, J);
+  if (nnz > 0) xb::launch_pdl(linear_combo_kernel, dim3((unsigned)((nnz + 255) / 256)), dim3(256), 0, stream, nnz, a, A, b, B, J);
 }
 
 }  // namespace xb

@@ -1,5 +1,6 @@
 // xyce_b200 -- kernels of the small compact models (sm_100a).  Memory-bound-ish (few hundred flops per
 // instance): records are read once, coalesced; planes written coalesced.
+#include "pdl.cuh"
 #include "simple_kernels.cuh"
 #include "diode_eval.h"
 #include "adms_rlc_eval.h"
@@ -15,6 +16,7 @@ namespace {
 __device__ __forceinline__ double gatherv(const double *__restrict__ x, int lid) { return lid >= 0 ? __ldg(x + lid) : 0.0; }
 
 __global__ void __launch_bounds__(128) diode_kernel(GroupDev g, b4::LoadArgs a) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const int n = g.n;
@@ -68,6 +70,7 @@ __device__ __forceinline__ void store_planes(const GroupDev &g, const b4::LoadAr
 }
 
 __global__ void __launch_bounds__(128) mos1_kernel(GroupDev g, b4::LoadArgs a) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const int n = g.n;
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(128) mos1_kernel(GroupDev g, b4::LoadArgs a) {
 }
 
 __global__ void __launch_bounds__(128) bjt_kernel(GroupDev g, b4::LoadArgs a) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const int n = g.n;
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(128) bjt_kernel(GroupDev g, b4::LoadArgs a) {
 }
 
 __global__ void __launch_bounds__(128) rlc_kernel(GroupDev g, b4::LoadArgs a) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const int n = g.n;
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(128) rlc_kernel(GroupDev g, b4::LoadArgs a) {
 
 // ADMS-generated MVS 2.0.0 ETSOI (N_DEV_ADMSmvs_2_0_0_etsoi.C): static contributions only, no limiting, no state
 __global__ void __launch_bounds__(128) mvs_kernel(GroupDev g, b4::LoadArgs a) {
+  xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.n) return;
   const int n = g.n;
@@ -216,11 +222,11 @@ void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
   if (g.n <= 0) return;
   const int blocks = (g.n + 127) / 128;
   switch (g.type) {
-    case kDiode: diode_kernel<<<blocks, 128, 0, s>>>(g, a); break;
-    case kMos1: mos1_kernel<<<blocks, 128, 0, s>>>(g, a); break;
-    case kBjt: bjt_kernel<<<blocks, 128, 0, s>>>(g, a); break;
-    case kRlc: rlc_kernel<<<blocks, 128, 0, s>>>(g, a); break;
-    case kMvs: mvs_kernel<<<blocks, 128, 0, s>>>(g, a); break;
+    case kDiode: xb::launch_pdl(diode_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
+    case kMos1: xb::launch_pdl(mos1_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
+    case kBjt: xb::launch_pdl(bjt_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
+    case kRlc: xb::launch_pdl(rlc_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
+    case kMvs: xb::launch_pdl(mvs_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
     default: break;
   }
 }
