@@ -76,3 +76,31 @@ def test_lead_currents_of_a_four_terminal_device_are_its_own_row_contributions(h
                 assert abs(got - want) <= 1e-12 * max(abs(want), 1e-3 * np.max(np.abs(lead[vec]))), (variant, i, k, key)
         assert lead["junctionV"][b] == V[kD] - V[kS] and lead["junctionV"][b + 1] == V[kGE] - V[kS]
         assert lead["junctionV"][b + 2] == 0.0 and lead["junctionV"][b + 3] == 0.0
+
+
+@pytest.mark.parametrize("extra", [dict(TEMP=125.0), dict(TEMP=-40.0, NF=2.0), dict(M=3.0),
+                                   dict(SA=2e-7, SB=3e-7, SD=1e-7, NF=2.0)], ids=["hot", "cold_nf2", "m3", "stress"])
+@pytest.mark.parametrize("variant", ["default", "igc2", "gidl", "default_v470", "igc2_v461"])
+def test_instance_parameters_reach_the_evaluator_through_the_records(host_mirror, variant, extra):
+    """instance temperature, finger count, multiplicity and stress parameters act through
+    processParams / updateTemperature of the reference (N_DEV_MOSFET_B4p82.C:120-2734 and the 4.7.0 / 4.6.1 twins),
+    i.e. through the exported records: the evaluator must reproduce the reference on them unchanged"""
+    from b4_common import host_mirror_case, records_from_ref
+    ref = isolated_devices(oracle_ref.RefCircuit, 3, variant, seed=10, inst_extra=extra)
+    rng = np.random.default_rng(1000)
+    x = rng.uniform(-0.3, 1.3, ref.n)
+    flags = dict(transient=1, newtonIter=1)
+    ref.set_flags(**flags)
+    nsto = rng.normal(0.3, 0.3, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    ref.set_state(curr_sto=nsto, next_sto=nsto, curr_sta=np.zeros(ref.n_sta)); ref.set_von(von)
+    want = ref.load(x)
+    g = dict(x=x, nsto=nsto, csto=nsto, von=von, rowptr=ref.rowptr, colind=ref.colind,
+             flags=np.array([flags.get(f, 1 if f == "voltageLimiter" else 0) for f in oracle_ref.FLAG_NAMES]),
+             curr_sta=np.zeros(ref.n_sta), n_sta=np.array(ref.n_sta), n_sto=np.array(ref.n_sto))
+    for k, v in records_from_ref(ref).items():
+        g["rec_" + k] = v
+    _, asm = host_mirror_case(host_mirror, g)
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(asm[k], want[k], scale) < 1e-12, (variant, extra, k)
