@@ -137,7 +137,7 @@ def run_reference(args):
                              "sample": "%d BSIM4 instances per core x %d cores, %.0f s budget, oracle/_ref "
                                        "(reference N_DEV_MOSFET_B4*.C compiled in place)" % (2 * sample_inv, cores, budget)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_json_line(line)
 
 
 def tran_extra(device):
@@ -202,7 +202,6 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner / diagnostics: not on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w = wl.inverter_array(args.inverters, seed=12345 + rank)
@@ -335,12 +334,31 @@ def run_ours(args):
                                               "N_DEV_MOSFET_B4*.C compiled in place, same cards/operating points" % reps}
         except Exception as exc:   # the oracle library did not travel: report, do not fake
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
-    print(json.dumps(line))
+    emit_json_line(line)
     if dist:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep the real stdout for it and point file descriptor 1 at stderr for
+    everything else (NCCL prints its version banner to fd 1, the reference code its netlist warnings, ...)."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
