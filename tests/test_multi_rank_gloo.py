@@ -97,3 +97,38 @@ def test_ring_partition_is_consistent():
     # the supply source (linear G stamps on shared unknowns + the source itself) is kept by rank 0 only
     assert len(parts[0]["sources"]["row"]) == 1 and all(len(p["sources"]["row"]) == 0 for p in parts[1:])
     assert len(parts[0]["linear"]["g_row"]) == 2 and all(len(p["linear"]["g_row"]) == 0 for p in parts[1:])
+
+
+def test_graph_partition_keeps_rings_whole_and_balances():
+    """partition_instances on the ring-oscillator array: the supply rail is recognised as a global net, every ring is a
+    connected component and lands on one rank, loads are balanced, and only the rail (and the unknowns no instance
+    touches) end up shared"""
+    from xyce_b200 import workloads as wl
+    w = wl.ring_oscillator_array(13, 11)
+    inst_nodes = np.asarray(w["lids"])                                   # [n_inst, 12], -1 = ground
+    for world in (2, 3, 4):
+        owner = pt.partition_instances(inst_nodes, w["n_unknowns"], world)
+        assert owner.min() == 0 and owner.max() == world - 1
+        ring = inst_nodes[:, 0] // 11                                    # drain node = stage output, 11 stages per ring
+        for r in range(13):
+            assert len(set(owner[ring == r].tolist())) == 1              # a ring is never split
+        counts = np.bincount(owner, minlength=world)
+        assert counts.max() - counts.min() <= 2 * 11                     # within one ring (22 MOSFETs) of each other
+        un = pt.classify_unknowns(inst_nodes, owner, w["n_unknowns"], world)
+        shared = np.where(un == -1)[0]
+        assert set(shared.tolist()) == {w["vdd"], w["branch"]}
+
+
+def test_graph_partition_cuts_one_big_component_along_bfs_order():
+    """a single chain of 2-terminal devices (one connected component heavier than any rank's share): graph growing cuts it
+    into contiguous runs, so the number of shared unknowns is world - 1"""
+    n = 1000
+    inst_nodes = np.stack([np.arange(n), np.arange(1, n + 1)], axis=1)
+    inst_nodes[-1, 1] = -1                                              # last device to ground
+    for world in (2, 4, 8):
+        owner = pt.partition_instances(inst_nodes, n, world)
+        counts = np.bincount(owner, minlength=world)
+        assert counts.max() <= 1.3 * n / world and counts.min() >= 0.7 * n / world
+        un = pt.classify_unknowns(inst_nodes, owner, n, world)
+        assert np.sum(un == -1) == world - 1
+        assert np.sum(np.diff(owner) != 0) == world - 1                 # contiguous runs along the chain

@@ -5,7 +5,8 @@ instances to ranks, loads into *overlapped* vectors/matrices and then exports gh
 (`N_LOA_CktLoader.C:600-601`, `:816-829`; `N_LAS_EpetraMultiVector.C:843-849`, `N_LAS_EpetraMatrix.C:202-208`);
 the direct solve gathers everything on rank 0.  Here:
 
-* instances are partitioned by graph partition (for ring/inverter arrays: contiguous ring ranges);
+* instances are partitioned by graph partition (`partition_instances`: connected components of the instance-node graph
+  without its global nets, packed / cut by graph growing; for ring/inverter arrays this gives whole rings per rank);
 * every rank keeps the unknowns only its own instances touch ("interior") plus a replicated copy of the
   unknowns touched from several ranks ("shared": supply rails, source branches);
 * after the local evaluation + assembly (CUDA, no communication) the shared rows of F, Q, dFdxdVp, dQdxdVp and
@@ -30,6 +31,64 @@ def split_ranges(n_items, world):
     for r in range(world):
         b.append(b[-1] + base + (1 if r < rem else 0))
     return b
+
+
+def partition_instances(inst_nodes, n_unknowns, world, weights=None, global_degree=None):
+    """Graph partition of the instance-node bipartite graph: assigns every device instance to a rank so
+    that the parts are balanced by weight and few unknowns are touched from more than one rank.
+
+    inst_nodes: [n_inst, k] unknown ids touched by each instance (-1 = ground).  Unknowns touched by more than
+    `global_degree` instances (default max(64, 8 sqrt(n_inst)): supply rails, clock nets) are treated as global --
+    they end up shared whatever the partition, so they must not glue the graph together.  Connected components of
+    what remains (rings, cells, sub-circuits) are packed into the ranks largest first; a component heavier than a
+    rank's share is cut along a breadth-first order (graph growing), which keeps neighbouring instances together.
+    Returns inst_owner[n_inst]."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import breadth_first_order, connected_components
+    inst_nodes = np.asarray(inst_nodes)
+    n_inst = inst_nodes.shape[0]
+    w = np.ones(n_inst) if weights is None else np.asarray(weights, dtype=float)
+    if world <= 1 or n_inst == 0:
+        return np.zeros(n_inst, dtype=np.int64)
+    ii = np.repeat(np.arange(n_inst), inst_nodes.shape[1])
+    nn = inst_nodes.reshape(-1)
+    keep = nn >= 0
+    ii, nn = ii[keep], nn[keep]
+    deg = np.bincount(nn, minlength=n_unknowns)
+    gd = max(64, int(8 * np.sqrt(n_inst))) if global_degree is None else global_degree
+    local = deg[nn] <= gd
+    B = sp.csr_matrix((np.ones(local.sum(), dtype=np.int8), (ii[local], nn[local])), shape=(n_inst, n_unknowns))
+    A = (B @ B.T).tocsr()                      # instances adjacent when they share a non-global unknown
+    ncomp, comp = connected_components(A, directed=False)
+    comp_w = np.bincount(comp, weights=w, minlength=ncomp)
+    target = w.sum() / world
+    owner = np.full(n_inst, -1, dtype=np.int64)
+    load = np.zeros(world)
+    order = np.argsort(-comp_w, kind="stable")
+    members = [None] * ncomp
+    srt = np.argsort(comp, kind="stable")
+    bounds = np.concatenate([[0], np.cumsum(np.bincount(comp, minlength=ncomp))])
+    for c in range(ncomp):
+        members[c] = srt[bounds[c]:bounds[c + 1]]
+    for c in order:
+        m = members[c]
+        if comp_w[c] <= 1.05 * target or len(m) == 1:
+            r = int(np.argmin(load))
+            owner[m] = r; load[r] += comp_w[c]
+            continue
+        # heavy component: breadth-first order from its first instance, cut into rank-sized runs
+        sub = A[m][:, m]
+        bfs, _ = breadth_first_order(sub, 0, directed=False)
+        seq = m[bfs]
+        k = 0
+        while k < len(seq):
+            r = int(np.argmin(load))
+            room = max(target - load[r], 0.25 * target)
+            cw = np.cumsum(w[seq[k:]])
+            take = max(1, int(np.searchsorted(cw, room, side="right")))
+            owner[seq[k:k + take]] = r; load[r] += cw[take - 1]
+            k += take
+    return owner
 
 
 def classify_unknowns(inst_nodes, inst_owner, n_unknowns, world, always_shared=()):
