@@ -218,3 +218,34 @@ def test_fused_load_equals_separate_calls_bitwise():
     for p, q in zip(a, b):
         assert torch.equal(p, q)
     eng.close()
+
+
+@pytest.mark.parametrize("zero_copy", [1, 0])
+def test_load_host_with_pinned_buffers(zero_copy):
+    """xgpu_load_host on pinned, mapped host buffers (the assembly kernel writes them directly over PCIe) gives bitwise
+    the results of the pageable-buffer copy path"""
+    import ctypes as C
+    import torch
+    ref = isolated_devices(oracle_ref.RefCircuit, 300, "default", seed=9, sorted_bins=True)
+    eng, _ = engine_from_ref(ref)
+    eng.set_option("zero_copy_out", zero_copy)
+    rng = np.random.default_rng(10)
+    x = rng.uniform(-0.2, 1.2, ref.n)
+    sto = rng.normal(0.3, 0.3, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    ss = solver_state(transient=1, newtonIter=1)
+    outs = []
+    for pinned in (False, True):
+        eng.set_state(0, sto); eng.set_state(1, sto); eng.b4_set_von(0, von)
+        if not pinned:
+            outs.append(eng.load_host(x, ss))
+            continue
+        hx = torch.tensor(x, dtype=torch.float64).pin_memory()
+        bufs = [torch.full((ref.n,), 3.0, dtype=torch.float64).pin_memory() for _ in range(4)] + \
+               [torch.full((eng.nnz,), 3.0, dtype=torch.float64).pin_memory() for _ in range(2)]
+        ptr = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+        assert eng.lib.xgpu_load_host(eng.h, ptr(hx), C.byref(ss), *[ptr(t) for t in bufs]) == 0
+        outs.append(dict(zip(("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"), [t.numpy().copy() for t in bufs])))
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    eng.close()

@@ -176,6 +176,7 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
   if (n == "b4_spec" && (value == 0 || value == 1)) { ctx->b4_spec = value; return 0; }
   if (n == "lu_graphs" && (value == 0 || value == 1)) { ctx->lu_graphs = value; return 0; }
+  if (n == "zero_copy_out" && (value == 0 || value == 1)) { ctx->zero_copy_out = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
 
@@ -688,6 +689,21 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
   if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
   double **b = ctx->buf;
   XG_CUDA(cudaMemcpyAsync(b[0], h_sol, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // Pinned, mapped host buffers (cudaHostAlloc / cudaHostRegister: what a GPU-aware caller provides) are written by the
+  // assembly kernel directly over PCIe -- the transfer overlaps the assembly and the six device-to-host copies with
+  // their launch overheads disappear.  Pageable buffers take the copy path below.
+  if (ctx->zero_copy_out && h_f && h_q && h_fl && h_ql && h_dFdx && h_dQdx) {
+    double *hp[6] = {h_f, h_q, h_fl, h_ql, h_dFdx, h_dQdx}, *dp[6];
+    bool mapped = true;
+    for (int p = 0; p < 6 && mapped; ++p)
+      if (cudaHostGetDevicePointer((void **)&dp[p], hp[p], 0) != cudaSuccess) { cudaGetLastError(); mapped = false; }
+    if (mapped) {
+      const int rc0 = xgpu_load_dae(ctx, b[0], b[9], b[10], b[7], b[8], ss, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], 0);
+      if (rc0) return rc0;
+      XG_CUDA(cudaStreamSynchronize(ctx->stream));
+      return 0;
+    }
+  }
   const int rc = xgpu_load_dae(ctx, b[0], b[9], b[10], b[7], b[8], ss, b[1], b[2], b[3], b[4], b[5], b[6], 0);
   if (rc) return rc;
   double *hv[4] = {h_f, h_q, h_fl, h_ql};

@@ -100,6 +100,8 @@ struct xgpu_ctx {
   struct LuGraph { cudaGraphExec_t exec = nullptr; const void *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; int launches = 0; };
   LuGraph g_refactor, g_solve;
   int lu_graphs = 1;          // option "lu_graphs": 0 = plain stream launches
+  int zero_copy_out = 0;      // option "zero_copy_out" = 1: xgpu_load_host lets the assembly kernel write pinned, mapped host outputs directly
+                              // (measured +2.6 % on the C2 host-buffer path; off by default: DMA copies behave predictably with many ranks)
   // work space of xgpu_tran_run, kept between runs (driver-level allocation and pinned-memory calls cost
   // milliseconds to tenths of a second each): device pool in doubles, small int arena, pinned readback words
   double *tran_pool = nullptr; size_t tran_pool_len = 0;
