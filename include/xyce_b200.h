@@ -101,7 +101,8 @@ int xgpu_finalize(xgpu_ctx *ctx);
  * (id, ig, is, ib are consecutive LIDs of the lead-current vectors; -1 = instance without lead currents).
  * xgpu_b4_lead_load, called after xgpu_update_state, ASSIGNS leadF, leadQ and junctionV at those LIDs (device
  * vectors of the DataStore: nextLeadCurrFCompRawPtr, nextLeadCurrQCompRawPtr, nextJunctionVCompRawPtr).
- * 4-terminal (default-topology) groups only; error 20 for groups with internal nodes. */
+ * 4-terminal groups take the values from the contribution planes (they are the instance's own row terms); groups with
+ * internal nodes get them from the evaluation kernel. */
 int xgpu_b4_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0);
 int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV);
 

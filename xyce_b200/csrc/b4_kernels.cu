@@ -138,6 +138,14 @@ __device__ __forceinline__ void eval_instance(const GroupDev &g, const LoadArgs 
   evaluate(a.S, M, P, I, V, sto_old, src != kOldNone, g.von[i], W, e);
 
   if (!valid) return;
+  if (GENERAL) {        // lead currents of devices with internal nodes (the 4-terminal fast path gets them from the planes)
+    if (g.lead) {
+      real lf[4], lq[4];
+      emit_lead(M, I, W, lf, lq);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { g.lead[(size_t)k * n + i] = to_double(lf[k]); g.lead[(size_t)(4 + k) * n + i] = to_double(lq[k]); }
+    }
+  }
   // ---- carried state, store and state vectors ----
   g.von[i] = to_double(W.von);
   g.orig_flag[i] = !W.limitedFlag;      // Instance::isConverged() (N_DEV_MOSFET_B4.h:2328-2331): only pnjlim invalidates convergence

@@ -43,6 +43,8 @@ struct GroupDev {
   // contribution planes (see assembly.cuh): element (row r, instance i) of this group lives at
   // vec_base + r*n + i inside each of the 4 vector planes; slot s at mat_base + s*n + i.
   long long vec_base, mat_base;
+  // general-topology groups with lead currents requested: [8][n] = leadF(id, ig, is, ib), leadQ(id, ig, is, ib); else null
+  double *lead;
 };
 
 struct LoadArgs {

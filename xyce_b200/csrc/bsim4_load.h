@@ -436,6 +436,40 @@ XB_HD void emit_vectors(const SolverFlags &S, const B4Model &M, const B4Inst &I,
   }
 }
 
+// Lead currents and charges of the four terminals (id, ig, is, ib): Master::loadDAEVectors' loadLeadCurrent block
+// (N_DEV_MOSFET_B4.C:10933-10987), for any topology.
+XB_HD void emit_lead(const B4Model &M, const B4Inst &I, const B4Mid &W, real (&leadF)[4], real (&leadQ)[4]) {
+  const real np = I.numberParallel;
+  const real sg = (M.dtype > 0) ? 1.0 : -1.0;
+  const real Qg = sg * W.qg, Qd = sg * W.qd, Qb = sg * W.qb;
+  const real Qjs = I.rbodyMod ? sg * W.qbs : 0.0;
+  const real Qjd = I.rbodyMod ? sg * W.qbd : 0.0;
+  const real Qgmid = (I.rgateMod == 3) ? sg * W.qgmid : 0.0;
+  leadQ[0] = (Qd) * np;
+  leadQ[1] = (Qg) * np;
+  leadQ[3] = (Qb) * np;
+  if (!I.rbodyMod) leadQ[2] = -(+Qg + Qb + Qd + Qgmid) * np;
+  else leadQ[2] = -(Qd + Qg + Qb + Qjd + Qjs + Qgmid) * np;
+  leadF[0] = -(W.ceqjd - W.ceqbd - W.ceqdrn + W.Idtoteq) * np;
+  leadF[2] = W.Isource * np;
+  leadF[1] = (-W.ceqgcrg + W.Igtoteq) * np;
+  leadF[3] = 0.0;
+  if (I.rgateMod == 1) leadF[1] += (W.Igate) * np;
+  else if (I.rgateMod == 2) leadF[1] += (W.Igate) * np;
+  else if (I.rgateMod == 3) leadF[1] += (W.IgateMid) * np;
+  if (!I.rbodyMod) {
+    leadF[3] += -(W.ceqbd + W.ceqbs - W.ceqjd - W.ceqjs + W.Ibtoteq) * np;
+    leadF[2] += -(W.ceqdrn - W.ceqbs + W.ceqjs + W.Istoteq) * np;
+  } else {
+    leadF[3] = -(W.Isbb + W.Idbb + W.Ibpb) * np;
+    leadF[2] += -(W.ceqdrn - W.ceqbs + W.ceqjs + W.Istoteq) * np;
+  }
+  if (M.rdsMod) {
+    leadF[0] += (W.ceqgdtot) * np;
+    leadF[2] += -(W.ceqgstot) * np;
+  }
+}
+
 template <class E>
 XB_HD void emit_matrices(const B4Model &M, const B4Inst &I, const B4Mid &W, E &e) {
   const real np = I.numberParallel;

@@ -142,7 +142,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto &g : ctx->groups) {
     cudaFree(g.d_inst_d); cudaFree(g.d_von); cudaFree(g.d_topo); cudaFree(g.d_model_idx);
-    cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); cudaFree(g.d_branch0);
+    cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); cudaFree(g.d_branch0); cudaFree(g.d_lead);
   }
   for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
@@ -478,7 +478,8 @@ int xgpu_finalize(xgpu_ctx *ctx) {
 }
 
 namespace {
-// Lead currents of 4-terminal (default-topology) BSIM4 instances.  With no internal nodes the lead quantities of
+// Lead currents of BSIM4 instances.  Groups with internal nodes: the evaluation kernel has written the lead block
+// (emit_lead, bsim4_load.h) to the group's [8][n] buffer.  4-terminal groups: with no internal nodes the lead quantities of
 // Master::loadDAEVectors (N_DEV_MOSFET_B4.C:10933-10987) ARE the instance's own F and Q contributions to its
 // drain / gate / source / bulk rows -- leadF[id] = -(ceqjd - ceqbd - ceqdrn + Idtoteq) np is the D' row term (:10691),
 // leadQ[is] = -(Qg + Qb + Qd) np the S' row term (:10893), and so on -- which the evaluation kernel has just
@@ -509,9 +510,13 @@ __global__ void b4_lead_kernel(int n, const double *__restrict__ planeF, const d
 int xgpu_b4_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0) {
   if (!ctx || group < 0 || group >= (int)ctx->groups.size() || !branch_lid0) return 1;
   XgHostGroup &g = ctx->groups[group];
-  if (g.general) return fail(ctx, 20, "lead currents are implemented for 4-terminal (default-topology) BSIM4 groups only");
   cudaFree(g.d_branch0); g.d_branch0 = nullptr;
   XG_CUDA(upload(&g.d_branch0, branch_lid0, (size_t)g.n));
+  if (g.general && !g.d_lead) {      // devices with internal nodes: the evaluation kernel computes the lead block itself
+    XG_CUDA(cudaMalloc((void **)&g.d_lead, (size_t)8 * std::max(g.n, 1) * sizeof(double)));
+    XG_CUDA(cudaMemset(g.d_lead, 0, (size_t)8 * std::max(g.n, 1) * sizeof(double)));
+    g.dev.lead = g.d_lead;
+  }
   return 0;
 }
 
@@ -521,6 +526,7 @@ int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, doubl
   for (auto &g : ctx->groups) {
     if (!g.d_branch0 || g.n == 0) continue;
     const double *pF = ctx->d_vec_planes + g.dev.vec_base, *pQ = ctx->d_vec_planes + ctx->vec_plane + g.dev.vec_base;
+    if (g.general) { pF = g.d_lead; pQ = g.d_lead + (size_t)4 * g.n; }
     b4_lead_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g.n, pF, pQ, g.d_lids, g.d_branch0, d_sol, d_leadF, d_leadQ, d_junctionV);
     ++ctx->launches;
   }

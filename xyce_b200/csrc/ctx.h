@@ -20,6 +20,7 @@ struct XgHostGroup {
   int *d_topo = nullptr, *d_model_idx = nullptr, *d_size_idx = nullptr, *d_lids = nullptr;
   int *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
   int *d_branch0 = nullptr;        // [n] first branch-data LID of every instance (lead currents), null = not requested
+  double *d_lead = nullptr;        // [8][n] lead block of a general-topology group (written by the evaluation kernel)
   // runs of equal (model, bin) along the instance order; packs = their records, rebuilt when the
   // model table changes (empty = more than kMaxUniformRuns runs -> per-thread-record kernel)
   std::vector<int32_t> run_model, run_size, run_start, run_count;
