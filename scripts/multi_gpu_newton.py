@@ -29,13 +29,14 @@ def main():
     ap.add_argument("--stages", type=int, default=101)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--graph-partition", type=int, default=0, help="1 = partition_instances (graph partition) instead of ring ranges")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     wg = wl.ring_oscillator_array(a.rings, a.stages)
-    w = pt.partition_ring_array(wg, world, rank)
+    w = pt.partition_workload(wg, world, rank) if a.graph_partition else pt.partition_ring_array(wg, world, rank)
     eng = wl.build_engine(w, device=local)
     stream = torch.cuda.current_stream(); eng.set_stream(stream.cuda_stream)
     n, nnz, ni, ns = w["n_unknowns"], eng.nnz, w["n_interior"], w["n_shared"]

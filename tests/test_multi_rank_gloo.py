@@ -132,3 +132,19 @@ def test_graph_partition_cuts_one_big_component_along_bfs_order():
         un = pt.classify_unknowns(inst_nodes, owner, n, world)
         assert np.sum(un == -1) == world - 1
         assert np.sum(np.diff(owner) != 0) == world - 1                 # contiguous runs along the chain
+
+
+def test_workload_partition_from_the_graph_partitioner():
+    """partition_workload with the default (graph) partition on the ring array: same invariants as the ring-range split"""
+    w = wl.ring_oscillator_array(7, 11)
+    world = 3
+    parts = [pt.partition_workload(w, world, r) for r in range(world)]
+    assert sum(p["n_inst"] for p in parts) == w["n_inst"]
+    assert sum(p["n_interior"] for p in parts) + parts[0]["n_shared"] == w["n_unknowns"]
+    for p in parts:
+        assert p["n_shared"] == 2 and p["lids"].max() < p["n_unknowns"] and p["n_inst"] % 22 == 0      # whole rings
+    allint = np.concatenate([p["glob_of_local"][:p["n_interior"]] for p in parts])
+    assert len(np.unique(allint)) == len(allint)
+    assert len(parts[0]["sources"]["row"]) == 1 and all(len(p["sources"]["row"]) == 0 for p in parts[1:])
+    # per-ring load capacitors stay with their ring's rank: C stamps of all parts together = the original ones
+    assert sum(len(p["linear"]["c_row"]) for p in parts) == len(w["linear"]["c_row"])

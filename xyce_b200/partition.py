@@ -118,12 +118,22 @@ def local_numbering(owner, rank):
 
 
 def partition_ring_array(w, world, rank):
-    """Split a workloads.ring_oscillator_array dict by ring ranges.  Linear devices and sources attached only to
-    shared unknowns (the supply source) are kept by rank 0 so that the all-reduce counts them once."""
+    """Split a workloads.ring_oscillator_array dict by contiguous ring ranges (what the graph partitioner finds for
+    this netlist, in a fixed order)."""
     stages, n_rings = w["stages"], w["n_rings"]
     ring_of_inst = (np.arange(w["n_inst"]) % (n_rings * stages)) // stages
     b = split_ranges(n_rings, world)
     inst_owner = np.searchsorted(np.array(b[1:]), ring_of_inst, side="right")
+    return partition_workload(w, world, rank, inst_owner)
+
+
+def partition_workload(w, world, rank, inst_owner=None):
+    """This rank's part of a workload dict (workloads.py layout: BSIM4 instances + linear devices + sources).
+    inst_owner: rank of every instance; default = partition_instances on the instance-node graph.  Linear devices and
+    sources attached only to shared unknowns (the supply source) are kept by rank 0 so that the all-reduce counts
+    them once."""
+    if inst_owner is None:
+        inst_owner = partition_instances(w["lids"][:, :4], w["n_unknowns"], world)
     owner = classify_unknowns(w["lids"][:, :4], inst_owner, w["n_unknowns"], world)
     glob, loc, n_int = local_numbering(owner, rank)
     mine = np.where(inst_owner == rank)[0]
