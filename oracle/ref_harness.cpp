@@ -752,7 +752,14 @@ struct RefBackend {
 };
 }  // namespace
 
+// step sequence for the next xref_tran_run (TranParams::replay_h / replay_order); consumed by that run
+static int g_replay_n = 0;
+static const double *g_replay_h = nullptr;
+static const int *g_replay_order = nullptr;
+
 extern "C" {
+
+void xref_tran_replay(int n, const double *h, const int *order) { g_replay_n = n; g_replay_h = h; g_replay_order = order; }
 
 // params: tstop, tstep, delmax, method (0 / 7 trapezoid, 8 Gear), dcop (0 / 1).  Linear part as COO (G, C), sources {row, scale, type, p[7]}.
 int xref_tran_run(void *h, const double *params5, const double *x0, int nG, const int *gr, const int *gc, const double *gv,
@@ -779,6 +786,8 @@ int xref_tran_run(void *h, const double *params5, const double *x0, int nG, cons
   P.tstop = params5[0]; P.tstep = params5[1]; P.delmax = params5[2];
   if ((int)params5[3] == 8) P.method = 8;
   P.dcop = params5[4] != 0.0;
+  if (g_replay_n > 0) { P.replay_h.assign(g_replay_h, g_replay_h + g_replay_n); P.replay_order.assign(g_replay_order, g_replay_order + g_replay_n); }
+  g_replay_n = 0;
   xb::sim::TransientDriver<RefBackend> drv(B, P);
   const int rc = drv.run();
   *n_out = std::min((int)B.times.size(), max_out);

@@ -171,10 +171,16 @@ class RefCircuit:
         r, c = np.ascontiguousarray(rows, dtype=np.int32), np.ascontiguousarray(cols, dtype=np.int32)
         self.lib.xref_add_pattern_entries(self.h, len(r), iptr(r), iptr(c))
 
-    def tran_run(self, x0, tstop, tstep, probes, linear, sources, delmax=0.0, max_out=200000, method=0, dcop=0):
-        """Transient run: tran_driver.h control flow around the reference device code + ksparse."""
+    def tran_run(self, x0, tstop, tstep, probes, linear, sources, delmax=0.0, max_out=200000, method=0, dcop=0,
+                 replay=None):
+        """Transient run: tran_driver.h control flow around the reference device code + ksparse.
+        replay = (h[], order[]): integrate on exactly these accepted steps (TranParams::replay_h) instead of
+        selecting steps -- used to compare a sub-circuit with a larger run on that run's own time points."""
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        if replay is not None:
+            rh, ro = f64(replay[0]), i32(replay[1])
+            self.lib.xref_tran_replay(len(rh), dptr(rh), iptr(ro))
         par = f64([tstop, tstep, delmax, method, dcop])
         L = {k: (i32(v) if k.endswith(("row", "col")) else f64(v)) for k, v in linear.items()}
         S = dict(row=i32(sources["row"]), scale=f64(sources["scale"]), type=i32(sources["type"]), params=f64(sources["params"]))

@@ -24,8 +24,12 @@ def run_bench(*flags):
 
 @pytest.mark.skipif(not oracle_ref.available(), reason="oracle/_ref not built")
 def test_reference_arm_line():
-    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1")
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--tran-budget", "1")
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    t = d["tran_c3"]                                    # .TRAN leg: BASELINE config 3 on the host cores
+    assert t["kind"] == "reference" and t["cores"] >= 1 and t["wall_s"] > 0 and t["rings_run"] >= t["cores"]
+    assert 20 < t["accepted_steps_per_ring"] < 200 and t["newton_iters_per_ring"] > t["accepted_steps_per_ring"]
+    assert d["config"]["instances_per_gpu"] == 100000   # the full array, not a sample
     assert d["metric"] == "bsim4_device_load_stamp_evals_per_sec" and d["unit"] == "evals/s" and d["dtype"] == "f64"
     assert d["value"] > 1e5 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
@@ -52,7 +56,7 @@ def test_reference_arm_under_torchrun_prints_once():
     """launched like the driver does for N > 1: rank 0 alone runs and prints the line, the other ranks exit 0"""
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900)
+                        "--steps", "1", "--warmup", "1", "--no-tran"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
     assert len(lines) == 1

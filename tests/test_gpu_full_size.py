@@ -175,3 +175,88 @@ def test_accumulate_keeps_the_plus_equals_contract():
     for z, b, c in zip(zero, base, [3.0] * 4 + [-2.0] * 2):
         assert torch.allclose(b, z + c, rtol=0, atol=1e-12 * float(z.abs().max() + 1))
     eng.close()
+
+
+# ---- BASELINE config 3 at its stated size against the oracle -------------------------------------------------------
+C3_RINGS, C3_STAGES = 4950, 101
+C3_SAMPLE = [0, 1, 617, 1234, 2475, 3333, 4500, 4949]      # rings probed across the array
+
+
+def _single_ring_oracle(w, r):
+    """Ring r of the array as its own circuit around the reference's BSIM4 objects (same rotation of the initial condition)."""
+    w1 = wl.ring_oscillator_array(1, C3_STAGES, shifts=[int(w["shift"][r])])
+    from b4_common import ref_circuit_from_workload
+    ref = ref_circuit_from_workload(oracle_ref.RefCircuit, w1)
+    return w1, ref
+
+
+def test_c3_sampled_oracle_parity_of_stamps_at_full_size():
+    """999 900 MOSFETs: residual rows and Jacobian entries of 8 rings spread over the array equal the reference objects'
+    on the same ring built alone (1e-12; per-entry scale = the largest entry of the ring's own stamp)."""
+    w = wl.ring_oscillator_array(C3_RINGS, C3_STAGES)
+    rng = np.random.default_rng(5)
+    x = w["x"].copy()
+    x[:C3_RINGS * C3_STAGES] += rng.normal(0.0, 0.05, C3_RINGS * C3_STAGES)      # off the rails: every region of the model
+    eng = wl.build_engine(w)
+    got = eng.load_host(x, solver_state(**FLAGS))
+    rp, ci = w["rowptr"], w["colind"]
+    S = C3_STAGES
+    for r in C3_SAMPLE:
+        w1, ref = _single_ring_oracle(w, r)
+        ref.set_flags(**FLAGS)
+        x1 = np.concatenate([x[r * S:(r + 1) * S], [x[w["vdd"]], x[w["branch"]]]])
+        want = ref.load(x1)
+        rows = slice(r * S, (r + 1) * S)
+        for k in ("f", "q", "dFdxdVp", "dQdxdVp"):
+            scale = 1e-3 * np.max(np.abs(want[k][:S])) if np.any(want[k][:S]) else 1e-300
+            assert rel_err(got[k][rows], want[k][:S], scale) < 1e-12, (k, r)
+        for k in ("dFdx", "dQdx"):
+            scale = 1e-3 * np.max(np.abs(want[k]))
+            cnt = 0
+            for lr in range(S):
+                gr = r * S + lr
+                have = {}
+                for p in range(rp[gr], rp[gr + 1]):
+                    c = ci[p]
+                    have[c - r * S if c < C3_RINGS * S else S + (c - C3_RINGS * S)] = got[k][p]
+                for p in range(ref.rowptr[lr], ref.rowptr[lr + 1]):
+                    g = have[ref.colind[p]]
+                    assert abs(g - want[k][p]) <= 1e-12 * max(abs(want[k][p]), scale), (k, r, lr)
+                    cnt += 1
+                assert len(have) == ref.rowptr[lr + 1] - ref.rowptr[lr]
+            assert cnt > 3 * S
+    eng.close()
+
+
+def test_c3_tran_every_sampled_ring_follows_the_single_ring_oracle():
+    """The 4 950-ring .TRAN (200 ps) against the oracle at size.  The rings interact only through the ideal supply, so
+    ring r of the array must follow the reference flow (reference BSIM4 objects + Kundert Sparse under the same driver)
+    of that ring alone WHEN BOTH TAKE THE SAME TIME STEPS: the array's accepted steps (size and order) are replayed on
+    the oracle side (the array's own step selection depends on norms over all 499 952 unknowns, which a 103-unknown
+    circuit cannot reproduce).  Checked: Newton iterations per step identical, all 101 node waveforms of 8 rings within
+    RELTOL / ABSTOL at every time point."""
+    w = wl.ring_oscillator_array(C3_RINGS, C3_STAGES)
+    S = C3_STAGES
+    probes = np.concatenate([r * S + np.arange(S) for r in C3_SAMPLE] + [[w["vdd"], w["branch"]]]).astype(np.int32)
+    eng = wl.build_engine(w)
+    got = eng.tran_run(w["x"], 2e-10, 1e-12, probes)
+    eng.close()
+    assert got["rc"] == 0, got.get("error")
+    acc = got["steps"][got["steps"][:, 4] > 0]
+    assert len(acc) == got["stats"]["accepted"] and len(acc) >= 40
+    h, order, iters = acc[:, 1], acc[:, 3].astype(np.int32), acc[:, 2]
+    worst = 0.0
+    for j, r in enumerate(C3_SAMPLE):
+        w1, ref = _single_ring_oracle(w, r)
+        ref.set_flags(transient=1)
+        want = ref.tran_run(w1["x"], 2e-10, 1e-12, np.arange(S), w1["linear"], w1["sources"], replay=(h, order))
+        assert want["rc"] == 0
+        assert len(want["t"]) == len(got["t"]) and np.allclose(want["t"], got["t"], rtol=1e-12, atol=0)
+        assert np.array_equal(want["steps"][:, 2], iters), (r, want["steps"][:, 2], iters)      # Newton iterations per step
+        gw = got["wave"][:, j * S:(j + 1) * S]
+        tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(gw)) + 1e-6
+        assert np.all(np.abs(gw - want["wave"]) <= tol), (r, float(np.max(np.abs(gw - want["wave"]))))
+        worst = max(worst, float(np.max(np.abs(gw - want["wave"]))))
+        assert np.ptp(want["wave"]) > 0.8          # the switching front moves through the ring
+    print("C3 .TRAN: %d accepted steps, %d Newton iterations, worst |dv| vs single-ring oracle %.3e V"
+          % (len(acc), int(iters.sum()), worst))

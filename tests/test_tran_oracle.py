@@ -68,3 +68,23 @@ def test_dc_operating_point_of_the_mixed_netlist():
     # starts from rest: the first accepted point moves the bias nodes only by what the input couples in
     # (SIN source, 12.6 mV after 1 ns, through the 100 pF capacitor into the base)
     assert np.max(np.abs(r["wave"][1, [B, C, E, D]] - x[[B, C, E, D]])) < 1.3e-2
+
+
+@pytest.mark.parametrize("method", [7, 8])
+def test_replaying_a_run_on_its_own_accepted_steps_reproduces_it(method):
+    """TranParams::replay_h / replay_order (verification mode used by the at-size tests): a run replayed on its own
+    accepted steps -- rejected attempts skipped -- takes the same Newton iterations and lands on the same waveform."""
+    w = wl.ring_oscillator_array(1, 11)
+    ref = ref_circuit_from_workload(oracle_ref.RefCircuit, w)
+    ref.set_flags(transient=1)
+    a = ref.tran_run(w["x"], 1.5e-9, 1e-12, [0, 5], w["linear"], w["sources"], method=method)
+    assert a["rc"] == 0 and a["stats"]["rejected"] > 0          # the interesting case: the original run rejected steps
+    acc = a["steps"][a["steps"][:, 4] > 0]
+    ref2 = ref_circuit_from_workload(oracle_ref.RefCircuit, w)
+    ref2.set_flags(transient=1)
+    b = ref2.tran_run(w["x"], 1.5e-9, 1e-12, [0, 5], w["linear"], w["sources"], method=method,
+                      replay=(acc[:, 1], acc[:, 3].astype(np.int32)))
+    assert b["rc"] == 0 and b["stats"]["rejected"] == 0
+    assert np.allclose(b["t"], a["t"], rtol=1e-13, atol=0)
+    assert np.array_equal(b["steps"][:, 2], acc[:, 2])
+    assert np.allclose(b["wave"], a["wave"], rtol=1e-9, atol=1e-12)

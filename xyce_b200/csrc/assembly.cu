@@ -98,7 +98,12 @@ __device__ __forceinline__ void chunk_body(const GatherMapDev &m, const PlaneSet
     }
     __syncthreads();
   }
-  if (threadIdx.x < NP) m.partials[(size_t)threadIdx.x * m.nchunks + c] = sh[threadIdx.x][0];
+  // thread 0 publishes ALL NP partials itself: its __threadfence() in chunk_then_finish then orders every one of
+  // them before the ticket (stores by other threads would not be covered by that fence)
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) m.partials[(size_t)p * m.nchunks + c] = sh[p][0];
+  }
 }
 
 // ---- one-launch assembly -------------------------------------------------------------------------------

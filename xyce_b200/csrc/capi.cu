@@ -297,7 +297,8 @@ int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const
     XB_B4_SIZE_D(GET)
 #undef GET
   }
-  for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
+  // only the two record tables are replaced; device groups (BSIM4 and small-device) keep their buffers
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes);
   ctx->d_models = nullptr; ctx->d_sizes = nullptr;
   XG_CUDA(upload(&ctx->d_models, M.data(), M.size()));

@@ -73,6 +73,12 @@ struct TranParams {
   // Newton, DC_OP mode defaults (NLParams constructor)
   int dcMaxNewtonStep = 200;
   double dcDeltaXTol = 1.0, dcAbsTol = 1e-12, dcRelTol = 1e-3, dcRHSTol = 1e-6;
+  // Verification mode (used by the oracle side of the at-size tests): follow a given sequence of accepted steps
+  // -- step size and integration order of each -- instead of the driver's own step-size / order selection and
+  // LTE accept test.  Everything else (coefficients, predictor, Newton solve, history updates) runs unchanged, so
+  // a sub-circuit can be integrated on exactly the time points a larger run chose.  Empty = normal operation.
+  std::vector<double> replay_h;
+  std::vector<int> replay_order;
 };
 
 struct StepRecord { double t, h; int newton_iters, order, status; };
@@ -150,7 +156,15 @@ class TransientDriver {
     B.record(0.0);
     while (!(currentTime >= stopTime - minTimeStep)) {
       if ((int)steps.size() >= P.maxSteps) return 3;
+      if (replay() && replayIdx_ >= P.replay_h.size()) break;
       if (beginningIntegration && stepAttemptStatus) initialize_integrator();
+      if (replay() && !beginningIntegration) {      // the recorded step instead of the one completeStep selected
+        currentTimeStep = P.replay_h[replayIdx_];
+        currentOrder = P.replay_order[replayIdx_];
+        nextTime = currentTime + currentTimeStep;
+        currentTimeStepRatio = currentTimeStep / lastTimeStep;
+        currentTimeStepSum = currentTimeStep + lastTimeStep;
+      }
       update_coeffs();
       // predictor (OneStep::obtainPredictor)
       if (gear()) {       // Gear12::obtainPredictor: sum over i = 0..order of beta_i * history_i
@@ -173,11 +187,12 @@ class TransientDriver {
       const bool testError = ok && stepNumber >= 1 && !beginningIntegration;
       if (testError) {
         estOverTol = ck * B.wrms_norm(vNewtCorr, vErrWt);
-        ok = estOverTol <= P.errTolAcceptance;
+        ok = estOverTol <= P.errTolAcceptance || replay();
       }
       stepAttemptStatus = ok;
       StepRecord rec{nextTime, currentTimeStep, nIterations, currentOrder, status};
       if (ok) {
+        ++replayIdx_;
         complete_step();
         B.copy(vCurrSol, vNextSol);
         B.accept_state();
@@ -204,6 +219,8 @@ class TransientDriver {
   double startingTimeStep, minTimeStep, maxTimeStep;
   double psi[3] = {0, 0, 0}, beta[3] = {1, 0, 0}, alpha[3] = {1, -1, 0}, alphas = -1.0, ck = 1.0, estOverTol = 0.0;
   bool gear() const { return P.method == 8; }
+  bool replay() const { return !P.replay_h.empty(); }
+  size_t replayIdx_ = 0;
   int currentOrder = 1, usedOrder = 1, numberOfSteps = 0, nef = 0, stepNumber = 0, nIterations = 0;
   int newtonConvergenceStatus = 0, iNumCalls = 0;
   bool beginningIntegration = true, stepAttemptStatus = true;
@@ -231,6 +248,7 @@ class TransientDriver {
       else h = 0.1 * std::min(savedTimeStep, std::fabs(time_to_stop));
     }
     if (startingTimeStep > 0.0 && currentTime == initialTime) h = std::min(startingTimeStep, h);
+    if (replay() && replayIdx_ < P.replay_h.size()) h = P.replay_h[replayIdx_];
     if (currentTime != initialTime) currentTimeStep = std::min(currentTimeStep, h);
     else currentTimeStep = h;
     currentTimeStep = std::max(currentTimeStep, minTimeStep);
@@ -311,6 +329,8 @@ class TransientDriver {
     return nn.rhs_norm2;
   }
   NewtonNorms nn;
+  int stagCount_ = 0;
+  double tmpConvRate_ = 0.0;
   const bool trace_ = std::getenv("XB_TRAN_TRACE") != nullptr;     // diagnostics: one line per Newton iteration on stderr
 
   // DampedNewton::solve with FULL search (step length 1); dc = DC_OP mode on NoTimeIntegration
@@ -326,8 +346,9 @@ class TransientDriver {
     double normRHS = residual(fl, dc);
     double normRHS_old = normRHS, normRHS_init = normRHS;
     if (!dc) B.sol_weights(vSolWt, relTol, absTol, vNextSol, vCurrSol);     // updateWeights_ (transient: once per solve)
-    int status = 0, count = 0;
-    double tmpConvRate = 0.0;
+    int status = 0;
+    int &count = stagCount_;            // DampedNewton::count / tmpConvRate are class members (N_NLS_DampedNewton.h:199-203):
+    double &tmpConvRate = tmpConvRate_; // they persist from one solve() to the next
     const double fs = (currentOrder == 2) ? 0.5 : 1.0;
     while (status == 0) {
       ++nlStep;
@@ -363,17 +384,18 @@ class TransientDriver {
       if (trace_) std::fprintf(stderr, "NEWTON t=%.9e it=%d ||rhs||2=%.17g ||rhs||inf=%.17g ||dx||w=%.17g devconv=%d\n", nextTime,
                                nlStep, normRHS, maxNormRHS, updateSize, (int)nn.devices_converged);
       if (maxNormRHS <= RHSTol && updateSize <= deltaXTol) { status = 2; break; }
-      if (nlStep >= maxNewtonStep && normRHS_rel <= 0.9 && resConvRate <= 1.0) { status = 3; break; }
+      // "near converged" and the stagnation test exist in TRANSIENT mode only (N_NLS_DampedNewton.C:1316-1323, :1341-1358)
+      if (!dc && nlStep >= maxNewtonStep && normRHS_rel <= 0.9 && resConvRate <= 1.0) { status = 3; break; }
       if (updateSize <= P.smallUpdateTol) { status = 4; break; }
       if (nlStep >= maxNewtonStep) { status = -1; break; }
       if (resConvRate > 0.5 * 1.7976931348623157e308) { status = -2; break; }
-      if (std::fabs(resConvRate - 1.0) <= 1.0e-3) {
+      if (!dc && std::fabs(resConvRate - 1.0) <= 1.0e-3) {
         if (count == 0 || resConvRate < tmpConvRate) tmpConvRate = resConvRate;
         ++count;
       } else {
         count = 0;
       }
-      if (count == 5) {
+      if (!dc && count == 5) {
         count = 0;
         status = (normRHS_rel < 0.9 && tmpConvRate <= 1.0) ? 3 : -3;
         break;
@@ -424,6 +446,7 @@ class TransientDriver {
     }
     if (rr >= r_hincr_test) { rr = r_hincr; newTimeStep = rr * currentTimeStep; }
     else if (rr <= 1) { rr = std::max(r_min, std::min(r_max, rr)); newTimeStep = rr * currentTimeStep; }
+    if (replay() && replayIdx_ < P.replay_order.size()) currentOrder = P.replay_order[replayIdx_];
     update_history();     // with the order selected for the NEXT step, as the reference does (:2228)
     newTimeStep = std::max(newTimeStep, minTimeStep);
     newTimeStep = std::min(newTimeStep, maxTimeStep);
