@@ -174,6 +174,13 @@ int xgpu_lu_info(const xgpu_ctx *ctx, double *info8);
  * xgpu_lu_analyze runs on the host, exposed so that CPU-only CI can test it. */
 int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colind, const double *vals,
                               const double *rhs, double *x, double *info8);
+/* Diagonal blocks with one common symbolic pattern (every ring of a ring array, every cell of a cell array) are
+ * refactored and solved as a BATCH: one thread per block, factor values interleaved across blocks, the pattern compiled
+ * on the host into a straight-line program shared by all blocks (lu.h).  Host-only self check of those programs:
+ * analyze on vals0, run the programs on vals1, compare with a plain left-looking refactorization / substitution.
+ * out4 = {groups, batched blocks, largest relative deviation of the factors, of the block solves}. */
+int xgpu_lu_host_batch_selfcheck(int n, const int32_t *rowptr, const int32_t *colind, const double *vals0,
+                                 const double *vals1, double *out4);
 
 /* ---- linear devices, sources, Newton + transient loop (callers of the hot path) ----
  * xgpu_linear_set: constant conductance (G) and capacitance (C) stamps of the linear devices as COO
@@ -215,6 +222,15 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
  * matrices nnz entries; next/curr store and state live in the context between calls. */
 int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double *h_f, double *h_q,
                    double *h_dFdxdVp, double *h_dQdxdVp, double *h_dFdx, double *h_dQdx);
+/* The same pass returning only what a host-side Newton solver consumes (4 MB instead of 9.6 MB of PCIe traffic on
+ * BASELINE config 2): the combined Jacobian  J = qscalar dQdx + fscalar dFdx  (OneStep::obtainJacobian,
+ * N_TIA_OneStep.C:490-495: qscalar = -alphas/h, fscalar = 1 or 1/2; Gear12: a0/h, 1) and the device part of the residual
+ *   r = -(qscalar Q + fscalar F) + qscalar dQdxdVp + fscalar dFdxdVp        (limiter terms when ss->voltageLimiterFlag)
+ * to which the caller adds the terms that live in its own history vectors (OneStep::obtainResidual :223-272:
+ * + qscalar qHistory[0] + fscalar B (- 1/2 qHistory[2] at order 2)).  h_rhs: n entries, h_jac: nnz entries.  With option
+ * "zero_copy_out" = 1 and pinned, mapped buffers the kernel stores straight into host memory. */
+int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double qscalar, double fscalar,
+                      double *h_rhs, double *h_jac);
 /* which: 0 next store, 1 curr store, 2 next state, 3 curr state */
 int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h_vals);
 int xgpu_state_get(xgpu_ctx *ctx, int which, double *h_vals);

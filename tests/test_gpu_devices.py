@@ -222,3 +222,26 @@ def test_rlc_plugin_equals_discrete_and_analytic():
     # LTE control uses point-global weights (reltol * max|x| with max|x| = 10 V), so the small branch current is
     # only held to a few per cent of its amplitude
     assert np.max(np.abs(i_gpu - sol.y[0])) < 5e-2 * np.max(np.abs(sol.y[0])) + 1e-9
+
+
+def test_models_set_keeps_small_device_groups_and_can_be_repeated():
+    """xgpu_b4_models_set replaces the BSIM4 record tables only: a diode group added BEFORE it stays valid (round 1 freed
+    its buffers there), and setting the models a second time is legal."""
+    from xyce_b200 import workloads as wl
+    ref = diode_circuit(oracle_ref.RefCircuit, "rs_bv", n_dev=40, seed=5)
+    ex = [ref.diode_export(i) for i in range(ref.n_inst)]
+    rec = wl.load_b4_records()
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(1, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1)
+    eng.b4_set_models(rec["model_d"], rec["model_i"], rec["size_d"])      # after the small-device group
+    eng.b4_set_models(rec["model_d"], rec["model_i"], rec["size_d"])      # and once more
+    eng.finalize()
+    eng.b4_set_models(rec["model_d"], rec["model_i"], rec["size_d"])      # re-set after finalize
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-9.0, 1.2, ref.n)
+    x[1::2] = rng.uniform(-0.3, 0.3, len(x[1::2]))
+    check(ref, eng, CASES["tran1"], x, rng.normal(0.3, 0.4, ref.n_sto), rng.normal(0.3, 0.4, ref.n_sto))
+    eng.close()

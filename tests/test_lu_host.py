@@ -95,3 +95,41 @@ def test_structurally_singular_is_reported():
     A = sp.csr_matrix(([1.0, 1.0, 1.0, 1.0], ([0, 0, 1, 1], [0, 1, 0, 1])), shape=(3, 3))
     rc, _, _ = host_solve(A, np.ones(3))
     assert rc == 1
+
+
+def batch_selfcheck(A0, A1):
+    lib = xyce_b200.load_library()
+    A0 = sp.csr_matrix(A0); A0.sort_indices()
+    A1 = sp.csr_matrix(A1); A1.sort_indices()
+    rp, ci = A0.indptr.astype(np.int32), A0.indices.astype(np.int32)
+    out = np.zeros(4)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    rc = lib.xgpu_lu_host_batch_selfcheck(A0.shape[0], ip(rp), ip(ci), dp(A0.data.astype(np.float64)), dp(A1.data.astype(np.float64)), dp(out))
+    return rc, out
+
+
+@pytest.mark.parametrize("n_rings,stages", [(16, 5), (40, 11), (64, 101), (20, 300)])
+def test_equal_pattern_blocks_are_batched_and_their_programs_are_right(n_rings, stages):
+    """Every ring of a ring array has the same symbolic pattern: one batched group holds them all, and its bundle
+    programs (refactor and solve, executed here on the host exactly as a GPU lane does) reproduce a plain
+    left-looking refactorization and the triangular solves of each block bit for bit: the bundles only regroup
+    independent operations, every factor entry still sees its updates in left-looking order."""
+    A0 = ring_array_matrix(n_rings, stages, seed=1)
+    A1 = A0.copy()
+    A1.data = A1.data * np.random.default_rng(2).uniform(0.8, 1.25, A1.nnz)
+    rc, out = batch_selfcheck(A0, A1)
+    assert rc == 0
+    assert out[0] == 1 and out[1] == n_rings, out
+    assert out[2] == 0.0 and out[3] == 0.0, out
+
+
+def test_few_or_unequal_blocks_are_not_batched():
+    A0 = ring_array_matrix(6, 11, seed=1)          # fewer than kBatchMinBlocks equal blocks
+    rc, out = batch_selfcheck(A0, A0)
+    assert rc == 0 and out[0] == 0 and out[1] == 0
+    rng = np.random.default_rng(0)                 # one irreducible random block
+    n = 300
+    A = sp.csr_matrix(sp.random(n, n, density=0.02, random_state=1, format="csr") + sp.diags(rng.uniform(1, 2, n)))
+    rc, out = batch_selfcheck(A, A)
+    assert rc == 0 and out[0] == 0

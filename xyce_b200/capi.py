@@ -202,6 +202,13 @@ class Engine:
                                           _dp(out["dFdxdVp"]), _dp(out["dQdxdVp"]), _dp(out["dFdx"]), _dp(out["dQdx"])))
         return out
 
+    def load_host_jr(self, x, ss, qscalar, fscalar):
+        """Host-buffer path for a host-side Newton solver: J = qscalar dQdx + fscalar dFdx and the device part of the residual."""
+        x = _f64(x)
+        rhs, jac = np.zeros(self.n), np.zeros(self.nnz)
+        self._chk(self.lib.xgpu_load_host_jr(self.h, _dp(x), C.byref(ss), C.c_double(qscalar), C.c_double(fscalar), _dp(rhs), _dp(jac)))
+        return rhs, jac
+
     def device_buffer(self, which):
         return self.lib.xgpu_device_buffer(self.h, which)
 
@@ -294,8 +301,9 @@ class Engine:
         return out
 
     def lu_refactor(self, d_vals):
+        """0 ok, 2 zero / non-finite pivot, 3 a pivot of the fixed sequence fails KLU's threshold test (re-analyse)"""
         rc = self.lib.xgpu_lu_refactor(self.h, C.c_void_p(d_vals))
-        if rc not in (0, 2):
+        if rc not in (0, 2, 3):
             self._chk(rc)
         return rc
 

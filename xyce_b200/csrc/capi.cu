@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "pdl.cuh"
 #include "vecops.cuh"
 
 using namespace xb;
@@ -176,6 +177,17 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
   if (n == "b4_spec" && (value == 0 || value == 1)) { ctx->b4_spec = value; return 0; }
   if (n == "lu_graphs" && (value == 0 || value == 1)) { ctx->lu_graphs = value; return 0; }
+  // "lu_pivot_check": 1 (default) = the refactorization tests every pivot of the fixed sequence against KLU's threshold
+  // (|pivot| >= 0.001 max |column|) and reports code 3 when one fails; "lu_repivot": 1 = KLU_REPIVOT=1 semantics, every
+  // xgpu_lu_refactor re-runs the pivoting host factorization (the reference's default, N_LAS_AmesosSolver.C:316-318)
+  if (n == "lu_pivot_check" && (value == 0 || value == 1)) {
+    ctx->lu_dev.pivot_check = value;
+    // captured refactor graphs carry the old value in their kernel parameters: drop them
+    for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) { if (g->exec) cudaGraphExecDestroy(g->exec); *g = xgpu_ctx::LuGraph(); }
+    return 0;
+  }
+  if (n == "lu_batch" && (value == 0 || value == 1)) { ctx->lu_batch = value; return 0; }      // takes effect at the next analysis / import
+  if (n == "lu_repivot" && (value == 0 || value == 1)) { ctx->lu_repivot = value; return 0; }
   if (n == "zero_copy_out" && (value == 0 || value == 1)) { ctx->zero_copy_out = value; return 0; }
   return fail(ctx, 16, "unknown option or value out of range: " + n);
 }
@@ -724,6 +736,55 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
 
 extern "C++" {
 namespace {
+// J = qs dQdx + fs dFdx over the nnz entries and r = -(qs Q + fs F) (+ qs dQdxdVp + fs dFdxdVp) over the n rows, one launch.
+// The outputs may be device buffers or pinned, mapped host memory (zero-copy: the stores travel over PCIe while the
+// kernel runs, no separate copy).
+__global__ void __launch_bounds__(256) jr_kernel(long long nnz, int n, double qs, double fs, const double *__restrict__ dQdx,
+                                                 const double *__restrict__ dFdx, const double *__restrict__ F,
+                                                 const double *__restrict__ Q, const double *__restrict__ Fl,
+                                                 const double *__restrict__ Ql, int limiter, double *__restrict__ J,
+                                                 double *__restrict__ r) {
+  xb::pdl_wait();
+  const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (k < nnz) J[k] = qs * dQdx[k] + fs * dFdx[k];
+  if (k < n) {
+    double v = -(qs * Q[k] + fs * F[k]);
+    if (limiter) v += qs * Ql[k] + fs * Fl[k];
+    r[k] = v;
+  }
+}
+}  // namespace
+}  // extern "C++"
+
+int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double qscalar, double fscalar,
+                      double *h_rhs, double *h_jac) {
+  if (!ctx || !h_sol || !ss || !h_rhs || !h_jac) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  double **b = ctx->buf;
+  XG_CUDA(cudaMemcpyAsync(b[0], h_sol, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = xgpu_load_dae(ctx, b[0], b[9], b[10], b[7], b[8], ss, b[1], b[2], b[3], b[4], b[5], b[6], 0);
+  if (rc) return rc;
+  double *dj = nullptr, *dr = nullptr;
+  bool mapped = ctx->zero_copy_out != 0;
+  if (mapped && (cudaHostGetDevicePointer((void **)&dj, h_jac, 0) != cudaSuccess ||
+                 cudaHostGetDevicePointer((void **)&dr, h_rhs, 0) != cudaSuccess)) { cudaGetLastError(); mapped = false; }
+  if (!mapped) { dj = b[5]; dr = b[1]; }      // in place: J over dFdx, r over F (element-wise, same index)
+  const long long m = std::max<long long>(ctx->nnz, ctx->n);
+  xb::launch_pdl(jr_kernel, dim3((unsigned)((m + 255) / 256)), dim3(256), 0, ctx->stream, (long long)ctx->nnz, ctx->n, qscalar,
+                 fscalar, (const double *)b[6], (const double *)b[5], (const double *)b[1], (const double *)b[2],
+                 (const double *)b[3], (const double *)b[4], ss->voltageLimiterFlag, dj, dr);
+  ++ctx->launches;
+  if (!mapped) {
+    XG_CUDA(cudaMemcpyAsync(h_rhs, dr, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaMemcpyAsync(h_jac, dj, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C++" {
+namespace {
 void lu_drop_graphs(xgpu_ctx *ctx) {
   for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) {
     if (g->exec) cudaGraphExecDestroy(g->exec);
@@ -780,6 +841,7 @@ int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
   std::vector<double> vals((size_t)ctx->nnz);
   XG_CUDA(cudaMemcpyAsync(vals.data(), d_vals, vals.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  xb::lu::set_batching(ctx->lu_batch != 0);
   const int rc = xb::lu::analyze_and_factor(ctx->n, ctx->rowptr.data(), ctx->colind.data(), vals.data(), 0.001, ctx->lu_plan);
   if (rc == 1) return fail(ctx, 1, "matrix is structurally singular");
   lu_drop_graphs(ctx);
@@ -795,6 +857,7 @@ int xgpu_lu_import(xgpu_ctx *ctx, const int32_t *row_perm, const int32_t *col_pe
   if (ctx->rowptr.empty()) return fail(ctx, 112, "no CSR pattern");
   XG_CUDA(cudaSetDevice(ctx->device));
   const char *why = "";
+  xb::lu::set_batching(ctx->lu_batch != 0);
   const int rc = xb::lu::import_factorization(ctx->n, ctx->rowptr.data(), ctx->colind.data(), row_perm, col_perm, nblocks,
                                               block_ptr, Lp, Li, Up, Ui, row_scale, ctx->lu_plan, &why);
   if (rc) { ctx->lu_ready = false; return fail(ctx, 3, std::string("xgpu_lu_import: ") + why); }
@@ -824,7 +887,8 @@ int xgpu_lu_export(xgpu_ctx *ctx, int32_t *row_perm, int32_t *col_perm, int32_t 
   if (Li) std::copy(p.Li.begin(), p.Li.end(), Li);
   if (Up) std::copy(p.Up.begin(), p.Up.end(), Up);
   if (Ui) std::copy(p.Ui.begin(), p.Ui.end(), Ui);
-  // numeric values of the latest factorization on the device
+  // numeric values of the latest factorization on the device (batched groups keep theirs interleaved: copy them over)
+  if ((Lx || Ux) && !ctx->lu_dev.batch.empty()) ctx->launches += xb::lu::launch_batch_export(ctx->lu_dev, ctx->stream);
   if (Lx && !p.Li.empty()) XG_CUDA(cudaMemcpyAsync(Lx, ctx->lu_dev.Lx, p.Li.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (Ux && !p.Ui.empty()) XG_CUDA(cudaMemcpyAsync(Ux, ctx->lu_dev.Ux, p.Ui.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -834,6 +898,7 @@ int xgpu_lu_export(xgpu_ctx *ctx, int32_t *row_perm, int32_t *col_perm, int32_t 
 int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
   if (!ctx || !d_vals) return 100;
   if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
+  if (ctx->lu_repivot) return xgpu_lu_analyze(ctx, d_vals);      // KLU_REPIVOT=1: pivoting factorization every time
   {
     const int rc = lu_run(ctx, ctx->g_refactor, d_vals, nullptr, nullptr,
                           [&] { return xb::lu::launch_refactor(ctx->lu_dev, d_vals, ctx->stream); });
@@ -842,7 +907,8 @@ int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
   int status = 0;
   XG_CUDA(cudaMemcpyAsync(&status, ctx->lu_dev.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (status) return fail(ctx, 2, "zero or non-finite pivot during refactorization");
+  if (status & 1) return fail(ctx, 2, "zero or non-finite pivot during refactorization");
+  if (status & 4) return fail(ctx, 3, "a pivot of the fixed sequence fails the partial-pivoting threshold: re-analyse (re-pivot)");
   return 0;
 }
 
@@ -867,6 +933,16 @@ int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colin
     info[4] = (double)p.Ui.size(); info[5] = (double)p.off_row.size(); info[6] = (double)p.level_ptr.size() - 1;
     info[7] = p.refactor_flops;
   }
+  return rc;
+}
+
+int xgpu_lu_host_batch_selfcheck(int n, const int32_t *rowptr, const int32_t *colind, const double *vals0, const double *vals1,
+                                 double *out4) {
+  if (n <= 0 || !rowptr || !colind || !vals0 || !vals1 || !out4) return 100;
+  xb::lu::LuPlan p;
+  const int rc = xb::lu::analyze_and_factor(n, rowptr, colind, vals0, 0.001, p);
+  if (rc == 1) return 1;
+  xb::lu::batch_selfcheck_host(p, vals1, out4);
   return rc;
 }
 

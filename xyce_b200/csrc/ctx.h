@@ -101,6 +101,8 @@ struct xgpu_ctx {
   struct LuGraph { cudaGraphExec_t exec = nullptr; const void *k0 = nullptr, *k1 = nullptr, *k2 = nullptr; int launches = 0; };
   LuGraph g_refactor, g_solve;
   int lu_graphs = 1;          // option "lu_graphs": 0 = plain stream launches
+  int lu_batch = 1;           // option "lu_batch": 0 = no batched groups (every block on the warp-per-block kernels)
+  int lu_repivot = 0;         // option "lu_repivot": 1 = every refactorization re-pivots on the host (KLU_REPIVOT=1)
   int zero_copy_out = 0;      // option "zero_copy_out" = 1: xgpu_load_host lets the assembly kernel write pinned, mapped host outputs directly
                               // (measured +2.6 % on the C2 host-buffer path; off by default: DMA copies behave predictably with many ranks)
   // work space of xgpu_tran_run, kept between runs (driver-level allocation and pinned-memory calls cost

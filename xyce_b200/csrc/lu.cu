@@ -37,11 +37,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d
       double p = 0.0;
       for (int q = d.acol_ptr[k0]; q < d.acol_ptr[k0 + 1]; ++q) p += A[d.acol_src[q]];
       d.Ux[d.Up[k0 + 1] - 1] = p;
-      if (bad_pivot(p)) *d.status = 1;
+      if (bad_pivot(p)) atomicOr(d.status, 1);
     }
     return;
   }
   double *x = (nb <= kSmemRows) ? (&sx[warp][0] - k0) : d.work;   // x[k0..k1) addressed by position
+  bool weak = false;
   for (int k = k0; k < k1; ++k) {
     const int ub = d.Up[k], ue = d.Up[k + 1] - 1;       // off-diagonal U entries [ub, ue), pivot at ue
     const int lb = d.Lp[k], le = d.Lp[k + 1];
@@ -63,11 +64,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d
     const double pivot = x[k];
     if (lane == 0) {
       d.Ux[ue] = pivot;
-      if (bad_pivot(pivot)) *d.status = 1;
+      if (bad_pivot(pivot)) atomicOr(d.status, 1);
     }
-    for (int q = lb + lane; q < le; q += 32) d.Lx[q] = x[d.Li[q]] / pivot;
+    for (int q = lb + lane; q < le; q += 32) {
+      const double c = x[d.Li[q]];
+      if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) weak = true;
+      d.Lx[q] = c / pivot;
+    }
     __syncwarp();
   }
+  if (weak) atomicOr(d.status, 4);
 }
 
 __global__ void __launch_bounds__(256) lu_permute_rhs_kernel(LuView d, const double *__restrict__ rhs) {
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(1024) lu_refactor_staged_kernel(LuView d, cons
     if (dst >= 0) v.Ux[dst - v.u0] = val; else v.Lx[~dst - v.l0] = val;
   }
   __syncwarp();
-  bool bad = false;
+  bool bad = false, weak = false;
   for (int k = 0; k < v.nb; ++k) {
     const int ub = v.Up[k], ue = v.Up[k + 1] - 1, lb = v.Lp[k], le = v.Lp[k + 1];
     // dense column from the slots
@@ -233,10 +239,15 @@ __global__ void __launch_bounds__(1024) lu_refactor_staged_kernel(LuView d, cons
     const double pivot = v.x[k];
     if (bad_pivot(pivot)) bad = true;
     if (lane == 0) v.Ux[ue] = pivot;
-    for (int q = lb + lane; q < le; q += 32) v.Lx[q] = v.x[v.Li[q]] / pivot;
+    for (int q = lb + lane; q < le; q += 32) {
+      const double c = v.x[v.Li[q]];
+      if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) weak = true;
+      v.Lx[q] = c / pivot;
+    }
     __syncwarp();
   }
-  if (bad && lane == 0) *d.status = 1;
+  if (bad && lane == 0) atomicOr(d.status, 1);
+  if (weak) atomicOr(d.status, 4);
   for (int i = lane; i < v.nl; i += 32) d.Lx[v.l0 + i] = v.Lx[i];
   for (int i = lane; i < v.nu; i += 32) d.Ux[v.u0 + i] = v.Ux[i];
 }
@@ -266,6 +277,119 @@ __global__ void __launch_bounds__(1024) lu_solve_staged_kernel(LuView d, int fir
     __syncwarp();
   }
   for (int i = lane; i < v.nb; i += 32) { const double yi = v.x[i]; d.work[v.k0 + i] = yi; xout[d.col_perm[v.k0 + i]] = yi; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched groups (block_big == 3, lu.h): one THREAD per block, `LB` blocks per one-warp CTA (lanes >= LB idle: the
+// work is a latency chain, not a throughput problem, so a narrow CTA that leaves room for more CTAs per SM wins).
+// The CTA keeps the factor values of its blocks in shared memory, slot-major ([slot][lane], conflict-free); every
+// lane owns its column, so there is no synchronisation inside the kernel.  The program (bundles of kBundle
+// {dst | type << 14, a, b} triples, the same for every block of the group) is read through uniform loads.
+// ---------------------------------------------------------------------------------------------
+struct BundleWords { unsigned short w[kBundle * 3]; };
+__device__ __forceinline__ BundleWords load_bundle(const unsigned short *__restrict__ prog, int bi) {
+  BundleWords r;
+  const uint2 *p = reinterpret_cast<const uint2 *>(prog + (size_t)bi * kBundle * 3);     // 24 bytes, 8-byte aligned
+  static_assert(kBundle * 3 * sizeof(unsigned short) == 24, "bundle = 3 x 8 bytes");
+  const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  const unsigned v[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { r.w[2 * k] = (unsigned short)(v[k] & 0xffffu); r.w[2 * k + 1] = (unsigned short)(v[k] >> 16); }
+  return r;
+}
+
+__global__ void __launch_bounds__(32) lu_refactor_batched_kernel(LuBatchDev g, const double *__restrict__ A, int LB, double tol,
+                                                                 int check, int *status) {
+  xb::pdl_wait();
+  extern __shared__ double bsm[];                 // [nu + nl][LB]
+  const int lane = threadIdx.x;
+  if (lane >= LB) return;
+  const int j = blockIdx.x * LB + lane;
+  const bool live = j < g.nblk;
+  const int jj = live ? j : g.nblk - 1;           // padding lanes redo the last block and store nothing
+  const int ns = g.nu + g.nl;
+  double *v = bsm + lane;
+  for (int s = 0; s < ns; ++s) v[s * LB] = 0.0;
+  // A -> factor slots; the index loads are coalesced (block fastest), the gathers land in neighbouring CSR rows
+  for (int e = 0; e < g.na; ++e) v[__ldg(g.a_dst + e) * LB] = A[__ldg(g.a_src + (size_t)e * g.nblk + jj)];
+  int flag = 0;
+  BundleWords nxt = load_bundle(g.rf_prog, 0);
+  for (int bi = 0; bi < g.rf_bundles; ++bi) {
+    const BundleWords cur = nxt;
+    if (bi + 1 < g.rf_bundles) nxt = load_bundle(g.rf_prog, bi + 1);
+    double d[kBundle], x[kBundle], y[kBundle];
+    int ty[kBundle], ds[kBundle];
+#pragma unroll
+    for (int k = 0; k < kBundle; ++k) {
+      ty[k] = cur.w[3 * k] >> 14; ds[k] = cur.w[3 * k] & 0x3fff;
+      d[k] = v[ds[k] * LB]; x[k] = v[cur.w[3 * k + 1] * LB]; y[k] = v[cur.w[3 * k + 2] * LB];
+    }
+#pragma unroll
+    for (int k = 0; k < kBundle; ++k) {
+      if (ty[k] == kOpFnma) v[ds[k] * LB] = d[k] - x[k] * y[k];
+      else if (ty[k] == kOpDiv) {
+        if (check && fabs(x[k]) < tol * fabs(d[k])) flag |= 4;      // the fixed pivot no longer passes KLU's threshold test
+        v[ds[k] * LB] = d[k] / x[k];
+      } else if (ty[k] == kOpChk) {
+        if (bad_pivot(x[k])) flag |= 1;
+      }
+    }
+  }
+  if (live) {
+    for (int s = 0; s < ns; ++s) g.LUx[(size_t)s * g.nblk + j] = v[s * LB];
+    if (flag) atomicOr(status, flag);
+  }
+}
+
+__global__ void __launch_bounds__(32) lu_solve_batched_kernel(LuBatchDev g, LuView d, int LB, double *__restrict__ xout) {
+  xb::pdl_wait();
+  extern __shared__ double bsm[];                 // factor [nu + nl][LB], then y [nb][LB]
+  const int lane = threadIdx.x;
+  if (lane >= LB) return;
+  const int j = blockIdx.x * LB + lane;
+  const bool live = j < g.nblk;
+  const int jj = live ? j : g.nblk - 1;
+  const int ns = g.nu + g.nl;
+  double *v = bsm + lane, *y = bsm + (size_t)ns * LB + lane;
+  const int k0 = __ldg(g.k0 + jj);
+  // factor values: asynchronous 8-byte copies straight into shared memory (all in flight at once)
+  {
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(v);
+    const double *src = g.LUx + jj;
+    for (int s = 0; s < ns; ++s)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (unsigned)(s * LB * 8)), "l"(src + (size_t)s * g.nblk) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = 0; i < g.nb; ++i) y[i * LB] = d.work[k0 + i];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  BundleWords nxt = load_bundle(g.sv_prog, 0);
+  for (int bi = 0; bi < g.sv_bundles; ++bi) {
+    const BundleWords cur = nxt;
+    if (bi + 1 < g.sv_bundles) nxt = load_bundle(g.sv_prog, bi + 1);
+    double dd[kBundle], x[kBundle], yy[kBundle];
+    int ty[kBundle], ds[kBundle];
+#pragma unroll
+    for (int k = 0; k < kBundle; ++k) {
+      ty[k] = cur.w[3 * k] >> 14; ds[k] = cur.w[3 * k] & 0x3fff;
+      dd[k] = y[ds[k] * LB]; x[k] = v[cur.w[3 * k + 1] * LB]; yy[k] = y[cur.w[3 * k + 2] * LB];
+    }
+#pragma unroll
+    for (int k = 0; k < kBundle; ++k) {
+      if (ty[k] == kOpFnma) y[ds[k] * LB] = dd[k] - x[k] * yy[k];
+      else if (ty[k] == kOpDiv) y[ds[k] * LB] = dd[k] / x[k];
+    }
+  }
+  if (live)
+    for (int i = 0; i < g.nb; ++i) { const double yi = y[i * LB]; d.work[k0 + i] = yi; xout[d.col_perm[k0 + i]] = yi; }
+}
+
+// factor values of a batched group -> the ordinary Lx / Ux arrays (export, diagnostics)
+__global__ void __launch_bounds__(256) lu_batch_export_kernel(LuBatchDev g, LuView d) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= g.nblk) return;
+  const int u0 = g.Up0[j], l0 = g.Lp0[j];
+  for (int s = 0; s < g.nu; ++s) d.Ux[u0 + s] = g.LUx[(size_t)s * g.nblk + j];
+  for (int s = 0; s < g.nl; ++s) d.Lx[l0 + s] = g.LUx[(size_t)(g.nu + s) * g.nblk + j];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,8 +429,14 @@ __global__ void __launch_bounds__(256) lu_big_cols_kernel(LuView d, const double
     __syncwarp();
   }
   const double pivot = d.Ux[ue];
-  if (lane == 0 && bad_pivot(pivot)) *d.status = 1;
-  for (int q = lb + lane; q < le; q += 32) d.Lx[q] = d.Lx[q] / pivot;
+  if (lane == 0 && bad_pivot(pivot)) atomicOr(d.status, 1);
+  bool weak = false;
+  for (int q = lb + lane; q < le; q += 32) {
+    const double c = d.Lx[q];
+    if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) weak = true;
+    d.Lx[q] = c / pivot;
+  }
+  if (weak) atomicOr(d.status, 4);
 }
 
 // Dense columns (supply rails): x = L^-1 A(:,k) over the whole block by the forward row stages, then gathered.
@@ -320,9 +450,13 @@ __global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuView d, int k) {
   const int ub = d.Up[k], ue = d.Up[k + 1] - 1, lb = d.Lp[k], le = d.Lp[k + 1];
   const double pivot = d.work2[k];
   const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t == 0) { d.Ux[ue] = pivot; if (bad_pivot(pivot)) *d.status = 1; }
+  if (t == 0) { d.Ux[ue] = pivot; if (bad_pivot(pivot)) atomicOr(d.status, 1); }
   if (t < ue - ub) d.Ux[ub + t] = d.work2[d.Ui[ub + t]];
-  if (t < le - lb) d.Lx[lb + t] = d.work2[d.Li[lb + t]] / pivot;
+  if (t < le - lb) {
+    const double c = d.work2[d.Li[lb + t]];
+    if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) atomicOr(d.status, 4);
+    d.Lx[lb + t] = c / pivot;
+  }
 }
 
 // One stage of a row-form triangular sweep: vec[r] -= sum_{col < col_limit} L(r, col) vec[col].
@@ -401,7 +535,13 @@ void free_plan(LuDev &d) {
   cudaFree(d.Lr_src); cudaFree(d.Ur_ptr); cudaFree(d.Ur_col); cudaFree(d.Ur_src); cudaFree(d.fs_short_rows); cudaFree(d.fs_long_rows);
   cudaFree(d.bs_short_rows); cudaFree(d.bs_long_rows);
   cudaFree(d.row_scale); cudaFree(d.As); cudaFree(d.nz_rowpos);
+  for (LuBatchDev &g : d.batch) {
+    cudaFree(g.k0); cudaFree(g.a_dst); cudaFree(g.a_src); cudaFree(g.rf_prog); cudaFree(g.sv_prog); cudaFree(g.LUx);
+    cudaFree(g.Up0); cudaFree(g.Lp0);
+  }
+  const double tol = d.pivot_tol; const int chk = d.pivot_check;
   d = LuDev();
+  d.pivot_tol = tol; d.pivot_check = chk;      // options survive a new analysis
 }
 
 cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
@@ -457,6 +597,55 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
     if ((e = cudaFuncSetAttribute(lu_refactor_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lu_solve_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
   }
+  // batched groups: device copies, CTA width (blocks per one-warp CTA): the narrowest of 8 / 16 / 32 whose grid still
+  // fits the SMs in one wave (more CTAs per SM = more latency chains in flight per SM)
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t max_rf = 0, max_sv = 0;
+    for (const LuPlan::BatchGroup &pg : p.batch) {
+      LuBatchDev g;
+      g.nblk = (int)pg.blocks.size(); g.nb = pg.nb; g.nu = pg.nu; g.nl = pg.nl; g.na = pg.na; g.level = pg.level;
+      g.rf_bundles = pg.rf_bundles; g.sv_bundles = pg.sv_bundles;
+      std::vector<int> k0(g.nblk), up0(g.nblk), lp0(g.nblk);
+      for (int j = 0; j < g.nblk; ++j) { k0[j] = p.block_ptr[pg.blocks[j]]; up0[j] = p.Up[k0[j]]; lp0[j] = p.Lp[k0[j]]; }
+      if ((e = up(&g.k0, k0)) != cudaSuccess) return e;
+      if ((e = up(&g.Up0, up0)) != cudaSuccess) return e;
+      if ((e = up(&g.Lp0, lp0)) != cudaSuccess) return e;
+      if ((e = up(&g.a_dst, pg.a_dst)) != cudaSuccess) return e;
+      if ((e = up(&g.a_src, pg.a_src)) != cudaSuccess) return e;
+      if ((e = up(&g.rf_prog, pg.rf_prog)) != cudaSuccess) return e;
+      if ((e = up(&g.sv_prog, pg.sv_prog)) != cudaSuccess) return e;
+      {   // values of the first (pivoting, host) factorization, interleaved -- a solve may follow the analysis directly
+        std::vector<double> lux((size_t)(g.nu + g.nl) * g.nblk, 0.0);
+        if (p.Ux.size() == p.Ui.size() && p.Lx.size() == p.Li.size())
+          for (int j = 0; j < g.nblk; ++j) {
+            for (int sl = 0; sl < g.nu; ++sl) lux[(size_t)sl * g.nblk + j] = p.Ux[up0[j] + sl];
+            for (int sl = 0; sl < g.nl; ++sl) lux[(size_t)(g.nu + sl) * g.nblk + j] = p.Lx[lp0[j] + sl];
+          }
+        if ((e = up(&g.LUx, lux)) != cudaSuccess) return e;
+      }
+      auto pick = [&](size_t bytes_per_block) {
+        for (int lb : {8, 16, 32}) {
+          const size_t per_cta = bytes_per_block * lb + 1024;
+          if (per_cta > 227 * 1024) break;
+          const long long resident = (long long)sms * std::min<long long>(32, (227 * 1024) / per_cta);
+          if ((g.nblk + lb - 1) / lb <= resident) return lb;
+        }
+        int lb = 32;
+        while (lb > 1 && bytes_per_block * lb + 1024 > 227 * 1024) lb >>= 1;
+        return lb;
+      };
+      g.lanes_rf = pick((size_t)(g.nu + g.nl) * 8);
+      g.lanes_sv = pick((size_t)(g.nu + g.nl + g.nb) * 8);
+      max_rf = std::max(max_rf, (size_t)(g.nu + g.nl) * 8 * g.lanes_rf);
+      max_sv = std::max(max_sv, (size_t)(g.nu + g.nl + g.nb) * 8 * g.lanes_sv);
+      d.batch.push_back(g);
+    }
+    if (max_rf > 48 * 1024 && (e = cudaFuncSetAttribute(lu_refactor_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_rf)) != cudaSuccess) return e;
+    if (max_sv > 48 * 1024 && (e = cudaFuncSetAttribute(lu_solve_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_sv)) != cudaSuccess) return e;
+  }
   if ((e = cudaMalloc((void **)&d.work2, (size_t)(p.n > 0 ? p.n : 1) * sizeof(double))) != cudaSuccess) return e;
   d.pull_short_ptr = p.pull_short_ptr; d.pull_long_ptr = p.pull_long_ptr; d.pull_chunk_ptr = p.pull_chunk_ptr;
   if ((e = cudaMalloc((void **)&d.pull_partials, (p.pull_chunk_begin.size() + 1) * sizeof(double))) != cudaSuccess) return e;
@@ -489,6 +678,12 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
     const int w = d.staged_warps;
     xb::launch_pdl(lu_refactor_staged_kernel, dim3((d.nblocks + w - 1) / w), dim3(32 * w), (size_t)w * d.staged_bytes, s, d, A); ++launches;
   }
+  for (const LuBatchDev &g : d.batch) {
+    const int lb = g.lanes_rf;
+    xb::launch_pdl(lu_refactor_batched_kernel, dim3((g.nblk + lb - 1) / lb), dim3(32), (size_t)(g.nu + g.nl) * 8 * lb, s, g, A, lb,
+                   d.pivot_tol, d.pivot_check, d.status);
+    ++launches;
+  }
   // large blocks: columns level by level; dense columns of a level after its normal columns
   const int nlev = (int)d.rf_level_ptr.size() - 1;
   for (int l = 0; l < nlev; ++l) {
@@ -504,6 +699,12 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
       ++launches;
     }
   }
+  return launches;
+}
+
+int launch_batch_export(const LuDev &d, cudaStream_t s) {
+  int launches = 0;
+  for (const LuBatchDev &g : d.batch) { lu_batch_export_kernel<<<(g.nblk + 255) / 256, 256, 0, s>>>(g, (const LuView &)d); ++launches; }
   return launches;
 }
 
@@ -529,6 +730,13 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
     if (d.staged_bytes > 0) {
       const int w = d.staged_warps;
       xb::launch_pdl(lu_solve_staged_kernel, dim3((count + w - 1) / w), dim3(32 * w), (size_t)w * d.staged_bytes, s, d, first, count, x);
+      ++launches;
+    }
+    for (const LuBatchDev &g : d.batch) {
+      if (g.level != l) continue;
+      const int lb = g.lanes_sv;
+      xb::launch_pdl(lu_solve_batched_kernel, dim3((g.nblk + lb - 1) / lb), dim3(32), (size_t)(g.nu + g.nl + g.nb) * 8 * lb, s, g,
+                     (const LuView &)d, lb, x);
       ++launches;
     }
     for (size_t bi = 0; bi < d.big_blocks.size(); ++bi) {

@@ -63,14 +63,42 @@ struct LuPlan {
   std::vector<int> bs_short_ptr, bs_short_rows, bs_long_ptr, bs_long_rows;   // backward (U) stages
   std::vector<int> big_blocks;                  // ids of the large blocks
   std::vector<int> big_fs_begin, big_fs_end, big_bs_begin, big_bs_end;       // per large block: its stage ranges
+
+  // ---- batched blocks (block_big == 3): diagonal blocks that share ONE symbolic pattern (same size, same L / U
+  // pattern, same positions of the A entries -- every ring of a ring-oscillator array, every cell of a cell array) ----
+  // Such a group is factored and solved with one THREAD per block: the factor values of the group are stored
+  // interleaved, slot-major with the block index fastest (coalesced), the pattern is compiled once on the host into
+  // a straight-line "elimination program" over factor slots that is the same for every block, so a warp executes it
+  // in lock step with uniform operands and no intra-warp synchronisation at all.  Independent operations are packed
+  // into bundles of kBundle (loads of a bundle first, then the arithmetic, then the stores) so that the
+  // shared-memory latency of a column chain is paid once per bundle, not once per operation.
+  struct BatchGroup {
+    int nb = 0, nu = 0, nl = 0, na = 0, level = 0;      // block size, U / L entries, A entries per block, solve level
+    std::vector<int> blocks;                            // block ids
+    std::vector<int> a_dst;                             // [na] factor slot of the e-th A entry (U slots [0, nu), L slots [nu, nu + nl))
+    std::vector<int> a_src;                             // [na][nblk] CSR value index, block fastest
+    std::vector<unsigned short> rf_prog, sv_prog;       // bundles of kBundle ops, op = {dst | type << 14, a, b}
+    int rf_bundles = 0, sv_bundles = 0;
+  };
+  std::vector<BatchGroup> batch;
 };
 constexpr int kBigBlock = 512, kDenseCol = 4096, kLongRow = 2048, kStagedBytes = 12288;
+constexpr int kBundle = 4;                 // operations per bundle of a batched-group program
+constexpr int kBatchMinBlocks = 16;        // fewer equal blocks than this stay on the warp-per-block kernels
+constexpr int kBatchMaxSlots = 3000;       // nu + nl + nb of a batched pattern (8 blocks per CTA must fit shared memory)
+// op types of the batched programs (high 2 bits of the first word)
+//   refactor: 0  v[dst] -= v[a] * v[b]      1  v[dst] = v[dst] / v[a] (+ pivot threshold test)    2  pivot check of v[a]    3 no-op
+//   solve   : 0  y[dst] -= v[a] * y[b]      1  y[dst] = y[dst] / v[a]                                                      3 no-op
+enum BatchOp { kOpFnma = 0, kOpDiv = 1, kOpChk = 2, kOpNop = 3 };
 
 // Symbolic analysis + first numeric factorization with threshold partial pivoting (KLU defaults:
 // pivot_tol = 0.001, diagonal preferred).  Returns 0 ok, 1 structurally singular, 2 numerically singular.
 int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol,
                        LuPlan &plan);
+// batched groups on / off for the plans built from now on (option "lu_batch"; default on)
+void set_batching(bool on);
 void solve_host(const LuPlan &plan, const double *b, double *x);
+void batch_selfcheck_host(const LuPlan &plan, const double *vals, double *out4);
 // Plan from an external factorization's permutations, block boundaries and L / U patterns (lu_host.cpp);
 // numeric values come from the first refactorization on the GPU.  0 ok, 3 malformed input.
 int import_factorization(int n, const int *rowptr, const int *colind, const int *row_perm, const int *col_perm,
@@ -94,7 +122,14 @@ struct LuView {
   double *pull_partials = nullptr;
   double *work = nullptr;         // [n] dense column / solution work vector
   double *work2 = nullptr;        // [n] dense-column work vector of the large-block refactor
-  int *status = nullptr;          // device flag: != 0 when a zero or non-finite pivot was met
+  int *status = nullptr;          // device flags: bit 0 = zero or non-finite pivot, bit 2 = a pivot failed the threshold test
+  // Pivot monitor of the refactorization (fixed pivot sequence): KLU's partial pivoting accepts a pivot only when
+  // |pivot| >= pivot_tol * max |candidate| of its column; a refactorization on an old pivot sequence (klu_refactor,
+  // KLU_REPIVOT=0) never re-tests that.  With pivot_check the kernels do, on the candidates they divide anyway, and
+  // report it (bit 2) so that the caller re-analyses = re-pivots exactly when the reference's default
+  // (KLU_REPIVOT=1: pivoting factorization every time, N_LAS_AmesosSolver.C:316-318) would have chosen differently.
+  double pivot_tol = 0.001;
+  int pivot_check = 1;
   double *row_scale = nullptr, *As = nullptr;   // row scaling (imported plans): factors by position, scaled copy of A's values
   int *nz_rowpos = nullptr; int nnz_a = 0;
   // large blocks (see LuPlan)
@@ -102,7 +137,17 @@ struct LuView {
   int *Lr_ptr = nullptr, *Lr_col = nullptr, *Lr_src = nullptr, *Ur_ptr = nullptr, *Ur_col = nullptr, *Ur_src = nullptr;
   int *fs_short_rows = nullptr, *fs_long_rows = nullptr, *bs_short_rows = nullptr, *bs_long_rows = nullptr;
 };
+struct LuBatchDev {
+  int nblk = 0, nb = 0, nu = 0, nl = 0, na = 0, level = 0, rf_bundles = 0, sv_bundles = 0;
+  int lanes_rf = 32, lanes_sv = 32;      // blocks per CTA (one warp; lanes beyond this idle) chosen at upload
+  int *k0 = nullptr;                     // [nblk] first position of each block
+  int *a_dst = nullptr, *a_src = nullptr;
+  unsigned short *rf_prog = nullptr, *sv_prog = nullptr;
+  double *LUx = nullptr;                 // [nu + nl][nblk] factor values, block fastest
+  int *Up0 = nullptr, *Lp0 = nullptr;    // [nblk] first U / L entry of each block in the ordinary factor arrays (export)
+};
 struct LuDev : LuView {
+  std::vector<LuBatchDev> batch;
   std::vector<int> level_ptr;     // host copy: one launch per level
   std::vector<int> pull_tiny_ptr;
   std::vector<int> pull_short_ptr, pull_long_ptr, pull_chunk_ptr;   // host copies
@@ -121,6 +166,8 @@ namespace lu {
 cudaError_t upload_plan(const LuPlan &p, LuDev &d);
 void free_plan(LuDev &d);
 int launch_refactor(const LuDev &d, const double *d_A, cudaStream_t s);                       // returns #launches
+// copies the factor values of the batched groups into the ordinary Lx / Ux arrays (export / diagnostics only)
+int launch_batch_export(const LuDev &d, cudaStream_t s);
 int launch_solve(const LuDev &d, const double *d_A, const double *d_rhs, double *d_x, cudaStream_t s);
 }  // namespace lu
 }  // namespace xb

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
 #include <numeric>
 #include <queue>
 
@@ -253,6 +254,135 @@ void factor_block(int n, const std::vector<std::vector<std::pair<int, double>>> 
 
 }  // namespace
 
+// ---- batched groups: blocks with one common symbolic pattern, compiled into bundle programs (lu.h) ----------------
+namespace {
+struct BOp { int type, dst, a, b; };
+
+// Greedy list scheduling in program order.  `nres` resources; op reads r[0..nr) and read-modify-writes w.
+// Within a bundle all loads precede all stores, so an op may share a bundle with an EARLIER op that reads what it
+// writes, never precede it; ops that update the same destination stay in program order (RAW chain): summation order
+// per factor entry is exactly the left-looking order of the warp-per-block kernels.
+void schedule_bundles(const std::vector<BOp> &ops, int nres, const std::vector<std::vector<int>> &reads, const std::vector<int> &writes,
+                      std::vector<unsigned short> &prog, int &nbundles) {
+  std::vector<int> lastW(nres, -1), lastR(nres, -1), fill;
+  std::vector<std::vector<int>> bundles;
+  size_t first_open = 0;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    int earliest = 0;
+    for (int r : reads[i]) earliest = std::max(earliest, lastW[r] + 1);
+    if (writes[i] >= 0) earliest = std::max(earliest, std::max(lastW[writes[i]] + 1, lastR[writes[i]]));
+    size_t bidx = std::max<size_t>(earliest, first_open);
+    while (bidx < bundles.size() && (int)bundles[bidx].size() >= kBundle) ++bidx;
+    if (bidx >= bundles.size()) bundles.resize(bidx + 1);
+    bundles[bidx].push_back((int)i);
+    while (first_open < bundles.size() && (int)bundles[first_open].size() >= kBundle) ++first_open;
+    for (int r : reads[i]) lastR[r] = std::max(lastR[r], (int)bidx);
+    if (writes[i] >= 0) lastW[writes[i]] = (int)bidx;
+  }
+  nbundles = (int)bundles.size();
+  prog.assign((size_t)nbundles * kBundle * 3, 0);
+  for (int bi = 0; bi < nbundles; ++bi)
+    for (int k = 0; k < kBundle; ++k) {
+      unsigned short *o = &prog[((size_t)bi * kBundle + k) * 3];
+      if (k < (int)bundles[bi].size()) {
+        const BOp &op = ops[bundles[bi][k]];
+        o[0] = (unsigned short)(op.dst | (op.type << 14)); o[1] = (unsigned short)op.a; o[2] = (unsigned short)op.b;
+      } else {
+        o[0] = (unsigned short)(kOpNop << 14); o[1] = 0; o[2] = 0;
+      }
+    }
+}
+
+bool g_batching = true;
+void build_batch_groups(LuPlan &plan, const std::vector<int> &level) {
+  const std::vector<int> &bptr = plan.block_ptr;
+  const int nblocks = (int)bptr.size() - 1;
+  plan.batch.clear();
+  if (!g_batching) return;
+  // signature of a block: everything the programs depend on, relative to the block's first position / entry
+  std::map<std::vector<int>, std::vector<int>> by_sig;
+  for (int b = 0; b < nblocks; ++b) {
+    const int k0 = bptr[b], k1 = bptr[b + 1], nb = k1 - k0;
+    if (nb < 2 || nb > kBigBlock) continue;
+    const int l0 = plan.Lp[k0], u0 = plan.Up[k0], a0 = plan.acol_ptr[k0];
+    const int nl = plan.Lp[k1] - l0, nu = plan.Up[k1] - u0, na = plan.acol_ptr[k1] - a0;
+    if (nu + nl + nb > kBatchMaxSlots) continue;
+    std::vector<int> sig;
+    sig.reserve(4 + 3 * (nb + 1) + nl + nu + na);
+    sig.push_back(nb); sig.push_back(nl); sig.push_back(nu); sig.push_back(level[b]);
+    for (int k = k0; k <= k1; ++k) { sig.push_back(plan.Lp[k] - l0); sig.push_back(plan.Up[k] - u0); sig.push_back(plan.acol_ptr[k] - a0); }
+    for (int q = l0; q < l0 + nl; ++q) sig.push_back(plan.Li[q] - k0);
+    for (int q = u0; q < u0 + nu; ++q) sig.push_back(plan.Ui[q] - k0);
+    for (int q = a0; q < a0 + na; ++q) { const int d = plan.acol_dst[q]; sig.push_back(d >= 0 ? d - u0 : nu + (~d - l0)); }
+    by_sig[sig].push_back(b);
+  }
+  for (auto &kv : by_sig) {
+    const std::vector<int> &blocks = kv.second;
+    if ((int)blocks.size() < kBatchMinBlocks) continue;
+    LuPlan::BatchGroup g;
+    const int b0 = blocks[0], k0 = bptr[b0], k1 = bptr[b0 + 1];
+    const int l0 = plan.Lp[k0], u0 = plan.Up[k0], a0 = plan.acol_ptr[k0];
+    g.nb = k1 - k0; g.nl = plan.Lp[k1] - l0; g.nu = plan.Up[k1] - u0; g.na = plan.acol_ptr[k1] - a0; g.level = level[b0];
+    g.blocks = blocks;
+    const int nblk = (int)blocks.size();
+    auto uslot = [&](int q) { return q - u0; };
+    auto lslot = [&](int q) { return g.nu + (q - l0); };
+    g.a_dst.resize(g.na);
+    for (int e = 0; e < g.na; ++e) { const int d = plan.acol_dst[a0 + e]; g.a_dst[e] = d >= 0 ? uslot(d) : lslot(~d); }
+    g.a_src.resize((size_t)g.na * nblk);
+    for (int j = 0; j < nblk; ++j) {
+      const int aj = plan.acol_ptr[bptr[blocks[j]]];
+      for (int e = 0; e < g.na; ++e) g.a_src[(size_t)e * nblk + j] = plan.acol_src[aj + e];
+    }
+    // ---- refactor program: left-looking column by column, on factor slots ----
+    {
+      std::vector<BOp> ops; std::vector<std::vector<int>> reads; std::vector<int> writes;
+      // slot of row r in column k (U part, pivot or L part)
+      auto col_slot = [&](int k, int r) {
+        const int ub = plan.Up[k], ue = plan.Up[k + 1] - 1, lb = plan.Lp[k], le = plan.Lp[k + 1];
+        if (r == k) return uslot(ue);
+        if (r < k) return uslot((int)(std::lower_bound(plan.Ui.begin() + ub, plan.Ui.begin() + ue, r) - plan.Ui.begin()));
+        return lslot((int)(std::lower_bound(plan.Li.begin() + lb, plan.Li.begin() + le, r) - plan.Li.begin()));
+      };
+      for (int k = k0; k < k1; ++k) {
+        const int ub = plan.Up[k], ue = plan.Up[k + 1] - 1, lb = plan.Lp[k], le = plan.Lp[k + 1];
+        for (int q = ub; q < ue; ++q) {
+          const int i = plan.Ui[q];
+          for (int t = plan.Lp[i]; t < plan.Lp[i + 1]; ++t) {
+            const int dst = col_slot(k, plan.Li[t]);
+            ops.push_back({kOpFnma, dst, lslot(t), uslot(q)}); reads.push_back({dst, lslot(t), uslot(q)}); writes.push_back(dst);
+          }
+        }
+        ops.push_back({kOpChk, 0, uslot(ue), 0}); reads.push_back({uslot(ue)}); writes.push_back(-1);
+        for (int q = lb; q < le; ++q) { ops.push_back({kOpDiv, lslot(q), uslot(ue), 0}); reads.push_back({lslot(q), uslot(ue)}); writes.push_back(lslot(q)); }
+      }
+      schedule_bundles(ops, g.nu + g.nl, reads, writes, g.rf_prog, g.rf_bundles);
+    }
+    // ---- solve program on the block's right-hand side y[0, nb): unit-lower forward, then backward with U ----
+    {
+      std::vector<BOp> ops; std::vector<std::vector<int>> reads; std::vector<int> writes;
+      // resources: y rows only (factor slots are read-only here)
+      for (int k = k0; k < k1; ++k)
+        for (int q = plan.Lp[k]; q < plan.Lp[k + 1]; ++q) {
+          const int dst = plan.Li[q] - k0;
+          ops.push_back({kOpFnma, dst, lslot(q), k - k0}); reads.push_back({dst, k - k0}); writes.push_back(dst);
+        }
+      for (int k = k1 - 1; k >= k0; --k) {
+        const int ue = plan.Up[k + 1] - 1;
+        ops.push_back({kOpDiv, k - k0, uslot(ue), 0}); reads.push_back({k - k0}); writes.push_back(k - k0);
+        for (int q = plan.Up[k]; q < ue; ++q) {
+          const int dst = plan.Ui[q] - k0;
+          ops.push_back({kOpFnma, dst, uslot(q), k - k0}); reads.push_back({dst, k - k0}); writes.push_back(dst);
+        }
+      }
+      schedule_bundles(ops, g.nb, reads, writes, g.sv_prog, g.sv_bundles);
+    }
+    for (int b : blocks) plan.block_big[b] = 3;
+    plan.batch.push_back(std::move(g));
+  }
+}
+}  // namespace
+
 // Everything the GPU kernels need beyond the permutations and the L / U patterns: scatter maps A -> factor slots,
 // off-diagonal entries by column and by row, block levels, pull lists, large-block schedules, flop count.
 // Inputs already in the plan: n, block_ptr, row_perm (through new_rowpos), col_perm, Lp / Li / Up / Ui.
@@ -361,6 +491,7 @@ static void finish_plan(LuPlan &plan, const std::vector<int> &Ap, const std::vec
         else plan.acol_dst[q] = ~(int)(std::lower_bound(plan.Li.begin() + lb, plan.Li.begin() + le, r) - plan.Li.begin());
       }
     }
+    build_batch_groups(plan, level);
     // small blocks whose factor (indices + values + one dense column) fits a per-warp shared-memory slice are
     // "staged": block_big = 2.  Slice = 2 (nb + 1) + nl + nu 16-bit indices and nb + nl + nu doubles.
     plan.staged_bytes = 0;
@@ -456,6 +587,8 @@ static void finish_plan(LuPlan &plan, const std::vector<int> &Ap, const std::vec
   }
   plan.refactor_flops = fl;
 }
+
+void set_batching(bool on) { g_batching = on; }
 
 int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol, LuPlan &plan) {
   plan = LuPlan();
@@ -644,6 +777,76 @@ int import_factorization(int n, const int *rowptr, const int *colind, const int 
 
 // CPU reference of the refactor + solve on a fixed plan (used by the first solve and by tests of the
 // plan itself; the product's per-iteration path is the GPU one).
+// Host execution of the batched-group programs (what lu_refactor_batched_kernel / lu_solve_batched_kernel do per
+// lane) against a plain left-looking refactorization and triangular solves of the same blocks on the same pattern.
+// out[0] = groups, out[1] = batched blocks, out[2] = largest deviation relative to the largest factor entry (refactor),
+// out[3] = same for the solve.  Used by the CPU tests: the programs are checked without a GPU.
+void batch_selfcheck_host(const LuPlan &p, const double *vals, double *out) {
+  out[0] = (double)p.batch.size(); out[1] = 0; out[2] = 0; out[3] = 0;
+  for (const LuPlan::BatchGroup &g : p.batch) {
+    const int nblk = (int)g.blocks.size(), ns = g.nu + g.nl;
+    out[1] += nblk;
+    for (int j = 0; j < nblk; ++j) {
+      const int b = g.blocks[j], k0 = p.block_ptr[b], k1 = p.block_ptr[b + 1], u0 = p.Up[k0], l0 = p.Lp[k0];
+      // program
+      std::vector<double> v(ns, 0.0);
+      for (int e = 0; e < g.na; ++e) v[g.a_dst[e]] = vals[g.a_src[(size_t)e * nblk + j]];
+      for (int bi = 0; bi < g.rf_bundles; ++bi) {
+        double d[kBundle], x[kBundle], y[kBundle]; int ty[kBundle], ds[kBundle];
+        for (int k = 0; k < kBundle; ++k) {
+          const unsigned short *o = &g.rf_prog[((size_t)bi * kBundle + k) * 3];
+          ty[k] = o[0] >> 14; ds[k] = o[0] & 0x3fff; d[k] = v[ds[k]]; x[k] = v[o[1]]; y[k] = v[o[2]];
+        }
+        for (int k = 0; k < kBundle; ++k) {
+          if (ty[k] == kOpFnma) v[ds[k]] = d[k] - x[k] * y[k];
+          else if (ty[k] == kOpDiv) v[ds[k]] = d[k] / x[k];
+        }
+      }
+      // plain left-looking refactorization of the block with a dense work column
+      std::vector<double> Lx(g.nl), Ux(g.nu), x(g.nb);
+      for (int k = k0; k < k1; ++k) {
+        std::fill(x.begin(), x.end(), 0.0);
+        for (int q = p.acol_ptr[k]; q < p.acol_ptr[k + 1]; ++q) x[p.acol_row[q] - k0] = vals[p.acol_src[q]];
+        const int ue = p.Up[k + 1] - 1;
+        for (int q = p.Up[k]; q < ue; ++q) {
+          const int i = p.Ui[q]; const double u = x[i - k0];
+          Ux[q - u0] = u;
+          for (int t = p.Lp[i]; t < p.Lp[i + 1]; ++t) x[p.Li[t] - k0] -= Lx[t - l0] * u;
+        }
+        Ux[ue - u0] = x[k - k0];
+        for (int q = p.Lp[k]; q < p.Lp[k + 1]; ++q) Lx[q - l0] = x[p.Li[q] - k0] / x[k - k0];
+      }
+      double mx = 0.0, dev = 0.0;
+      for (int s2 = 0; s2 < g.nu; ++s2) { mx = std::max(mx, std::fabs(Ux[s2])); dev = std::max(dev, std::fabs(Ux[s2] - v[s2])); }
+      for (int s2 = 0; s2 < g.nl; ++s2) { mx = std::max(mx, std::fabs(Lx[s2])); dev = std::max(dev, std::fabs(Lx[s2] - v[g.nu + s2])); }
+      out[2] = std::max(out[2], dev / (mx > 0 ? mx : 1.0));
+      // solve: program against direct substitution, right-hand side 1, 2, 3, ...
+      std::vector<double> y(g.nb), z(g.nb);
+      for (int i = 0; i < g.nb; ++i) y[i] = z[i] = 1.0 + i;
+      for (int bi = 0; bi < g.sv_bundles; ++bi) {
+        double d[kBundle], xx[kBundle], yy[kBundle]; int ty[kBundle], ds[kBundle];
+        for (int k = 0; k < kBundle; ++k) {
+          const unsigned short *o = &g.sv_prog[((size_t)bi * kBundle + k) * 3];
+          ty[k] = o[0] >> 14; ds[k] = o[0] & 0x3fff; d[k] = y[ds[k]]; xx[k] = v[o[1]]; yy[k] = y[o[2]];
+        }
+        for (int k = 0; k < kBundle; ++k) {
+          if (ty[k] == kOpFnma) y[ds[k]] = d[k] - xx[k] * yy[k];
+          else if (ty[k] == kOpDiv) y[ds[k]] = d[k] / xx[k];
+        }
+      }
+      for (int k = k0; k < k1; ++k) for (int q = p.Lp[k]; q < p.Lp[k + 1]; ++q) z[p.Li[q] - k0] -= Lx[q - l0] * z[k - k0];
+      for (int k = k1 - 1; k >= k0; --k) {
+        const int ue = p.Up[k + 1] - 1;
+        z[k - k0] /= Ux[ue - u0];
+        for (int q = p.Up[k]; q < ue; ++q) z[p.Ui[q] - k0] -= Ux[q - u0] * z[k - k0];
+      }
+      double zm = 0.0, zd = 0.0;
+      for (int i = 0; i < g.nb; ++i) { zm = std::max(zm, std::fabs(z[i])); zd = std::max(zd, std::fabs(z[i] - y[i])); }
+      out[3] = std::max(out[3], zd / (zm > 0 ? zm : 1.0));
+    }
+  }
+}
+
 void solve_host(const LuPlan &p, const double *b, double *x) {
   const int n = p.n;
   std::vector<double> y(n);

@@ -135,7 +135,7 @@ struct GpuBackend {
     if (!lu_analyzed) { rc = xgpu_lu_analyze(ctx, J); lu_analyzed = (rc == 0 || rc == 2); ++lu_analyses; }
     else {
       rc = xgpu_lu_refactor(ctx, J); ++lu_refactors;
-      if (rc == 2) { rc = xgpu_lu_analyze(ctx, J); ++lu_analyses; }      // re-pivot on the host
+      if (rc == 2 || rc == 3) { rc = xgpu_lu_analyze(ctx, J); ++lu_analyses; }      // bad or sub-threshold pivot: re-pivot on the host
     }
     if (rc != 0) { vec::fill(v[sim::vDX], 0.0, n_, s); return rc; }
     return xgpu_lu_solve(ctx, J, v[sim::vRHS], v[sim::vDX]);
