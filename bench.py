@@ -6,9 +6,9 @@ Workload (config.workload): BASELINE config 2 -- 100 000-instance BSIM4 inverter
   value : whole-job evaluations/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the host-buffer C-ABI call (H2D of x, D2H of F,Q,dFdxdVp,dQdxdVp,dFdx,dQdx)
   --impl reference : the reference's own BSIM4 C++ (oracle/_ref, compiled from /root/reference)
-                     on all host cores, bounded sample of the same workload.
-Multi-GPU: instances are partitioned into independent arrays, one per rank (no data-path
-collective; weak scaling).
+                     on all host cores, the full 100k-instance array partitioned over the cores.
+Multi-GPU: the ranks hold the partitions of one N x 100k-instance circuit on a common supply rail; the border rows
+are summed over the ranks every step by the library's NCCL communicator (weak scaling).
 """
 import argparse
 import json
@@ -329,8 +329,22 @@ def run_ours(args):
     state_args = (d_x.data_ptr(), d_sta[0].data_ptr(), d_sta[1].data_ptr(), d_sto[0].data_ptr(), d_sto[1].data_ptr(), ss)
     out_args = tuple(t.data_ptr() for t in d_vec) + (d_mat[0].data_ptr(), d_mat[1].data_ptr())
 
+    # N > 1: the ranks' arrays are the partitions of ONE circuit -- N x 100k instances on a common supply rail.  The
+    # supply node is the border unknown of every partition (last local unknown); after the local assembly its rows of
+    # F, Q, dFdxdVp, dQdxdVp are summed over the ranks by the library's own NCCL communicator (pack -> ncclAllReduce ->
+    # unpack on the stream; the reference's reverse export with Add, N_LOA_CktLoader.C:816-829).
+    shared = world > 1
+    if shared:
+        from xyce_b200.capi import Engine
+        ids = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.comm_init(ids[0], rank, world)
+        eng.border_set(1)
+
     def step():          # one pass of the hot path: updateState + loadDAEVectors + loadDAEMatrices (xgpu_load_dae)
         eng.load_dae(*state_args, *out_args, accumulate=False)
+        if shared:
+            eng.shared_reduce(*out_args[:4])
 
     def eval_only():     # the dominant kernel alone (roofline figure)
         eng.update_state(*state_args)
@@ -426,7 +440,9 @@ def run_ours(args):
             "config": {"workload": "100k-instance BSIM4 (level 54, v4.8.2) inverter array, updateState+loadDAEVectors+"
                                    "loadDAEMatrices at a fixed operating point (BASELINE config 2)",
                        "instances_per_gpu": n_inst, "unknowns_per_gpu": n, "nnz_per_gpu": nnz,
-                       "parallelism": "instances partitioned per rank, no data-path collective",
+                       "parallelism": ("one circuit of %d x %d instances on a common supply rail, instance-partitioned per rank; border "
+                                       "(supply) rows of F, Q, dFdxdVp, dQdxdVp summed per step with ncclAllReduce inside the library" % (world, n_inst))
+                                      if shared else "single GPU",
                        "host_affinity": ("rank pinned to its GPU's NUMA node %s" % numa_node) if (numa_node is not None and numa_node >= 0) else "default (single NUMA node)",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + nnz),

@@ -182,6 +182,36 @@ int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colin
 int xgpu_lu_host_batch_selfcheck(int n, const int32_t *rowptr, const int32_t *colind, const double *vals0,
                                  const double *vals1, double *out4);
 
+/* ---- bordered block-diagonal solve and multi-GPU (one process per GPU, NCCL over NVLink) ----
+ * Replaces Xyce's MPI "parallel load" + gathered direct solve: reverse export of ghost rows with Add
+ * (N_LOA_CktLoader.C:600-601, :816-829; N_LAS_EpetraMultiVector.C:843-849, N_LAS_EpetraMatrix.C:202-208), halo import of
+ * the solution (:468-470), DeviceMgr::allDevicesConverged's reduction (Core/N_DEV_DeviceMgr.C:5628).
+ * Each rank holds its partition with the unknowns ordered [interior | border]; the border unknowns (shared between
+ * partitions: supply rails, source branches; or dense nodes a single GPU wants out of its BTF blocks) are the LAST
+ * n_border unknowns, replicated on every rank in the same order.  Devices attached only to border unknowns belong to
+ * one rank; sources on border rows are replicated (the B vector is not reduced).
+ *   xgpu_comm_unique_id / xgpu_comm_init: NCCL communicator of the context (the id is created on one rank and
+ *     distributed by the host application: MPI_Bcast in Xyce, the store of torch.distributed in bench.py).  libnccl is
+ *     loaded at run time; without it xgpu_comm_init fails and everything else works.
+ *   xgpu_border_set: declares the border (after xgpu_finalize; at most 96 unknowns).  world = 1 is allowed.
+ *   xgpu_shared_reduce: sums the border rows of the given vectors (NULL = skip) over the ranks, in place, on the
+ *     context's stream: pack -> ncclAllReduce -> unpack, no host synchronisation.  No-op without a communicator.
+ *   xgpu_border_analyze / xgpu_border_solve: the interior block A_ii is analysed / refactored with the KLU-pattern LU
+ *     straight out of the full CSR values; Y = A_ii^-1 [A_is | b_i]; the rank's part of the Schur system
+ *     [A_ss - A_si Y_s | b_s - A_si y] is all-reduced (ONE collective), solved redundantly by every rank, and the
+ *     interior unknowns are back-substituted.  d_vals holds this rank's partial sums in the border block;
+ *     rhs_border_reduced != 0: the border rows of d_rhs are already summed (replicated), else they are partial sums.
+ *     Return codes as xgpu_lu_refactor.  xgpu_tran_run uses these automatically once a border is declared, and with a
+ *     communicator combines the norms / convergence flags of the ranks in one small all-gather per evaluation. */
+int xgpu_comm_unique_id(unsigned char *id128);
+int xgpu_comm_init(xgpu_ctx *ctx, const unsigned char *id128, int rank, int world);
+int xgpu_comm_info(const xgpu_ctx *ctx, int *rank, int *world);
+int xgpu_border_set(xgpu_ctx *ctx, int n_border);
+int xgpu_border_info(const xgpu_ctx *ctx, int *n_interior, int *n_border, long long *n_global);
+int xgpu_shared_reduce(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_dFdxdVp, double *d_dQdxdVp);
+int xgpu_border_analyze(xgpu_ctx *ctx, const double *d_vals);
+int xgpu_border_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x, int rhs_border_reduced);
+
 /* ---- linear devices, sources, Newton + transient loop (callers of the hot path) ----
  * xgpu_linear_set: constant conductance (G) and capacitance (C) stamps of the linear devices as COO
  *   triplets (duplicates are summed, entries with a -1 index = ground are dropped).  Replayed on every
@@ -213,6 +243,20 @@ int xgpu_linear_set(xgpu_ctx *ctx, int nG, const int32_t *g_row, const int32_t *
                     int nC, const int32_t *c_row, const int32_t *c_col, const double *c_val);
 int xgpu_sources_set(xgpu_ctx *ctx, int n_sources, const int32_t *row, const double *scale, const int32_t *type,
                      const double *params7);
+/* Table of the piece-wise linear sources: n_points (time, value) pairs shared by all PWL sources; a source of type 5
+ * has params7 = {TD, offset (in points), count, REPEAT (0 / 1), REPEATTIME} (PWLinData, Core/N_DEV_SourceData.C:1770-1886).
+ * Source types of xgpu_sources_set: 0 DC {v}, 1 PULSE {v1 v2 td tr tf pw per}, 2 SIN {v0 va freq td theta phase},
+ * 3 EXP {v1 v2 td1 tau1 td2 tau2} (:811), 4 SFFM {v0 va fc mdi fs} (:2908), 5 PWL.  PULSE and PWL sources announce break
+ * points (PulseData::getBreakPoints :1442, PWLinData::getBreakPoints :2044): xgpu_tran_run steps exactly onto them and
+ * restarts the integration there (order 1, fresh initial step) as Transient / StepErrorControl do
+ * (N_ANP_Transient.C:1900-1948, N_TIA_StepErrorControl.C:370-420, :742-850); a PULSE source also caps the step at a
+ * tenth of its period (PulseData::getMaxTimeStepSize :1518). */
+int xgpu_sources_pwl_set(xgpu_ctx *ctx, int n_points, const double *tv_pairs);
+/* Host-only views of the source routines (no GPU, no context), for tests: value at time t, break points announced at t
+ * (returns their number, writes at most max_out), step cap at t. */
+double xgpu_source_value(int type, const double *params7, const double *pwl_tv_pairs, double t, double bp_tol);
+int xgpu_source_breakpoints(int type, const double *params7, const double *pwl_tv_pairs, double t, int max_out, double *out);
+double xgpu_source_max_step(int type, const double *params7, double t);
 int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0, int n_probes,
                   const int32_t *probes, int max_out, int *n_out, double *h_times, double *h_wave,
                   int max_steps_out, int *n_steps_out, double *h_step_info5, double *stats16);

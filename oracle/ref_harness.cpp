@@ -43,6 +43,7 @@
 #include <signal.h>
 #include <unistd.h>
 
+#include "../adaptor/N_DEV_GpuMaster_B4.h"      // the Xyce-side adaptor (product code for the reference tree), driven by tests/test_gpu_adaptor.py
 #include "../xyce_b200/csrc/bsim4_fields.def"
 #include "b4_mid_members.def"
 #include "../xyce_b200/csrc/tran_driver.h"   // control flow only (Newton / OneStep restatement)
@@ -174,7 +175,12 @@ struct Ctx {
   int master(const std::string &t) {
     for (size_t i = 0; i < masterType.size(); ++i) if (masterType[i] == t) return (int)i;
     Configuration *cfg = 0; Xyce::Device::Device *m = 0;
-    if (t == "b4") { auto *c = &Config<MOSFET_B4::Traits>::addConfiguration(); cfg = c; m = MOSFET_B4::Traits::factory(*c, *fb); }
+    if (t == "b4") {
+      auto *c = &Config<MOSFET_B4::Traits>::addConfiguration(); cfg = c;
+      // the factory hook (N_DEV_MOSFET_B4.C:11688-11692): stock Master, or the GPU adaptor with the same constructor arguments
+      if (gpuB4) m = new MOSFET_B4::GpuMaster(*c, *fb, fb->solverState_, fb->deviceOptions_);
+      else m = MOSFET_B4::Traits::factory(*c, *fb);
+    }
     else if (t == "m1") { auto *c = &Config<MOSFET1::Traits>::addConfiguration(); cfg = c; m = MOSFET1::Traits::factory(*c, *fb); }
     else if (t == "d") { auto *c = &Config<Diode::Traits>::addConfiguration(); cfg = c; m = Diode::Traits::factory(*c, *fb); }
     else if (t == "q") { auto *c = &Config<BJT::Traits>::addConfiguration(); cfg = c; m = BJT::Traits::factory(*c, *fb); }
@@ -200,6 +206,7 @@ struct Ctx {
     for (auto *m : masters) ok = m->loadDAEMatrices(dFdx, dQdx) && ok;
     return ok;
   }
+  bool gpuB4 = false;        // BSIM4 instances go to MOSFET_B4::GpuMaster (adaptor/N_DEV_GpuMaster_B4.h) instead of the stock Master
   std::vector<double> staDeriv, leadF, leadQ, junctionV;
   bool lead = false;         // DeviceInstance::enableLeadCurrentCalc on every instance (what .PRINT I(...) / P(...) triggers)
   std::vector<InstRec> insts;
@@ -372,6 +379,32 @@ int xref_finalize(void *h) {
   for (auto &r : c->insts) r.inst->setupPointers();
   c->finalized = true;
   return c->n;
+}
+
+// ---- the Xyce-side GPU adaptor in place of the stock BSIM4 Master ----
+// xref_use_gpu_master: before the first BSIM4 model / instance is added.  xref_gpu_attach: after xref_finalize
+// (all LIDs registered).  From then on updateAll / loadVectorsAll / loadMatricesAll reach the GPU through the same
+// Device virtuals the stock Master answers.
+void xref_use_gpu_master(void *h, int on) { ((Ctx *)h)->gpuB4 = on != 0; }
+int xref_gpu_attach(void *h, int cuda_device) {
+  Ctx *c = (Ctx *)h;
+  const int d = c->master("b4");
+  MOSFET_B4::GpuMaster *g = d >= 0 ? dynamic_cast<MOSFET_B4::GpuMaster *>(c->masters[d]) : nullptr;
+  if (!g) return 1;
+  if (!g->attach(cuda_device, c->n, c->n, c->nSta, c->nSto)) { std::cerr << "xref_gpu_attach: " << g->lastError() << std::endl; return 2; }
+  return 0;
+}
+int xref_gpu_set_von(void *h, const double *von) {      // von[i] of the i-th BSIM4 instance (harness order = instance-vector order)
+  Ctx *c = (Ctx *)h;
+  const int d = c->master("b4");
+  MOSFET_B4::GpuMaster *g = d >= 0 ? dynamic_cast<MOSFET_B4::GpuMaster *>(c->masters[d]) : nullptr;
+  return (g && g->setVon(von)) ? 0 : 1;
+}
+int xref_all_converged(void *h) {
+  Ctx *c = (Ctx *)h;
+  bool ok = true;
+  for (auto *m : c->masters) ok = m->isConverged() && ok;      // DeviceMgr::allDevicesConverged (Core/N_DEV_DeviceMgr.C:5603-5640)
+  return ok ? 1 : 0;
 }
 
 int xref_nnz(void *h) { return (int)((Ctx *)h)->dFdx.colind.size(); }
@@ -653,6 +686,13 @@ struct RefBackend {
   std::vector<int> Gpos, Cpos;
   struct Src { int row; double scale; int type; double p[7]; };
   std::vector<Src> sources;
+  std::vector<double> pwl;      // (time, value) pairs of the PWL sources
+  void breakpoints(double t, std::vector<double> &out) { for (const Src &q : sources) xb::sim::source_breakpoints(q.type, q.p, pwl.data(), t, out); }
+  double max_source_step(double t) {
+    double m = 1.0e99;
+    for (const Src &q : sources) { const double v = xb::sim::source_max_step(q.type, q.p, t); if (v > 0.0) m = std::min(m, v); }
+    return m;
+  }
   std::vector<int> probes;
   std::vector<double> times, wave;
   char *M = 0;
@@ -683,7 +723,7 @@ struct RefBackend {
     ok = c->loadVectorsAll() && ok;
     for (size_t k = 0; k < G.r.size(); ++k) c->f[G.r[k]] += G.v[k] * c->sol[G.c[k]];
     for (size_t k = 0; k < C.r.size(); ++k) c->q[C.r[k]] += C.v[k] * c->sol[C.c[k]];
-    for (const Src &q : sources) c->b[q.row] += q.scale * xb::sim::source_value(q.type, q.p, time);
+    for (const Src &q : sources) c->b[q.row] += q.scale * xb::sim::source_value(q.type, q.p, time, pwl.data(), fl.bpTol);
     std::copy(c->f.begin(), c->f.begin() + n_, v[xb::sim::vF].begin());
     std::copy(c->q.begin(), c->q.begin() + n_, v[xb::sim::vQ].begin());
     std::copy(c->b.begin(), c->b.begin() + n_, v[xb::sim::vB].begin());
@@ -753,12 +793,15 @@ struct RefBackend {
 }  // namespace
 
 // step sequence for the next xref_tran_run (TranParams::replay_h / replay_order); consumed by that run
+static int g_pwl_n = 0;
+static const double *g_pwl = nullptr;
 static int g_replay_n = 0;
 static const double *g_replay_h = nullptr;
 static const int *g_replay_order = nullptr;
 
 extern "C" {
 
+void xref_tran_pwl(int n_points, const double *tv_pairs) { g_pwl_n = n_points; g_pwl = tv_pairs; }      // PWL table of the next xref_tran_run
 void xref_tran_replay(int n, const double *h, const int *order) { g_replay_n = n; g_replay_h = h; g_replay_order = order; }
 
 // params: tstop, tstep, delmax, method (0 / 7 trapezoid, 8 Gear), dcop (0 / 1).  Linear part as COO (G, C), sources {row, scale, type, p[7]}.
@@ -786,6 +829,8 @@ int xref_tran_run(void *h, const double *params5, const double *x0, int nG, cons
   P.tstop = params5[0]; P.tstep = params5[1]; P.delmax = params5[2];
   if ((int)params5[3] == 8) P.method = 8;
   P.dcop = params5[4] != 0.0;
+  if (g_pwl_n > 0) B.pwl.assign(g_pwl, g_pwl + 2 * (size_t)g_pwl_n);
+  g_pwl_n = 0;
   if (g_replay_n > 0) { P.replay_h.assign(g_replay_h, g_replay_h + g_replay_n); P.replay_order.assign(g_replay_order, g_replay_order + g_replay_n); }
   g_replay_n = 0;
   xb::sim::TransientDriver<RefBackend> drv(B, P);

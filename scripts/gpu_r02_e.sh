@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_lu.py -x -q -k "pivot_monitor" 2>&1 | grep -v Netlist | tail -4
+python -m pytest tests/test_gpu_lu.py -x -q -k "pivot_monitor or batched or ring_arrays" 2>&1 | grep -v Netlist | tail -4
 cat > /tmp/one.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -9,10 +9,10 @@ eng = wl.build_engine(w)
 r = eng.tran_run(w["x"], 1e-11, 1e-12, [0])
 print(r["stats"])
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 700 --csv --log-file gpurun_out/r02_launches_tran_c3_v1.csv python /tmp/one.py > gpurun_out/r02_tran_ncu_v1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 700 --csv --log-file gpurun_out/r02_launches_tran_c3_v2.csv python /tmp/one.py > gpurun_out/r02_tran_ncu_v2.log 2>&1
 python - <<'PY'
 import csv, collections
-rows = list(csv.reader(open("gpurun_out/r02_launches_tran_c3_v1.csv")))
+rows = list(csv.reader(open("gpurun_out/r02_launches_tran_c3_v2.csv")))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 h = rows[hdr]
 ik, iv = h.index("Kernel Name"), h.index("Metric Value")

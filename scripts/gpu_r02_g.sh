@@ -1,0 +1,12 @@
+mkdir -p gpurun_out
+cat > /tmp/one.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+from xyce_b200 import workloads as wl
+w = wl.ring_oscillator_array(4950, 101)
+eng = wl.build_engine(w)
+r = eng.tran_run(w["x"], 6e-12, 1e-12, [0])
+print(r["stats"])
+PY
+python -m pytest tests/test_gpu_lu.py tests/test_gpu_border.py tests/test_gpu_lu_import.py -x -q 2>&1 | grep -v Netlist | tail -12
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:batched -s 4 -c 4 --csv python /tmp/one.py 2>&1 | grep batched | cut -c60-250

@@ -162,6 +162,19 @@ class RefCircuit:
         assert rc == 0
         return out
 
+    # ---- the Xyce-side GPU adaptor (adaptor/N_DEV_GpuMaster_B4.h) in place of the stock BSIM4 Master ----
+    def use_gpu_master(self, on=True):
+        """call before the first BSIM4 model / instance is added"""
+        self.lib.xref_use_gpu_master(self.h, int(on))
+
+    def gpu_attach(self, device=0):
+        """after finalize(): extract the records from the reference objects and upload them through the C ABI"""
+        rc = self.lib.xref_gpu_attach(self.h, int(device))
+        assert rc == 0, "xref_gpu_attach failed (%d)" % rc
+
+    def all_converged(self):
+        return bool(self.lib.xref_all_converged(self.h))
+
     def load_repeat(self, x, reps):
         x = np.ascontiguousarray(x, dtype=np.float64)
         self.lib.xref_set_solution(self.h, dptr(x))
@@ -172,7 +185,7 @@ class RefCircuit:
         self.lib.xref_add_pattern_entries(self.h, len(r), iptr(r), iptr(c))
 
     def tran_run(self, x0, tstop, tstep, probes, linear, sources, delmax=0.0, max_out=200000, method=0, dcop=0,
-                 replay=None):
+                 replay=None, pwl=None):
         """Transient run: tran_driver.h control flow around the reference device code + ksparse.
         replay = (h[], order[]): integrate on exactly these accepted steps (TranParams::replay_h) instead of
         selecting steps -- used to compare a sub-circuit with a larger run on that run's own time points."""
@@ -181,6 +194,9 @@ class RefCircuit:
         if replay is not None:
             rh, ro = f64(replay[0]), i32(replay[1])
             self.lib.xref_tran_replay(len(rh), dptr(rh), iptr(ro))
+        if pwl is not None:
+            tv = f64(np.asarray(pwl, dtype=np.float64).reshape(-1, 2))
+            self.lib.xref_tran_pwl(len(tv), dptr(tv))
         par = f64([tstop, tstep, delmax, method, dcop])
         L = {k: (i32(v) if k.endswith(("row", "col")) else f64(v)) for k, v in linear.items()}
         S = dict(row=i32(sources["row"]), scale=f64(sources["scale"]), type=i32(sources["type"]), params=f64(sources["params"]))

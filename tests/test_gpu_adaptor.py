@@ -1,0 +1,59 @@
+"""The COMPILED Xyce-side adaptor (adaptor/N_DEV_GpuMaster_B4.h : MOSFET_B4::GpuMaster, a subclass of the reference's
+BSIM4 Master created through the factory hook) against the stock Master, both driven through the same Device virtuals
+-- updateState -> loadDAEVectors -> loadDAEMatrices -> isConverged (Core/N_DEV_Device.h:312-531) -- on the reference's
+own objects, Linear::Matrix addressing and ExternData vectors, in one process.  The adaptor extracts the records from the
+reference's Instance / Model / SizeDependParam objects itself (no Python in between) and reaches the GPU through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle_ref
+from b4_common import FLAG_NAMES, VARIANTS, isolated_devices, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class GpuRef(oracle_ref.RefCircuit):
+    def __init__(self, n):
+        super().__init__(n)
+        self.use_gpu_master(True)
+
+
+CASES = {"tran1": dict(transient=1, newtonIter=1), "tran_init": dict(transient=1, initTran=1, newtonIter=0),
+         "dcop_jct": dict(dcop=1, tranop=1, initJct=1, newtonIter=0), "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0)}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("variant", ["default", "rgate3", "rbody", "rdsmod", "igc2_v470", "mob1_v461"])
+def test_gpu_master_equals_stock_master_through_the_device_virtuals(variant, case):
+    assert variant in VARIANTS
+    stock = isolated_devices(oracle_ref.RefCircuit, 24, variant, seed=3)
+    gpu = isolated_devices(GpuRef, 24, variant, seed=3)
+    gpu.gpu_attach(0)
+    assert gpu.n == stock.n and np.array_equal(gpu.rowptr, stock.rowptr) and np.array_equal(gpu.colind, stock.colind)
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-0.3, 1.3, stock.n)
+    csto, nsto = rng.normal(0.3, 0.3, stock.n_sto), rng.normal(0.3, 0.3, stock.n_sto)
+    von = rng.uniform(0.2, 0.6, stock.n_inst)
+    flags = CASES[case]
+    out = []
+    for c in (stock, gpu):
+        c.set_flags(**flags)
+        c.set_state(curr_sto=csto, next_sto=nsto)
+        c.set_von(von)
+    gpu_eng_von(gpu, von)
+    want, got = stock.load(x), gpu.load(x)
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, k
+    ws, gs = stock.get_state(), gpu.get_state()
+    # store slots the reference never writes (vged, vgmd) keep their input on both sides
+    assert rel_err(gs["next_sto"], ws["next_sto"], 1e-30) < 1e-12
+    assert rel_err(gs["next_sta"], ws["next_sta"], 1e-30) < 1e-12
+    if case == "tran_init":
+        assert rel_err(gs["curr_sta"], ws["curr_sta"], 1e-30) < 1e-12
+    assert gpu.all_converged() == stock.all_converged()
+
+
+def gpu_eng_von(gpu, von):
+    """the carried limiter threshold lives in the GPU context (Instance::von on the stock side)"""
+    gpu.lib.xref_gpu_set_von(gpu.h, oracle_ref.dptr(np.ascontiguousarray(von, dtype=np.float64)))

@@ -94,9 +94,27 @@ def test_ring_partition_is_consistent():
         # interior unknowns of different ranks are disjoint
     allint = np.concatenate([p["glob_of_local"][:p["n_interior"]] for p in parts])
     assert len(np.unique(allint)) == len(allint)
-    # the supply source (linear G stamps on shared unknowns + the source itself) is kept by rank 0 only
-    assert len(parts[0]["sources"]["row"]) == 1 and all(len(p["sources"]["row"]) == 0 for p in parts[1:])
+    # the supply source's linear G stamps (shared unknowns only) are kept by rank 0 alone: the border reduction counts
+    # them once; the source VALUE sits on a shared row and is replicated on every rank (B is not reduced)
+    assert all(len(p["sources"]["row"]) == 1 for p in parts)
     assert len(parts[0]["linear"]["g_row"]) == 2 and all(len(p["linear"]["g_row"]) == 0 for p in parts[1:])
+
+
+def test_linear_device_across_the_cut_makes_both_unknowns_shared():
+    """A resistor between two rings owned by different ranks couples their interiors: both of its nodes must become
+    shared (the classifier used to look at the BSIM4 nodes only and silently kept a foreign index)."""
+    w = wl.ring_oscillator_array(4, 11)
+    a, b = 3, 2 * 11 + 5                                   # node of ring 0 and node of ring 2
+    L = w["linear"]
+    for k, v in (("g_row", [a, a, b, b]), ("g_col", [a, b, a, b])):
+        L[k] = np.concatenate([L[k], np.array(v, dtype=np.int32)])
+    L["g_val"] = np.concatenate([L["g_val"], [1e-3, -1e-3, -1e-3, 1e-3]])
+    parts = [pt.partition_ring_array(w, 2, r) for r in range(2)]
+    for p in parts:
+        assert p["n_shared"] == 4 and p["owner"][a] == -1 and p["owner"][b] == -1
+        assert np.all(p["linear"]["g_row"] >= 0) and np.all(p["linear"]["g_col"] >= 0)
+    # every stamp entry is kept exactly once
+    assert sum(len(p["linear"]["g_row"]) for p in parts) == len(L["g_row"])
 
 
 def test_graph_partition_keeps_rings_whole_and_balances():
@@ -145,6 +163,6 @@ def test_workload_partition_from_the_graph_partitioner():
         assert p["n_shared"] == 2 and p["lids"].max() < p["n_unknowns"] and p["n_inst"] % 22 == 0      # whole rings
     allint = np.concatenate([p["glob_of_local"][:p["n_interior"]] for p in parts])
     assert len(np.unique(allint)) == len(allint)
-    assert len(parts[0]["sources"]["row"]) == 1 and all(len(p["sources"]["row"]) == 0 for p in parts[1:])
+    assert all(len(p["sources"]["row"]) == 1 for p in parts)          # sources on shared rows are replicated
     # per-ring load capacitors stay with their ring's rank: C stamps of all parts together = the original ones
     assert sum(len(p["linear"]["c_row"]) for p in parts) == len(w["linear"]["c_row"])

@@ -209,6 +209,44 @@ class Engine:
         self._chk(self.lib.xgpu_load_host_jr(self.h, _dp(x), C.byref(ss), C.c_double(qscalar), C.c_double(fscalar), _dp(rhs), _dp(jac)))
         return rhs, jac
 
+    # ---- bordered solve / multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        lib = load_library()
+        buf = (C.c_ubyte * 128)()
+        rc = lib.xgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError("xgpu_comm_unique_id failed with code %d (libnccl.so.2 missing?)" % rc)
+        return bytes(buf)
+
+    def comm_init(self, id128, rank, world):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id128))
+        self._chk(self.lib.xgpu_comm_init(self.h, buf, int(rank), int(world)))
+
+    def border_set(self, n_border):
+        self._chk(self.lib.xgpu_border_set(self.h, int(n_border)))
+
+    def border_info(self):
+        ni, ns, ng = C.c_int(), C.c_int(), C.c_longlong()
+        self._chk(self.lib.xgpu_border_info(self.h, C.byref(ni), C.byref(ns), C.byref(ng)))
+        return ni.value, ns.value, ng.value
+
+    def shared_reduce(self, d_f, d_q, d_fl, d_ql):
+        p = C.c_void_p
+        self._chk(self.lib.xgpu_shared_reduce(self.h, p(d_f), p(d_q), p(d_fl), p(d_ql)))
+
+    def border_analyze(self, d_vals):
+        rc = self.lib.xgpu_border_analyze(self.h, C.c_void_p(d_vals))
+        if rc not in (0, 2):
+            self._chk(rc)
+        return rc
+
+    def border_solve(self, d_vals, d_rhs, d_x, rhs_border_reduced=False):
+        rc = self.lib.xgpu_border_solve(self.h, C.c_void_p(d_vals), C.c_void_p(d_rhs), C.c_void_p(d_x), int(bool(rhs_border_reduced)))
+        if rc not in (0, 2, 3):
+            self._chk(rc)
+        return rc
+
     def device_buffer(self, which):
         return self.lib.xgpu_device_buffer(self.h, which)
 
@@ -245,6 +283,11 @@ class Engine:
     def set_sources(self, row, scale, stype, params7):
         a = [_i32(row), _f64(scale), _i32(stype), _f64(params7)]
         self._chk(self.lib.xgpu_sources_set(self.h, len(a[0]), _ip(a[0]), _dp(a[1]), _ip(a[2]), _dp(a[3])))
+
+    def set_pwl_table(self, tv_pairs):
+        """(time, value) pairs of all PWL sources (type 5: params = {td, offset, count, repeat, repeattime})"""
+        tv = _f64(np.asarray(tv_pairs, dtype=np.float64).reshape(-1, 2))
+        self._chk(self.lib.xgpu_sources_pwl_set(self.h, len(tv), _dp(tv)))
 
     def tran_run(self, x0, tstop, tstep, probes, delmax=0.0, max_out=200000, **kw):
         tp = TranParams(tstop=tstop, tstep=tstep, delmax=delmax, **kw)

@@ -153,6 +153,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
   cudaFree(ctx->tran_pool); cudaFree(ctx->tran_ints); cudaFreeHost(ctx->tran_pinned);
   xb::lu::free_plan(ctx->lu_dev);
+  xg_dist_free(ctx);
   for (XgLinearPart *L : {&ctx->linG, &ctx->linC}) { cudaFree(L->rows); cudaFree(L->ptr); cudaFree(L->col); cudaFree(L->pos); cudaFree(L->val); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -834,6 +835,18 @@ int lu_run(xgpu_ctx *ctx, xgpu_ctx::LuGraph &g, const void *k0, const void *k1, 
 }  // namespace
 }  // extern "C++"
 
+}  // extern "C"
+int xg_lu_refactor_async(xgpu_ctx *ctx, const double *d_vals) {
+  return lu_run(ctx, ctx->g_refactor, d_vals, nullptr, nullptr,
+                [&] { return xb::lu::launch_refactor(ctx->lu_dev, d_vals, ctx->stream); });
+}
+int xg_lu_status(xgpu_ctx *ctx, int *status) {
+  XG_CUDA(cudaMemcpyAsync(status, ctx->lu_dev.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" {
+
 int xgpu_lu_analyze(xgpu_ctx *ctx, const double *d_vals) {
   if (!ctx || !d_vals) return 100;
   if (ctx->rowptr.empty()) return fail(ctx, 112, "no CSR pattern");
@@ -900,13 +913,11 @@ int xgpu_lu_refactor(xgpu_ctx *ctx, const double *d_vals) {
   if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
   if (ctx->lu_repivot) return xgpu_lu_analyze(ctx, d_vals);      // KLU_REPIVOT=1: pivoting factorization every time
   {
-    const int rc = lu_run(ctx, ctx->g_refactor, d_vals, nullptr, nullptr,
-                          [&] { return xb::lu::launch_refactor(ctx->lu_dev, d_vals, ctx->stream); });
+    const int rc = xg_lu_refactor_async(ctx, d_vals);
     if (rc) return rc;
   }
   int status = 0;
-  XG_CUDA(cudaMemcpyAsync(&status, ctx->lu_dev.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  { const int rc = xg_lu_status(ctx, &status); if (rc) return rc; }
   if (status & 1) return fail(ctx, 2, "zero or non-finite pivot during refactorization");
   if (status & 4) return fail(ctx, 3, "a pivot of the fixed sequence fails the partial-pivoting threshold: re-analyse (re-pivot)");
   return 0;

@@ -52,6 +52,31 @@ struct XgLinearPart {
 
 struct XgSource { int row; double scale; int type; double p[7]; };
 
+// Bordered block-diagonal form of the local system and the communicator of a multi-GPU run (dist.cu).
+// Local unknown order: [interior | border]; border = unknowns shared between partitions (supply rails, source
+// branches) and/or dense nodes the caller wants out of the BTF blocks.  With world > 1 every rank holds a replica of
+// the border unknowns in the same order.
+struct XgDist {
+  int rank = 0, world = 1;
+  void *comm = nullptr;              // ncclComm_t
+  int ni = 0, ns = 0;                // interior / border unknowns of this rank (ns equal on all ranks)
+  long long n_global = 0;            // sum of ni over the ranks + ns
+  // A_is entries (interior row, border column): CSR position, row, border column index
+  int n_is = 0; int *is_pos = nullptr, *is_row = nullptr, *is_col = nullptr;
+  // A_si entries by border row (interior columns), cut into chunks of kSiChunk for the deterministic row reductions
+  int n_si = 0, n_chunks = 0; int *si_pos = nullptr, *si_col = nullptr, *chunk_row = nullptr, *chunk_begin = nullptr, *chunk_end = nullptr;
+  int *row_chunk_ptr = nullptr;      // [ns + 1] chunks of each border row
+  int *ss_pos = nullptr;             // [ns * ns] CSR position of border entry (r, c) or -1
+  double *B = nullptr;               // [ns + 1][ni] right-hand sides A_is | b_i, overwritten by A_ii^-1 (.)
+  double *partials = nullptr;        // [ns + 1][n_chunks]
+  double *red = nullptr;             // [ns][ns + 1] reduced (Schur) system, then its solution in column ns
+  double *pack = nullptr;            // small device buffer of the collectives (>= 8 ns + 64 doubles)
+  double *h_pack = nullptr;          // pinned mirror (>= 8 * world + 64 doubles)
+  std::vector<int32_t> sub_rowptr, sub_colind, sub_index;      // interior x interior sub-pattern and its positions in the CSR values
+  bool analyzed = false;
+  int reanalyses = 0;                // host re-pivots triggered inside xg_border_solve (bad or sub-threshold pivot)
+};
+
 struct xgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -89,6 +114,7 @@ struct xgpu_ctx {
   // linear devices and independent sources
   XgLinearPart linG, linC;
   std::vector<XgSource> sources;
+  std::vector<double> pwl;           // (time, value) pairs of all PWL sources (XgSource::p = {td, offset, count, repeat, repeattime})
   double *d_bsrc = nullptr;          // staging for source values
 
   // sparse LU
@@ -110,6 +136,18 @@ struct xgpu_ctx {
   double *tran_pool = nullptr; size_t tran_pool_len = 0;
   int *tran_ints = nullptr; size_t tran_ints_len = 0;
   double *tran_pinned = nullptr;
+  XgDist *dist = nullptr;     // bordered solve / multi-GPU state (xgpu_border_set, xgpu_comm_init); null = plain single-GPU path
 };
+
+// internal entry points shared between capi.cu, sim_gpu.cu and dist.cu
+int xg_lu_refactor_async(xgpu_ctx *ctx, const double *d_vals);          // launches only; status stays on the device
+int xg_lu_status(xgpu_ctx *ctx, int *status);                           // reads the status word (synchronises)
+void xg_dist_free(xgpu_ctx *ctx);
+bool xg_dist_multi(const xgpu_ctx *ctx);                                // a communicator with more than one rank is attached
+int xg_dist_reduce_border_rows(xgpu_ctx *ctx, double *const *vecs, int nvec);
+// every rank contributes k doubles (device); the world * k gathered values arrive in ctx->dist->h_pack (host, after the
+// stream synchronisation the caller does anyway)
+int xg_dist_allgather(xgpu_ctx *ctx, const double *d_send, int k);
+int xg_border_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x, int rhs_border_reduced);
 
 int xg_fail(xgpu_ctx *c, int code, const std::string &msg);

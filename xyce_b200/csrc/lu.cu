@@ -23,6 +23,20 @@ constexpr int kSmemRows = 512;     // rows staged in shared memory per warp (4 K
 
 __device__ __forceinline__ bool bad_pivot(double p) { return p == 0.0 || !(fabs(p) <= 1.7976931348623157e308); }
 
+// a / b for the factor scaling and the triangular solves: reciprocal seed (MUFU.RCP64H) + one Newton step + quotient +
+// one residual correction -- <= 1 ulp for normal operands, a dependent chain of ~70 cycles where IEEE division is
+// ~250.  The division sits on the critical path of every column (pivot -> L column -> next column's updates), which
+// is what bounds the refactorization of chain-like blocks.  EVERY LU kernel uses this one routine, so the
+// warp-per-block, staged, batched and large-block paths stay bitwise identical to each other; zero / non-finite
+// pivots are reported separately (bad_pivot), pivots outside the normal range are not supported.
+__device__ __forceinline__ double lu_div(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(fma(-b, r, 1.0), r, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
 __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d, const double *__restrict__ A) {
   xb::pdl_wait();
   __shared__ double sx[kWarpsPerCta][kSmemRows];
@@ -69,7 +83,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_refactor_kernel(LuView d
     for (int q = lb + lane; q < le; q += 32) {
       const double c = x[d.Li[q]];
       if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) weak = true;
-      d.Lx[q] = c / pivot;
+      d.Lx[q] = lu_div(c, pivot);
     }
     __syncwarp();
   }
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) lu_solve_level_kernel(LuVie
   // backward substitution with U (pivot stored last in each column)
   for (int k = k1 - 1; k >= k0; --k) {
     const int ue = d.Up[k + 1] - 1;
-    const double yk = y[k] / d.Ux[ue];
+    const double yk = lu_div(y[k], d.Ux[ue]);
     __syncwarp();
     if (lane == 0) { y[k] = yk; xout[d.col_perm[k]] = yk; }
     for (int q = d.Up[k] + lane; q < ue; q += 32) y[d.Ui[q]] -= d.Ux[q] * yk;
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(1024) lu_refactor_staged_kernel(LuView d, cons
     for (int q = lb + lane; q < le; q += 32) {
       const double c = v.x[v.Li[q]];
       if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) weak = true;
-      v.Lx[q] = c / pivot;
+      v.Lx[q] = lu_div(c, pivot);
     }
     __syncwarp();
   }
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(1024) lu_solve_staged_kernel(LuView d, int fir
   }
   for (int k = v.nb - 1; k >= 0; --k) {                  // backward substitution, pivot stored last in the column
     const int ue = v.Up[k + 1] - 1;
-    const double yk = v.x[k] / v.Ux[ue];
+    const double yk = lu_div(v.x[k], v.Ux[ue]);
     __syncwarp();
     if (lane == 0) v.x[k] = yk;
     for (int q = v.Up[k] + lane; q < ue; q += 32) v.x[v.Ui[q]] -= v.Ux[q] * yk;
@@ -280,107 +294,162 @@ __global__ void __launch_bounds__(1024) lu_solve_staged_kernel(LuView d, int fir
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batched groups (block_big == 3, lu.h): one THREAD per block, `LB` blocks per one-warp CTA (lanes >= LB idle: the
-// work is a latency chain, not a throughput problem, so a narrow CTA that leaves room for more CTAs per SM wins).
-// The CTA keeps the factor values of its blocks in shared memory, slot-major ([slot][lane], conflict-free); every
-// lane owns its column, so there is no synchronisation inside the kernel.  The program (bundles of kBundle
-// {dst | type << 14, a, b} triples, the same for every block of the group) is read through uniform loads.
+// Batched groups (block_big == 3, lu.h): a TILE of kBundle lanes owns one block, a one-warp CTA holds LB <= 32 / kBundle
+// blocks.  The CTA keeps the factor values of its blocks in shared memory, slot-major ([slot][block], conflict-free);
+// per step every lane executes ONE operation of the current bundle on its tile's column: loads, arithmetic, store,
+// warp barrier (the next bundle may read what a neighbouring lane just wrote).  The program (kBundle 8-byte words
+// {dst | type << 14, a, b, 0} per bundle, the same for every block of the group) sits in shared memory too.
+// Per warp this is ~25 instructions per bundle instead of ~125 when one lane ran all kBundle operations.
 // ---------------------------------------------------------------------------------------------
-struct BundleWords { unsigned short w[kBundle * 3]; };
-__device__ __forceinline__ BundleWords load_bundle(const unsigned short *__restrict__ prog, int bi) {
-  BundleWords r;
-  const uint2 *p = reinterpret_cast<const uint2 *>(prog + (size_t)bi * kBundle * 3);     // 24 bytes, 8-byte aligned
-  static_assert(kBundle * 3 * sizeof(unsigned short) == 24, "bundle = 3 x 8 bytes");
-  const uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-  const unsigned v[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { r.w[2 * k] = (unsigned short)(v[k] & 0xffffu); r.w[2 * k + 1] = (unsigned short)(v[k] >> 16); }
-  return r;
+// 16-byte asynchronous copies global -> shared by the whole warp (n16 = number of 16-byte units); nothing is waited for here
+__device__ __forceinline__ void stage_async16(const void *__restrict__ src, void *dst, int n16) {
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(dst);
+  const char *g = reinterpret_cast<const char *>(src);
+  for (int i = threadIdx.x; i < n16; i += 32)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (unsigned)i * 16u), "l"(g + (size_t)i * 16) : "memory");
 }
+__device__ __forceinline__ void async_commit_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+__host__ __device__ constexpr int round16(int bytes) { return (bytes + 15) & ~15; }
 
 __global__ void __launch_bounds__(32) lu_refactor_batched_kernel(LuBatchDev g, const double *__restrict__ A, int LB, double tol,
                                                                  int check, int *status) {
   xb::pdl_wait();
-  extern __shared__ double bsm[];                 // [nu + nl][LB]
+  extern __shared__ __align__(16) unsigned char bsm_raw[];
+  // shared memory: values [nu + nl][LB] doubles | program | this CTA's A indices [na][LB] ints | slot of each A entry [na]
   const int lane = threadIdx.x;
-  if (lane >= LB) return;
-  const int j = blockIdx.x * LB + lane;
-  const bool live = j < g.nblk;
-  const int jj = live ? j : g.nblk - 1;           // padding lanes redo the last block and store nothing
   const int ns = g.nu + g.nl;
-  double *v = bsm + lane;
-  for (int s = 0; s < ns; ++s) v[s * LB] = 0.0;
-  // A -> factor slots; the index loads are coalesced (block fastest), the gathers land in neighbouring CSR rows
-  for (int e = 0; e < g.na; ++e) v[__ldg(g.a_dst + e) * LB] = A[__ldg(g.a_src + (size_t)e * g.nblk + jj)];
-  int flag = 0;
-  BundleWords nxt = load_bundle(g.rf_prog, 0);
-  for (int bi = 0; bi < g.rf_bundles; ++bi) {
-    const BundleWords cur = nxt;
-    if (bi + 1 < g.rf_bundles) nxt = load_bundle(g.rf_prog, bi + 1);
-    double d[kBundle], x[kBundle], y[kBundle];
-    int ty[kBundle], ds[kBundle];
-#pragma unroll
-    for (int k = 0; k < kBundle; ++k) {
-      ty[k] = cur.w[3 * k] >> 14; ds[k] = cur.w[3 * k] & 0x3fff;
-      d[k] = v[ds[k] * LB]; x[k] = v[cur.w[3 * k + 1] * LB]; y[k] = v[cur.w[3 * k + 2] * LB];
+  double *bsm = reinterpret_cast<double *>(bsm_raw);
+  const int off_prog = round16(ns * LB * 8), off_idx = off_prog + round16(g.rf_bundles * kBundle * 8);
+  const int off_dst = off_idx + round16(g.na * LB * 4);
+  uint2 *prog_s = reinterpret_cast<uint2 *>(bsm_raw + off_prog);
+  int *idx_s = reinterpret_cast<int *>(bsm_raw + off_idx);
+  int *dst_s = reinterpret_cast<int *>(bsm_raw + off_dst);        // [na] factor slot of each A entry (padded to 16 bytes)
+  const int j0 = blockIdx.x * LB;
+  // Staging, two memory round trips in all: (1) program and index list of this CTA (contiguous, 16-byte asynchronous
+  // copies) while the slots are zeroed; (2) A -> factor slots, one asynchronous 8-byte copy per entry straight into its
+  // slot -- every gather of the CTA in flight at once, no registers tied up.
+  const int idx_units = round16(g.na * LB * 4) / 16;
+  stage_async16(g.rf_prog, prog_s, g.rf_bundles * kBundle * 8 / 16);
+  stage_async16(g.a_src_cta + (size_t)blockIdx.x * idx_units * 4, idx_s, idx_units);
+  stage_async16(g.a_dst, dst_s, round16(g.na * 4) / 16);
+  for (int t = lane; t < ns * LB; t += 32) bsm[t] = 0.0;
+  async_commit_wait();
+  {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(bsm);
+    const int total = g.na * LB, de = 32 / LB, dl = 32 - de * LB;      // t += 32  <=>  e += de, lj += dl (with carry)
+    int e = lane / LB, lj = lane - e * LB;
+    for (int t = lane; t < total; t += 32) {
+      const int dst = dst_s[e] * LB + lj;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)dst * 8u), "l"(A + idx_s[t]) : "memory");
+      e += de; lj += dl;
+      if (lj >= LB) { lj -= LB; ++e; }
     }
-#pragma unroll
-    for (int k = 0; k < kBundle; ++k) {
-      if (ty[k] == kOpFnma) v[ds[k] * LB] = d[k] - x[k] * y[k];
-      else if (ty[k] == kOpDiv) {
-        if (check && fabs(x[k]) < tol * fabs(d[k])) flag |= 4;      // the fixed pivot no longer passes KLU's threshold test
-        v[ds[k] * LB] = d[k] / x[k];
-      } else if (ty[k] == kOpChk) {
-        if (bad_pivot(x[k])) flag |= 1;
+    async_commit_wait();
+  }
+  const int blk = lane / kBundle, sub = lane - blk * kBundle;      // tile = block, lane of the tile = operation of the bundle
+  const bool active = blk < LB;
+  double *v = bsm + (active ? blk : 0);
+  int flag = 0;
+  uint2 nxt = prog_s[sub];
+  for (int bi = 0; bi < g.rf_bundles; ++bi) {
+    const uint2 cur = nxt;
+    if (bi + 1 < g.rf_bundles) nxt = prog_s[(bi + 1) * kBundle + sub];
+    const int ty = (cur.x >> 14) & 3, ds = cur.x & 0x3fff, a = cur.x >> 16, b = cur.y & 0xffff;
+    if (active && ty != kOpNop) {
+      const double x = v[a * LB];
+      if (ty == kOpFnma) {
+        const double d = v[ds * LB], y = v[b * LB];
+        v[ds * LB] = d - x * y;
+      } else if (ty == kOpDiv) {
+        const double d = v[ds * LB];
+        if (bad_pivot(x)) flag |= 1;
+        if (check && fabs(x) < tol * fabs(d)) flag |= 4;      // the fixed pivot no longer passes KLU's threshold test
+        v[ds * LB] = lu_div(d, x);
+      } else {
+        if (bad_pivot(x)) flag |= 1;
       }
     }
+    __syncwarp();
   }
-  if (live) {
-    for (int s = 0; s < ns; ++s) g.LUx[(size_t)s * g.nblk + j] = v[s * LB];
-    if (flag) atomicOr(status, flag);
+  // write back, the whole warp again (slot-major, block fastest: coalesced)
+  {
+    const int total = ns * LB, de = 32 / LB, dl = 32 - de * LB;
+    int sl = lane / LB, lj = lane - sl * LB;
+    for (int t = lane; t < total; t += 32) {
+      if (j0 + lj < g.nblk) g.LUx[(size_t)sl * g.nblk + j0 + lj] = bsm[t];
+      sl += de; lj += dl;
+      if (lj >= LB) { lj -= LB; ++sl; }
+    }
   }
+  if (flag && active && j0 + blk < g.nblk) atomicOr(status, flag);
 }
 
 __global__ void __launch_bounds__(32) lu_solve_batched_kernel(LuBatchDev g, LuView d, int LB, double *__restrict__ xout) {
   xb::pdl_wait();
-  extern __shared__ double bsm[];                 // factor [nu + nl][LB], then y [nb][LB]
+  extern __shared__ __align__(16) double bsm[];   // factor [nu + nl][LB], y [nb][LB], the program (later: column permutation)
   const int lane = threadIdx.x;
-  if (lane >= LB) return;
-  const int j = blockIdx.x * LB + lane;
-  const bool live = j < g.nblk;
-  const int jj = live ? j : g.nblk - 1;
   const int ns = g.nu + g.nl;
-  double *v = bsm + lane, *y = bsm + (size_t)ns * LB + lane;
-  const int k0 = __ldg(g.k0 + jj);
-  // factor values: asynchronous 8-byte copies straight into shared memory (all in flight at once)
+  uint2 *prog_s = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(bsm) + round16((ns + g.nb) * LB * 8));
+  stage_async16(g.sv_prog, prog_s, g.sv_bundles * kBundle * 8 / 16);
+  // factor values and right-hand sides: asynchronous 8-byte copies straight into shared memory, issued by the whole
+  // warp (item t = slot t / LB of block t % LB -- coalesced), all in flight at once
+  const int j0 = blockIdx.x * LB;
+  const int de = 32 / LB, dl = 32 - de * LB;
   {
-    const unsigned sdst = (unsigned)__cvta_generic_to_shared(v);
-    const double *src = g.LUx + jj;
-    for (int s = 0; s < ns; ++s)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + (unsigned)(s * LB * 8)), "l"(src + (size_t)s * g.nblk) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(bsm);
+    int sl = lane / LB, lj = lane - sl * LB;
+    for (int t = lane; t < ns * LB; t += 32) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)t * 8u),
+                   "l"(g.LUx + (size_t)sl * g.nblk + min(j0 + lj, g.nblk - 1)) : "memory");
+      sl += de; lj += dl;
+      if (lj >= LB) { lj -= LB; ++sl; }
+    }
   }
-  for (int i = 0; i < g.nb; ++i) y[i * LB] = d.work[k0 + i];
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  BundleWords nxt = load_bundle(g.sv_prog, 0);
+  const int blk = lane / kBundle, sub = lane - blk * kBundle;
+  const bool active = blk < LB;
+  const int kl = __ldg(g.k0 + min(j0 + (active ? blk : 0), g.nblk - 1));      // first position of this tile's block
+  if (active) {      // right-hand side of the tile's block: its kBundle lanes share the rows
+    const unsigned ybase = (unsigned)__cvta_generic_to_shared(bsm + (size_t)ns * LB + blk);
+    for (int i = sub; i < g.nb; i += kBundle)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ybase + (unsigned)(i * LB) * 8u), "l"(d.work + kl + i) : "memory");
+  }
+  async_commit_wait();
+  const double *v = bsm + (active ? blk : 0);
+  double *y = bsm + (size_t)ns * LB + (active ? blk : 0);
+  uint2 nxt = prog_s[sub];
   for (int bi = 0; bi < g.sv_bundles; ++bi) {
-    const BundleWords cur = nxt;
-    if (bi + 1 < g.sv_bundles) nxt = load_bundle(g.sv_prog, bi + 1);
-    double dd[kBundle], x[kBundle], yy[kBundle];
-    int ty[kBundle], ds[kBundle];
-#pragma unroll
-    for (int k = 0; k < kBundle; ++k) {
-      ty[k] = cur.w[3 * k] >> 14; ds[k] = cur.w[3 * k] & 0x3fff;
-      dd[k] = y[ds[k] * LB]; x[k] = v[cur.w[3 * k + 1] * LB]; yy[k] = y[cur.w[3 * k + 2] * LB];
+    const uint2 cur = nxt;
+    if (bi + 1 < g.sv_bundles) nxt = prog_s[(bi + 1) * kBundle + sub];
+    const int ty = (cur.x >> 14) & 3, ds = cur.x & 0x3fff, a = cur.x >> 16, b = cur.y & 0xffff;
+    if (active && ty != kOpNop) {
+      const double x = v[a * LB], dd = y[ds * LB];
+      if (ty == kOpFnma) y[ds * LB] = dd - x * y[b * LB];
+      else if (ty == kOpDiv) y[ds * LB] = lu_div(dd, x);
     }
-#pragma unroll
-    for (int k = 0; k < kBundle; ++k) {
-      if (ty[k] == kOpFnma) y[ds[k] * LB] = dd[k] - x[k] * yy[k];
-      else if (ty[k] == kOpDiv) y[ds[k] * LB] = dd[k] / x[k];
-    }
+    __syncwarp();
   }
-  if (live)
-    for (int i = 0; i < g.nb; ++i) { const double yi = y[i * LB]; d.work[k0 + i] = yi; xout[d.col_perm[k0 + i]] = yi; }
+  // solution back to the work vector and, through the column permutation, to the caller's ordering; the permutation
+  // entries of the CTA's blocks are fetched (asynchronously, all at once) into the program area, which is dead now --
+  // the program needs at least as much room as they do whenever a block has an entry per row
+  int *cperm_s = reinterpret_cast<int *>(prog_s);
+  const bool staged_perm = g.nb * LB * 4 <= g.sv_bundles * kBundle * 8;
+  if (staged_perm) {
+    if (active) {
+      const unsigned cbase = (unsigned)__cvta_generic_to_shared(cperm_s + blk);
+      for (int i = sub; i < g.nb; i += kBundle)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cbase + (unsigned)(i * LB) * 4u), "l"(d.col_perm + kl + i) : "memory");
+    }
+    async_commit_wait();
+  }
+  if (active && j0 + blk < g.nblk)
+    for (int i = sub; i < g.nb; i += kBundle) {
+      const double yi = y[i * LB];
+      d.work[kl + i] = yi; xout[staged_perm ? cperm_s[i * LB + blk] : __ldg(d.col_perm + kl + i)] = yi;
+    }
 }
 
 // factor values of a batched group -> the ordinary Lx / Ux arrays (export, diagnostics)
@@ -434,7 +503,7 @@ __global__ void __launch_bounds__(256) lu_big_cols_kernel(LuView d, const double
   for (int q = lb + lane; q < le; q += 32) {
     const double c = d.Lx[q];
     if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) weak = true;
-    d.Lx[q] = c / pivot;
+    d.Lx[q] = lu_div(c, pivot);
   }
   if (weak) atomicOr(d.status, 4);
 }
@@ -455,7 +524,7 @@ __global__ void __launch_bounds__(256) lu_dense_gather_kernel(LuView d, int k) {
   if (t < le - lb) {
     const double c = d.work2[d.Li[lb + t]];
     if (d.pivot_check && fabs(pivot) < d.pivot_tol * fabs(c)) atomicOr(d.status, 4);
-    d.Lx[lb + t] = c / pivot;
+    d.Lx[lb + t] = lu_div(c, pivot);
   }
 }
 
@@ -508,7 +577,7 @@ __global__ void __launch_bounds__(256) lu_bwd_rows_kernel(LuView d, const int *_
     total = block_tree_sum(acc, sh);
   }
   if ((WARP ? lane : (int)threadIdx.x) == 0) {
-    const double yr = (y[r] - total) / d.Ux[d.Up[r + 1] - 1];
+    const double yr = lu_div(y[r] - total, d.Ux[d.Up[r + 1] - 1]);
     y[r] = yr;
     xout[d.col_perm[r]] = yr;
   }
@@ -536,7 +605,7 @@ void free_plan(LuDev &d) {
   cudaFree(d.bs_short_rows); cudaFree(d.bs_long_rows);
   cudaFree(d.row_scale); cudaFree(d.As); cudaFree(d.nz_rowpos);
   for (LuBatchDev &g : d.batch) {
-    cudaFree(g.k0); cudaFree(g.a_dst); cudaFree(g.a_src); cudaFree(g.rf_prog); cudaFree(g.sv_prog); cudaFree(g.LUx);
+    cudaFree(g.k0); cudaFree(g.a_dst); cudaFree(g.a_src_cta); cudaFree(g.rf_prog); cudaFree(g.sv_prog); cudaFree(g.LUx);
     cudaFree(g.Up0); cudaFree(g.Lp0);
   }
   const double tol = d.pivot_tol; const int chk = d.pivot_check;
@@ -613,8 +682,7 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
       if ((e = up(&g.k0, k0)) != cudaSuccess) return e;
       if ((e = up(&g.Up0, up0)) != cudaSuccess) return e;
       if ((e = up(&g.Lp0, lp0)) != cudaSuccess) return e;
-      if ((e = up(&g.a_dst, pg.a_dst)) != cudaSuccess) return e;
-      if ((e = up(&g.a_src, pg.a_src)) != cudaSuccess) return e;
+      { std::vector<int> ad(pg.a_dst); ad.resize((ad.size() + 3) / 4 * 4, 0); if ((e = up(&g.a_dst, ad)) != cudaSuccess) return e; }      // padded: copied in 16-byte units
       if ((e = up(&g.rf_prog, pg.rf_prog)) != cudaSuccess) return e;
       if ((e = up(&g.sv_prog, pg.sv_prog)) != cudaSuccess) return e;
       {   // values of the first (pivoting, host) factorization, interleaved -- a solve may follow the analysis directly
@@ -626,21 +694,35 @@ cudaError_t upload_plan(const LuPlan &p, LuDev &d) {
           }
         if ((e = up(&g.LUx, lux)) != cudaSuccess) return e;
       }
-      auto pick = [&](size_t bytes_per_block) {
-        for (int lb : {8, 16, 32}) {
-          const size_t per_cta = bytes_per_block * lb + 1024;
+      // blocks per one-warp CTA (a tile of kBundle lanes each): the work is a latency chain per warp, so the time is
+      // (number of waves) x (chain time); take the width that needs the fewest waves, and among those the widest
+      // (fewer CTAs to launch and to stage programs for: measured 53 us against 92 us at two waves)
+      auto pick = [&](size_t bytes_per_block, size_t prog_bytes) {
+        int best = 1; long long best_waves = -1;
+        for (int lb = 1; lb <= 32 / kBundle; ++lb) {
+          const size_t per_cta = bytes_per_block * lb + prog_bytes + 1024;
           if (per_cta > 227 * 1024) break;
           const long long resident = (long long)sms * std::min<long long>(32, (227 * 1024) / per_cta);
-          if ((g.nblk + lb - 1) / lb <= resident) return lb;
+          const long long ctas = (g.nblk + lb - 1) / lb, waves = (ctas + resident - 1) / resident;
+          if (best_waves < 0 || waves <= best_waves) { best_waves = waves; best = lb; }      // ties: the widest (fewest CTAs; measured)
         }
-        int lb = 32;
-        while (lb > 1 && bytes_per_block * lb + 1024 > 227 * 1024) lb >>= 1;
-        return lb;
+        return best;
       };
-      g.lanes_rf = pick((size_t)(g.nu + g.nl) * 8);
-      g.lanes_sv = pick((size_t)(g.nu + g.nl + g.nb) * 8);
-      max_rf = std::max(max_rf, (size_t)(g.nu + g.nl) * 8 * g.lanes_rf);
-      max_sv = std::max(max_sv, (size_t)(g.nu + g.nl + g.nb) * 8 * g.lanes_sv);
+      g.lanes_rf = pick((size_t)(g.nu + g.nl) * 8 + (size_t)g.na * 4, (size_t)g.rf_bundles * kBundle * 8 + (size_t)g.na * 4 + 64);
+      g.lanes_sv = pick((size_t)(g.nu + g.nl + g.nb) * 8, (size_t)g.sv_bundles * kBundle * 8 + 32);
+      g.smem_rf = round16((g.nu + g.nl) * g.lanes_rf * 8) + round16(g.rf_bundles * kBundle * 8) + round16(g.na * g.lanes_rf * 4) + round16(g.na * 4);
+      g.smem_sv = round16((g.nu + g.nl + g.nb) * g.lanes_sv * 8) + g.sv_bundles * kBundle * 8;
+      max_rf = std::max(max_rf, (size_t)g.smem_rf);
+      max_sv = std::max(max_sv, (size_t)g.smem_sv);
+      {   // A indices regrouped per CTA: [cta][entry][block of the CTA] (one contiguous, 16-byte padded chunk per CTA)
+        const int lb = g.lanes_rf, nctas = (g.nblk + lb - 1) / lb, chunk = round16(g.na * lb * 4) / 4;
+        std::vector<int> cta((size_t)nctas * chunk, 0);
+        for (int c = 0; c < nctas; ++c)
+          for (int en = 0; en < g.na; ++en)
+            for (int lj = 0; lj < lb; ++lj)
+              cta[(size_t)c * chunk + en * lb + lj] = pg.a_src[(size_t)en * g.nblk + std::min(c * lb + lj, g.nblk - 1)];
+        if ((e = up(&g.a_src_cta, cta)) != cudaSuccess) return e;
+      }
       d.batch.push_back(g);
     }
     if (max_rf > 48 * 1024 && (e = cudaFuncSetAttribute(lu_refactor_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_rf)) != cudaSuccess) return e;
@@ -680,7 +762,7 @@ int launch_refactor(const LuDev &d, const double *A, cudaStream_t s) {
   }
   for (const LuBatchDev &g : d.batch) {
     const int lb = g.lanes_rf;
-    xb::launch_pdl(lu_refactor_batched_kernel, dim3((g.nblk + lb - 1) / lb), dim3(32), (size_t)(g.nu + g.nl) * 8 * lb, s, g, A, lb,
+    xb::launch_pdl(lu_refactor_batched_kernel, dim3((g.nblk + lb - 1) / lb), dim3(32), (size_t)g.smem_rf, s, g, A, lb,
                    d.pivot_tol, d.pivot_check, d.status);
     ++launches;
   }
@@ -735,7 +817,7 @@ int launch_solve(const LuDev &d, const double *A, const double *rhs, double *x, 
     for (const LuBatchDev &g : d.batch) {
       if (g.level != l) continue;
       const int lb = g.lanes_sv;
-      xb::launch_pdl(lu_solve_batched_kernel, dim3((g.nblk + lb - 1) / lb), dim3(32), (size_t)(g.nu + g.nl + g.nb) * 8 * lb, s, g,
+      xb::launch_pdl(lu_solve_batched_kernel, dim3((g.nblk + lb - 1) / lb), dim3(32), (size_t)g.smem_sv, s, g,
                      (const LuView &)d, lb, x);
       ++launches;
     }

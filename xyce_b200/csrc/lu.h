@@ -68,16 +68,17 @@ struct LuPlan {
   // pattern, same positions of the A entries -- every ring of a ring-oscillator array, every cell of a cell array) ----
   // Such a group is factored and solved with one THREAD per block: the factor values of the group are stored
   // interleaved, slot-major with the block index fastest (coalesced), the pattern is compiled once on the host into
-  // a straight-line "elimination program" over factor slots that is the same for every block, so a warp executes it
-  // in lock step with uniform operands and no intra-warp synchronisation at all.  Independent operations are packed
-  // into bundles of kBundle (loads of a bundle first, then the arithmetic, then the stores) so that the
-  // shared-memory latency of a column chain is paid once per bundle, not once per operation.
+  // a straight-line "elimination program" over factor slots that is the same for every block.  Independent operations
+  // are packed into bundles of kBundle; a TILE of kBundle lanes owns one block and executes one bundle per step, one
+  // operation per lane (all loads of the bundle, then the arithmetic, then the stores, then a warp barrier), so the
+  // shared-memory latency of a column chain is paid once per bundle and a warp (32 / kBundle blocks) runs in lock
+  // step with uniform program words.
   struct BatchGroup {
     int nb = 0, nu = 0, nl = 0, na = 0, level = 0;      // block size, U / L entries, A entries per block, solve level
     std::vector<int> blocks;                            // block ids
     std::vector<int> a_dst;                             // [na] factor slot of the e-th A entry (U slots [0, nu), L slots [nu, nu + nl))
     std::vector<int> a_src;                             // [na][nblk] CSR value index, block fastest
-    std::vector<unsigned short> rf_prog, sv_prog;       // bundles of kBundle ops, op = {dst | type << 14, a, b}
+    std::vector<unsigned short> rf_prog, sv_prog;       // bundles of kBundle ops, op = {dst | type << 14, a, b, 0} (8 bytes)
     int rf_bundles = 0, sv_bundles = 0;
   };
   std::vector<BatchGroup> batch;
@@ -93,8 +94,11 @@ enum BatchOp { kOpFnma = 0, kOpDiv = 1, kOpChk = 2, kOpNop = 3 };
 
 // Symbolic analysis + first numeric factorization with threshold partial pivoting (KLU defaults:
 // pivot_tol = 0.001, diagonal preferred).  Returns 0 ok, 1 structurally singular, 2 numerically singular.
+// val_index (optional): the pattern given here is a SUB-pattern of a larger CSR matrix and val_index[k] is the position
+// of its k-th entry in that matrix's value array; `vals` is then the larger array, and the plan's scatter maps address
+// it directly (bordered solve: the interior block is factored straight out of the full Jacobian values).
 int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol,
-                       LuPlan &plan);
+                       LuPlan &plan, const int *val_index = nullptr);
 // batched groups on / off for the plans built from now on (option "lu_batch"; default on)
 void set_batching(bool on);
 void solve_host(const LuPlan &plan, const double *b, double *x);
@@ -139,9 +143,11 @@ struct LuView {
 };
 struct LuBatchDev {
   int nblk = 0, nb = 0, nu = 0, nl = 0, na = 0, level = 0, rf_bundles = 0, sv_bundles = 0;
-  int lanes_rf = 32, lanes_sv = 32;      // blocks per CTA (one warp; lanes beyond this idle) chosen at upload
+  int lanes_rf = 8, lanes_sv = 8;        // blocks per one-warp CTA (each owned by a tile of kBundle lanes; at most 32 / kBundle) chosen at upload
   int *k0 = nullptr;                     // [nblk] first position of each block
-  int *a_dst = nullptr, *a_src = nullptr;
+  int *a_dst = nullptr;                  // [na] factor slot of each A entry
+  int *a_src_cta = nullptr;              // CSR value indices regrouped per CTA of the refactor kernel: [cta][entry][block in CTA]
+  int smem_rf = 0, smem_sv = 0;          // dynamic shared memory of the two kernels
   unsigned short *rf_prog = nullptr, *sv_prog = nullptr;
   double *LUx = nullptr;                 // [nu + nl][nblk] factor values, block fastest
   int *Up0 = nullptr, *Lp0 = nullptr;    // [nblk] first U / L entry of each block in the ordinary factor arrays (export)

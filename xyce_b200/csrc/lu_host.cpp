@@ -259,31 +259,32 @@ namespace {
 struct BOp { int type, dst, a, b; };
 
 // Greedy list scheduling in program order.  `nres` resources; op reads r[0..nr) and read-modify-writes w.
-// Within a bundle all loads precede all stores, so an op may share a bundle with an EARLIER op that reads what it
-// writes, never precede it; ops that update the same destination stay in program order (RAW chain): summation order
-// per factor entry is exactly the left-looking order of the warp-per-block kernels.
+// A bundle is executed by kBundle lanes at once (one op each): all its loads precede all its stores, so an op may
+// share a bundle with an EARLIER op that reads what it writes, never precede it; ops that update the same destination
+// stay in program order (RAW chain): summation order per factor entry is exactly the left-looking order of the
+// warp-per-block kernels.  Bundles are TYPED (all ops of a bundle have one type: the lanes of a tile do not diverge).
 void schedule_bundles(const std::vector<BOp> &ops, int nres, const std::vector<std::vector<int>> &reads, const std::vector<int> &writes,
                       std::vector<unsigned short> &prog, int &nbundles) {
-  std::vector<int> lastW(nres, -1), lastR(nres, -1), fill;
+  std::vector<int> lastW(nres, -1), lastR(nres, -1), btype;
   std::vector<std::vector<int>> bundles;
-  size_t first_open = 0;
   for (size_t i = 0; i < ops.size(); ++i) {
     int earliest = 0;
     for (int r : reads[i]) earliest = std::max(earliest, lastW[r] + 1);
     if (writes[i] >= 0) earliest = std::max(earliest, std::max(lastW[writes[i]] + 1, lastR[writes[i]]));
-    size_t bidx = std::max<size_t>(earliest, first_open);
-    while (bidx < bundles.size() && (int)bundles[bidx].size() >= kBundle) ++bidx;
-    if (bidx >= bundles.size()) bundles.resize(bidx + 1);
+    size_t bidx = (size_t)earliest;
+    while (bidx < bundles.size() && ((int)bundles[bidx].size() >= kBundle || btype[bidx] != ops[i].type)) ++bidx;
+    if (bidx >= bundles.size()) { bundles.resize(bidx + 1); btype.resize(bidx + 1, -1); }
+    if (btype[bidx] < 0) btype[bidx] = ops[i].type;
     bundles[bidx].push_back((int)i);
-    while (first_open < bundles.size() && (int)bundles[first_open].size() >= kBundle) ++first_open;
     for (int r : reads[i]) lastR[r] = std::max(lastR[r], (int)bidx);
     if (writes[i] >= 0) lastW[writes[i]] = (int)bidx;
   }
+  // bundles left empty by the search (a later op needed a later slot) stay as no-ops
   nbundles = (int)bundles.size();
-  prog.assign((size_t)nbundles * kBundle * 3, 0);
+  prog.assign((size_t)nbundles * kBundle * 4, 0);
   for (int bi = 0; bi < nbundles; ++bi)
     for (int k = 0; k < kBundle; ++k) {
-      unsigned short *o = &prog[((size_t)bi * kBundle + k) * 3];
+      unsigned short *o = &prog[((size_t)bi * kBundle + k) * 4];      // 8 bytes per op: {dst | type << 14, a, b, 0}
       if (k < (int)bundles[bi].size()) {
         const BOp &op = ops[bundles[bi][k]];
         o[0] = (unsigned short)(op.dst | (op.type << 14)); o[1] = (unsigned short)op.a; o[2] = (unsigned short)op.b;
@@ -353,7 +354,8 @@ void build_batch_groups(LuPlan &plan, const std::vector<int> &level) {
             ops.push_back({kOpFnma, dst, lslot(t), uslot(q)}); reads.push_back({dst, lslot(t), uslot(q)}); writes.push_back(dst);
           }
         }
-        ops.push_back({kOpChk, 0, uslot(ue), 0}); reads.push_back({uslot(ue)}); writes.push_back(-1);
+        // the division also tests the pivot (zero / non-finite / below threshold); a column without L entries gets an explicit check
+        if (lb == le) { ops.push_back({kOpChk, 0, uslot(ue), 0}); reads.push_back({uslot(ue)}); writes.push_back(-1); }
         for (int q = lb; q < le; ++q) { ops.push_back({kOpDiv, lslot(q), uslot(ue), 0}); reads.push_back({lslot(q), uslot(ue)}); writes.push_back(lslot(q)); }
       }
       schedule_bundles(ops, g.nu + g.nl, reads, writes, g.rf_prog, g.rf_bundles);
@@ -590,7 +592,8 @@ static void finish_plan(LuPlan &plan, const std::vector<int> &Ap, const std::vec
 
 void set_batching(bool on) { g_batching = on; }
 
-int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol, LuPlan &plan) {
+int analyze_and_factor(int n, const int *rowptr, const int *colind, const double *vals, double pivot_tol, LuPlan &plan,
+                       const int *val_index) {
   plan = LuPlan();
   plan.n = n;
   const int nnz = rowptr[n];
@@ -602,7 +605,7 @@ int analyze_and_factor(int n, const int *rowptr, const int *colind, const double
   {
     std::vector<int> fill(Ap.begin(), Ap.end() - 1);
     for (int i = 0; i < n; ++i)
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { const int p = fill[colind[k]]++; Ai[p] = i; Aidx[p] = k; }
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) { const int p = fill[colind[k]]++; Ai[p] = i; Aidx[p] = val_index ? val_index[k] : k; }
   }
   // 1. maximum transversal: column matched to each row; Q0[i] = column placed at diagonal position i
   std::vector<int> col_of_row;
@@ -794,7 +797,7 @@ void batch_selfcheck_host(const LuPlan &p, const double *vals, double *out) {
       for (int bi = 0; bi < g.rf_bundles; ++bi) {
         double d[kBundle], x[kBundle], y[kBundle]; int ty[kBundle], ds[kBundle];
         for (int k = 0; k < kBundle; ++k) {
-          const unsigned short *o = &g.rf_prog[((size_t)bi * kBundle + k) * 3];
+          const unsigned short *o = &g.rf_prog[((size_t)bi * kBundle + k) * 4];
           ty[k] = o[0] >> 14; ds[k] = o[0] & 0x3fff; d[k] = v[ds[k]]; x[k] = v[o[1]]; y[k] = v[o[2]];
         }
         for (int k = 0; k < kBundle; ++k) {
@@ -826,7 +829,7 @@ void batch_selfcheck_host(const LuPlan &p, const double *vals, double *out) {
       for (int bi = 0; bi < g.sv_bundles; ++bi) {
         double d[kBundle], xx[kBundle], yy[kBundle]; int ty[kBundle], ds[kBundle];
         for (int k = 0; k < kBundle; ++k) {
-          const unsigned short *o = &g.sv_prog[((size_t)bi * kBundle + k) * 3];
+          const unsigned short *o = &g.sv_prog[((size_t)bi * kBundle + k) * 4];
           ty[k] = o[0] >> 14; ds[k] = o[0] & 0x3fff; d[k] = y[ds[k]]; xx[k] = v[o[1]]; yy[k] = y[o[2]];
         }
         for (int k = 0; k < kBundle; ++k) {

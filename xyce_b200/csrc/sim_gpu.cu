@@ -81,10 +81,30 @@ struct GpuBackend {
   void scale(int d, double a) { vec::axpby(v[d], a, v[d], 0.0, v[d], n_, s); ++ctx->launches; }
   void axpby(int d, double a, int x, double b, int y) { vec::axpby(v[d], a, v[x], b, v[y], n_, s); ++ctx->launches; }
   void axpy(int d, double a, int x) { vec::axpby(v[d], 1.0, v[d], a, v[x], n_, s); ++ctx->launches; }
-  double norm2(int x) { ctx->launches += 2; return std::sqrt(vec::reduce(vec::kSumSq, v[x], nullptr, n_, scratch, s)); }
-  double norm_inf(int x) { ctx->launches += 2; return vec::reduce(vec::kMaxAbs, v[x], nullptr, n_, scratch, s); }
-  double wmax_norm(int x, int w) { ctx->launches += 2; return vec::reduce(vec::kWMaxAbs, v[x], v[w], n_, scratch, s); }
-  double wrms_norm(int x, int w) { ctx->launches += 2; return std::sqrt(vec::reduce(vec::kWSumSq, v[x], v[w], n_, scratch, s) / n_); }
+  // Reductions over ALL unknowns of the circuit.  One GPU: over the local vector.  Several ranks: every rank reduces
+  // its interior part and (identically) the replicated border part; the interior parts travel in one small all-gather
+  // and are combined in rank order, so every rank computes bitwise the same number and takes the same decisions.
+  bool multi() const { return xg_dist_multi(ctx); }
+  double dreduce(vec::Reduce mode, const double *x, const double *w) {
+    ctx->launches += 2;
+    if (!multi()) return vec::reduce(mode, x, w, n_, scratch, s);
+    const XgDist *d = ctx->dist;
+    vec::reduce_dev(mode, x, w, d->ni, scratch, s);
+    vec::reduce_dev(mode, x + d->ni, w ? w + d->ni : nullptr, d->ns, scratch + 2048, s);
+    ctx->launches += 2;
+    xg_dist_allgather(ctx, scratch, 1);
+    cudaMemcpyAsync(h_norms + 4, scratch + 2048, sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    const bool is_max = (mode == vec::kMaxAbs || mode == vec::kWMaxAbs);
+    double acc = h_norms[4];
+    for (int r = 0; r < d->world; ++r) acc = is_max ? ((acc != acc || d->h_pack[r] != d->h_pack[r]) ? acc + d->h_pack[r] : std::max(acc, d->h_pack[r])) : acc + d->h_pack[r];
+    return acc;
+  }
+  double n_global() const { return (ctx->dist && multi()) ? (double)ctx->dist->n_global : (double)n_; }
+  double norm2(int x) { return std::sqrt(dreduce(vec::kSumSq, v[x], nullptr)); }
+  double norm_inf(int x) { return dreduce(vec::kMaxAbs, v[x], nullptr); }
+  double wmax_norm(int x, int w) { return dreduce(vec::kWMaxAbs, v[x], v[w]); }
+  double wrms_norm(int x, int w) { return std::sqrt(dreduce(vec::kWSumSq, v[x], v[w]) / n_global()); }
   void sol_weights(int d, double rel, double ab, int a, int b) { vec::sol_weights(v[d], rel, ab, v[a], v[b], n_, s); ++ctx->launches; }
   void abs_weights(int d, double rel, double ab, int a) { vec::abs_weights(v[d], rel, ab, v[a], n_, s); ++ctx->launches; }
 
@@ -98,6 +118,9 @@ struct GpuBackend {
     vec::spmv_add(G.nrows, G.rows, G.ptr, G.col, G.val, v[sim::vNextSol], v[sim::vF], s);
     vec::spmv_add(C.nrows, C.rows, C.ptr, C.col, C.val, v[sim::vNextSol], v[sim::vQ], s);
     ctx->launches += (G.nrows > 0) + (C.nrows > 0);
+    // several ranks: the border rows hold partial sums -- add them up over the ranks (the reference's reverse export
+    // with Add, N_LOA_CktLoader.C:816-829); the sources on border rows are replicated, B needs no reduction
+    if (multi()) { double *vv[4] = {v[sim::vF], v[sim::vQ], v[sim::vFlim], v[sim::vQlim]}; rc |= xg_dist_reduce_border_rows(ctx, vv, 4); }
     // independent sources evaluated on the host (DeviceMgr::updateSources), B assembled on the device
     vec::fill(v[sim::vB], 0.0, n_, s); ++ctx->launches;
     const int ns = (int)ctx->sources.size();
@@ -105,14 +128,14 @@ struct GpuBackend {
       SrcVals sv; sv.n = ns;
       for (int k = 0; k < ns; ++k) {
         const XgSource &q = ctx->sources[k];
-        sv.rows[k] = q.row; sv.vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time);
+        sv.rows[k] = q.row; sv.vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time, ctx->pwl.data(), fl.bpTol);
       }
       xb::launch_pdl(set_sources_byval_kernel, dim3(1), dim3(32), 0, s, v[sim::vB], sv); ++ctx->launches;
     } else if (ns > 0) {
       std::vector<double> vals(ns);
       for (int k = 0; k < ns; ++k) {
         const XgSource &q = ctx->sources[k];
-        vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time);
+        vals[k] = q.scale * xb::sim::source_value(q.type, q.p, time, ctx->pwl.data(), fl.bpTol);
       }
       cudaMemcpyAsync(d_src_vals, vals.data(), ns * sizeof(double), cudaMemcpyHostToDevice, s);
       cudaStreamSynchronize(s);     // vals is a stack-lifetime buffer
@@ -132,6 +155,17 @@ struct GpuBackend {
 
   int solve() {
     int rc;
+    if (ctx->dist && (ctx->dist->ns > 0 || multi())) {      // bordered form: interior LU per rank + replicated border system
+      if (!ctx->dist->analyzed) {
+        rc = xgpu_border_analyze(ctx, J); ++lu_analyses;
+        if (rc != 0 && rc != 2) { vec::fill(v[sim::vDX], 0.0, n_, s); return rc; }
+      }
+      const int before = ctx->dist->reanalyses;
+      rc = xg_border_solve(ctx, J, v[sim::vRHS], v[sim::vDX], multi() ? 1 : 0); ++lu_refactors;
+      lu_analyses += ctx->dist->reanalyses - before;
+      if (rc != 0) vec::fill(v[sim::vDX], 0.0, n_, s);
+      return rc;
+    }
     if (!lu_analyzed) { rc = xgpu_lu_analyze(ctx, J); lu_analyzed = (rc == 0 || rc == 2); ++lu_analyses; }
     else {
       rc = xgpu_lu_refactor(ctx, J); ++lu_refactors;
@@ -139,6 +173,16 @@ struct GpuBackend {
     }
     if (rc != 0) { vec::fill(v[sim::vDX], 0.0, n_, s); return rc; }
     return xgpu_lu_solve(ctx, J, v[sim::vRHS], v[sim::vDX]);
+  }
+
+  // Loader::getBreakPoints / getMaxTimeStepSize over the independent sources (host side, like DeviceMgr)
+  void breakpoints(double t, std::vector<double> &out) {
+    for (const XgSource &q : ctx->sources) xb::sim::source_breakpoints(q.type, q.p, ctx->pwl.data(), t, out);
+  }
+  double max_source_step(double t) {
+    double m = 1.0e99;
+    for (const XgSource &q : ctx->sources) { const double v = xb::sim::source_max_step(q.type, q.p, t); if (v > 0.0) m = std::min(m, v); }
+    return m;
   }
 
   bool all_devices_converged() {
@@ -161,6 +205,33 @@ struct GpuBackend {
     bool overflow = false;
     for (auto &g : ctx->groups) { if (a.nflag_arrays < 8) { a.flags[a.nflag_arrays] = g.d_orig; a.flag_n[a.nflag_arrays++] = g.n; } else overflow = true; }
     for (auto &g : ctx->sgroups) { if (a.nflag_arrays < 8) { a.flags[a.nflag_arrays] = g.d_orig; a.flag_n[a.nflag_arrays++] = g.n; } else overflow = true; }
+    if (multi()) {
+      // interior rows (with the device flags) and the replicated border rows separately; the interior results of all
+      // ranks arrive in one all-gather (norm parts + convergence flag: DeviceMgr::allDevicesConverged's reduction)
+      const XgDist *d = ctx->dist;
+      vec::ResidualArgs ai = a, ab = a;
+      ai.n = d->ni;
+      ab.n = d->ns; ab.nflag_arrays = 0;
+      ab.rhs += d->ni; ab.q += d->ni; ab.qh0 += d->ni; ab.qh1 += d->ni; ab.f += d->ni; ab.b += d->ni; ab.qh2 += d->ni;
+      ab.qlim += d->ni; ab.flim += d->ni; ab.dx += d->ni; ab.w += d->ni;
+      vec::residual_norms(ai, scratch, scratch + 4 * 1024, s);
+      vec::residual_norms(ab, scratch, scratch + 4 * 1024 + 8, s); ctx->launches += 4;
+      xg_dist_allgather(ctx, scratch + 4 * 1024, 4);
+      cudaMemcpyAsync(h_norms, scratch + 4 * 1024 + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
+      const auto w0 = std::chrono::steady_clock::now();
+      cudaStreamSynchronize(s);
+      max_wait_s = std::max(max_wait_s, std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());
+      double s2 = h_norms[0], mx = h_norms[1], wm = h_norms[2], ok = 1.0;
+      for (int r = 0; r < d->world; ++r) {
+        const double *p = d->h_pack + 4 * r;
+        s2 += p[0];
+        mx = (mx != mx || p[1] != p[1]) ? mx + p[1] : std::max(mx, p[1]);
+        wm = (wm != wm || p[2] != p[2]) ? wm + p[2] : std::max(wm, p[2]);
+        ok = std::min(ok, p[3]);
+      }
+      out.rhs_norm2 = std::sqrt(s2); out.rhs_norm_inf = mx; out.dx_wmax = wm; out.devices_converged = ok != 0.0;
+      return;
+    }
     vec::residual_norms(a, scratch, scratch + 4 * 1024, s); ctx->launches += 2;
     cudaMemcpyAsync(h_norms, scratch + 4 * 1024, 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
     const auto w0 = std::chrono::steady_clock::now();
@@ -237,6 +308,25 @@ int xgpu_sources_set(xgpu_ctx *ctx, int ns, const int32_t *row, const double *sc
     std::memcpy(q.p, params7 + 7 * (size_t)k, 7 * sizeof(double));
     ctx->sources.push_back(q);
   }
+  return 0;
+}
+
+// host-only views of the source routines the transient driver uses (no GPU, no context): CPU-only CI pins them on
+// values worked from the reference's formulas
+double xgpu_source_value(int type, const double *params7, const double *pwl_tv_pairs, double t, double bp_tol) {
+  return xb::sim::source_value(type, params7, t, pwl_tv_pairs, bp_tol);
+}
+int xgpu_source_breakpoints(int type, const double *params7, const double *pwl_tv_pairs, double t, int max_out, double *out) {
+  std::vector<double> v;
+  xb::sim::source_breakpoints(type, params7, pwl_tv_pairs, t, v);
+  for (int i = 0; i < (int)v.size() && i < max_out; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+double xgpu_source_max_step(int type, const double *params7, double t) { return xb::sim::source_max_step(type, params7, t); }
+
+int xgpu_sources_pwl_set(xgpu_ctx *ctx, int n_points, const double *tv_pairs) {
+  if (!ctx || n_points < 0 || (n_points > 0 && !tv_pairs)) return 1;
+  ctx->pwl.assign(tv_pairs, tv_pairs + 2 * (size_t)n_points);
   return 0;
 }
 

@@ -35,16 +35,24 @@ enum Vec {
   vXh0, vXh1, vXh2, vQh0, vQh1, vQh2, vNewtCorr, vQNewtCorr, vTmp, kNumVec
 };
 
-// SPICE PULSE(v1 v2 td tr tf pw per) (PulseData, src/DeviceModelPKG/Core/N_DEV_SourceData.C); no breakpoints.
-inline double pulse_value(const double *p, double t) {
-  const double v1 = p[0], v2 = p[1], td = p[2], tr = p[3], tf = p[4], pw = p[5], per = p[6];
-  double tt = t - td;
-  if (tt <= 0.0) return v1;
-  if (per > 0.0) tt = std::fmod(tt, per);
-  if (tt < tr) return v1 + (v2 - v1) * tt / tr;
-  if (tt < tr + pw) return v2;
-  if (tt < tr + pw + tf) return v2 + (v1 - v2) * (tt - tr - pw) / tf;
-  return v1;
+// ---- independent-source waveforms (src/DeviceModelPKG/Core/N_DEV_SourceData.C) ----
+// type 0 DC          p = {v}
+//      1 PULSE       p = {v1, v2, td, tr, tf, pw, per}            PulseData::updateSource :1168-1248, getBreakPoints :1442-1500
+//      2 SIN         p = {v0, va, freq, td, theta, phase_deg}     SinData::updateSource :475-496
+//      3 EXP         p = {v1, v2, td1, tau1, td2, tau2}           ExpData::updateSource :811-835
+//      4 SFFM        p = {v0, va, fc, mdi, fs}                    SFFMData::updateSource :2908-2922
+//      5 PWL         p = {td, offset, count, repeat, repeattime}; the (time, value) pairs sit at pwl[2 offset ..)
+//                                                                 PWLinData::updateSource :1770-1886, getBreakPoints :2044-2110
+// bpTol = the break-point tolerance of the step control (2 minTimeStep, N_TIA_StepErrorControl.C:756): the PULSE corner
+// tests are tolerant to it exactly as the reference's are.
+inline double pulse_value(const double *p, double t, double bpTol = 0.0) {
+  const double V1 = p[0], V2 = p[1], TD = p[2], TR = p[3], TF = p[4], PW = p[5], PER = p[6];
+  double time = t - TD;
+  if (time > PER && PER != 0.0) time -= PER * std::floor(time / PER);
+  if (time <= 0 || (time > (TR + PW + TF) && (std::fabs(time - (TR + PW + TF)) > bpTol))) return V1;
+  if ((time > TR && std::fabs(time - TR) > bpTol) && (time < (TR + PW) || std::fabs(time - (TR + PW)) < bpTol)) return V2;
+  if (time > 0 && (time < TR || std::fabs(time - TR) < bpTol)) return TR != 0.0 ? V1 + (V2 - V1) * time / TR : V1;
+  return TF != 0.0 ? V2 + (V1 - V2) * (time - (TR + PW)) / TF : V2;
 }
 
 // SPICE SIN(v0 va freq td theta phase_deg) (SinData, N_DEV_SourceData.C)
@@ -54,8 +62,91 @@ inline double sin_value(const double *p, double t) {
   if (t < td) return v0 + va * std::sin(two_pi * ph / 360.0);
   return v0 + va * std::sin(two_pi * (f * (t - td) + ph / 360.0)) * std::exp(-(t - td) * theta);
 }
-inline double source_value(int type, const double *p, double t) {
-  return type == 1 ? pulse_value(p, t) : (type == 2 ? sin_value(p, t) : p[0]);
+inline double exp_value(const double *p, double t) {
+  const double V1 = p[0], V2 = p[1], TD1 = p[2], TAU1 = p[3], TD2 = p[4], TAU2 = p[5];
+  if (t <= TD1) return V1;
+  if (t <= TD2) return V1 + (V2 - V1) * (1 - std::exp(-(t - TD1) / TAU1));
+  return V1 + (V2 - V1) * (1 - std::exp(-(t - TD1) / TAU1)) + (V1 - V2) * (1 - std::exp(-(t - TD2) / TAU2));
+}
+inline double sffm_value(const double *p, double t) {
+  const double mpi = 3.14159265358979323846;
+  return p[0] + p[1] * std::sin((2 * mpi * p[2] * t) + p[3] * std::sin(2 * mpi * p[4] * t));
+}
+inline double pwl_value(const double *p, const double *pwl, double t) {
+  const double TD = p[0];
+  const int NUM = (int)p[2];
+  const bool REPEAT = p[3] != 0.0;
+  const double REPEATTIME = p[4];
+  const double *tv = pwl + 2 * (size_t)p[1];
+  if (!(t >= TD) || NUM <= 0) return 0.0;
+  double time = t - TD, time1, time2, voltage1, voltage2;
+  int loc = 0;
+  if (time <= tv[2 * (NUM - 1)]) {
+    for (int i = 0; i < NUM; ++i) if (time < tv[2 * i]) { loc = i; break; }
+    if (loc == 0) { time1 = 0.0; voltage1 = 0.0; } else { time1 = tv[2 * (loc - 1)]; voltage1 = tv[2 * (loc - 1) + 1]; }
+    time2 = tv[2 * loc]; voltage2 = tv[2 * loc + 1];
+  } else if (!REPEAT) {
+    time1 = 0.0; time2 = 1.0; voltage1 = voltage2 = tv[2 * (NUM - 1) + 1];
+  } else {
+    const double looptime = tv[2 * (NUM - 1)] - REPEATTIME;
+    time -= tv[2 * (NUM - 1)];
+    time -= looptime * std::floor(time / looptime);
+    time += REPEATTIME;
+    for (int i = 0; i < NUM; ++i) if (time < tv[2 * i]) { loc = i; break; }
+    if (time == REPEATTIME) { time1 = 0.0; time2 = 1.0; voltage1 = voltage2 = tv[2 * (NUM - 1) + 1]; }
+    else {
+      if (loc == 0) { time1 = REPEATTIME; voltage1 = tv[2 * (NUM - 1) + 1]; } else { time1 = tv[2 * (loc - 1)]; voltage1 = tv[2 * (loc - 1) + 1]; }
+      time2 = tv[2 * loc]; voltage2 = tv[2 * loc + 1];
+    }
+  }
+  if (time1 == time2) return voltage2;
+  const double length = time2 - time1;
+  double v = (time2 - time) * voltage1 / length;
+  v += (-time1 + time) * voltage2 / length;
+  return v;
+}
+inline double source_value(int type, const double *p, double t, const double *pwl = nullptr, double bpTol = 0.0) {
+  switch (type) {
+    case 1: return pulse_value(p, t, bpTol);
+    case 2: return sin_value(p, t);
+    case 3: return exp_value(p, t);
+    case 4: return sffm_value(p, t);
+    case 5: return pwl ? pwl_value(p, pwl, t) : 0.0;
+    default: return p[0];
+  }
+}
+// Break points a source announces at circuit time t (Loader::getBreakPoints -> SourceData::getBreakPoints): the corners
+// of the current and the next PULSE period, the PWL points (the current and the next repetition when it repeats).
+inline void source_breakpoints(int type, const double *p, const double *pwl, double t, std::vector<double> &out) {
+  if (type == 1) {
+    const double TD = p[2], TR = p[3], TF = p[4], PW = p[5], PER = p[6];
+    double time = t - TD, basetime = 0.0;
+    if (time >= PER && PER != 0.0) basetime = PER * (double)(int)std::floor(time / PER);
+    out.push_back(basetime + TD); out.push_back(basetime + TD + TR); out.push_back(basetime + TD + TR + PW); out.push_back(basetime + TD + TR + PW + TF);
+    if (PER != 0.0) {
+      out.push_back(basetime + TD + PER); out.push_back(basetime + TD + PER + TR); out.push_back(basetime + TD + PER + TR + PW);
+      out.push_back(basetime + TD + PER + TR + PW + TF); out.push_back(basetime + TD + PER + PER);
+    }
+  } else if (type == 5 && pwl) {
+    const double TD = p[0], REPEATTIME = p[4];
+    const int NUM = (int)p[2];
+    const double *tv = pwl + 2 * (size_t)p[1];
+    const double time = t - TD;
+    if (NUM <= 0) return;
+    if (p[3] != 0.0 && time >= tv[2 * (NUM - 1)]) {
+      const double looptime = tv[2 * (NUM - 1)] - REPEATTIME;
+      const double loopBaseTime = looptime * (1.0 + std::floor((time - tv[2 * (NUM - 1)]) / looptime));
+      for (int i = 0; i < NUM; ++i) if (tv[2 * i] >= REPEATTIME) out.push_back(tv[2 * i] + loopBaseTime + TD);
+    } else {
+      for (int i = 0; i < NUM; ++i) out.push_back(tv[2 * i] + TD);
+    }
+  }
+}
+// SourceData::getMaxTimeStepSize (:242, PulseData :1518-1537): a PULSE source caps the step at a tenth of its period
+// (of its delay while still in the delay); everything else imposes nothing.  Values <= 0 are ignored by the caller.
+inline double source_max_step(int type, const double *p, double t) {
+  if (type == 1) return t < p[2] ? 0.1 * p[2] : 0.1 * p[6];
+  return 1.0e99;
 }
 
 struct TranParams {
@@ -87,6 +178,7 @@ struct TranStats {
   int accepted = 0, rejected = 0, newton_total = 0, jacobian_loads = 0, residual_loads = 0, linear_solves = 0;
   int failed = 0;
   int dcop_newton = 0, dcop_status = 0;
+  int breakpoints = 0;      // accepted steps that landed on a source break point
 };
 
 // Backend concept:
@@ -106,6 +198,8 @@ struct TranStats {
 //        element by element in the operation order of the vector-update sequence it replaces; then ||RHS||_2,
 //        ||RHS||_inf, max |vDX / vSolWt| and the AND of the devices' convergence flags
 //   bool limiter_active();
+//   void breakpoints(double t, std::vector<double> &out);   break points the sources announce at time t
+//   double max_source_step(double t);                        smallest step cap of the sources (<= 0: none)
 //   void accept_state();                                               curr state/store <- next
 //   void record(double t);                                             sample probes
 // everything DampedNewton::converged_ looks at after one residual evaluation, fetched in one go
@@ -120,6 +214,7 @@ struct ResidualForm {
 struct Flags {
   int dcop = 0, tranop = 0, transient = 1, initTran = 0, newtonIter = 0, initJct = 0, initFix = 0;
   double currTimeStep = 0;
+  double bpTol = 0;       // break-point tolerance, for the sources' corner tests
 };
 
 template <class Backend>
@@ -133,10 +228,12 @@ class TransientDriver {
   int run() {
     const double machEps = 2.220446049250313e-16;
     // --- StepErrorControl state (N_TIA_StepErrorControl.C:100-170 defaults) ---
-    initialTime = 0.0; currentTime = 0.0; stopTime = P.tstop;
+    initialTime = 0.0; currentTime = 0.0; finalTime = P.tstop; stopTime = finalTime;
     startingTimeStep = P.tstep;
-    maxTimeStep = (P.delmax > 0.0) ? P.delmax : 0.1 * (stopTime - initialTime);
-    minTimeStep = (stopTime - initialTime) * 4.0 * machEps;
+    minTimeStep = (finalTime - initialTime) * 4.0 * machEps;
+    bpTol = 2.0 * minTimeStep;                      // StepErrorControl::updateBreakPoints (:756)
+    update_max_time_step();
+    update_stop_time();
     beginningIntegration = true; stepAttemptStatus = true; stepNumber = 0; iNumCalls = 0;
     nef = 0;
     if (P.dcop) {      // Transient::doInit: DC operating point, then the solution becomes the current one
@@ -148,16 +245,16 @@ class TransientDriver {
       iNumCalls = 0;
     }
     // initial load: Q, F, B at x(0)
-    Flags fl; fl.initTran = 1; fl.newtonIter = 0; fl.currTimeStep = startingTimeStep;
+    Flags fl; fl.initTran = 1; fl.newtonIter = 0; fl.currTimeStep = startingTimeStep; fl.bpTol = bpTol;
     B.load_rhs(fl, 0.0); ++stats.residual_loads;
     set_error_weights();
     B.fill(vQh1, 0.0);
     initialize_integrator();          // Transient::doInit
     B.record(0.0);
-    while (!(currentTime >= stopTime - minTimeStep)) {
+    while (!(currentTime >= finalTime - minTimeStep)) {
       if ((int)steps.size() >= P.maxSteps) return 3;
       if (replay() && replayIdx_ >= P.replay_h.size()) break;
-      if (beginningIntegration && stepAttemptStatus) initialize_integrator();
+      if (beginningIntegration && stepAttemptStatus) { update_max_time_step(); initialize_integrator(); }
       if (replay() && !beginningIntegration) {      // the recorded step instead of the one completeStep selected
         currentTimeStep = P.replay_h[replayIdx_];
         currentOrder = P.replay_order[replayIdx_];
@@ -197,7 +294,15 @@ class TransientDriver {
         B.copy(vCurrSol, vNextSol);
         B.accept_state();
         ++stepNumber; ++stats.accepted;
-        beginningIntegration = false;
+        // a step that lands on a break point (not the final time) restarts the integration there: order 1, fresh
+        // initial step, no LTE test on the first step (Transient::doHandlePredictor / processSuccessfulStep,
+        // N_ANP_Transient.C:1900-1948)
+        if (std::fabs(currentTime - stopTime) <= bpTol && std::fabs(currentTime - finalTime) > bpTol) {
+          beginningIntegration = true; ++stats.breakpoints;
+          update_stop_time();
+        } else {
+          beginningIntegration = false;
+        }
         set_error_weights();
         B.record(currentTime);
       } else {
@@ -217,6 +322,25 @@ class TransientDriver {
   double initialTime, currentTime, nextTime, stopTime, lastTime;
   double currentTimeStep, lastTimeStep, currentTimeStepRatio, currentTimeStepSum, savedTimeStep = 0;
   double startingTimeStep, minTimeStep, maxTimeStep;
+  double finalTime = 0.0, bpTol = 0.0;
+  std::vector<double> bps_;
+
+  // StepErrorControl::updateMaxTimeStep (:879-940): DELMAX or a tenth of the run, capped by the sources' own limits
+  void update_max_time_step() {
+    maxTimeStep = (P.delmax > 0.0) ? P.delmax : 0.1 * (finalTime - initialTime);
+    const double maxDevStep = B.max_source_step(currentTime);
+    if (maxDevStep > 0.0) maxTimeStep = std::min(maxTimeStep, maxDevStep);
+  }
+  // StepErrorControl::updateBreakPoints + updateStopTime (:742-850, :370-420): the stop time is the first break point
+  // after the current time, or the final time
+  void update_stop_time() {
+    bps_.clear();
+    B.breakpoints(currentTime, bps_);
+    std::sort(bps_.begin(), bps_.end());
+    stopTime = finalTime;
+    for (double b : bps_) if (b > currentTime + bpTol && b < finalTime) { stopTime = b; break; }
+  }
+
   double psi[3] = {0, 0, 0}, beta[3] = {1, 0, 0}, alpha[3] = {1, -1, 0}, alphas = -1.0, ck = 1.0, estOverTol = 0.0;
   bool gear() const { return P.method == 8; }
   bool replay() const { return !P.replay_h.empty(); }
@@ -338,6 +462,7 @@ class TransientDriver {
     Flags fl;
     if (dc) { fl.dcop = 1; fl.tranop = 1; fl.initJct = 1; fl.currTimeStep = 0.0; }
     else { fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep; }
+    fl.bpTol = bpTol;
     const int maxNewtonStep = dc ? P.dcMaxNewtonStep : P.maxNewtonStep;
     const double deltaXTol = dc ? P.dcDeltaXTol : P.deltaXTol, RHSTol = dc ? P.dcRHSTol : P.RHSTol;
     const double relTol = dc ? P.dcRelTol : P.relTol, absTol = dc ? P.dcAbsTol : P.absTol;

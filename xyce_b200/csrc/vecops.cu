@@ -62,10 +62,14 @@ __global__ void __launch_bounds__(256) reduce_final_k(double *part, int m) {
   if (threadIdx.x == 0) part[0] = sh[0];
 }
 template <int MODE>
-double reduce_t(const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
+void reduce_dev_t(const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
   const int blocks = n < 256 * 1024 ? (n + 255) / 256 : 1024;
   xb::launch_pdl(reduce_k<MODE>, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, s, x, w, n, scratch);
   xb::launch_pdl(reduce_final_k<MODE>, dim3(1), dim3(256), 0, s, scratch, blocks > 0 ? blocks : 1);
+}
+template <int MODE>
+double reduce_t(const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
+  reduce_dev_t<MODE>(x, w, n, scratch, s);
   double h = 0.0;
   cudaMemcpyAsync(&h, scratch, sizeof(double), cudaMemcpyDeviceToHost, s);
   cudaStreamSynchronize(s);
@@ -180,6 +184,14 @@ double reduce(Reduce mode, const double *x, const double *w, int n, double *scra
     case kMaxAbs: return reduce_t<kMaxAbs>(x, w, n, scratch, s);
     case kWMaxAbs: return reduce_t<kWMaxAbs>(x, w, n, scratch, s);
     default: return reduce_t<kWSumSq>(x, w, n, scratch, s);
+  }
+}
+void reduce_dev(Reduce mode, const double *x, const double *w, int n, double *scratch, cudaStream_t s) {
+  switch (mode) {
+    case kSumSq: reduce_dev_t<kSumSq>(x, w, n, scratch, s); break;
+    case kMaxAbs: reduce_dev_t<kMaxAbs>(x, w, n, scratch, s); break;
+    case kWMaxAbs: reduce_dev_t<kWMaxAbs>(x, w, n, scratch, s); break;
+    default: reduce_dev_t<kWSumSq>(x, w, n, scratch, s); break;
   }
 }
 void residual_norms(const ResidualArgs &a, double *scratch, double *out4, cudaStream_t s) {

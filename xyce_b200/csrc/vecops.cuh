@@ -12,6 +12,9 @@ void abs_weights(double *dst, double rel, double abs, const double *a, int n, cu
 enum Reduce { kSumSq = 0, kMaxAbs = 1, kWMaxAbs = 2, kWSumSq = 3 };
 // returns the reduced scalar on the host (synchronises the stream); scratch: >= 1024 doubles of device memory
 double reduce(Reduce mode, const double *x, const double *w, int n, double *scratch, cudaStream_t s);
+// same reduction, result left in scratch[0] on the device (no copy, no synchronisation): multi-GPU norms combine the
+// ranks' parts first
+void reduce_dev(Reduce mode, const double *x, const double *w, int n, double *scratch, cudaStream_t s);
 // Newton residual + everything the convergence test reads, two launches and no host round trip of their own:
 //   form 0: rhs = -[(q - qh0) inv_h + fs f + (-fs) b (+ 0.5 qh2)] (+ qlim_coef qlim + fs flim)    (operation order of the
 //   axpby sequence of OneStep::obtainResidual, so results are bit-identical to it)

@@ -91,9 +91,11 @@ def partition_instances(inst_nodes, n_unknowns, world, weights=None, global_degr
     return owner
 
 
-def classify_unknowns(inst_nodes, inst_owner, n_unknowns, world, always_shared=()):
+def classify_unknowns(inst_nodes, inst_owner, n_unknowns, world, always_shared=(), linear_pairs=None):
     """inst_nodes: [n_inst, k] global unknown ids (-1 = ground) touched by each instance; inst_owner: rank of
-    each instance.  Returns owner[n_unknowns]: rank that touches the unknown exclusively, or -1 if shared."""
+    each instance.  Returns owner[n_unknowns]: rank that touches the unknown exclusively, or -1 if shared.
+    linear_pairs = (rows, cols) of the linear-device stamps: a linear device whose two unknowns are interior to
+    DIFFERENT ranks couples them across the cut, so both become shared."""
     owner = np.full(n_unknowns, -2, dtype=np.int64)       # -2 untouched
     for r in range(world):
         nodes = np.unique(inst_nodes[inst_owner == r])
@@ -103,6 +105,12 @@ def classify_unknowns(inst_nodes, inst_owner, n_unknowns, world, always_shared=(
     for s in always_shared:
         owner[s] = -1
     owner[owner == -2] = -1       # unknowns no instance touches (e.g. source branches) are replicated
+    if linear_pairs is not None:
+        r, c = np.asarray(linear_pairs[0]), np.asarray(linear_pairs[1])
+        ok = (r >= 0) & (c >= 0)
+        r, c = r[ok], c[ok]
+        cut = (owner[r] >= 0) & (owner[c] >= 0) & (owner[r] != owner[c])
+        owner[r[cut]] = -1; owner[c[cut]] = -1
     return owner
 
 
@@ -129,12 +137,14 @@ def partition_ring_array(w, world, rank):
 
 def partition_workload(w, world, rank, inst_owner=None):
     """This rank's part of a workload dict (workloads.py layout: BSIM4 instances + linear devices + sources).
-    inst_owner: rank of every instance; default = partition_instances on the instance-node graph.  Linear devices and
-    sources attached only to shared unknowns (the supply source) are kept by rank 0 so that the all-reduce counts
-    them once."""
+    inst_owner: rank of every instance; default = partition_instances on the instance-node graph.  Linear devices
+    attached only to shared unknowns (the supply source's stamps) are kept by rank 0 so that the reduction counts them
+    once; sources on shared rows are replicated (B is not reduced)."""
     if inst_owner is None:
         inst_owner = partition_instances(w["lids"][:, :4], w["n_unknowns"], world)
-    owner = classify_unknowns(w["lids"][:, :4], inst_owner, w["n_unknowns"], world)
+    L0 = w["linear"]
+    owner = classify_unknowns(w["lids"][:, :4], inst_owner, w["n_unknowns"], world,
+                              linear_pairs=(np.concatenate([L0["g_row"], L0["c_row"]]), np.concatenate([L0["g_col"], L0["c_col"]])))
     glob, loc, n_int = local_numbering(owner, rank)
     mine = np.where(inst_owner == rank)[0]
     out = dict(w)
@@ -148,7 +158,7 @@ def partition_workload(w, world, rank, inst_owner=None):
     out["sto_lid0"] = np.arange(n_i, dtype=np.int32); out["sto_stride"] = n_i
     out["sta_lid0"] = np.arange(n_i, dtype=np.int32); out["sta_stride"] = n_i
     out["n_store"], out["n_state"] = 22 * n_i, 3 * n_i
-    out["store"] = np.zeros(22 * n_i)
+    out["store"] = np.asarray(w["store"]).reshape(22, -1)[:, mine].reshape(-1)      # slot-major layout of workloads.py
     out["x"] = w["x"][glob]
     L = w["linear"]
     lin = {}
@@ -158,9 +168,12 @@ def partition_workload(w, world, rank, inst_owner=None):
         keep = ((owner[r] == rank) | (owner[c] == rank)) | (shared_only & (rank == 0))
         lin[p + "_row"] = loc[r[keep]].astype(np.int32); lin[p + "_col"] = loc[c[keep]].astype(np.int32)
         lin[p + "_val"] = v[keep]
+        assert np.all(lin[p + "_row"] >= 0) and np.all(lin[p + "_col"] >= 0), "a kept linear stamp touches a foreign unknown"
     out["linear"] = lin
     S = w["sources"]
-    keep = (owner[S["row"]] == rank) | ((owner[S["row"]] == -1) & (rank == 0))
+    # sources on shared (border) rows are REPLICATED on every rank: the library does not reduce the B vector
+    # (include/xyce_b200.h, multi-GPU section); sources on interior rows belong to their rank
+    keep = (owner[S["row"]] == rank) | (owner[S["row"]] == -1)
     out["sources"] = dict(row=loc[S["row"][keep]].astype(np.int32), scale=S["scale"][keep], type=S["type"][keep],
                           params=S["params"][keep])
     out["glob_of_local"], out["n_interior"], out["n_shared"] = glob, n_int, len(glob) - n_int
