@@ -217,8 +217,11 @@ struct Flags {
   double bpTol = 0;       // break-point tolerance, for the sources' corner tests
 };
 
+struct DriverProbe;      // test access to the step-control state (tests/host_mirror/driver_host.cpp)
+
 template <class Backend>
 class TransientDriver {
+  friend struct DriverProbe;
  public:
   TransientDriver(Backend &b, const TranParams &p) : B(b), P(p) {}
   std::vector<StepRecord> steps;
