@@ -339,6 +339,10 @@ def run_ours(args):
         ids = [Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         eng.comm_init(ids[0], rank, world)
+        if os.environ.get("XYCE_B200_P2P", "1") != "0":      # small collectives through NVLink peer mailboxes instead of NCCL calls
+            hs = [None] * world
+            dist.all_gather_object(hs, eng.p2p_handle())
+            eng.p2p_attach(hs)
         eng.border_set(1)
 
     def step():          # one pass of the hot path: updateState + loadDAEVectors + loadDAEMatrices (xgpu_load_dae)
@@ -441,7 +445,8 @@ def run_ours(args):
                                    "loadDAEMatrices at a fixed operating point (BASELINE config 2)",
                        "instances_per_gpu": n_inst, "unknowns_per_gpu": n, "nnz_per_gpu": nnz,
                        "parallelism": ("one circuit of %d x %d instances on a common supply rail, instance-partitioned per rank; border "
-                                       "(supply) rows of F, Q, dFdxdVp, dQdxdVp summed per step with ncclAllReduce inside the library" % (world, n_inst))
+                                       "(supply) rows of F, Q, dFdxdVp, dQdxdVp summed per step inside the library (%s)"
+                                       % (world, n_inst, "one kernel over NVLink peer mailboxes" if os.environ.get("XYCE_B200_P2P", "1") != "0" else "ncclAllReduce"))
                                       if shared else "single GPU",
                        "host_affinity": ("rank pinned to its GPU's NUMA node %s" % numa_node) if (numa_node is not None and numa_node >= 0) else "default (single NUMA node)",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)"},

@@ -206,6 +206,15 @@ int xgpu_lu_host_batch_selfcheck(int n, const int32_t *rowptr, const int32_t *co
 int xgpu_comm_unique_id(unsigned char *id128);
 int xgpu_comm_init(xgpu_ctx *ctx, const unsigned char *id128, int rank, int world);
 int xgpu_comm_info(const xgpu_ctx *ctx, int *rank, int *world);
+/* Optional: peer-memory mailboxes for the small collectives (border rows, border system, norm parts -- a handful of
+ * doubles each).  With them every such collective is ONE kernel that stores straight into the peers' HBM over NVLink /
+ * NVSwitch and combines in rank order (a few microseconds, bitwise identical on all ranks) instead of an NCCL call
+ * (15-25 us for such a message).  Call xgpu_p2p_handle on every rank (after xgpu_comm_init), exchange the 64-byte CUDA IPC
+ * handles through the host application, then xgpu_p2p_attach with all of them in rank order (single node, <= 16 ranks).
+ * xgpu_p2p_error returns 1 if a mailbox wait timed out (a peer did not take part in a collective). */
+int xgpu_p2p_handle(xgpu_ctx *ctx, unsigned char *handle64);
+int xgpu_p2p_attach(xgpu_ctx *ctx, const unsigned char *handles64_by_rank);
+int xgpu_p2p_error(xgpu_ctx *ctx);
 int xgpu_border_set(xgpu_ctx *ctx, int n_border);
 int xgpu_border_info(const xgpu_ctx *ctx, int *n_interior, int *n_border, long long *n_global);
 int xgpu_shared_reduce(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_dFdxdVp, double *d_dQdxdVp);

@@ -22,10 +22,12 @@ def torchrun(n, *args):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("graph_partition", [0, 1])
-def test_two_gpu_tran_equals_one_gpu_and_the_oracle(graph_partition):
+@pytest.mark.parametrize("graph_partition,p2p", [(0, 1), (1, 1), (1, 0)])
+def test_two_gpu_tran_equals_one_gpu_and_the_oracle(graph_partition, p2p):
+    """p2p = 1: small collectives through the NVLink peer mailboxes; p2p = 0: the same through NCCL calls"""
     d = torchrun(2, os.path.join(ROOT, "scripts", "multi_gpu_tran.py"), "--rings", "40", "--stages", "31", "--tstop", "3e-10",
-                 "--graph-partition", str(graph_partition))
+                 "--graph-partition", str(graph_partition), "--p2p", str(p2p))
     assert d["n_gpus"] == 2 and d["border_unknowns"] == 2
     assert d["single_gpu"]["identical_step_sequence_and_newton_counts"] and d["single_gpu"]["max_abs_waveform_diff"] < 1e-9
-    assert all(r["newton_counts_and_tolerance_ok"] for r in d["oracle_single_ring_replay"])
+    assert all(r["waveforms_within_reltol_abstol"] and r["newton_counts_equal"] for r in d["oracle_single_ring_replay"])
+    assert d["p2p_error"] == 0

@@ -223,6 +223,19 @@ class Engine:
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id128))
         self._chk(self.lib.xgpu_comm_init(self.h, buf, int(rank), int(world)))
 
+    def p2p_handle(self):
+        buf = (C.c_ubyte * 64)()
+        self._chk(self.lib.xgpu_p2p_handle(self.h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, handles_by_rank):
+        blob = b"".join(bytes(h) for h in handles_by_rank)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._chk(self.lib.xgpu_p2p_attach(self.h, buf))
+
+    def p2p_error(self):
+        return int(self.lib.xgpu_p2p_error(self.h))
+
     def border_set(self, n_border):
         self._chk(self.lib.xgpu_border_set(self.h, int(n_border)))
 

@@ -74,6 +74,13 @@ struct XgDist {
   double *h_pack = nullptr;          // pinned mirror (>= 8 * world + 64 doubles)
   std::vector<int32_t> sub_rowptr, sub_colind, sub_index;      // interior x interior sub-pattern and its positions in the CSR values
   bool analyzed = false;
+  // peer-memory mailboxes for the small collectives (dist.cu): own allocation, every rank's mailbox as mapped here
+  double *p2p_own = nullptr, *p2p_box[16] = {nullptr};
+  double **p2p_vecs = nullptr;        // device copy of up to 4 vector pointers (fused pack / unpack of the border rows)
+  double *p2p_vecs_host[4] = {nullptr, nullptr, nullptr, nullptr};      // what p2p_vecs currently holds
+  bool p2p_attached = false;
+  unsigned long long p2p_epoch = 0;
+  std::vector<char> col_nonzero;     // [ns] border column has entries in interior rows (its A_ii^-1 solve is needed)
   int reanalyses = 0;                // host re-pivots triggered inside xg_border_solve (bad or sub-threshold pivot)
 };
 

@@ -199,6 +199,62 @@ __global__ void __launch_bounds__(256) back_subst_k(int ni, int ns, const double
   }
 }
 
+// ---- small collectives over NVLink peer memory (one kernel, no NCCL launch) -------------------------------------
+// The collectives of this path move a handful of doubles (border rows, the border system, norm parts).  NCCL needs
+// ~15-25 us for such a message; the exchange below needs one kernel of a few microseconds: every rank owns a mailbox
+// in its own HBM (cudaMalloc + CUDA IPC, mapped by all peers through NVSwitch), writes its values straight into slot
+// [rank] of every peer's mailbox (P2P stores), publishes a per-sender epoch flag (release, system scope), waits for
+// the flags of all senders in its own mailbox (acquire) and combines the slots IN RANK ORDER -- every rank computes
+// bitwise the same sum.  Two slot sets alternate with the epoch parity: a sender can only be one epoch ahead of the
+// slowest receiver (it needs that receiver's flag of the previous epoch to finish its own), so the set it writes is
+// never the one a peer still reads.  A spin that does not finish within ~2 s sets an error flag instead of hanging.
+constexpr int kBoxDoubles = 64;                    // payload per sender and epoch
+struct P2PView {
+  int rank, world;
+  double *box[16];                                 // mailbox of every rank as mapped in THIS process (box[rank] = own)
+  // mailbox layout: double slots[2][world][kBoxDoubles]; unsigned long long flags[world]; int error
+};
+__device__ __forceinline__ double *box_slots(double *box, int world, int parity, int sender) { return box + ((size_t)parity * world + sender) * kBoxDoubles; }
+__device__ __forceinline__ unsigned long long *box_flags(double *box, int world) { return reinterpret_cast<unsigned long long *>(box + (size_t)2 * world * kBoxDoubles); }
+
+// mode 0: out[0 .. k) = sum over ranks (rank order); mode 1: out[r * k + i] = value i of rank r (all-gather).
+// in / out may be vectors addressed through an index list: gather_idx / scatter_idx (null = contiguous).
+__global__ void __launch_bounds__(64) p2p_exchange_k(P2PView v, unsigned long long epoch, int k, int mode, const double *in, double *out,
+                                                    double *const *in_vecs, int nvec, int ns, int ni) {
+  xb::pdl_wait();
+  const int t = threadIdx.x, parity = (int)(epoch & 1);
+  // payload: either the contiguous `in`, or border rows [ni, ni + ns) of up to 4 vectors (fused pack)
+  double mine = 0.0;
+  if (t < k) mine = in_vecs ? in_vecs[t / ns][ni + (t % ns)] : in[t];
+  if (t < k) for (int p = 0; p < v.world; ++p) box_slots(v.box[p], v.world, parity, v.rank)[t] = mine;
+  __threadfence_system();
+  __syncthreads();
+  if (t < v.world) {
+    unsigned long long *f = box_flags(v.box[t], v.world) + v.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+  }
+  if (t < v.world) {
+    const unsigned long long *f = box_flags(v.box[v.rank], v.world) + t;
+    unsigned long long seen = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+      if (seen < epoch && clock64() - t0 > 4000000000LL) { *reinterpret_cast<int *>(box_flags(v.box[v.rank], v.world) + v.world) = 1; break; }
+    } while (seen < epoch);
+  }
+  __syncthreads();
+  double *own = v.box[v.rank];
+  if (mode == 0) {
+    if (t < k) {
+      double acc = 0.0;
+      for (int r = 0; r < v.world; ++r) acc += box_slots(own, v.world, parity, r)[t];
+      if (in_vecs) in_vecs[t / ns][ni + (t % ns)] = acc; else out[t] = acc;
+    }
+  } else {
+    for (int q = t; q < k * v.world; q += 64) out[q] = box_slots(own, v.world, parity, q / k)[q % k];
+  }
+}
+
 int nccl_fail(xgpu_ctx *ctx, int rc, const char *what) {
   return xg_fail(ctx, 300 + rc, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "NCCL error"));
 }
@@ -214,6 +270,9 @@ void xg_dist_free(xgpu_ctx *ctx) {
   XgDist *d = ctx->dist;
   if (!d) return;
   if (d->comm && nccl().CommDestroy) nccl().CommDestroy(d->comm);
+  for (int r = 0; r < 16; ++r) if (d->p2p_box[r] && r != d->rank && d->p2p_attached) cudaIpcCloseMemHandle(d->p2p_box[r]);
+  if (d->p2p_own) cudaFree(d->p2p_own);
+  cudaFree(d->p2p_vecs);
   cudaFree(d->is_pos); cudaFree(d->is_row); cudaFree(d->is_col); cudaFree(d->si_pos); cudaFree(d->si_col);
   cudaFree(d->chunk_row); cudaFree(d->chunk_begin); cudaFree(d->chunk_end); cudaFree(d->row_chunk_ptr); cudaFree(d->ss_pos);
   cudaFree(d->B); cudaFree(d->partials); cudaFree(d->red); cudaFree(d->pack); cudaFreeHost(d->h_pack);
@@ -221,12 +280,35 @@ void xg_dist_free(xgpu_ctx *ctx) {
   ctx->dist = nullptr;
 }
 
-bool xg_dist_multi(const xgpu_ctx *ctx) { return ctx->dist && ctx->dist->comm && ctx->dist->world > 1; }
+bool xg_dist_multi(const xgpu_ctx *ctx) { return ctx->dist && (ctx->dist->comm || ctx->dist->p2p_attached) && ctx->dist->world > 1; }
+
+namespace {
+P2PView p2p_view(const XgDist *d) {
+  P2PView v{};
+  v.rank = d->rank; v.world = d->world;
+  for (int r = 0; r < d->world && r < 16; ++r) v.box[r] = d->p2p_box[r];
+  return v;
+}
+bool p2p_ready(const XgDist *d) { return d && d->p2p_attached && d->world > 1 && d->world <= 16; }
+}  // namespace
 
 int xg_dist_reduce_border_rows(xgpu_ctx *ctx, double *const *vecs, int nvec) {
   XgDist *d = ctx->dist;
-  if (!d || !d->comm || d->world <= 1 || d->ns == 0 || nvec <= 0) return 0;
+  if (!d || d->world <= 1 || d->ns == 0 || nvec <= 0) return 0;
   if (nvec > 4) return xg_fail(ctx, 1, "at most 4 vectors per border reduction");
+  if (p2p_ready(d) && nvec * d->ns <= kBoxDoubles) {      // fused pack + exchange + unpack: one kernel
+    bool same = true;      // the vectors rarely change between calls: upload the pointer list only when they do
+    for (int k = 0; k < nvec; ++k) same = same && d->p2p_vecs_host[k] == vecs[k];
+    if (!same) {
+      for (int k = 0; k < 4; ++k) d->p2p_vecs_host[k] = k < nvec ? vecs[k] : nullptr;
+      XD_CUDA(cudaMemcpyAsync(d->p2p_vecs, d->p2p_vecs_host, 4 * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    xb::launch_pdl(p2p_exchange_k, dim3(1), dim3(64), 0, ctx->stream, p2p_view(d), ++d->p2p_epoch, nvec * d->ns, 0, (const double *)nullptr,
+                   (double *)nullptr, (double *const *)d->p2p_vecs, nvec, d->ns, d->ni);
+    ++ctx->launches;
+    return 0;
+  }
+  if (!d->comm) return 0;
   double *v[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int k = 0; k < nvec; ++k) v[k] = vecs[k];
   const int cnt = nvec * d->ns, blocks = (cnt + 255) / 256;
@@ -242,7 +324,11 @@ int xg_dist_allgather(xgpu_ctx *ctx, const double *d_send, int k) {
   XgDist *d = ctx->dist;
   if (!d || k <= 0 || k > 8) return xg_fail(ctx, 1, "allgather: 1 .. 8 doubles per rank");
   double *recv = d->pack + 8 * d->ns + 8;          // behind the border-row pack area
-  if (d->comm && d->world > 1) {
+  if (p2p_ready(d) && k <= kBoxDoubles) {
+    xb::launch_pdl(p2p_exchange_k, dim3(1), dim3(64), 0, ctx->stream, p2p_view(d), ++d->p2p_epoch, k, 1, d_send, recv,
+                   (double *const *)nullptr, 0, 1, 0);
+    ++ctx->launches;
+  } else if (d->comm && d->world > 1) {
     const int rc = nccl().AllGather(d_send, recv, (size_t)k, kNcclFloat64, d->comm, ctx->stream);
     if (rc) return nccl_fail(ctx, rc, "ncclAllGather");
   } else {
@@ -271,6 +357,7 @@ int xg_border_solve(xgpu_ctx *ctx, const double *J, const double *rhs, double *x
     if (d->n_is > 0) { xb::launch_pdl(scatter_is_k, dim3((d->n_is + 255) / 256), dim3(256), 0, s, d->n_is, (const int *)d->is_pos, (const int *)d->is_row, (const int *)d->is_col, J, ni, d->B); ++ctx->launches; }
     XD_CUDA(cudaMemcpyAsync(d->B + (size_t)ns * ni, rhs, (size_t)ni * sizeof(double), cudaMemcpyDeviceToDevice, s));
     for (int c = 0; c <= ns; ++c) {
+      if (c < ns && !d->col_nonzero[c]) continue;      // a border column without interior entries: A_ii^-1 0 = 0 (e.g. a source branch)
       const int rc = xgpu_lu_solve(ctx, J, d->B + (size_t)c * ni, d->B + (size_t)c * ni);
       if (rc) return rc;
     }
@@ -285,11 +372,15 @@ int xg_border_solve(xgpu_ctx *ctx, const double *J, const double *rhs, double *x
                    (const int *)d->si_pos, (const int *)d->si_col, J, (const double *)d->B, ni, d->partials);
     ++ctx->launches;
   }
-  const int take_b = (!rhs_border_reduced || d->rank == 0 || !(d->comm && d->world > 1)) ? 1 : 0;
+  const int take_b = (!rhs_border_reduced || d->rank == 0 || !xg_dist_multi(ctx)) ? 1 : 0;
   xb::launch_pdl(si_finish_k, dim3((ns * (ns + 1) + 63) / 64), dim3(64), 0, s, ns, d->n_chunks, (const int *)d->row_chunk_ptr,
                  (const double *)d->partials, (const int *)d->ss_pos, J, rhs, ni, take_b, d->red);
   ++ctx->launches;
-  if (d->comm && d->world > 1) {
+  if (p2p_ready(d) && ns * (ns + 1) <= kBoxDoubles) {
+    xb::launch_pdl(p2p_exchange_k, dim3(1), dim3(64), 0, s, p2p_view(d), ++d->p2p_epoch, ns * (ns + 1), 0, (const double *)d->red, d->red,
+                   (double *const *)nullptr, 0, 1, 0);
+    ++ctx->launches;
+  } else if (d->comm && d->world > 1) {
     const int rc = nccl().AllReduce(d->red, d->red, (size_t)ns * (ns + 1), kNcclFloat64, kNcclSum, d->comm, s);
     if (rc) return nccl_fail(ctx, rc, "ncclAllReduce (border system)");
   }
@@ -332,6 +423,53 @@ int xgpu_comm_init(xgpu_ctx *ctx, const unsigned char *id128, int rank, int worl
   return 0;
 }
 
+// ---- peer-memory mailboxes (CUDA IPC): xgpu_p2p_handle on every rank, exchange the 64-byte handles through the host
+// application, xgpu_p2p_attach with all of them (rank order).  Needs xgpu_comm_init first (rank / world).
+int xgpu_p2p_handle(xgpu_ctx *ctx, unsigned char *handle64) {
+  if (!ctx || !handle64) return 1;
+  XgDist *d = ctx->dist;
+  if (!d || d->world < 1) return xg_fail(ctx, 1, "xgpu_comm_init must precede xgpu_p2p_handle");
+  if (d->world > 16) return xg_fail(ctx, 1, "peer mailboxes support at most 16 ranks");
+  XD_CUDA(cudaSetDevice(ctx->device));
+  if (!d->p2p_own) {
+    const size_t bytes = (size_t)2 * d->world * kBoxDoubles * sizeof(double) + (size_t)(d->world + 2) * sizeof(unsigned long long);
+    XD_CUDA(cudaMalloc((void **)&d->p2p_own, bytes));
+    XD_CUDA(cudaMemset(d->p2p_own, 0, bytes));
+    XD_CUDA(cudaMalloc((void **)&d->p2p_vecs, 4 * sizeof(double *)));
+    XD_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  XD_CUDA(cudaIpcGetMemHandle(&h, d->p2p_own));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+int xgpu_p2p_attach(xgpu_ctx *ctx, const unsigned char *handles64_by_rank) {
+  if (!ctx || !handles64_by_rank) return 1;
+  XgDist *d = ctx->dist;
+  if (!d || !d->p2p_own) return xg_fail(ctx, 1, "xgpu_p2p_handle must precede xgpu_p2p_attach");
+  XD_CUDA(cudaSetDevice(ctx->device));
+  for (int r = 0; r < d->world; ++r) {
+    if (r == d->rank) { d->p2p_box[r] = d->p2p_own; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles64_by_rank + 64 * (size_t)r, 64);
+    void *p = nullptr;
+    XD_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    d->p2p_box[r] = (double *)p;
+  }
+  d->p2p_attached = true;
+  d->p2p_epoch = 0;
+  return 0;
+}
+// 1 when a mailbox spin timed out since the last call (a peer did not take part in a collective)
+int xgpu_p2p_error(xgpu_ctx *ctx) {
+  if (!ctx || !ctx->dist || !ctx->dist->p2p_own) return 0;
+  int e = 0;
+  const XgDist *d = ctx->dist;
+  cudaMemcpy(&e, reinterpret_cast<const unsigned long long *>(d->p2p_own + (size_t)2 * d->world * kBoxDoubles) + d->world, sizeof(int), cudaMemcpyDeviceToHost);
+  return e;
+}
+
 int xgpu_comm_info(const xgpu_ctx *ctx, int *rank, int *world) {
   if (!ctx || !rank || !world) return 1;
   *rank = ctx->dist ? ctx->dist->rank : 0;
@@ -367,6 +505,8 @@ int xgpu_border_set(xgpu_ctx *ctx, int n_border) {
   }
   while ((int)rcp.size() < ns + 1) rcp.push_back((int)cb.size());
   d->n_is = (int)is_pos.size(); d->n_si = (int)si_pos.size(); d->n_chunks = (int)cb.size();
+  d->col_nonzero.assign(ns, 0);
+  for (int c : is_col) d->col_nonzero[c] = 1;
   XD_CUDA(up(&d->is_pos, is_pos)); XD_CUDA(up(&d->is_row, is_row)); XD_CUDA(up(&d->is_col, is_col));
   XD_CUDA(up(&d->si_pos, si_pos)); XD_CUDA(up(&d->si_col, si_col));
   XD_CUDA(up(&d->chunk_begin, cb)); XD_CUDA(up(&d->chunk_end, ce)); XD_CUDA(up(&d->chunk_row, crow)); XD_CUDA(up(&d->row_chunk_ptr, rcp));
