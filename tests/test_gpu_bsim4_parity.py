@@ -176,7 +176,11 @@ def test_gpu_matches_reference_golden(case):
         want = g["ref_" + k]
         scale = 1e-3 * np.max(np.abs(want)) if np.any(want) else 1e-300
         assert rel_err(got[k], want, scale) < TOL, (case, k)
-    assert rel_err(eng.get_state(0), g["next_sto"], 1e-30) < TOL
+    # store vector: entry-wise with the cancellation floor per slot kind, as in run_case (the published Cgs / Cgd are
+    # differences of capacitances: -1.8e-20 F beside 1e-16 F terms in igc2_v461)
+    sto, want_sto = eng.get_state(0).reshape(-1, 22), g["next_sto"].reshape(-1, 22)
+    floor = np.maximum(1e-3 * np.max(np.abs(want_sto), axis=0, keepdims=True), 1e-300)
+    assert np.max(np.abs(sto - want_sto) / np.maximum(np.abs(want_sto), floor)) < TOL
     assert rel_err(eng.get_state(2), g["next_sta"], 1e-30) < TOL
     assert rel_err(eng.get_state(3), g["curr_sta"], 1e-30) < TOL
     assert rel_err(eng.b4_get_von(0, len(g["von"])), g["von_out"], 1e-30) < TOL

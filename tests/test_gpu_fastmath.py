@@ -52,4 +52,14 @@ def test_div(eng):
     b = rng.normal(0, 1, 400000) * 10.0 ** rng.uniform(-100, 100, 400000)
     got = eng.selftest_fastmath(2, a, b)
     want = (a.astype(np.longdouble) / b.astype(np.longdouble)).astype(np.float64)
+    assert np.max(ulps(got, want)) <= 2.0       # a * (1/b) with the reciprocal at <= 1 ulp
+
+
+def test_sqrt(eng):
+    rng = np.random.default_rng(4)
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 300000), rng.uniform(0.0, 4.0, 200000), [1.0, 2.0, 4.0, 1e-300, 1e300]])
+    got = eng.selftest_fastmath(3, x)
+    want = np.sqrt(x.astype(np.longdouble)).astype(np.float64)
     assert np.max(ulps(got, want)) <= 1.0
+    sp = eng.selftest_fastmath(3, np.array([0.0, np.inf, -1.0, np.nan]))
+    assert sp[0] == 0.0 and sp[1] == np.inf and np.isnan(sp[2]) and np.isnan(sp[3])

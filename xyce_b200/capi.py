@@ -3,7 +3,8 @@ import ctypes as C
 import os
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libxyce_b200.so")
+# XYCE_B200_LIB selects another build of the same library (kernel experiments: scripts/build_variant.sh)
+LIB_PATH = os.environ.get("XYCE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libxyce_b200.so")
 _lib = None
 
 FLAG_FIELDS = ["dcopFlag", "tranopFlag", "acopFlag", "transientFlag", "dcsweepFlag", "initJctFlag", "initFixFlag",

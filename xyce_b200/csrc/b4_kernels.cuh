@@ -71,8 +71,13 @@ constexpr int kMaxUniformRuns = 64;   // groups with more distinct runs use the 
 
 // (threads per block, resident blocks per SM) shapes compiled for the default-topology kernel;
 // registers per thread = 65536 / (threads * blocks), capped at 255.
+#if defined(XB_B4_EXTRA)       // experiment builds only (scripts/build_variant.sh)
+#define XB_B4_EXTRA_SHAPES(X) X(128, 5) X(128, 6) X(352, 1)
+#else
+#define XB_B4_EXTRA_SHAPES(X)
+#endif
 #define XB_B4_LAUNCH_SHAPES(X) \
-  X(64, 4) X(64, 6) X(96, 4) X(128, 2) X(128, 3) X(128, 4) X(256, 1) X(384, 1) X(512, 1)
+  X(64, 4) X(64, 6) X(96, 4) X(128, 2) X(128, 3) X(128, 4) X(256, 1) X(384, 1) X(512, 1) XB_B4_EXTRA_SHAPES(X)
 // (20-24 warps per SM -- 128 x 5, 128 x 6, 64 x 11 at 80-96 registers -- were measured and are slower at every
 // group size: the local-memory spills cost more than the occupancy gains; profiles/r01_b4_occupancy.json)
 

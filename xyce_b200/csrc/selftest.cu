@@ -10,13 +10,14 @@ __global__ void fastmath_kernel(int which, int n, const double *a, const double 
   switch (which) {
     case 0: out[i] = xb::fm::exp(a[i]); break;
     case 1: out[i] = xb::fm::log(a[i]); break;
+    case 3: out[i] = xb::fm::sqrt(a[i]); break;
     default: out[i] = xb::fm::div(a[i], b[i]); break;
   }
 }
 }  // namespace
 
 extern "C" int xgpu_selftest_fastmath(xgpu_ctx *ctx, int which, int n, const double *h_a, const double *h_b, double *h_out) {
-  if (!ctx || n <= 0 || !h_a || !h_out || which < 0 || which > 2 || (which == 2 && !h_b)) return 1;
+  if (!ctx || n <= 0 || !h_a || !h_out || which < 0 || which > 3 || (which == 2 && !h_b)) return 1;
   double *d = nullptr;
   if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc((void **)&d, 3 * (size_t)n * sizeof(double)) != cudaSuccess)
     return xg_fail(ctx, 11, "device allocation failed in selftest");

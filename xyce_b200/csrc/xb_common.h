@@ -106,11 +106,24 @@ struct SolverFlags {
 
 // ---- smoothed exponentials (B4p82.C:82-105) --------------------------------
 XB_HD void dexp(real a, real &b, real &c) {
+#if defined(XB_DEXP_SELECT) && defined(__CUDA_ARCH__)
+  // branch-free: the exponential is evaluated unconditionally (its argument saturates inside fm::exp) and the
+  // linear / floor continuations are selected afterwards
+  const real ex = exp(a);
+  const bool hi = a > kExpThr, lo = a < -kExpThr;
+  b = hi ? kMaxExp * (1.0 + a - kExpThr) : (lo ? real(kMinExp) : ex);
+  c = hi ? real(kMaxExp) : (lo ? real(0.0) : ex);
+  return;
+#endif
   if (a > kExpThr) { b = kMaxExp * (1.0 + a - kExpThr); c = kMaxExp; }
   else if (a < -kExpThr) { b = kMinExp; c = 0.0; }
   else { b = exp(a); c = b; }
 }
 XB_HD real dexp2(real a) {
+#if defined(XB_DEXP_SELECT) && defined(__CUDA_ARCH__)
+  const real ex = exp(a);
+  return a > kExpThr ? kMaxExp * (1.0 + a - kExpThr) : (a < -kExpThr ? real(kMinExp) : ex);
+#endif
   if (a > kExpThr) return kMaxExp * (1.0 + a - kExpThr);
   if (a < -kExpThr) return kMinExp;
   return exp(a);

@@ -12,7 +12,13 @@
 //             exp(r) by its degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation < 4e-18)
 //   log(x)  = e ln2 + 2 atanh(f), x = 2^e m, m in [sqrt(1/2), sqrt(2)), f = (m - 1) / (m + 1),
 //             atanh by its odd Taylor series up to f^21 on |f| <= 0.1716 (truncation < 2e-18)
-//   a / b   = reciprocal seed (MUFU.RCP64H), one Newton step, quotient, one residual correction
+//   a / b   = a * (1/b); 1/b = reciprocal seed (MUFU.RCP64H) + two Newton steps.  The reciprocal depends on b alone, so
+//             the compiler shares it between all divisions by the same value (the evaluators divide by the same
+//             denominators again and again) and the quotient is one multiply after `a` is known
+//             (XB_DIV_MODE 0 = the round-1 form: one Newton step, quotient, one residual correction).
+//             Measured on B200 (profiles/r02_b4_eval_ilp_experiments.md): C2 kernel 62.5 -> 59.4 us
+//   sqrt(x) = reciprocal-root seed (MUFU.RSQ64H), one coupled Goldschmidt step, one residual correction, inlined and
+//             branch-free (a call costs ~8 instructions and ends the scheduling block): 59.4 -> 56.3 us
 #pragma once
 #if defined(__CUDACC__)
 
@@ -37,13 +43,46 @@ __device__ __forceinline__ double rcp_seed(double b) {
   return r;
 }
 
-// <= 1 ulp for normal operands; b = 0, inf, denormal give NaN/inf like the seed does (the model code
+// Reciprocal to <= 1 ulp: seed + two Newton steps.  Depends on b only, so the compiler shares one reciprocal between
+// every division by the same value (XB_DIV_MODE 1).
+__device__ __forceinline__ double rcp(double b) {
+  double r = rcp_seed(b);
+  r = fma(fma(-b, r, 1.0), r, r);
+  return fma(fma(-b, r, 1.0), r, r);
+}
+
+// <= 1 ulp for normal operands (mode 1: <= 2 ulp); b = 0, inf, denormal give NaN/inf like the seed does (the model code
 // guards its denominators; the strict variants keep IEEE division)
+#ifndef XB_DIV_MODE
+#define XB_DIV_MODE 1
+#endif
 __device__ __forceinline__ double div(double a, double b) {
+#if XB_DIV_MODE == 1
+  return a * rcp(b);
+#else
   double r = rcp_seed(b);
   r = fma(fma(-b, r, 1.0), r, r);
   const double q = a * r;
   return fma(fma(-b, q, a), r, q);
+#endif
+}
+
+__device__ __forceinline__ double rsqrt_seed(double b) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  return r;
+}
+// Branch-free square root, <= 1 ulp for normal x: reciprocal-root seed, one coupled (Goldschmidt) step for sqrt and
+// 1/(2 sqrt), one residual correction.  0 and +inf are passed through by a select; x < 0 and NaN give NaN;
+// denormal x (never an argument of the model code) is not supported.
+__device__ __forceinline__ double sqrt_inline(double x) {
+  const double y = rsqrt_seed(x);
+  double g = x * y, h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  g = fma(fma(-g, g, x), h, g);
+  return (x == 0.0 || x == __longlong_as_double(0x7ff0000000000000LL)) ? x : g;
 }
 
 // exp / log / sqrt are real functions (not inlined): the evaluation kernel is bound by instruction delivery, and
@@ -51,8 +90,18 @@ __device__ __forceinline__ double div(double a, double b) {
 #ifndef XB_FM_INLINE
 #define XB_FM_INLINE __noinline__
 #endif
+#if defined(XB_SQRT_CALL)
 static __device__ XB_FM_INLINE double sqrt(double x) { return ::sqrt(x); }
-static __device__ XB_FM_INLINE double exp(double x) {
+#else
+static __device__ __forceinline__ double sqrt(double x) { return sqrt_inline(x); }
+#endif
+#ifndef XB_EXP_INLINE
+#define XB_EXP_INLINE XB_FM_INLINE
+#endif
+#ifndef XB_LOG_INLINE
+#define XB_LOG_INLINE XB_FM_INLINE
+#endif
+static __device__ XB_EXP_INLINE double exp(double x) {
   x = x < kExpK[3] ? kExpK[3] : x;          // NaN stays NaN (comparisons false)
   x = x > kExpK[4] ? kExpK[4] : x;
   const double shifter = 6755399441055744.0;              // 1.5 * 2^52
@@ -72,7 +121,7 @@ static __device__ XB_FM_INLINE double exp(double x) {
   return p * s1 * s2;
 }
 
-static __device__ XB_FM_INLINE double log(double x) {
+static __device__ XB_LOG_INLINE double log(double x) {
   if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return ::log(x);   // 0, < 0, denormal, inf, NaN
   int hi = __double2hiint(x);
   const int lo = __double2loint(x);
