@@ -284,6 +284,17 @@ int xgpu_load_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *
  * "zero_copy_out" = 1 and pinned, mapped buffers the kernel stores straight into host memory. */
 int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double qscalar, double fscalar,
                       double *h_rhs, double *h_jac);
+/* One whole Newton iteration behind host buffers: what NonlinearSolver::rhs_() + jacobian_() + newton_() do between two
+ * solution vectors (N_NLS_DampedNewton.C:362-515: Loader::loadRHS + loadJacobian, then Linear::Solver::solve on
+ * J dx = -r).  In: x (n), the time integrator's scalars as in xgpu_load_host_jr, and optionally h_hist (n) = the part of
+ * the residual that lives in the caller's history vectors (qscalar qHistory[0] - fscalar B ...; null = none).
+ * Out: dx (n) and optionally the right-hand side r = -(qscalar Q + fscalar F + hist) + limiter terms (n; null = not
+ * wanted).  PCIe traffic is 8n bytes each way (0.8 MB on BASELINE config 2 instead of the 4 MB of J + r); evaluation,
+ * assembly, linear-device replay, refactorization on the previous call's pivot sequence and the triangular solves run
+ * back to back on the device with ONE host synchronisation at the end.  The first call (and any call whose pivots fail
+ * the threshold check, or every call under "lu_repivot") analyses on the host like xgpu_lu_analyze. */
+int xgpu_newton_step_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double qscalar, double fscalar,
+                          const double *h_hist, double *h_dx, double *h_rhs);
 /* which: 0 next store, 1 curr store, 2 next state, 3 curr state */
 int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h_vals);
 int xgpu_state_get(xgpu_ctx *ctx, int which, double *h_vals);

@@ -9,7 +9,7 @@ tag=$1; shift
 mkdir -p ../lib/exp
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr \
   --extended-lambda -Xcompiler -fPIC -fmad=true -DXB_ARITH=2 -DXB_SPEC=1 -DXB_HELPERS_INLINE "$@" \
-  -c gen_spec/b4_kernels.cu -o ../lib/exp/a2x_$tag.o
+  -c ${SRC_DIR:-gen_spec}/b4_kernels.cu -o ../lib/exp/a2x_$tag.o
 objs=$(ls ../lib/obj/*.o | grep -v b4_kernels_a2x.o)
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/exp/libxyce_b200_$tag.so $objs ../lib/exp/a2x_$tag.o -lcudart -ldl
 echo built ../lib/exp/libxyce_b200_$tag.so

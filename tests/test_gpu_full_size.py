@@ -285,3 +285,42 @@ def test_load_host_jr_is_the_combination_of_the_six_arrays(zero_copy):
     assert np.allclose(hj.numpy(), want_j, rtol=1e-15, atol=0) and np.any(want_j)
     assert np.allclose(hr.numpy(), want_r, rtol=0, atol=1e-15 * np.max(np.abs(qs * six["q"]))) and np.any(six["dQdxdVp"])
     eng.close()
+
+
+@pytest.mark.parametrize("workload", ["inverters", "rings"])
+def test_newton_step_host_solves_the_system_the_loads_return(workload):
+    """xgpu_newton_step_host (x in, dx out, everything between on the device) against SciPy's solution of J dx = r with
+    J and r as xgpu_load_host_jr returns them plus the linear-device stamps (rings: load capacitors + the supply branch)
+    and the caller's history term; second call = refactorization on the first call's pivot sequence."""
+    import scipy.sparse as sp, scipy.sparse.linalg as spl
+    if workload == "inverters":
+        w = wl.inverter_array(2000, store_noise=0.3)
+    else:
+        w = wl.ring_oscillator_array(40, 31)
+    eng = wl.build_engine(w)
+    n, nnz = eng.n, eng.nnz
+    rowptr, colind = w["rowptr"], w["colind"]
+    qs, fs = 1.0 / 2e-12, 1.0
+    ss = solver_state(**FLAGS)
+    rng = np.random.default_rng(5)
+    hist = rng.normal(0, 1e-6, n)
+    xs = [w["x"], w["x"] + rng.normal(0, 0.02, n)]
+    for it, x in enumerate(xs):
+        eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
+        r, J = eng.load_host_jr(x, ss, qs, fs)
+        A = sp.csr_matrix((J, colind, rowptr), shape=(n, n)).tolil()
+        if "linear" in w:
+            L = w["linear"]
+            G = sp.coo_matrix((L["g_val"], (L["g_row"], L["g_col"])), shape=(n, n)).tocsr()
+            Cm = sp.coo_matrix((L["c_val"], (L["c_row"], L["c_col"])), shape=(n, n)).tocsr()
+            A = A + qs * Cm + fs * G
+            r = r - (qs * (Cm @ x) + fs * (G @ x))
+        r = r - hist
+        want = spl.spsolve(sp.csc_matrix(A), r)
+        eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
+        rhs = np.zeros(n)
+        got = eng.newton_step_host(x, ss, qs, fs, hist=hist, rhs=rhs)
+        assert np.allclose(rhs, r, rtol=1e-12, atol=1e-12 * np.max(np.abs(r)))
+        scale = np.max(np.abs(want))
+        assert np.max(np.abs(got - want)) <= 1e-9 * scale, (workload, it, float(np.max(np.abs(got - want))), scale)
+    eng.close()

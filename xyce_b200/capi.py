@@ -133,6 +133,15 @@ class Engine:
         self._chk(self.lib.xgpu_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    def newton_step_host(self, x, ss, qscalar, fscalar, hist=None, dx=None, rhs=None):
+        """xgpu_newton_step_host: one Newton iteration (load, stamp, J and r, LU refactor, solves) behind host buffers."""
+        x = _f64(x)
+        dx = np.empty(self.n) if dx is None else dx
+        hist = None if hist is None else _f64(hist)
+        self._chk(self.lib.xgpu_newton_step_host(self.h, _dp(x), C.byref(ss), C.c_double(qscalar), C.c_double(fscalar),
+                                                  _dp(hist), _dp(dx), _dp(rhs)))
+        return dx
+
     def selftest_fastmath(self, which, a, b=None):
         """fast-variant exp (0) / log (1) / a/b (2) of the BSIM4 kernel, evaluated on the device."""
         a = _f64(a)

@@ -151,7 +151,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
   for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
-  cudaFree(ctx->tran_pool); cudaFree(ctx->tran_ints); cudaFreeHost(ctx->tran_pinned);
+  cudaFree(ctx->tran_pool); cudaFree(ctx->tran_ints); cudaFreeHost(ctx->tran_pinned); cudaFree(ctx->d_hist);
   xb::lu::free_plan(ctx->lu_dev);
   xg_dist_free(ctx);
   for (XgLinearPart *L : {&ctx->linG, &ctx->linC}) { cudaFree(L->rows); cudaFree(L->ptr); cudaFree(L->col); cudaFree(L->pos); cudaFree(L->val); }
@@ -928,6 +928,74 @@ int xgpu_lu_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, doub
   if (!ctx->lu_ready) return fail(ctx, 113, "xgpu_lu_analyze has not been called");
   return lu_run(ctx, ctx->g_solve, d_vals, d_rhs, d_x,
                 [&] { return xb::lu::launch_solve(ctx->lu_dev, d_vals, d_rhs, d_x, ctx->stream); });
+}
+
+// One Newton iteration for a caller that keeps its vectors on the host: x in, dx (and optionally the residual) out.
+// Everything between the two copies stays on the device: evaluation, assembly, linear-device replay, J and r in one
+// pass, refactorization on the plan of the previous call (first call, or a failed pivot check: host analysis), solves.
+int xgpu_newton_step_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double qscalar, double fscalar,
+                          const double *h_hist, double *h_dx, double *h_rhs) {
+  if (!ctx || !h_sol || !ss || !h_dx) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  double **b = ctx->buf;
+  XG_CUDA(cudaMemcpyAsync(b[0], h_sol, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (h_hist) {      // the caller's history / source terms of the residual
+    if (!ctx->d_hist) XG_CUDA(cudaMalloc((void **)&ctx->d_hist, (size_t)ctx->n * sizeof(double)));
+    XG_CUDA(cudaMemcpyAsync(ctx->d_hist, h_hist, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = xgpu_load_dae(ctx, b[0], b[9], b[10], b[7], b[8], ss, b[1], b[2], b[3], b[4], b[5], b[6], 0);
+  if (rc) return rc;
+  // linear devices: F += G x, Q += C x, dFdx += G, dQdx += C (FilteredMatrix replay, N_LOA_CktLoader.C:700-788)
+  const XgLinearPart &G = ctx->linG, &C = ctx->linC;
+  xb::vec::spmv_add(G.nrows, G.rows, G.ptr, G.col, G.val, b[0], b[1], ctx->stream);
+  xb::vec::spmv_add(C.nrows, C.rows, C.ptr, C.col, C.val, b[0], b[2], ctx->stream);
+  xb::vec::scatter_add(G.nnz, G.pos, G.val, b[5], ctx->stream);
+  xb::vec::scatter_add(C.nnz, C.pos, C.val, b[6], ctx->stream);
+  ctx->launches += (G.nrows > 0) + (C.nrows > 0) + (G.nnz > 0) + (C.nnz > 0);
+  const bool bordered = ctx->dist && (ctx->dist->ns > 0 || xg_dist_multi(ctx));
+  if (bordered && xg_dist_multi(ctx)) {      // border rows hold per-rank partial sums (N_LOA_CktLoader.C:816-829)
+    double *vv[4] = {b[1], b[2], b[3], b[4]};
+    rc = xg_dist_reduce_border_rows(ctx, vv, 4);
+    if (rc) return rc;
+  }
+  const long long m = std::max<long long>(ctx->nnz, ctx->n);
+  xb::launch_pdl(jr_kernel, dim3((unsigned)((m + 255) / 256)), dim3(256), 0, ctx->stream, (long long)ctx->nnz, ctx->n, qscalar,
+                 fscalar, (const double *)b[6], (const double *)b[5], (const double *)b[1], (const double *)b[2],
+                 (const double *)b[3], (const double *)b[4], ss->voltageLimiterFlag, b[5], b[1]);
+  ++ctx->launches;
+  if (bordered) {      // interior LU per rank + the replicated border (Schur) system, dist.cu
+    if (h_hist) { xb::vec::axpby(b[1], 1.0, b[1], -1.0, ctx->d_hist, ctx->n, ctx->stream); ++ctx->launches; }
+    if (h_rhs) XG_CUDA(cudaMemcpyAsync(h_rhs, b[1], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->dist->analyzed) { rc = xgpu_border_analyze(ctx, b[5]); if (rc != 0 && rc != 2) return rc; }
+    rc = xg_border_solve(ctx, b[5], b[1], b[2], xg_dist_multi(ctx) ? 1 : 0);
+    if (rc) return rc;
+    XG_CUDA(cudaMemcpyAsync(h_dx, b[2], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    XG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (h_hist) { xb::vec::axpby(b[1], 1.0, b[1], -1.0, ctx->d_hist, ctx->n, ctx->stream); ++ctx->launches; }   // r -= hist
+  if (h_rhs) XG_CUDA(cudaMemcpyAsync(h_rhs, b[1], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  bool analysed = false;
+  if (!ctx->lu_ready || ctx->lu_repivot) { rc = xgpu_lu_analyze(ctx, b[5]); analysed = true; }
+  else rc = xg_lu_refactor_async(ctx, b[5]);
+  if (rc) return rc;
+  rc = xgpu_lu_solve(ctx, b[5], b[1], b[2]);
+  if (rc) return rc;
+  XG_CUDA(cudaMemcpyAsync(h_dx, b[2], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  int status = 0;
+  if (!analysed) { rc = xg_lu_status(ctx, &status); if (rc) return rc; }      // the one synchronisation of the call
+  else XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (status & 5) {                                  // bad or sub-threshold pivot of the fixed sequence: re-pivot
+    rc = xgpu_lu_analyze(ctx, b[5]);
+    if (rc) return rc;
+    rc = xgpu_lu_solve(ctx, b[5], b[1], b[2]);
+    if (rc) return rc;
+    XG_CUDA(cudaMemcpyAsync(h_dx, b[2], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  XG_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int xgpu_lu_host_factor_solve(int n, const int32_t *rowptr, const int32_t *colind, const double *vals,

@@ -143,6 +143,7 @@ struct xgpu_ctx {
   double *tran_pool = nullptr; size_t tran_pool_len = 0;
   int *tran_ints = nullptr; size_t tran_ints_len = 0;
   double *tran_pinned = nullptr;
+  double *d_hist = nullptr;           // xgpu_newton_step_host: the caller's history term on the device
   XgDist *dist = nullptr;     // bordered solve / multi-GPU state (xgpu_border_set, xgpu_comm_init); null = plain single-GPU path
 };
 
