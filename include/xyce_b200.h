@@ -89,6 +89,19 @@ int xgpu_b4_group_add(xgpu_ctx *ctx, int n_inst, const double *inst_d, const int
  * first store / state LID.  Replaces Device::addInstance + registerLIDs/StoreLIDs/StateLIDs of
  * N_DEV_Diode.C, N_DEV_MOSFET1.C, N_DEV_BJT.C and the ADMS-generated classes.  Returns the group id. */
 int xgpu_simple_field_count(int type);
+/* Models translated from admsXml output (the C++ that Xyce's `_nosac` templates emit, utils/ADMS/
+ * xyceImplementationFile_nosac.xml; any of src/DeviceModelPKG/ADMS/N_DEV_ADMS*.C or a user plugin built with
+ * buildxyceplugin) by xyce_b200/adms/translate.py and compiled into the library at build time.  They are small-device
+ * types like the ones above: xgpu_simple_group_add with type = info5[0].
+ *   info5 = {type id, unknowns per instance (nodes + branch currents, admsNodeID / admsBRA_ID order), external nodes,
+ *            Jacobian stamp entries (constructor's jacobianElements order), record fields}
+ *   fields = space-separated record layout: "M:x" = Model member x, "I:x" = Instance member x (after processParams /
+ *            updateTemperature; admsTemperature and adms_vt_nom included when the analog block reads them)
+ *   slot_row / slot_col (info5[3] entries each, may be NULL): unknown index of each stamp entry.
+ * Replaces Instance::updateIntermediateVars + loadDAEFVector / loadDAEQVector / loadDAEdFdx / loadDAEdQdx of the
+ * generated classes (e.g. N_DEV_ADMSmvs_2_0_0_etsoi.C:704-745, :819-1456, :1458-1532). */
+int xgpu_adms_gen_count(void);
+int xgpu_adms_gen_info(int idx, const char **name, const char **fields, int32_t *info5, int32_t *slot_row, int32_t *slot_col);
 int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n_inst, const double *rec, const int32_t *flags,
                           const int32_t *lids, const int32_t *sto_lid0, int sto_stride,
                           const int32_t *sta_lid0, int sta_stride);

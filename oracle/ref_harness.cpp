@@ -29,6 +29,12 @@
 #include <N_DEV_Diode.h>
 #include <N_DEV_BJT.h>
 #include <N_DEV_ADMSmvs_2_0_0_etsoi.h>
+// models that went through the ADMS translator (xyce_b200/adms/translate.py): the reference's generated classes
+// + the fillers that copy their members into the flat records
+#if __has_include("gen_adms/oracle_registry.h")
+#include "gen_adms/oracle_registry.h"
+#define XB_HAVE_ADMS_ORACLE 1
+#endif
 #include <N_DEV_Configuration.h>
 #include <N_DEV_DeviceBlock.h>
 #include <N_DEV_DeviceMaster.h>
@@ -185,6 +191,11 @@ struct Ctx {
     else if (t == "d") { auto *c = &Config<Diode::Traits>::addConfiguration(); cfg = c; m = Diode::Traits::factory(*c, *fb); }
     else if (t == "q") { auto *c = &Config<BJT::Traits>::addConfiguration(); cfg = c; m = BJT::Traits::factory(*c, *fb); }
     else if (t == "mvs") { auto *c = &Config<ADMSmvs_2_0_0_etsoi::Traits>::addConfiguration(); cfg = c; m = ADMSmvs_2_0_0_etsoi::Traits::factory(*c, *fb); }
+#ifdef XB_HAVE_ADMS_ORACLE
+#define XB_ORACLE_MASTER(nm_, ns_) else if (t == "adms:" #nm_) { auto *c = &Config<ns_::Traits>::addConfiguration(); cfg = c; m = ns_::Traits::factory(*c, *fb); }
+    XB_ADMS_ORACLE_LIST(XB_ORACLE_MASTER)
+#undef XB_ORACLE_MASTER
+#endif
     else return -1;
     masters.push_back(m); masterType.push_back(t); masterCfg.push_back(cfg);
     return (int)masters.size() - 1;
@@ -596,6 +607,22 @@ int xref_mvs_export(void *h, int idx, double *rec, int *lids7) {
   const int g = c->n;
   const int l[7] = {in.li_d, in.li_g, in.li_s, in.li_di, in.li_si, in.li_sf, in.li_BRA_sf_GND};
   for (int i = 0; i < 7; ++i) lids7[i] = (l[i] == g) ? -1 : l[i];
+  return k;
+}
+
+// Any model of the ADMS translator's registry: record in the evaluator's field order + the unknowns' LIDs (-1 = ground)
+int xref_adms_export(void *h, int idx, const char *name, double *rec, int *lids, int *n_lids) {
+  Ctx *c = (Ctx *)h;
+  const std::string nm(name);
+  int k = -1, nl = 0;
+#ifdef XB_HAVE_ADMS_ORACLE
+#define XB_ORACLE_FILL(nm_, ns_) if (nm == #nm_) { ns_::Instance &in = *static_cast<ns_::Instance *>(c->insts[idx].inst); \
+    k = adms_fill_##nm_(in, rec, lids); nl = in.getNumExtVars() + in.getNumIntVars(); }
+  XB_ADMS_ORACLE_LIST(XB_ORACLE_FILL)
+#undef XB_ORACLE_FILL
+#endif
+  for (int i = 0; i < nl; ++i) if (lids[i] == c->n) lids[i] = -1;
+  *n_lids = nl;
   return k;
 }
 

@@ -9,9 +9,14 @@
 #endif
 #include "../../xyce_b200/csrc/bsim4_instance.h"
 #include "../../xyce_b200/csrc/diode_eval.h"
+#include <string>
 #include "../../xyce_b200/csrc/mos1_eval.h"
 #include "../../xyce_b200/csrc/bjt_eval.h"
 #include "../../xyce_b200/csrc/adms_mvs_eval.h"
+#if __has_include("../../xyce_b200/csrc/gen_adms/registry.h")
+#include "../../xyce_b200/csrc/gen_adms/registry.h"      // evaluators written by the ADMS translator
+#define XB_HAVE_ADMS_GEN 1
+#endif
 
 using namespace xb;
 using namespace xb::b4;
@@ -201,6 +206,24 @@ int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const
     out[k++] = 1;
   }
   return k;
+}
+
+// One instance of a translated ADMS model through the host build of its generated evaluator.
+// out = F, Q (nodes each), JF, JQ (slots each); returns the number of values or -1 for an unknown model.
+int xbh_adms_gen_eval(const char *name, const double *rec, const double *Vn, double gmin, double *out) {
+#ifdef XB_HAVE_ADMS_GEN
+  const std::string nm(name);
+#define XB_GEN_EVAL(i, nm_) if (nm == #nm_) { typedef xb::adms::gen_##nm_::Traits T; T::Rec R; T::Out o; real V[T::kNodes]; \
+    for (int k = 0; k < T::kNumFields; ++k) R.f[k] = rec[k]; for (int k = 0; k < T::kNodes; ++k) V[k] = Vn[k]; \
+    SolverFlags S{}; S.gmin = gmin; T::eval(S, R, V, o); int k = 0; \
+    for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.F[r]); for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.Q[r]); \
+    for (int s = 0; s < T::kSlots; ++s) out[k++] = to_double(o.JF[s]); for (int s = 0; s < T::kSlots; ++s) out[k++] = to_double(o.JQ[s]); \
+    return k; }
+  XB_ADMS_GEN_LIST(XB_GEN_EVAL)
+#undef XB_GEN_EVAL
+#endif
+  (void)name; (void)rec; (void)Vn; (void)gmin; (void)out;
+  return -1;
 }
 
 void xbh_b4_slot_tables(int *row, int *col) {

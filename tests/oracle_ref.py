@@ -102,6 +102,16 @@ class RefCircuit:
         info = self.inst_info(idx)
         return dict(rec=rec[:k].copy(), flags=flags.value, lids=lids, sto0=info["sto0"], sta0=info["sta0"])
 
+    def adms_export(self, idx, name):
+        """record (field order of the ADMS translator's evaluator) and unknown LIDs of an instance of a translated model"""
+        rec = np.zeros(512)
+        lids = np.zeros(64, dtype=np.int32)
+        nl = C.c_int()
+        k = self.lib.xref_adms_export(self.h, idx, name.encode(), dptr(rec), iptr(lids), C.byref(nl))
+        assert k >= 0, "model %s is not in the oracle's ADMS registry" % name
+        info = self.inst_info(idx)
+        return dict(rec=rec[:k].copy(), flags=0, lids=lids[:nl.value].copy(), sto0=info["sto0"], sta0=info["sta0"])
+
     def enable_lead_currents(self):
         """DeviceInstance::enableLeadCurrentCalc on every instance (before finalize)"""
         self.lib.xref_enable_lead_currents(self.h)

@@ -1,0 +1,119 @@
+"""The ADMS translator (xyce_b200/adms/translate.py: admsXml `_nosac` C++ -> single-source evaluator): every
+translated model against the reference's own generated class compiled into oracle/_ref.
+CPU part: the generated evaluator compiled for the host (same statements, no FMA contraction) must reproduce the
+reference object to the last bits; the translation of MVS 2.0.0 ETSOI must also agree with the hand restatement
+(adms_mvs_eval.h).  GPU part (marked gpu): the same through xgpu_simple_group_add / the generic kernel."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import oracle_ref
+from adms_common import ADMS_CARDS, BIAS, adms_circuit, bias_vector
+from b4_common import rel_err, solver_state
+from dev_common import HostDevices, assemble
+
+pytestmark = pytest.mark.skipif(not oracle_ref.available(), reason="oracle/_ref not built")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import xyce_b200
+from xyce_b200.capi import Engine
+
+MODELS = {m["name"]: m for m in Engine.adms_gen_models()}
+PAIRS = [(m, c) for m in sorted(ADMS_CARDS) for c in sorted(ADMS_CARDS[m])]
+
+
+def test_registry_lists_the_translated_models():
+    assert set(ADMS_CARDS) <= set(MODELS), "build with the reference tree present translates %s" % sorted(ADMS_CARDS)
+    e = MODELS["mvs_2_0_0_etsoi"]
+    assert (e["nodes"], e["ext"], e["slots"]) == (7, 3, 17) and "M:type" in e["fields"]
+    k = MODELS["ekv_va"]
+    assert (k["nodes"], k["ext"], k["slots"]) == (4, 4, 16) and "I:L" in k["fields"] and "M:L" not in k["fields"]
+    assert "I:admsTemperature" in k["fields"]
+
+
+def host_eval(hd, name, info, rec, V, gmin=1e-12):
+    n, s = info["nodes"], info["slots"]
+    out = np.zeros(2 * n + 2 * s)
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    k = hd.lib.xbh_adms_gen_eval(name.encode(), dp(rec), dp(np.asarray(V, dtype=np.float64)), C.c_double(gmin), out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert k == len(out), k
+    z = np.zeros(n)
+    return dict(F=out[:n], Q=out[n:2 * n], FL=z, QL=z, JF=out[2 * n:2 * n + s], JQ=out[2 * n + s:])
+
+
+@pytest.mark.parametrize("model,card", PAIRS)
+@pytest.mark.parametrize("case", ["tran1", "dcop2"])
+def test_generated_evaluator_on_host_equals_reference_object(model, card, case):
+    info = MODELS[model]
+    hd = HostDevices()
+    ref = adms_circuit(oracle_ref.RefCircuit, model, card, info["ext"], n_dev=8, seed=2)
+    flags = dict(tran1=dict(transient=1, newtonIter=1), dcop2=dict(dcop=1, tranop=1, newtonIter=2))[case]
+    ref.set_flags(**flags)
+    rng = np.random.default_rng(11)
+    exports = [ref.adms_export(i, model) for i in range(ref.n_inst)]
+    x = bias_vector(model, ref.n, [e["lids"] for e in exports], rng)
+    want = ref.load(x)
+    assert not any(np.any(np.isnan(v)) for v in want.values())
+    per, lids = [], []
+    for i in range(ref.n_inst):
+        e = exports[i]
+        assert len(e["rec"]) == len(info["fields"]) and len(e["lids"]) == info["nodes"]
+        V = [x[g] if g >= 0 else 0.0 for g in e["lids"]]
+        per.append(host_eval(hd, model, info, e["rec"], V)); lids.append(e["lids"])
+    asm = assemble(per, lids, info["slot_row"], info["slot_col"], ref.n, ref.rowptr, ref.colind)
+    for k in ("f", "q", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(asm[k], want[k], scale) < 1e-13, (model, card, case, k)      # same statements: last-bit agreement
+    assert np.any(want["dFdx"])
+    if model == "ekv_va":
+        assert np.any(want["q"]) and np.any(want["dQdx"])      # dynamic contributions are exercised
+
+
+@pytest.mark.parametrize("card", sorted(ADMS_CARDS["mvs_2_0_0_etsoi"]))
+def test_translated_mvs_agrees_with_the_hand_restatement(card):
+    """adms_mvs_eval.h (dual numbers, written by hand in round 1) and the translator's output for the same model."""
+    from dev_common import SIMPLE
+    type_id, key, nodes, nstore, nstate, srow, scol = SIMPLE["mvs"]
+    info = MODELS["mvs_2_0_0_etsoi"]
+    hd = HostDevices()
+    ref = adms_circuit(oracle_ref.RefCircuit, "mvs_2_0_0_etsoi", card, 3, n_dev=6, seed=4)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-0.6, 1.0, ref.n)
+    for i in range(ref.n_inst):
+        eg, eh = ref.adms_export(i, "mvs_2_0_0_etsoi"), ref.dev_export(i, "mvs")
+        V = [x[g] if g >= 0 else 0.0 for g in eg["lids"]]
+        a = host_eval(hd, "mvs_2_0_0_etsoi", info, eg["rec"], V)
+        b = hd.simple(type_id, eh, dict(transient=1, newtonIter=1), V, [], [], [], nodes, len(srow), 0, 0)
+        assert list(info["slot_row"]) == list(srow) and list(info["slot_col"]) == list(scol)
+        for k in ("F", "JF"):
+            sc = 1e-3 * np.max(np.abs(b[k]))
+            assert rel_err(a[k], b[k], sc) < 1e-12, (card, i, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,card", PAIRS)
+def test_gpu_generic_adms_kernel_matches_reference_object(model, card):
+    info = MODELS[model]
+    ref = adms_circuit(oracle_ref.RefCircuit, model, card, info["ext"], n_dev=200, seed=5)
+    ex = [ref.adms_export(i, model) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(info["type"], np.array([e["rec"] for e in ex]), [0] * len(ex), np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.finalize()
+    rng = np.random.default_rng(6)
+    for case, flags in (("tran1", dict(transient=1, newtonIter=1)), ("dcop2", dict(dcop=1, tranop=1, newtonIter=2))):
+        x = bias_vector(model, ref.n, [e["lids"] for e in ex], rng)
+        ref.set_flags(**flags)
+        want = ref.load(x)
+        got = eng.load_host(x, solver_state(**flags))
+        for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+            scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+            assert rel_err(got[k], want[k], scale) < 1e-12, (model, card, case, k)
+        assert np.any(want["dFdx"] != 0.0) and eng.all_converged()
+    eng.close()

@@ -133,6 +133,22 @@ class Engine:
         self._chk(self.lib.xgpu_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    @staticmethod
+    def adms_gen_models():
+        """Models of the ADMS translator compiled into the library (xgpu_adms_gen_info): list of dicts with
+        name, type (for add_simple_group), nodes, ext, slots, fields, slot_row, slot_col."""
+        lib = load_library()
+        out = []
+        for idx in range(lib.xgpu_adms_gen_count()):
+            name, fields = C.c_char_p(), C.c_char_p()
+            info = (C.c_int32 * 5)()
+            rows, cols = (C.c_int32 * 512)(), (C.c_int32 * 512)()
+            if lib.xgpu_adms_gen_info(idx, C.byref(name), C.byref(fields), info, rows, cols) != 0:
+                continue
+            out.append(dict(name=name.value.decode(), type=info[0], nodes=info[1], ext=info[2], slots=info[3],
+                            fields=fields.value.decode().split(), slot_row=list(rows[:info[3]]), slot_col=list(cols[:info[3]])))
+        return out
+
     def newton_step_host(self, x, ss, qscalar, fscalar, hist=None, dx=None, rhs=None):
         """xgpu_newton_step_host: one Newton iteration (load, stamp, J and r, LU refactor, solves) behind host buffers."""
         x = _f64(x)

@@ -421,6 +421,17 @@ int xgpu_simple_field_count(int type) {
   return ti ? ti->nfields : -1;
 }
 
+int xgpu_adms_gen_count(void) { return xb::simple::adms_gen_count(); }
+int xgpu_adms_gen_info(int idx, const char **name, const char **fields, int32_t *info5, int32_t *slot_row, int32_t *slot_col) {
+  const xb::simple::TypeInfo *ti = xb::simple::type_info(xb::simple::kAdmsGenBase + idx);
+  if (idx < 0 || idx >= xb::simple::adms_gen_count() || !ti) return 1;
+  if (name) *name = xb::simple::adms_gen_name(idx);
+  if (fields) *fields = xb::simple::adms_gen_fields(idx);
+  if (info5) { info5[0] = xb::simple::kAdmsGenBase + idx; info5[1] = ti->nodes; info5[2] = xb::simple::adms_gen_ext(idx); info5[3] = ti->slots; info5[4] = ti->nfields; }
+  for (int s = 0; s < ti->slots; ++s) { if (slot_row) slot_row[s] = ti->slot_row[s]; if (slot_col) slot_col[s] = ti->slot_col[s]; }
+  return 0;
+}
+
 int xgpu_finalize(xgpu_ctx *ctx) {
   if (!ctx) return 1;
   if (ctx->finalized) return 0;

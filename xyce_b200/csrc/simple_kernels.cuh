@@ -8,6 +8,13 @@ namespace xb {
 namespace simple {
 
 enum Type { kDiode = 1, kMos1 = 2, kBjt = 3, kRlc = 4, kMvs = 5 };
+// Models produced by the ADMS translator (xyce_b200/adms/translate.py -> gen_adms/registry.h at build time) take the type
+// ids kAdmsGenBase + position in the registry; adms_gen_* describe them to the callers of xgpu_simple_group_add.
+constexpr int kAdmsGenBase = 100;
+int adms_gen_count();
+const char *adms_gen_name(int idx);        // nullptr when idx is out of range
+const char *adms_gen_fields(int idx);      // space-separated record fields: "M:x" model member, "I:x" instance member
+int adms_gen_ext(int idx);                 // number of external nodes
 
 struct GroupDev {
   int type, n;
