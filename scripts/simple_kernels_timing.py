@@ -13,8 +13,17 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 out_path = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/simple_kernels.json"
 res = []
 cases = [("diode", 1, None), ("mos1", 2, "basic"), ("bjt", 3, "basic"), ("mvs", 5, "nmos")]
+# models written by the ADMS translator (generic kernel adms_gen_kernel<Traits>)
+from adms_common import ADMS_CARDS, adms_circuit
+GEN = {m["name"]: m for m in xyce_b200.capi.Engine.adms_gen_models()}
+cases += [("adms:" + n, GEN[n]["type"], sorted(ADMS_CARDS[n])[0]) for n in sorted(GEN) if n in ADMS_CARDS]
 for kind, tid, card in cases:
-    if kind == "diode":
+    if kind.startswith("adms:"):
+        g = GEN[kind[5:]]
+        ref = adms_circuit(oracle_ref.RefCircuit, g["name"], card, g["ext"], n_dev=4, seed=1)
+        ex = [ref.adms_export(i, g["name"]) for i in range(ref.n_inst)]
+        nodes, nstore, nstate, srow, scol = g["nodes"], 0, 0, g["slot_row"], g["slot_col"]
+    elif kind == "diode":
         ref = diode_circuit(oracle_ref.RefCircuit, sorted(DIODE_CARDS)[0], n_dev=4, seed=1)
         ex = [ref.diode_export(i) for i in range(ref.n_inst)]
         nodes, nstore, nstate, srow, scol = 3, 3, 0, DIODE_SLOT_ROW, DIODE_SLOT_COL
@@ -40,6 +49,8 @@ for kind, tid, card in cases:
     ss = SolverState(transientFlag=1, newtonIter=1)
     rng = np.random.default_rng(3)
     x = rng.uniform(-0.3, 0.8, n_unk)
+    if kind == "adms:mvs_2_0_0_hemt":
+        x[5::nn] = rng.uniform(-0.6, -0.02, N)      # V(sf) window of the HEMT variant (tests/adms_common.py)
     eng.load_host(x, ss)
     b = [eng.device_buffer(i) for i in range(11)]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")

@@ -117,3 +117,54 @@ def test_gpu_generic_adms_kernel_matches_reference_object(model, card):
             assert rel_err(got[k], want[k], scale) < 1e-12, (model, card, case, k)
         assert np.any(want["dFdx"] != 0.0) and eng.all_converged()
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_ekv_inverter_dcop_and_tran_match_reference_flow():
+    """CMOS inverter from two instances of the TRANSLATED EKV 2.6 model (static + dynamic contributions, temperature
+    update), PULSE input, load capacitor: DC operating point and .TRAN on the GPU against the same driver around the
+    reference's generated class and Kundert Sparse -- identical step sequence and Newton counts, waveforms within
+    RELTOL / ABSTOL."""
+    info = MODELS["ekv_va"]
+    IN, VDD, OUT, BR_IN, BR_DD = range(5)
+    ref = oracle_ref.RefCircuit(5)
+    tn, pn, inn = ADMS_CARDS["ekv_va"]["nmos"]
+    tp, pp, inp = ADMS_CARDS["ekv_va"]["pmos"]
+    ref.add_dev_model("adms:ekv_va", "nmod", tn, 1, pn)
+    ref.add_dev_model("adms:ekv_va", "pmod", tp, 1, pp)
+    ref.add_dev_instance("adms:ekv_va", "M:n", "nmod", [OUT, IN, -1, -1], inn)
+    ref.add_dev_instance("adms:ekv_va", "M:p", "pmod", [OUT, IN, VDD, VDD], inp)
+    g, c = [], []
+    for node, br in ((IN, BR_IN), (VDD, BR_DD)):
+        g.append((node, br, 1.0)); g.append((br, node, 1.0))
+    c.append((OUT, OUT, 20e-15))
+    lin = dict(g_row=np.array([t[0] for t in g], dtype=np.int32), g_col=np.array([t[1] for t in g], dtype=np.int32),
+               g_val=np.array([t[2] for t in g]), c_row=np.array([t[0] for t in c], dtype=np.int32),
+               c_col=np.array([t[1] for t in c], dtype=np.int32), c_val=np.array([t[2] for t in c]))
+    # PULSE(0 1.8 0.1n 0.1n 0.1n 0.5n 1.2n) on the input, DC 1.8 V supply
+    src = dict(row=np.array([BR_IN, BR_DD], dtype=np.int32), scale=np.ones(2), type=np.array([1, 0], dtype=np.int32),
+               params=np.array([[0.0, 1.8, 1e-10, 1e-10, 1e-10, 5e-10, 1.2e-9], [1.8, 0, 0, 0, 0, 0, 0]]))
+    ref.add_pattern_entries(np.concatenate([lin["g_row"], lin["c_row"]]), np.concatenate([lin["g_col"], lin["c_col"]]))
+    ref.finalize()
+    x0 = np.zeros(ref.n); x0[VDD] = 1.8; x0[OUT] = 1.8
+    probes = list(range(ref.n))
+    ref.set_flags(transient=1)
+    want = ref.tran_run(x0, 1.0e-9, 1e-11, probes, lin, src, dcop=1)
+    ex = [ref.adms_export(i, "ekv_va") for i in range(2)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(info["type"], np.array([e["rec"] for e in ex]), [0, 0], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.set_linear(lin["g_row"], lin["g_col"], lin["g_val"], lin["c_row"], lin["c_col"], lin["c_val"])
+    eng.set_sources(src["row"], src["scale"], src["type"], src["params"])
+    eng.finalize()
+    got = eng.tran_run(x0, 1.0e-9, 1e-11, probes, dcop=1)
+    eng.close()
+    assert want["rc"] == 0 and got["rc"] == 0, got.get("error")
+    assert got["stats"]["dcop_newton_iters"] == want["stats"]["dcop_newton_iters"] >= 2
+    assert got["stats"]["accepted"] == want["stats"]["accepted"] and got["stats"]["rejected"] == want["stats"]["rejected"]
+    assert np.array_equal(got["steps"][:, 2], want["steps"][:, 2])
+    tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
+    assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
+    assert want["wave"][0, OUT] > 1.7 and np.min(want["wave"][:, OUT]) < 0.1      # the inverter switches
