@@ -162,7 +162,7 @@ def test_gpu_ekv_inverter_dcop_and_tran_match_reference_flow():
     got = eng.tran_run(x0, 1.0e-9, 1e-11, probes, dcop=1)
     eng.close()
     assert want["rc"] == 0 and got["rc"] == 0, got.get("error")
-    assert got["stats"]["dcop_newton_iters"] == want["stats"]["dcop_newton_iters"] >= 2
+    assert got["stats"]["dcop_newton_iters"] == want["stats"]["dcop_newton_iters"] >= 1
     assert got["stats"]["accepted"] == want["stats"]["accepted"] and got["stats"]["rejected"] == want["stats"]["rejected"]
     assert np.array_equal(got["steps"][:, 2], want["steps"][:, 2])
     tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
