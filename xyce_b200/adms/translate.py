@@ -213,7 +213,9 @@ def emit(info, name):
     out.append("struct Out { real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots]; };\n")
     out.append("XB_HD real adms_vt(real T) { return kKoverQ * T; }\n")
     out.append("XB_HD real adms_max(real a, real b) { return a < b ? b : a; }\nXB_HD real adms_min(real a, real b) { return b < a ? b : a; }\n")
-    out.append("XB_HD void evaluate(const SolverFlags &S, const Rec &R, const real *V, Out &o) {\n")
+    out.append("// RecT: anything with f[k] -> field k (Rec on the host; on the device a view that loads a field where it is used,\n"
+               "// so that a 76-field record does not sit in registers for the whole evaluation)\n")
+    out.append("template <class RecT>\nXB_HD void evaluate(const SolverFlags &S, const RecT &R, const real *V, Out &o) {\n")
     out.append("  real probeVars[kProbes];\n  real staticContributions[kNodes], dynamicContributions[kNodes];\n")
     out.append("  real d_staticContributions[kNodes][kProbes], d_dynamicContributions[kNodes][kProbes];\n")
     out.append("  real noiseContribsPower[16], noiseContribsExponent[16];\n  (void)noiseContribsPower; (void)noiseContribsExponent; (void)S;\n")
@@ -229,7 +231,7 @@ def emit(info, name):
     out.append("// what the generic kernel (simple_kernels.cu: adms_gen_kernel<Traits>) and the registry need\n")
     out.append("struct Traits {\n  typedef gen_%s::Rec Rec;\n  typedef gen_%s::Out Out;\n" % (name, name))
     out.append("  static constexpr int kNodes = gen_%s::kNodes, kExt = gen_%s::kExt, kSlots = gen_%s::kSlots, kNumFields = gen_%s::kNumFields;\n" % (name, name, name, name))
-    out.append("  static XB_HD void eval(const SolverFlags &S, const Rec &R, const real *V, Out &o) { evaluate(S, R, V, o); }\n")
+    out.append("  template <class RecT> static XB_HD void eval(const SolverFlags &S, const RecT &R, const real *V, Out &o) { evaluate(S, R, V, o); }\n")
     out.append("  static const char *name() { return \"%s\"; }\n  static const char *fields() { return XB_ADMS_GEN_%s_FIELDS; }\n" % (name, name))
     out.append("  static const int *slot_row() { return kSlotRow; }\n  static const int *slot_col() { return kSlotCol; }\n};\n")
     out.append("}  // namespace gen_%s\n}  // namespace adms\n}  // namespace xb\n" % name)

@@ -7,12 +7,6 @@
 #include "adms_mvs_eval.h"
 #include "bjt_eval.h"
 #include "mos1_eval.h"
-#if defined(__has_include)
-#if __has_include("gen_adms/registry.h")
-#include "gen_adms/registry.h"      // evaluators translated from admsXml output at build time
-#define XB_HAVE_ADMS_GEN 1
-#endif
-#endif
 
 namespace xb {
 namespace simple {
@@ -192,34 +186,6 @@ __global__ void __launch_bounds__(128) mvs_kernel(GroupDev g, b4::LoadArgs a) {
   store_planes<M::Out, M::kNodes, M::kSlots>(g, a, o, i);
 }
 
-// Any model translated from admsXml's `_nosac` output (xyce_b200/adms/translate.py): same shape as the hand-restated
-// MVS above -- flat record, node voltages through the gather map, static + dynamic contributions and their probe
-// derivatives copied onto rows and stamp slots; no limiting, no store / state.
-template <class T>
-__global__ void __launch_bounds__(128) adms_gen_kernel(GroupDev g, b4::LoadArgs a) {
-  xb::pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
-  const int n = g.n;
-  typename T::Rec R;
-#pragma unroll
-  for (int k = 0; k < T::kNumFields; ++k) R.f[k] = __ldg(g.rec + (size_t)k * n + i);
-  real V[T::kNodes];
-#pragma unroll
-  for (int t = 0; t < T::kNodes; ++t) V[t] = gatherv(a.sol, __ldg(g.lids + (size_t)t * n + i));
-  typename T::Out o;
-  T::eval(a.S, R, V, o);
-  g.orig_flag[i] = 1;
-  store_planes<typename T::Out, T::kNodes, T::kSlots>(g, a, o, i);
-}
-
-#ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_INFO(idx_, nm_) {adms::gen_##nm_::Traits::kNodes, adms::gen_##nm_::Traits::kSlots, adms::gen_##nm_::Traits::kNumFields, 0, 0, \
-                                adms::gen_##nm_::Traits::slot_row(), adms::gen_##nm_::Traits::slot_col()},
-const TypeInfo kGenInfo[XB_ADMS_GEN_COUNT] = {XB_ADMS_GEN_LIST(XB_GEN_INFO)};
-#undef XB_GEN_INFO
-#endif
-
 const int kMvsRow[adms::mvs::kSlots] = {0, 0, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 6, 6, 6, 6};
 const int kMvsCol[adms::mvs::kSlots] = {3, 0, 2, 4, 4, 3, 5, 0, 4, 3, 5, 2, 6, 5, 4, 1, 3};
 const TypeInfo kMvsInfo = {adms::mvs::kNodes, adms::mvs::kSlots, adms::mvs::kNumFields, 0, 0, kMvsRow, kMvsCol};
@@ -250,45 +216,7 @@ const TypeInfo *type_info(int type) {
     case kMvs: return &kMvsInfo;
     default: break;
   }
-#ifdef XB_HAVE_ADMS_GEN
-  if (type >= kAdmsGenBase && type < kAdmsGenBase + XB_ADMS_GEN_COUNT) return &kGenInfo[type - kAdmsGenBase];
-#endif
-  return nullptr;
-}
-
-int adms_gen_count() {
-#ifdef XB_HAVE_ADMS_GEN
-  return XB_ADMS_GEN_COUNT;
-#else
-  return 0;
-#endif
-}
-const char *adms_gen_name(int idx) {
-#ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_NAME(i, nm_) if (idx == i) return adms::gen_##nm_::Traits::name();
-  XB_ADMS_GEN_LIST(XB_GEN_NAME)
-#undef XB_GEN_NAME
-#endif
-  (void)idx;
-  return nullptr;
-}
-const char *adms_gen_fields(int idx) {
-#ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_FIELDS(i, nm_) if (idx == i) return adms::gen_##nm_::Traits::fields();
-  XB_ADMS_GEN_LIST(XB_GEN_FIELDS)
-#undef XB_GEN_FIELDS
-#endif
-  (void)idx;
-  return nullptr;
-}
-int adms_gen_ext(int idx) {
-#ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_EXT(i, nm_) if (idx == i) return adms::gen_##nm_::Traits::kExt;
-  XB_ADMS_GEN_LIST(XB_GEN_EXT)
-#undef XB_GEN_EXT
-#endif
-  (void)idx;
-  return -1;
+  return adms_gen_type_info(type);      // translated ADMS models (adms_gen_kernels.cu), nullptr when unknown
 }
 
 void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
@@ -300,13 +228,7 @@ void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
     case kBjt: xb::launch_pdl(bjt_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
     case kRlc: xb::launch_pdl(rlc_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
     case kMvs: xb::launch_pdl(mvs_kernel, dim3(blocks), dim3(128), 0, s, g, a); break;
-    default:
-#ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_LAUNCH(i, nm_) if (g.type == kAdmsGenBase + i) xb::launch_pdl(adms_gen_kernel<adms::gen_##nm_::Traits>, dim3(blocks), dim3(128), 0, s, g, a);
-      XB_ADMS_GEN_LIST(XB_GEN_LAUNCH)
-#undef XB_GEN_LAUNCH
-#endif
-      break;
+    default: launch_adms_gen_group(g, a, s); break;
   }
 }
 

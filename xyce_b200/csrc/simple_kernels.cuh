@@ -32,6 +32,9 @@ struct TypeInfo { int nodes, slots, nfields, nstore, nstate; const int *slot_row
 const TypeInfo *type_info(int type);
 
 void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
+// adms_gen_kernels.cu (its own translation unit: fast arithmetic variant)
+const TypeInfo *adms_gen_type_info(int type);
+void launch_adms_gen_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
 
 }  // namespace simple
 }  // namespace xb
