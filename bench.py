@@ -30,7 +30,7 @@ BYTES_PER_EVAL_KERNEL = 1128.0   # the evaluation kernel's share of U1: 544 B re
 # dram__bytes_read.sum + dram__bytes_write.sum of one b4_eval launch on this workload (ncu --set full capture
 # summarised in profiles/r01_b4_eval_kernel_v3_ncu_summary.md): 31.7 MB read + 8.8 MB written (most of the freshly
 # written contribution planes stay in the 126 MB L2 until the assembly kernel reads them)
-EVAL_KERNEL_DRAM_BYTES = 40.5e6
+EVAL_KERNEL_DRAM_BYTES = 42.2e6
 FLOPS_PER_EVAL = 1889.0      # executed fp64 operations per evaluation, measured (xyce_b200/data/b4_flop_count.json)
 
 
@@ -476,9 +476,9 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": EVAL_KERNEL_DRAM_BYTES, "peak_source": peak_kind,
-                         "kernel": "b4_eval_uniform_kernel<default topology, 128 threads x 3 blocks/SM (168 regs), FMA + constant-bank exp/log/div>",
+                         "kernel": "b4_eval_uniform_kernel<default topology, 128 threads x 3 blocks/SM (168 regs), FMA + shared-reciprocal division, inlined sqrt, lean exp / log>",
                          "kernel_ms": 1e3 * eval_s, "algorithmic_bytes_per_eval": BYTES_PER_EVAL_KERNEL,
-                         "note": "the kernel is bound by instruction issue of a straight-line scalar FP64 program (dependency stalls, then instruction delivery), not by HBM; FP64 pipe 30-41 % busy (DESIGN.md section 3)",
+                         "note": "the kernel is bound by instruction issue of a straight-line scalar FP64 program (dependency stalls, then instruction delivery), not by HBM; FP64 pipe 30-41 % busy; half of the executed instructions are division / exp / log / sqrt (profiles/r02_b4_eval_kernel_v5_ncu_summary.md)",
                          "fp64": {"achieved_tflops": FLOPS_PER_EVAL * n_inst / eval_s / 1e12,
                                   "measured_peak_tflops": fp64_peak,
                                   "frac": FLOPS_PER_EVAL * n_inst / eval_s / 1e12 / fp64_peak}},

@@ -46,9 +46,15 @@ __device__ __forceinline__ double rcp_seed(double b) {
 // Reciprocal to <= 1 ulp: seed + two Newton steps.  Depends on b only, so the compiler shares one reciprocal between
 // every division by the same value (XB_DIV_MODE 1).
 __device__ __forceinline__ double rcp(double b) {
-  double r = rcp_seed(b);
-  r = fma(fma(-b, r, 1.0), r, r);
-  return fma(fma(-b, r, 1.0), r, r);
+  const double r = rcp_seed(b);
+#if defined(XB_RCP_NEWTON2)
+  const double r1 = fma(fma(-b, r, 1.0), r, r);
+  return fma(fma(-b, r1, 1.0), r1, r1);
+#else
+  // one third-order step: e = 1 - b r (|e| < 2^-20 from the seed), 1/b = r (1 + e + e^2 + ...): r + r (e + e^2) leaves e^3
+  const double e = fma(-b, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#endif
 }
 
 // <= 1 ulp for normal operands (mode 1: <= 2 ulp); b = 0, inf, denormal give NaN/inf like the seed does (the model code
@@ -73,7 +79,7 @@ __device__ __forceinline__ double rsqrt_seed(double b) {
   return r;
 }
 // Branch-free square root, <= 1 ulp for normal x: reciprocal-root seed, one coupled (Goldschmidt) step for sqrt and
-// 1/(2 sqrt), one residual correction.  0 and +inf are passed through by a select; x < 0 and NaN give NaN;
+// 1/(2 sqrt), one residual correction.  0 is passed through by a select; x < 0, NaN and +inf give NaN;
 // denormal x (never an argument of the model code) is not supported.
 __device__ __forceinline__ double sqrt_inline(double x) {
   const double y = rsqrt_seed(x);
@@ -82,7 +88,11 @@ __device__ __forceinline__ double sqrt_inline(double x) {
   g = fma(g, r, g);
   h = fma(h, r, h);
   g = fma(fma(-g, g, x), h, g);
+#if defined(XB_SQRT_INF)
   return (x == 0.0 || x == __longlong_as_double(0x7ff0000000000000LL)) ? x : g;
+#else
+  return x == 0.0 ? x : g;      // +inf gives NaN (0 * inf in the first product): never an argument of the model code
+#endif
 }
 
 // exp / log / sqrt are real functions (not inlined): the evaluation kernel is bound by instruction delivery, and
@@ -101,7 +111,36 @@ static __device__ __forceinline__ double sqrt(double x) { return sqrt_inline(x);
 #ifndef XB_LOG_INLINE
 #define XB_LOG_INLINE XB_FM_INLINE
 #endif
-static __device__ XB_EXP_INLINE double exp(double x) {
+static __device__ XB_EXP_INLINE double exp_general(double x);
+// exp on the range the model code uses (|x| < 700: results are normal numbers), inlined: no clamps, 2^n by an integer
+// add on the exponent field.  Everything else (NaN, +-inf, |x| >= 700) takes the saturating general version below, a
+// call.  ~30 instructions instead of ~52 (clamps with their constant loads, two-factor scaling, callee spills);
+// line-level attribution: profiles/r02_b4_eval_kernel_v4_ncu_summary.md.
+__device__ __forceinline__ double exp_lean(double x) {
+  if (!(fabs(x) < 700.0)) return exp_general(x);
+  const double shifter = 6755399441055744.0;              // 1.5 * 2^52
+  const double t = fma(x, kExpK[0], shifter);
+  const double fn = t - shifter;
+  double r = fma(-fn, kExpK[1], x);
+  r = fma(-fn, kExpK[2], r);
+  double p = kExpC[11];
+#pragma unroll
+  for (int k = 10; k >= 0; --k) p = fma(p, r, kExpC[k]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+}
+// Measured on B200 (C2 kernel / 1M instances, profiles/r02_b4_eval_ilp_experiments.md): general version through a call
+// 54.3 / 375.8 us, lean version inlined at its 36 call sites 54.3 / 373.8 us (+1 250 static instructions), lean version
+// as ONE real function 54.3 / 372.7 us -> the default.
+#if defined(XB_EXP_CALL)
+static __device__ __forceinline__ double exp(double x) { return exp_general(x); }
+#elif defined(XB_EXP_LEAN_INLINE)
+static __device__ __forceinline__ double exp(double x) { return exp_lean(x); }
+#else
+static __device__ XB_EXP_INLINE double exp(double x) { return exp_lean(x); }
+#endif
+static __device__ XB_EXP_INLINE double exp_general(double x) {
   x = x < kExpK[3] ? kExpK[3] : x;          // NaN stays NaN (comparisons false)
   x = x > kExpK[4] ? kExpK[4] : x;
   const double shifter = 6755399441055744.0;              // 1.5 * 2^52
