@@ -978,10 +978,21 @@ int xgpu_newton_step_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_
     if (h_hist) { xb::vec::axpby(b[1], 1.0, b[1], -1.0, ctx->d_hist, ctx->n, ctx->stream); ++ctx->launches; }
     if (h_rhs) XG_CUDA(cudaMemcpyAsync(h_rhs, b[1], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (!ctx->dist->analyzed) { rc = xgpu_border_analyze(ctx, b[5]); if (rc != 0 && rc != 2) return rc; }
-    rc = xg_border_solve(ctx, b[5], b[1], b[2], xg_dist_multi(ctx) ? 1 : 0);
+    const bool defer = !xg_dist_multi(ctx) && !ctx->lu_repivot;
+    rc = xg_border_solve(ctx, b[5], b[1], b[2], xg_dist_multi(ctx) ? 1 : 0, defer);
     if (rc) return rc;
     XG_CUDA(cudaMemcpyAsync(h_dx, b[2], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    int status = 0;
+    if (defer) { rc = xg_lu_status(ctx, &status); if (rc) return rc; }      // the one synchronisation of the call
+    else XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (status & 5) {      // bad or sub-threshold pivot of the fixed sequence: re-pivot the interior, solve again
+      rc = xgpu_border_analyze(ctx, b[5]); ++ctx->dist->reanalyses;
+      if (rc != 0 && rc != 2) return rc;
+      rc = xg_border_solve(ctx, b[5], b[1], b[2], 0, false);
+      if (rc) return rc;
+      XG_CUDA(cudaMemcpyAsync(h_dx, b[2], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     XG_CUDA(cudaGetLastError());
     return 0;
   }

@@ -156,6 +156,6 @@ int xg_dist_reduce_border_rows(xgpu_ctx *ctx, double *const *vecs, int nvec);
 // every rank contributes k doubles (device); the world * k gathered values arrive in ctx->dist->h_pack (host, after the
 // stream synchronisation the caller does anyway)
 int xg_dist_allgather(xgpu_ctx *ctx, const double *d_send, int k);
-int xg_border_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x, int rhs_border_reduced);
+int xg_border_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x, int rhs_border_reduced, bool defer_status = false);
 
 int xg_fail(xgpu_ctx *c, int code, const std::string &msg);

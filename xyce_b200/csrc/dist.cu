@@ -338,7 +338,7 @@ int xg_dist_allgather(xgpu_ctx *ctx, const double *d_send, int k) {
   return 0;
 }
 
-int xg_border_solve(xgpu_ctx *ctx, const double *J, const double *rhs, double *x, int rhs_border_reduced) {
+int xg_border_solve(xgpu_ctx *ctx, const double *J, const double *rhs, double *x, int rhs_border_reduced, bool defer_status) {
   XgDist *d = ctx->dist;
   if (!d || !d->analyzed) return xg_fail(ctx, 113, "xgpu_border_analyze has not been called");
   const int ni = d->ni, ns = d->ns;
@@ -346,8 +346,10 @@ int xg_border_solve(xgpu_ctx *ctx, const double *J, const double *rhs, double *x
   // interior factorization (fixed pattern and pivot sequence; status checked like xgpu_lu_refactor)
   // A bad or sub-threshold pivot re-pivots HERE (host analysis of this rank's interior on the current values, whose
   // factor values are then already those of J) so that every rank still issues the same sequence of collectives.
+  // defer_status (single rank only): launches only, the caller reads the status word with its own synchronisation
+  // (xg_lu_status) and repeats the solve after a re-analysis if it has to.
   if (ni > 0) {
-    int rc = xgpu_lu_refactor(ctx, J);
+    int rc = (defer_status && !xg_dist_multi(ctx) && !ctx->lu_repivot) ? xg_lu_refactor_async(ctx, J) : xgpu_lu_refactor(ctx, J);
     if (rc == 2 || rc == 3) { rc = xgpu_border_analyze(ctx, J); ++d->reanalyses; }
     if (rc) return rc;
   }
@@ -565,7 +567,7 @@ int xgpu_border_analyze(xgpu_ctx *ctx, const double *d_vals) {
 
 int xgpu_border_solve(xgpu_ctx *ctx, const double *d_vals, const double *d_rhs, double *d_x, int rhs_border_reduced) {
   if (!ctx || !d_vals || !d_rhs || !d_x) return 100;
-  return xg_border_solve(ctx, d_vals, d_rhs, d_x, rhs_border_reduced);
+  return xg_border_solve(ctx, d_vals, d_rhs, d_x, rhs_border_reduced, false);
 }
 
 int xgpu_shared_reduce(xgpu_ctx *ctx, double *d_f, double *d_q, double *d_dFdxdVp, double *d_dQdxdVp) {
