@@ -7,6 +7,10 @@
 #include "../../xyce_b200/csrc/xb_real.h"
 #define XB_REAL xb::CountReal
 #endif
+#ifdef XB_TAINT
+#include "../../xyce_b200/csrc/xb_real.h"
+#define XB_REAL xb::TaintReal
+#endif
 #include "../../xyce_b200/csrc/bsim4_instance.h"
 #include "../../xyce_b200/csrc/diode_eval.h"
 #include <string>
@@ -77,12 +81,20 @@ int xbh_b4_eval(const double *model_d, const int *model_i, const double *size_d,
   GeneralEmitter e;
   std::memset(&e, 0, sizeof(e));
   real Vr[kNumNodes], so[13];
+#ifdef XB_TAINT
+  for (int t = 0; t < kNumNodes; ++t) Vr[t] = real(V12[t], true);      // the bias point: node voltages,
+  for (int t = 0; t < 13; ++t) so[t] = real(sto_old13[t], true);       // previous limiting voltages,
+  const real von_in(von_prev, true);                                   // carried threshold
+  xb::taint_counts() = xb::TaintCounts{};
+#else
   for (int t = 0; t < kNumNodes; ++t) Vr[t] = V12[t];
   for (int t = 0; t < 13; ++t) so[t] = sto_old13[t];
+  const real von_in(von_prev);
+#endif
 #ifdef XB_COUNT_OPS
   xb::op_counts() = xb::OpCounts{};
 #endif
-  evaluate(S, M, P, I, Vr, so, have_old != 0, real(von_prev), W, e);
+  evaluate(S, M, P, I, Vr, so, have_old != 0, von_in, W, e);
   std::memcpy(F, e.F, sizeof(e.F)); std::memcpy(Q, e.Q, sizeof(e.Q));
   std::memcpy(FL, e.FL, sizeof(e.FL)); std::memcpy(QL, e.QL, sizeof(e.QL));
   std::memcpy(JF, e.JF, sizeof(e.JF)); std::memcpy(JQ, e.JQ, sizeof(e.JQ));
@@ -106,6 +118,18 @@ void xbh_op_counts(unsigned long long *out) {
   out[0] = c.add; out[1] = c.mul; out[2] = c.div; out[3] = c.sqrt_; out[4] = c.exp_; out[5] = c.log_; out[6] = c.cmp;
 #else
   for (int i = 0; i < 7; ++i) out[i] = 0;
+#endif
+}
+
+// TaintReal build: operations of the last xbh_b4_eval call, [bias-independent | bias-dependent] x [add, mul, div, sqrt,
+// exp, log], then the divisions of a bias-dependent value by a bias-independent divisor
+void xbh_taint_counts(unsigned long long *out13) {
+#ifdef XB_TAINT
+  const xb::TaintCounts &c = xb::taint_counts();
+  for (int b = 0; b < 2; ++b) for (int k = 0; k < 6; ++k) out13[6 * b + k] = c.ops[b][k];
+  out13[12] = c.div_const_divisor;
+#else
+  for (int i = 0; i < 13; ++i) out13[i] = 0;
 #endif
 }
 

@@ -247,3 +247,49 @@ def test_load_host_with_pinned_buffers(zero_copy):
     for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
     eng.close()
+
+
+@pytest.mark.parametrize("variant", ["default", "igc", "igc2", "gidl", "capmod1", "rdsmod"])
+def test_per_instance_stamps_with_row_wise_scale(variant):
+    """Every terminal of every device sits on its own node, so each CSR row holds ONE instance's stamp row before any
+    assembly with other devices.  Entries are compared relative to max(|entry|, 1e-3 * largest entry of the SAME row of the
+    SAME instance) instead of a system-wide floor: the gate row (tunnelling currents, 1e-12 S and below) is held to its own
+    scale beside the drain row (1e-3 S); the only cancellation left under the floor is the one inside a KCL row.  F and Q
+    rows: relative to the largest |row term| of the same instance."""
+    if variant not in VARIANTS:
+        pytest.skip("no such card variant")
+    ref = isolated_devices(oracle_ref.RefCircuit, 24, variant, seed=21)
+    eng, _ = engine_from_ref(ref)
+    rng = np.random.default_rng(22)
+    x = rng.uniform(-0.2, 1.2, ref.n)
+    sto = rng.normal(0.3, 0.2, ref.n_sto)
+    von = rng.uniform(0.2, 0.6, ref.n_inst)
+    flags = FLAG_CASES["tran_iter1"]
+    ref.set_flags(**flags); ref.set_state(curr_sto=sto, next_sto=sto); ref.set_von(von)
+    eng.set_state(0, sto); eng.set_state(1, sto); eng.b4_set_von(0, von)
+    want, got = ref.load(x), eng.load_host(x, solver_state(**flags))
+    rowptr = ref.rowptr
+    worst = 0.0
+    for k in ("dFdx", "dQdx"):
+        w, g = want[k], got[k]
+        for r in range(ref.n):
+            a, b = rowptr[r], rowptr[r + 1]
+            if b == a:
+                continue
+            floor = 1e-3 * np.max(np.abs(w[a:b]))
+            if floor == 0.0:
+                assert not np.any(g[a:b]), (k, r)
+                continue
+            worst = max(worst, float(np.max(np.abs(g[a:b] - w[a:b]) / np.maximum(np.abs(w[a:b]), floor))))
+    assert worst < TOL, ("matrix", worst)
+    # vectors: unknowns of one instance = its 4 external nodes (4 * i ...) and its internal nodes
+    for k in ("f", "q"):
+        w, g = want[k], got[k]
+        for i in range(ref.n_inst):
+            rows = [l for l in ref.inst_info(i)["lids"] if 0 <= l < ref.n]
+            floor = 1e-3 * np.max(np.abs(w[rows]))
+            if floor == 0.0:
+                continue
+            worst = max(worst, float(np.max(np.abs(g[rows] - w[rows]) / np.maximum(np.abs(w[rows]), floor))))
+    assert worst < TOL, ("vectors", worst)
+    eng.close()

@@ -88,6 +88,45 @@ struct RealT {
   friend XBR_HD double to_double(const RealT &a) { return a.v; }
 };
 
+// xb::TaintReal   host only (analysis tool): every value carries a flag "depends on the bias point" (node voltages,
+//                   previous limiting voltages); operations are counted separately for bias-dependent and
+//                   bias-independent results, and divisions whose DIVISOR is bias-independent are counted on their own:
+//                   the work that could move into the per-bin / per-instance records (scripts/count_hoistable.py).
+#if !defined(__CUDA_ARCH__)
+struct TaintCounts { unsigned long long ops[2][6]; unsigned long long div_const_divisor; };
+inline TaintCounts &taint_counts() { static thread_local TaintCounts c{}; return c; }
+struct TaintReal {
+  double v; bool b;
+  TaintReal() : v(0.0), b(false) {}
+  TaintReal(double x) : v(x), b(false) {}
+  TaintReal(double x, bool bias) : v(x), b(bias) {}
+  static TaintReal mk(double x, bool bias, int kind) { ++taint_counts().ops[bias ? 1 : 0][kind]; return TaintReal(x, bias); }
+  TaintReal &operator+=(const TaintReal &o) { *this = mk(v + o.v, b || o.b, 0); return *this; }
+  TaintReal &operator-=(const TaintReal &o) { *this = mk(v - o.v, b || o.b, 0); return *this; }
+  TaintReal &operator*=(const TaintReal &o) { *this = mk(v * o.v, b || o.b, 1); return *this; }
+  TaintReal &operator/=(const TaintReal &o) { if (b && !o.b) ++taint_counts().div_const_divisor; *this = mk(v / o.v, b || o.b, 2); return *this; }
+  friend TaintReal operator-(const TaintReal &a) { return TaintReal(-a.v, a.b); }
+  friend TaintReal operator+(const TaintReal &a) { return a; }
+  friend TaintReal operator+(TaintReal a, const TaintReal &o) { a += o; return a; }
+  friend TaintReal operator-(TaintReal a, const TaintReal &o) { a -= o; return a; }
+  friend TaintReal operator*(TaintReal a, const TaintReal &o) { a *= o; return a; }
+  friend TaintReal operator/(TaintReal a, const TaintReal &o) { a /= o; return a; }
+  friend bool operator<(const TaintReal &a, const TaintReal &o) { return a.v < o.v; }
+  friend bool operator>(const TaintReal &a, const TaintReal &o) { return a.v > o.v; }
+  friend bool operator<=(const TaintReal &a, const TaintReal &o) { return a.v <= o.v; }
+  friend bool operator>=(const TaintReal &a, const TaintReal &o) { return a.v >= o.v; }
+  friend bool operator==(const TaintReal &a, const TaintReal &o) { return a.v == o.v; }
+  friend bool operator!=(const TaintReal &a, const TaintReal &o) { return a.v != o.v; }
+  friend TaintReal sqrt(const TaintReal &a) { return mk(::sqrt(a.v), a.b, 3); }
+  friend TaintReal exp(const TaintReal &a) { return mk(::exp(a.v), a.b, 4); }
+  friend TaintReal log(const TaintReal &a) { return mk(::log(a.v), a.b, 5); }
+  friend TaintReal rpow(const TaintReal &a, const TaintReal &o) { return mk(::pow(a.v, o.v), a.b || o.b, 4); }
+  friend TaintReal rtan(const TaintReal &a) { return TaintReal(::tan(a.v), a.b); }
+  friend TaintReal fabs(const TaintReal &a) { return TaintReal(::fabs(a.v), a.b); }
+  friend double to_double(const TaintReal &a) { return a.v; }
+};
+#endif
+
 using CountReal = RealT<CountPolicy>;
 using FastReal = RealT<FastDivPolicy>;
 
