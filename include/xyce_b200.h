@@ -81,6 +81,11 @@ int xgpu_b4_models_set(xgpu_ctx *ctx, int n_models, const double *model_d, const
 int xgpu_b4_group_add(xgpu_ctx *ctx, int n_inst, const double *inst_d, const int32_t *inst_i,
                       const int32_t *model_idx, const int32_t *size_idx, const int32_t *lids12,
                       const int32_t *sto_lid0, int sto_stride, const int32_t *sta_lid0, int sta_stride);
+/* Diagnostics: which mode-specialised build of the BSIM4 kernel the group's last evaluation ran.  The uniform-record
+ * kernel is compiled once per mode tuple (capMod, mobMod, igcMod, igbMod, rdsMod, dioMod, ...) listed in
+ * xyce_b200/csrc/bsim4_spec_tuples.def; a group whose model cards all carry one of them (VERSION >= 4.8, default
+ * topology, at most 64 model / bin runs) uses that object.  Returns the tuple id, -1 for the generic build. */
+int xgpu_b4_group_spec(const xgpu_ctx *ctx, int group);
 /* ---- small compact models: junction diode (type 1), MOSFET level 1 (2), Gummel-Poon BJT (3), ADMS-shaped
  * series RLC (4), ADMS-generated MVS 2.0.0 ETSOI transistor (5; N_DEV_ADMSmvs_2_0_0_etsoi.C) ----
  * One flat record per instance holding the model-card values and the temperature-adjusted instance

@@ -49,18 +49,22 @@ def test_benchmark_fixture_matches_field_lists():
         assert list(rec["names_" + key]) == lib.xgpu_b4_field_names(which).decode().split()
 
 
-def test_specialised_kernel_mode_set_is_consistent():
-    """the mode set substituted by scripts/gen_spec.py must be the one the launcher checks model cards against"""
-    import importlib.util
+def test_specialised_kernel_mode_tuples_are_consistent():
+    """bsim4_spec_tuples.def is the single source of the mode tuples: scripts/gen_spec.py substitutes them by name in
+    XB_B4_MODEL_I order, the launcher checks model cards against the same rows -- the name order must be the library's."""
+    import re
     src = open(os.path.join(ROOT, "scripts", "gen_spec.py")).read()
-    spec = eval("dict(" + src.split("SPEC = dict(")[1].split(")\n")[0] + ")")
-    hdr = open(os.path.join(ROOT, "xyce_b200", "csrc", "b4_kernels.cuh")).read()
-    modes = [int(v) for v in hdr.split("kSpecModes[17] = {")[1].split("}")[0].split(",")]
+    names_py = eval(src.split("NAMES = ")[1].split("]")[0] + "]")
     lib = xyce_b200.load_library()
     names = lib.xgpu_b4_field_names(1).decode().split()
-    assert len(names) == len(modes) == 17
-    for n, m in zip(names, modes):
-        if m == -2:
-            assert n not in spec
-        else:
-            assert spec[n] == m, n
+    assert names_py == names and len(names) == 17
+    rows = re.findall(r"^\s*X\(([-0-9, ]+)\)", open(os.path.join(ROOT, "xyce_b200", "csrc", "bsim4_spec_tuples.def")).read(), re.M)
+    ids = [int(r.split(",")[0]) for r in rows]
+    assert ids == list(range(len(ids))) and all(len(r.split(",")) == 18 for r in rows)
+    hdr = open(os.path.join(ROOT, "xyce_b200", "csrc", "bsim4_spec_tuples.def")).read()
+    assert "kNumSpecTuples = %d" % len(ids) in hdr
+    # every tuple has a launcher in the library
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", xyce_b200.capi.LIB_PATH], capture_output=True, text=True).stdout
+    for i in ids:
+        assert ("launch_b4_group_a2x%s" % ("" if i == 0 else str(i))) in syms

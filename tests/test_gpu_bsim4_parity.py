@@ -293,3 +293,30 @@ def test_per_instance_stamps_with_row_wise_scale(variant):
             worst = max(worst, float(np.max(np.abs(g[rows] - w[rows]) / np.maximum(np.abs(w[rows]), floor))))
     assert worst < TOL, ("vectors", worst)
     eng.close()
+
+
+@pytest.mark.parametrize("variant,want_spec", [("default", 0), ("igc", 1), ("capmod1", -1)])
+def test_mode_specialised_objects_are_picked_by_the_cards_mode_tuple(variant, want_spec):
+    """bsim4_spec_tuples.def: groups whose cards carry a listed mode tuple run that tuple's kernel object (same stamps
+    at 1e-12, checked inside run_case), every other card the generic build."""
+    ref = isolated_devices(oracle_ref.RefCircuit, 150, variant, seed=31, sorted_bins=True)
+    eng, _ = engine_from_ref(ref)
+    rng = np.random.default_rng(32)
+    x = rng.uniform(-0.2, 1.2, ref.n)
+    flags = FLAG_CASES["tran_iter1"]
+    ref.set_flags(**flags)
+    sto = rng.normal(0.3, 0.2, ref.n_sto); von = rng.uniform(0.2, 0.6, ref.n_inst)
+    ref.set_state(curr_sto=sto, next_sto=sto); ref.set_von(von)
+    eng.set_state(0, sto); eng.set_state(1, sto); eng.b4_set_von(0, von)
+    want, got = ref.load(x), eng.load_host(x, solver_state(**flags))
+    assert eng.b4_group_spec(0) == want_spec
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < TOL, (variant, k)
+    eng.set_option("b4_spec", 0)
+    eng.set_state(0, sto); eng.set_state(1, sto); eng.b4_set_von(0, von)
+    gen = eng.load_host(x, solver_state(**flags))
+    assert eng.b4_group_spec(0) == -1
+    for k in ("f", "dFdx", "dQdx"):
+        assert rel_err(gen[k], got[k], 1e-3 * np.max(np.abs(got[k]))) < TOL
+    eng.close()

@@ -133,6 +133,10 @@ class Engine:
         self._chk(self.lib.xgpu_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    def b4_group_spec(self, group=0):
+        """id of the mode-specialised kernel object the group's last evaluation ran, -1 = generic build"""
+        return int(self.lib.xgpu_b4_group_spec(self.h, int(group)))
+
     @staticmethod
     def adms_gen_models():
         """Models of the ADMS translator compiled into the library (xgpu_adms_gen_info): list of dicts with

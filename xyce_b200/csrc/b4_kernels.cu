@@ -264,7 +264,12 @@ void launch_variant(const GroupDev &g, const LoadArgs &a, const BinPack *packs, 
 #ifndef XB_SPEC
 #define XB_SPEC 0
 #endif
-#if XB_SPEC
+#ifndef XB_SPEC_ID
+#define XB_SPEC_ID 0
+#endif
+#if XB_SPEC && XB_SPEC_ID > 0
+#define XB_LAUNCH_NAME XB_CAT(XB_CAT(XB_CAT(launch_b4_group_a, XB_ARITH), x), XB_SPEC_ID)
+#elif XB_SPEC
 #define XB_LAUNCH_NAME XB_CAT(XB_CAT(launch_b4_group_a, XB_ARITH), x)
 #elif XB_LOCKSTEP
 #define XB_LAUNCH_NAME XB_CAT(XB_CAT(launch_b4_group_a, XB_ARITH), s)

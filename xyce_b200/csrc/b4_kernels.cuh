@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "bsim4_instance.h"
+#include "bsim4_spec_tuples.def"
 
 namespace xb {
 namespace b4 {
@@ -76,8 +77,12 @@ constexpr int kMaxUniformRuns = 64;   // groups with more distinct runs use the 
 #else
 #define XB_B4_EXTRA_SHAPES(X)
 #endif
+#if defined(XB_B4_FEW_SHAPES)      // additional mode-specialised objects: only the two shapes the launcher picks by itself
+#define XB_B4_LAUNCH_SHAPES(X) X(128, 3) X(128, 4)
+#else
 #define XB_B4_LAUNCH_SHAPES(X) \
   X(64, 4) X(64, 6) X(96, 4) X(128, 2) X(128, 3) X(128, 4) X(256, 1) X(384, 1) X(512, 1) XB_B4_EXTRA_SHAPES(X)
+#endif
 // (20-24 warps per SM -- 128 x 5, 128 x 6, 64 x 11 at 80-96 registers -- were measured and are slower at every
 // group size: the local-memory spills cost more than the occupancy gains; profiles/r01_b4_occupancy.json)
 
@@ -89,13 +94,23 @@ int launch_b4_group_a0(const GroupDev &g, const LoadArgs &a, int threads, int mi
 int launch_b4_group_a1(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
 int launch_b4_group_a2(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
 int launch_b4_group_a2s(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
-// mode-specialised build (scripts/gen_spec.py): only for groups whose model cards all carry kSpecModes
+// mode-specialised builds (scripts/gen_spec.py, one object per tuple of bsim4_spec_tuples.def): only for groups whose
+// model cards all carry that tuple
 int launch_b4_group_a2x(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
-// mode set of the specialised object in XB_B4_MODEL_I order; -2 = not specialised (dtype)
-constexpr int kSpecModes[17] = {2, 0, 1, -2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+int launch_b4_group_a2x1(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+int launch_b4_group_a2x2(const GroupDev &g, const LoadArgs &a, int threads, int minblocks, const BinPack *packs, int npacks, cudaStream_t stream);
+// mode sets of the specialised objects in XB_B4_MODEL_I order; -2 = not specialised (dtype)
+#define XB_SPEC_ROW(id, ...) {__VA_ARGS__},
+constexpr int kSpecModes[kNumSpecTuples][17] = {XB_B4_SPEC_TUPLES(XB_SPEC_ROW)};
+#undef XB_SPEC_ROW
+// spec_id: -1 = generic build, else the tuple's id
 inline int launch_b4_group(const GroupDev &g, const LoadArgs &a, int arith, int lockstep, int threads, int minblocks,
-                           const BinPack *packs, int npacks, cudaStream_t stream, bool spec = false) {
-  if (arith == 2 && spec && !lockstep && !g.general && packs) return launch_b4_group_a2x(g, a, threads, minblocks, packs, npacks, stream);
+                           const BinPack *packs, int npacks, cudaStream_t stream, int spec_id = -1) {
+  if (arith == 2 && spec_id >= 0 && !lockstep && !g.general && packs) {
+    if (spec_id == 0) return launch_b4_group_a2x(g, a, threads, minblocks, packs, npacks, stream);
+    if (spec_id == 1) return launch_b4_group_a2x1(g, a, threads, minblocks, packs, npacks, stream);
+    if (spec_id == 2) return launch_b4_group_a2x2(g, a, threads, minblocks, packs, npacks, stream);
+  }
   if (arith == 2) return lockstep ? launch_b4_group_a2s(g, a, threads, minblocks, packs, npacks, stream)
                                   : launch_b4_group_a2(g, a, threads, minblocks, packs, npacks, stream);
   if (arith == 1) return launch_b4_group_a1(g, a, threads, minblocks, packs, npacks, stream);

@@ -421,6 +421,12 @@ int xgpu_simple_field_count(int type) {
   return ti ? ti->nfields : -1;
 }
 
+// mode-specialised kernel object the group's last evaluation ran (id of bsim4_spec_tuples.def), -1 = generic build
+int xgpu_b4_group_spec(const xgpu_ctx *ctx, int group) {
+  if (!ctx || group < 0 || group >= (int)ctx->groups.size()) return -2;
+  return ctx->groups[group].last_spec;
+}
+
 int xgpu_adms_gen_count(void) { return xb::simple::adms_gen_count(); }
 int xgpu_adms_gen_info(int idx, const char **name, const char **fields, int32_t *info5, int32_t *slot_row, int32_t *slot_col) {
   const xb::simple::TypeInfo *ti = xb::simple::type_info(xb::simple::kAdmsGenBase + idx);
@@ -601,26 +607,32 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
         br.start = g.run_start[r]; br.count = g.run_count[r];
       }
       g.packs_valid = true;
-      g.spec_ok = true;
-      for (size_t r = 0; r < g.run_start.size(); ++r) {
-        const B4Model &M = ctx->h_models[g.run_model[r]];
-        int k = 0;
-#define CHK(name) if (kSpecModes[k] != -2 && M.name != kSpecModes[k]) g.spec_ok = false; ++k;
-        XB_B4_MODEL_I(CHK)
+      // the specialised object whose mode tuple every run's model card carries (bsim4_spec_tuples.def), or none
+      g.spec_id = -1;
+      for (int t = 0; t < kNumSpecTuples && g.spec_id < 0; ++t) {
+        bool ok = true;
+        for (size_t r = 0; r < g.run_start.size(); ++r) {
+          const B4Model &M = ctx->h_models[g.run_model[r]];
+          int k = 0;
+#define CHK(name) if (kSpecModes[t][k] != -2 && M.name != kSpecModes[t][k]) ok = false; ++k;
+          XB_B4_MODEL_I(CHK)
 #undef CHK
-        if (!(M.versionDouble >= 4.8)) g.spec_ok = false;      // the specialised build is the 4.8.2 evaluator
+          if (!(M.versionDouble >= 4.8)) ok = false;      // the specialised builds are the 4.8.2 evaluator
+        }
+        if (ok) g.spec_id = t;
       }
     }
     // b4_threads == 0: pick the block shape (measured on B200 at the C2 operating point,
     // profiles/r01_b4_kernel_variants_v3.json).  Once the kernel image is compact enough for the instruction
     // caches, 12 warps per SM (128 x 3, 168 registers) beat 8 warps without spills; the mode-specialised build
     // on large groups gains a little more from 16 warps (128 x 4).
-    const bool spec = ctx->b4_spec && uniform && g.spec_ok && ctx->b4_arith == 2 && !lockstep && !g.general;
+    const bool spec = ctx->b4_spec && uniform && g.spec_id >= 0 && ctx->b4_arith == 2 && !lockstep && !g.general;
     int threads = ctx->b4_threads, minblocks = ctx->b4_minblocks;
     if (threads == 0) { threads = 128; minblocks = (spec && g.n > 150000) ? 4 : 3; }      // crossover between 100k and 200k (profiles/r01_b4_occupancy.json)
     const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, threads, minblocks,
                                    uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream,
-                                   spec);
+                                   spec ? g.spec_id : -1);
+    g.last_spec = spec ? g.spec_id : -1;
     if (nl < 0) return fail(ctx, 19, "unsupported BSIM4 launch shape (b4_threads, b4_minblocks)");
     ctx->launches += nl;
   }

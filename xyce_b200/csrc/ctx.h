@@ -26,7 +26,8 @@ struct XgHostGroup {
   std::vector<int32_t> run_model, run_size, run_start, run_count;
   std::vector<xb::b4::BinPack> packs;
   bool packs_valid = false;
-  bool spec_ok = false;            // every run's model card carries the mode set of the specialised kernel build
+  int spec_id = -1;                // the mode-specialised kernel object that fits every run's model card (bsim4_spec_tuples.def), -1 = none
+  int last_spec = -1;              // object used by the last evaluation (diagnostics: xgpu_b4_group_spec)
 };
 
 // groups of the small compact models (diode, MOSFET level 1, BJT, ADMS-shaped rlc): flat per-instance records
