@@ -313,6 +313,13 @@ int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_stat
  * the threshold check, or every call under "lu_repivot") analyses on the host like xgpu_lu_analyze. */
 int xgpu_newton_step_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_state *ss, double qscalar, double fscalar,
                           const double *h_hist, double *h_dx, double *h_rhs);
+/* xgpu_load_host_jr pipelines when the circuit allows it (option "pipeline_host", default 1): every (model, bin) run of
+ * the BSIM4 group is evaluated in two parts ("pipe_percent" of its length first, default 50, set before xgpu_finalize);
+ * the rows / nonzeros that only the first part feeds -- a prefix for circuits numbered device by device, found in
+ * xgpu_finalize -- are assembled, combined and copied over PCIe on a second stream while the second part is evaluated.
+ * Same sums in the same order: bitwise the one-pass result.  info3 = {usable for this circuit, rows in the first window,
+ * nonzeros in the first window}. */
+int xgpu_pipe_info(const xgpu_ctx *ctx, long long *info3);
 /* which: 0 next store, 1 curr store, 2 next state, 3 curr state */
 int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h_vals);
 int xgpu_state_get(xgpu_ctx *ctx, int which, double *h_vals);

@@ -324,3 +324,33 @@ def test_newton_step_host_solves_the_system_the_loads_return(workload):
         scale = np.max(np.abs(want))
         assert np.max(np.abs(got - want)) <= 1e-9 * scale, (workload, it, float(np.max(np.abs(got - want))), scale)
     eng.close()
+
+
+@pytest.mark.parametrize("workload", ["inverters", "rings"])
+@pytest.mark.parametrize("percent", [50, 57])
+def test_pipelined_host_path_is_bitwise_the_one_pass_path(workload, percent):
+    """xgpu_load_host_jr in two parts (first part of every (model, bin) run evaluated, its destinations assembled,
+    combined and copied on a second stream while the second part is evaluated) against the one-pass path: J, r, store,
+    state, carried limiter thresholds bit for bit."""
+    w = wl.inverter_array(3000, store_noise=0.3) if workload == "inverters" else wl.ring_oscillator_array(40, 31)
+    qs, fs = 1.0 / 3e-12, 0.5
+    ss = solver_state(**FLAGS)
+    rng = np.random.default_rng(9)
+    x = w["x"] + rng.normal(0, 0.05, len(w["x"]))
+    out = {}
+    for pipe in (0, 1):
+        import xyce_b200
+        eng = wl.build_engine(w) if pipe == 0 else None
+        if pipe == 1:
+            # the share of the first part must be chosen before xgpu_finalize: build by hand like wl.build_engine does
+            eng = wl.build_engine(w, options={"pipe_percent": percent})
+        eng.set_option("pipeline_host", pipe)
+        eng.set_state(0, w["store"]); eng.set_state(1, w["store"]); eng.b4_set_von(0, w["von"])
+        r, J = eng.load_host_jr(x, ss, qs, fs)
+        out[pipe] = (r, J, eng.get_state(0), eng.get_state(2), eng.b4_get_von(0, w["n_inst"]), eng.pipe_info())
+        eng.close()
+    assert out[0][5][0] == out[1][5][0] == 1                 # both circuits are numbered device by device: they pipeline
+    assert out[1][5][1] > 0.3 * len(x) and out[1][5][2] > 0.3 * len(out[0][1])
+    for a, b in zip(out[0][:5], out[1][:5]):
+        assert np.array_equal(a, b)
+    assert np.any(out[0][1]) and np.any(out[0][0])

@@ -133,6 +133,12 @@ class Engine:
         self._chk(self.lib.xgpu_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    def pipe_info(self):
+        """(pipelines?, rows in the first window, nonzeros in the first window) of the pipelined host-buffer path"""
+        v = (C.c_longlong * 3)()
+        self._chk(self.lib.xgpu_pipe_info(self.h, v))
+        return int(v[0]), int(v[1]), int(v[2])
+
     def b4_group_spec(self, group=0):
         """id of the mode-specialised kernel object the group's last evaluation ran, -1 = generic build"""
         return int(self.lib.xgpu_b4_group_spec(self.h, int(group)))

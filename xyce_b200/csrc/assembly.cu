@@ -22,12 +22,13 @@ template <int NP>
 __device__ __forceinline__ void short_body(const GatherMapDev &m, const double *const (&in)[NP], double *const (&out)[NP],
                                            int d0, bool accumulate) {
   constexpr int U = ShortUnroll<NP>::U;
+  const int hi = m.d_hi < 0 ? m.ndst : m.d_hi;
   int32_t s[U][kEllMax];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int d = d0 + j * 256;
 #pragma unroll
-    for (int k = 0; k < kEllMax; ++k) s[j][k] = (k < m.ell_w && d < m.ndst) ? __ldg(m.ell + (size_t)k * m.ndst + d) : -1;
+    for (int k = 0; k < kEllMax; ++k) s[j][k] = (k < m.ell_w && d < hi) ? __ldg(m.ell + (size_t)k * m.ndst + d) : -1;
   }
   double val[U][kEllMax][NP];
 #pragma unroll
@@ -39,7 +40,7 @@ __device__ __forceinline__ void short_body(const GatherMapDev &m, const double *
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int d = d0 + j * 256;
-    if (d >= m.ndst || s[j][0] == kEllLong) continue;      // out of range / handled by the chunk blocks
+    if (d >= hi || s[j][0] == kEllLong) continue;          // out of the window / handled by the chunk blocks
     const bool tail = (s[j][1] == kEllTail) || (s[j][kEllMax - 1] == kEllTail);      // the flag sits in slot ell_w - 1
     double acc[NP];
 #pragma unroll
@@ -159,21 +160,22 @@ __global__ void __launch_bounds__(256) assemble_kernel(GatherMapDev ma, PlaneSet
   // produces the planes is still draining; wait here until that kernel has completed and flushed
   asm volatile("griddepcontrol.wait;" ::: "memory");
   int b = blockIdx.x;
-  if (b < ma.nchunks) { chunk_then_finish<NPA>(ma, pa, b, accumulate, sh); return; }
-  b -= ma.nchunks;
-  if (b < mb.nchunks) { chunk_then_finish<NPB>(mb, pb, b, accumulate, sh); return; }
-  b -= mb.nchunks;
+  const int ca = ma.with_chunks ? ma.nchunks : 0, cb = mb.with_chunks ? mb.nchunks : 0;
+  if (b < ca) { chunk_then_finish<NPA>(ma, pa, b, accumulate, sh); return; }
+  b -= ca;
+  if (b < cb) { chunk_then_finish<NPB>(mb, pb, b, accumulate, sh); return; }
+  b -= cb;
   // plane pointers into registers (static indices only: no local-memory copy of the parameter structs)
   if (b < short_a) {
     const double *in[NPA]; double *out[NPA];
 #pragma unroll
     for (int p = 0; p < NPA; ++p) { in[p] = pa.in[p]; out[p] = pa.out[p]; }
-    short_body<NPA>(ma, in, out, b * (256 * ShortUnroll<NPA>::U) + threadIdx.x, accumulate);
+    short_body<NPA>(ma, in, out, ma.d_lo + b * (256 * ShortUnroll<NPA>::U) + threadIdx.x, accumulate);
   } else {
     const double *in[NPB]; double *out[NPB];
 #pragma unroll
     for (int p = 0; p < NPB; ++p) { in[p] = pb.in[p]; out[p] = pb.out[p]; }
-    short_body<NPB>(mb, in, out, (b - short_a) * (256 * ShortUnroll<NPB>::U) + threadIdx.x, accumulate);
+    short_body<NPB>(mb, in, out, mb.d_lo + (b - short_a) * (256 * ShortUnroll<NPB>::U) + threadIdx.x, accumulate);
   }
 }
 
@@ -210,9 +212,10 @@ void launch_dependent(void (*kernel)(KArgs...), int blocks, cudaStream_t stream,
 template <int NP>
 void launch_np(const GatherMapDev &m, const PlaneSet &ps, bool accumulate, cudaStream_t stream) {
   const int per = 256 * ShortUnroll<NP>::U;
-  const int sb = (m.ndst + per - 1) / per;
+  const int sb = ((m.d_hi < 0 ? m.ndst : m.d_hi) - m.d_lo + per - 1) / per;
+  const int ch = m.with_chunks ? m.nchunks : 0;
   GatherMapDev none{};
-  if (m.nchunks + sb > 0) launch_dependent(assemble_kernel<NP, 1>, m.nchunks + sb, stream, m, ps, none, PlaneSet{}, sb, accumulate);
+  if (ch + sb > 0) launch_dependent(assemble_kernel<NP, 1>, ch + sb, stream, m, ps, none, PlaneSet{}, sb, accumulate);
 }
 
 }  // namespace
@@ -235,8 +238,8 @@ int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, do
   for (int p = 0; p < 4; ++p) { pv.in[p] = vplanes[p]; pv.out[p] = vdst[p]; }
   for (int p = 0; p < 2; ++p) { pm.in[p] = mplanes[p]; pm.out[p] = mdst[p]; }
   const int pv_ = 256 * ShortUnroll<4>::U, pm_ = 256 * ShortUnroll<2>::U;
-  const int vb = (mv.ndst + pv_ - 1) / pv_, mb = (mm.ndst + pm_ - 1) / pm_;
-  const int blocks = mv.nchunks + mm.nchunks + vb + mb;
+  const int vb = ((mv.d_hi < 0 ? mv.ndst : mv.d_hi) - mv.d_lo + pv_ - 1) / pv_, mb = ((mm.d_hi < 0 ? mm.ndst : mm.d_hi) - mm.d_lo + pm_ - 1) / pm_;
+  const int blocks = (mv.with_chunks ? mv.nchunks : 0) + (mm.with_chunks ? mm.nchunks : 0) + vb + mb;
   if (blocks == 0) return 0;
   launch_dependent(assemble_kernel<4, 2>, blocks, stream, mv, pv, mm, pm, vb, accumulate);
   return 1;

@@ -47,6 +47,9 @@ struct GatherMapDev {
   int ell_w = 0;
   int32_t *ell = nullptr;
   int32_t *done = nullptr;             // [nlong] chunk blocks finished so far (ticket counter; zero between launches)
+  // window of this launch over the short destinations: [d_lo, d_hi) (d_hi < 0 = ndst); with_chunks = 0 leaves the long
+  // destinations to another launch (pipelined host path: first the destinations fed by the first half of the instances)
+  int d_lo = 0, d_hi = -1, with_chunks = 1;
 };
 
 constexpr int kLongThreshold = 96;
@@ -61,6 +64,7 @@ void launch_gather(const GatherMapDev &m, int nplanes, const double *const *plan
 
 // Vector planes (4, map mv) and matrix planes (2, map mm) in the same launch.  Same sums in the same
 // order as two launch_gather calls; returns the number of kernel launches.
+// (windows: set d_lo / d_hi / with_chunks in copies of the maps)
 int launch_gather_fused(const GatherMapDev &mv, const double *const *vplanes, double *const *vdst, const GatherMapDev &mm,
                         const double *const *mplanes, double *const *mdst, bool accumulate, cudaStream_t stream);
 

@@ -34,6 +34,12 @@ cudaError_t upload(T **dst, const T *src, size_t count) {
   return e;
 }
 
+// first-part length of a run of `count` instances (pipelined host path)
+inline int xg_pipe_cut(const xgpu_ctx *ctx, int count) {
+  int cut = (int)(ctx->pipe_frac * count + 0.5);
+  return cut < 0 ? 0 : (cut > count ? count : cut);
+}
+
 cudaError_t upload_map(const GatherMapHost &h, GatherMapDev &d) {
   d.ndst = (int)h.ptr.size() - 1;
   d.total = (int64_t)h.src.size();
@@ -152,6 +158,9 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   for (double *b : ctx->buf) cudaFree(b);
   for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
   cudaFree(ctx->tran_pool); cudaFree(ctx->tran_ints); cudaFreeHost(ctx->tran_pinned); cudaFree(ctx->d_hist);
+  if (ctx->pipe.s2) cudaStreamDestroy(ctx->pipe.s2);
+  if (ctx->pipe.ev_a) cudaEventDestroy(ctx->pipe.ev_a);
+  if (ctx->pipe.ev_x) cudaEventDestroy(ctx->pipe.ev_x);
   xb::lu::free_plan(ctx->lu_dev);
   xg_dist_free(ctx);
   for (XgLinearPart *L : {&ctx->linG, &ctx->linC}) { cudaFree(L->rows); cudaFree(L->ptr); cudaFree(L->col); cudaFree(L->pos); cudaFree(L->val); }
@@ -177,6 +186,11 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   if (n == "b4_uniform" && (value == 0 || value == 1)) { ctx->b4_uniform = value; return 0; }
   if (n == "b4_lockstep" && (value == 0 || value == 1)) { ctx->b4_lockstep = value; return 0; }
   if (n == "b4_spec" && (value == 0 || value == 1)) { ctx->b4_spec = value; return 0; }
+  // "pipeline_host": 1 (default) = xgpu_load_host_jr evaluates in two parts and overlaps the PCIe transfer of the first
+  // window with the evaluation of the second part when the circuit's numbering allows it; "pipe_percent" = share of every
+  // run in the first part (before xgpu_finalize)
+  if (n == "pipeline_host" && (value == 0 || value == 1)) { ctx->pipeline_host = value; return 0; }
+  if (n == "pipe_percent" && value >= 10 && value <= 90 && !ctx->finalized) { ctx->pipe_frac = value / 100.0; return 0; }
   if (n == "lu_graphs" && (value == 0 || value == 1)) { ctx->lu_graphs = value; return 0; }
   // "lu_pivot_check": 1 (default) = the refactorization tests every pivot of the fixed sequence against KLU's threshold
   // (|pivot| >= 0.001 max |column|) and reports code 3 when one fails; "lu_repivot": 1 = KLU_REPIVOT=1 semantics, every
@@ -421,6 +435,13 @@ int xgpu_simple_field_count(int type) {
   return ti ? ti->nfields : -1;
 }
 
+// pipelined host-buffer path: {usable for this circuit, rows in the first window, nonzeros in the first window}
+int xgpu_pipe_info(const xgpu_ctx *ctx, long long *info3) {
+  if (!ctx || !info3) return 1;
+  info3[0] = ctx->pipe.ok ? 1 : 0; info3[1] = ctx->pipe.vec_split; info3[2] = ctx->pipe.mat_split;
+  return 0;
+}
+
 // mode-specialised kernel object the group's last evaluation ran (id of bsim4_spec_tuples.def), -1 = generic build
 int xgpu_b4_group_spec(const xgpu_ctx *ctx, int group) {
   if (!ctx || group < 0 || group >= (int)ctx->groups.size()) return -2;
@@ -491,6 +512,36 @@ int xgpu_finalize(xgpu_ctx *ctx) {
   }
   XG_CUDA(upload_map(vm, ctx->vec_map));
   XG_CUDA(upload_map(mm, ctx->mat_map));
+  // Pipelined host path: with ONE 4-terminal BSIM4 group of uniform runs, find the prefix of rows / nonzeros whose
+  // contributions all come from the first part of the runs (and that are not long destinations).  Circuits numbered
+  // device by device (arrays, anything a netlist lists block by block) have a long such prefix; others simply do not
+  // pipeline.
+  ctx->pipe.ok = false;
+  if (ctx->groups.size() == 1 && ctx->sgroups.empty() && !ctx->groups[0].general &&
+      (int)ctx->groups[0].run_start.size() <= kMaxUniformRuns && ctx->groups[0].n > 0) {
+    const XgHostGroup &g = ctx->groups[0];
+    std::vector<char> part1((size_t)g.n, 0);
+    for (size_t r = 0; r < g.run_start.size(); ++r) {
+      const int cut = xg_pipe_cut(ctx, g.run_count[r]);
+      for (int k = cut; k < g.run_count[r]; ++k) part1[(size_t)g.run_start[r] + k] = 1;
+    }
+    auto prefix = [&](const GatherMapHost &h) -> int64_t {
+      const int64_t nd = (int64_t)h.ptr.size() - 1;
+      for (int64_t d = 0; d < nd; ++d) {
+        if (h.ptr[d + 1] - h.ptr[d] > kLongThreshold) return d;
+        for (int64_t k = h.ptr[d]; k < h.ptr[d + 1]; ++k) if (part1[(size_t)(h.src[k] % g.n)]) return d;      // plane element (row, i) = base + row * n + i, base = 0
+      }
+      return nd;
+    };
+    ctx->pipe.vec_split = (int)prefix(vm);
+    ctx->pipe.mat_split = prefix(mm);
+    ctx->pipe.ok = ctx->pipe.vec_split >= n / 4 && ctx->pipe.mat_split >= ctx->nnz / 4;
+    if (ctx->pipe.ok && !ctx->pipe.s2) {
+      XG_CUDA(cudaStreamCreateWithFlags(&ctx->pipe.s2, cudaStreamNonBlocking));
+      XG_CUDA(cudaEventCreateWithFlags(&ctx->pipe.ev_a, cudaEventDisableTiming));
+      XG_CUDA(cudaEventCreateWithFlags(&ctx->pipe.ev_x, cudaEventDisableTiming));
+    }
+  }
   XG_CUDA(cudaMalloc((void **)&ctx->d_vec_planes, std::max<int64_t>(4 * vb, 1) * sizeof(double)));
   XG_CUDA(cudaMalloc((void **)&ctx->d_mat_planes, std::max<int64_t>(2 * mb, 1) * sizeof(double)));
   XG_CUDA(cudaMemset(ctx->d_vec_planes, 0, std::max<int64_t>(4 * vb, 1) * sizeof(double)));
@@ -606,6 +657,15 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
         br.M = ctx->h_models[g.run_model[r]]; br.P = ctx->h_sizes[g.run_size[r]];
         br.start = g.run_start[r]; br.count = g.run_count[r];
       }
+      // the same runs cut in two (pipelined host path): part 0 = the first pipe_frac of every run, part 1 = the rest
+      for (int part = 0; part < 2; ++part) {
+        g.packs_part[part] = g.packs;
+        for (auto &pk : g.packs_part[part])
+          for (int r = 0; r < pk.nruns; ++r) {
+            const int cut = xg_pipe_cut(ctx, pk.run[r].count);
+            if (part == 0) pk.run[r].count = cut; else { pk.run[r].start += cut; pk.run[r].count -= cut; }
+          }
+      }
       g.packs_valid = true;
       // the specialised object whose mode tuple every run's model card carries (bsim4_spec_tuples.def), or none
       g.spec_id = -1;
@@ -629,14 +689,17 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
     const bool spec = ctx->b4_spec && uniform && g.spec_id >= 0 && ctx->b4_arith == 2 && !lockstep && !g.general;
     int threads = ctx->b4_threads, minblocks = ctx->b4_minblocks;
     if (threads == 0) { threads = 128; minblocks = (spec && g.n > 150000) ? 4 : 3; }      // crossover between 100k and 200k (profiles/r01_b4_occupancy.json)
+    if (ctx->eval_part >= 0 && !uniform) return fail(ctx, 20, "partial evaluation needs the uniform-record kernel");
+    const std::vector<BinPack> &pk = (ctx->eval_part >= 0) ? g.packs_part[ctx->eval_part] : g.packs;
     const int nl = launch_b4_group(g.dev, a, ctx->b4_arith, lockstep, threads, minblocks,
-                                   uniform ? g.packs.data() : nullptr, uniform ? (int)g.packs.size() : 0, ctx->stream,
+                                   uniform ? pk.data() : nullptr, uniform ? (int)pk.size() : 0, ctx->stream,
                                    spec ? g.spec_id : -1);
     g.last_spec = spec ? g.spec_id : -1;
     if (nl < 0) return fail(ctx, 19, "unsupported BSIM4 launch shape (b4_threads, b4_minblocks)");
     ctx->launches += nl;
   }
-  for (auto &g : ctx->sgroups) { xb::simple::launch_group(g.dev, a, ctx->stream); ++ctx->launches; }
+  if (ctx->eval_part <= 0)      // the small-device groups belong to the first part
+    for (auto &g : ctx->sgroups) { xb::simple::launch_group(g.dev, a, ctx->stream); ++ctx->launches; }
   XG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -769,7 +832,7 @@ __global__ void __launch_bounds__(256) jr_kernel(long long nnz, int n, double qs
                                                  const double *__restrict__ Ql, int limiter, double *__restrict__ J,
                                                  double *__restrict__ r) {
   xb::pdl_wait();
-  const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long k = (long long)blockIdx.x * 256 + threadIdx.x;      // callers pass pointers offset to their window
   if (k < nnz) J[k] = qs * dQdx[k] + fs * dFdx[k];
   if (k < n) {
     double v = -(qs * Q[k] + fs * F[k]);
@@ -786,6 +849,47 @@ int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_stat
   if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
   double **b = ctx->buf;
   XG_CUDA(cudaMemcpyAsync(b[0], h_sol, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->pipe.ok && ctx->pipeline_host && !ctx->zero_copy_out && ctx->b4_uniform && !ctx->b4_lockstep && !xg_dist_multi(ctx)) {
+    // Two parts: evaluate the first part of every run, assemble and combine the destinations only it feeds, start their
+    // DMA on the second stream; meanwhile evaluate the second part, assemble and combine the rest, copy it.  Same kernels
+    // on the same data in the same order per destination: bitwise the result of the one-pass path.
+    const int rs = ctx->pipe.vec_split; const long long ks = ctx->pipe.mat_split;
+    const double *vin[4], *min_[2];
+    double *vout[4] = {b[1], b[2], b[3], b[4]}, *mout[2] = {b[5], b[6]};
+    for (int p = 0; p < 4; ++p) vin[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
+    for (int p = 0; p < 2; ++p) min_[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
+    for (int part = 0; part < 2; ++part) {
+      ctx->eval_part = part;
+      const int rc = xgpu_update_state(ctx, b[0], b[9], b[10], b[7], b[8], ss);
+      ctx->eval_part = -1;
+      if (rc) return rc;
+      xb::GatherMapDev mv = ctx->vec_map, mm = ctx->mat_map;
+      if (part == 0) { mv.d_lo = 0; mv.d_hi = rs; mv.with_chunks = 0; mm.d_lo = 0; mm.d_hi = (int)ks; mm.with_chunks = 0; }
+      else { mv.d_lo = rs; mv.d_hi = -1; mm.d_lo = (int)ks; mm.d_hi = -1; }
+      ctx->launches += launch_gather_fused(mv, vin, vout, mm, min_, mout, false, ctx->stream);
+      const long long k0 = part == 0 ? 0 : ks, k1 = part == 0 ? ks : ctx->nnz;
+      const int r0 = part == 0 ? 0 : rs, r1 = part == 0 ? rs : ctx->n;
+      const long long m = std::max<long long>(k1 - k0, r1 - r0);
+      if (m > 0) {
+        xb::launch_pdl(jr_kernel, dim3((unsigned)((m + 255) / 256)), dim3(256), 0, ctx->stream, k1 - k0, r1 - r0, qscalar, fscalar,
+                       (const double *)(b[6] + k0), (const double *)(b[5] + k0), (const double *)(b[1] + r0), (const double *)(b[2] + r0),
+                       (const double *)(b[3] + r0), (const double *)(b[4] + r0), ss->voltageLimiterFlag, b[5] + k0, b[1] + r0);
+        ++ctx->launches;
+      }
+      cudaStream_t cs = ctx->stream;
+      if (part == 0) {      // the first window travels on the second stream while the second part is evaluated
+        XG_CUDA(cudaEventRecord(ctx->pipe.ev_a, ctx->stream));
+        XG_CUDA(cudaStreamWaitEvent(ctx->pipe.s2, ctx->pipe.ev_a, 0));
+        cs = ctx->pipe.s2;
+      }
+      if (r1 > r0) XG_CUDA(cudaMemcpyAsync(h_rhs + r0, b[1] + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, cs));
+      if (k1 > k0) XG_CUDA(cudaMemcpyAsync(h_jac + k0, b[5] + k0, (size_t)(k1 - k0) * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    }
+    XG_CUDA(cudaStreamSynchronize(ctx->pipe.s2));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    XG_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int rc = xgpu_load_dae(ctx, b[0], b[9], b[10], b[7], b[8], ss, b[1], b[2], b[3], b[4], b[5], b[6], 0);
   if (rc) return rc;
   double *dj = nullptr, *dr = nullptr;

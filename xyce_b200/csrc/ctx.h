@@ -25,6 +25,7 @@ struct XgHostGroup {
   // model table changes (empty = more than kMaxUniformRuns runs -> per-thread-record kernel)
   std::vector<int32_t> run_model, run_size, run_start, run_count;
   std::vector<xb::b4::BinPack> packs;
+  std::vector<xb::b4::BinPack> packs_part[2];      // the same runs cut at pipe_frac of their length (pipelined host path)
   bool packs_valid = false;
   int spec_id = -1;                // the mode-specialised kernel object that fits every run's model card (bsim4_spec_tuples.def), -1 = none
   int last_spec = -1;              // object used by the last evaluation (diagnostics: xgpu_b4_group_spec)
@@ -145,6 +146,13 @@ struct xgpu_ctx {
   int *tran_ints = nullptr; size_t tran_ints_len = 0;
   double *tran_pinned = nullptr;
   double *d_hist = nullptr;           // xgpu_newton_step_host: the caller's history term on the device
+  // Pipelined host-buffer path (xgpu_load_host_jr): the instances are evaluated in two parts (every (model, bin) run cut
+  // at pipe_frac of its length); the destinations that only the first part feeds -- a prefix of the rows / nonzeros for
+  // circuits numbered device by device -- are assembled and shipped over PCIe while the second part is evaluated.
+  struct Pipe { bool ok = false; int vec_split = 0; long long mat_split = 0; cudaStream_t s2 = nullptr; cudaEvent_t ev_a = nullptr, ev_x = nullptr; } pipe;
+  int pipeline_host = 1;              // option "pipeline_host": 0 = never pipeline
+  double pipe_frac = 0.5;             // option "pipe_percent": share of every run in the first part
+  int eval_part = -1;                 // -1 = all instances, 0 / 1 = that part only (set around xgpu_update_state by the pipelined path)
   XgDist *dist = nullptr;     // bordered solve / multi-GPU state (xgpu_border_set, xgpu_comm_init); null = plain single-GPU path
 };
 
