@@ -49,6 +49,7 @@
 #include <signal.h>
 #include <unistd.h>
 
+#include "../adaptor/N_DEV_GpuMaster_Simple.h"  // the same for Diode / MOSFET level 1 / BJT and for translated ADMS models
 #include "../adaptor/N_DEV_GpuMaster_B4.h"      // the Xyce-side adaptor (product code for the reference tree), driven by tests/test_gpu_adaptor.py
 #include "../xyce_b200/csrc/bsim4_fields.def"
 #include "b4_mid_members.def"
@@ -167,6 +168,24 @@ struct InstRec {
   int br0 = -1;              // first branch-data LID (lead currents), -1 when not enabled
 };
 
+#ifdef XB_HAVE_ADMS_ORACLE
+// record fillers of the translated ADMS models for GpuSimpleMaster: the generated adms_fill_<model>() + the type id the
+// library's registry gives that model
+#define XB_ORACLE_GPUFILL(nm_, ns_) \
+  struct GpuAdmsFill_##nm_ { \
+    typedef ns_::Instance Inst; \
+    static int type() { static const int t = gpu_adms_type_by_name(#nm_); return t; } \
+    static int fill(Inst &in, std::vector<double> &rec, std::vector<int32_t> &lids, int &flags) { \
+      double r[1024]; int l[64]; \
+      const int k = adms_fill_##nm_(in, r, l), nl = in.getNumExtVars() + in.getNumIntVars(); \
+      rec.insert(rec.end(), r, r + k); lids.insert(lids.end(), l, l + nl); flags = 0; \
+      return nl; \
+    } \
+  };
+XB_ADMS_ORACLE_LIST(XB_ORACLE_GPUFILL)
+#undef XB_ORACLE_GPUFILL
+#endif
+
 struct Ctx {
   DeviceOptions devOptions;
   SolverState solState;
@@ -187,12 +206,17 @@ struct Ctx {
       if (gpuB4) m = new MOSFET_B4::GpuMaster(*c, *fb, fb->solverState_, fb->deviceOptions_);
       else m = MOSFET_B4::Traits::factory(*c, *fb);
     }
-    else if (t == "m1") { auto *c = &Config<MOSFET1::Traits>::addConfiguration(); cfg = c; m = MOSFET1::Traits::factory(*c, *fb); }
-    else if (t == "d") { auto *c = &Config<Diode::Traits>::addConfiguration(); cfg = c; m = Diode::Traits::factory(*c, *fb); }
-    else if (t == "q") { auto *c = &Config<BJT::Traits>::addConfiguration(); cfg = c; m = BJT::Traits::factory(*c, *fb); }
+    else if (t == "m1") { auto *c = &Config<MOSFET1::Traits>::addConfiguration(); cfg = c;
+      m = gpuAll ? static_cast<Xyce::Device::Device *>(new GpuMos1Master(*c, *fb, fb->solverState_, fb->deviceOptions_)) : MOSFET1::Traits::factory(*c, *fb); }
+    else if (t == "d") { auto *c = &Config<Diode::Traits>::addConfiguration(); cfg = c;
+      m = gpuAll ? static_cast<Xyce::Device::Device *>(new GpuDiodeMaster(*c, *fb, fb->solverState_, fb->deviceOptions_)) : Diode::Traits::factory(*c, *fb); }
+    else if (t == "q") { auto *c = &Config<BJT::Traits>::addConfiguration(); cfg = c;
+      m = gpuAll ? static_cast<Xyce::Device::Device *>(new GpuBjtMaster(*c, *fb, fb->solverState_, fb->deviceOptions_)) : BJT::Traits::factory(*c, *fb); }
     else if (t == "mvs") { auto *c = &Config<ADMSmvs_2_0_0_etsoi::Traits>::addConfiguration(); cfg = c; m = ADMSmvs_2_0_0_etsoi::Traits::factory(*c, *fb); }
 #ifdef XB_HAVE_ADMS_ORACLE
-#define XB_ORACLE_MASTER(nm_, ns_) else if (t == "adms:" #nm_) { auto *c = &Config<ns_::Traits>::addConfiguration(); cfg = c; m = ns_::Traits::factory(*c, *fb); }
+#define XB_ORACLE_MASTER(nm_, ns_) else if (t == "adms:" #nm_) { auto *c = &Config<ns_::Traits>::addConfiguration(); cfg = c; \
+      m = gpuAll ? static_cast<Xyce::Device::Device *>(new GpuSimpleMaster<DeviceMaster<ns_::Traits>, GpuAdmsFill_##nm_>(*c, *fb, fb->solverState_, fb->deviceOptions_)) \
+                 : ns_::Traits::factory(*c, *fb); }
     XB_ADMS_ORACLE_LIST(XB_ORACLE_MASTER)
 #undef XB_ORACLE_MASTER
 #endif
@@ -217,6 +241,7 @@ struct Ctx {
     for (auto *m : masters) ok = m->loadDAEMatrices(dFdx, dQdx) && ok;
     return ok;
   }
+  bool gpuAll = false;       // Diode / MOSFET1 / BJT / translated ADMS instances go to GpuSimpleMaster (adaptor/N_DEV_GpuMaster_Simple.h)
   bool gpuB4 = false;        // BSIM4 instances go to MOSFET_B4::GpuMaster (adaptor/N_DEV_GpuMaster_B4.h) instead of the stock Master
   std::vector<double> staDeriv, leadF, leadQ, junctionV;
   bool lead = false;         // DeviceInstance::enableLeadCurrentCalc on every instance (what .PRINT I(...) / P(...) triggers)
@@ -396,14 +421,21 @@ int xref_finalize(void *h) {
 // xref_use_gpu_master: before the first BSIM4 model / instance is added.  xref_gpu_attach: after xref_finalize
 // (all LIDs registered).  From then on updateAll / loadVectorsAll / loadMatricesAll reach the GPU through the same
 // Device virtuals the stock Master answers.
-void xref_use_gpu_master(void *h, int on) { ((Ctx *)h)->gpuB4 = on != 0; }
+// on = 1: BSIM4 only; on = 2: every device type that has an adaptor (BSIM4, diode, MOSFET level 1, BJT, translated ADMS)
+void xref_use_gpu_master(void *h, int on) { ((Ctx *)h)->gpuB4 = on != 0; ((Ctx *)h)->gpuAll = on >= 2; }
 int xref_gpu_attach(void *h, int cuda_device) {
   Ctx *c = (Ctx *)h;
-  const int d = c->master("b4");
-  MOSFET_B4::GpuMaster *g = d >= 0 ? dynamic_cast<MOSFET_B4::GpuMaster *>(c->masters[d]) : nullptr;
-  if (!g) return 1;
-  if (!g->attach(cuda_device, c->n, c->n, c->nSta, c->nSto)) { std::cerr << "xref_gpu_attach: " << g->lastError() << std::endl; return 2; }
-  return 0;
+  int attached = 0;
+  for (auto *m : c->masters) {
+    if (MOSFET_B4::GpuMaster *g = dynamic_cast<MOSFET_B4::GpuMaster *>(m)) {
+      if (!g->attach(cuda_device, c->n, c->n, c->nSta, c->nSto)) { std::cerr << "xref_gpu_attach: " << g->lastError() << std::endl; return 2; }
+      ++attached;
+    } else if (GpuAttachable *g = dynamic_cast<GpuAttachable *>(m)) {
+      if (!g->attach(cuda_device, c->n, c->n, c->nSta, c->nSto)) { std::cerr << "xref_gpu_attach: " << g->lastError() << std::endl; return 2; }
+      ++attached;
+    }
+  }
+  return attached > 0 ? 0 : 1;
 }
 int xref_gpu_set_von(void *h, const double *von) {      // von[i] of the i-th BSIM4 instance (harness order = instance-vector order)
   Ctx *c = (Ctx *)h;

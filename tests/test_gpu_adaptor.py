@@ -57,3 +57,68 @@ def test_gpu_master_equals_stock_master_through_the_device_virtuals(variant, cas
 def gpu_eng_von(gpu, von):
     """the carried limiter threshold lives in the GPU context (Instance::von on the stock side)"""
     gpu.lib.xref_gpu_set_von(gpu.h, oracle_ref.dptr(np.ascontiguousarray(von, dtype=np.float64)))
+
+
+class GpuRefAll(oracle_ref.RefCircuit):
+    """every device type that has an adaptor goes to its GPU master (adaptor/N_DEV_GpuMaster_Simple.h)"""
+    def __init__(self, n):
+        super().__init__(n)
+        self.use_gpu_master(2)
+
+
+def _compare_through_virtuals(stock, gpu, x, flags, seed=9):
+    gpu.gpu_attach(0)
+    assert gpu.n == stock.n and np.array_equal(gpu.rowptr, stock.rowptr) and np.array_equal(gpu.colind, stock.colind)
+    rng = np.random.default_rng(seed)
+    csto, nsto = rng.normal(0.2, 0.4, stock.n_sto), rng.normal(0.2, 0.4, stock.n_sto)
+    csta = rng.normal(0.0, 1e-14, stock.n_sta)
+    for c in (stock, gpu):
+        c.set_flags(**flags)
+        c.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta)
+    want, got = stock.load(x), gpu.load(x)
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, k
+    ws, gs = stock.get_state(), gpu.get_state()
+    if stock.n_sto:
+        assert rel_err(gs["next_sto"], ws["next_sto"], 1e-25) < 1e-12
+    if stock.n_sta:
+        assert rel_err(gs["next_sta"], ws["next_sta"], 1e-25) < 1e-12
+    assert gpu.all_converged() == stock.all_converged()
+    assert np.any(want["dFdx"])
+
+
+@pytest.mark.parametrize("case", ["tran1", "dcop_jct", "nolimit"])
+@pytest.mark.parametrize("kind,card", [("mos1", "basic"), ("mos1", "pmos_rs"), ("bjt", "basic"), ("bjt", "res_pnp")])
+def test_simple_gpu_masters_equal_the_stock_masters_through_the_device_virtuals(kind, card, case):
+    """GpuSimpleMaster<MOSFET1::Master, ...> / <BJT::Master, ...> created in place of the stock Masters: records extracted
+    from the reference's Instance / Model objects by the adaptor itself, GPU reached through the C ABI."""
+    from dev_common import simple_circuit
+    stock = simple_circuit(oracle_ref.RefCircuit, kind, card, n_dev=30, seed=4)
+    gpu = simple_circuit(GpuRefAll, kind, card, n_dev=30, seed=4)
+    x = np.random.default_rng(5).uniform(-1.5, 1.5, stock.n)
+    _compare_through_virtuals(stock, gpu, x, CASES[case])
+
+
+@pytest.mark.parametrize("case", ["tran1", "dcop_jct"])
+def test_diode_gpu_master(case):
+    from dev_common import DIODE_CARDS, diode_circuit
+    for card in sorted(DIODE_CARDS):
+        stock = diode_circuit(oracle_ref.RefCircuit, card, n_dev=20, seed=2)
+        gpu = diode_circuit(GpuRefAll, card, n_dev=20, seed=2)
+        x = np.random.default_rng(3).uniform(-1.0, 1.0, stock.n)
+        _compare_through_virtuals(stock, gpu, x, CASES[case])
+
+
+@pytest.mark.parametrize("model,card", [("mvs_2_0_0_etsoi", "nmos"), ("mvs_2_0_0_hemt", "wide"), ("ekv_va", "pmos"), ("ekv_va", "short_hot")])
+def test_translated_adms_models_behind_the_generic_device_master(model, card):
+    """the admsXml-generated models use DeviceMaster<Traits> itself (no Master subclass): GpuSimpleMaster<DeviceMaster<Traits>,
+    generated filler> takes its place; the record comes from the translator's adms_fill_<model>()."""
+    from adms_common import adms_circuit, bias_vector
+    import xyce_b200
+    info = {m["name"]: m for m in xyce_b200.capi.Engine.adms_gen_models()}[model]
+    stock = adms_circuit(oracle_ref.RefCircuit, model, card, info["ext"], n_dev=25, seed=6)
+    gpu = adms_circuit(GpuRefAll, model, card, info["ext"], n_dev=25, seed=6)
+    lids = [stock.adms_export(i, model)["lids"] for i in range(stock.n_inst)]
+    x = bias_vector(model, stock.n, lids, np.random.default_rng(7))
+    _compare_through_virtuals(stock, gpu, x, CASES["tran1"])
