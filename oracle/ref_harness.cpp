@@ -176,8 +176,8 @@ struct InstRec {
     typedef ns_::Instance Inst; \
     static int type() { static const int t = gpu_adms_type_by_name(#nm_); return t; } \
     static int fill(Inst &in, std::vector<double> &rec, std::vector<int32_t> &lids, int &flags) { \
-      double r[1024]; int l[64]; \
-      const int k = adms_fill_##nm_(in, r, l), nl = in.getNumExtVars() + in.getNumIntVars(); \
+      double r[4096]; int l[64]; \
+      const int k = adms_fill_##nm_(in, r, l), nl = adms_nlids_##nm_; \
       rec.insert(rec.end(), r, r + k); lids.insert(lids.end(), l, l + nl); flags = 0; \
       return nl; \
     } \
@@ -649,7 +649,7 @@ int xref_adms_export(void *h, int idx, const char *name, double *rec, int *lids,
   int k = -1, nl = 0;
 #ifdef XB_HAVE_ADMS_ORACLE
 #define XB_ORACLE_FILL(nm_, ns_) if (nm == #nm_) { ns_::Instance &in = *static_cast<ns_::Instance *>(c->insts[idx].inst); \
-    k = adms_fill_##nm_(in, rec, lids); nl = in.getNumExtVars() + in.getNumIntVars(); }
+    k = adms_fill_##nm_(in, rec, lids); nl = adms_nlids_##nm_; }
   XB_ADMS_ORACLE_LIST(XB_ORACLE_FILL)
 #undef XB_ORACLE_FILL
 #endif

@@ -20,9 +20,30 @@ ADMS_CARDS = {
                                    LETA=0.3, IBA=2e8, IBB=2e8, IBN=0.6, TCV=1e-3, BEX=-1.4, UCEX=1.6, TNOM=25.0, TRISE=40.0),
                       dict(L=0.25e-6, W=5e-6, AS=5e-12, AD=5e-12, PS=12e-6, PD=12e-6)),
     },
+    # JUNCAP 200.3 junction diode (2 terminals, 129 record fields)
+    "JUNCAP200": {
+        "default": ("D", {}, {}),
+        "sized": ("D", dict(CJORBOT=1.5e-3, CJORSTI=2e-9, IDSATRBOT=5e-12, CSRHBOT=2e2, CTATBOT=1e2, VBIRBOT=0.9), dict(AB=2e-12, LS=3e-6, LG=1e-6)),
+    },
+    # HICUM level 0 and level 2 bipolar transistors: default card = every internal node collapsed, "res" = series
+    # resistances present (internal collector / base / emitter nodes are real unknowns)
+    "hic0_full": {
+        "default": ("NPN", {}, {}),
+        "res": ("NPN", dict(RCX=12.0, RBX=8.0, RBI0=25.0, RE=1.5, IS=2e-17, CJE0=8e-15, CJCI0=3e-15, T0=3e-12), {}),
+    },
+    "hicumL2va": {
+        "default": ("NPN", {}, {}),
+        "res": ("NPN", dict(RCX=12.0, RBX=8.0, RBI0=25.0, RE=1.5, C10=3e-30, QP0=4e-14, CJEI0=8e-15, CJCI0=3e-15, T0=3e-12), {}),
+    },
+    # PSP 103 MOSFET (13 unknowns before collapsing, 636 record fields)
+    "PSP103VA": {
+        "nmos": ("NMOS", dict(TYPE=1), dict(L=1e-7, W=1e-6)),
+        "pmos_rg": ("PMOS", dict(TYPE=-1, RGO=30.0, RBULKO=50.0, SWJUNCAP=3), dict(L=2e-7, W=2e-6)),
+    },
 }
 # bias windows (uniform node voltages) that keep every model inside its working range
-BIAS = {"mvs_2_0_0_etsoi": (-0.6, 1.0), "mvs_2_0_0_hemt": (-0.6, 1.0), "ekv_va": (-1.2, 1.8)}
+BIAS = {"mvs_2_0_0_etsoi": (-0.6, 1.0), "mvs_2_0_0_hemt": (-0.6, 1.0), "ekv_va": (-1.2, 1.8), "JUNCAP200": (-0.8, 0.6),
+        "hic0_full": (0.0, 0.7), "hicumL2va": (0.0, 0.7), "PSP103VA": (0.0, 0.6)}
 
 
 # unknowns that need their own window: V(sf) of the HEMT variant (the Fermi-Dirac fit of the model takes a fractional
@@ -40,7 +61,7 @@ def bias_vector(model, n, lids_list, rng):
 
 
 def adms_circuit(ref_cls, model, card, n_ext, n_dev=6, seed=0):
-    nt = 4
+    nt = max(4, n_ext)
     c = ref_cls(nt * n_dev)
     mtype, mp, ip = ADMS_CARDS[model][card]
     c.add_dev_model("adms:" + model, "amod", mtype, 1, mp)

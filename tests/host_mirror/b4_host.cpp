@@ -17,7 +17,7 @@
 #include "../../xyce_b200/csrc/mos1_eval.h"
 #include "../../xyce_b200/csrc/bjt_eval.h"
 #include "../../xyce_b200/csrc/adms_mvs_eval.h"
-#if __has_include("../../xyce_b200/csrc/gen_adms/registry.h")
+#if __has_include("../../xyce_b200/csrc/gen_adms/registry.h") && !defined(XB_TAINT)
 #include "../../xyce_b200/csrc/gen_adms/registry.h"      // evaluators written by the ADMS translator
 #define XB_HAVE_ADMS_GEN 1
 #endif

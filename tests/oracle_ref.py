@@ -104,7 +104,7 @@ class RefCircuit:
 
     def adms_export(self, idx, name):
         """record (field order of the ADMS translator's evaluator) and unknown LIDs of an instance of a translated model"""
-        rec = np.zeros(512)
+        rec = np.zeros(4096)            # PSP103 has 636 fields
         lids = np.zeros(64, dtype=np.int32)
         nl = C.c_int()
         k = self.lib.xref_adms_export(self.h, idx, name.encode(), dptr(rec), iptr(lids), C.byref(nl))

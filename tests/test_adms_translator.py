@@ -33,6 +33,9 @@ def test_registry_lists_the_translated_models():
     k = MODELS["ekv_va"]
     assert (k["nodes"], k["ext"], k["slots"]) == (4, 4, 16) and "I:L" in k["fields"] and "M:L" not in k["fields"]
     assert "I:admsTemperature" in k["fields"]
+    p = MODELS["PSP103VA"]
+    assert (p["nodes"], p["ext"]) == (13, 4) and len(p["fields"]) > 600 and any(f.startswith("I:collapseNode_") for f in p["fields"])
+    assert MODELS["hicumL2va"]["nodes"] == 15 and MODELS["JUNCAP200"]["nodes"] == 2
 
 
 def host_eval(hd, name, info, rec, V, gmin=1e-12):
@@ -69,7 +72,7 @@ def test_generated_evaluator_on_host_equals_reference_object(model, card, case):
         scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
         assert rel_err(asm[k], want[k], scale) < 1e-13, (model, card, case, k)      # same statements: last-bit agreement
     assert np.any(want["dFdx"])
-    if model == "ekv_va":
+    if model in ("ekv_va", "hic0_full", "hicumL2va", "PSP103VA", "JUNCAP200"):
         assert np.any(want["q"]) and np.any(want["dQdx"])      # dynamic contributions are exercised
 
 

@@ -110,7 +110,8 @@ def test_diode_gpu_master(case):
         _compare_through_virtuals(stock, gpu, x, CASES[case])
 
 
-@pytest.mark.parametrize("model,card", [("mvs_2_0_0_etsoi", "nmos"), ("mvs_2_0_0_hemt", "wide"), ("ekv_va", "pmos"), ("ekv_va", "short_hot")])
+@pytest.mark.parametrize("model,card", [("mvs_2_0_0_etsoi", "nmos"), ("mvs_2_0_0_hemt", "wide"), ("ekv_va", "pmos"), ("ekv_va", "short_hot"),
+                                         ("hicumL2va", "res"), ("hic0_full", "default"), ("PSP103VA", "pmos_rg"), ("JUNCAP200", "sized")])
 def test_translated_adms_models_behind_the_generic_device_master(model, card):
     """the admsXml-generated models use DeviceMaster<Traits> itself (no Master subclass): GpuSimpleMaster<DeviceMaster<Traits>,
     generated filler> takes its place; the record comes from the translator's adms_fill_<model>()."""

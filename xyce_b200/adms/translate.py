@@ -90,8 +90,11 @@ def parse(cfile, hfile):
     # Jacobian stamp in constructor order
     stamp = re.findall(r"jacobianElements\.push_back\(IntPair\((\w+),(\w+)\)\);", C)
     info["stamp"] = [(ids[r], ids[c]) for r, c in stamp]
-    if "collapseNode" in C:
-        raise Unsupported("parameter-dependent node collapsing")
+    # Node collapsing (collapseNode_x set in Instance::collapseNodes from the parameters): the generated registerLIDs
+    # aliases li_x to the node it collapses onto (or -1 = ground), which is exactly what the gather map needs -- the
+    # evaluator keeps all its unknowns and the aliased rows / entries sum up.  The flags themselves are instance members
+    # that the analog block and the loads may test.
+    info["inst_members"] += [(m, "bool") for m in sorted(set(re.findall(r"\bbool\s+(collapseNode_\w+)\s*;", H)))]
     # analog block
     fn = _function_body(C, "bool Instance::updateIntermediateVars()")
     a = fn.index("// Local variables")
@@ -162,8 +165,21 @@ def emit(info, name):
     t = re.sub(r"\(\*solVectorPtr\)\[li_(\w+)\]", sol, t)
     t = re.sub(r"^\s*d_probeVars\[\w+\]\[\w+\]\s*=\s*1\.0;\s*$", "", t, flags=re.M)      # the independent variables' own seeds
     t = re.sub(r"d_probeVars\[(\w+)\]\[(\w+)\]", lambda m: "1.0" if m.group(1) == m.group(2) else "0.0", t)
+    # diagnostics inside the analog block ($strobe / $warning / $error of the Verilog-A source) have no place in a kernel
+    t = re.sub(r"\b(?:UserWarning0?|UserError0?|UserFatal0?|Report::\w+)\s*\([^;]*;", ";", t)
     mtype = dict(info["model_members"])
     itype = dict(info["inst_members"])
+    # members that the analog block ASSIGNS (variables of global_instance / global_model scope, operating-point outputs):
+    # they become locals initialised from the record
+    assigned = []
+    for n in used_model:
+        if re.search(r"model_\.%s\s*(?:[-+*/]?=)(?!=)" % re.escape(n), t):
+            assigned.append(("M:" + n, "m_%s_" % n, mtype[n]))
+            t = re.sub(r"\(?model_\.%s\b\)?" % re.escape(n), lambda m, n=n: "m_%s_" % n if not (m.group(0).startswith("(") ^ m.group(0).endswith(")")) else m.group(0).replace("model_.%s" % n, "m_%s_" % n), t)
+    for n in list(inst_used):
+        if re.search(r"(?<![\w.])%s\s*(?:[-+*/]?=)(?!=)" % re.escape(n), t):
+            assigned.append(("I:" + n, "i_%s_" % n, itype[n]))
+            t = re.sub(r"(?<![\w.])%s\b(?!\s*\()" % re.escape(n), "i_%s_" % n, t)
     def field(key, ctype):          # integer / boolean members keep their C type (conditions, integer arithmetic)
         return "R.f[%d]" % fidx[key] if ctype == "double" else "%s(to_double(R.f[%d]))" % (ctype, fidx[key])
     t = re.sub(r"model_\.(\w+)", lambda m: field("M:" + m.group(1), mtype[m.group(1)]), t)
@@ -181,6 +197,9 @@ def emit(info, name):
     if leftovers:
         raise Unsupported("untranslated constructs in the analog block: %s" % sorted(set(leftovers))[:6])
     lt = re.sub(r"\bdouble\b", "real", locals_text)
+    for key, local, ctype in assigned:
+        lt += "\n  %s %s = %s;" % ("real" if ctype == "double" else ctype, local,
+                                   "R.f[%d]" % fidx[key] if ctype == "double" else "%s(to_double(R.f[%d]))" % (ctype, fidx[key]))
 
     # ---- loads ----
     slot_of = {rc: k for k, rc in enumerate(info["stamp"])}
@@ -213,6 +232,8 @@ def emit(info, name):
     out.append("struct Out { real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots]; };\n")
     out.append("XB_HD real adms_vt(real T) { return kKoverQ * T; }\n")
     out.append("XB_HD real adms_max(real a, real b) { return a < b ? b : a; }\nXB_HD real adms_min(real a, real b) { return b < a ? b : a; }\n")
+    out.append("// the templates' limited exponential (N_DEV_ADMS*.h: exp below 80, its tangent above)\n"
+               "XB_HD real limexp(real x) { return (x < 80.0) ? exp(x) : exp(real(80.0)) * (x - 79.0); }\n")
     out.append("// RecT: anything with f[k] -> field k (Rec on the host; on the device a view that loads a field where it is used,\n"
                "// so that a 76-field record does not sit in registers for the whole evaluation)\n")
     out.append("template <class RecT>\nXB_HD void evaluate(const SolverFlags &S, const RecT &R, const real *V, Out &o) {\n")
@@ -251,6 +272,7 @@ def emit_fill(info, name, fields):
         li = "li_" + (u[len("admsNodeID_"):] if u.startswith("admsNodeID_") else "BRA_" + u[len("admsBRA_ID_"):])
         out.append("  lids[j++] = in.%s;\n" % li)
     out.append("  return k;\n}\n")
+    out.append("static const int adms_nlids_%s = %d;      // unknowns of the evaluator (collapsed nodes alias their targets, -1 = ground)\n" % (name, len(info["unknowns"])))
     return "".join(out)
 
 

@@ -85,6 +85,20 @@ struct RealT {
   friend XBR_HD RealT rpow(const RealT &a, const RealT &b) { return RealT(::pow(a.v, b.v)); }
   friend XBR_HD RealT rtan(const RealT &a) { return RealT(::tan(a.v)); }
   friend XBR_HD RealT fabs(const RealT &a) { return RealT(::fabs(a.v)); }
+  // the rest of the Verilog-A math library as the translated ADMS models call it (plain library versions)
+  friend XBR_HD RealT sin(const RealT &a) { return RealT(::sin(a.v)); }
+  friend XBR_HD RealT cos(const RealT &a) { return RealT(::cos(a.v)); }
+  friend XBR_HD RealT tan(const RealT &a) { return RealT(::tan(a.v)); }
+  friend XBR_HD RealT atan(const RealT &a) { return RealT(::atan(a.v)); }
+  friend XBR_HD RealT asin(const RealT &a) { return RealT(::asin(a.v)); }
+  friend XBR_HD RealT acos(const RealT &a) { return RealT(::acos(a.v)); }
+  friend XBR_HD RealT sinh(const RealT &a) { return RealT(::sinh(a.v)); }
+  friend XBR_HD RealT cosh(const RealT &a) { return RealT(::cosh(a.v)); }
+  friend XBR_HD RealT tanh(const RealT &a) { return RealT(::tanh(a.v)); }
+  friend XBR_HD RealT log10(const RealT &a) { return RealT(::log10(a.v)); }
+  friend XBR_HD RealT atan2(const RealT &a, const RealT &b) { return RealT(::atan2(a.v, b.v)); }
+  friend XBR_HD RealT floor(const RealT &a) { return RealT(::floor(a.v)); }
+  friend XBR_HD RealT ceil(const RealT &a) { return RealT(::ceil(a.v)); }
   friend XBR_HD double to_double(const RealT &a) { return a.v; }
 };
 
