@@ -34,7 +34,7 @@ def test_registry_lists_the_translated_models():
     assert (k["nodes"], k["ext"], k["slots"]) == (4, 4, 16) and "I:L" in k["fields"] and "M:L" not in k["fields"]
     assert "I:admsTemperature" in k["fields"]
     p = MODELS["PSP103VA"]
-    assert (p["nodes"], p["ext"]) == (13, 4) and len(p["fields"]) > 600 and any(f.startswith("I:collapseNode_") for f in p["fields"])
+    assert (p["nodes"], p["ext"]) == (13, 4) and len(p["fields"]) > 600
     assert MODELS["hicumL2va"]["nodes"] == 15 and MODELS["JUNCAP200"]["nodes"] == 2
 
 
