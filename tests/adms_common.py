@@ -40,10 +40,26 @@ ADMS_CARDS = {
         "nmos": ("NMOS", dict(TYPE=1), dict(L=1e-7, W=1e-6)),
         "pmos_rg": ("PMOS", dict(TYPE=-1, RGO=30.0, RBULKO=50.0, SWJUNCAP=3), dict(L=2e-7, W=2e-6)),
     },
+    # BSIM6 bulk MOSFET (analog functions, given() tests, node collapsing incl. the thermal node to ground)
+    "bsim6": {
+        "nmos": ("NMOS", dict(TYPE=1), dict(L=1e-7, W=1e-6)),
+        "pmos_rg": ("PMOS", dict(TYPE=-1, RGATEMOD=1, RBODYMOD=1, RDSMOD=1), dict(L=2e-7, W=2e-6, NF=2)),
+    },
+    # BSIM-CMG 110 multi-gate (FinFET) model: 1 379 record fields
+    "bsimcmg_110": {
+        "nfin": ("NMOS", dict(DEVTYPE=1), dict(L=3e-8, NFIN=4)),
+        "pfin_rg": ("PMOS", dict(DEVTYPE=0, RGATEMOD=1, RDSMOD=1), dict(L=5e-8, NFIN=2)),
+    },
+    # CMC diode (internal nodes for the series resistance and the depletion / charge states)
+    "DIODE_CMC": {
+        "default": ("D", {}, {}),
+        "rs": ("D", dict(RS=5.0, CJORBOT=1.5e-3, IDSATRBOT=5e-12), dict(AB=2e-12, LS=3e-6)),
+    },
 }
 # bias windows (uniform node voltages) that keep every model inside its working range
 BIAS = {"mvs_2_0_0_etsoi": (-0.6, 1.0), "mvs_2_0_0_hemt": (-0.6, 1.0), "ekv_va": (-1.2, 1.8), "JUNCAP200": (-0.8, 0.6),
-        "hic0_full": (0.0, 0.7), "hicumL2va": (0.0, 0.7), "PSP103VA": (0.0, 0.6)}
+        "hic0_full": (0.0, 0.7), "hicumL2va": (0.0, 0.7), "PSP103VA": (0.0, 0.6), "bsim6": (0.0, 0.6), "bsimcmg_110": (0.0, 0.6),
+        "DIODE_CMC": (-0.5, 0.5)}
 
 
 # unknowns that need their own window: V(sf) of the HEMT variant (the Fermi-Dirac fit of the model takes a fractional

@@ -72,7 +72,7 @@ def test_generated_evaluator_on_host_equals_reference_object(model, card, case):
         scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
         assert rel_err(asm[k], want[k], scale) < 1e-13, (model, card, case, k)      # same statements: last-bit agreement
     assert np.any(want["dFdx"])
-    if model in ("ekv_va", "hic0_full", "hicumL2va", "PSP103VA", "JUNCAP200"):
+    if model in ("ekv_va", "hic0_full", "hicumL2va", "PSP103VA", "JUNCAP200", "bsim6", "bsimcmg_110"):
         assert np.any(want["q"]) and np.any(want["dQdx"])      # dynamic contributions are exercised
 
 

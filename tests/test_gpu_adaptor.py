@@ -111,7 +111,8 @@ def test_diode_gpu_master(case):
 
 
 @pytest.mark.parametrize("model,card", [("mvs_2_0_0_etsoi", "nmos"), ("mvs_2_0_0_hemt", "wide"), ("ekv_va", "pmos"), ("ekv_va", "short_hot"),
-                                         ("hicumL2va", "res"), ("hic0_full", "default"), ("PSP103VA", "pmos_rg"), ("JUNCAP200", "sized")])
+                                         ("hicumL2va", "res"), ("hic0_full", "default"), ("PSP103VA", "pmos_rg"), ("JUNCAP200", "sized"),
+                                         ("bsim6", "pmos_rg"), ("bsimcmg_110", "nfin"), ("DIODE_CMC", "rs")])
 def test_translated_adms_models_behind_the_generic_device_master(model, card):
     """the admsXml-generated models use DeviceMaster<Traits> itself (no Master subclass): GpuSimpleMaster<DeviceMaster<Traits>,
     generated filler> takes its place; the record comes from the translator's adms_fill_<model>()."""

@@ -14,13 +14,12 @@ src/DeviceModelPKG/ADMS/N_DEV_ADMSmvs_2_0_0_etsoi.C):
     and the stamp entries.
 The translator keeps the arithmetic statements verbatim (same operations in the same order as the reference
 object, so results agree to the last bits) and rewrites only the plumbing around them:
-  model_.X            -> R.f[k]   (flat per-instance record; k = position of "M:X" in the field list)
-  instance member X   -> R.f[k]   ("I:X"; admsTemperature / adms_vt_nom included)
+  model_.X            -> rec.f[k] (flat per-instance record; k = position of "M:X" in the field list)
+  instance member X   -> rec.f[k] ("I:X"; admsTemperature / adms_vt_nom included)
   (*solVectorPtr)[li] -> V[node]  (node voltages gathered by the kernel)
   d_probeVars[p][p]   -> 1.0
   loads               -> o.F / o.Q rows and o.JF / o.JQ slots in constructor order
-Not supported (the translator stops with a message): $limit / limited probes (Jdxp terms), node collapsing that
-depends on parameters, analog functions defined in the model file.
+Not supported (the translator stops with a message): $limit / limited probes (Jdxp terms).
 
 usage: python -m xyce_b200.adms.translate <N_DEV_ADMSname.C> <N_DEV_ADMSname.h> <out.h> [name]
        python -m xyce_b200.adms.translate --all <dir with N_DEV_ADMS*.C/.h> <out_dir> name...
@@ -54,6 +53,61 @@ def _function_body(text, signature):
             if depth == 0:
                 return text[j + 1:k]
         k += 1
+
+
+def _namespace_block(text, name):
+    """Body of `namespace <name> { ... }` (first occurrence, brace matched), or None."""
+    m = re.search(r"namespace\s+%s\s*\{" % re.escape(name), text)
+    if not m:
+        return None
+    depth, k = 0, m.end() - 1
+    while True:
+        c = text[k]
+        if c == "{":
+            depth += 1
+        elif c == "}":
+            depth -= 1
+            if depth == 0:
+                return text[m.end():k]
+        k += 1
+
+
+def _analog_functions(C, H):
+    """Analog functions of the Verilog-A source: admsXml writes each as a value function, a derivative function and an
+    Evaluator class (declared in the header, defined in the .C, both inside namespace AnalogFunctions).  They are carried
+    over whole: `double` -> real, every function and member marked host / device inline."""
+    decl, defn = _namespace_block(H, "AnalogFunctions"), _namespace_block(C, "AnalogFunctions")
+    if decl is None or defn is None:
+        return ""
+    def common(t):
+        t = re.sub(r"/\*.*?\*/", "", t, flags=re.S)
+        t = re.sub(r"//[^\n]*", "", t)
+        t = re.sub(r"\bstd::(exp|log|sqrt|pow|fabs|tanh|sinh|cosh|atan|sin|cos|tan|log10|abs)\b", r"\1", t)
+        t = t.replace("std::max", "adms_max").replace("std::min", "adms_min")
+        t = re.sub(r"static_cast<double>\(([^()]*)\)", r"real(\1)", t)
+        t = re.sub(r"\bpow\(", "rpow(", t)
+        return re.sub(r"\bdouble\b", "real", t)
+    decl, defn = common(decl), common(defn)
+    # declarations: free functions and members (lines ending in ");" that are not statements inside a body)
+    out_decl, depth = [], 0
+    for line in decl.split("\n"):
+        st = line.strip()
+        is_fn = re.match(r"^[\w:<>&\s\*]*\b[\w~]+\s*\([^;{}]*\)\s*(const)?\s*;$", st) is not None and not st.startswith(("return", "typedef"))
+        out_decl.append(("XB_HD " + st) if is_fn else line)
+    # definitions: a signature is a non-blank line at depth 0 that is followed by "{"
+    lines = defn.split("\n")
+    out_defn, depth = [], 0
+    for i, line in enumerate(lines):
+        st = line.strip()
+        if depth == 0 and st and not st.startswith(("{", "}", "#")) and st.endswith(")"):
+            j = i + 1
+            while j < len(lines) and not lines[j].strip():
+                j += 1
+            if j < len(lines) and lines[j].strip().startswith("{"):
+                line = "XB_HD " + st
+        out_defn.append(line)
+        depth += line.count("{") - line.count("}")
+    return "namespace AnalogFunctions {\n" + "\n".join(out_decl) + "\n" + "\n".join(out_defn) + "\n}  // namespace AnalogFunctions\n"
 
 
 def _members(section):
@@ -107,8 +161,9 @@ def parse(cfile, hfile):
     info["analog_text"] = re.sub(r"//[^\n]*", "", body[s1:])      # the Verilog-A source echoed in comments is not code
     if "Jdxp" in C or "origFlag = false" in info["analog_text"]:
         raise Unsupported("limited probes ($limit): Jdxp terms")
-    if re.search(r"AnalogFunctions::", info["analog_text"]):
-        raise Unsupported("analog functions defined in the model file")
+    info["analog_functions"] = _analog_functions(C, H) if re.search(r"AnalogFunctions::", info["analog_text"]) else ""
+    if re.search(r"AnalogFunctions::", info["analog_text"]) and not info["analog_functions"]:
+        raise Unsupported("analog functions are called but namespace AnalogFunctions was not found")
     # loads: vector rows and matrix slots (offset form after #else: row and column are spelled out)
     loads = {}
     for key, fname, vec in (("F", "bool Instance::loadDAEFVector()", "daeFVectorPtr"), ("Q", "bool Instance::loadDAEQVector()", "daeQVectorPtr")):
@@ -135,6 +190,21 @@ def emit(info, name):
     ids = info["ids"]
     nunk, nprobe = len(info["unknowns"]), len(info["probes"])
     locals_text, analog = info["locals_text"], info["analog_text"]
+    # given("X") / model_.given("X") (DeviceEntity::given: was the parameter set in the netlist?) -> flag fields
+    given_fields = []
+    def given_sub(m):
+        key = ("MG:" if m.group(1) else "IG:") + m.group(2)
+        if key not in given_fields:
+            given_fields.append(key)
+        return "XB_GIVEN_%d_" % given_fields.index(key)
+    analog = re.sub(r"(model_\.)?\bgiven\(\"(\w+)\"\)", given_sub, analog)
+    # $port_connected: DeviceInstance::portsConnected_[k]
+    def port_sub(m):
+        key = "IP:" + m.group(1)
+        if key not in given_fields:
+            given_fields.append(key)
+        return "XB_GIVEN_%d_" % given_fields.index(key)
+    analog = re.sub(r"\bportsConnected_\[(\w+)\]", port_sub, analog)
     local_names = set(re.findall(r"\b(?:double|int|bool)\s+(\w+)\s*=", locals_text + analog))
     # ---- record fields: model members and instance members that the analog block reads ----
     fields = []
@@ -154,6 +224,7 @@ def emit(info, name):
         if re.search(r"(?<![\w.])%s\b(?!\s*\()" % re.escape(n), analog):
             inst_used.append(n)
             fields.append("I:" + n)
+    fields += given_fields
     fidx = {f: k for k, f in enumerate(fields)}
 
     # ---- rewrite the analog block ----
@@ -166,22 +237,22 @@ def emit(info, name):
     t = re.sub(r"^\s*d_probeVars\[\w+\]\[\w+\]\s*=\s*1\.0;\s*$", "", t, flags=re.M)      # the independent variables' own seeds
     t = re.sub(r"d_probeVars\[(\w+)\]\[(\w+)\]", lambda m: "1.0" if m.group(1) == m.group(2) else "0.0", t)
     # diagnostics inside the analog block ($strobe / $warning / $error of the Verilog-A source) have no place in a kernel
-    t = re.sub(r"\b(?:UserWarning0?|UserError0?|UserFatal0?|Report::\w+)\s*\([^;]*;", ";", t)
+    t = re.sub(r"\b(?:UserWarning0?|UserError0?|UserFatal0?|UserInfo0?|Report::\w+)\s*\([^;]*;", ";", t)
     mtype = dict(info["model_members"])
     itype = dict(info["inst_members"])
     # members that the analog block ASSIGNS (variables of global_instance / global_model scope, operating-point outputs):
     # they become locals initialised from the record
     assigned = []
     for n in used_model:
-        if re.search(r"model_\.%s\s*(?:[-+*/]?=)(?!=)" % re.escape(n), t):
+        if re.search(r"model_\.%s\)?\s*(?:[-+*/]?=)(?!=)" % re.escape(n), t):
             assigned.append(("M:" + n, "m_%s_" % n, mtype[n]))
             t = re.sub(r"\(?model_\.%s\b\)?" % re.escape(n), lambda m, n=n: "m_%s_" % n if not (m.group(0).startswith("(") ^ m.group(0).endswith(")")) else m.group(0).replace("model_.%s" % n, "m_%s_" % n), t)
     for n in list(inst_used):
-        if re.search(r"(?<![\w.])%s\s*(?:[-+*/]?=)(?!=)" % re.escape(n), t):
+        if re.search(r"(?<![\w.])%s\)?\s*(?:[-+*/]?=)(?!=)" % re.escape(n), t):
             assigned.append(("I:" + n, "i_%s_" % n, itype[n]))
             t = re.sub(r"(?<![\w.])%s\b(?!\s*\()" % re.escape(n), "i_%s_" % n, t)
     def field(key, ctype):          # integer / boolean members keep their C type (conditions, integer arithmetic)
-        return "R.f[%d]" % fidx[key] if ctype == "double" else "%s(to_double(R.f[%d]))" % (ctype, fidx[key])
+        return "xbrec_.f[%d]" % fidx[key] if ctype == "double" else "%s(to_double(xbrec_.f[%d]))" % (ctype, fidx[key])
     t = re.sub(r"model_\.(\w+)", lambda m: field("M:" + m.group(1), mtype[m.group(1)]), t)
     for n in inst_used:
         t = re.sub(r"(?<![\w.])%s\b(?!\s*\()" % re.escape(n), field("I:" + n, itype[n]), t)
@@ -193,13 +264,14 @@ def emit(info, name):
     t = re.sub(r"\bstd::(exp|log|sqrt|pow|fabs|tanh|sinh|cosh|atan|sin|cos|tan|log10|abs)\b", r"\1", t)
     t = re.sub(r"\bpow\(", "rpow(", t)
     t = re.sub(r"\bdouble\b", "real", t)
+    t = re.sub(r"XB_GIVEN_(\d+)_", lambda m: "(xbrec_.f[%d] != 0.0)" % fidx[given_fields[int(m.group(1))]], t)
     leftovers = re.findall(r"\b(?:std::\w+|Xyce::\w+|UserError|Report::\w+|extData\.\w+|getName\(\))", t)
     if leftovers:
         raise Unsupported("untranslated constructs in the analog block: %s" % sorted(set(leftovers))[:6])
     lt = re.sub(r"\bdouble\b", "real", locals_text)
     for key, local, ctype in assigned:
         lt += "\n  %s %s = %s;" % ("real" if ctype == "double" else ctype, local,
-                                   "R.f[%d]" % fidx[key] if ctype == "double" else "%s(to_double(R.f[%d]))" % (ctype, fidx[key]))
+                                   "xbrec_.f[%d]" % fidx[key] if ctype == "double" else "%s(to_double(xbrec_.f[%d]))" % (ctype, fidx[key]))
 
     # ---- loads ----
     slot_of = {rc: k for k, rc in enumerate(info["stamp"])}
@@ -234,9 +306,11 @@ def emit(info, name):
     out.append("XB_HD real adms_max(real a, real b) { return a < b ? b : a; }\nXB_HD real adms_min(real a, real b) { return b < a ? b : a; }\n")
     out.append("// the templates' limited exponential (N_DEV_ADMS*.h: exp below 80, its tangent above)\n"
                "XB_HD real limexp(real x) { return (x < 80.0) ? exp(x) : exp(real(80.0)) * (x - 79.0); }\n")
+    if info.get("analog_functions"):
+        out.append(info["analog_functions"])
     out.append("// RecT: anything with f[k] -> field k (Rec on the host; on the device a view that loads a field where it is used,\n"
                "// so that a 76-field record does not sit in registers for the whole evaluation)\n")
-    out.append("template <class RecT>\nXB_HD void evaluate(const SolverFlags &S, const RecT &R, const real *V, Out &o) {\n")
+    out.append("template <class RecT>\nXB_HD void evaluate(const SolverFlags &S, const RecT &xbrec_, const real *V, Out &o) {\n")
     out.append("  real probeVars[kProbes];\n  real staticContributions[kNodes], dynamicContributions[kNodes];\n")
     out.append("  real d_staticContributions[kNodes][kProbes], d_dynamicContributions[kNodes][kProbes];\n")
     out.append("  real noiseContribsPower[16], noiseContribsExponent[16];\n  (void)noiseContribsPower; (void)noiseContribsExponent; (void)S;\n")
@@ -266,7 +340,12 @@ def emit_fill(info, name, fields):
     out.append("template <class Instance>\ninline int adms_fill_%s(const Instance &in, double *rec, int *lids) {\n  int k = 0;\n" % name)
     for f in fields:
         kind, n = f.split(":")
-        out.append("  rec[k++] = (double)%s%s;\n" % ("in.model_." if kind == "M" else "in.", n))
+        if kind == "IP":
+            out.append("  rec[k++] = in.portsConnected_[%s%s] ? 1.0 : 0.0;\n" % ("" if n.isdigit() else "Instance::", n))
+        elif kind in ("MG", "IG"):
+            out.append("  rec[k++] = %sgiven(\"%s\") ? 1.0 : 0.0;\n" % ("in.model_." if kind == "MG" else "in.", n))
+        else:
+            out.append("  rec[k++] = (double)%s%s;\n" % ("in.model_." if kind == "M" else "in.", n))
     out.append("  int j = 0;\n")
     for u in info["unknowns"]:
         li = "li_" + (u[len("admsNodeID_"):] if u.startswith("admsNodeID_") else "BRA_" + u[len("admsBRA_ID_"):])
@@ -284,7 +363,7 @@ def translate(cfile, hfile, out_path, name=None):
     open(out_path, "w").write(text)
     open(os.path.splitext(out_path)[0] + "_fill.h", "w").write(emit_fill(info, name, fields))
     return dict(name=name, namespace=info["namespace"], fields=fields, nodes=len(info["unknowns"]), n_ext=info["n_ext"],
-                slots=len(info["stamp"]), unknown_names=info["unknowns"])
+                slots=len(info["stamp"]), unknown_names=info["unknowns"], stamp=info["stamp"])
 
 
 def translate_all(adms_dir, out_dir, names):
@@ -295,11 +374,28 @@ def translate_all(adms_dir, out_dir, names):
         c, h = os.path.join(adms_dir, "N_DEV_ADMS%s.C" % n), os.path.join(adms_dir, "N_DEV_ADMS%s.h" % n)
         r = translate(c, h, os.path.join(out_dir, "adms_%s.h" % n), n)
         done.append(r)
+    # registry.h: every evaluator (host mirror); registry_info.h: the tables only (library dispatch, compiles in no
+    # time); kernel_<model>.cu: one translation unit per model so that the library build compiles them in parallel
     with open(os.path.join(out_dir, "registry.h"), "w") as f:
         f.write("// GENERATED by xyce_b200/adms/translate.py\n#pragma once\n")
         for r in done:
             f.write("#include \"adms_%s.h\"\n" % r["name"])
         f.write("#define XB_ADMS_GEN_COUNT %d\n#define XB_ADMS_GEN_LIST(X) %s\n" % (len(done), " ".join("X(%d, %s)" % (i, r["name"]) for i, r in enumerate(done))))
+    with open(os.path.join(out_dir, "registry_info.h"), "w") as f:
+        f.write("// GENERATED by xyce_b200/adms/translate.py -- tables of the translated models, no evaluator code\n#pragma once\n")
+        for r in done:
+            f.write("static const int kAdmsRow_%s[] = {%s};\nstatic const int kAdmsCol_%s[] = {%s};\n"
+                    % (r["name"], ", ".join(str(a) for a, _ in r["stamp"]), r["name"], ", ".join(str(b) for _, b in r["stamp"])))
+            f.write("static const char kAdmsFields_%s[] = \"%s\";\n" % (r["name"], " ".join(r["fields"])))
+        f.write("#define XB_ADMS_GEN_COUNT %d\n// X(index, name, unknowns, external nodes, stamp entries, record fields)\n#define XB_ADMS_GEN_LIST(X) %s\n"
+                % (len(done), " ".join("X(%d, %s, %d, %d, %d, %d)" % (i, r["name"], r["nodes"], r["n_ext"], r["slots"], len(r["fields"])) for i, r in enumerate(done))))
+    for r in done:
+        with open(os.path.join(out_dir, "kernel_%s.cu" % r["name"]), "w") as f:
+            f.write("// GENERATED by xyce_b200/adms/translate.py -- the generic kernel instantiated for one translated model\n"
+                    "#include \"../adms_gen_kernel.cuh\"\n#include \"adms_%s.h\"\n"
+                    "namespace xb {\nnamespace simple {\n"
+                    "void launch_adms_gen_%s(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) { launch_adms_gen<adms::gen_%s::Traits>(g, a, s); }\n"
+                    "}  // namespace simple\n}  // namespace xb\n" % (r["name"], r["name"], r["name"]))
     with open(os.path.join(out_dir, "oracle_registry.h"), "w") as f:
         f.write("// GENERATED by xyce_b200/adms/translate.py -- oracle (test infrastructure) side\n#pragma once\n")
         for r in done:

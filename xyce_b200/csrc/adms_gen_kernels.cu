@@ -1,20 +1,11 @@
-// xyce_b200 -- kernels of the models written by the ADMS translator (xyce_b200/adms/translate.py -> gen_adms/).
-//
-// Any model that admsXml emits with Xyce's `_nosac` templates has the same shape as the hand-restated MVS of
-// simple_kernels.cu: flat per-instance record, node voltages through the gather map, static + dynamic contributions and
-// their probe derivatives copied onto rows and Jacobian stamp slots; no limiting, no store / state.  One kernel template
-// serves them all; the registry (gen_adms/registry.h, written at build time) instantiates it per model.
-// Its own translation unit so that it can use the fast arithmetic variant (FastReal: shared-reciprocal division,
-// constant-bank exp / log, inlined sqrt, FMA contraction; <= 2 ulp per operation, tests hold 1e-12 against the
-// reference's generated classes) independently of the strict small-device kernels.
-#include "xb_real.h"
-#define XB_REAL xb::FastReal
-#include "pdl.cuh"
+// xyce_b200 -- registry and dispatch of the models written by the ADMS translator (xyce_b200/adms/translate.py).
+// The kernels themselves are one translation unit per model (gen_adms/kernel_<model>.cu, instantiating
+// adms_gen_kernel.cuh); this file only holds the tables (gen_adms/registry_info.h, written at build time) behind
+// xgpu_adms_gen_count / xgpu_adms_gen_info and routes a group's launch to its model.
 #include "simple_kernels.cuh"
-#include "xb_common.h"
 #if defined(__has_include)
-#if __has_include("gen_adms/registry.h")
-#include "gen_adms/registry.h"
+#if __has_include("gen_adms/registry_info.h")
+#include "gen_adms/registry_info.h"
 #define XB_HAVE_ADMS_GEN 1
 #endif
 #endif
@@ -22,55 +13,16 @@
 namespace xb {
 namespace simple {
 
-namespace {
-
-// field k of the record is loaded (coalesced, read-only path) where the analog block reads it: a 76-field record
-// (EKV) does not sit in registers for the whole evaluation
-struct LazyRec {
-  struct Fields {
-    const double *p; size_t n;
-    __device__ __forceinline__ real operator[](int k) const { return real(__ldg(p + (size_t)k * n)); }
-  } f;
-};
-
-template <class T>
-__global__ void __launch_bounds__(128) adms_gen_kernel(GroupDev g, b4::LoadArgs a) {
-  xb::pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
-  const int n = g.n;
-  const LazyRec R{{g.rec + i, (size_t)n}};
-  real V[T::kNodes];
-#pragma unroll
-  for (int t = 0; t < T::kNodes; ++t) {
-    const int lid = __ldg(g.lids + (size_t)t * n + i);
-    V[t] = real(lid >= 0 ? __ldg(a.sol + lid) : 0.0);
-  }
-  typename T::Out o;
-  T::eval(a.S, R, V, o);
-  g.orig_flag[i] = 1;
-#pragma unroll
-  for (int r = 0; r < T::kNodes; ++r) {
-    a.vec_planes[0][g.vec_base + (size_t)r * n + i] = to_double(o.F[r]);
-    a.vec_planes[1][g.vec_base + (size_t)r * n + i] = to_double(o.Q[r]);
-    a.vec_planes[2][g.vec_base + (size_t)r * n + i] = to_double(o.FL[r]);
-    a.vec_planes[3][g.vec_base + (size_t)r * n + i] = to_double(o.QL[r]);
-  }
-#pragma unroll
-  for (int s = 0; s < T::kSlots; ++s) {
-    a.mat_planes[0][g.mat_base + (size_t)s * n + i] = to_double(o.JF[s]);
-    a.mat_planes[1][g.mat_base + (size_t)s * n + i] = to_double(o.JQ[s]);
-  }
-}
-
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_INFO(idx_, nm_) {adms::gen_##nm_::Traits::kNodes, adms::gen_##nm_::Traits::kSlots, adms::gen_##nm_::Traits::kNumFields, 0, 0, \
-                                adms::gen_##nm_::Traits::slot_row(), adms::gen_##nm_::Traits::slot_col()},
+#define XB_GEN_DECL(i_, nm_, nodes_, ext_, slots_, nf_) void launch_adms_gen_##nm_(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
+XB_ADMS_GEN_LIST(XB_GEN_DECL)
+#undef XB_GEN_DECL
+namespace {
+#define XB_GEN_INFO(i_, nm_, nodes_, ext_, slots_, nf_) {nodes_, slots_, nf_, 0, 0, kAdmsRow_##nm_, kAdmsCol_##nm_},
 const TypeInfo kGenInfo[XB_ADMS_GEN_COUNT] = {XB_ADMS_GEN_LIST(XB_GEN_INFO)};
 #undef XB_GEN_INFO
-#endif
-
 }  // namespace
+#endif
 
 const TypeInfo *adms_gen_type_info(int type) {
 #ifdef XB_HAVE_ADMS_GEN
@@ -89,7 +41,7 @@ int adms_gen_count() {
 }
 const char *adms_gen_name(int idx) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_NAME(i, nm_) if (idx == i) return adms::gen_##nm_::Traits::name();
+#define XB_GEN_NAME(i_, nm_, nodes_, ext_, slots_, nf_) if (idx == i_) return #nm_;
   XB_ADMS_GEN_LIST(XB_GEN_NAME)
 #undef XB_GEN_NAME
 #endif
@@ -98,7 +50,7 @@ const char *adms_gen_name(int idx) {
 }
 const char *adms_gen_fields(int idx) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_FIELDS(i, nm_) if (idx == i) return adms::gen_##nm_::Traits::fields();
+#define XB_GEN_FIELDS(i_, nm_, nodes_, ext_, slots_, nf_) if (idx == i_) return kAdmsFields_##nm_;
   XB_ADMS_GEN_LIST(XB_GEN_FIELDS)
 #undef XB_GEN_FIELDS
 #endif
@@ -107,7 +59,7 @@ const char *adms_gen_fields(int idx) {
 }
 int adms_gen_ext(int idx) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_EXT(i, nm_) if (idx == i) return adms::gen_##nm_::Traits::kExt;
+#define XB_GEN_EXT(i_, nm_, nodes_, ext_, slots_, nf_) if (idx == i_) return ext_;
   XB_ADMS_GEN_LIST(XB_GEN_EXT)
 #undef XB_GEN_EXT
 #endif
@@ -116,14 +68,12 @@ int adms_gen_ext(int idx) {
 }
 
 void launch_adms_gen_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
-  if (g.n <= 0) return;
-  const int blocks = (g.n + 127) / 128;
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_LAUNCH(i, nm_) if (g.type == kAdmsGenBase + i) xb::launch_pdl(adms_gen_kernel<adms::gen_##nm_::Traits>, dim3(blocks), dim3(128), 0, s, g, a);
+#define XB_GEN_LAUNCH(i_, nm_, nodes_, ext_, slots_, nf_) if (g.type == kAdmsGenBase + i_) { launch_adms_gen_##nm_(g, a, s); return; }
   XB_ADMS_GEN_LIST(XB_GEN_LAUNCH)
 #undef XB_GEN_LAUNCH
 #endif
-  (void)blocks; (void)a; (void)s;
+  (void)g; (void)a; (void)s;
 }
 
 }  // namespace simple

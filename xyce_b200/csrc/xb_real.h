@@ -95,6 +95,10 @@ struct RealT {
   friend XBR_HD RealT sinh(const RealT &a) { return RealT(::sinh(a.v)); }
   friend XBR_HD RealT cosh(const RealT &a) { return RealT(::cosh(a.v)); }
   friend XBR_HD RealT tanh(const RealT &a) { return RealT(::tanh(a.v)); }
+  friend XBR_HD RealT asinh(const RealT &a) { return RealT(::asinh(a.v)); }
+  friend XBR_HD RealT acosh(const RealT &a) { return RealT(::acosh(a.v)); }
+  friend XBR_HD RealT atanh(const RealT &a) { return RealT(::atanh(a.v)); }
+  friend XBR_HD RealT hypot(const RealT &a, const RealT &b) { return RealT(::hypot(a.v, b.v)); }
   friend XBR_HD RealT log10(const RealT &a) { return RealT(::log10(a.v)); }
   friend XBR_HD RealT atan2(const RealT &a, const RealT &b) { return RealT(::atan2(a.v, b.v)); }
   friend XBR_HD RealT floor(const RealT &a) { return RealT(::floor(a.v)); }
