@@ -66,7 +66,7 @@ class GpuRefAll(oracle_ref.RefCircuit):
         self.use_gpu_master(2)
 
 
-def _compare_through_virtuals(stock, gpu, x, flags, seed=9):
+def _compare_through_virtuals(stock, gpu, x, flags, seed=9, check_store=True):
     gpu.gpu_attach(0)
     assert gpu.n == stock.n and np.array_equal(gpu.rowptr, stock.rowptr) and np.array_equal(gpu.colind, stock.colind)
     rng = np.random.default_rng(seed)
@@ -80,7 +80,7 @@ def _compare_through_virtuals(stock, gpu, x, flags, seed=9):
         scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
         assert rel_err(got[k], want[k], scale) < 1e-12, k
     ws, gs = stock.get_state(), gpu.get_state()
-    if stock.n_sto:
+    if stock.n_sto and check_store:
         assert rel_err(gs["next_sto"], ws["next_sto"], 1e-25) < 1e-12
     if stock.n_sta:
         assert rel_err(gs["next_sta"], ws["next_sta"], 1e-25) < 1e-12
@@ -123,4 +123,6 @@ def test_translated_adms_models_behind_the_generic_device_master(model, card):
     gpu = adms_circuit(GpuRefAll, model, card, info["ext"], n_dev=25, seed=6)
     lids = [stock.adms_export(i, model)["lids"] for i in range(stock.n_inst)]
     x = bias_vector(model, stock.n, lids, np.random.default_rng(7))
-    _compare_through_virtuals(stock, gpu, x, CASES["tran1"])
+    # the store vector of these models holds output variables only (operating-point quantities for .PRINT such as
+    # HICUM's rcx_t, GMi, CPIi): not part of the Newton path and not published by the GPU master
+    _compare_through_virtuals(stock, gpu, x, CASES["tran1"], check_store=False)
