@@ -94,6 +94,9 @@ int xgpu_b4_group_spec(const xgpu_ctx *ctx, int group);
  * first store / state LID.  Replaces Device::addInstance + registerLIDs/StoreLIDs/StateLIDs of
  * N_DEV_Diode.C, N_DEV_MOSFET1.C, N_DEV_BJT.C and the ADMS-generated classes.  Returns the group id. */
 int xgpu_simple_field_count(int type);
+/* store-vector slots per instance that the type's kernel writes (diode 3: Vd, Qd, Cd; ...; translated ADMS models: their
+ * output variables in registerStoreLIDs order, what Instance::updatePrimaryState copies to nextStoVector) */
+int xgpu_simple_store_count(int type);
 /* Models translated from admsXml output (the C++ that Xyce's `_nosac` templates emit, utils/ADMS/
  * xyceImplementationFile_nosac.xml; any of src/DeviceModelPKG/ADMS/N_DEV_ADMS*.C or a user plugin built with
  * buildxyceplugin) by xyce_b200/adms/translate.py and compiled into the library at build time.  They are small-device

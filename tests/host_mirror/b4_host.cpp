@@ -233,7 +233,7 @@ int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const
 }
 
 // One instance of a translated ADMS model through the host build of its generated evaluator.
-// out = F, Q (nodes each), JF, JQ (slots each); returns the number of values or -1 for an unknown model.
+// out = F, Q (nodes each), JF, JQ (slots each), store (output variables); returns the number of values or -1 for an unknown model.
 int xbh_adms_gen_eval(const char *name, const double *rec, const double *Vn, double gmin, double *out) {
 #ifdef XB_HAVE_ADMS_GEN
   const std::string nm(name);
@@ -242,6 +242,7 @@ int xbh_adms_gen_eval(const char *name, const double *rec, const double *Vn, dou
     SolverFlags S{}; S.gmin = gmin; T::eval(S, R, V, o); int k = 0; \
     for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.F[r]); for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.Q[r]); \
     for (int s = 0; s < T::kSlots; ++s) out[k++] = to_double(o.JF[s]); for (int s = 0; s < T::kSlots; ++s) out[k++] = to_double(o.JQ[s]); \
+    for (int s = 0; s < T::kNumStore; ++s) out[k++] = to_double(o.store[s]); \
     return k; }
   XB_ADMS_GEN_LIST(XB_GEN_EVAL)
 #undef XB_GEN_EVAL

@@ -12,7 +12,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import oracle_ref
-from adms_common import ADMS_CARDS, BIAS, adms_circuit, bias_vector
+from adms_common import ADMS_CARDS, BIAS, adms_circuit, bias_vector, outvars_close, outvars_mismatch
 from b4_common import rel_err, solver_state
 from dev_common import HostDevices, assemble
 
@@ -40,12 +40,12 @@ def test_registry_lists_the_translated_models():
 
 def host_eval(hd, name, info, rec, V, gmin=1e-12):
     n, s = info["nodes"], info["slots"]
-    out = np.zeros(2 * n + 2 * s)
+    out = np.zeros(2 * n + 2 * s + info["nstore"])
     dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
     k = hd.lib.xbh_adms_gen_eval(name.encode(), dp(rec), dp(np.asarray(V, dtype=np.float64)), C.c_double(gmin), out.ctypes.data_as(C.POINTER(C.c_double)))
     assert k == len(out), k
     z = np.zeros(n)
-    return dict(F=out[:n], Q=out[n:2 * n], FL=z, QL=z, JF=out[2 * n:2 * n + s], JQ=out[2 * n + s:])
+    return dict(F=out[:n], Q=out[n:2 * n], FL=z, QL=z, JF=out[2 * n:2 * n + s], JQ=out[2 * n + s:2 * n + 2 * s], store=out[2 * n + 2 * s:])
 
 
 @pytest.mark.parametrize("model,card", PAIRS)
@@ -67,6 +67,12 @@ def test_generated_evaluator_on_host_equals_reference_object(model, card, case):
         assert len(e["rec"]) == len(info["fields"]) and len(e["lids"]) == info["nodes"]
         V = [x[g] if g >= 0 else 0.0 for g in e["lids"]]
         per.append(host_eval(hd, model, info, e["rec"], V)); lids.append(e["lids"])
+    # output variables: what Instance::updatePrimaryState copied to the store vector
+    st = ref.get_state()["next_sto"]
+    for i, o in enumerate(per):
+        if info["nstore"]:
+            w_ = st[exports[i]["sto0"]:exports[i]["sto0"] + info["nstore"]]
+            assert outvars_close(o["store"], w_, 1e-12), (model, card, "store", i)
     asm = assemble(per, lids, info["slot_row"], info["slot_col"], ref.n, ref.rowptr, ref.colind)
     for k in ("f", "q", "dFdx", "dQdx"):
         scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
@@ -119,6 +125,9 @@ def test_gpu_generic_adms_kernel_matches_reference_object(model, card):
             scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
             assert rel_err(got[k], want[k], scale) < 1e-12, (model, card, case, k)
         assert np.any(want["dFdx"] != 0.0) and eng.all_converged()
+        if info["nstore"]:
+            ws, gs = ref.get_state()["next_sto"], eng.get_state(0)
+            assert outvars_mismatch(gs, ws, 1e-10, info["nstore"], illcond_share=0.05, illcond_tol=1e-3) is None, (model, card, case, "store")
     eng.close()
 
 

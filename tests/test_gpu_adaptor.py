@@ -66,7 +66,7 @@ class GpuRefAll(oracle_ref.RefCircuit):
         self.use_gpu_master(2)
 
 
-def _compare_through_virtuals(stock, gpu, x, flags, seed=9, check_store=True):
+def _compare_through_virtuals(stock, gpu, x, flags, seed=9, check_store=True, adms=False, nstore=None):
     gpu.gpu_attach(0)
     assert gpu.n == stock.n and np.array_equal(gpu.rowptr, stock.rowptr) and np.array_equal(gpu.colind, stock.colind)
     rng = np.random.default_rng(seed)
@@ -81,7 +81,8 @@ def _compare_through_virtuals(stock, gpu, x, flags, seed=9, check_store=True):
         assert rel_err(got[k], want[k], scale) < 1e-12, k
     ws, gs = stock.get_state(), gpu.get_state()
     if stock.n_sto and check_store:
-        assert rel_err(gs["next_sto"], ws["next_sto"], 1e-25) < 1e-12
+        from adms_common import outvars_close
+        assert outvars_close(gs["next_sto"], ws["next_sto"], 1e-10 if adms else 1e-12, nstore, illcond_share=0.05 if adms else 0.0, illcond_tol=1e-3)
     if stock.n_sta:
         assert rel_err(gs["next_sta"], ws["next_sta"], 1e-25) < 1e-12
     assert gpu.all_converged() == stock.all_converged()
@@ -123,6 +124,6 @@ def test_translated_adms_models_behind_the_generic_device_master(model, card):
     gpu = adms_circuit(GpuRefAll, model, card, info["ext"], n_dev=25, seed=6)
     lids = [stock.adms_export(i, model)["lids"] for i in range(stock.n_inst)]
     x = bias_vector(model, stock.n, lids, np.random.default_rng(7))
-    # the store vector of these models holds output variables only (operating-point quantities for .PRINT such as
-    # HICUM's rcx_t, GMi, CPIi): not part of the Newton path and not published by the GPU master
-    _compare_through_virtuals(stock, gpu, x, CASES["tran1"], check_store=False)
+    # the store vector of these models holds their output variables (operating-point quantities for .PRINT such as
+    # HICUM's rcx_t, GMi, CPIi), published by the generic kernel like Instance::updatePrimaryState does
+    _compare_through_virtuals(stock, gpu, x, CASES["tran1"], adms=True, nstore=info["nstore"])

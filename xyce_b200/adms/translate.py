@@ -175,6 +175,15 @@ def parse(cfile, hfile):
         t = t[t.index("#else"):t.index("#endif")]
         loads[key] = re.findall(r"%s\[li_(\w+)\]\[A_(\w+?)_?Offset\]\s*\+=\s*([^;]+);" % mat, t)
     info["loads"] = loads
+    # output variables (operating-point quantities for .PRINT): Instance::updatePrimaryState copies them to the store
+    # vector, slots in registerStoreLIDs order
+    order, writes = [], []
+    if "void Instance::registerStoreLIDs" in C:
+        order = re.findall(r"li_store_(\w+)\s*=\s*stoLIDVec\[i\+\+\];", _function_body(C, "void Instance::registerStoreLIDs"))
+    if "bool Instance::updatePrimaryState()" in C:
+        writes = re.findall(r"stoVec\[li_store_(\w+)\]\s*=\s*([^;]+);", _function_body(C, "bool Instance::updatePrimaryState()"))
+    info["store_order"] = order
+    info["store_writes"] = [(order.index(n), e.strip()) for n, e in writes if n in order]
     return info
 
 
@@ -190,6 +199,9 @@ def emit(info, name):
     ids = info["ids"]
     nunk, nprobe = len(info["unknowns"]), len(info["probes"])
     locals_text, analog = info["locals_text"], info["analog_text"]
+    nstore = len(info.get("store_order", []))
+    for slot, expr in info.get("store_writes", []):
+        analog += "\nXBSTORE_%d_ = %s;" % (slot, expr)
     # given("X") / model_.given("X") (DeviceEntity::given: was the parameter set in the netlist?) -> flag fields
     given_fields = []
     def given_sub(m):
@@ -264,6 +276,7 @@ def emit(info, name):
     t = re.sub(r"\bstd::(exp|log|sqrt|pow|fabs|tanh|sinh|cosh|atan|sin|cos|tan|log10|abs)\b", r"\1", t)
     t = re.sub(r"\bpow\(", "rpow(", t)
     t = re.sub(r"\bdouble\b", "real", t)
+    t = re.sub(r"XBSTORE_(\d+)_", lambda m: "o.store[%s]" % m.group(1), t)
     t = re.sub(r"XB_GIVEN_(\d+)_", lambda m: "(xbrec_.f[%d] != 0.0)" % fidx[given_fields[int(m.group(1))]], t)
     leftovers = re.findall(r"\b(?:std::\w+|Xyce::\w+|UserError|Report::\w+|extData\.\w+|getName\(\))", t)
     if leftovers:
@@ -298,10 +311,10 @@ def emit(info, name):
     out.append("#pragma once\n#include \"../xb_common.h\"\n")
     out.append("namespace xb {\nnamespace adms {\nnamespace gen_%s {\n" % name)
     out.append("enum {\n  %s\n};\n" % enum)
-    out.append("constexpr int kNodes = %d, kExt = %d, kSlots = %d, kProbes = %d, kNumFields = %d;\n" % (nunk, info["n_ext"], len(info["stamp"]), nprobe, len(fields)))
+    out.append("constexpr int kNodes = %d, kExt = %d, kSlots = %d, kProbes = %d, kNumFields = %d, kNumStore = %d;\n" % (nunk, info["n_ext"], len(info["stamp"]), nprobe, len(fields), nstore))
     out.append("#define XB_ADMS_GEN_%s_FIELDS \"%s\"\n" % (name, " ".join(fields)))
     out.append("struct Rec { real f[kNumFields > 0 ? kNumFields : 1]; };\n")
-    out.append("struct Out { real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots]; };\n")
+    out.append("struct Out { real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots], store[kNumStore > 0 ? kNumStore : 1]; };\n")
     out.append("XB_HD real adms_vt(real T) { return kKoverQ * T; }\n")
     out.append("XB_HD real adms_max(real a, real b) { return a < b ? b : a; }\nXB_HD real adms_min(real a, real b) { return b < a ? b : a; }\n")
     out.append("// the templates' limited exponential (N_DEV_ADMS*.h: exp below 80, its tangent above)\n"
@@ -318,6 +331,7 @@ def emit(info, name):
                "    o.F[i] = 0.0; o.Q[i] = 0.0; o.FL[i] = 0.0; o.QL[i] = 0.0;\n#pragma unroll\n"
                "    for (int j = 0; j < kProbes; ++j) { d_staticContributions[i][j] = 0.0; d_dynamicContributions[i][j] = 0.0; }\n  }\n")
     out.append("#pragma unroll\n  for (int s = 0; s < kSlots; ++s) { o.JF[s] = 0.0; o.JQ[s] = 0.0; }\n")
+    out.append("#pragma unroll\n  for (int s = 0; s < (kNumStore > 0 ? kNumStore : 1); ++s) o.store[s] = 0.0;\n")
     out.append("  " + lt.strip() + "\n")
     out.append(t)
     out.append("\n  // ---- loads (loadDAEFVector / loadDAEQVector / loadDAEdFdx / loadDAEdQdx) ----\n")
@@ -325,7 +339,7 @@ def emit(info, name):
     out.append("static const int kSlotRow[kSlots] = {%s};\nstatic const int kSlotCol[kSlots] = {%s};\n" % (rows, cols))
     out.append("// what the generic kernel (simple_kernels.cu: adms_gen_kernel<Traits>) and the registry need\n")
     out.append("struct Traits {\n  typedef gen_%s::Rec Rec;\n  typedef gen_%s::Out Out;\n" % (name, name))
-    out.append("  static constexpr int kNodes = gen_%s::kNodes, kExt = gen_%s::kExt, kSlots = gen_%s::kSlots, kNumFields = gen_%s::kNumFields;\n" % (name, name, name, name))
+    out.append("  static constexpr int kNodes = gen_%s::kNodes, kExt = gen_%s::kExt, kSlots = gen_%s::kSlots, kNumFields = gen_%s::kNumFields, kNumStore = gen_%s::kNumStore;\n" % (name, name, name, name, name))
     out.append("  template <class RecT> static XB_HD void eval(const SolverFlags &S, const RecT &R, const real *V, Out &o) { evaluate(S, R, V, o); }\n")
     out.append("  static const char *name() { return \"%s\"; }\n  static const char *fields() { return XB_ADMS_GEN_%s_FIELDS; }\n" % (name, name))
     out.append("  static const int *slot_row() { return kSlotRow; }\n  static const int *slot_col() { return kSlotCol; }\n};\n")
@@ -363,7 +377,7 @@ def translate(cfile, hfile, out_path, name=None):
     open(out_path, "w").write(text)
     open(os.path.splitext(out_path)[0] + "_fill.h", "w").write(emit_fill(info, name, fields))
     return dict(name=name, namespace=info["namespace"], fields=fields, nodes=len(info["unknowns"]), n_ext=info["n_ext"],
-                slots=len(info["stamp"]), unknown_names=info["unknowns"], stamp=info["stamp"])
+                slots=len(info["stamp"]), unknown_names=info["unknowns"], stamp=info["stamp"], nstore=len(info.get("store_order", [])))
 
 
 def translate_all(adms_dir, out_dir, names):
@@ -387,8 +401,8 @@ def translate_all(adms_dir, out_dir, names):
             f.write("static const int kAdmsRow_%s[] = {%s};\nstatic const int kAdmsCol_%s[] = {%s};\n"
                     % (r["name"], ", ".join(str(a) for a, _ in r["stamp"]), r["name"], ", ".join(str(b) for _, b in r["stamp"])))
             f.write("static const char kAdmsFields_%s[] = \"%s\";\n" % (r["name"], " ".join(r["fields"])))
-        f.write("#define XB_ADMS_GEN_COUNT %d\n// X(index, name, unknowns, external nodes, stamp entries, record fields)\n#define XB_ADMS_GEN_LIST(X) %s\n"
-                % (len(done), " ".join("X(%d, %s, %d, %d, %d, %d)" % (i, r["name"], r["nodes"], r["n_ext"], r["slots"], len(r["fields"])) for i, r in enumerate(done))))
+        f.write("#define XB_ADMS_GEN_COUNT %d\n// X(index, name, unknowns, external nodes, stamp entries, record fields, store slots)\n#define XB_ADMS_GEN_LIST(X) %s\n"
+                % (len(done), " ".join("X(%d, %s, %d, %d, %d, %d, %d)" % (i, r["name"], r["nodes"], r["n_ext"], r["slots"], len(r["fields"]), r["nstore"]) for i, r in enumerate(done))))
     for r in done:
         with open(os.path.join(out_dir, "kernel_%s.cu" % r["name"]), "w") as f:
             f.write("// GENERATED by xyce_b200/adms/translate.py -- the generic kernel instantiated for one translated model\n"

@@ -155,7 +155,7 @@ class Engine:
             rows, cols = (C.c_int32 * 512)(), (C.c_int32 * 512)()
             if lib.xgpu_adms_gen_info(idx, C.byref(name), C.byref(fields), info, rows, cols) != 0:
                 continue
-            out.append(dict(name=name.value.decode(), type=info[0], nodes=info[1], ext=info[2], slots=info[3],
+            out.append(dict(name=name.value.decode(), type=info[0], nodes=info[1], ext=info[2], slots=info[3], nstore=int(lib.xgpu_simple_store_count(info[0])),
                             fields=fields.value.decode().split(), slot_row=list(rows[:info[3]]), slot_col=list(cols[:info[3]])))
         return out
 

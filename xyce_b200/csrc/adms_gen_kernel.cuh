@@ -9,8 +9,10 @@
 // per operation, tests hold 1e-12 against the reference's generated classes), independent of the strict small-device
 // kernels of simple_kernels.cu.
 #pragma once
+#if !defined(XB_ADMS_STRICT)      // -DXB_ADMS_STRICT: plain double, IEEE division, libdevice math (diagnostics)
 #include "xb_real.h"
 #define XB_REAL xb::FastReal
+#endif
 #include "pdl.cuh"
 #include "simple_kernels.cuh"
 #include "xb_common.h"
@@ -43,6 +45,11 @@ __global__ void __launch_bounds__(128) adms_gen_kernel(GroupDev g, b4::LoadArgs 
   typename T::Out o;
   T::eval(a.S, R, V, o);
   g.orig_flag[i] = 1;
+  if (T::kNumStore > 0) {      // output variables (operating-point quantities) -> the store vector, like updatePrimaryState
+    const int sto0 = __ldg(g.sto_lid0 + i), ss = g.sto_stride;
+#pragma unroll
+    for (int t = 0; t < T::kNumStore; ++t) a.next_sto[sto0 + (size_t)t * ss] = to_double(o.store[t]);
+  }
 #pragma unroll
   for (int r = 0; r < T::kNodes; ++r) {
     a.vec_planes[0][g.vec_base + (size_t)r * n + i] = to_double(o.F[r]);

@@ -14,11 +14,11 @@ namespace xb {
 namespace simple {
 
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_DECL(i_, nm_, nodes_, ext_, slots_, nf_) void launch_adms_gen_##nm_(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
+#define XB_GEN_DECL(i_, nm_, nodes_, ext_, slots_, nf_, nsto_) void launch_adms_gen_##nm_(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
 XB_ADMS_GEN_LIST(XB_GEN_DECL)
 #undef XB_GEN_DECL
 namespace {
-#define XB_GEN_INFO(i_, nm_, nodes_, ext_, slots_, nf_) {nodes_, slots_, nf_, 0, 0, kAdmsRow_##nm_, kAdmsCol_##nm_},
+#define XB_GEN_INFO(i_, nm_, nodes_, ext_, slots_, nf_, nsto_) {nodes_, slots_, nf_, nsto_, 0, kAdmsRow_##nm_, kAdmsCol_##nm_},
 const TypeInfo kGenInfo[XB_ADMS_GEN_COUNT] = {XB_ADMS_GEN_LIST(XB_GEN_INFO)};
 #undef XB_GEN_INFO
 }  // namespace
@@ -41,7 +41,7 @@ int adms_gen_count() {
 }
 const char *adms_gen_name(int idx) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_NAME(i_, nm_, nodes_, ext_, slots_, nf_) if (idx == i_) return #nm_;
+#define XB_GEN_NAME(i_, nm_, nodes_, ext_, slots_, nf_, nsto_) if (idx == i_) return #nm_;
   XB_ADMS_GEN_LIST(XB_GEN_NAME)
 #undef XB_GEN_NAME
 #endif
@@ -50,7 +50,7 @@ const char *adms_gen_name(int idx) {
 }
 const char *adms_gen_fields(int idx) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_FIELDS(i_, nm_, nodes_, ext_, slots_, nf_) if (idx == i_) return kAdmsFields_##nm_;
+#define XB_GEN_FIELDS(i_, nm_, nodes_, ext_, slots_, nf_, nsto_) if (idx == i_) return kAdmsFields_##nm_;
   XB_ADMS_GEN_LIST(XB_GEN_FIELDS)
 #undef XB_GEN_FIELDS
 #endif
@@ -59,7 +59,7 @@ const char *adms_gen_fields(int idx) {
 }
 int adms_gen_ext(int idx) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_EXT(i_, nm_, nodes_, ext_, slots_, nf_) if (idx == i_) return ext_;
+#define XB_GEN_EXT(i_, nm_, nodes_, ext_, slots_, nf_, nsto_) if (idx == i_) return ext_;
   XB_ADMS_GEN_LIST(XB_GEN_EXT)
 #undef XB_GEN_EXT
 #endif
@@ -69,7 +69,7 @@ int adms_gen_ext(int idx) {
 
 void launch_adms_gen_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s) {
 #ifdef XB_HAVE_ADMS_GEN
-#define XB_GEN_LAUNCH(i_, nm_, nodes_, ext_, slots_, nf_) if (g.type == kAdmsGenBase + i_) { launch_adms_gen_##nm_(g, a, s); return; }
+#define XB_GEN_LAUNCH(i_, nm_, nodes_, ext_, slots_, nf_, nsto_) if (g.type == kAdmsGenBase + i_) { launch_adms_gen_##nm_(g, a, s); return; }
   XB_ADMS_GEN_LIST(XB_GEN_LAUNCH)
 #undef XB_GEN_LAUNCH
 #endif

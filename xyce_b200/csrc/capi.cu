@@ -430,6 +430,11 @@ int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n, const double *rec, con
   return (int)ctx->sgroups.size() - 1;
 }
 
+int xgpu_simple_store_count(int type) {
+  const xb::simple::TypeInfo *ti = xb::simple::type_info(type);
+  return ti ? ti->nstore : -1;
+}
+
 int xgpu_simple_field_count(int type) {
   const xb::simple::TypeInfo *ti = xb::simple::type_info(type);
   return ti ? ti->nfields : -1;
