@@ -234,20 +234,33 @@ int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const
 
 // One instance of a translated ADMS model through the host build of its generated evaluator.
 // out = F, Q (nodes each), JF, JQ (slots each), store (output variables); returns the number of values or -1 for an unknown model.
+int xbh_adms_gen_eval2(const char *name, const double *rec, const double *Vn, const int *fl, const double *fd, const double *curr_sto,
+                       const double *next_sto, double *out);
 int xbh_adms_gen_eval(const char *name, const double *rec, const double *Vn, double gmin, double *out) {
+  const int fl[12] = {0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 1};
+  const double fd[3] = {gmin, 1.0, 1.0};
+  return xbh_adms_gen_eval2(name, rec, Vn, fl, fd, nullptr, nullptr, out);
+}
+// the same with the solver flags (b4_common FLAG order) and the store vectors of the instance (limited probes);
+// out additionally ends with FL, QL (nodes each) and origFlag
+int xbh_adms_gen_eval2(const char *name, const double *rec, const double *Vn, const int *fl, const double *fd, const double *curr_sto,
+                       const double *next_sto, double *out) {
 #ifdef XB_HAVE_ADMS_GEN
   const std::string nm(name);
 #define XB_GEN_EVAL(i, nm_) if (nm == #nm_) { typedef xb::adms::gen_##nm_::Traits T; T::Rec R; T::Out o; real V[T::kNodes]; \
     for (int k = 0; k < T::kNumFields; ++k) R.f[k] = rec[k]; for (int k = 0; k < T::kNodes; ++k) V[k] = Vn[k]; \
-    SolverFlags S{}; S.gmin = gmin; T::eval(S, R, V, o); int k = 0; \
+    SolverFlags S; fill_flags(S, fl, fd); real cs[T::kNumStore + 1], ns[T::kNumStore + 1]; \
+    for (int t = 0; t < T::kNumStore; ++t) { cs[t] = curr_sto ? curr_sto[t] : 0.0; ns[t] = next_sto ? next_sto[t] : 0.0; } \
+    T::eval(S, R, V, o, cs, ns); int k = 0; \
     for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.F[r]); for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.Q[r]); \
     for (int s = 0; s < T::kSlots; ++s) out[k++] = to_double(o.JF[s]); for (int s = 0; s < T::kSlots; ++s) out[k++] = to_double(o.JQ[s]); \
     for (int s = 0; s < T::kNumStore; ++s) out[k++] = to_double(o.store[s]); \
+    if (curr_sto) { for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.FL[r]); for (int r = 0; r < T::kNodes; ++r) out[k++] = to_double(o.QL[r]); out[k++] = o.origFlag; } \
     return k; }
   XB_ADMS_GEN_LIST(XB_GEN_EVAL)
 #undef XB_GEN_EVAL
 #endif
-  (void)name; (void)rec; (void)Vn; (void)gmin; (void)out;
+  (void)name; (void)rec; (void)Vn; (void)fl; (void)fd; (void)curr_sto; (void)next_sto; (void)out;
   return -1;
 }
 

@@ -12,7 +12,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import oracle_ref
-from adms_common import ADMS_CARDS, BIAS, adms_circuit, bias_vector, outvars_close, outvars_mismatch
+from adms_common import ADMS_CARDS, BIAS, LIMITED, adms_circuit, bias_vector, outvars_close, outvars_mismatch
 from b4_common import rel_err, solver_state
 from dev_common import HostDevices, assemble
 
@@ -23,7 +23,11 @@ import xyce_b200
 from xyce_b200.capi import Engine
 
 MODELS = {m["name"]: m for m in Engine.adms_gen_models()}
-PAIRS = [(m, c) for m in sorted(ADMS_CARDS) for c in sorted(ADMS_CARDS[m])]
+PAIRS = [(m, c) for m in sorted(ADMS_CARDS) for c in sorted(ADMS_CARDS[m]) if m not in LIMITED]
+LIMITED_PAIRS = [(m, c) for m in LIMITED for c in sorted(ADMS_CARDS[m])]
+LIMIT_CASES = {"tran_iter1": dict(transient=1, newtonIter=1), "tran_iter0": dict(transient=1, newtonIter=0),
+               "dcop_initjct": dict(dcop=1, tranop=1, initJct=1, newtonIter=0), "dcop_iter2": dict(dcop=1, tranop=1, newtonIter=2),
+               "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0)}
 
 
 def test_registry_lists_the_translated_models():
@@ -180,3 +184,86 @@ def test_gpu_ekv_inverter_dcop_and_tran_match_reference_flow():
     tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
     assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
     assert want["wave"][0, OUT] > 1.7 and np.min(want["wave"][:, OUT]) < 0.1      # the inverter switches
+
+
+def host_eval_limited(hd, name, info, rec, V, flags, cs, ns):
+    from dev_common import flag_arrays
+    n, s_, k_ = info["nodes"], info["slots"], info["nstore"]
+    out = np.zeros(4 * n + 2 * s_ + k_ + 1)
+    fl, fd = flag_arrays(flags)
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (rec, V, cs, ns)]
+    k = hd.lib.xbh_adms_gen_eval2(name.encode(), dp(keep[0]), dp(keep[1]), fl.ctypes.data_as(C.POINTER(C.c_int)), dp(fd), dp(keep[2]), dp(keep[3]),
+                                  out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert k == len(out), k
+    o = 2 * n + 2 * s_ + k_
+    return dict(F=out[:n], Q=out[n:2 * n], JF=out[2 * n:2 * n + s_], JQ=out[2 * n + s_:2 * n + 2 * s_], store=out[2 * n + 2 * s_:o],
+                FL=out[o:o + n], QL=out[o + n:o + 2 * n], orig=int(out[o + 2 * n]))
+
+
+@pytest.mark.parametrize("model,card", LIMITED_PAIRS)
+@pytest.mark.parametrize("case", sorted(LIMIT_CASES))
+def test_limited_models_on_host_equal_reference_object(model, card, case):
+    """$limit: VBIC 1.3 and Mextram 504 -- limited junction voltages (pnjlim / pnjlim_new / the model's own limRTH), the
+    dFdxdVp / dQdxdVp correction vectors, the limited probes saved to the store vector and Instance::isConverged (origFlag)
+    against the reference's generated classes, with the previous-iterate voltages far enough from the new ones that the
+    limiters act."""
+    info = MODELS[model]
+    hd = HostDevices()
+    ref = adms_circuit(oracle_ref.RefCircuit, model, card, info["ext"], n_dev=8, seed=3)
+    flags = LIMIT_CASES[case]
+    ref.set_flags(**flags)
+    rng = np.random.default_rng(12)
+    exports = [ref.adms_export(i, model) for i in range(ref.n_inst)]
+    x = bias_vector(model, ref.n, [e["lids"] for e in exports], rng)
+    csto, nsto = rng.uniform(0.0, 0.3, ref.n_sto), rng.uniform(0.0, 0.3, ref.n_sto)
+    ref.set_state(curr_sto=csto, next_sto=nsto)
+    want = ref.load(x)
+    assert not any(np.any(np.isnan(v)) for v in want.values())
+    st = ref.get_state()["next_sto"]
+    per, lids, limited = [], [], 0
+    for i, e in enumerate(exports):
+        V = [x[g] if g >= 0 else 0.0 for g in e["lids"]]
+        k0 = e["sto0"]
+        o = host_eval_limited(hd, model, info, e["rec"], V, flags, csto[k0:k0 + info["nstore"]], nsto[k0:k0 + info["nstore"]])
+        per.append(o); lids.append(e["lids"])
+        assert outvars_close(o["store"], st[k0:k0 + info["nstore"]], 1e-12), (model, card, case, "store", i)
+        assert o["orig"] == ref.lib.xref_inst_converged(ref.h, i), (i, "isConverged")
+        limited += 1 - o["orig"]
+    asm = assemble(per, lids, info["slot_row"], info["slot_col"], ref.n, ref.rowptr, ref.colind)
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(asm[k], want[k], scale) < 1e-13, (model, card, case, k)
+    if case in ("tran_iter1", "tran_iter0", "dcop_iter2"):
+        assert limited > 0 and np.any(want["dFdxdVp"])      # the limiters did act
+    if case == "nolimit":
+        assert limited == 0 and not np.any(want["dFdxdVp"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,card", LIMITED_PAIRS)
+def test_gpu_limited_models_match_reference_object(model, card):
+    info = MODELS[model]
+    ref = adms_circuit(oracle_ref.RefCircuit, model, card, info["ext"], n_dev=150, seed=5)
+    ex = [ref.adms_export(i, model) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(info["type"], np.array([e["rec"] for e in ex]), [0] * len(ex), np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.finalize()
+    rng = np.random.default_rng(6)
+    for case in sorted(LIMIT_CASES):
+        flags = LIMIT_CASES[case]
+        x = bias_vector(model, ref.n, [e["lids"] for e in ex], rng)
+        csto, nsto = rng.uniform(0.0, 0.3, ref.n_sto), rng.uniform(0.0, 0.3, ref.n_sto)
+        ref.set_flags(**flags); ref.set_state(curr_sto=csto, next_sto=nsto)
+        eng.set_state(0, nsto); eng.set_state(1, csto)
+        want = ref.load(x)
+        got = eng.load_host(x, solver_state(**flags))
+        for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+            scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+            assert rel_err(got[k], want[k], scale) < 1e-12, (model, card, case, k)
+        assert outvars_mismatch(eng.get_state(0), ref.get_state()["next_sto"], 1e-10, info["nstore"], illcond_share=0.05, illcond_tol=1e-3) is None, (model, card, case)
+        assert eng.all_converged() == all(ref.lib.xref_inst_converged(ref.h, i) for i in range(ref.n_inst))
+    eng.close()

@@ -19,7 +19,8 @@ object, so results agree to the last bits) and rewrites only the plumbing around
   (*solVectorPtr)[li] -> V[node]  (node voltages gathered by the kernel)
   d_probeVars[p][p]   -> 1.0
   loads               -> o.F / o.Q rows and o.JF / o.JQ slots in constructor order
-Not supported (the translator stops with a message): $limit / limited probes (Jdxp terms).
+$limit (limited probes, Jdxp correction terms, origFlag), analog functions, node collapsing, given() / $port_connected
+tests and output variables are handled (see emit()); noise contributions are dropped.
 
 usage: python -m xyce_b200.adms.translate <N_DEV_ADMSname.C> <N_DEV_ADMSname.h> <out.h> [name]
        python -m xyce_b200.adms.translate --all <dir with N_DEV_ADMS*.C/.h> <out_dir> name...
@@ -159,8 +160,10 @@ def parse(cfile, hfile):
     s1 = body.index("// extract solution variables")
     info["locals_text"] = body[:s0]
     info["analog_text"] = re.sub(r"//[^\n]*", "", body[s1:])      # the Verilog-A source echoed in comments is not code
-    if "Jdxp" in C or "origFlag = false" in info["analog_text"]:
-        raise Unsupported("limited probes ($limit): Jdxp terms")
+    # $limit: limited probes.  The generated code keeps the limited voltages (X_limited / X_old / X_orig), the correction
+    # terms (probeDiffs, Jdxp_static / Jdxp_dynamic) and origFlag as ordinary statements of the analog block; they are
+    # carried over, with the previous-iterate values read from the store vectors the kernel passes in.
+    info["has_limit"] = "Jdxp_static" in info["analog_text"]
     info["analog_functions"] = _analog_functions(C, H) if re.search(r"AnalogFunctions::", info["analog_text"]) else ""
     if re.search(r"AnalogFunctions::", info["analog_text"]) and not info["analog_functions"]:
         raise Unsupported("analog functions are called but namespace AnalogFunctions was not found")
@@ -174,6 +177,9 @@ def parse(cfile, hfile):
         t = _function_body(C, fname)
         t = t[t.index("#else"):t.index("#endif")]
         loads[key] = re.findall(r"%s\[li_(\w+)\]\[A_(\w+?)_?Offset\]\s*\+=\s*([^;]+);" % mat, t)
+    for key, fname, vec, arr in (("FL", "bool Instance::loadDAEFVector()", "dFdxdVp", "Jdxp_static"), ("QL", "bool Instance::loadDAEQVector()", "dQdxdVp", "Jdxp_dynamic")):
+        t = _function_body(C, fname)
+        loads[key] = re.findall(r"%s\[li_(\w+)\]\s*\+=\s*([^;]+);" % vec, t)
     info["loads"] = loads
     # output variables (operating-point quantities for .PRINT): Instance::updatePrimaryState copies them to the store
     # vector, slots in registerStoreLIDs order
@@ -246,8 +252,23 @@ def emit(info, name):
     def sol(m):
         return "V[%d]" % _unknown_index(info, m.group(1))
     t = re.sub(r"\(\*solVectorPtr\)\[li_(\w+)\]", sol, t)
-    t = re.sub(r"^\s*d_probeVars\[\w+\]\[\w+\]\s*=\s*1\.0;\s*$", "", t, flags=re.M)      # the independent variables' own seeds
-    t = re.sub(r"d_probeVars\[(\w+)\]\[(\w+)\]", lambda m: "1.0" if m.group(1) == m.group(2) else "0.0", t)
+    has_limit = info.get("has_limit", False)
+    if has_limit:
+        # previous-iterate values of the limited probes: store slots in registerStoreLIDs order
+        order = info.get("store_order", [])
+        def sto(m):
+            return "%s[%d]" % ("xbcs_" if m.group(1) == "curr" else "xbns_", order.index(m.group(2)))
+        t = re.sub(r"\(\(\*extData\.(curr|next)StoVectorPtr\)\)\[li_store_(\w+)\]", sto, t)
+        t = re.sub(r"\bdevSupport\.(\w+)\(", r"adms_\1(", t)
+        t = re.sub(r"getSolverState\(\)\.newtonIter\b", "S.newtonIter", t)
+        t = re.sub(r"getSolverState\(\)\.initJctFlag_?\b", "(S.initJctFlag != 0)", t)
+        t = re.sub(r"getSolverState\(\)\.locaEnabledFlag\b", "(S.locaEnabledFlag != 0)", t)
+        t = re.sub(r"getSolverState\(\)\.inputOPFlag\b", "false", t)
+        t = t.replace("getDeviceOptions().voltageLimiterFlag", "(S.voltageLimiterFlag != 0)")
+    else:
+        t = re.sub(r"^\s*d_probeVars\[\w+\]\[\w+\]\s*=\s*1\.0;\s*$", "", t, flags=re.M)      # the independent variables' own seeds
+    if not has_limit:
+      t = re.sub(r"d_probeVars\[(\w+)\]\[(\w+)\]", lambda m: "1.0" if m.group(1) == m.group(2) else "0.0", t)
     # diagnostics inside the analog block ($strobe / $warning / $error of the Verilog-A source) have no place in a kernel
     t = re.sub(r"\b(?:UserWarning0?|UserError0?|UserFatal0?|UserInfo0?|Report::\w+)\s*\([^;]*;", ";", t)
     mtype = dict(info["model_members"])
@@ -292,6 +313,10 @@ def emit(info, name):
     for key, arr in (("F", "staticContributions"), ("Q", "dynamicContributions")):
         for li, expr in info["loads"][key]:
             lines.append("  o.%s[%d] += %s;" % (key, _unknown_index(info, li), expr.strip()))
+    lim_lines = []
+    for key in ("FL", "QL"):
+        for li, expr in info["loads"].get(key, []):
+            lim_lines.append("    o.%s[%d] += %s;" % (key, _unknown_index(info, li), expr.strip()))
     for key in ("JF", "JQ"):
         for li, ptr, expr in info["loads"][key]:
             row = _unknown_index(info, li)
@@ -314,19 +339,38 @@ def emit(info, name):
     out.append("constexpr int kNodes = %d, kExt = %d, kSlots = %d, kProbes = %d, kNumFields = %d, kNumStore = %d;\n" % (nunk, info["n_ext"], len(info["stamp"]), nprobe, len(fields), nstore))
     out.append("#define XB_ADMS_GEN_%s_FIELDS \"%s\"\n" % (name, " ".join(fields)))
     out.append("struct Rec { real f[kNumFields > 0 ? kNumFields : 1]; };\n")
-    out.append("struct Out { real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots], store[kNumStore > 0 ? kNumStore : 1]; };\n")
+    out.append("struct Out { real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots], store[kNumStore > 0 ? kNumStore : 1]; int origFlag; };\n")
     out.append("XB_HD real adms_vt(real T) { return kKoverQ * T; }\n")
     out.append("XB_HD real adms_max(real a, real b) { return a < b ? b : a; }\nXB_HD real adms_min(real a, real b) { return b < a ? b : a; }\n")
     out.append("// the templates' limited exponential (N_DEV_ADMS*.h: exp below 80, its tangent above)\n"
                "XB_HD real limexp(real x) { return (x < 80.0) ? exp(x) : exp(real(80.0)) * (x - 79.0); }\n")
+    out.append("// SPICE3 junction limiters as the templates call them (Core/N_DEV_DeviceSupport.C:161-300)\n"
+               "XB_HD real adms_pnjlim(real vnew, real vold, real vt, real vcrit, int *icheck) { int ic = 0; const real v = pnjlim(vnew, vold, vt, vcrit, ic); *icheck = ic; return v; }\n"
+               "XB_HD real adms_pnjlim_new(real vnew, real vold, real vt, real vcrit, int *icheck) {\n"
+               "  if ((vnew > vcrit) && (fabs(vnew - vold) > (vt + vt))) {\n"
+               "    if (vold > 0) { const real arg = (vnew - vold) / vt; vnew = (arg > 0) ? vold + vt * (2 + log(arg - 2)) : vold - vt * (2 + log(2 - arg)); }\n"
+               "    else vnew = vt * log(vnew / vt);\n"
+               "    *icheck = 1;\n"
+               "  } else if (vnew < 0) {\n"
+               "    const real arg = (vold > 0) ? -vold - 1 : 2 * vold - 1;\n"
+               "    if (vnew < arg) { vnew = arg; *icheck = 1; } else *icheck = 0;\n"
+               "  } else *icheck = 0;\n"
+               "  return vnew;\n}\n"
+               "XB_HD real adms_fetlim(real vnew, real vold, real vto) { return fetlim(vnew, vold, vto); }\n"
+               "XB_HD real adms_limvds(real vnew, real vold) { return limvds(vnew, vold); }\n")
     if info.get("analog_functions"):
         out.append(info["analog_functions"])
     out.append("// RecT: anything with f[k] -> field k (Rec on the host; on the device a view that loads a field where it is used,\n"
                "// so that a 76-field record does not sit in registers for the whole evaluation)\n")
-    out.append("template <class RecT>\nXB_HD void evaluate(const SolverFlags &S, const RecT &xbrec_, const real *V, Out &o) {\n")
+    out.append("template <class RecT>\nXB_HD void evaluate(const SolverFlags &S, const RecT &xbrec_, const real *V, Out &o, const real *xbcs_ = nullptr, const real *xbns_ = nullptr) {\n")
     out.append("  real probeVars[kProbes];\n  real staticContributions[kNodes], dynamicContributions[kNodes];\n")
     out.append("  real d_staticContributions[kNodes][kProbes], d_dynamicContributions[kNodes][kProbes];\n")
-    out.append("  real noiseContribsPower[16], noiseContribsExponent[16];\n  (void)noiseContribsPower; (void)noiseContribsExponent; (void)S;\n")
+    out.append("  real noiseContribsPower[16], noiseContribsExponent[16];\n  (void)noiseContribsPower; (void)noiseContribsExponent; (void)S; (void)xbcs_; (void)xbns_;\n")
+    out.append("  bool origFlag = true; (void)origFlag;\n")
+    if info.get("has_limit"):
+        out.append("  real d_probeVars[kProbes][kProbes], probeDiffs[kProbes], Jdxp_static[kNodes], Jdxp_dynamic[kNodes];\n"
+                   "#pragma unroll\n  for (int i = 0; i < kProbes; ++i) { probeDiffs[i] = 0.0;\n#pragma unroll\n    for (int j = 0; j < kProbes; ++j) d_probeVars[i][j] = 0.0; }\n"
+                   "#pragma unroll\n  for (int i = 0; i < kNodes; ++i) { Jdxp_static[i] = 0.0; Jdxp_dynamic[i] = 0.0; }\n")
     out.append("#pragma unroll\n  for (int i = 0; i < kNodes; ++i) {\n    staticContributions[i] = 0.0; dynamicContributions[i] = 0.0;\n"
                "    o.F[i] = 0.0; o.Q[i] = 0.0; o.FL[i] = 0.0; o.QL[i] = 0.0;\n#pragma unroll\n"
                "    for (int j = 0; j < kProbes; ++j) { d_staticContributions[i][j] = 0.0; d_dynamicContributions[i][j] = 0.0; }\n  }\n")
@@ -335,12 +379,16 @@ def emit(info, name):
     out.append("  " + lt.strip() + "\n")
     out.append(t)
     out.append("\n  // ---- loads (loadDAEFVector / loadDAEQVector / loadDAEdFdx / loadDAEdQdx) ----\n")
-    out.append("\n".join(lines) + "\n}\n")
+    out.append("\n".join(lines) + "\n")
+    if lim_lines:
+        out.append("  if ((S.voltageLimiterFlag != 0) && !origFlag) {      // loadDAEFVector / loadDAEQVector: dFdxdVp, dQdxdVp\n" + "\n".join(lim_lines) + "\n  }\n")
+    out.append("  o.origFlag = origFlag ? 1 : 0;\n}\n")
     out.append("static const int kSlotRow[kSlots] = {%s};\nstatic const int kSlotCol[kSlots] = {%s};\n" % (rows, cols))
     out.append("// what the generic kernel (simple_kernels.cu: adms_gen_kernel<Traits>) and the registry need\n")
     out.append("struct Traits {\n  typedef gen_%s::Rec Rec;\n  typedef gen_%s::Out Out;\n" % (name, name))
     out.append("  static constexpr int kNodes = gen_%s::kNodes, kExt = gen_%s::kExt, kSlots = gen_%s::kSlots, kNumFields = gen_%s::kNumFields, kNumStore = gen_%s::kNumStore;\n" % (name, name, name, name, name))
-    out.append("  template <class RecT> static XB_HD void eval(const SolverFlags &S, const RecT &R, const real *V, Out &o) { evaluate(S, R, V, o); }\n")
+    out.append("  template <class RecT> static XB_HD void eval(const SolverFlags &S, const RecT &R, const real *V, Out &o, const real *cs = nullptr, const real *ns = nullptr) { evaluate(S, R, V, o, cs, ns); }\n")
+    out.append("  static constexpr bool kHasLimit = %s;\n" % ("true" if info.get("has_limit") else "false"))
     out.append("  static const char *name() { return \"%s\"; }\n  static const char *fields() { return XB_ADMS_GEN_%s_FIELDS; }\n" % (name, name))
     out.append("  static const int *slot_row() { return kSlotRow; }\n  static const int *slot_col() { return kSlotCol; }\n};\n")
     out.append("}  // namespace gen_%s\n}  // namespace adms\n}  // namespace xb\n" % name)

@@ -43,10 +43,17 @@ __global__ void __launch_bounds__(128) adms_gen_kernel(GroupDev g, b4::LoadArgs 
     V[t] = real(lid >= 0 ? __ldg(a.sol + lid) : 0.0);
   }
   typename T::Out o;
-  T::eval(a.S, R, V, o);
-  g.orig_flag[i] = 1;
-  if (T::kNumStore > 0) {      // output variables (operating-point quantities) -> the store vector, like updatePrimaryState
-    const int sto0 = __ldg(g.sto_lid0 + i), ss = g.sto_stride;
+  const int sto0 = (T::kNumStore > 0) ? __ldg(g.sto_lid0 + i) : 0, ss = g.sto_stride;
+  if (T::kHasLimit) {          // $limit: previous-iterate values of the limited probes come from the store vectors
+    real cs[T::kNumStore > 0 ? T::kNumStore : 1], ns[T::kNumStore > 0 ? T::kNumStore : 1];
+#pragma unroll
+    for (int t = 0; t < T::kNumStore; ++t) { cs[t] = a.curr_sto[sto0 + (size_t)t * ss]; ns[t] = a.next_sto[sto0 + (size_t)t * ss]; }
+    T::eval(a.S, R, V, o, cs, ns);
+  } else {
+    T::eval(a.S, R, V, o);
+  }
+  g.orig_flag[i] = o.origFlag;
+  if (T::kNumStore > 0) {      // limited probes and output variables -> the store vector, like updatePrimaryState
 #pragma unroll
     for (int t = 0; t < T::kNumStore; ++t) a.next_sto[sto0 + (size_t)t * ss] = to_double(o.store[t]);
   }
