@@ -267,3 +267,54 @@ def test_gpu_limited_models_match_reference_object(model, card):
         assert outvars_mismatch(eng.get_state(0), ref.get_state()["next_sto"], 1e-10, info["nstore"], illcond_share=0.05, illcond_tol=1e-3) is None, (model, card, case)
         assert eng.all_converged() == all(ref.lib.xref_inst_converged(ref.h, i) for i in range(ref.n_inst))
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vbic_amplifier_dcop_and_tran_with_limiting_match_reference_flow():
+    """Common-emitter stage around the TRANSLATED VBIC 1.3 ($limit: junction limiting through the store vectors, initJct
+    start, origFlag in the convergence test): DC operating point from zero, then .TRAN with a SIN input, on the GPU against
+    the same driver around the reference's generated class and Kundert Sparse -- identical DCOP Newton count, step sequence
+    and per-step Newton counts, waveforms within RELTOL / ABSTOL."""
+    info = MODELS["vbic13"]
+    IN, VCC, B, Cn, BR_IN, BR_CC = range(6)
+    ref = oracle_ref.RefCircuit(6)
+    mt, mp, ip = ADMS_CARDS["vbic13"]["npn"]
+    ref.add_dev_model("adms:vbic13", "qmod", mt, 1, dict(mp, RCX=10.0, RBX=20.0, RE=1.0, CJE=2e-14, CJC=1e-14, TF=1e-11))
+    ref.add_dev_instance("adms:vbic13", "Q:1", "qmod", [Cn, B, -1], ip)
+    g, c = [], []
+    def res(a, b, r):
+        for (i, j, v) in ((a, a, 1 / r), (a, b, -1 / r), (b, a, -1 / r), (b, b, 1 / r)):
+            if i >= 0 and j >= 0: g.append((i, j, v))
+    for node, br in ((IN, BR_IN), (VCC, BR_CC)):
+        g.append((node, br, 1.0)); g.append((br, node, 1.0))
+    res(VCC, Cn, 5e2); res(IN, B, 2e4); res(VCC, B, 2e5)
+    c.append((Cn, Cn, 1e-13))
+    lin = dict(g_row=np.array([t[0] for t in g], dtype=np.int32), g_col=np.array([t[1] for t in g], dtype=np.int32),
+               g_val=np.array([t[2] for t in g]), c_row=np.array([t[0] for t in c], dtype=np.int32),
+               c_col=np.array([t[1] for t in c], dtype=np.int32), c_val=np.array([t[2] for t in c]))
+    # SIN(0.9 0.2 1GHz) at the input, 3 V supply
+    src = dict(row=np.array([BR_IN, BR_CC], dtype=np.int32), scale=np.ones(2), type=np.array([2, 0], dtype=np.int32),
+               params=np.array([[0.9, 0.2, 1e9, 0, 0, 0, 0], [3.0, 0, 0, 0, 0, 0, 0]]))
+    ref.add_pattern_entries(np.concatenate([lin["g_row"], lin["c_row"]]), np.concatenate([lin["g_col"], lin["c_col"]]))
+    ref.finalize()
+    x0 = np.zeros(ref.n)
+    probes = list(range(ref.n))
+    ref.set_flags(transient=1)
+    want = ref.tran_run(x0, 2.0e-9, 2e-11, probes, lin, src, dcop=1)
+    e = ref.adms_export(0, "vbic13")
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(info["type"], np.array([e["rec"]]), [0], np.array([e["lids"]]), [e["sto0"]], 1, [e["sta0"]], 1)
+    eng.set_linear(lin["g_row"], lin["g_col"], lin["g_val"], lin["c_row"], lin["c_col"], lin["c_val"])
+    eng.set_sources(src["row"], src["scale"], src["type"], src["params"])
+    eng.finalize()
+    got = eng.tran_run(x0, 2.0e-9, 2e-11, probes, dcop=1)
+    eng.close()
+    assert want["rc"] == 0 and got["rc"] == 0, got.get("error")
+    assert got["stats"]["dcop_newton_iters"] == want["stats"]["dcop_newton_iters"] >= 4      # from zero: the limiters walk the junctions up
+    assert got["stats"]["accepted"] == want["stats"]["accepted"] and got["stats"]["rejected"] == want["stats"]["rejected"]
+    assert np.array_equal(got["steps"][:, 2], want["steps"][:, 2])
+    tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
+    assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
+    assert 0.2 < want["wave"][0, Cn] < 2.9 and np.ptp(want["wave"][:, Cn]) > 0.1      # biased in the active region, the collector follows the input
