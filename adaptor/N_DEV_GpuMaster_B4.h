@@ -142,6 +142,7 @@ class GpuMaster : public Master {
     ss.voltageLimiterFlag = o.voltageLimiterFlag;
     ss.gmin = o.gmin; ss.gainScale = s.gainScale_; ss.nltermScale = s.nltermScale_; ss.vgstConst = o.vgstConst; ss.vdsScaleMin = o.vdsScaleMin;
     ss.sizeScale = s.sizeScale_; ss.currTimeStep = s.currTimeStep_;
+    ss.lastTimeStep = s.lastTimeStep_; ss.beginIntegrationFlag = s.beginIntegrationFlag_;
     const ExternData &e = extData_();
     // host-resident DataStore: the time integrator rotates curr / next on the host, so both travel every time
     if (!chk(xgpu_state_set(ctx_, 0, e.nextStoVectorRawPtr)) || !chk(xgpu_state_set(ctx_, 1, e.currStoVectorRawPtr))) return false;

@@ -27,6 +27,8 @@ typedef struct xgpu_solver_state {
   int initJctFlag, initFixFlag, initTranFlag, newtonIter, locaEnabledFlag;
   int artParameterFlag, voltageLimiterFlag;
   double gmin, gainScale, nltermScale, vgstConst, vdsScaleMin, sizeScale, currTimeStep;
+  double lastTimeStep;         /* SolverState::lastTimeStep_ (BJT excess phase, N_DEV_BJT.C:2768-2769) */
+  int beginIntegrationFlag;    /* SolverState::beginIntegrationFlag_: first step out of a break point, t = 0 included */
 } xgpu_solver_state;
 
 /* ---- lifetime ---- */
@@ -116,6 +118,12 @@ int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n_inst, const double *rec
 /* Builds the stamp -> CSR gather maps (replaces Instance::registerJacLIDs/setupPointers,
  * N_DEV_MOSFET_B4.C:6524-6846, and Indexor::matrixGlobalToLocal, N_TOP_Indexor.C:149-214). */
 int xgpu_finalize(xgpu_ctx *ctx);
+/* Store vector of the step before (DataStore::lastStoVectorRawPtr, device pointer) for the following xgpu_update_state
+ * calls.  Only the Gummel-Poon BJT with excess phase (model PTF != 0) reads it: Weil's approximation keeps two history
+ * values of the store entry CEXBC (Instance::oldDAEExcessPhaseCalculation1/2, N_DEV_BJT.C:2706-2799).  Without this
+ * call (or with NULL) the current store stands in.  xgpu_tran_run keeps the history itself. */
+int xgpu_last_store_set(xgpu_ctx *ctx, double *d_last_sto);
+int xgpu_needs_last_store(const xgpu_ctx *ctx);      /* 1 when a group reads the last store (BJT with PTF != 0) */
 
 /* Lead currents (Instance::loadLeadCurrent, set by .PRINT I(M1) / P(M1): Master::loadDAEVectors
  * N_DEV_MOSFET_B4.C:10933-10987; registerBranchDataLIDs :6482-6500).  branch_lid0[i] = li_branch_dev_id of instance i
@@ -323,11 +331,12 @@ int xgpu_newton_step_host(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_
  * Same sums in the same order: bitwise the one-pass result.  info3 = {usable for this circuit, rows in the first window,
  * nonzeros in the first window}. */
 int xgpu_pipe_info(const xgpu_ctx *ctx, long long *info3);
-/* which: 0 next store, 1 curr store, 2 next state, 3 curr state */
+/* which: 0 next store, 1 curr store, 2 next state, 3 curr state, 4 last store (no-op unless xgpu_needs_last_store) */
 int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h_vals);
 int xgpu_state_get(xgpu_ctx *ctx, int which, double *h_vals);
 /* Device pointers of the context-owned buffers used by xgpu_load_host:
- * 0 sol, 1 f, 2 q, 3 dFdxdVp, 4 dQdxdVp, 5 dFdx, 6 dQdx, 7 next sto, 8 curr sto, 9 next sta, 10 curr sta */
+ * 0 sol, 1 f, 2 q, 3 dFdxdVp, 4 dQdxdVp, 5 dFdx, 6 dQdx, 7 next sto, 8 curr sto, 9 next sta, 10 curr sta,
+ * 11 last sto (one element unless a BJT group with excess phase is present) */
 double *xgpu_device_buffer(xgpu_ctx *ctx, int which);
 
 /* Measured FP64 FMA throughput of this GPU (dependent-chain DFMA microbenchmark, TFLOP/s with

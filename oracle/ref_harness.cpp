@@ -190,7 +190,7 @@ struct Ctx {
   DeviceOptions devOptions;
   SolverState solState;
   ExternData extData;
-  RawVector vSol, vCurrSta, vNextSta, vCurrSto, vNextSto, vF, vQ;
+  RawVector vSol, vCurrSta, vNextSta, vCurrSto, vNextSto, vLastSto, vF, vQ;
   MatrixLoadData mlData;
   FactoryBlock *fb = 0;
   // one Master per device type, in creation order (= DeviceMgr::devicePtrVec_ order)
@@ -248,7 +248,7 @@ struct Ctx {
   std::vector<InstRec> insts;
   int nExt = 0, n = 0, nSta = 0, nSto = 0;
   CsrMatrix dFdx, dQdx;
-  std::vector<double> f, q, b, fl, ql, nextSta, currSta, nextSto, currSto, sol;
+  std::vector<double> f, q, b, fl, ql, nextSta, currSta, nextSto, currSto, lastSto, sol;
   bool finalized = false;
   std::vector<std::pair<int, int>> extra_pattern;   // linear-device entries
 };
@@ -397,7 +397,7 @@ int xref_finalize(void *h) {
   c->f.assign(c->n + 1, 0); c->q = c->b = c->fl = c->ql = c->f;
   c->sol.assign(c->n + 1, 0);
   c->nextSta.assign(sta + 1, 0); c->currSta = c->nextSta; c->staDeriv = c->nextSta;
-  c->nextSto.assign(sto + 1, 0); c->currSto = c->nextSto;
+  c->nextSto.assign(sto + 1, 0); c->currSto = c->nextSto; c->lastSto = c->nextSto;
   ExternData &e = c->extData;
   e.dFdxMatrixPtr = &c->dFdx; e.dQdxMatrixPtr = &c->dQdx;
   e.daeFVectorRawPtr = c->f.data(); e.daeQVectorRawPtr = c->q.data(); e.daeBVectorRawPtr = c->b.data();
@@ -405,13 +405,13 @@ int xref_finalize(void *h) {
   e.nextSolVectorRawPtr = e.currSolVectorRawPtr = e.lastSolVectorRawPtr = c->sol.data();
   e.nextStaVectorRawPtr = c->nextSta.data(); e.currStaVectorRawPtr = e.lastStaVectorRawPtr = c->currSta.data();
   e.nextStaDerivVectorRawPtr = c->staDeriv.data();
-  e.nextStoVectorRawPtr = c->nextSto.data(); e.currStoVectorRawPtr = e.lastStoVectorRawPtr = c->currSto.data();
-  c->vSol.v = &c->sol; c->vCurrSta.v = &c->currSta; c->vNextSta.v = &c->nextSta; c->vCurrSto.v = &c->currSto; c->vNextSto.v = &c->nextSto;
+  e.nextStoVectorRawPtr = c->nextSto.data(); e.currStoVectorRawPtr = c->currSto.data(); e.lastStoVectorRawPtr = c->lastSto.data();
+  c->vSol.v = &c->sol; c->vCurrSta.v = &c->currSta; c->vNextSta.v = &c->nextSta; c->vCurrSto.v = &c->currSto; c->vNextSto.v = &c->nextSto; c->vLastSto.v = &c->lastSto;
   e.nextSolVectorPtr = e.currSolVectorPtr = e.lastSolVectorPtr = &c->vSol;
   c->vF.v = &c->f; c->vQ.v = &c->q;
   e.daeFVectorPtr = &c->vF; e.daeQVectorPtr = &c->vQ;      // ADMS-generated devices load through the Linear::Vector objects
   e.currStaVectorPtr = e.lastStaVectorPtr = &c->vCurrSta; e.nextStaVectorPtr = &c->vNextSta;
-  e.currStoVectorPtr = e.lastStoVectorPtr = &c->vCurrSto; e.nextStoVectorPtr = &c->vNextSto;
+  e.currStoVectorPtr = &c->vCurrSto; e.lastStoVectorPtr = &c->vLastSto; e.nextStoVectorPtr = &c->vNextSto;
   for (auto &r : c->insts) r.inst->setupPointers();
   c->finalized = true;
   return c->n;
@@ -472,6 +472,16 @@ void xref_set_flags(void *h, const int *fl, const double *dv) {
   c->devOptions.gmin = dv[0]; s.gainScale_ = dv[1]; s.nltermScale_ = dv[2];
 }
 
+// step history read by the BJT excess phase (SolverState::currTimeStep_ / lastTimeStep_ / beginIntegrationFlag_, last store)
+void xref_set_step(void *h, double currTimeStep, double lastTimeStep, int beginIntegration) {
+  Ctx *c = (Ctx *)h;
+  c->solState.currTimeStep_ = currTimeStep; c->solState.lastTimeStep_ = lastTimeStep; c->solState.beginIntegrationFlag_ = beginIntegration != 0;
+}
+void xref_last_store(void *h, const double *set, double *get) {
+  Ctx *c = (Ctx *)h;
+  if (set) std::copy(set, set + c->nSto, c->lastSto.begin());
+  if (get) std::copy(c->lastSto.begin(), c->lastSto.begin() + c->nSto, get);
+}
 void xref_set_state(void *h, const double *currSto, const double *nextSto, const double *currSta) {
   Ctx *c = (Ctx *)h;
   if (currSto) std::copy(currSto, currSto + c->nSto, c->currSto.begin());
@@ -775,6 +785,7 @@ struct RefBackend {
     SolverState &s = c->solState;
     s.dcopFlag = fl.dcop; s.tranopFlag = fl.tranop; s.transientFlag = fl.transient; s.initTranFlag_ = fl.initTran;
     s.newtonIter = fl.newtonIter; s.initJctFlag_ = fl.initJct; s.initFixFlag = fl.initFix; s.currTimeStep_ = fl.currTimeStep;
+    s.lastTimeStep_ = fl.lastTimeStep; s.beginIntegrationFlag_ = fl.beginIntegration != 0;
     std::copy(v[xb::sim::vNextSol].begin(), v[xb::sim::vNextSol].end(), c->sol.begin());
     c->sol[c->n] = 0.0;
     for (auto *q : {&c->f, &c->q, &c->b, &c->fl, &c->ql}) std::fill(q->begin(), q->end(), 0.0);
@@ -846,7 +857,7 @@ struct RefBackend {
     out.devices_converged = all_devices_converged();
   }
   bool limiter_active() const { return c->devOptions.voltageLimiterFlag; }
-  void accept_state() { c->currSta = c->nextSta; c->currSto = c->nextSto; }
+  void accept_state() { c->currSta = c->nextSta; c->lastSto = c->currSto; c->currSto = c->nextSto; }
   void record(double t) { times.push_back(t); for (int p : probes) wave.push_back(v[xb::sim::vNextSol][p]); }
 };
 }  // namespace

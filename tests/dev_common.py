@@ -63,6 +63,24 @@ class HostDevices:
                     JQ=out[4 * n + s:4 * n + 2 * s], store=out[4 * n + 2 * s:4 * n + 2 * s + nstore],
                     state=out[4 * n + 2 * s + nstore:4 * n + 2 * s + nstore + nstate], orig=int(out[-1]))
 
+    def bjt_xp(self, e, flags, step3, V, curr_sto, next_sto, cex2):
+        """BJT with the step history of the excess phase; returns (outputs like simple(), [mode, next, init])"""
+        nodes, slots, nstore, nstate = 7, 24, 3, 6
+        fl, fd = flag_arrays(flags)
+        out = np.zeros(4 * nodes + 2 * slots + nstore + nstate + 1)
+        cex_out = np.zeros(3)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (e["rec"], step3, V, curr_sto, next_sto, cex2)]
+        self.lib.xbh_bjt_eval_xp.restype = C.c_int
+        k = self.lib.xbh_bjt_eval_xp(dp(keep[0]), int(e["flags"]), fl.ctypes.data_as(C.POINTER(C.c_int)), dp(fd), dp(keep[1]),
+                                     dp(keep[2]), dp(keep[3]), dp(keep[4]), dp(keep[5]), dp(out), dp(cex_out))
+        assert k == len(out)
+        n, s = nodes, slots
+        o = dict(F=out[0:n], Q=out[n:2 * n], FL=out[2 * n:3 * n], QL=out[3 * n:4 * n], JF=out[4 * n:4 * n + s],
+                 JQ=out[4 * n + s:4 * n + 2 * s], store=out[4 * n + 2 * s:4 * n + 2 * s + nstore],
+                 state=out[4 * n + 2 * s + nstore:4 * n + 2 * s + nstore + nstate], orig=int(out[-1]))
+        return o, cex_out
+
 
 MOS1_SLOT_ROW = [0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5]
 MOS1_SLOT_COL = [0, 4, 1, 3, 4, 5, 2, 5, 1, 3, 4, 5, 0, 1, 3, 4, 5, 1, 2, 3, 4, 5]
@@ -96,6 +114,13 @@ BJT_CARDS = {
     "hicur": ("NPN", dict(IS=5e-16, BF=200.0, IKF=1e-2, NK=0.6, RB=100.0, RE=1.0, CJE=8e-13, CJC=4e-13, TF=1e-10, XTF=1.0, ITF=0.02)),
 }
 
+# excess phase: PTF degrees at f = 1 / (2 pi TF) -> Weil's approximation on the step history (N_DEV_BJT.C:2706-2799);
+# kept out of BJT_CARDS: it needs the step sizes set (0 / 0 otherwise, in the reference too)
+BJT_PTF_CARDS = {
+    "ptf": ("NPN", dict(IS=1e-15, BF=150.0, BR=2.0, VAF=70.0, IKF=2e-2, RB=40.0, RC=5.0, CJE=1e-12, CJC=5e-13, TF=2e-10, TR=5e-9,
+                        PTF=35.0)),
+}
+
 
 def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0):
     """n_dev isolated devices, every terminal on its own node"""
@@ -115,7 +140,7 @@ def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0):
         for i in range(n_dev):
             c.add_dev_instance("mvs", "M:%d" % i, "vsmod", [nt * i, nt * i + 1, nt * i + 2], {})
     else:
-        mtype, p = BJT_CARDS[card]
+        mtype, p = {**BJT_CARDS, **BJT_PTF_CARDS}[card]
         c.add_dev_model("q", "qmod", mtype, 1, p)
         for i in range(n_dev):
             c.add_dev_instance("q", "Q:%d" % i, "qmod", [nt * i, nt * i + 1, nt * i + 2, nt * i + 3], dict(AREA=float(rng.choice([1.0, 3.0]))))

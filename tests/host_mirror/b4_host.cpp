@@ -164,6 +164,35 @@ int xbh_diode_eval(const double *rec, int flags, const int *fl, const double *fd
   return k;
 }
 
+// BJT with excess phase (model PTF != 0): step3 = {currTimeStep, lastTimeStep, beginIntegrationFlag}, cex2 = {current, last}
+// store entry CEXBC; out as xbh_simple_eval, cex_out = {mode bits, next, initial history value}
+int xbh_bjt_eval_xp(const double *rec, int flags, const int *fl, const double *fd, const double *step3, const double *Vn,
+                    const double *curr_sto, const double *next_sto, const double *cex2, double *out, double *cex_out) {
+  SolverFlags S; fill_flags(S, fl, fd);
+  S.currTimeStep = step3[0]; S.lastTimeStep = step3[1]; S.beginIntegrationFlag = (int)step3[2];
+  namespace D = xb::bjt;
+  D::Rec R; int j = 0, k = 0;
+#define GET(n) R.n = rec[j++];
+  XB_BJT_FIELDS(GET, GET)
+#undef GET
+  real V[D::kNodes], cs[3], ns[3];
+  for (int i = 0; i < D::kNodes; ++i) V[i] = Vn[i];
+  for (int i = 0; i < 3; ++i) { cs[i] = curr_sto[i]; ns[i] = next_sto[i]; }
+  D::Out o;
+  D::evaluate(S, R, flags, V, cs, ns, o, real(cex2[0]), real(cex2[1]));
+  for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.F[i]);
+  for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.Q[i]);
+  for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.FL[i]);
+  for (int i = 0; i < D::kNodes; ++i) out[k++] = to_double(o.QL[i]);
+  for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JF[i]);
+  for (int i = 0; i < D::kSlots; ++i) out[k++] = to_double(o.JQ[i]);
+  for (int i = 0; i < 3; ++i) out[k++] = to_double(o.store[i]);
+  for (int i = 0; i < D::kNumState; ++i) out[k++] = to_double(o.state[i]);
+  out[k++] = o.origFlag;
+  cex_out[0] = o.cexbc_mode; cex_out[1] = to_double(o.cexbc_next); cex_out[2] = to_double(o.cexbc_init);
+  return k;
+}
+
 // MOSFET level 1 (type 2) / BJT (type 3):
 // out = F[n] Q[n] FL[n] QL[n] JF[s] JQ[s] store[..] state[..] origFlag; returns the number of doubles written
 int xbh_simple_eval(int type, const double *rec, int flags, const int *fl, const double *fd, const double *Vn,

@@ -147,6 +147,17 @@ class RefCircuit:
         a, b, c = cv(curr_sto), cv(next_sto), cv(curr_sta)
         self.lib.xref_set_state(self.h, dptr(a), dptr(b), dptr(c))
 
+    def set_step(self, curr_dt, last_dt, begin_integration):
+        self.lib.xref_set_step.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
+        self.lib.xref_set_step(self.h, curr_dt, last_dt, int(begin_integration))
+
+    def last_store(self, vals=None):
+        out = np.zeros(self.n_sto)
+        v = None if vals is None else np.ascontiguousarray(vals, dtype=np.float64)
+        self.lib.xref_last_store.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.xref_last_store(self.h, None if v is None else v.ctypes.data, out.ctypes.data)
+        return out
+
     def get_state(self):
         cs, ns = np.zeros(self.n_sto), np.zeros(self.n_sto)
         ca, na = np.zeros(self.n_sta), np.zeros(self.n_sta)

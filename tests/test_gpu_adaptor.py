@@ -101,6 +101,33 @@ def test_simple_gpu_masters_equal_the_stock_masters_through_the_device_virtuals(
     _compare_through_virtuals(stock, gpu, x, CASES[case])
 
 
+@pytest.mark.parametrize("begin", [1, 0])
+def test_bjt_gpu_master_with_excess_phase(begin):
+    """PTF != 0 behind GpuSimpleMaster<BJT::Master, ...>: the adaptor hands the last store vector over and, on the first step
+    out of a break point, brings the seeded history (current and last store entry CEXBC) back -- N_DEV_BJT.C:2706-2799."""
+    from dev_common import simple_circuit
+    stock = simple_circuit(oracle_ref.RefCircuit, "bjt", "ptf", n_dev=30, seed=4)
+    gpu = simple_circuit(GpuRefAll, "bjt", "ptf", n_dev=30, seed=4)
+    gpu.gpu_attach(0)
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-0.2, 0.9, stock.n)
+    nsto, csto, lsto = (rng.normal(0.2, 0.4, stock.n_sto) for _ in range(3))
+    csto[3::4] = rng.uniform(1e-4, 2e-3, len(csto[3::4])); lsto[3::4] = csto[3::4] * rng.uniform(0.7, 1.2, len(csto[3::4]))
+    csta = rng.normal(0.0, 1e-14, stock.n_sta)
+    for c in (stock, gpu):
+        c.set_flags(**CASES["tran1"]); c.set_step(3e-11, 2e-11, begin)
+        c.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta); c.last_store(lsto)
+    want, got = stock.load(x), gpu.load(x)
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, k
+    ws, gs = stock.get_state(), gpu.get_state()
+    for k in ("next_sto", "curr_sto"):
+        assert rel_err(gs[k], ws[k], 1e-30) < 1e-12, k
+    assert rel_err(gpu.last_store(), stock.last_store(), 1e-30) < 1e-12
+    assert np.array_equal(ws["curr_sto"][3::4], csto[3::4]) == (not begin)
+
+
 @pytest.mark.parametrize("case", ["tran1", "dcop_jct"])
 def test_diode_gpu_master(case):
     from dev_common import DIODE_CARDS, diode_circuit

@@ -6,7 +6,7 @@ import pytest
 import oracle_ref
 import xyce_b200
 from b4_common import rel_err, solver_state
-from dev_common import BJT_CARDS, DIODE_CARDS, MOS1_CARDS, MVS_CARDS, SIMPLE, diode_circuit, simple_circuit
+from dev_common import BJT_CARDS, BJT_PTF_CARDS, DIODE_CARDS, MOS1_CARDS, MVS_CARDS, SIMPLE, diode_circuit, simple_circuit
 
 pytestmark = pytest.mark.gpu
 
@@ -100,6 +100,103 @@ def test_adms_mvs(card, case):
         assert rel_err(got[k], want[k], scale) < 1e-12, k
     assert np.any(want["dFdx"] != 0.0) and not np.any(want["q"]) and eng.all_converged()
     eng.close()
+
+
+@pytest.mark.parametrize("begin", [1, 0])
+@pytest.mark.parametrize("case", ["tran1", "nolimit", "dcop_init"])
+def test_bjt_excess_phase(case, begin):
+    """Model PTF != 0 (Weil's approximation, Instance::oldDAEExcessPhaseCalculation1 / 2, N_DEV_BJT.C:2706-2799): the
+    collector current follows iBE / qB through the history in the store entry CEXBC of the current and the LAST store;
+    the first step out of a break point seeds both.  Loads and all three store vectors against the reference objects."""
+    type_id, key, nodes, nstore, nstate, srow, scol = SIMPLE["bjt"]
+    ref = simple_circuit(oracle_ref.RefCircuit, "bjt", "ptf", n_dev=150, seed=5)
+    ex = [ref.dev_export(i, key) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(type_id, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e["sta0"] for e in ex], 1)
+    eng.finalize()
+    assert eng.lib.xgpu_needs_last_store(eng.h) == 1
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-0.2, 0.9, ref.n)
+    flags = CASES[case]
+    dt0, dt1 = 3e-11, 2e-11
+    nsto, csto, lsto = (rng.normal(0.2, 0.5, ref.n_sto) for _ in range(3))
+    csto[3::4] = rng.uniform(1e-4, 2e-3, len(csto[3::4])); lsto[3::4] = csto[3::4] * rng.uniform(0.7, 1.2, len(csto[3::4]))
+    csta = rng.normal(0.0, 1e-14, ref.n_sta)
+    ref.set_flags(**flags); ref.set_step(dt0, dt1, begin)
+    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta); ref.last_store(lsto)
+    eng.set_state(0, nsto); eng.set_state(1, csto); eng.set_state(4, lsto); eng.set_state(3, csta)
+    want = ref.load(x)
+    got = eng.load_host(x, solver_state(currTimeStep=dt0, lastTimeStep=dt1, beginIntegrationFlag=begin, **flags))
+    for k in ("f", "q", "dFdxdVp", "dQdxdVp", "dFdx", "dQdx"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, k
+    st = ref.get_state()
+    assert rel_err(eng.get_state(0), st["next_sto"], 1e-30) < 1e-12
+    assert rel_err(eng.get_state(1), st["curr_sto"], 1e-30) < 1e-12
+    assert rel_err(eng.get_state(4), ref.last_store(), 1e-30) < 1e-12
+    if not flags.get("dcop"):
+        assert np.any(st["next_sto"][3::4] != nsto[3::4])
+        assert np.array_equal(st["curr_sto"][3::4], csto[3::4]) == (not begin)
+    eng.close()
+
+
+def test_bjt_excess_phase_tran_matches_reference_flow():
+    """Common-emitter stage (PULSE base drive through a resistor, resistor load) with PTF = 40 degrees: .TRAN on the GPU
+    against the same driver around the reference's BJT objects -- same step sequence, waveforms within RELTOL / ABSTOL;
+    the break points of the pulse restart the history (beginIntegrationFlag), the step rotation keeps the last store.
+    The same circuit with PTF = 0 gives a visibly different collector waveform."""
+    IN, B, C_, VCC, BR_IN, BR_CC = range(6)
+    def build(ptf):
+        ref = oracle_ref.RefCircuit(6)
+        mt, mp = BJT_PTF_CARDS["ptf"]
+        ref.add_dev_model("q", "qmod", mt, 1, dict(mp, PTF=ptf, TF=4e-10))
+        ref.add_dev_instance("q", "Q:1", "qmod", [C_, B, -1, -1], dict(AREA=1.0))
+        g = []
+        def res(a, b, r):
+            for (i, j, v) in ((a, a, 1 / r), (a, b, -1 / r), (b, a, -1 / r), (b, b, 1 / r)):
+                if i >= 0 and j >= 0: g.append((i, j, v))
+        for node, br in ((IN, BR_IN), (VCC, BR_CC)):
+            g.append((node, br, 1.0)); g.append((br, node, 1.0))
+        res(IN, B, 200.0); res(VCC, C_, 1e3)
+        c = [(C_, C_, 2e-14)]
+        lin = dict(g_row=np.array([t[0] for t in g], dtype=np.int32), g_col=np.array([t[1] for t in g], dtype=np.int32),
+                   g_val=np.array([t[2] for t in g]), c_row=np.array([t[0] for t in c], dtype=np.int32),
+                   c_col=np.array([t[1] for t in c], dtype=np.int32), c_val=np.array([t[2] for t in c]))
+        src = dict(row=np.array([BR_IN, BR_CC], dtype=np.int32), scale=np.ones(2), type=np.array([1, 0], dtype=np.int32),
+                   params=np.array([[0.6, 1.1, 2e-10, 5e-11, 5e-11, 1.2e-9, 6e-9], [3.0, 0, 0, 0, 0, 0, 0]]))
+        ref.add_pattern_entries(np.concatenate([lin["g_row"], lin["c_row"]]), np.concatenate([lin["g_col"], lin["c_col"]]))
+        ref.finalize()
+        return ref, lin, src
+    ref, lin, src = build(40.0)
+    x0 = np.zeros(ref.n); x0[VCC] = 3.0; x0[C_] = 3.0; x0[IN] = 0.6; x0[B] = 0.6
+    probes = list(range(ref.n))
+    ref.set_flags(transient=1)
+    want = ref.tran_run(x0, 3e-9, 1e-11, probes, lin, src, dcop=1)
+    e = ref.dev_export(0, "q")
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(3, np.array([e["rec"]]), [e["flags"]], np.array([e["lids"]]), [e["sto0"]], 1, [e["sta0"]], 1)
+    eng.set_linear(lin["g_row"], lin["g_col"], lin["g_val"], lin["c_row"], lin["c_col"], lin["c_val"])
+    eng.set_sources(src["row"], src["scale"], src["type"], src["params"])
+    eng.finalize()
+    got = eng.tran_run(x0, 3e-9, 1e-11, probes, dcop=1)
+    eng.close()
+    assert want["rc"] == 0 and got["rc"] == 0, got.get("error")
+    assert got["stats"]["accepted"] == want["stats"]["accepted"] > 20 and got["stats"]["rejected"] == want["stats"]["rejected"]
+    assert np.array_equal(got["steps"][:, 2], want["steps"][:, 2])
+    tol = 1e-3 * np.maximum(np.abs(want["wave"]), np.abs(got["wave"])) + 1e-6
+    assert np.all(np.abs(got["wave"] - want["wave"]) <= tol)
+    assert np.ptp(want["wave"][:, C_]) > 0.5          # the stage switches
+    ref0, lin0, src0 = build(0.0)
+    ref0.set_flags(transient=1)
+    base = ref0.tran_run(x0, 3e-9, 1e-11, probes, lin0, src0, dcop=1)
+    tt = np.linspace(2.2e-10, 2.8e-9, 400)
+    d = np.interp(tt, want["t"], want["wave"][:, C_]) - np.interp(tt, base["t"], base["wave"][:, C_])
+    assert np.max(np.abs(d)) > 0.1                   # the excess phase delays the collector response
 
 
 def test_adms_mvs_amplifier_dcop_and_tran_match_reference_flow():

@@ -62,3 +62,54 @@ def test_adms_mvs(card, case):
     """ADMS-generated model (MVS 2.0.0 ETSOI, N_DEV_ADMSmvs_2_0_0_etsoi.C): 3 internal nodes + a branch equation; the
     reference object runs through the generic per-instance DeviceMaster loops (Core/N_DEV_DeviceMaster.h:666-823)"""
     run("mvs", card, case)
+
+
+@pytest.mark.parametrize("begin", [1, 0])
+@pytest.mark.parametrize("case", ["tran1", "nolimit", "dcop2"])
+def test_bjt_excess_phase(case, begin):
+    """Model PTF != 0: Weil's approximation of the excess phase (Instance::oldDAEExcessPhaseCalculation1 / 2,
+    N_DEV_BJT.C:2706-2799).  In transient the collector current follows iBE / qB through the step history kept in the
+    store entry CEXBC (current and last store); the first step out of a break point seeds both history values.  DC
+    operating point: no effect."""
+    type_id, key, nodes, nstore, nstate, srow, scol = SIMPLE["bjt"]
+    hd = HostDevices()
+    ref = simple_circuit(oracle_ref.RefCircuit, "bjt", "ptf", seed=5)
+    rng = np.random.default_rng(11)
+    flags = CASES[case]
+    ref.set_flags(**flags)
+    dt0, dt1 = 3e-11, 2e-11
+    ref.set_step(dt0, dt1, begin)
+    x = rng.uniform(-0.2, 0.9, ref.n)
+    nsto, csto, lsto = (rng.normal(0.2, 0.5, ref.n_sto) for _ in range(3))
+    csto[3::4] = rng.uniform(1e-4, 2e-3, len(csto[3::4])); lsto[3::4] = csto[3::4] * rng.uniform(0.7, 1.2, len(csto[3::4]))
+    ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=rng.normal(0.0, 1e-14, ref.n_sta))
+    ref.last_store(lsto)
+    want = ref.load(x)
+    st = ref.get_state(); last_after = ref.last_store()
+    per, lids = [], []
+    for i in range(ref.n_inst):
+        e = ref.dev_export(i, key)
+        assert e["rec"][25] != 0.0          # excessPhaseFac = PTF (rad) * TF
+        s0 = e["sto0"]
+        V = [x[g] if g >= 0 else 0.0 for g in e["lids"]]
+        o, cex = hd.bjt_xp(e, flags, [dt0, dt1, begin], V, csto[s0:s0 + 3], nsto[s0:s0 + 3],
+                           [0.0, 0.0] if begin else [csto[s0 + 3], lsto[s0 + 3]])
+        per.append(o); lids.append(e["lids"])
+        assert rel_err(o["store"], st["next_sto"][s0:s0 + 3], 1e-25) < 1e-12
+        tran = not flags.get("dcop")
+        assert int(cex[0]) == ((1 if tran else 0) | (2 if tran and begin else 0))
+        if tran:
+            assert abs(cex[1] - st["next_sto"][s0 + 3]) <= 1e-12 * abs(cex[1]), (i, "next CEXBC")
+            if begin:
+                assert abs(cex[2] - st["curr_sto"][s0 + 3]) <= 1e-12 * abs(cex[2]) and st["curr_sto"][s0 + 3] == last_after[s0 + 3]
+            else:
+                assert st["curr_sto"][s0 + 3] == csto[s0 + 3] and last_after[s0 + 3] == lsto[s0 + 3]
+        else:
+            assert st["next_sto"][s0 + 3] == nsto[s0 + 3]
+    asm = assemble(per, lids, srow, scol, ref.n, ref.rowptr, ref.colind)
+    for k in want:
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(asm[k], want[k], scale) < 1e-12, (case, begin, k)
+    if not flags.get("dcop"):      # the history really enters: the same point without it gives another collector current
+        ref.set_step(dt0, dt1, 1)
+        assert np.max(np.abs(ref.load(x)["f"] - want["f"])) > 1e-6 or begin

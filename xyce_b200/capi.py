@@ -9,7 +9,7 @@ _lib = None
 
 FLAG_FIELDS = ["dcopFlag", "tranopFlag", "acopFlag", "transientFlag", "dcsweepFlag", "initJctFlag", "initFixFlag",
                "initTranFlag", "newtonIter", "locaEnabledFlag", "artParameterFlag", "voltageLimiterFlag"]
-REAL_FIELDS = ["gmin", "gainScale", "nltermScale", "vgstConst", "vdsScaleMin", "sizeScale", "currTimeStep"]
+REAL_FIELDS = ["gmin", "gainScale", "nltermScale", "vgstConst", "vdsScaleMin", "sizeScale", "currTimeStep", "lastTimeStep"]
 
 
 class TranParams(C.Structure):
@@ -22,7 +22,7 @@ class TranParams(C.Structure):
 
 class SolverState(C.Structure):
     """Mirror of xgpu_solver_state (Device::SolverState + DeviceOptions subset)."""
-    _fields_ = [(n, C.c_int) for n in FLAG_FIELDS] + [(n, C.c_double) for n in REAL_FIELDS]
+    _fields_ = [(n, C.c_int) for n in FLAG_FIELDS] + [(n, C.c_double) for n in REAL_FIELDS] + [("beginIntegrationFlag", C.c_int)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -224,7 +224,7 @@ class Engine:
         self._chk(self.lib.xgpu_state_set(self.h, which, _dp(vals)))
 
     def get_state(self, which):
-        out = np.zeros(self.n_store if which < 2 else self.n_state)
+        out = np.zeros(self.n_store if which < 2 or which == 4 else self.n_state)      # 4 = last store
         self._chk(self.lib.xgpu_state_get(self.h, which, _dp(out)))
         return out
 

@@ -29,12 +29,25 @@ struct LazyRec {
   } f;
 };
 
+constexpr int kAdmsPrefetchMaxFields = 232;
+
 template <class T>
 __global__ void __launch_bounds__(128) adms_gen_kernel(GroupDev g, b4::LoadArgs a) {
   xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n) return;
   const int n = g.n;
+  if (T::kNumFields <= kAdmsPrefetchMaxFields) {
+    // the warp asks L2 for its 256 B of every record field up front: the lazy loads below then wait for an L2 hit, not a
+    // DRAM miss.  Measured (200 000 instances, profiles/r02_simple_kernels_timing_v3.json): JUNCAP200 -17 %, EKV -10 %,
+    // HICUM/L0 -7 %, VBIC -3 %; records of which one evaluation reads a small part (PSP 103, BSIM-CMG: +6..11 %) are
+    // left alone.
+    const int lane = threadIdx.x & 31, i0 = i - lane;
+    for (int k = lane; k < 2 * T::kNumFields; k += 32) {
+      const int ii = i0 + (k & 1) * 16;
+      if (ii < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.rec + (size_t)(k >> 1) * n + ii));
+    }
+  }
+  if (i >= n) return;
   const LazyRec R{{g.rec + i, (size_t)n}};
   real V[T::kNodes];
 #pragma unroll

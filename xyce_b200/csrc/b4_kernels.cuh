@@ -52,6 +52,7 @@ struct LoadArgs {
   SolverFlags S;
   const double *sol;        // next solution (length >= n_unknowns)
   double *next_sto, *curr_sto;
+  double *last_sto;         // store vector of the step before (BJT excess phase only; = curr_sto when the caller keeps no history)
   double *next_sta, *curr_sta;
   double *vec_planes[4];    // F, Q, dFdxdVp, dQdxdVp contribution planes
   double *mat_planes[2];    // dFdx, dQdx contribution planes

@@ -1,11 +1,12 @@
 // xyce_b200 -- Gummel-Poon BJT: one instance evaluation =
 //   Instance::updateIntermediateVars + auxDAECalculations   (src/DeviceModelPKG/OpenModels/N_DEV_BJT.C:2810-3434, :2139-2198)
 //   Master::updateState / loadDAEVectors / loadDAEMatrices   (N_DEV_BJT.C:4112-4160, :4199-4398, :4400-4520)
-// restated for a one-thread-per-instance SoA kernel.  Scope: excess phase off (model PTF = 0, the default;
-// with PTF != 0 the reference adds history terms / extra unknowns -- rejected by the C ABI) and
-// DeviceOptions::newExcessPhase = false (the build default, N_DEV_DeviceOptions.C:55-59).
+//   Instance::oldDAEExcessPhaseCalculation1 / 2              (N_DEV_BJT.C:2706-2799: Weil's approximation of the excess
+//                                                             phase, model PTF != 0, history in the store entry CEXBC)
+// restated for a one-thread-per-instance SoA kernel.  Scope: DeviceOptions::newExcessPhase = false (the build
+// default, N_DEV_DeviceOptions.C:55-59; the other formulation adds two unknowns per instance).
 // Nodes: 0 Coll, 1 Base, 2 Emit, 3 Subst, 4 Coll' , 5 Base', 6 Emit' (primed nodes alias the external ones
-// when RC / RB / RE = 0).  Store: vBE vBC capeqCB (cexbc unused).  State: qBEdiff qBEdep qCS qBCdiff qBCdep qBX.
+// when RC / RB / RE = 0).  Store: vBE vBC capeqCB cexbc.  State: qBEdiff qBEdep qCS qBCdiff qBCdep qBX.
 #pragma once
 #include "xb_common.h"
 #include "simple_fields.def"
@@ -41,6 +42,10 @@ struct Out {
   real F[kNodes], Q[kNodes], FL[kNodes], QL[kNodes], JF[kSlots], JQ[kSlots];
   real store[3], state[kNumState];
   int origFlag;
+  // excess phase: bit 0 = cexbc_next goes to the next store, bit 1 = cexbc_init goes to the current AND the last store
+  // (no history yet: first step out of a break point, N_DEV_BJT.C:2716-2721)
+  int cexbc_mode;
+  real cexbc_next, cexbc_init;
 };
 
 // depletion charge / capacitance of one junction (the four copies at N_DEV_BJT.C:3223-3330)
@@ -78,7 +83,7 @@ XB_HD void junction(real v, real csat, real vte, real ileak, real vtleak, real g
 }
 
 XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V, const real *curr_sto,
-                    const real *next_sto, Out &o) {
+                    const real *next_sto, Out &o, real cexbc_curr = 0.0, real cexbc_last = 0.0) {
   const real ty = M.TYPE;
   const real AREA = M.AREA, vt = M.vt;
   const real vEEp = V[kE] - V[kEP], vBBp = V[kB] - V[kBP], vCCp = V[kC] - V[kCP];
@@ -212,14 +217,35 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
     capCS = czCS * (1.0 + M.expSubst * vCS / M.potSubst);
   }
 
-  // terminal currents (excess phase off: iEX = iBE, gEX = gBE)
-  const real iCE = (iBE - iBC) / qB;
-  const real iC = iCE - iBC / M.tBetaR - iBCleak;
+  // terminal currents; excess phase (oldDAEExcessPhaseCalculation1 / 2): in transient with td != 0 the collector current
+  // follows iBE / qB through a second-order Bessel response integrated with backward Euler on the step history
+  real iEX = iBE, gEX = gBE, iC_local = 0.0;
+  o.cexbc_mode = 0; o.cexbc_next = o.cexbc_init = 0.0;
+  const real td = M.excessPhaseFac;
+  if (!S.dcopFlag && td != 0.0) {
+    const real dt0 = S.currTimeStep, dt1 = S.lastTimeStep;
+    real arg1 = dt0 / td;
+    const real arg2 = 3.0 * arg1;
+    arg1 = arg2 * arg1;
+    const real denom = 1.0 + arg1 + arg2;
+    const real phaseScalar = arg1 / denom;
+    real currCexbc = cexbc_curr, lastCexbc = cexbc_last;
+    if (S.beginIntegrationFlag) {
+      currCexbc = lastCexbc = iBE / qB;
+      o.cexbc_init = currCexbc; o.cexbc_mode |= 2;
+    }
+    iC_local = ((currCexbc) * (1 + dt0 / dt1 + arg2) - (lastCexbc) * dt0 / dt1) / denom;
+    iEX = iBE * phaseScalar;
+    gEX = gBE * phaseScalar;
+    o.cexbc_next = iC_local + iEX / qB; o.cexbc_mode |= 1;
+  }
+  const real iCE = (iEX - iBC) / qB;
+  const real iC = iC_local + (iCE - iBC / M.tBetaR - iBCleak);
   const real iB = iBE / M.tBetaF + iBEleak + iBC / M.tBetaR + iBCleak;
   const real iE = -iC - iB;
-  const real diCEdvEp = invqB * (iCE * dqBdvEp - gBE);
+  const real diCEdvEp = invqB * (iCE * dqBdvEp - gEX);
   const real diCEdvCp = invqB * (iCE * dqBdvCp + gBC);
-  const real diCEdvBp = invqB * (iCE * dqBdvBp + gBE - gBC);
+  const real diCEdvBp = invqB * (iCE * dqBdvBp + gEX - gBC);
   const real gEpr = M.emitterConduct * AREA, gCpr = M.collectorConduct * AREA;
   const real rBpr = M.minBaseResist / AREA;
   const real rBpi = M.baseResist / AREA - rBpr;

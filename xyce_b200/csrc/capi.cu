@@ -426,8 +426,20 @@ int xgpu_simple_group_add(xgpu_ctx *ctx, int type, int n, const double *rec, con
   xb::simple::GroupDev &d = g.dev;
   d.type = type; d.n = n; d.rec = g.d_rec; d.flags = g.d_flags; d.lids = g.d_lids; d.sto_lid0 = g.d_sto0; d.sta_lid0 = g.d_sta0;
   d.sto_stride = sto_stride; d.sta_stride = sta_stride; d.orig_flag = g.d_orig;
+  if (type == xb::simple::kBjt) {      // excess phase (model PTF != 0): the evaluation reads the store vector of the step before
+    const size_t k = (size_t)xb::simple::bjt_excess_phase_field();
+    for (int i = 0; i < n; ++i) if (rec[(size_t)i * g.nfields + k] != 0.0) { ctx->needs_last_sto = true; break; }
+  }
   ctx->sgroups.push_back(std::move(g));
   return (int)ctx->sgroups.size() - 1;
+}
+
+int xgpu_needs_last_store(const xgpu_ctx *ctx) { return ctx && ctx->needs_last_sto ? 1 : 0; }
+
+int xgpu_last_store_set(xgpu_ctx *ctx, double *d_last_sto) {
+  if (!ctx) return 1;
+  ctx->d_last_sto = d_last_sto;
+  return 0;
 }
 
 int xgpu_simple_store_count(int type) {
@@ -553,12 +565,14 @@ int xgpu_finalize(xgpu_ctx *ctx) {
   XG_CUDA(cudaMemset(ctx->d_mat_planes, 0, std::max<int64_t>(2 * mb, 1) * sizeof(double)));
   XG_CUDA(cudaMalloc((void **)&ctx->d_conv, sizeof(int)));
   // context-owned system buffers
-  const size_t sizes[11] = {(size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)ctx->nnz, (size_t)ctx->nnz,
-                            (size_t)ctx->n_store, (size_t)ctx->n_store, (size_t)ctx->n_state, (size_t)ctx->n_state};
-  for (int b = 0; b < 11; ++b) {
+  const size_t sizes[12] = {(size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)n, (size_t)ctx->nnz, (size_t)ctx->nnz,
+                            (size_t)ctx->n_store, (size_t)ctx->n_store, (size_t)ctx->n_state, (size_t)ctx->n_state,
+                            ctx->needs_last_sto ? (size_t)ctx->n_store : 0};
+  for (int b = 0; b < 12; ++b) {
     XG_CUDA(cudaMalloc((void **)&ctx->buf[b], std::max<size_t>(sizes[b], 1) * sizeof(double)));
     XG_CUDA(cudaMemset(ctx->buf[b], 0, std::max<size_t>(sizes[b], 1) * sizeof(double)));
   }
+  if (ctx->needs_last_sto && !ctx->d_last_sto) ctx->d_last_sto = ctx->buf[11];
   { const int rc = xg_finalize_linear(ctx); if (rc) return rc; }
   ctx->finalized = true;
   return 0;
@@ -646,8 +660,10 @@ int xgpu_update_state(xgpu_ctx *ctx, const double *d_sol, double *d_next_sta, do
   S.locaEnabledFlag = ss->locaEnabledFlag; S.artParameterFlag = ss->artParameterFlag;
   S.voltageLimiterFlag = ss->voltageLimiterFlag; S.gmin = ss->gmin; S.gainScale = ss->gainScale;
   S.nltermScale = ss->nltermScale; S.vgstConst = ss->vgstConst; S.vdsScaleMin = ss->vdsScaleMin;
-  S.sizeScale = ss->sizeScale; S.currTimeStep = ss->currTimeStep;
+  S.sizeScale = ss->sizeScale; S.currTimeStep = ss->currTimeStep; S.lastTimeStep = ss->lastTimeStep;
+  S.beginIntegrationFlag = ss->beginIntegrationFlag;
   a.sol = d_sol; a.next_sta = d_next_sta; a.curr_sta = d_curr_sta; a.next_sto = d_next_sto; a.curr_sto = d_curr_sto;
+  a.last_sto = ctx->d_last_sto ? ctx->d_last_sto : d_curr_sto;
   for (int p = 0; p < 4; ++p) a.vec_planes[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
   for (int p = 0; p < 2; ++p) a.mat_planes[p] = ctx->d_mat_planes + (int64_t)p * ctx->mat_plane;
   for (auto &g : ctx->groups) {
@@ -775,22 +791,24 @@ int xgpu_all_converged(xgpu_ctx *ctx, int *converged) {
 }
 
 int xgpu_state_set(xgpu_ctx *ctx, int which, const double *h) {
-  if (!ctx || which < 0 || which > 3 || !h || !ctx->finalized) return 1;
-  const size_t cnt = which < 2 ? ctx->n_store : ctx->n_state;
+  if (!ctx || which < 0 || which > 4 || !h || !ctx->finalized) return 1;
+  const size_t cnt = which == 4 ? (ctx->needs_last_sto ? ctx->n_store : 0) : which < 2 ? ctx->n_store : ctx->n_state;
+  if (cnt == 0) return 0;
   XG_CUDA(cudaMemcpyAsync(ctx->buf[7 + which], h, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int xgpu_state_get(xgpu_ctx *ctx, int which, double *h) {
-  if (!ctx || which < 0 || which > 3 || !h || !ctx->finalized) return 1;
-  const size_t cnt = which < 2 ? ctx->n_store : ctx->n_state;
+  if (!ctx || which < 0 || which > 4 || !h || !ctx->finalized) return 1;
+  const size_t cnt = which == 4 ? (ctx->needs_last_sto ? ctx->n_store : 0) : which < 2 ? ctx->n_store : ctx->n_state;
+  if (cnt == 0) return 0;
   XG_CUDA(cudaMemcpyAsync(h, ctx->buf[7 + which], cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   XG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
 double *xgpu_device_buffer(xgpu_ctx *ctx, int which) {
-  if (!ctx || which < 0 || which > 10 || !ctx->finalized) return nullptr;
+  if (!ctx || which < 0 || which > 11 || !ctx->finalized) return nullptr;
   return ctx->buf[which];
 }
 

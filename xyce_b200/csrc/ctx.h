@@ -118,7 +118,9 @@ struct xgpu_ctx {
   int *d_conv = nullptr;
 
   // context-owned system buffers (host-convenience path)
-  double *buf[11] = {nullptr};
+  double *buf[12] = {nullptr};        // xgpu_device_buffer order; 11 = last store
+  double *d_last_sto = nullptr;       // xgpu_last_store_set / the transient driver: store vector of the step before
+  bool needs_last_sto = false;        // a BJT group with excess phase (PTF != 0) is present
 
   // linear devices and independent sources
   XgLinearPart linG, linC;

@@ -65,7 +65,7 @@ struct GpuBackend {
   int n_;
   std::vector<double *> v;          // kNumVec device vectors
   double *dFdx = nullptr, *dQdx = nullptr, *J = nullptr, *scratch = nullptr;
-  double *sta[2] = {nullptr, nullptr}, *sto[2] = {nullptr, nullptr};
+  double *sta[2] = {nullptr, nullptr}, *sto[3] = {nullptr, nullptr, nullptr};      // sto: next, current, last
   int *d_src_rows = nullptr; double *d_src_vals = nullptr;
   int *d_probe = nullptr; double *d_probe_out = nullptr;
   std::vector<int> probes;
@@ -111,6 +111,7 @@ struct GpuBackend {
   bool load_rhs(const sim::Flags &fl, double time) {
     ss.dcopFlag = fl.dcop; ss.tranopFlag = fl.tranop; ss.transientFlag = fl.transient; ss.initTranFlag = fl.initTran;
     ss.newtonIter = fl.newtonIter; ss.initJctFlag = fl.initJct; ss.initFixFlag = fl.initFix; ss.currTimeStep = fl.currTimeStep;
+    ss.lastTimeStep = fl.lastTimeStep; ss.beginIntegrationFlag = fl.beginIntegration;
     int rc = xgpu_update_state(ctx, v[sim::vNextSol], sta[0], sta[1], sto[0], sto[1], &ss);
     rc |= xgpu_load_vectors(ctx, v[sim::vF], v[sim::vQ], v[sim::vFlim], v[sim::vQlim], 0);
     // linear devices: F += G x, Q += C x  (N_LOA_CktLoader.C:774-782)
@@ -246,6 +247,8 @@ struct GpuBackend {
   bool limiter_active() const { return ss.voltageLimiterFlag != 0; }
   void accept_state() {
     cudaMemcpyAsync(sta[1], sta[0], (size_t)ctx->n_state * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    // DataStore::updateSolDataArrays rotates last <- current <- next; the last store is only read by the BJT excess phase
+    if (ctx->needs_last_sto) cudaMemcpyAsync(sto[2], sto[1], (size_t)ctx->n_store * sizeof(double), cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(sto[1], sto[0], (size_t)ctx->n_store * sizeof(double), cudaMemcpyDeviceToDevice, s);
   }
   void record(double t) {
@@ -362,7 +365,7 @@ int xgpu_tran_run(xgpu_ctx *ctx, const xgpu_tran_params *tp, const double *h_x0,
   XS_CUDA(cudaMemsetAsync(pool, 0, need_d * sizeof(double), ctx->stream));
   for (int i = 0; i < sim::kNumVec; ++i) B.v[i] = pool + i * n;
   B.dFdx = pool + sim::kNumVec * n; B.dQdx = B.dFdx + ctx->nnz; B.J = B.dQdx + ctx->nnz; B.scratch = B.J + ctx->nnz;
-  B.sto[0] = ctx->buf[7]; B.sto[1] = ctx->buf[8]; B.sta[0] = ctx->buf[9]; B.sta[1] = ctx->buf[10];
+  B.sto[0] = ctx->buf[7]; B.sto[1] = ctx->buf[8]; B.sto[2] = ctx->buf[11]; ctx->d_last_sto = ctx->buf[11]; B.sta[0] = ctx->buf[9]; B.sta[1] = ctx->buf[10];
   B.d_src_vals = B.scratch + 8192; B.d_probe_out = B.d_src_vals + srows.size() + 1;
   B.d_src_rows = ctx->tran_ints; B.d_probe = ctx->tran_ints + srows.size() + 1;
   if (!srows.empty()) XS_CUDA(cudaMemcpyAsync(B.d_src_rows, srows.data(), srows.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -122,9 +122,14 @@ __global__ void __launch_bounds__(128) bjt_kernel(GroupDev g, b4::LoadArgs a) {
 #pragma unroll
   for (int t = 0; t < 3; ++t) { cs[t] = a.curr_sto[sto0 + (size_t)t * ss]; ns[t] = a.next_sto[sto0 + (size_t)t * ss]; }
   D::Out o;
-  D::evaluate(a.S, R, __ldg(g.flags + i), V, cs, ns, o);
+  real cex_c = 0.0, cex_l = 0.0;
+  const size_t cex = sto0 + (size_t)D::st_cexbc * ss;
+  if (R.excessPhaseFac != 0.0 && !a.S.dcopFlag && !a.S.beginIntegrationFlag) { cex_c = a.curr_sto[cex]; cex_l = a.last_sto[cex]; }
+  D::evaluate(a.S, R, __ldg(g.flags + i), V, cs, ns, o, cex_c, cex_l);
 #pragma unroll
   for (int t = 0; t < 3; ++t) a.next_sto[sto0 + (size_t)t * ss] = to_double(o.store[t]);
+  if (o.cexbc_mode & 1) a.next_sto[cex] = to_double(o.cexbc_next);
+  if (o.cexbc_mode & 2) { a.curr_sto[cex] = to_double(o.cexbc_init); a.last_sto[cex] = to_double(o.cexbc_init); }
 #pragma unroll
   for (int t = 0; t < D::kNumState; ++t) a.next_sta[sta0 + (size_t)t * as] = to_double(o.state[t]);
   // first Newton step of the first transient step: charges also go to the current state (N_DEV_BJT.C:4135-4147)
@@ -206,6 +211,8 @@ const int kDiodeCol[diode::kSlots] = {0, 2, 1, 2, 0, 1, 2};
 const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3, 0, kDiodeRow, kDiodeCol};
 
 }  // namespace
+
+int bjt_excess_phase_field() { return (int)(offsetof(bjt::Rec, excessPhaseFac) / sizeof(double)); }
 
 const TypeInfo *type_info(int type) {
   switch (type) {

@@ -8,6 +8,7 @@ namespace xb {
 namespace simple {
 
 enum Type { kDiode = 1, kMos1 = 2, kBjt = 3, kRlc = 4, kMvs = 5 };
+int bjt_excess_phase_field();      // index of excessPhaseFac in the BJT record
 // Models produced by the ADMS translator (xyce_b200/adms/translate.py -> gen_adms/registry.h at build time) take the type
 // ids kAdmsGenBase + position in the registry; adms_gen_* describe them to the callers of xgpu_simple_group_add.
 constexpr int kAdmsGenBase = 100;

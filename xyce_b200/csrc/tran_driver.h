@@ -213,7 +213,8 @@ struct ResidualForm {
 
 struct Flags {
   int dcop = 0, tranop = 0, transient = 1, initTran = 0, newtonIter = 0, initJct = 0, initFix = 0;
-  double currTimeStep = 0;
+  double currTimeStep = 0, lastTimeStep = 0;
+  int beginIntegration = 0;   // SolverState::beginIntegrationFlag_ (first step out of a break point, t = 0 included)
   double bpTol = 0;       // break-point tolerance, for the sources' corner tests
 };
 
@@ -464,7 +465,8 @@ class TransientDriver {
   int newton_solve(bool dc) {
     Flags fl;
     if (dc) { fl.dcop = 1; fl.tranop = 1; fl.initJct = 1; fl.currTimeStep = 0.0; }
-    else { fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep; }
+    else { fl.initTran = (stepNumber == 0); fl.currTimeStep = currentTimeStep; fl.lastTimeStep = lastTimeStep; }
+    fl.beginIntegration = beginningIntegration;
     fl.bpTol = bpTol;
     const int maxNewtonStep = dc ? P.dcMaxNewtonStep : P.maxNewtonStep;
     const double deltaXTol = dc ? P.dcDeltaXTol : P.deltaXTol, RHSTol = dc ? P.dcRHSTol : P.RHSTol;

@@ -102,6 +102,8 @@ struct SolverFlags {
   double vdsScaleMin;
   double sizeScale;      // MOS1 homotopy (unused by BSIM4)
   double currTimeStep;   // unused by BSIM4 eval
+  double lastTimeStep;   // BJT excess phase (Weil's approximation, N_DEV_BJT.C:2742-2799)
+  int beginIntegrationFlag;   // first step out of a break point, t = 0 included (N_DEV_SolverState.h:169)
 };
 
 // ---- smoothed exponentials (B4p82.C:82-105) --------------------------------
