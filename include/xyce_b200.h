@@ -281,6 +281,14 @@ int xgpu_linear_set(xgpu_ctx *ctx, int nG, const int32_t *g_row, const int32_t *
                     int nC, const int32_t *c_row, const int32_t *c_col, const double *c_val);
 int xgpu_sources_set(xgpu_ctx *ctx, int n_sources, const int32_t *row, const double *scale, const int32_t *type,
                      const double *params7);
+/* The same by device: kind 0 Resistor {R}, 1 Capacitor {C}, 2 Inductor {L} (branch unknown: F[p] += i,
+ * F[n] -= i, F[b] -= vp - vn, Q[b] += L i; N_DEV_Inductor.C:880-910, :960-985), 3 Vsrc (branch unknown; N_DEV_Vsrc.C:1323-,
+ * :1454-1457), 4 ISRC (B[p] -= i(t), B[n] += i(t); N_DEV_ISRC.C:1100-1130).  nodes3[i] = {pos, neg, branch} unknown
+ * indices (-1 = ground / no branch); value[i] for kinds 0-2; src_type[i] / src_params7[i] (the types of
+ * xgpu_sources_set) for kinds 3-4.  Stamps are added to the replayed G / C pair, sources are appended; may be mixed
+ * with xgpu_linear_set / xgpu_sources_set, which REPLACE the stamps / the source list: call those first.  Before xgpu_pattern_build. */
+int xgpu_linear_devices_add(xgpu_ctx *ctx, int kind, int n, const int32_t *nodes3, const double *value,
+                            const int32_t *src_type, const double *src_params7);
 /* Table of the piece-wise linear sources: n_points (time, value) pairs shared by all PWL sources; a source of type 5
  * has params7 = {TD, offset (in points), count, REPEAT (0 / 1), REPEATTIME} (PWLinData, Core/N_DEV_SourceData.C:1770-1886).
  * Source types of xgpu_sources_set: 0 DC {v}, 1 PULSE {v1 v2 td tr tf pw per}, 2 SIN {v0 va freq td theta phase},

@@ -342,3 +342,42 @@ def test_models_set_keeps_small_device_groups_and_can_be_repeated():
     x[1::2] = rng.uniform(-0.3, 0.3, len(x[1::2]))
     check(ref, eng, CASES["tran1"], x, rng.normal(0.3, 0.4, ref.n_sto), rng.normal(0.3, 0.4, ref.n_sto))
     eng.close()
+
+
+def test_linear_devices_by_device_equal_the_coo_stamps_and_analytic():
+    """xgpu_linear_devices_add (R, C, L, Vsrc, ISRC as devices; N_DEV_Resistor.C / Capacitor.C / Inductor.C:880-985 /
+    Vsrc.C:1323-1457 / ISRC.C:1100-1130): (a) the series R-L-C of BASELINE config 5 built device by device gives bitwise
+    the run of the hand-written COO stamps; (b) a current source into R || C follows i R (1 - exp(-t / RC))."""
+    from xyce_b200 import workloads as wl
+    w = wl.rlc_series(2, as_plugin=False)
+    eng = wl.build_engine_generic(w)
+    want = eng.tran_run(w["x"], 1e-6, 1e-9, w["probes"])
+    eng.close()
+    k = np.arange(2)
+    n1, i1, i2, br, vb = 5 * k, 5 * k + 1, 5 * k + 2, 5 * k + 3, 5 * k + 4
+    none = np.full(2, -1)
+    eng = xyce_b200.Engine(0)
+    eng.set_sizes(0, 0)
+    eng.add_linear_devices("V", np.stack([n1, none, vb], 1), stype=[2, 2], params7=np.tile([5.0, 5.0, 20e6, 0, 0, 0, 0], (2, 1)))
+    eng.add_linear_devices("R", np.stack([n1, i1, none], 1), value=[1e3, 1e3])
+    eng.add_linear_devices("C", np.stack([i1, i2, none], 1), value=[1e-12, 1e-12])
+    eng.add_linear_devices("L", np.stack([i2, none, br], 1), value=[1e-3, 1e-3])
+    rowptr, colind = eng.build_pattern(10)
+    assert np.array_equal(rowptr, w["rowptr"]) and np.array_equal(colind, w["colind"])
+    eng.finalize()
+    got = eng.tran_run(w["x"], 1e-6, 1e-9, w["probes"])
+    eng.close()
+    assert want["rc"] == 0 and got["rc"] == 0
+    assert np.array_equal(got["t"], want["t"]) and np.array_equal(got["wave"], want["wave"])
+    # (b) ISRC 1 mA from ground into node 0, R = 1 k || C = 1 nF: tau = 1 us
+    eng = xyce_b200.Engine(0)
+    eng.set_sizes(0, 0)
+    eng.add_linear_devices("I", [[-1, 0, -1]], stype=[0], params7=[[1e-3, 0, 0, 0, 0, 0, 0]])
+    eng.add_linear_devices("R", [[0, -1, -1]], value=[1e3])
+    eng.add_linear_devices("C", [[0, -1, -1]], value=[1e-9])
+    eng.build_pattern(1)
+    eng.finalize()
+    r = eng.tran_run(np.zeros(1), 5e-6, 1e-8, [0])
+    eng.close()
+    assert r["rc"] == 0 and len(r["t"]) > 20
+    assert np.max(np.abs(r["wave"][:, 0] - (1.0 - np.exp(-r["t"] / 1e-6)))) < 5e-3

@@ -333,6 +333,16 @@ class Engine:
         a = [_i32(row), _f64(scale), _i32(stype), _f64(params7)]
         self._chk(self.lib.xgpu_sources_set(self.h, len(a[0]), _ip(a[0]), _dp(a[1]), _ip(a[2]), _dp(a[3])))
 
+    def add_linear_devices(self, kind, nodes3, value=None, stype=None, params7=None):
+        """kind: "R", "C", "L" (value) or "V", "I" (source type + params); nodes3 = [n][pos, neg, branch]"""
+        k = "RCLVI".index(kind)
+        nd = _i32(np.asarray(nodes3, dtype=np.int32).reshape(-1, 3))
+        v = None if value is None else _f64(value)
+        t = None if stype is None else _i32(stype)
+        p = None if params7 is None else _f64(np.asarray(params7, dtype=np.float64).reshape(-1, 7))
+        self._chk(self.lib.xgpu_linear_devices_add(self.h, k, len(nd), _ip(nd), None if v is None else _dp(v),
+                                                   None if t is None else _ip(t), None if p is None else _dp(p)))
+
     def set_pwl_table(self, tv_pairs):
         """(time, value) pairs of all PWL sources (type 5: params = {td, offset, count, repeat, repeattime})"""
         tv = _f64(np.asarray(tv_pairs, dtype=np.float64).reshape(-1, 2))

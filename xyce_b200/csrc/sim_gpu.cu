@@ -33,6 +33,13 @@ void merge_coo(int n, const int32_t *r, const int32_t *c, const double *v, XgLin
   for (auto &e : m) { L.h_row.push_back(e.first.first); L.h_col.push_back(e.first.second); L.h_val.push_back(e.second); }
 }
 
+// the same, added to the entries already there
+void append_coo(int n, const int32_t *r, const int32_t *c, const double *v, XgLinearPart &L) {
+  std::vector<int32_t> rr(L.h_row), cc(L.h_col); std::vector<double> vv(L.h_val);
+  rr.insert(rr.end(), r, r + n); cc.insert(cc.end(), c, c + n); vv.insert(vv.end(), v, v + n);
+  merge_coo((int)vv.size(), rr.data(), cc.data(), vv.data(), L);
+}
+
 __global__ void and_flags_kernel(const int *flags, int n, int *out) {
   xb::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +318,55 @@ int xgpu_sources_set(xgpu_ctx *ctx, int ns, const int32_t *row, const double *sc
     std::memcpy(q.p, params7 + 7 * (size_t)k, 7 * sizeof(double));
     ctx->sources.push_back(q);
   }
+  return 0;
+}
+
+// Linear devices by device: the constant stamps of the reference's Master loads, merged into the replayed G / C pair, and
+// the independent sources appended to the source list.
+int xgpu_linear_devices_add(xgpu_ctx *ctx, int kind, int n, const int32_t *nodes3, const double *value, const int32_t *src_type,
+                            const double *src_params7) {
+  if (!ctx || n < 0 || kind < 0 || kind > 4 || (n > 0 && !nodes3)) return 1;
+  if (ctx->finalized) return xg_fail(ctx, 5, "linear_devices_add after finalize");
+  if (kind <= 2 && n > 0 && !value) return 1;
+  if (kind >= 3 && n > 0 && (!src_type || !src_params7)) return 1;
+  std::vector<int32_t> gr, gc, cr, cc; std::vector<double> gv, cv;
+  auto G = [&](int r, int c, double v) { if (r >= 0 && c >= 0) { gr.push_back(r); gc.push_back(c); gv.push_back(v); } };
+  auto Cq = [&](int r, int c, double v) { if (r >= 0 && c >= 0) { cr.push_back(r); cc.push_back(c); cv.push_back(v); } };
+  for (int i = 0; i < n; ++i) {
+    const int p = nodes3[3 * (size_t)i], m = nodes3[3 * (size_t)i + 1], b = nodes3[3 * (size_t)i + 2];
+    if (kind >= 2 && kind <= 3 && b < 0) return xg_fail(ctx, 18, "inductor / voltage source without a branch unknown");
+    switch (kind) {
+      case 0: {      // Resistor: i = G (vp - vn)  (N_DEV_Resistor.C Master::loadDAEMatrices: +G -G -G +G)
+        if (value[i] == 0.0) return xg_fail(ctx, 18, "resistor with R = 0");
+        const double g = 1.0 / value[i];
+        G(p, p, g); G(p, m, -g); G(m, p, -g); G(m, m, g);
+      } break;
+      case 1: {      // Capacitor: q = C (vp - vn)  (N_DEV_Capacitor.C Master::loadDAEMatrices, constant C)
+        const double c = value[i];
+        Cq(p, p, c); Cq(p, m, -c); Cq(m, p, -c); Cq(m, m, c);
+      } break;
+      case 2:        // Inductor: F[p] += i, F[n] -= i, F[b] -= vp - vn, Q[b] += L i  (N_DEV_Inductor.C:880-910, :960-985)
+        G(p, b, 1.0); G(m, b, -1.0); G(b, p, -1.0); G(b, m, 1.0); Cq(b, b, value[i]);
+        break;
+      case 3: {      // Vsrc: F[p] += i, F[n] -= i, F[b] += vp - vn, B[b] += v(t)  (N_DEV_Vsrc.C:1323-1420, :1454-1457)
+        G(p, b, 1.0); G(m, b, -1.0); G(b, p, 1.0); G(b, m, -1.0);
+        XgSource q; q.row = b; q.scale = 1.0; q.type = src_type[i];
+        std::memcpy(q.p, src_params7 + 7 * (size_t)i, 7 * sizeof(double));
+        ctx->sources.push_back(q);
+      } break;
+      case 4:        // ISRC: B[p] -= i(t), B[n] += i(t)  (N_DEV_ISRC.C:1100-1130)
+        for (int e = 0; e < 2; ++e) {
+          const int row = e ? m : p;
+          if (row < 0) continue;
+          XgSource q; q.row = row; q.scale = e ? 1.0 : -1.0; q.type = src_type[i];
+          std::memcpy(q.p, src_params7 + 7 * (size_t)i, 7 * sizeof(double));
+          ctx->sources.push_back(q);
+        }
+        break;
+    }
+  }
+  append_coo((int)gv.size(), gr.data(), gc.data(), gv.data(), ctx->linG);
+  append_coo((int)cv.size(), cr.data(), cc.data(), cv.data(), ctx->linC);
   return 0;
 }
 
