@@ -134,6 +134,12 @@ int xgpu_needs_last_store(const xgpu_ctx *ctx);      /* 1 when a group reads the
  * internal nodes get them from the evaluation kernel. */
 int xgpu_b4_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0);
 int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV);
+/* The same for diode (1 branch-data entry), MOSFET level 1 (id ig is ib) and BJT (ib ie ic is) groups of
+ * xgpu_simple_group_add (Master::loadDAEVectors, N_DEV_Diode.C:1889-1897, N_DEV_MOSFET1.C:4544-4572, N_DEV_BJT.C:4358-4383;
+ * branch order of registerBranchDataLIDs).  xgpu_lead_load = xgpu_b4_lead_load: one call serves every group that has
+ * branch LIDs set. */
+int xgpu_simple_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0);
+int xgpu_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV);
 
 /* Carried per-instance limiter threshold (Instance::von); instance order = insertion order. */
 int xgpu_b4_von_set(xgpu_ctx *ctx, int group, const double *von);

@@ -19,7 +19,7 @@ def flag_arrays(flags):
     return fl, fd
 
 
-def diode_circuit(ref_cls, card, n_dev=6, seed=0):
+def diode_circuit(ref_cls, card, n_dev=6, seed=0, lead=False):
     rng = np.random.default_rng(seed)
     c = ref_cls(2 * n_dev)
     p = dict(DIODE_CARDS[card])
@@ -27,6 +27,8 @@ def diode_circuit(ref_cls, card, n_dev=6, seed=0):
     c.add_dev_model("d", "dmod", "D", level, p)
     for i in range(n_dev):
         c.add_dev_instance("d", "D:%d" % i, "dmod", [2 * i, 2 * i + 1], dict(AREA=float(rng.choice([1.0, 2.5]))))
+    if lead:
+        c.enable_lead_currents()
     c.finalize()
     return c
 
@@ -122,7 +124,7 @@ BJT_PTF_CARDS = {
 }
 
 
-def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0):
+def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0, lead=False):
     """n_dev isolated devices, every terminal on its own node"""
     rng = np.random.default_rng(seed)
     nt = 4
@@ -144,6 +146,8 @@ def simple_circuit(ref_cls, kind, card, n_dev=6, seed=0):
         c.add_dev_model("q", "qmod", mtype, 1, p)
         for i in range(n_dev):
             c.add_dev_instance("q", "Q:%d" % i, "qmod", [nt * i, nt * i + 1, nt * i + 2, nt * i + 3], dict(AREA=float(rng.choice([1.0, 3.0]))))
+    if lead:
+        c.enable_lead_currents()
     c.finalize()
     return c
 

@@ -381,3 +381,50 @@ def test_linear_devices_by_device_equal_the_coo_stamps_and_analytic():
     eng.close()
     assert r["rc"] == 0 and len(r["t"]) > 20
     assert np.max(np.abs(r["wave"][:, 0] - (1.0 - np.exp(-r["t"] / 1e-6)))) < 5e-3
+
+
+@pytest.mark.parametrize("case", ["tran1", "dcop_init"])
+@pytest.mark.parametrize("kind,card", [("diode", c) for c in sorted(DIODE_CARDS)] + [("mos1", c) for c in sorted(MOS1_CARDS)] +
+                         [("bjt", c) for c in sorted(BJT_CARDS)])
+def test_small_device_lead_currents(kind, card, case):
+    """loadLeadCurrent (.PRINT I(D1) / IC(Q1) / P(M1)) for diode, MOSFET level 1 and BJT groups: leadF, leadQ, junctionV at
+    the branch-data LIDs against Master::loadDAEVectors of the reference objects (N_DEV_Diode.C:1889-1897,
+    N_DEV_MOSFET1.C:4544-4572, N_DEV_BJT.C:4358-4383); entries the reference does not write keep their value."""
+    import torch
+    if kind == "diode":
+        ref = diode_circuit(oracle_ref.RefCircuit, card, n_dev=120, seed=5, lead=True)
+        type_id, key, nlead = 1, "d", 1
+        ex = [ref.diode_export(i) for i in range(ref.n_inst)]
+    else:
+        type_id, key = SIMPLE[kind][0], SIMPLE[kind][1]
+        nlead = 4
+        ref = simple_circuit(oracle_ref.RefCircuit, kind, card, n_dev=120, seed=5, lead=True)
+        ex = [ref.dev_export(i, key) for i in range(ref.n_inst)]
+    eng = xyce_b200.Engine(0)
+    eng.set_pattern(ref.rowptr, ref.colind)
+    eng.set_sizes(ref.n_sta, ref.n_sto)
+    eng.add_simple_group(type_id, np.array([e["rec"] for e in ex]), [e["flags"] for e in ex], np.array([e["lids"] for e in ex]),
+                         [e["sto0"] for e in ex], 1, [e.get("sta0", 0) for e in ex], 1)
+    eng.finalize()
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1.0, 1.0, ref.n)
+    flags = CASES[case]
+    nsto, csto = rng.normal(0.2, 0.5, ref.n_sto), rng.normal(0.2, 0.5, ref.n_sto)
+    csta = rng.normal(0.0, 1e-14, ref.n_sta)
+    ref.set_flags(**flags); ref.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta)
+    eng.set_state(0, nsto); eng.set_state(1, csto)
+    if ref.n_sta:
+        eng.set_state(3, csta)
+    ref.load(x)
+    want = ref.lead()
+    assert len(want["leadF"]) == nlead * ref.n_inst and np.any(want["leadF"])
+    eng.simple_lead_set(0, want["branch0"])
+    eng.load_host(x, solver_state(**flags))
+    out = [torch.zeros(len(want["leadF"]), dtype=torch.float64, device="cuda") for _ in range(3)]
+    eng.lead_load(eng.device_buffer(0), *[t.data_ptr() for t in out])
+    eng.sync()
+    for k, t in zip(("leadF", "leadQ", "junctionV"), out):
+        got = t.cpu().numpy()
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got, want[k], scale) < 1e-12, (kind, card, case, k)
+    eng.close()

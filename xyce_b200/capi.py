@@ -375,6 +375,13 @@ class Engine:
         b = _i32(branch_lid0)
         self._chk(self.lib.xgpu_b4_lead_set(self.h, int(group), _ip(b)))
 
+    def simple_lead_set(self, group, branch_lid0):
+        b = _i32(branch_lid0)
+        self._chk(self.lib.xgpu_simple_lead_set(self.h, int(group), _ip(b)))
+
+    def lead_load(self, d_sol, d_leadF, d_leadQ, d_junctionV):
+        self._chk(self.lib.xgpu_lead_load(self.h, C.c_void_p(d_sol), C.c_void_p(d_leadF), C.c_void_p(d_leadQ), C.c_void_p(d_junctionV)))
+
     def b4_lead_load(self, d_sol, d_leadF, d_leadQ, d_junctionV):
         self._chk(self.lib.xgpu_b4_lead_load(self.h, C.c_void_p(d_sol), C.c_void_p(d_leadF), C.c_void_p(d_leadQ), C.c_void_p(d_junctionV)))
 

@@ -46,6 +46,8 @@ struct Out {
   // (no history yet: first step out of a break point, N_DEV_BJT.C:2716-2721)
   int cexbc_mode;
   real cexbc_next, cexbc_init;
+  // lead currents (Master::loadDAEVectors, N_DEV_BJT.C:4358-4378), branch order ib, ie, ic, is (registerBranchDataLIDs :1548-1551)
+  real leadF[4], leadQ[4];
 };
 
 // depletion charge / capacitance of one junction (the four copies at N_DEV_BJT.C:3223-3330)
@@ -298,6 +300,15 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
     o.QL[kBP] += b * ty * mf;
     o.QL[kEP] += e * ty * mf;
   }
+
+  o.leadQ[2] = -ty * (qCS + qBX + qBCdep + qBCdiff) * mf;
+  o.leadQ[0] = ty * (qBX + qBEdep + qBEdiff + qBCdep + qBCdiff) * mf;
+  o.leadQ[1] = -ty * (qBEdep + qBEdiff) * mf;
+  o.leadQ[3] = ty * qCS * mf;
+  o.leadF[2] = ty * (iC) * mf;
+  o.leadF[3] = 0.0;
+  o.leadF[1] = ty * (iE) * mf;
+  o.leadF[0] = ty * (iB) * mf;
 
   // ---- Master::loadDAEMatrices ----
   for (int s = 0; s < kSlots; ++s) o.JF[s] = o.JQ[s] = 0.0;

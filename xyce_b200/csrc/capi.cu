@@ -151,7 +151,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
     cudaFree(g.d_inst_d); cudaFree(g.d_von); cudaFree(g.d_topo); cudaFree(g.d_model_idx);
     cudaFree(g.d_size_idx); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); cudaFree(g.d_branch0); cudaFree(g.d_lead);
   }
-  for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); }
+  for (auto &g : ctx->sgroups) { cudaFree(g.d_rec); cudaFree(g.d_flags); cudaFree(g.d_lids); cudaFree(g.d_sto0); cudaFree(g.d_sta0); cudaFree(g.d_orig); cudaFree(g.d_branch0); cudaFree(g.d_lead); }
   cudaFree(ctx->d_models); cudaFree(ctx->d_sizes); cudaFree(ctx->d_vec_planes); cudaFree(ctx->d_mat_planes);
   for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); cudaFree(m->ell); cudaFree(m->done); }
   cudaFree(ctx->d_conv);
@@ -621,6 +621,24 @@ int xgpu_b4_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0) {
   return 0;
 }
 
+int xgpu_simple_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0) {
+  if (!ctx || group < 0 || group >= (int)ctx->sgroups.size() || !branch_lid0) return 1;
+  XgSimpleGroup &g = ctx->sgroups[group];
+  if (xb::simple::lead_count(g.type) == 0) return fail(ctx, 17, "this device type has no lead currents in the library");
+  cudaFree(g.d_branch0); g.d_branch0 = nullptr;
+  XG_CUDA(upload(&g.d_branch0, branch_lid0, (size_t)g.n));
+  if (g.type == xb::simple::kBjt && !g.d_lead) {
+    XG_CUDA(cudaMalloc((void **)&g.d_lead, (size_t)8 * std::max(g.n, 1) * sizeof(double)));
+    XG_CUDA(cudaMemset(g.d_lead, 0, (size_t)8 * std::max(g.n, 1) * sizeof(double)));
+    g.dev.lead = g.d_lead;
+  }
+  return 0;
+}
+
+int xgpu_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV) {
+  return xgpu_b4_lead_load(ctx, d_sol, d_leadF, d_leadQ, d_junctionV);
+}
+
 int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV) {
   if (!ctx || !d_sol || !d_leadF || !d_leadQ || !d_junctionV) return 1;
   if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
@@ -629,6 +647,12 @@ int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, doubl
     const double *pF = ctx->d_vec_planes + g.dev.vec_base, *pQ = ctx->d_vec_planes + ctx->vec_plane + g.dev.vec_base;
     if (g.general) { pF = g.d_lead; pQ = g.d_lead + (size_t)4 * g.n; }
     b4_lead_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g.n, pF, pQ, g.d_lids, g.d_branch0, d_sol, d_leadF, d_leadQ, d_junctionV);
+    ++ctx->launches;
+  }
+  for (auto &g : ctx->sgroups) {
+    if (!g.d_branch0 || g.n == 0) continue;
+    xb::simple::launch_lead(g.dev, g.d_branch0, ctx->d_vec_planes + g.dev.vec_base, ctx->d_vec_planes + ctx->vec_plane + g.dev.vec_base,
+                            d_sol, d_leadF, d_leadQ, d_junctionV, ctx->stream);
     ++ctx->launches;
   }
   XG_CUDA(cudaGetLastError());

@@ -40,6 +40,8 @@ struct XgSimpleGroup {
   xb::simple::GroupDev dev{};
   double *d_rec = nullptr;
   int *d_flags = nullptr, *d_lids = nullptr, *d_sto0 = nullptr, *d_sta0 = nullptr, *d_orig = nullptr;
+  int *d_branch0 = nullptr;        // [n] first branch-data LID (lead currents), null = not requested
+  double *d_lead = nullptr;        // BJT: [8][n] lead block written by the evaluation kernel
 };
 
 // linear-device part (R, C, V, I): constant stamps replayed every load, like the reference's

@@ -138,7 +138,50 @@ __global__ void __launch_bounds__(128) bjt_kernel(GroupDev g, b4::LoadArgs a) {
     for (int t = 0; t < D::kNumState; ++t) a.curr_sta[sta0 + (size_t)t * as] = to_double(o.state[t]);
   }
   g.orig_flag[i] = o.origFlag;
+  if (g.lead) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { g.lead[(size_t)t * n + i] = to_double(o.leadF[t]); g.lead[(size_t)(4 + t) * n + i] = to_double(o.leadQ[t]); }
+  }
   store_planes<D::Out, D::kNodes, D::kSlots>(g, a, o, i);
+}
+
+// Lead currents (Instance::loadLeadCurrent; what .PRINT I(D1) / IC(Q1) / P(M1) switches on).  Diode and MOSFET level 1: the
+// lead quantities ARE terms the evaluation has just written to the contribution planes -- diode leadF = Id mf = -(Neg row
+// term) (N_DEV_Diode.C:1889-1897); MOSFET1 leadF[id] = the Drain row term when RD != 0, else the Drain' one, and so on
+// (N_DEV_MOSFET1.C:4544-4572) -- BJT: the block the evaluation kernel wrote (terminal currents are not row terms when
+// RC / RB / RE != 0).  ASSIGNS, like the reference.
+__global__ void __launch_bounds__(256) lead_kernel(GroupDev g, const int *__restrict__ branch0, const double *__restrict__ pF,
+                                                   const double *__restrict__ pQ, const double *__restrict__ sol, double *leadF,
+                                                   double *leadQ, double *junctionV, int f0, int f1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.n) return;
+  const int b = branch0[i];
+  if (b < 0) return;
+  const size_t n = g.n;
+  auto v = [&](int node) { const int l = g.lids[node * n + i]; return l >= 0 ? sol[l] : 0.0; };
+  if (g.type == kDiode) {
+    leadF[b] = -pF[diode::kNeg * n + i];
+    if (g.rec[f0 * n + i] != 0.0) leadQ[b] = -pQ[diode::kNeg * n + i];      // model CJO != 0 (tJctCap = CJO x temperature factor)
+    junctionV[b] = v(diode::kPos) - v(diode::kNeg);
+  } else if (g.type == kMos1) {
+    const bool rd = g.rec[f0 * n + i] != 0.0, rs = g.rec[f1 * n + i] != 0.0;      // drainConductance / sourceConductance
+    leadF[b + 0] = pF[(rd ? mos1::kD : mos1::kDP) * n + i];
+    if (!rd) leadQ[b + 0] = pQ[mos1::kDP * n + i];
+    leadF[b + 2] = pF[(rs ? mos1::kS : mos1::kSP) * n + i];
+    if (!rs) leadQ[b + 2] = pQ[mos1::kSP * n + i];
+    leadF[b + 1] = pF[mos1::kG * n + i]; leadQ[b + 1] = pQ[mos1::kG * n + i];
+    leadF[b + 3] = pF[mos1::kB * n + i]; leadQ[b + 3] = pQ[mos1::kB * n + i];
+    junctionV[b + 0] = v(mos1::kD) - v(mos1::kS);
+    junctionV[b + 1] = v(mos1::kG) - v(mos1::kS);
+    junctionV[b + 2] = 0.0; junctionV[b + 3] = 0.0;
+  } else if (g.type == kBjt) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { leadF[b + t] = g.lead[t * n + i]; leadQ[b + t] = g.lead[(4 + t) * n + i]; }
+    junctionV[b + 2] = v(bjt::kC) - v(bjt::kE);
+    junctionV[b + 3] = 0.0;
+    junctionV[b + 0] = v(bjt::kB) - v(bjt::kE);
+    junctionV[b + 1] = 0.0;
+  }
 }
 
 __global__ void __launch_bounds__(128) rlc_kernel(GroupDev g, b4::LoadArgs a) {
@@ -211,6 +254,17 @@ const int kDiodeCol[diode::kSlots] = {0, 2, 1, 2, 0, 1, 2};
 const TypeInfo kDiodeInfo = {diode::kNodes, diode::kSlots, diode::kNumFields, 3, 0, kDiodeRow, kDiodeCol};
 
 }  // namespace
+
+int lead_count(int type) { return type == kDiode ? 1 : (type == kMos1 || type == kBjt) ? 4 : 0; }
+
+void launch_lead(const GroupDev &g, const int *branch0, const double *planeF, const double *planeQ, const double *sol,
+                 double *leadF, double *leadQ, double *junctionV, cudaStream_t s) {
+  if (g.n <= 0 || lead_count(g.type) == 0) return;
+  int f0 = 0, f1 = 0;
+  if (g.type == kDiode) f0 = (int)(offsetof(diode::Rec, tJctCap) / sizeof(double));
+  if (g.type == kMos1) { f0 = (int)(offsetof(mos1::Rec, drainConductance) / sizeof(double)); f1 = (int)(offsetof(mos1::Rec, sourceConductance) / sizeof(double)); }
+  lead_kernel<<<(g.n + 255) / 256, 256, 0, s>>>(g, branch0, planeF, planeQ, sol, leadF, leadQ, junctionV, f0, f1);
+}
 
 int bjt_excess_phase_field() { return (int)(offsetof(bjt::Rec, excessPhaseFac) / sizeof(double)); }
 

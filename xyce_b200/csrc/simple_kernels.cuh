@@ -9,6 +9,7 @@ namespace simple {
 
 enum Type { kDiode = 1, kMos1 = 2, kBjt = 3, kRlc = 4, kMvs = 5 };
 int bjt_excess_phase_field();      // index of excessPhaseFac in the BJT record
+int lead_count(int type);           // branch-data entries per instance (0 = the type has no lead currents here)
 // Models produced by the ADMS translator (xyce_b200/adms/translate.py -> gen_adms/registry.h at build time) take the type
 // ids kAdmsGenBase + position in the registry; adms_gen_* describe them to the callers of xgpu_simple_group_add.
 constexpr int kAdmsGenBase = 100;
@@ -26,6 +27,7 @@ struct GroupDev {
   int sto_stride, sta_stride;
   int *orig_flag;
   long long vec_base, mat_base;
+  double *lead;           // BJT with lead currents requested: [8][n] block (F ib ie ic is, Q ib ie ic is), else null
 };
 
 // static description of a device type (host side)
@@ -33,6 +35,9 @@ struct TypeInfo { int nodes, slots, nfields, nstore, nstate; const int *slot_row
 const TypeInfo *type_info(int type);
 
 void launch_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
+// copies / derives leadF, leadQ, junctionV of one group at its branch-data LIDs (assign): after the evaluation launch
+void launch_lead(const GroupDev &g, const int *branch0, const double *planeF, const double *planeQ, const double *sol,
+                 double *leadF, double *leadQ, double *junctionV, cudaStream_t s);
 // adms_gen_kernels.cu (its own translation unit: fast arithmetic variant)
 const TypeInfo *adms_gen_type_info(int type);
 void launch_adms_gen_group(const GroupDev &g, const b4::LoadArgs &a, cudaStream_t s);
