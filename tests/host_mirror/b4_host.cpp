@@ -2,6 +2,12 @@
 // for the host so that CPU-only CI can check its arithmetic against the reference-built
 // oracle (oracle/_ref) without a GPU.  Never loaded by the product; the product path is
 // the CUDA library and fails loudly when that is missing.
+#if defined(XB_TAINT_TRACE)
+#include <execinfo.h>
+#include <dlfcn.h>
+#include <map>
+#include <array>
+#endif
 #include <cstring>
 #ifdef XB_COUNT_OPS
 #include "../../xyce_b200/csrc/xb_real.h"
@@ -120,6 +126,34 @@ void xbh_op_counts(unsigned long long *out) {
   for (int i = 0; i < 7; ++i) out[i] = 0;
 #endif
 }
+
+#if defined(XB_TAINT_TRACE)
+// call stacks of the bias-independent operations (tool build only: -O0 -g; scripts/hoistable_lines.py resolves them)
+static std::map<std::array<void *, 9>, unsigned long long> g_taint_stacks;
+void xb_taint_event(int kind) {
+  void *fr[12];
+  const int n = backtrace(fr, 12);
+  std::array<void *, 9> key{};
+  key[0] = (void *)(long)kind;
+  for (int i = 1; i < n && i <= 8; ++i) key[i] = fr[i];
+  ++g_taint_stacks[key];
+}
+int xbh_taint_dump(const char *path) {
+  FILE *f = std::fopen(path, "w");
+  if (!f) return 1;
+  Dl_info info;
+  dladdr((void *)&xbh_taint_dump, &info);
+  std::fprintf(f, "base %p\n", info.dli_fbase);
+  for (auto &e : g_taint_stacks) {
+    std::fprintf(f, "%llu %ld", e.second, (long)e.first[0]);
+    for (int i = 1; i < 9; ++i) std::fprintf(f, " %p", e.first[i]);
+    std::fprintf(f, "\n");
+  }
+  std::fclose(f);
+  g_taint_stacks.clear();
+  return 0;
+}
+#endif
 
 // TaintReal build: operations of the last xbh_b4_eval call, [bias-independent | bias-dependent] x [add, mul, div, sqrt,
 // exp, log], then the divisions of a bias-dependent value by a bias-independent divisor

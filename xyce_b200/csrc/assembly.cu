@@ -152,8 +152,13 @@ __device__ __forceinline__ void chunk_then_finish(const GatherMapDev &m, const P
   }
 }
 
+// resident blocks per SM: 3 (85 registers) measured 1.3 % faster on the config-2 step than 2 (98 registers, the compiler's
+// choice); 4 (64 registers) spills and is slower (72.0 / 72.9 / 73.8 us per step)
+#ifndef XB_ASM_MINBLOCKS
+#define XB_ASM_MINBLOCKS 3
+#endif
 template <int NPA, int NPB>
-__global__ void __launch_bounds__(256) assemble_kernel(GatherMapDev ma, PlaneSet pa, GatherMapDev mb, PlaneSet pb,
+__global__ void __launch_bounds__(256, XB_ASM_MINBLOCKS) assemble_kernel(GatherMapDev ma, PlaneSet pa, GatherMapDev mb, PlaneSet pb,
                                                        int short_a, bool accumulate) {
   __shared__ double sh[(NPA > NPB ? NPA : NPB)][256];
   // launched with programmatic stream serialization: the grid may start while the evaluation kernel that

@@ -112,17 +112,23 @@ struct RealT {
 //                   the work that could move into the per-bin / per-instance records (scripts/count_hoistable.py).
 #if !defined(__CUDA_ARCH__)
 struct TaintCounts { unsigned long long ops[2][6]; unsigned long long div_const_divisor; };
+#if defined(XB_TAINT_TRACE)      // scripts/hoistable_lines.py: where the bias-independent operations are (call-stack sampling)
+extern "C" void xb_taint_event(int kind);
+#define XB_TAINT_EVENT(k) xb_taint_event(k)
+#else
+#define XB_TAINT_EVENT(k) ((void)0)
+#endif
 inline TaintCounts &taint_counts() { static thread_local TaintCounts c{}; return c; }
 struct TaintReal {
   double v; bool b;
   TaintReal() : v(0.0), b(false) {}
   TaintReal(double x) : v(x), b(false) {}
   TaintReal(double x, bool bias) : v(x), b(bias) {}
-  static TaintReal mk(double x, bool bias, int kind) { ++taint_counts().ops[bias ? 1 : 0][kind]; return TaintReal(x, bias); }
+  static TaintReal mk(double x, bool bias, int kind) { ++taint_counts().ops[bias ? 1 : 0][kind]; if (!bias) XB_TAINT_EVENT(kind); return TaintReal(x, bias); }
   TaintReal &operator+=(const TaintReal &o) { *this = mk(v + o.v, b || o.b, 0); return *this; }
   TaintReal &operator-=(const TaintReal &o) { *this = mk(v - o.v, b || o.b, 0); return *this; }
   TaintReal &operator*=(const TaintReal &o) { *this = mk(v * o.v, b || o.b, 1); return *this; }
-  TaintReal &operator/=(const TaintReal &o) { if (b && !o.b) ++taint_counts().div_const_divisor; *this = mk(v / o.v, b || o.b, 2); return *this; }
+  TaintReal &operator/=(const TaintReal &o) { if (b && !o.b) { ++taint_counts().div_const_divisor; XB_TAINT_EVENT(6); } *this = mk(v / o.v, b || o.b, 2); return *this; }
   friend TaintReal operator-(const TaintReal &a) { return TaintReal(-a.v, a.b); }
   friend TaintReal operator+(const TaintReal &a) { return a; }
   friend TaintReal operator+(TaintReal a, const TaintReal &o) { a += o; return a; }
