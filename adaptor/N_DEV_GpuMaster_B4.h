@@ -16,7 +16,8 @@
 //
 // Compiled against the reference headers (it is reference-side code): oracle/Makefile builds it into the oracle
 // library, where tests/test_gpu_adaptor.py drives it and the stock Master through the same Device virtuals in one process.
-// Not supported (keep such instances on the stock Master): trnqsMod = 1, IC= rows, lead currents through this path.
+// Lead currents (loadLeadCurrent) are forwarded (xgpu_b4_lead_set / xgpu_lead_load_host).
+// Not supported (keep such instances on the stock Master): trnqsMod = 1, IC= rows.
 #ifndef Xyce_N_DEV_GpuMaster_B4_h
 #define Xyce_N_DEV_GpuMaster_B4_h
 
@@ -102,12 +103,16 @@ class GpuMaster : public Master {
       for (int t = 0; t < 12; ++t) lids.push_back(l[t] == ground_lid ? -1 : l[t]);
       sto0.push_back(in.li_store_vbd);       // the 22 store slots and the state slots are consecutive LIDs (registerStoreLIDs :6445-6487)
       sta0.push_back(in.li_state_qb);
+      const int b0 = in.loadLeadCurrent ? in.li_branch_dev_id : -1;      // id, ig, is, ib (registerBranchDataLIDs :6482-6500)
+      branch0_.push_back(b0);
+      if (b0 >= 0) nBranch_ = std::max(nBranch_, b0 + 4);
     }
     if (order.empty()) { err_ = "no BSIM4 instances"; return false; }
     if (!chk(xgpu_b4_models_set(ctx_, (int)mmap.size(), md.data(), mi.data(), (int)smap.size(), sd.data()))) return false;
     if (!chk(xgpu_sizes_set(ctx_, n_state, n_store))) return false;
     if (xgpu_b4_group_add(ctx_, (int)order.size(), id.data(), ii.data(), midx.data(), sidx.data(), lids.data(), sto0.data(), 1,
                           sta0.data(), 1) < 0) { err_ = xgpu_last_error(ctx_); return false; }
+    if (nBranch_ > 0 && !chk(xgpu_b4_lead_set(ctx_, 0, branch0_.data()))) return false;
     if (!chk(xgpu_pattern_build(ctx_, n_unknowns))) return false;          // the union of this device type's stamps
     if (!chk(xgpu_finalize(ctx_))) return false;
     nnz_ = xgpu_pattern_nnz(ctx_);
@@ -159,7 +164,8 @@ class GpuMaster : public Master {
 
   // Device::loadDAEVectors (N_DEV_Device.h:378): "+=" into F, Q and the voltage-limiter vectors
   bool loadDAEVectors(double *solVec, double *fVec, double *qVec, double *bVec, double *leadF, double *leadQ, double *junctionV) override {
-    (void)solVec; (void)bVec; (void)leadF; (void)leadQ; (void)junctionV;
+    (void)solVec; (void)bVec;
+    if (nBranch_ > 0 && leadF && leadQ && junctionV && !chk(xgpu_lead_load_host(ctx_, nBranch_, leadF, leadQ, junctionV))) return false;
     const ExternData &e = extData_();
     for (int i = 0; i < n_; ++i) { fVec[i] += f_[i]; qVec[i] += q_[i]; }
     if (getDeviceOptions().voltageLimiterFlag) {
@@ -193,7 +199,8 @@ class GpuMaster : public Master {
   const ExternData &extData_() const { return (*getInstanceBegin())->extData; }
   bool chk(int rc) { if (rc != 0) { err_ = ctx_ ? xgpu_last_error(ctx_) : "no context"; return false; } return true; }
   xgpu_ctx *ctx_ = nullptr;
-  int n_ = 0, nnz_ = 0, nState_ = 0, nStore_ = 0;
+  int n_ = 0, nnz_ = 0, nState_ = 0, nStore_ = 0, nBranch_ = 0;
+  std::vector<int32_t> branch0_;      // first branch-data LID of every instance (sorted order), -1 = no lead currents
   std::vector<int32_t> rowptr_, colind_;
   std::vector<double> f_, q_, fl_, ql_, dF_, dQ_;
   std::vector<double *> pF_, pQ_;

@@ -140,6 +140,9 @@ int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, doubl
  * branch LIDs set. */
 int xgpu_simple_lead_set(xgpu_ctx *ctx, int group, const int32_t *branch_lid0);
 int xgpu_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, double *d_leadQ, double *d_junctionV);
+/* Host-buffer form (what Master::loadDAEVectors gets: leadF, leadQ, junctionV of length n_branch), evaluated at the
+ * solution of the last xgpu_load_host / xgpu_load_host_jr call; entries no instance writes keep their values. */
+int xgpu_lead_load_host(xgpu_ctx *ctx, int n_branch, double *h_leadF, double *h_leadQ, double *h_junctionV);
 
 /* Carried per-instance limiter threshold (Instance::von); instance order = insertion order. */
 int xgpu_b4_von_set(xgpu_ctx *ctx, int group, const double *von);

@@ -181,6 +181,8 @@ struct InstRec {
       rec.insert(rec.end(), r, r + k); lids.insert(lids.end(), l, l + nl); flags = 0; \
       return nl; \
     } \
+    static int branch0(Inst &) { return -1; } \
+    static int branches() { return 0; } \
   };
 XB_ADMS_ORACLE_LIST(XB_ORACLE_GPUFILL)
 #undef XB_ORACLE_GPUFILL

@@ -154,3 +154,39 @@ def test_translated_adms_models_behind_the_generic_device_master(model, card):
     # the store vector of these models holds their output variables (operating-point quantities for .PRINT such as
     # HICUM's rcx_t, GMi, CPIi), published by the generic kernel like Instance::updatePrimaryState does
     _compare_through_virtuals(stock, gpu, x, CASES["tran1"], adms=True, nstore=info["nstore"])
+
+
+@pytest.mark.parametrize("kind,card", [("b4", "default"), ("b4", "rdsmod"), ("diode", None), ("mos1", "pmos_rs"), ("bjt", "res_pnp")])
+def test_gpu_masters_forward_lead_currents(kind, card):
+    """loadLeadCurrent (.PRINT I(...) / P(...)): leadF, leadQ, junctionV handed to Device::loadDAEVectors come back from the
+    GPU masters as the stock Masters write them (branch-data LIDs; entries nobody writes stay as they were)."""
+    from dev_common import DIODE_CARDS, diode_circuit, simple_circuit
+    if kind == "b4":
+        stock = isolated_devices(oracle_ref.RefCircuit, 20, card, seed=3, lead=True)
+        gpu = isolated_devices(GpuRef, 20, card, seed=3, lead=True)
+    elif kind == "diode":
+        c0 = sorted(DIODE_CARDS)[0]
+        stock = diode_circuit(oracle_ref.RefCircuit, c0, n_dev=30, seed=4, lead=True)
+        gpu = diode_circuit(GpuRefAll, c0, n_dev=30, seed=4, lead=True)
+    else:
+        stock = simple_circuit(oracle_ref.RefCircuit, kind, card, n_dev=30, seed=4, lead=True)
+        gpu = simple_circuit(GpuRefAll, kind, card, n_dev=30, seed=4, lead=True)
+    gpu.gpu_attach(0)
+    rng = np.random.default_rng(10)
+    x = rng.uniform(-0.3, 1.2, stock.n)
+    csto, nsto = rng.normal(0.3, 0.3, stock.n_sto), rng.normal(0.3, 0.3, stock.n_sto)
+    csta = rng.normal(0.0, 1e-14, stock.n_sta)
+    von = rng.uniform(0.2, 0.6, stock.n_inst)
+    for c in (stock, gpu):
+        c.set_flags(**CASES["tran1"])
+        c.set_state(curr_sto=csto, next_sto=nsto, curr_sta=csta)
+        if kind == "b4":
+            c.set_von(von)
+    if kind == "b4":
+        gpu_eng_von(gpu, von)
+    stock.load(x); gpu.load(x)
+    want, got = stock.lead(), gpu.lead()
+    assert np.array_equal(want["branch0"], got["branch0"]) and np.any(want["leadF"])
+    for k in ("leadF", "leadQ", "junctionV"):
+        scale = 1e-3 * np.max(np.abs(want[k])) if np.any(want[k]) else 1e-300
+        assert rel_err(got[k], want[k], scale) < 1e-12, (kind, k)

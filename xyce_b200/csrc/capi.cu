@@ -156,6 +156,7 @@ void xgpu_destroy(xgpu_ctx *ctx) {
   for (GatherMapDev *m : {&ctx->vec_map, &ctx->mat_map}) { cudaFree(m->ptr); cudaFree(m->src); cudaFree(m->long_dst); cudaFree(m->chunk_begin); cudaFree(m->chunk_dst_slot); cudaFree(m->long_chunk_ptr); cudaFree(m->partials); cudaFree(m->ell); cudaFree(m->done); }
   cudaFree(ctx->d_conv);
   for (double *b : ctx->buf) cudaFree(b);
+  cudaFree(ctx->d_lead_host);
   for (xgpu_ctx::LuGraph *g : {&ctx->g_refactor, &ctx->g_solve}) if (g->exec) cudaGraphExecDestroy(g->exec);
   cudaFree(ctx->tran_pool); cudaFree(ctx->tran_ints); cudaFreeHost(ctx->tran_pinned); cudaFree(ctx->d_hist);
   if (ctx->pipe.s2) cudaStreamDestroy(ctx->pipe.s2);
@@ -656,6 +657,26 @@ int xgpu_b4_lead_load(xgpu_ctx *ctx, const double *d_sol, double *d_leadF, doubl
     ++ctx->launches;
   }
   XG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// host-buffer form for the adaptors: the three lead vectors go up (entries the kernels do not write keep their values, as in
+// the reference), the lead kernels run against the solution of the last xgpu_load_host call, the vectors come back
+int xgpu_lead_load_host(xgpu_ctx *ctx, int n_branch, double *h_leadF, double *h_leadQ, double *h_junctionV) {
+  if (!ctx || n_branch <= 0 || !h_leadF || !h_leadQ || !h_junctionV) return 1;
+  if (!ctx->finalized) return fail(ctx, 15, "xgpu_finalize has not been called");
+  if (ctx->lead_len < n_branch) {
+    cudaFree(ctx->d_lead_host); ctx->d_lead_host = nullptr; ctx->lead_len = 0;
+    XG_CUDA(cudaMalloc((void **)&ctx->d_lead_host, (size_t)3 * n_branch * sizeof(double)));
+    ctx->lead_len = n_branch;
+  }
+  double *d[3] = {ctx->d_lead_host, ctx->d_lead_host + n_branch, ctx->d_lead_host + 2 * (size_t)n_branch};
+  double *h[3] = {h_leadF, h_leadQ, h_junctionV};
+  for (int k = 0; k < 3; ++k) XG_CUDA(cudaMemcpyAsync(d[k], h[k], (size_t)n_branch * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = xgpu_b4_lead_load(ctx, ctx->buf[0], d[0], d[1], d[2]);
+  if (rc) return rc;
+  for (int k = 0; k < 3; ++k) XG_CUDA(cudaMemcpyAsync(h[k], d[k], (size_t)n_branch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  XG_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
