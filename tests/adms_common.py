@@ -64,12 +64,21 @@ ADMS_CARDS = {
         "npn": ("NPN", {}, {}),
         "res": ("NPN", dict(RCC=20.0, RCV=120.0, RBC=15.0, RBV=80.0, RE=3.0, IS=3e-17, CJE=8e-15, CJC=5e-15, TAUE=3e-12), {}),
     },
+    # the variants with a substrate terminal / a thermal node (self heating)
+    "vbic13_4t": {
+        "npn": ("NPN", {}, {}),
+        "pnp_res": ("PNP", dict(TYPE=1, RCX=15.0, RCI=40.0, RBX=10.0, RBI=30.0, RE=2.0, RS=5.0, IS=3e-17, CJE=8e-15, CJC=3e-15, TF=5e-12), {}),
+    },
+    "bjt504tva": {
+        "npn": ("NPN", {}, {}),
+        "res": ("NPN", dict(RCC=20.0, RCV=120.0, RBC=15.0, RBV=80.0, RE=3.0, IS=3e-17, CJE=8e-15, CJC=5e-15, TAUE=3e-12, RTH=300.0, CTH=3e-9), {}),
+    },
 }
 # bias windows (uniform node voltages) that keep every model inside its working range
 BIAS = {"mvs_2_0_0_etsoi": (-0.6, 1.0), "mvs_2_0_0_hemt": (-0.6, 1.0), "ekv_va": (-1.2, 1.8), "JUNCAP200": (-0.8, 0.6),
         "hic0_full": (0.0, 0.7), "hicumL2va": (0.0, 0.7), "PSP103VA": (0.0, 0.6), "bsim6": (0.0, 0.6), "bsimcmg_110": (0.0, 0.6),
-        "DIODE_CMC": (-0.5, 0.5), "vbic13": (0.0, 1.5), "bjt504va": (0.0, 1.5)}
-LIMITED = ("vbic13", "bjt504va")
+        "DIODE_CMC": (-0.5, 0.5), "vbic13": (0.0, 1.5), "bjt504va": (0.0, 1.5), "vbic13_4t": (0.0, 1.5), "bjt504tva": (0.0, 1.5)}
+LIMITED = ("vbic13", "bjt504va", "vbic13_4t", "bjt504tva")
 
 
 # unknowns that need their own window: V(sf) of the HEMT variant (the Fermi-Dirac fit of the model takes a fractional
