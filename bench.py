@@ -384,6 +384,29 @@ def run_ours(args):
         ev2[k][1].record(stream)
     torch.cuda.synchronize()
     ms_eval = sum(e[0].elapsed_time(e[1]) for e in ev2)
+    # second operating point of SURVEY 8d: previous-iterate junction voltages 1 V (rms) away from the solution, so that
+    # fetlim / limvds / pnjlim engage and the dFdxdVp / dQdxdVp planes carry data (an extra, not part of `value`)
+    limiter_extra = None
+    if world == 1:
+        w2 = wl.inverter_array(args.inverters, seed=12345 + rank, store_noise=1.0)
+        sto_off = torch.tensor(w2["store"], **f64)
+        d_sto[1].copy_(sto_off)
+        for _ in range(3):
+            d_sto[0].copy_(sto_off); step()
+        ev3 = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        for k in range(args.steps):
+            d_sto[0].copy_(sto_off)          # every evaluation writes the limited voltages back: restore the offset (not timed)
+            flush.fill_(0.0)
+            ev3[k][0].record(stream)
+            step()
+            ev3[k][1].record(stream)
+        torch.cuda.synchronize()
+        ms_lim = sum(e[0].elapsed_time(e[1]) for e in ev3) / args.steps
+        limiter_extra = {"ms_per_step": ms_lim, "value": n_inst / (ms_lim * 1e-3), "unit": "evals/s",
+                         "nonzero_dFdxdVp_rows": int(torch.count_nonzero(d_vec[2]).item()),
+                         "note": "same step with the stored junction voltages 1 V rms off the iterate: fetlim / limvds / pnjlim engage where the reference would limit"}
+        for t in d_sto:
+            t.copy_(torch.tensor(w["store"], **f64))
     if os.environ.get("XYCE_B200_BENCH_VERBOSE"):
         print("step ms:", ["%.4f" % e[0].elapsed_time(e[1]) for e in ev], file=sys.stderr)
         print("eval ms:", ["%.4f" % e[0].elapsed_time(e[1]) for e in ev2], file=sys.stderr)
@@ -490,6 +513,8 @@ def run_ours(args):
                                   "measured_peak_tflops": fp64_peak,
                                   "frac": FLOPS_PER_EVAL * n_inst / eval_s / 1e12 / fp64_peak}},
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}
+    if limiter_extra is not None:
+        line["limiter_active"] = limiter_extra
     if world == 1 and not args.no_tran:
         try:
             line["tran_c3"] = tran_extra(local)
