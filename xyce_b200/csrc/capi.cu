@@ -191,6 +191,7 @@ int xgpu_set_option(xgpu_ctx *ctx, const char *name, int value) {
   // window with the evaluation of the second part when the circuit's numbering allows it; "pipe_percent" = share of every
   // run in the first part (before xgpu_finalize)
   if (n == "pipeline_host" && (value == 0 || value == 1)) { ctx->pipeline_host = value; return 0; }
+  if (n == "pipe_r_mapped" && (value == 0 || value == 1)) { ctx->pipe_r_mapped = value; return 0; }
   if (n == "pipe_percent" && value >= 10 && value <= 90 && !ctx->finalized) { ctx->pipe_frac = value / 100.0; return 0; }
   if (n == "lu_graphs" && (value == 0 || value == 1)) { ctx->lu_graphs = value; return 0; }
   // "lu_pivot_check": 1 (default) = the refactorization tests every pivot of the fixed sequence against KLU's threshold
@@ -922,6 +923,11 @@ int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_stat
     // DMA on the second stream; meanwhile evaluate the second part, assemble and combine the rest, copy it.  Same kernels
     // on the same data in the same order per destination: bitwise the result of the one-pass path.
     const int rs = ctx->pipe.vec_split; const long long ks = ctx->pipe.mat_split;
+    // option "pipe_r_mapped" (off): the residual part (0.8 MB) stored straight into the caller's mapped pinned buffer, so
+    // that two of the four DMA transfers go away.  Measured on config 2 (scripts/pipe_r_time.py): 168 us vs 162 us with the
+    // DMA copies, bitwise equal -- the stores over PCIe cost more than the fixed cost of two transfers; kept for other hosts
+    double *r_host = nullptr;
+    if (ctx->pipe_r_mapped && cudaHostGetDevicePointer((void **)&r_host, h_rhs, 0) != cudaSuccess) { cudaGetLastError(); r_host = nullptr; }
     const double *vin[4], *min_[2];
     double *vout[4] = {b[1], b[2], b[3], b[4]}, *mout[2] = {b[5], b[6]};
     for (int p = 0; p < 4; ++p) vin[p] = ctx->d_vec_planes + (int64_t)p * ctx->vec_plane;
@@ -941,7 +947,8 @@ int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_stat
       if (m > 0) {
         xb::launch_pdl(jr_kernel, dim3((unsigned)((m + 255) / 256)), dim3(256), 0, ctx->stream, k1 - k0, r1 - r0, qscalar, fscalar,
                        (const double *)(b[6] + k0), (const double *)(b[5] + k0), (const double *)(b[1] + r0), (const double *)(b[2] + r0),
-                       (const double *)(b[3] + r0), (const double *)(b[4] + r0), ss->voltageLimiterFlag, b[5] + k0, b[1] + r0);
+                       (const double *)(b[3] + r0), (const double *)(b[4] + r0), ss->voltageLimiterFlag, b[5] + k0,
+                       r_host ? r_host + r0 : b[1] + r0);
         ++ctx->launches;
       }
       cudaStream_t cs = ctx->stream;
@@ -950,7 +957,7 @@ int xgpu_load_host_jr(xgpu_ctx *ctx, const double *h_sol, const xgpu_solver_stat
         XG_CUDA(cudaStreamWaitEvent(ctx->pipe.s2, ctx->pipe.ev_a, 0));
         cs = ctx->pipe.s2;
       }
-      if (r1 > r0) XG_CUDA(cudaMemcpyAsync(h_rhs + r0, b[1] + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, cs));
+      if (r1 > r0 && !r_host) XG_CUDA(cudaMemcpyAsync(h_rhs + r0, b[1] + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost, cs));
       if (k1 > k0) XG_CUDA(cudaMemcpyAsync(h_jac + k0, b[5] + k0, (size_t)(k1 - k0) * sizeof(double), cudaMemcpyDeviceToHost, cs));
     }
     XG_CUDA(cudaStreamSynchronize(ctx->pipe.s2));

@@ -123,6 +123,7 @@ struct xgpu_ctx {
   double *buf[12] = {nullptr};        // xgpu_device_buffer order; 11 = last store
   double *d_last_sto = nullptr;       // xgpu_last_store_set / the transient driver: store vector of the step before
   bool needs_last_sto = false;
+  int pipe_r_mapped = 0;              // pipelined host path: store the residual part straight into mapped pinned host memory
   double *d_lead_host = nullptr; int lead_len = 0;      // xgpu_lead_load_host: leadF | leadQ | junctionV staging        // a BJT group with excess phase (PTF != 0) is present
 
   // linear devices and independent sources
