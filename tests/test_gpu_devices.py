@@ -51,7 +51,8 @@ def test_diode(card, case):
     eng.close()
 
 
-SIMPLE_CASES = dict(CASES, dcop2=dict(dcop=1, tranop=1, newtonIter=2), tran_init=dict(transient=1, newtonIter=0, initTran=1))
+SIMPLE_CASES = dict(CASES, dcop2=dict(dcop=1, tranop=1, newtonIter=2), tran_init=dict(transient=1, newtonIter=0, initTran=1),
+                    homotopy=dict(dcop=1, tranop=1, newtonIter=1, artParameter=1, gainScale=0.35, nltermScale=0.6))
 
 
 @pytest.mark.parametrize("case", sorted(SIMPLE_CASES))

@@ -12,7 +12,9 @@ pytestmark = pytest.mark.skipif(not oracle_ref.available(), reason="oracle/_ref 
 
 CASES = {"tran1": dict(transient=1, newtonIter=1), "tran0": dict(transient=1, newtonIter=0),
          "dcop_init": dict(dcop=1, tranop=1, initJct=1, newtonIter=0), "dcop2": dict(dcop=1, tranop=1, newtonIter=2),
-         "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0)}
+         "nolimit": dict(transient=1, newtonIter=2, voltageLimiter=0),
+         # DCOP continuation (MOSFET homotopy): vds / gate drive scaled inside the drain-current code (N_DEV_MOSFET1.C:2978-3001)
+         "homotopy": dict(dcop=1, tranop=1, newtonIter=1, artParameter=1, gainScale=0.35, nltermScale=0.6)}
 
 
 def run(kind, card, case, seed=3):

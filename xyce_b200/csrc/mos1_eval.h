@@ -177,8 +177,18 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
   }
   const int mode = (vds >= 0) ? 1 : -1;
 
-  // Shichman-Hodges drain current (the DCOP-continuation scaling of vds / vgs is not part of .TRAN;
-  // artParameterFlag is rejected by the C ABI for this device)
+  // DCOP continuation ("MOSFET homotopy", N_DEV_MOSFET1.C:2978-3001): the drain-current and Meyer-capacitance code below
+  // sees vds scaled by nltermScale and the controlling gate voltage blended towards vgstConst by gainScale
+  // (DeviceSupport::contVds / contVgst, Core/N_DEV_DeviceSupport.C:779-835); the loads use the saved values (:3410-3412)
+  const real vds_save = vds, vgs_save = vgs, vgd_save = vgd;
+  if (S.artParameterFlag) {
+    real mn = S.vdsScaleMin; if (mn <= 0.0) mn = 0.3;
+    vds = vds * (S.nltermScale * (1.0 - mn) + mn);
+    if (mode == 1) vgs = S.gainScale * vgs + (1.0 - S.gainScale) * S.vgstConst;
+    else vgd = S.gainScale * vgd + (1.0 - S.gainScale) * S.vgstConst;
+  }
+
+  // Shichman-Hodges drain current
   real cdrain, gm, gds, gmbs, Vdsat;
   {
     const real vbx = (mode == 1 ? vbs : vbd);
@@ -284,6 +294,7 @@ XB_HD void evaluate(const SolverFlags &S, const Rec &M, int flags, const real *V
   } else {
     Gm = -gm; Gmbs = -gmbs; nrmsum = 0; revsum = -(Gm + Gmbs); cdreq = -(ty)*cdrain;
   }
+  vds = vds_save; vgs = vgs_save; vgd = vgd_save;
 
   // ---- Master::updateState: store, Meyer charges ----
   o.store[st_vbd] = vbd; o.store[st_vbs] = vbs; o.store[st_vgs] = vgs; o.store[st_vds] = vds;
