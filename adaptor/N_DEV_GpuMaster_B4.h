@@ -140,6 +140,8 @@ class GpuMaster : public Master {
     if (!ctx_) return false;
     const SolverState &s = getSolverState();
     const DeviceOptions &o = getDeviceOptions();
+    // initial junction voltages taken from an operating-point file (flagSolVectorPtr) are not restated: fail loudly
+    if (s.inputOPFlag) { err_ = "inputOPFlag (operating point read from a file) is not supported by the GPU master"; return false; }
     xgpu_solver_state ss;
     ss.dcopFlag = s.dcopFlag; ss.tranopFlag = s.tranopFlag; ss.acopFlag = s.acopFlag; ss.transientFlag = s.transientFlag;
     ss.dcsweepFlag = s.dcsweepFlag; ss.initJctFlag = s.initJctFlag_; ss.initFixFlag = s.initFixFlag; ss.initTranFlag = s.initTranFlag_;
