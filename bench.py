@@ -28,9 +28,9 @@ UNIT = "evals/s"
 BYTES_PER_EVAL = 1592.0      # SURVEY.md 8(d) unit U1 (algorithmic bytes per instance evaluation incl. assembly re-read)
 BYTES_PER_EVAL_KERNEL = 1128.0   # the evaluation kernel's share of U1: 544 B read + 584 B written per instance
 # dram__bytes_read.sum + dram__bytes_write.sum of one b4_eval launch on this workload (ncu --set full capture
-# summarised in profiles/r02_b4_eval_kernel_v5_ncu_summary.md): 31.8 MB read + 10.4 MB written (most of the freshly
+# of the final build: profiles/r02_b4_eval_kernel_final2_ncu_raw.txt): 31.7 MB read + 12.7 MB written (most of the freshly
 # written contribution planes stay in the 126 MB L2 until the assembly kernel reads them)
-EVAL_KERNEL_DRAM_BYTES = 42.2e6
+EVAL_KERNEL_DRAM_BYTES = 44.4e6
 FLOPS_PER_EVAL = 1889.0      # executed fp64 operations per evaluation, measured (xyce_b200/data/b4_flop_count.json)
 
 
